@@ -1,0 +1,160 @@
+"""CPU tests (-m "not gpu"): the render oracle against the committed goldens that
+oracle/make_golden.py produced from the unmodified reference, and -- when
+/root/reference is present -- against the reference itself."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refshim, render_oracle as ro
+from oracle.noise import NumpyNoise, PhiloxNoise
+from oracle.make_golden import C3_PROPS
+
+CLEAN = dict(C3_PROPS, background_intensity=[0, 0], poisson_noise=-1)
+PSF = [2, 1.75, 1.5, 1.25, 1]
+NOISE = [0, 1 / 50, 1 / 25, 1 / 20, 1 / 10, 1 / 5]
+PSFNOISE_PROPS = dict(C3_PROPS, particle_intensity=[5000, 500], background_intensity=[5000, 0])
+FRAMERATE_PROPS = dict(C3_PROPS, output_size=13)
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return (np.load(os.path.join(golden_dir, "render_inputs.npz")),
+            np.load(os.path.join(golden_dir, "render_golden.npz")),
+            np.load(os.path.join(golden_dir, "render_noise_stats.npz")))
+
+
+def test_literal_is_bit_exact(gold):
+    inp, g, _ = gold
+    out = ro.render_v1(inp["traj30"][:2], 10, True, CLEAN, mode="literal")
+    assert out.dtype == np.float32
+    assert np.array_equal(out, g["v1_p9_center"][:2])
+    out = ro.render_v1(inp["traj30"][:1], 10, False, CLEAN, mode="literal")
+    assert np.array_equal(out, g["v1_p9_nocenter"][:1])
+
+
+@pytest.mark.parametrize("key,sl,n,center,over", [
+    ("v1_p9_center", slice(0, 8), 10, True, {}),
+    ("v1_p9_nocenter", slice(0, 2), 10, False, {}),
+    ("v1_p13_center", slice(0, 2), 10, True, {"output_size": 13}),
+    ("v1_p8_center", slice(0, 1), 10, True, {"output_size": 8}),
+    ("v1_p7u10_n15", slice(0, 1), 15, True, {"output_size": 7, "upsampling_factor": 10}),
+])
+def test_separable_matches_reference(gold, key, sl, n, center, over):
+    inp, g, _ = gold
+    out = ro.render_v1(inp["traj30"][sl], n, center, dict(CLEAN, **over), mode="separable")
+    assert out.shape == g[key].shape
+    # layout: the brightest pixel of every frame sits where the reference puts it
+    assert np.array_equal(out.reshape(*out.shape[:2], -1).argmax(-1), g[key].reshape(*out.shape[:2], -1).argmax(-1))
+    assert relmax(out, g[key]) < 1e-6            # north_star: <= 1e-5 relative in fp32
+
+
+def test_flip_side_effect_and_sum(gold):
+    inp, g, _ = gold
+    assert np.allclose(g["v1_flipped_input_y"], -inp["traj30"][:, :4, 1])
+    # SURVEY.md 8c smoke values of the reference
+    assert abs(float(g["v1_p9_center"].sum(dtype=np.float64)) - 9825153.410454) < 1e-2
+    assert abs(float(g["v1_p9_center"][0, 0, 4, 4]) - 3566.737549) < 1e-3
+
+
+def test_background_and_normalise(gold):
+    inp, g, _ = gold
+    v = ro.render_v1(inp["traj30"][:2], 10, True, dict(C3_PROPS, poisson_noise=-1))
+    vn, meta = ro.normalize_images(v, 1420, 290, 6000)
+    assert vn.dtype == np.float32 and meta == (1420, 290, 6000)
+    assert np.abs(vn - g["v1_p9_bgmean_norm"]).max() < 2e-6
+    with pytest.raises(ValueError):
+        ro.normalize_images(v, 10, 0, 10)
+
+
+def test_psfnoise_and_framerate_mean(gold):
+    inp, g, _ = gold
+    out = ro.render_psfnoise(inp["traj20"][:1], 10, True, PSFNOISE_PROPS, PSF, NOISE)
+    assert out.shape == (1, 5, 6, 20, 9, 9)
+    assert relmax(out, g["psfnoise_mean"]) < 1e-6
+    # the double-background quirk: noise index >= 1 carries the background twice
+    assert abs(out[:, :, 1].mean() - out[:, :, 0].mean() - 5000) < 1.0
+    fr = ro.render_framerates(inp["traj30b"][:1], [5, 10, 15, 20, 30, 50], True, FRAMERATE_PROPS)
+    assert fr.shape == (1, 6, 60, 13, 13)
+    assert np.abs(fr - g["framerate_mean"]).max() < 2e-6
+    assert np.all(fr[:, 5, 6:] == 0)             # zero padding beyond T // n frames
+
+
+def test_errors():
+    t = np.zeros((1, 25, 2))
+    with pytest.raises(Exception, match="divisble"):
+        ro.render_v1(t, 10, True, CLEAN)
+    with pytest.raises(Exception, match="No settings given"):
+        ro.render_psfnoise(np.zeros((1, 20, 2)), 10, True, PSFNOISE_PROPS, [], [])
+
+
+def _ks_from_quantiles(sample, qvals):
+    """sup |F_sample - F_ref| with F_ref given by its quantile table."""
+    q = np.linspace(0, 1, len(qvals))
+    s = np.sort(sample.ravel())
+    f_s = np.searchsorted(s, qvals, side="right") / s.size
+    return float(np.abs(f_s - q).max())
+
+
+@pytest.mark.parametrize("source", ["philox", "numpy"])
+def test_noisy_v1_statistics(gold, source):
+    inp, _, st = gold
+    R = 6
+    outs = []
+    for r in range(R):
+        nz = PhiloxNoise(1000 + r) if source == "philox" else NumpyNoise(r)
+        outs.append(ro.render_v1(inp["traj30"], 10, True, C3_PROPS, noise=nz))
+    v = np.stack(outs).astype(np.float64)
+    assert abs(v.mean() - st["v1_mean"]) / st["v1_mean"] < 3e-3
+    assert abs(v.std() - st["v1_std"]) / st["v1_std"] < 1e-2
+    assert np.abs(v.mean(axis=(0, 1, 2)) - st["v1_pix_mean"]).max() / st["v1_pix_mean"].max() < 1e-2
+    assert _ks_from_quantiles(v, st["v1_quantiles"]) < 0.01
+
+
+def test_noisy_psfnoise_statistics(gold):
+    inp, _, st = gold
+    outs = [ro.render_psfnoise(inp["traj20"], 10, True, PSFNOISE_PROPS, PSF, NOISE, noise=PhiloxNoise(77 + r))
+            for r in range(3)]
+    v = np.stack(outs).astype(np.float64)
+    m = v.mean(axis=(0, 1, 4, 5, 6))
+    s = v.std(axis=(0, 1, 4, 5, 6))
+    assert np.abs(m / st["psf_mean"] - 1).max() < 5e-3
+    assert np.abs(s / st["psf_std"] - 1).max() < 3e-2
+    for i in range(5):
+        for j in range(6):
+            assert _ks_from_quantiles(v[:, :, i, j], st["psf_quantiles"][i, j]) < 0.03
+
+
+def test_poisson_sampler_chi_square():
+    from scipy import stats
+    n = 120000
+    for lam in (3.0, 10.0, 100.0):
+        _, pois = PhiloxNoise(5).pixel(3, n)
+        k = pois(np.full(n, lam, dtype=np.float32)).astype(np.int64)
+        lo, hi = int(stats.poisson.ppf(1e-4, lam)), int(stats.poisson.ppf(1 - 1e-4, lam))
+        obs = np.array([(k == i).sum() for i in range(lo, hi + 1)], dtype=np.float64)
+        exp = stats.poisson.pmf(np.arange(lo, hi + 1), lam) * n
+        keep = exp > 20
+        chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+        assert chi2 < stats.chi2.ppf(1 - 1e-4, keep.sum() - 1), (lam, chi2)
+    # lam ~ 1e6 (PSFNoise regime): moments
+    _, pois = PhiloxNoise(6).pixel(0, n)
+    k = pois(np.full(n, 1.5e6, dtype=np.float32)).astype(np.float64)
+    assert abs(k.mean() - 1.5e6) < 5 * np.sqrt(1.5e6 / n)
+    assert abs(k.var() / 1.5e6 - 1) < 0.03
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="reference checkout not present")
+def test_against_live_reference(gold):
+    inp, g, _ = gold
+    from oracle.make_golden import _Deterministic, _quiet
+    gen, _ = refshim.import_reference()
+    with _Deterministic():
+        t = inp["traj30"][2:4].copy()
+        ref = _quiet(gen.trajectories_to_video, t, 10, True, CLEAN)
+    assert np.array_equal(ref, g["v1_p9_center"][2:4])
+    assert np.array_equal(ro.render_v1(inp["traj30"][2:4], 10, True, CLEAN, mode="literal"), ref)

@@ -1,0 +1,66 @@
+"""CPU tests (-m "not gpu"): the plain-PyTorch ViT oracle against goldens produced by
+the unmodified reference nn.Module (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as vo
+
+CASES = {
+    "deepcnn_n": dict(embedding="deepresnet", embed_dim=64, num_heads=4, num_layers=6, activation="relu",
+                      use_pos_encoding=False, use_regression_token=True),
+    "linear_s_pos": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="relu",
+                         use_pos_encoding=True, use_regression_token=True),
+    "cnn_s_mean": dict(embedding="cnn", embed_dim=32, num_heads=2, num_layers=3, activation="gelu",
+                       use_pos_encoding=True, use_regression_token=False),
+    "linear_s_feat_early": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="relu",
+                                use_pos_encoding=False, use_regression_token=True, use_global_features=True,
+                                fusion_type="early"),
+    "linear_s_feat_late": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="relu",
+                               use_pos_encoding=False, use_regression_token=True, use_global_features=True,
+                               fusion_type="late"),
+}
+PARAM_COUNTS = {"deepcnn_n": 506081, "linear_s_pos": 36865}   # SURVEY.md section 4 (reference notebooks)
+
+
+def load_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "vit_%s.npz" % name))
+    sd = {k[3:]: torch.tensor(z[k]) for k in z.files if k.startswith("sd/")}
+    feats = torch.tensor(z["features"]) if "features" in z.files else None
+    return z, sd, torch.tensor(z["x"]), torch.tensor(z["target"]), feats
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_loss_grads(golden_dir, name):
+    z, sd, x, tgt, feats = load_case(golden_dir, name)
+    if name in PARAM_COUNTS:
+        assert sum(v.numel() for k, v in sd.items() if not vo.is_buffer(k)) == PARAM_COUNTS[name]
+    pred, loss, g, _ = vo.loss_and_grads(sd, CASES[name], x, tgt, feats)
+    assert np.abs(pred.numpy() - z["pred"]).max() < 2e-6
+    assert abs(float(loss) - float(z["loss"])) < 1e-6
+    gmax = max(float(z[k]) for k in z.files if k.startswith("gradnorm/"))
+    for k in g:
+        assert abs(float(g[k].double().norm()) - float(z["gradnorm/" + k])) < 1e-4 * gmax + 1e-4 * float(z["gradnorm/" + k])
+        if "grad/" + k in z.files:
+            ref = z["grad/" + k]
+            assert np.abs(g[k].numpy() - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-3 * gmax)
+
+
+@pytest.mark.parametrize("name", ["deepcnn_n", "linear_s_feat_late"])
+def test_train_step(golden_dir, name):
+    z, sd, x, tgt, feats = load_case(golden_dir, name)
+    st = vo.new_opt_state(sd)
+    loss = vo.train_step(sd, st, CASES[name], x, tgt, feats)
+    assert abs(loss - float(z["loss"])) < 1e-6
+    gmax = max(float(z[k]) for k in z.files if k.startswith("gradnorm/"))
+    for k, v in sd.items():
+        ref_sum, ref_abs = float(z["after_sum/" + k]), float(z["after_abs/" + k])
+        tol = 1e-5 * max(ref_abs, 1.0)
+        if "gradnorm/" + k in z.files and float(z["gradnorm/" + k]) < 1e-6 * gmax:
+            # mathematically-zero gradient (k_proj.bias: softmax is shift invariant): Adam turns
+            # rounding noise into +-lr per element, so only bound the update size
+            tol += 2 * 1e-4 * v.numel()
+        assert abs(float(v.double().sum()) - ref_sum) < tol, k
+        assert abs(float(v.double().abs().sum()) - ref_abs) < tol, k
