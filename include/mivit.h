@@ -1,0 +1,112 @@
+/* mivit_b200 -- C ABI of the B200-native MiViT hot path (render + ViT train step).
+ *
+ * The reference (Biomedical-Imaging-Group/MolecularDiffusion_MiViT) is pure Python and has
+ * no FFI; the boundary it exposes for this path is the Python call surface listed in
+ * SURVEY.md section 8b.  Each entry point below names the reference function whose work it
+ * replaces (paths relative to the reference root).  The Python mirrors in
+ * moleculardiffusion_mivit_b200/{helpersGeneration,experiments,models}.py bind these symbols
+ * with ctypes.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  All data pointers are DEVICE pointers
+ *    unless the name ends in _host.  Nothing is allocated inside; the caller owns buffers.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls enqueue work and return without
+ *    synchronising.
+ *  - return value: 0 = ok, non-zero = error; mivit_last_error() gives the thread-local text.
+ *  - sm_100a only; there is no CPU fallback.
+ */
+#ifndef MIVIT_H_
+#define MIVIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIVIT_ABI_VERSION 1
+
+int mivit_abi_version(void);
+const char* mivit_last_error(void);
+/* number of kernels launched by this library since the last reset (bench.py: gpu_launches) */
+int64_t mivit_launch_count(void);
+void mivit_reset_launch_count(void);
+
+/* ------------------------------------------------------------------ renderer ---------- */
+
+/* Scalar set-up that helpers/helpersGeneration.py:225-247 derives from `image_props`. */
+typedef struct mivit_render_params {
+  double scale;      /* trajectory -> pixel factor: unit/(resolution*1e9)  (:231), 1 if unit == -1 */
+  double sigma_hr;   /* PSF sigma in high-res pixels: U/resolution*fwhm/2.355 (:242)               */
+  int32_t P;         /* output_size                                                                */
+  int32_t U;         /* upsampling_factor                                                          */
+  int32_t n;         /* nPosPerFrame                                                               */
+  int32_t center;    /* subtract the frame's mean sub-position (:291)                              */
+  int32_t flip_y;    /* render with -y (the effect of the in-place flip :197)                      */
+  int32_t draw;      /* particle_mean > 1e-4 && particle_std > 1e-4 (:299); 0 -> blank particle    */
+  float part_mean;   /* particle_intensity[0]                                                      */
+  float part_std;    /* particle_intensity[1]                                                      */
+  float bg_mean;     /* background_intensity[0]                                                    */
+  float bg_std;      /* background_intensity[1]                                                    */
+  float poisson;     /* poisson_noise; -1 disables (:316)                                          */
+  int32_t normalize; /* fuse normalize_images (:389-395): (v - norm_sub) / norm_div                */
+  float norm_sub;    /* background_mean - background_sigma                                         */
+  float norm_div;    /* theoretical_max - (background_mean - background_sigma)                     */
+  int32_t mean_noise;/* test hook: every normal draw returns its mean, Poisson(lam) -> lam         */
+} mivit_render_params;
+
+/* Replaces helpers/helpersGeneration.py:128-278 trajectories_to_video + :283-319
+ * trajectory_to_video (+ optional :356-400 normalize_images).
+ * traj: [N,T,2] float64, read only (the caller applies the reference's in-place y flip).
+ * out : float32; frame f of sequence s is written at out + s*out_seq_stride + f*P*P
+ *       (out_seq_stride = F*P*P for the plain (N,F,P,P) result).
+ * seq_offset: global id of sequence 0 (noise streams are keyed by global id). */
+int mivit_render_v1(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm,
+                    uint64_t seed, uint64_t seq_offset, float* out, int64_t out_seq_stride,
+                    void* stream);
+
+/* Replaces Experiments/PSFNoise/trainSettingsPSFNoise.py:196-309 trajs_to_vid_psf_noise.
+ * psf_div[n_psf], noise_frac[n_noise] are HOST arrays (PSF_Settings, Noise_Settings);
+ * part_mean_global is the module-level `part_mean` used for the background sigma (:302).
+ * out: [N, n_psf, n_noise, F, P, P] float32.  prm->flip_y and prm->normalize are ignored. */
+int mivit_render_psfnoise(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm,
+                          const float* psf_div_host, int32_t n_psf, const float* noise_frac_host,
+                          int32_t n_noise, float part_mean_global, uint64_t seed,
+                          uint64_t seq_offset, float* out, void* stream);
+
+/* Trajectory source.  Replaces the call sites of andi_datasets models_phenom().single_state
+ * (Experiments/PSFNoise/trainModelsPSFNoise.py:128-132) with the in-repo equivalent
+ * helpers/helpersGeneration.py:9-45 brownian_motion: D ~ N(mean, sqrt(var)) redrawn until
+ * positive, steps ~ N(0, 2 D) per axis, positions = cumulative sum starting at 0, divided
+ * by `div` (traj_div_factor).  Sequence with global id g uses group g % n_groups.
+ * traj: [N,T,2] float64 out;  D_out: [N] float32 out (the label before /D_max). */
+int mivit_brownian(int64_t N, int32_t T, const float* group_mean_host, const float* group_var_host,
+                   int32_t n_groups, double div, uint64_t seed, uint64_t seq_offset, double* traj,
+                   float* D_out, void* stream);
+
+/* ------------------------------------------------- ViT building blocks (tests / ViT) ---- */
+
+/* Activation layout of the DeepResNetEmbedding kernels ("pitched rows", bf16, channels last):
+ * frame f, pixel (y,x) -> row f*(P+1)^2 + y*(P+1) + x of a [rows, C] matrix; column P of every
+ * line and line P of every frame are zero; >= 128 zero guard rows precede row 0 and follow the
+ * last 128-row tile.  `*_row0` pointers address row 0. */
+
+/* nn.Conv2d weight fp32 [cout][cin][k][k] (reference helpers/models.py:206,209,216,233) ->
+ * bf16 operand pack.  dgrad = 0: [k*k][cin/8][cout][8];  dgrad = 1: [k*k][cout/8][cin][8]. */
+int mivit_conv_pack_weights(const float* W, void* out_bf16, int32_t cout, int32_t cin, int32_t ksize,
+                            int32_t dgrad, void* stream);
+
+/* Stride-1 / pad-(k/2) convolution on pitched rows: Y[r,:] = sum_tap X[r + delta_tap,:] * W_tap^T
+ * (F.conv2d of helpers/models.py:222,225,247 without bias).  mirrored = 1 negates the tap
+ * shifts (input gradient with a dgrad weight pack; cin/cout are then those of the GEMM, i.e.
+ * swapped).  stats (optional): [2][cout] fp32, per-channel sum and sum of squares of the
+ * stored outputs are ADDED (BatchNorm2d batch statistics).  impl: 1 = tcgen05 kernel,
+ * 0 = SIMT cross-check kernel. */
+int mivit_conv_rows(const void* X_row0, const void* Wp, void* Y_row0, float* stats, int64_t rows,
+                    int32_t P, int32_t cin, int32_t cout, int32_t ksize, int32_t mirrored, int32_t impl,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIVIT_H_ */

@@ -1,0 +1,86 @@
+"""ctypes binding of the C-ABI library (include/mivit.h).  There is no CPU fallback:
+importing this module without a built libmivit_b200.so raises."""
+import ctypes
+import os
+import shutil
+
+from . import build as _build
+
+_LIB = None
+
+
+class RenderParams(ctypes.Structure):
+    """struct mivit_render_params (include/mivit.h)."""
+    _fields_ = [
+        ("scale", ctypes.c_double), ("sigma_hr", ctypes.c_double),
+        ("P", ctypes.c_int32), ("U", ctypes.c_int32), ("n", ctypes.c_int32), ("center", ctypes.c_int32),
+        ("flip_y", ctypes.c_int32), ("draw", ctypes.c_int32),
+        ("part_mean", ctypes.c_float), ("part_std", ctypes.c_float), ("bg_mean", ctypes.c_float),
+        ("bg_std", ctypes.c_float), ("poisson", ctypes.c_float),
+        ("normalize", ctypes.c_int32), ("norm_sub", ctypes.c_float), ("norm_div", ctypes.c_float),
+        ("mean_noise", ctypes.c_int32),
+    ]
+
+
+class MivitError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i32, i64, u64, f32, f64 = c.c_void_p, c.c_int32, c.c_int64, c.c_uint64, c.c_float, c.c_double
+    fp = c.POINTER(c.c_float)
+    sigs = {
+        "mivit_abi_version": (i32, []),
+        "mivit_last_error": (c.c_char_p, []),
+        "mivit_launch_count": (i64, []),
+        "mivit_reset_launch_count": (None, []),
+        "mivit_render_v1": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, i64, vp]),
+        "mivit_render_psfnoise": (i32, [vp, i64, i32, c.POINTER(RenderParams), fp, i32, fp, i32, f32, u64, u64, vp, vp]),
+        "mivit_brownian": (i32, [i64, i32, fp, fp, i32, f64, u64, u64, vp, vp, vp]),
+        "mivit_conv_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "mivit_conv_rows": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return sigs
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        if shutil.which(_build.NVCC) or os.path.exists(_build.NVCC):
+            if _build.needs_build():
+                _build.build()
+        if not os.path.exists(path):
+            raise ImportError(
+                "moleculardiffusion_mivit_b200: %s is missing and nvcc is not available to build it. "
+                "Run `python -m moleculardiffusion_mivit_b200.build` (there is no CPU fallback)." % path)
+        _LIB = ctypes.CDLL(path)
+        _declare(_LIB)
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise MivitError(lib().mivit_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise MivitError("moleculardiffusion_mivit_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())

@@ -1,0 +1,61 @@
+// Weight packing for the shifted-row implicit-GEMM convolutions + C-ABI entry points that
+// expose the convolution on the pitched-rows layout (used by the ViT and by the parity tests).
+#include "common.cuh"
+#include "vit.h"
+#include "../../include/mivit.h"
+
+namespace {
+
+// W fp32 [cout][cin][k][k]  ->  forward pack  bf16 [taps][cin/8][cout][8]   (B operand, K = cin)
+//                               dgrad pack    bf16 [taps][cout/8][cin][8]   (B operand, K = cout)
+__global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int cout, int cin,
+                                    int taps, int dgrad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = taps * cout * cin;
+  if (idx >= total) return;
+  const int t = idx / (cout * cin);
+  const int rem = idx - t * cout * cin;
+  int co, ci;
+  size_t dst;
+  if (!dgrad) {
+    const int chunk = rem / (cout * 8);
+    const int r2 = rem - chunk * cout * 8;
+    co = r2 / 8;
+    ci = chunk * 8 + (r2 & 7);
+    dst = (size_t)idx;
+  } else {
+    const int chunk = rem / (cin * 8);
+    const int r2 = rem - chunk * cin * 8;
+    ci = r2 / 8;
+    co = chunk * 8 + (r2 & 7);
+    dst = (size_t)idx;
+  }
+  out[dst] = __float2bfloat16_rn(W[((size_t)co * cin + ci) * taps + t]);
+}
+
+}  // namespace
+
+int pack_conv_weights(const float* W, __nv_bfloat16* out, int cout, int cin, int taps, int dgrad, cudaStream_t st) {
+  const int total = taps * cout * cin;
+  pack_weights_kernel<<<mivit_ceil_div(total, 256), 256, 0, st>>>(W, out, cout, cin, taps, dgrad);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_conv_pack_weights(const float* W, void* out_bf16, int32_t cout, int32_t cin, int32_t ksize,
+                                       int32_t dgrad, void* stream) {
+  MIVIT_CHECK_ARG(W && out_bf16, "NULL pointer");
+  MIVIT_CHECK_ARG(ksize == 1 || ksize == 3, "kernel size must be 1 or 3");
+  MIVIT_CHECK_ARG(cin % 8 == 0 && cout % 8 == 0, "channels must be multiples of 8");
+  return pack_conv_weights(W, (__nv_bfloat16*)out_bf16, cout, cin, ksize * ksize, dgrad, (cudaStream_t)stream);
+}
+
+extern "C" int mivit_conv_rows(const void* X_row0, const void* Wp, void* Y_row0, float* stats, int64_t rows, int32_t P,
+                               int32_t cin, int32_t cout, int32_t ksize, int32_t mirrored, int32_t impl, void* stream) {
+  MIVIT_CHECK_ARG(X_row0 && Wp && Y_row0, "NULL pointer");
+  MIVIT_CHECK_ARG(ksize == 1 || ksize == 3, "kernel size must be 1 or 3");
+  const ConvShifts sh = make_shifts(P, ksize * ksize, mirrored != 0);
+  return conv_rows_forward((const __nv_bfloat16*)X_row0, (const __nv_bfloat16*)Wp, (__nv_bfloat16*)Y_row0, stats, rows, P,
+                           cin, cout, ksize * ksize, sh, impl, (cudaStream_t)stream);
+}

@@ -1,0 +1,119 @@
+// Counter-based RNG for the renderer and the trajectory source.
+// Philox4x32-10 (Salmon et al., SC'11).  Stream layout (mirrored bit-for-bit by
+// oracle/philox.py and oracle/noise.py so noisy frames can be checked draw-for-draw):
+//     key     = (seed_lo, seed_hi)
+//     counter = (item, block, seq_id, stream | variant << 8)
+// The reference draws from the global np.random state
+// (helpers/helpersGeneration.py:300,312,317), which has no parallel equivalent; a
+// counter stream keyed by the GLOBAL sequence id makes the generated data set
+// independent of how sequences are sharded over GPUs.
+#pragma once
+#include <stdint.h>
+
+#define MIVIT_STREAM_TRAJ 0u
+#define MIVIT_STREAM_D 1u
+#define MIVIT_STREAM_INTENSITY 2u
+#define MIVIT_STREAM_PIXEL 3u
+#define MIVIT_STREAM_LOCERR 4u
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint32_t stream_word(uint32_t stream, uint32_t variant) {
+  return (stream & 0xFFu) | (variant << 8);
+}
+
+// uint32 -> (0,1] float32 (curand's _curand_uniform)
+__device__ __forceinline__ float u01(uint32_t x) {
+  return __fmaf_rn((float)x, 2.3283064365386963e-10f, 2.3283064365386963e-10f / 2.0f);
+}
+
+// two words -> two standard normals
+__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
+  const float u = u01(xa);
+  const float v = u01(xb) * 6.2831853071795860f;
+  const float r = sqrtf(-2.0f * logf(u));
+  float s, c;
+  sincosf(v, &s, &c);
+  z0 = r * s;
+  z1 = r * c;
+}
+
+__constant__ float kLogFact[16] = {
+    0.0f, 0.0f, 0.693147180559945f, 1.791759469228055f, 3.178053830347946f, 4.787491742782046f,
+    6.579251212010101f, 8.525161361065415f, 10.604602902745251f, 12.801827480081469f,
+    15.104412573075516f, 17.502307845873887f, 19.987214495661885f, 22.552163853123425f,
+    25.191221182738680f, 27.899271383840890f};
+
+// log Poisson pmf, float32, cancellation free for large lam (see oracle/noise.py)
+__device__ __forceinline__ float poisson_logpmf(float k, float lam, float li, float lf, float loglam) {
+  if (k < 12.0f) return -lam + k * loglam - kLogFact[(int)k];
+  const float dk = (li - k) + lf;  // lam - k
+  const float t = k * log1pf(dk / k);
+  const float inv = 1.0f / k;
+  const float corr = inv * (1.0f / 12.0f - inv * inv * (1.0f / 360.0f));
+  return t - dk - 0.5f * logf(6.2831853071795860f * k) - corr;
+}
+
+// Uniform-word stream of one pixel: words 2,3 of block 0, then blocks 1,2,...
+struct PixelStream {
+  uint32_t item, seq, sw, k0, k1;
+  uint4 cur;
+  int q;
+  __device__ __forceinline__ uint32_t next() {
+    uint32_t w;
+    if (q < 2) {
+      w = q == 0 ? cur.z : cur.w;
+    } else {
+      const int r = (q - 2) & 3;
+      if (r == 0) cur = philox4x32_10(item, 1u + (uint32_t)((q - 2) >> 2), seq, sw, k0, k1);
+      w = r == 0 ? cur.x : r == 1 ? cur.y : r == 2 ? cur.z : cur.w;
+    }
+    ++q;
+    return w;
+  }
+};
+
+// numpy's random_poisson (legacy-distributions.c): multiplication method below 10,
+// Hoermann PTRS above, float32.
+__device__ __forceinline__ float poisson_draw(float lam, PixelStream& st) {
+  if (!(lam > 0.0f)) return 0.0f;
+  if (lam < 10.0f) {
+    const float enlam = expf(-lam);
+    float prod = 1.0f, x = 0.0f;
+    for (int it = 0; it < 4096; ++it) {
+      prod *= u01(st.next());
+      if (prod > enlam) x += 1.0f; else break;
+    }
+    return x;
+  }
+  const float slam = sqrtf(lam), loglam = logf(lam);
+  const float b = __fadd_rn(0.931f, __fmul_rn(2.53f, slam));
+  const float a = __fadd_rn(-0.059f, __fmul_rn(0.02483f, b));
+  const float invalpha = 1.1239f + 1.1328f / (b - 3.4f);
+  const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+  const float li = floorf(lam), lf = lam - li;
+  for (int it = 0; it < 512; ++it) {
+    const float U = u01(st.next()) - 0.5f;
+    const float V = u01(st.next());
+    const float us = 0.5f - fabsf(U);
+    // explicit roundings (no FMA contraction) so the oracle reproduces k exactly
+    const float d = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(__fmul_rn(2.0f, a), us), b), U), 0.43f);
+    const float kf = li + floorf(lf + d);
+    if (us >= 0.07f && V <= vr) return kf;
+    if (!(kf >= 0.0f) || !isfinite(kf) || (us < 0.013f && V > us)) continue;
+    const float lhs = logf(V) + logf(invalpha) - logf(a / (us * us) + b);
+    if (lhs <= poisson_logpmf(kf, lam, li, lf, loglam)) return kf;
+  }
+  return li;
+}

@@ -1,0 +1,418 @@
+// Trajectory -> fluorescence frame renderer (sm_100a).
+//
+// Replaces the triple Python loop of the reference
+//   helpers/helpersGeneration.py:128-278 trajectories_to_video
+//   helpers/helpersGeneration.py:283-319 trajectory_to_video
+//   helpers/helpersGeneration.py:77-97   gaussian_2d
+//   helpers/helpersGeneration.py:356-400 normalize_images (fused, optional)
+//   Experiments/PSFNoise/trainSettingsPSFNoise.py:196-309 trajs_to_vid_psf_noise
+// by the separable closed form: the reference evaluates a GxG exp
+// grid per sub-position and renormalises it by its on-grid maximum; that is exactly
+//   I * ay (x) ax,  a[j] = exp(-((x_j-c)^2 - min_j (x_j-c)^2) / (2 sigma^2)),
+// so the UxU block mean factorises into two length-P vectors of U-term sums.
+//
+// One warp renders one frame: (1) sub-position centres in float64 (scale, flip, centring),
+// reduced to (nearest grid node, float32 offset); (2) the 2*n*P axis table in shared memory;
+// (3) every lane accumulates its pixels over the n sub-positions, adds the clipped Gaussian
+// background and the Poisson factor from the pixel's own Philox stream, normalises and
+// stores -- consecutive lanes write consecutive pixels (coalesced, frames are contiguous).
+#include "common.cuh"
+#include "philox.cuh"
+#include "../../include/mivit.h"
+
+namespace {
+
+constexpr int kMaxVariants = 8;
+
+struct RenderDev {
+  double scale, ysign, inv2s2_d, step_d;
+  int P, U, n, center, draw, G, limit, T, F;
+  float imean, istd;  // per-sub-position intensity mean/std (V1) or per-frame (PSFNoise)
+  float bg_mean, bg_std, bg_hi, poisson;
+  int normalize, mean_noise;
+  float norm_sub, norm_div;
+  float inv2s2, step;
+  uint32_t k0, k1;
+  unsigned long long seq_offset;
+  long long out_seq_stride;
+};
+
+struct PsfNoiseDev {
+  int n_psf, n_noise;
+  float inv2s2[kMaxVariants];
+  double inv2s2_d[kMaxVariants];
+  float bg_std[kMaxVariants], bg_hi[kMaxVariants];
+};
+
+// per-warp shared memory carve-up
+struct WarpSmem {
+  float* tab;   // [n][2][P]   axis 0 = x (columns), axis 1 = y (rows)
+  float* inten; // [n]
+  float* c0;    // [2n]  (x: p, y: n+p)
+  int* jc;      // [2n]
+  float* msq;   // [n]   min squared distance (x+y) in HR pixels^2, for the NaN rule
+};
+
+__device__ __forceinline__ WarpSmem carve(float* base, int n, int P) {
+  WarpSmem w;
+  w.tab = base;
+  w.inten = base + 2 * n * P;
+  w.c0 = w.inten + n;
+  w.jc = reinterpret_cast<int*>(w.c0 + 2 * n);
+  w.msq = reinterpret_cast<float*>(w.jc + 2 * n);
+  return w;
+}
+__host__ __device__ inline int warp_smem_floats(int n, int P) { return 2 * n * P + 6 * n; }
+
+// (1) centres of the n sub-positions of frame f  (helpersGeneration.py:289-293)
+__device__ __forceinline__ void frame_centres(const RenderDev& d, const double* __restrict__ traj_seq, int f,
+                                              int lane, WarpSmem& w) {
+  const double* seg = traj_seq + (size_t)f * d.n * 2;
+  double mx = 0.0, my = 0.0;
+  if (d.center) {
+    for (int p = 0; p < d.n; ++p) {  // sequential like np.mean(axis=0)
+      mx += seg[2 * p] * d.scale;
+      my += seg[2 * p + 1] * d.scale * d.ysign;
+    }
+    mx /= (double)d.n;
+    my /= (double)d.n;
+  }
+  for (int p = lane; p < d.n; p += 32) {
+    const double cx = (seg[2 * p] * d.scale - mx) * (double)d.U;
+    const double cy = (seg[2 * p + 1] * d.scale * d.ysign - my) * (double)d.U;
+    int jx = (int)fmin(fmax(rint((cx + d.limit) / d.step_d), 0.0), (double)(d.G - 1));
+    int jy = (int)fmin(fmax(rint((cy + d.limit) / d.step_d), 0.0), (double)(d.G - 1));
+    const double ox = cx - (-(double)d.limit + jx * d.step_d);
+    const double oy = cy - (-(double)d.limit + jy * d.step_d);
+    w.jc[p] = jx;
+    w.jc[d.n + p] = jy;
+    w.c0[p] = (float)ox;
+    w.c0[d.n + p] = (float)oy;
+    const float fx = (float)ox, fy = (float)oy;
+    w.msq[p] = (float)((double)fx * (double)fx + (double)fy * (double)fy);
+  }
+}
+
+// (2) axis table: block means of exp(-(k (k - 2 c0)) / 2 sigma^2)
+__device__ __forceinline__ void axis_table(const RenderDev& d, float inv2s2, int lane, WarpSmem& w) {
+  const int P = d.P, U = d.U, n = d.n;
+  const int entries = 2 * n * P;
+  const float invU = 1.0f;  // division below (matches np.mean)
+  (void)invU;
+  for (int e = lane; e < entries; e += 32) {
+    const int p = e / (2 * P);
+    const int r = e - p * 2 * P;
+    const int axis = r / P;
+    const int b = r - axis * P;
+    const int idx = axis * n + p;
+    const int jc = w.jc[idx];
+    const float c0 = w.c0[idx];
+    float acc = 0.0f;
+    for (int u = 0; u < U; ++u) {
+      const float k = __fmul_rn((float)(b * U + u - jc), d.step);
+      const float t = __fmul_rn(k, __fsub_rn(k, 2.0f * c0));
+      acc += expf(__fmul_rn(-t, inv2s2));
+    }
+    w.tab[(p * 2 + axis) * P + b] = acc / (float)U;
+  }
+}
+
+__device__ __forceinline__ float pixel_signal(const RenderDev& d, const WarpSmem& w, int a, int b) {
+  float acc = 0.0f;
+  const int P = d.P;
+  for (int p = 0; p < d.n; ++p) {
+    const float t = __fmul_rn(w.inten[p], w.tab[(p * 2 + 1) * P + a]);
+    acc = __fadd_rn(acc, __fmul_rn(t, w.tab[(p * 2 + 0) * P + b]));
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict__ traj, long long n_frames_total,
+                                                        RenderDev d, float* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  WarpSmem w = carve(smem + (size_t)warp * warp_smem_floats(d.n, d.P), d.n, d.P);
+  const long long gf = (long long)blockIdx.x * warps + warp;  // global frame index
+  if (gf >= n_frames_total) return;
+  const long long s = gf / d.F;
+  const int f = (int)(gf - s * d.F);
+  const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
+  const int P = d.P, n = d.n;
+
+  if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
+  __syncwarp();
+  if (d.draw) {
+    for (int p = lane; p < n; p += 32) {  // spot intensities (helpersGeneration.py:300)
+      float z = 0.0f, z1;
+      if (!d.mean_noise) {
+        const uint4 r = philox4x32_10((uint32_t)(f * n + p), 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
+        box_muller(r.x, r.y, z, z1);
+      }
+      float I = __fadd_rn(d.imean, __fmul_rn(d.istd, z));
+      if ((double)w.msq[p] * d.inv2s2_d > 745.0) I = __int_as_float(0x7fc00000);  // spot underflows: NaN frame (:305-308)
+      w.inten[p] = I;
+    }
+    __syncwarp();
+    axis_table(d, d.inv2s2, lane, w);
+    __syncwarp();
+  }
+  float* dst = out + s * d.out_seq_stride + (long long)f * P * P;
+  for (int pix = lane; pix < P * P; pix += 32) {
+    const int a = pix / P, b = pix - a * P;
+    float v = d.draw ? pixel_signal(d, w, a, b) : 0.0f;
+    PixelStream st;
+    float zb = 0.0f, z1;
+    if (!d.mean_noise) {
+      st.item = (uint32_t)(f * P * P + pix); st.seq = seq; st.sw = stream_word(MIVIT_STREAM_PIXEL, 0);
+      st.k0 = d.k0; st.k1 = d.k1; st.q = 0;
+      st.cur = philox4x32_10(st.item, 0u, seq, st.sw, d.k0, d.k1);
+      box_muller(st.cur.x, st.cur.y, zb, z1);
+    }
+    const float bg = fminf(fmaxf(__fadd_rn(d.bg_mean, __fmul_rn(d.bg_std, zb)), 0.0f), d.bg_hi);  // :312-313
+    v = __fadd_rn(v, bg);
+    if (d.poisson != -1.0f) {  // :316-317 multiplicative Poisson
+      const float k = d.mean_noise ? d.poisson : poisson_draw(d.poisson, st);
+      v = __fdiv_rn(__fmul_rn(v, k), d.poisson);
+    }
+    if (d.normalize) v = __fdiv_rn(__fsub_rn(v, d.norm_sub), d.norm_div);  // :395
+    dst[pix] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) render_psfnoise_kernel(const double* __restrict__ traj, long long n_frames_total,
+                                                              RenderDev d, PsfNoiseDev v, float* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  WarpSmem w = carve(smem + (size_t)warp * warp_smem_floats(d.n, d.P), d.n, d.P);
+  const long long gf = (long long)blockIdx.x * warps + warp;
+  if (gf >= n_frames_total) return;
+  const long long s = gf / d.F;
+  const int f = (int)(gf - s * d.F);
+  const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
+  const int P = d.P, n = d.n, PP = d.P * d.P;
+
+  if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
+  float spot = 0.0f;
+  if (d.draw) {  // one intensity per frame, shared by sub-positions and PSFs (trainSettingsPSFNoise.py:279,286)
+    float z = 0.0f, z1;
+    if (!d.mean_noise) {
+      const uint4 r = philox4x32_10((uint32_t)f, 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
+      box_muller(r.x, r.y, z, z1);
+    }
+    spot = __fdiv_rn(__fadd_rn(d.imean, __fmul_rn(d.istd, z)), (float)n);
+  }
+  __syncwarp();
+  for (int i = 0; i < v.n_psf; ++i) {
+    if (d.draw) {
+      for (int p = lane; p < n; p += 32)
+        w.inten[p] = ((double)w.msq[p] * v.inv2s2_d[i] > 745.0) ? __int_as_float(0x7fc00000) : spot;
+      __syncwarp();
+      axis_table(d, v.inv2s2[i], lane, w);
+      __syncwarp();
+    }
+    for (int pix = lane; pix < PP; pix += 32) {
+      const int a = pix / P, b = pix - a * P;
+      float prev = d.draw ? pixel_signal(d, w, a, b) : 0.0f;
+      for (int j = 0; j < v.n_noise; ++j) {
+        PixelStream st;
+        float zb = 0.0f, z1;
+        if (!d.mean_noise) {
+          st.item = (uint32_t)(f * PP + pix); st.seq = seq;
+          st.sw = stream_word(MIVIT_STREAM_PIXEL, (uint32_t)(1 + i * v.n_noise + j));
+          st.k0 = d.k0; st.k1 = d.k1; st.q = 0;
+          st.cur = philox4x32_10(st.item, 0u, seq, st.sw, d.k0, d.k1);
+          box_muller(st.cur.x, st.cur.y, zb, z1);
+        }
+        const float bg = fminf(fmaxf(__fadd_rn(d.bg_mean, __fmul_rn(v.bg_std[j], zb)), 0.0f), v.bg_hi[j]);  // :303
+        const float lam = __fmul_rn(__fadd_rn(prev, bg), d.poisson);
+        const float k = d.mean_noise ? lam : poisson_draw(lam, st);
+        const float val = __fdiv_rn(k, d.poisson);                                                          // :305
+        if (j == 0) prev = val;  // out[psf,0,f] is overwritten by its noisy version (:303-305)
+        out[((((size_t)s * v.n_psf + i) * v.n_noise + j) * d.F + f) * PP + pix] = val;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// One warp per sequence: D draw, steps, float64 prefix sum.
+struct DGroups { float mean[16], var[16]; };
+
+__global__ void __launch_bounds__(128) brownian_kernel(long long N, int T, DGroups g, int n_groups, double div,
+                                                       uint32_t k0, uint32_t k1, unsigned long long seq_offset,
+                                                       double* __restrict__ traj, float* __restrict__ D_out) {
+  const int lane = threadIdx.x & 31;
+  const long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= N) return;
+  const unsigned long long gid = seq_offset + (unsigned long long)s;
+  const uint32_t seq = (uint32_t)gid;
+  const int grp = (int)(gid % (unsigned long long)n_groups);
+  float D = 0.0f;
+  if (lane == 0) {
+    const float mu = g.mean[grp], sd = sqrtf(g.var[grp]);
+    for (uint32_t blk = 0; blk < 64 && !(D > 0.0f); ++blk) {
+      const uint4 r = philox4x32_10(0u, blk, seq, stream_word(MIVIT_STREAM_D, 0), k0, k1);
+      float z[4];
+      box_muller(r.x, r.y, z[0], z[1]);
+      box_muller(r.z, r.w, z[2], z[3]);
+      for (int i = 0; i < 4 && !(D > 0.0f); ++i) D = __fadd_rn(mu, __fmul_rn(sd, z[i]));
+    }
+    if (!(D > 0.0f)) D = mu > 0.0f ? mu : 1.0f;
+    D_out[s] = D;
+  }
+  D = __shfl_sync(0xffffffffu, D, 0);
+  const float sig = sqrtf(2.0f * D);
+  const int C = (T + 31) / 32;
+  const int t0 = lane * C, t1 = min(T, t0 + C);
+  double sx = 0.0, sy = 0.0;
+  for (int t = max(t0, 1); t < t1; ++t) {  // position 0 is the origin; step t moves to position t
+    const uint4 r = philox4x32_10((uint32_t)t, 0u, seq, stream_word(MIVIT_STREAM_TRAJ, 0), k0, k1);
+    float zx, zy;
+    box_muller(r.x, r.y, zx, zy);
+    sx += (double)__fmul_rn(sig, zx);
+    sy += (double)__fmul_rn(sig, zy);
+  }
+  double px = sx, py = sy;  // inclusive scan of lane totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double ux = __shfl_up_sync(0xffffffffu, px, o), uy = __shfl_up_sync(0xffffffffu, py, o);
+    if (lane >= o) { px += ux; py += uy; }
+  }
+  double ax = px - sx, ay = py - sy;  // exclusive prefix
+  double* dst = traj + (size_t)s * T * 2;
+  for (int t = t0; t < t1; ++t) {
+    if (t >= 1) {
+      const uint4 r = philox4x32_10((uint32_t)t, 0u, seq, stream_word(MIVIT_STREAM_TRAJ, 0), k0, k1);
+      float zx, zy;
+      box_muller(r.x, r.y, zx, zy);
+      ax += (double)__fmul_rn(sig, zx);
+      ay += (double)__fmul_rn(sig, zy);
+    }
+    dst[2 * t] = ax / div;
+    dst[2 * t + 1] = ay / div;
+  }
+}
+
+int fill_dev(const mivit_render_params* prm, int T, uint64_t seed, uint64_t seq_offset, RenderDev& d) {
+  MIVIT_CHECK_ARG(prm != nullptr, "render params are NULL");
+  MIVIT_CHECK_ARG(prm->P >= 1 && prm->P <= 128, "output_size %d out of range [1,128]", prm->P);
+  MIVIT_CHECK_ARG(prm->U >= 1 && prm->U <= 64, "upsampling_factor %d out of range [1,64]", prm->U);
+  MIVIT_CHECK_ARG(prm->n >= 1 && prm->n <= 1024, "nPosPerFrame %d out of range [1,1024]", prm->n);
+  MIVIT_CHECK_ARG(T % prm->n == 0, "T is not divisble by posPerFrame");
+  MIVIT_CHECK_ARG(prm->sigma_hr > 0.0, "PSF sigma must be positive");
+  d.scale = prm->scale;
+  d.ysign = prm->flip_y ? -1.0 : 1.0;
+  d.P = prm->P; d.U = prm->U; d.n = prm->n; d.center = prm->center; d.draw = prm->draw;
+  d.G = prm->P * prm->U;
+  d.limit = (d.G - 1) / 2;
+  d.step_d = d.G > 1 ? 2.0 * d.limit / (double)(d.G - 1) : 1.0;
+  if (d.step_d == 0.0) d.step_d = 1.0;
+  d.step = (float)d.step_d;
+  d.inv2s2_d = 1.0 / (2.0 * prm->sigma_hr * prm->sigma_hr);
+  d.inv2s2 = (float)d.inv2s2_d;
+  d.T = T; d.F = T / prm->n;
+  d.imean = prm->part_mean; d.istd = prm->part_std;
+  d.bg_mean = prm->bg_mean; d.bg_std = prm->bg_std;
+  d.bg_hi = (float)((double)prm->bg_mean + 3.0 * (double)prm->bg_std);
+  d.poisson = prm->poisson;
+  d.normalize = prm->normalize; d.norm_sub = prm->norm_sub; d.norm_div = prm->norm_div;
+  d.mean_noise = prm->mean_noise;
+  d.k0 = (uint32_t)(seed & 0xFFFFFFFFull); d.k1 = (uint32_t)(seed >> 32);
+  d.seq_offset = seq_offset;
+  return MIVIT_OK;
+}
+
+int pick_warps(int n, int P, int* warps, size_t* smem) {
+  const size_t per_warp = (size_t)warp_smem_floats(n, P) * sizeof(float);
+  int w = 8;
+  while (w > 1 && per_warp * w > 48 * 1024) w >>= 1;
+  MIVIT_CHECK_ARG(per_warp * w <= 200 * 1024, "nPosPerFrame*output_size too large for shared memory (%zu bytes per frame)", per_warp);
+  *warps = w;
+  *smem = per_warp * w;
+  return MIVIT_OK;
+}
+
+}  // namespace
+
+extern "C" int mivit_render_v1(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
+                               uint64_t seq_offset, float* out, int64_t out_seq_stride, void* stream) {
+  RenderDev d;
+  int rc = fill_dev(prm, T, seed, seq_offset, d);
+  if (rc) return rc;
+  MIVIT_CHECK_ARG(N >= 0, "negative N");
+  if (N == 0) return MIVIT_OK;
+  MIVIT_CHECK_ARG(traj && out, "NULL device pointer");
+  // V1 draws one intensity per sub-position: N(mean/n, std/n)  (helpersGeneration.py:300)
+  d.imean = (float)((double)prm->part_mean / prm->n);
+  d.istd = (float)((double)prm->part_std / prm->n);
+  d.out_seq_stride = out_seq_stride;
+  int warps; size_t smem;
+  rc = pick_warps(d.n, d.P, &warps, &smem);
+  if (rc) return rc;
+  if (smem > 48 * 1024)
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long frames = (long long)N * d.F;
+  render_v1_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, out);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_render_psfnoise(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm,
+                                     const float* psf_div_host, int32_t n_psf, const float* noise_frac_host,
+                                     int32_t n_noise, float part_mean_global, uint64_t seed, uint64_t seq_offset,
+                                     float* out, void* stream) {
+  RenderDev d;
+  int rc = fill_dev(prm, T, seed, seq_offset, d);
+  if (rc) return rc;
+  MIVIT_CHECK_ARG(n_psf >= 1 && n_noise >= 1 && psf_div_host && noise_frac_host, "No settings given");
+  MIVIT_CHECK_ARG(n_psf <= kMaxVariants && n_noise <= kMaxVariants, "at most %d PSF and %d noise settings", kMaxVariants, kMaxVariants);
+  MIVIT_CHECK_ARG(prm->poisson > 0.0f, "PSFNoise renderer needs poisson_noise > 0");
+  if (N == 0) return MIVIT_OK;
+  MIVIT_CHECK_ARG(traj && out, "NULL device pointer");
+  d.ysign = 1.0;  // no y flip in this variant
+  d.normalize = 0;
+  PsfNoiseDev v;
+  v.n_psf = n_psf; v.n_noise = n_noise;
+  for (int i = 0; i < n_psf; ++i) {
+    MIVIT_CHECK_ARG(psf_div_host[i] > 0.0f, "PSF setting must be positive");
+    const double sg = prm->sigma_hr / (double)psf_div_host[i];  // :290
+    v.inv2s2_d[i] = 1.0 / (2.0 * sg * sg);
+    v.inv2s2[i] = (float)v.inv2s2_d[i];
+  }
+  for (int j = 0; j < n_noise; ++j) {
+    const double bs = (double)part_mean_global * (double)noise_frac_host[j];  // :302
+    v.bg_std[j] = (float)bs;
+    v.bg_hi[j] = (float)((double)prm->bg_mean + 3.0 * (double)v.bg_std[j]);
+  }
+  int warps; size_t smem;
+  rc = pick_warps(d.n, d.P, &warps, &smem);
+  if (rc) return rc;
+  if (smem > 48 * 1024)
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_psfnoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long frames = (long long)N * d.F;
+  render_psfnoise_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, v, out);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_brownian(int64_t N, int32_t T, const float* group_mean_host, const float* group_var_host,
+                              int32_t n_groups, double div, uint64_t seed, uint64_t seq_offset, double* traj,
+                              float* D_out, void* stream) {
+  MIVIT_CHECK_ARG(N >= 0 && T >= 1, "bad N/T");
+  MIVIT_CHECK_ARG(n_groups >= 1 && n_groups <= 16 && group_mean_host && group_var_host, "need 1..16 D groups");
+  MIVIT_CHECK_ARG(div != 0.0, "div must be non-zero");
+  if (N == 0) return MIVIT_OK;
+  MIVIT_CHECK_ARG(traj && D_out, "NULL device pointer");
+  DGroups g;
+  for (int i = 0; i < 16; ++i) { g.mean[i] = i < n_groups ? group_mean_host[i] : 0.f; g.var[i] = i < n_groups ? group_var_host[i] : 0.f; }
+  brownian_kernel<<<mivit_ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(
+      N, T, g, n_groups, div, (uint32_t)(seed & 0xFFFFFFFFull), (uint32_t)(seed >> 32),
+      seq_offset, traj, D_out);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}

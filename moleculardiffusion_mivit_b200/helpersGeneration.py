@@ -1,0 +1,172 @@
+"""Drop-in mirror of the reference's helpers/helpersGeneration.py renderer API
+ on top of the CUDA renderer (csrc/render.cu).
+
+Same names, positional order, defaults, return types, error messages and side effects:
+  trajectories_to_video   helpers/helpersGeneration.py:128-278 (flips the caller's y in place, :197)
+  normalize_images        helpers/helpersGeneration.py:356-400
+  brownian_motion         helpers/helpersGeneration.py:9-45   (device Philox source)
+Extra keyword-only arguments (`seed`, `seq_offset`, ...) are additions; with seed=None a
+seed is drawn from np.random so unseeded behaviour stays random and np.random.seed still
+controls it.  Inputs may be numpy arrays (host: copied to the GPU and back inside the
+call) or CUDA float64 torch tensors (device resident: a CUDA float32 tensor is returned).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["trajectories_to_video", "normalize_images", "brownian_motion", "derive_render_params",
+           "DEFAULT_IMAGE_PROPS", "render_device"]
+
+DEFAULT_IMAGE_PROPS = {  # helpers/helpersGeneration.py:205-222
+    "particle_intensity": [500, 20],
+    "NA": 1.46,
+    "wavelength": 500e-9,
+    "psf_division_factor": 1,
+    "resolution": 100e-9,
+    "output_size": 32,
+    "upsampling_factor": 5,
+    "background_intensity": [100, 10],
+    "poisson_noise": 100,
+    "trajectory_unit": 100,
+}
+
+
+def _draw_seed(seed):
+    if seed is None:
+        return int(np.random.randint(0, 2 ** 62, dtype=np.int64))
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+def derive_render_params(image_props, nPosPerFrame, center, variant="v1"):
+    """Host-side scalar set-up of :225-247 (or trainSettingsPSFNoise.py:237-259) -> RenderParams."""
+    d = dict(DEFAULT_IMAGE_PROPS)
+    if variant == "psfnoise":
+        d["poisson_noise"] = 1
+    d.update(image_props)
+    res, unit = d["resolution"], d["trajectory_unit"]
+    if unit == -1:
+        scale = 1.0
+    elif variant == "psfnoise":
+        scale = unit * 1e-9 / res
+    else:
+        scale = unit / (res * 1e9)
+    U = int(d["upsampling_factor"])
+    if variant == "psfnoise":
+        fwhm = d["wavelength"] / 2 * d["NA"]
+    else:
+        fwhm = d["wavelength"] / 2 * d["NA"] / d["psf_division_factor"]
+    sigma = U / res * fwhm / 2.355
+    pm, pstd = d["particle_intensity"][0], d["particle_intensity"][1]
+    bm, bs = d["background_intensity"][0], d["background_intensity"][1]
+    p = _lib.RenderParams()
+    p.scale, p.sigma_hr = float(scale), float(sigma)
+    p.P, p.U, p.n = int(d["output_size"]), U, int(nPosPerFrame)
+    p.center, p.flip_y = int(bool(center)), 0 if variant == "psfnoise" else 1
+    p.draw = int(pm > 0.0001 and pstd > 0.0001)
+    p.part_mean, p.part_std, p.bg_mean, p.bg_std = float(pm), float(pstd), float(bm), float(bs)
+    p.poisson = float(d["poisson_noise"])
+    p.normalize, p.norm_sub, p.norm_div, p.mean_noise = 0, 0.0, 1.0, 0
+    return p
+
+
+def _to_device_f64(trajectories, dev):
+    """numpy (host) or torch tensor -> contiguous CUDA float64 tensor.  Returns (tensor, was_host)."""
+    import torch
+    if isinstance(trajectories, torch.Tensor):
+        t = trajectories
+        if t.device.type != "cuda":
+            t = t.to(dev, non_blocking=True)
+        return t.to(torch.float64).contiguous(), False
+    host = torch.from_numpy(np.ascontiguousarray(trajectories, dtype=np.float64))
+    return host.to(dev, non_blocking=False), True
+
+
+def render_device(traj_dev, prm, seed, seq_offset=0, out=None, out_seq_stride=None, flip_y_applied=True):
+    """Device-resident core: traj_dev CUDA float64 (N,T,2) -> CUDA float32 (N,F,P,P).
+    prm.flip_y selects the sign the frames are rendered with; traj_dev is not modified."""
+    import torch
+    N, T, _ = traj_dev.shape
+    F = T // prm.n
+    if out is None:
+        out = torch.empty((N, F, prm.P, prm.P), dtype=torch.float32, device=traj_dev.device)
+        out_seq_stride = F * prm.P * prm.P
+    _lib.check(_lib.lib().mivit_render_v1(_lib.ptr(traj_dev), N, T, ctypes.byref(prm), seed, int(seq_offset),
+                                          _lib.ptr(out), int(out_seq_stride), _lib.current_stream()))
+    return out
+
+
+def trajectories_to_video(trajectories, nPosPerFrame, center=False, image_props={}, use_multiprocessing=False, *,
+                          seed=None, seq_offset=0, normalize=None, _mean_noise=False):
+    """helpers/helpersGeneration.py:128-278.  `use_multiprocessing` is accepted and ignored (the
+    reference's branch is dead code: it raises TypeError, :344-348 vs :283).
+    normalize=(background_mean, background_sigma, theoretical_max) fuses normalize_images."""
+    import torch
+    dev = _lib.require_cuda()
+    N, T, _ = trajectories.shape
+    # Invert the y axis IN PLACE, exactly like the reference (:197) -- callers rely on it
+    # (trajs_to_vid_framerates alternates sign per variant; create_video_and_feature_pairs
+    # computes features from the flipped trajectories).
+    trajectories[:, :, 1] *= -1
+    if T % nPosPerFrame != 0:
+        raise Exception("T is not divisble by posPerFrame")
+    prm = derive_render_params(image_props, nPosPerFrame, center, "v1")
+    prm.flip_y = 0                      # the array we upload is already flipped
+    prm.mean_noise = int(bool(_mean_noise))
+    if normalize is not None:
+        m, s, mx = normalize
+        den = mx - (m - s)
+        if den == 0:
+            raise ValueError("Denominator in normalization is zero. Check your inputs.")
+        prm.normalize, prm.norm_sub, prm.norm_div = 1, float(m - s), float(den)
+    t_dev, was_host = _to_device_f64(trajectories, dev)
+    out = render_device(t_dev, prm, _draw_seed(seed), seq_offset)
+    if was_host:
+        return out.cpu().numpy()
+    return out
+
+
+def normalize_images(images, background_mean=None, background_sigma=None, theoretical_max=None, clip_image=False):
+    """helpers/helpersGeneration.py:356-400 -- elementwise; works on numpy arrays and torch tensors
+    (host metadata only, the arithmetic of the array type is used as in the reference)."""
+    import torch
+    is_t = isinstance(images, torch.Tensor)
+    if background_mean is None:
+        background_mean = images.mean().item() if is_t else np.mean(images)
+    if background_sigma is None:
+        background_sigma = images.std(unbiased=False).item() if is_t else np.std(images)
+    if theoretical_max is None:
+        theoretical_max = images.max().item() if is_t else np.max(images)
+    denominator = theoretical_max - (background_mean - background_sigma)
+    if denominator == 0:
+        raise ValueError("Denominator in normalization is zero. Check your inputs.")
+    normalized = (images - (background_mean - background_sigma)) / denominator
+    if clip_image:
+        normalized = normalized.clamp(0, 1.5) if is_t else np.clip(normalized, 0, 1.5)
+    return normalized, (background_mean, background_sigma, theoretical_max)
+
+
+def brownian_motion(nparticles, nframes, nposframe, D, dt, startAtZero=False, *, seed=None, seq_offset=0,
+                    D_var=0.0, div=1.0, return_device=False, return_D=False):
+    """helpers/helpersGeneration.py:9-45 on the device: steps ~ N(0, 2 D dt / nposframe) per axis,
+    cumulative sum.  Positions start at the origin (the reference starts at the first step unless
+    startAtZero; with centring only differences matter).  D may be a scalar or a list of group
+    means (global sequence id g uses group g % len(D)); D_var is the variance of the per-sequence D
+    (the andi_datasets `Ds=[mean, var]` call sites, trainModelsPSFNoise.py:128-132)."""
+    import torch
+    dev = _lib.require_cuda()
+    T = int(nframes) * int(nposframe)
+    means = np.atleast_1d(np.asarray(D, dtype=np.float32)) * np.float32(dt / nposframe)
+    vars_ = np.broadcast_to(np.atleast_1d(np.asarray(D_var, dtype=np.float32)) * np.float32((dt / nposframe) ** 2),
+                            means.shape).astype(np.float32).copy()
+    traj = torch.empty((nparticles, T, 2), dtype=torch.float64, device=dev)
+    Dout = torch.empty((nparticles,), dtype=torch.float32, device=dev)
+    fp = ctypes.POINTER(ctypes.c_float)
+    _lib.check(_lib.lib().mivit_brownian(nparticles, T, means.ctypes.data_as(fp), vars_.ctypes.data_as(fp), len(means),
+                                         float(div), _draw_seed(seed), int(seq_offset), _lib.ptr(traj), _lib.ptr(Dout),
+                                         _lib.current_stream()))
+    Dout = Dout / float(dt / nposframe)
+    if not return_device:
+        traj, Dout = traj.cpu().numpy(), Dout.cpu().numpy()
+    return (traj, Dout) if return_D else traj

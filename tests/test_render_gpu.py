@@ -1,0 +1,195 @@
+"""GPU parity tests (-m gpu) of the CUDA renderer, called through the Python mirrors which go
+through the C ABI (include/mivit.h).  Checker = oracle/ (numpy) + goldens from the reference."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import render_oracle as ro
+from oracle.make_golden import C3_PROPS
+from oracle.noise import PhiloxNoise
+from oracle.trajectory_oracle import brownian_oracle
+
+CLEAN = dict(C3_PROPS, background_intensity=[0, 0], poisson_noise=-1)
+PSF = [2, 1.75, 1.5, 1.25, 1]
+NOISE = [0, 1 / 50, 1 / 25, 1 / 20, 1 / 10, 1 / 5]
+PSFNOISE_PROPS = dict(C3_PROPS, particle_intensity=[5000, 500], background_intensity=[5000, 0])
+FRAMERATE_PROPS = dict(C3_PROPS, output_size=13)
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return (np.load(os.path.join(golden_dir, "render_inputs.npz")),
+            np.load(os.path.join(golden_dir, "render_golden.npz")),
+            np.load(os.path.join(golden_dir, "render_noise_stats.npz")))
+
+
+@pytest.fixture(scope="module")
+def gen():
+    from moleculardiffusion_mivit_b200 import helpersGeneration
+    return helpersGeneration
+
+
+@pytest.fixture(scope="module")
+def exp():
+    from moleculardiffusion_mivit_b200 import experiments
+    return experiments
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("key,sl,n,center,over", [
+    ("v1_p9_center", slice(0, 8), 10, True, {}),
+    ("v1_p9_nocenter", slice(0, 2), 10, False, {}),
+    ("v1_p13_center", slice(0, 2), 10, True, {"output_size": 13}),
+    ("v1_p8_center", slice(0, 1), 10, True, {"output_size": 8}),
+    ("v1_p7u10_n15", slice(0, 1), 15, True, {"output_size": 7, "upsampling_factor": 10}),
+])
+def test_noise_free_matches_reference_golden(gold, gen, key, sl, n, center, over):
+    inp, g, _ = gold
+    t = inp["traj30"][sl].copy()
+    props = dict(CLEAN, **over)
+    out = gen.trajectories_to_video(t, n, center, props, _mean_noise=True)
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == g[key].shape
+    assert np.array_equal(t[:, :, 1], -inp["traj30"][sl][:, :, 1])      # in-place y flip (reference :197)
+    flat, ref = out.reshape(*out.shape[:2], -1), g[key].reshape(*out.shape[:2], -1)
+    assert np.array_equal(flat.argmax(-1), ref.argmax(-1))              # index / patch layout: exact
+    assert relmax(out, g[key]) < 1e-5                                   # north_star tolerance (fp32)
+    orc = ro.render_v1(inp["traj30"][sl], n, center, props)
+    assert relmax(out, orc) < 2e-6
+
+
+def test_fused_normalisation_and_background(gold, gen):
+    inp, g, _ = gold
+    out = gen.trajectories_to_video(inp["traj30"][:2].copy(), 10, True, dict(C3_PROPS, poisson_noise=-1),
+                                    normalize=(1420, 290, 6000), _mean_noise=True)
+    assert np.abs(out - g["v1_p9_bgmean_norm"]).max() < 5e-6
+    raw = gen.trajectories_to_video(inp["traj30"][:2].copy(), 10, True, dict(C3_PROPS, poisson_noise=-1), _mean_noise=True)
+    nrm, meta = gen.normalize_images(raw, 1420, 290, 6000)
+    assert meta == (1420, 290, 6000) and np.abs(nrm - out).max() < 1e-6
+    with pytest.raises(ValueError, match="Denominator"):
+        gen.normalize_images(raw, 10, 0, 10)
+
+
+def test_errors_and_edge_cases(gen, exp):
+    with pytest.raises(Exception, match="T is not divisble by posPerFrame"):
+        gen.trajectories_to_video(np.zeros((1, 25, 2)), 10, True, CLEAN)
+    with pytest.raises(Exception, match="No settings given"):
+        exp.trajs_to_vid_psf_noise(np.zeros((1, 20, 2)), 10, True, PSFNOISE_PROPS, [], [])
+    out = gen.trajectories_to_video(np.zeros((0, 20, 2)), 10, True, CLEAN)
+    assert out.shape == (0, 2, 9, 9)
+    # particle_std <= 1e-4 -> no particle is drawn (reference :299): background only
+    props = dict(C3_PROPS, particle_intensity=[4580, 0], poisson_noise=-1)
+    out = gen.trajectories_to_video(np.zeros((1, 20, 2)), 10, True, props, _mean_noise=True)
+    assert np.all(out == 1420)
+    # a spot tens of pixels outside the image underflows in the reference and yields NaN frames
+    far = np.zeros((1, 10, 2)); far[:, :, 0] = 1e4
+    out = gen.trajectories_to_video(far, 10, False, CLEAN, _mean_noise=True)
+    assert np.isnan(out).all()
+
+
+def test_noisy_v1_matches_philox_oracle(gold, gen):
+    inp, _, _ = gold
+    t = inp["traj30"][:3]
+    out = gen.trajectories_to_video(t.copy(), 10, True, C3_PROPS, seed=1234, seq_offset=5)
+    orc = ro.render_v1(t, 10, True, C3_PROPS, noise=PhiloxNoise(1234), seq_offset=5)
+    bad = np.abs(out - orc) > 1e-4 * np.abs(orc) + 1e-2
+    assert bad.mean() < 2e-3, bad.mean()        # same counter stream -> same draws (rare fp ties differ)
+
+
+def test_noisy_v1_statistics_vs_reference(gold, gen):
+    inp, _, st = gold
+    v = np.stack([gen.trajectories_to_video(inp["traj30"].copy(), 10, True, C3_PROPS, seed=50 + r)
+                  for r in range(40)]).astype(np.float64)
+    assert abs(v.mean() - st["v1_mean"]) / st["v1_mean"] < 2e-3
+    assert abs(v.std() - st["v1_std"]) / st["v1_std"] < 5e-3
+    assert np.abs(v.mean(axis=(0, 1, 2)) - st["v1_pix_mean"]).max() / st["v1_pix_mean"].max() < 5e-3
+    assert np.abs(v.std(axis=(0, 1, 2)) / st["v1_pix_std"] - 1).max() < 3e-2
+    q = np.linspace(0, 1, len(st["v1_quantiles"]))
+    s = np.sort(v.ravel())
+    ks = np.abs(np.searchsorted(s, st["v1_quantiles"], side="right") / s.size - q).max()
+    assert ks < 5e-3, ks
+
+
+def test_psfnoise(gold, exp):
+    inp, g, st = gold
+    t = inp["traj20"][:1]
+    out = exp.trajs_to_vid_psf_noise(t.copy(), 10, True, PSFNOISE_PROPS, PSF, NOISE, _mean_noise=True)
+    assert out.shape == (1, 5, 6, 20, 9, 9) and out.dtype == np.float32
+    assert relmax(out, g["psfnoise_mean"]) < 1e-5
+    tt = inp["traj20"].copy()
+    out = exp.trajs_to_vid_psf_noise(tt, 10, True, PSFNOISE_PROPS, PSF, NOISE, seed=99)
+    assert np.array_equal(tt, inp["traj20"])                              # no y flip in this variant
+    orc = ro.render_psfnoise(inp["traj20"], 10, True, PSFNOISE_PROPS, PSF, NOISE, noise=PhiloxNoise(99))
+    bad = np.abs(out - orc) > 1e-4 * np.abs(orc) + 0.011                  # counts are multiples of 1/100
+    assert bad.mean() < 5e-3, bad.mean()
+    v = np.stack([exp.trajs_to_vid_psf_noise(inp["traj20"].copy(), 10, True, PSFNOISE_PROPS, PSF, NOISE, seed=7 + r)
+                  for r in range(12)]).astype(np.float64)
+    m, s = v.mean(axis=(0, 1, 4, 5, 6)), v.std(axis=(0, 1, 4, 5, 6))
+    assert np.abs(m / st["psf_mean"] - 1).max() < 3e-3                    # incl. the 5236 / 10235 double-background quirk
+    assert np.abs(s / st["psf_std"] - 1).max() < 2e-2
+    qq = np.linspace(0, 1, st["psf_quantiles"].shape[-1])
+    for i in range(5):
+        for j in range(6):
+            srt = np.sort(v[:, :, i, j].ravel())
+            ks = np.abs(np.searchsorted(srt, st["psf_quantiles"][i, j], side="right") / srt.size - qq).max()
+            assert ks < 0.02, (i, j, ks)
+
+
+def test_framerates(gold, exp):
+    import torch
+    inp, g, _ = gold
+    t = inp["traj30b"][:1].copy()
+    out = exp.trajs_to_vid_framerates(t, [5, 10, 15, 20, 30, 50], True, FRAMERATE_PROPS, _mean_noise=True)
+    assert isinstance(out, torch.Tensor) and out.device.type == "cpu" and tuple(out.shape) == (1, 6, 60, 13, 13)
+    assert np.array_equal(t, inp["traj30b"][:1])                          # six flips restore the caller's array
+    assert np.abs(out.numpy() - g["framerate_mean"]).max() < 5e-6
+    assert torch.all(out[:, 5, 6:] == 0)
+
+
+def test_brownian_source(gen):
+    gm = [1, 3, 5, 7, 9, 10.2]
+    import ctypes
+    import torch
+    from moleculardiffusion_mivit_b200 import _lib
+    N, T = 64, 300
+    traj = torch.empty((N, T, 2), dtype=torch.float64, device="cuda")
+    D = torch.empty((N,), dtype=torch.float32, device="cuda")
+    m = np.asarray(gm, dtype=np.float32); v = np.ones(6, dtype=np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    _lib.check(_lib.lib().mivit_brownian(N, T, m.ctypes.data_as(fp), v.ctypes.data_as(fp), 6, 100.0, 42, 10,
+                                         _lib.ptr(traj), _lib.ptr(D), _lib.current_stream()))
+    ot, oD = brownian_oracle(N, T, gm, [1.0] * 6, 100.0, 42, seq_offset=10)
+    assert np.abs(D.cpu().numpy() - oD).max() < 1e-5
+    assert np.abs(traj.cpu().numpy() - ot).max() < 1e-6
+    tr = gen.brownian_motion(2000, 30, 10, 2.0, 1.0, seed=1)
+    assert abs(np.diff(tr, axis=1).std() - np.sqrt(2 * 2.0 / 10)) < 0.01
+
+
+def test_full_size_properties(gen):
+    """BASELINE-size batch: sharding invariance (global sequence ids), determinism, linearity."""
+    import torch
+    from moleculardiffusion_mivit_b200.helpersGeneration import derive_render_params, render_device
+    N, T = 4096, 300
+    traj = gen.brownian_motion(N, 30, 10, [1, 3, 5, 7, 9, 10.2], 1.0, seed=3, D_var=1.0, div=100.0, return_device=True)
+    prm = derive_render_params(FRAMERATE_PROPS, 10, True)
+    a = render_device(traj, prm, seed=77)
+    b = render_device(traj, prm, seed=77)
+    assert torch.equal(a, b)
+    h0 = render_device(traj[:1000].contiguous(), prm, seed=77, seq_offset=0)
+    h1 = render_device(traj[1000:].contiguous(), prm, seed=77, seq_offset=1000)
+    assert torch.equal(torch.cat([h0, h1]), a)
+    assert torch.isfinite(a).all()
+    clean = derive_render_params(dict(FRAMERATE_PROPS, background_intensity=[0, 0], poisson_noise=-1), 10, True)
+    clean.mean_noise = 1
+    c1 = render_device(traj, clean, seed=0)
+    clean.part_mean *= 2
+    c2 = render_device(traj, clean, seed=0)
+    assert torch.allclose(c2, 2 * c1, rtol=1e-6, atol=0)
+    # centred particle: flux conserved up to the part of the PSF that falls outside the 13x13 window
+    tot = c1.sum(dim=(2, 3))
+    assert (tot > 0).all()
