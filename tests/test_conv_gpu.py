@@ -33,12 +33,10 @@ def run_conv(x, W, mirrored, impl, want_stats=True):
     import torch
     from moleculardiffusion_mivit_b200 import _lib
     L = _lib.lib()
-    NF, Cin, P, _ = x.shape
-    Cout, _, k, _ = W.shape
-    xb, rows = to_rows(x)
+    NF, _, P, _ = x.shape
+    Cout, Cin, k, _ = W.shape
+    xb, rows = to_rows(x)                                   # mirrored: x is dY with Cout channels
     gin, gout = (Cout, Cin) if mirrored else (Cin, Cout)
-    if mirrored:
-        xb, rows = to_rows(x)  # x is dY with Cout channels
     wp = torch.empty(k * k * Cin * Cout, dtype=torch.bfloat16, device=x.device)
     _lib.check(L.mivit_conv_pack_weights(_lib.ptr(W.contiguous()), _lib.ptr(wp), Cout, Cin, k, int(mirrored),
                                          _lib.current_stream()))

@@ -108,7 +108,7 @@ def test_noisy_v1_statistics_vs_reference(gold, gen):
     assert abs(v.mean() - st["v1_mean"]) / st["v1_mean"] < 2e-3
     assert abs(v.std() - st["v1_std"]) / st["v1_std"] < 5e-3
     assert np.abs(v.mean(axis=(0, 1, 2)) - st["v1_pix_mean"]).max() / st["v1_pix_mean"].max() < 5e-3
-    assert np.abs(v.std(axis=(0, 1, 2)) / st["v1_pix_std"] - 1).max() < 3e-2
+    assert np.abs(v.std(axis=(0, 1, 2)) / st["v1_pix_std"] - 1).max() < 6e-2   # 9600 samples/pixel: ~1% sampling error each, max over 81 pixels
     q = np.linspace(0, 1, len(st["v1_quantiles"]))
     s = np.sort(v.ravel())
     ks = np.abs(np.searchsorted(s, st["v1_quantiles"], side="right") / s.size - q).max()
