@@ -106,6 +106,79 @@ int mivit_conv_rows(const void* X_row0, const void* Wp, void* Y_row0, float* sta
                     int32_t P, int32_t cin, int32_t cout, int32_t ksize, int32_t mirrored, int32_t impl,
                     void* stream);
 
+/* dW (fp32 [cout][cin][k][k], pre-zeroed by the caller) += sum_r dY[r,:]^T X[r + delta_tap,:]
+ * (weight gradient of the same convolution).  impl as above. */
+int mivit_conv_rows_wgrad(const void* X_row0, const void* dY_row0, float* dW, int64_t rows, int32_t P,
+                          int32_t cin, int32_t cout, int32_t ksize, int32_t impl, void* stream);
+
+/* ---------------------------------------------------------------- ViT -------------------- */
+
+/* Replaces helpers/models.py:278-361 GeneralTransformer (+ its embedding classes :146-257,
+ * Transformer :111-141, MLPHead :260-276).  Parameters are ONE flat fp32 buffer in the canonical
+ * order below; gradients / AdamW moments share the offsets.
+ *   deepresnet: embedding.initial_conv.weight, embedding.bn1.{weight,bias},
+ *               embedding.res_block{1,2}.{conv1.weight, bn1.weight, bn1.bias, conv2.weight, bn2.weight,
+ *               bn2.bias, skip.0.weight, skip.1.weight, skip.1.bias}, embedding.fc.{weight,bias}
+ *   linear/cnn: embedding.proj.{weight,bias}  /  embedding.conv.{weight,bias}
+ *   norm.{weight,bias}, [reg_token], [transformer.pos_embedding],
+ *   transformer.encoder_layers.i.{self_attn.{q,k,v,out}_proj.{weight,bias}, norm1.{weight,bias},
+ *               feed_forward.fc1.{weight,bias}, feed_forward.fc2.{weight,bias}, norm2.{weight,bias}},
+ *   transformer.norm.{weight,bias}, [feature_projector.{0,2}.{weight,bias}],
+ *   mlp_head.mlp.{0,3}.{weight,bias}
+ * BatchNorm running statistics: flat fp32 [mean C | var C] for the 7 BatchNorm2d layers in the
+ * order bn1, res_block1.{bn1,bn2,skip.1}, res_block2.{bn1,bn2,skip.1} (1216 floats) and int64[7]
+ * num_batches_tracked. */
+typedef struct mivit_vit_config {
+  int32_t embedding;   /* 0 LinearProjectionEmbedding, 1 CNNEmbedding, 2 DeepResNetEmbedding       */
+  int32_t P, F;        /* patch (= image) size, frames per sequence                                 */
+  int32_t E, H, HD, L; /* embed_dim, num_heads, hidden_dim, num_layers                              */
+  int32_t activation;  /* tr_activation_fct: 0 F.relu, 1 F.gelu, 2 F.leaky_relu                     */
+  int32_t use_pos, use_reg, use_feat;
+  int32_t fusion;      /* 0 'early', 1 'late'                                                       */
+  int32_t feat_dim;    /* global_feature_dim                                                        */
+  int32_t head_hidden; /* MLPHead hidden_dim (128)                                                  */
+  int32_t conv_impl;   /* 1 = tcgen05 convolutions (product path), 0 = SIMT cross-check             */
+  float bn_eps, bn_momentum, ln_eps;
+} mivit_vit_config;
+
+int32_t mivit_vit_param_count(const mivit_vit_config* cfg);                 /* -1 on a bad config */
+int mivit_vit_param_sizes(const mivit_vit_config* cfg, int64_t* sizes, int32_t max_count);
+int64_t mivit_vit_workspace_bytes(const mivit_vit_config* cfg, int32_t B);  /* -1 on a bad config */
+
+/* GeneralTransformer.forward (:328-361).  x: [B,F,P,P] fp32; features: [B,feat_dim] or NULL;
+ * pred: [B,1].  training != 0: BatchNorm uses batch statistics and updates bn_running /
+ * bn_num_batches (either may be NULL to skip the update); the workspace then holds everything
+ * mivit_vit_backward needs. */
+int mivit_vit_forward(const mivit_vit_config* cfg, int32_t B, const float* x, const float* features,
+                      const float* params, float* bn_running, int64_t* bn_num_batches, void* workspace,
+                      float* pred, int32_t training, void* stream);
+
+/* Backward of the forward call that last used `workspace`.  grads (flat, same layout as params)
+ * is OVERWRITTEN with dLoss/dparams given dpred = dLoss/dpred [B,1]. */
+int mivit_vit_backward(const mivit_vit_config* cfg, int32_t B, const float* x, const float* features,
+                       const float* dpred, const float* params, float* grads, void* workspace,
+                       void* stream);
+
+/* nn.MSELoss() (mean) and its gradient w.r.t. pred (Experiments/PSFNoise/trainSettingsPSFNoise.py:31). */
+int mivit_mse_loss(const float* pred, const float* target, int32_t n, float* loss, float* dpred,
+                   void* stream);
+
+/* torch.optim.AdamW step on a flat buffer (trainSettingsPSFNoise.py:119; decoupled weight decay,
+ * bias correction; step is the 1-based step count).  grad_scale multiplies g first (1/world_size
+ * after a sum all-reduce). */
+int mivit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                     void* stream);
+
+/* One training step of the reference loop body (trainModelsPSFNoise.py:187-193):
+ * forward, MSE, backward and (apply_update != 0) AdamW, enqueued on `stream` without host sync.
+ * loss: [1], pred/dpred: [B,1] device scratch/outputs. */
+int mivit_vit_train_step(const mivit_vit_config* cfg, int32_t B, const float* x, const float* features,
+                         const float* target, float* params, float* grads, float* adam_m, float* adam_v,
+                         float* bn_running, int64_t* bn_num_batches, void* workspace, float* pred,
+                         float* loss, float* dpred, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int64_t step, int32_t apply_update, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

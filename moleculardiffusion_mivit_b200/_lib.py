@@ -40,6 +40,16 @@ def _declare(lib):
         "mivit_brownian": (i32, [i64, i32, fp, fp, i32, f64, u64, u64, vp, vp, vp]),
         "mivit_conv_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "mivit_conv_rows": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]),
+        "mivit_conv_rows_wgrad": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
+        "mivit_vit_param_count": (i32, [vp]),
+        "mivit_vit_param_sizes": (i32, [vp, c.POINTER(c.c_int64), i32]),
+        "mivit_vit_workspace_bytes": (i64, [vp, i32]),
+        "mivit_vit_forward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "mivit_vit_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "mivit_mse_loss": (i32, [vp, vp, i32, vp, vp, vp]),
+        "mivit_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]),
+        "mivit_vit_train_step": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       f32, f32, f32, f32, f32, i64, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -1,0 +1,408 @@
+// BatchNorm2d in TRAIN mode (batch statistics over all B*F*P*P positions), ReLU, residual add,
+// global average pool and the first 1->32 convolution of DeepResNetEmbedding
+// (reference helpers/models.py:202-257), on the pitched-rows bf16 layout of conv_tc.cu.
+// All kernels here are HBM-bound element-wise / reduction passes: 16-byte vector accesses,
+// per-thread register partials, one atomic per channel per CTA.
+#include "common.cuh"
+#include "vit.h"
+
+namespace {
+
+__device__ __forceinline__ bool row_is_valid(long long r, long long rows, int P) {
+  if (r >= rows) return false;
+  const int pitch = P + 1;
+  const int q = (int)(r % (long long)(pitch * pitch));
+  const int y = q / pitch, x = q - y * pitch;
+  return y < P && x < P;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// ---------------------------------------------------------------- statistics -> affine ---
+// stats = [sum | sumsq] (train) ; writes mean, invstd, scale = gamma*invstd, shift = beta - mean*scale
+// and the running-stat update of nn.BatchNorm2d (momentum 0.1, unbiased running variance).
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                   int C, double count, float eps, float momentum, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    const double m = (double)stats[c] / count;
+    double v = (double)stats[C + c] / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean) {
+      const double unb = count > 1.0 ? v * count / (count - 1.0) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+      if (c == 0 && num_batches) *num_batches += 1;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] - mean * sc;
+}
+
+// ---------------------------------------------------------------- apply (+relu, +residual) ---
+// act = relu(raw_a*scale_a + shift_a [+ raw_b*scale_b + shift_b]); pad rows -> 0.
+template <int C>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a,
+                                                       const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
+                                                       __nv_bfloat16* __restrict__ act, long long rows, long long rows_pad,
+                                                       int P) {
+  constexpr int CH = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_pad * CH) return;
+  const long long r = idx / CH;
+  const int ch = (int)(idx - r * CH);
+  float o[8] = {};
+  if (row_is_valid(r, rows, P)) {
+    float a[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], ss_a[ch * 8 + i], ss_a[C + ch * 8 + i]);
+    if (raw_b != nullptr) {
+      float b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += fmaf(b[i], ss_b[ch * 8 + i], ss_b[C + ch * 8 + i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+  }
+  reinterpret_cast<uint4*>(act)[idx] = pack8(o);
+}
+
+// pooled[f,c] = mean over the P*P valid rows of frame f of act[r,c]   (AdaptiveAvgPool2d(1), :240,254)
+template <int C>
+__global__ void __launch_bounds__(C) pool_rows_kernel(const __nv_bfloat16* __restrict__ act, float* __restrict__ pooled, int P) {
+  const long long f = blockIdx.x;
+  const int c = threadIdx.x;
+  const int pitch = P + 1;
+  const __nv_bfloat16* base = act + (size_t)f * pitch * pitch * C;
+  float s = 0.f;
+  for (int y = 0; y < P; ++y)
+    for (int x = 0; x < P; ++x) s += __bfloat162float(base[(size_t)(y * pitch + x) * C + c]);
+  pooled[f * C + c] = s / (float)(P * P);
+}
+
+// ---------------------------------------------------------------- backward ----------------
+// upstream gradient of the (post-ReLU) activation:
+//   g = (up_a [+ up_b]  |  dpooled[f]/P^2) * 1[act > 0]
+// sums[0][c] = sum g, sums[1][c] = sum g*xhat_a, sums[2][c] = sum g*xhat_b
+template <int C>
+__device__ __forceinline__ bool load_g(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled,
+                                       const __nv_bfloat16* act, long long r, int ch, long long rows, int P, float (&g)[8]) {
+  if (!row_is_valid(r, rows, P)) return false;
+  constexpr int CH = C / 8;
+  const long long idx = r * CH + ch;
+  float a[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(act) + idx), a);
+  if (dpooled != nullptr) {
+    const long long f = r / ((long long)(P + 1) * (P + 1));
+    const float inv = 1.0f / (float)(P * P);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = a[i] > 0.f ? dpooled[f * C + ch * 8 + i] * inv : 0.f;
+  } else {
+    float u[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(up_a) + idx), u);
+    if (up_b != nullptr) {
+      float w[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(up_b) + idx), w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] += w[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = a[i] > 0.f ? u[i] : 0.f;
+  }
+  return true;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b,
+                                                            const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ act,
+                                                            const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mi_a,
+                                                            const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mi_b,
+                                                            float* __restrict__ sums, long long rows, int P, int rows_per_block) {
+  constexpr int CH = C / 8;
+  constexpr int RL = 256 / CH;  // row lanes
+  const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s0[8] = {}, s1[8] = {}, s2[8] = {};
+  for (long long r = r0 + rl; r < r1; r += RL) {
+    float g[8];
+    if (!load_g<C>(up_a, up_b, dpooled, act, r, ch, rows, P, g)) continue;
+    float a[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + r * CH + ch), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s0[i] += g[i];
+      s1[i] = fmaf(g[i], (a[i] - mi_a[ch * 8 + i]) * mi_a[C + ch * 8 + i], s1[i]);
+    }
+    if (raw_b != nullptr) {
+      float b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + r * CH + ch), b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s2[i] = fmaf(g[i], (b[i] - mi_b[ch * 8 + i]) * mi_b[C + ch * 8 + i], s2[i]);
+    }
+  }
+  __shared__ float red[3][RL][C + 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[0][rl][ch * 8 + i] = s0[i];
+    red[1][rl][ch * 8 + i] = s1[i];
+    red[2][rl][ch * 8 + i] = s2[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    const int k = i / C, c = i % C;
+    if (k == 2 && raw_b == nullptr) continue;
+    float t = 0.f;
+    for (int j = 0; j < RL; ++j) t += red[k][j][c];
+    atomicAdd(sums + k * C + c, t);
+  }
+}
+
+// draw = gamma*invstd * (g - sum_g/cnt - xhat * sum_gx/cnt); also emits dgamma = sum_gx, dbeta = sum_g
+template <int C>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b,
+                                                           const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ act,
+                                                           const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mi_a,
+                                                           const float* __restrict__ gamma_a, __nv_bfloat16* __restrict__ draw_a,
+                                                           const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mi_b,
+                                                           const float* __restrict__ gamma_b, __nv_bfloat16* __restrict__ draw_b,
+                                                           const float* __restrict__ sums, long long rows, long long rows_pad, int P,
+                                                           float inv_count) {
+  constexpr int CH = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_pad * CH) return;
+  const long long r = idx / CH;
+  const int ch = (int)(idx - r * CH);
+  float oa[8] = {}, ob[8] = {};
+  float g[8];
+  if (load_g<C>(up_a, up_b, dpooled, act, r, ch, rows, P, g)) {
+    float a[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = ch * 8 + i;
+      const float xh = (a[i] - mi_a[c]) * mi_a[C + c];
+      oa[i] = gamma_a[c] * mi_a[C + c] * (g[i] - sums[c] * inv_count - xh * sums[C + c] * inv_count);
+    }
+    if (raw_b != nullptr) {
+      float b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = ch * 8 + i;
+        const float xh = (b[i] - mi_b[c]) * mi_b[C + c];
+        ob[i] = gamma_b[c] * mi_b[C + c] * (g[i] - sums[c] * inv_count - xh * sums[2 * C + c] * inv_count);
+      }
+    }
+  }
+  reinterpret_cast<uint4*>(draw_a)[idx] = pack8(oa);
+  if (raw_b != nullptr) reinterpret_cast<uint4*>(draw_b)[idx] = pack8(ob);
+}
+
+// dgamma_a = sums[1], dbeta_a = sums[0]; dgamma_b = sums[2], dbeta_b = sums[0]
+__global__ void bn_param_grads_kernel(const float* __restrict__ sums, float* __restrict__ dgamma_a, float* __restrict__ dbeta_a,
+                                      float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dgamma_a[c] = sums[C + c];
+  dbeta_a[c] = sums[c];
+  if (dgamma_b) {
+    dgamma_b[c] = sums[2 * C + c];
+    dbeta_b[c] = sums[c];
+  }
+}
+
+// ---------------------------------------------------------------- first convolution -------
+// raw0[r, 0:32] = sum_tap x[f, y+dy, x+dx] * W0[c, tap]   (Conv2d(1,32,3,padding=1,bias=False), :233)
+__global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ frames, const float* __restrict__ W0,
+                                                        __nv_bfloat16* __restrict__ raw0, float* __restrict__ stats, long long rows,
+                                                        long long rows_pad, int P) {
+  __shared__ float w[32 * 9];
+  __shared__ float red[2][64][33];
+  for (int i = threadIdx.x; i < 288; i += 256) w[i] = W0[i];
+  __syncthreads();
+  const int pitch = P + 1, rpf = pitch * pitch;
+  const int ch = threadIdx.x & 3;  // 4 chunks of 8 channels
+  float s0[8] = {}, s1[8] = {};
+  for (long long r = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); r < rows_pad; r += (long long)gridDim.x * 64) {
+    float o[8] = {};
+    if (r < rows) {
+      const long long f = r / rpf;
+      const int q = (int)(r - f * rpf), y = q / pitch, x = q - y * pitch;
+      if (y < P && x < P) {
+        const float* img = frames + f * P * P;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            const float v = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + yy * P + xx) : 0.f;
+            const int t = (dy + 1) * 3 + dx + 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(v, w[(ch * 8 + i) * 9 + t], o[i]);
+          }
+      }
+    }
+    const uint4 pk = pack8(o);
+    reinterpret_cast<uint4*>(raw0)[r * 4 + ch] = pk;
+    float rb[8];
+    unpack8(pk, rb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0[i] += rb[i]; s1[i] = fmaf(rb[i], rb[i], s1[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x >> 2][ch * 8 + i] = s0[i]; red[1][threadIdx.x >> 2][ch * 8 + i] = s1[i]; }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x >> 5, c = threadIdx.x & 31;
+    float t = 0.f;
+    for (int j = 0; j < 64; ++j) t += red[k][j][c];
+    atomicAdd(stats + k * 32 + c, t);
+  }
+}
+
+// dW0[c, tap] = sum_r draw0[r, c] * x[f, y+dy, x+dx]
+__global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ frames, const __nv_bfloat16* __restrict__ draw0,
+                                                          float* __restrict__ dW0, long long rows, int P) {
+  __shared__ float red[288];
+  for (int i = threadIdx.x; i < 288; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const int pitch = P + 1, rpf = pitch * pitch;
+  const int ch = threadIdx.x & 3;
+  float acc[8][9] = {};
+  for (long long r = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); r < rows; r += (long long)gridDim.x * 64) {
+    const long long f = r / rpf;
+    const int q = (int)(r - f * rpf), y = q / pitch, x = q - y * pitch;
+    if (y >= P || x >= P) continue;
+    float g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(draw0) + r * 4 + ch), g);
+    const float* img = frames + f * P * P;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        const float v = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + yy * P + xx) : 0.f;
+        const int t = (dy + 1) * 3 + dx + 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][t] = fmaf(g[i], v, acc[i][t]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(&red[(ch * 8 + i) * 9 + t], acc[i][t]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 288; i += 256) atomicAdd(dW0 + i, red[i]);
+}
+
+}  // namespace
+
+int bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                long long* num_batches, float* mean, float* invstd, float* scale, float* shift, int C, double count, float eps,
+                float momentum, int training, cudaStream_t st) {
+  bn_finalize_kernel<<<mivit_ceil_div(C, 128), 128, 0, st>>>(stats, gamma, beta, running_mean, running_var, num_batches, mean,
+                                                             invstd, scale, shift, C, count, eps, momentum, training);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+#define BN_DISPATCH_C(C_, CALL)                                    \
+  switch (C_) {                                                    \
+    case 32: { constexpr int CC = 32; CALL; break; }               \
+    case 64: { constexpr int CC = 64; CALL; break; }               \
+    case 128: { constexpr int CC = 128; CALL; break; }             \
+    default: mivit_set_error("BatchNorm width %d not supported", C_); return MIVIT_ERR_INVALID; \
+  }
+
+int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b,
+             __nv_bfloat16* act, long long rows, long long rows_pad, int P, int C, cudaStream_t st) {
+  const long long n = rows_pad * (C / 8);
+  BN_DISPATCH_C(C, (bn_apply_kernel<CC><<<mivit_ceil_div(n, 256), 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, rows, rows_pad, P)));
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P, int C, cudaStream_t st) {
+  if (n_frames <= 0) return MIVIT_OK;
+  BN_DISPATCH_C(C, (pool_rows_kernel<CC><<<(unsigned)n_frames, CC, 0, st>>>(act, pooled, P)));
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* act,
+                const __nv_bfloat16* raw_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a,
+                float* dbeta_a, const __nv_bfloat16* raw_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
+                float* dgamma_b, float* dbeta_b, float* sums /*[3][C] scratch*/, long long rows, long long rows_pad, int P, int C,
+                double count, cudaStream_t st) {
+  MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
+  const int rpb = 4096;
+  const int blocks = mivit_ceil_div(rows, rpb);
+  BN_DISPATCH_C(C, (bn_bwd_reduce_kernel<CC><<<blocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, raw_b, mi_b, sums, rows, P, rpb)));
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  const long long n = rows_pad * (C / 8);
+  BN_DISPATCH_C(C, (bn_bwd_apply_kernel<CC><<<mivit_ceil_div(n, 256), 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, gamma_a, draw_a,
+                                                                                   raw_b, mi_b, gamma_b, draw_b, sums, rows, rows_pad, P,
+                                                                                   (float)(1.0 / count))));
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  bn_param_grads_kernel<<<mivit_ceil_div(C, 128), 128, 0, st>>>(sums, dgamma_a, dbeta_a, raw_b ? dgamma_b : nullptr, dbeta_b, C);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad, int P,
+                  cudaStream_t st) {
+  int blocks = mivit_ceil_div(rows_pad, 64);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv0_fwd_kernel<<<blocks, 256, 0, st>>>(frames, W0, raw0, stats, rows, rows_pad, P);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st) {
+  MIVIT_CUDA_CHECK(cudaMemsetAsync(dW0, 0, 288 * sizeof(float), st));
+  int blocks = mivit_ceil_div(rows, 64);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  conv0_wgrad_kernel<<<blocks, 256, 0, st>>>(frames, draw0, dW0, rows, P);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}

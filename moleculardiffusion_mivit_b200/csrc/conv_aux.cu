@@ -59,3 +59,12 @@ extern "C" int mivit_conv_rows(const void* X_row0, const void* Wp, void* Y_row0,
   return conv_rows_forward((const __nv_bfloat16*)X_row0, (const __nv_bfloat16*)Wp, (__nv_bfloat16*)Y_row0, stats, rows, P,
                            cin, cout, ksize * ksize, sh, impl, (cudaStream_t)stream);
 }
+
+extern "C" int mivit_conv_rows_wgrad(const void* X_row0, const void* dY_row0, float* dW, int64_t rows, int32_t P, int32_t cin,
+                                     int32_t cout, int32_t ksize, int32_t impl, void* stream) {
+  MIVIT_CHECK_ARG(X_row0 && dY_row0 && dW, "NULL pointer");
+  MIVIT_CHECK_ARG(ksize == 1 || ksize == 3, "kernel size must be 1 or 3");
+  const ConvShifts sh = make_shifts(P, ksize * ksize, false);
+  return conv_rows_wgrad((const __nv_bfloat16*)X_row0, (const __nv_bfloat16*)dY_row0, dW, rows, P, cin, cout, ksize * ksize, sh,
+                         impl, (cudaStream_t)stream);
+}

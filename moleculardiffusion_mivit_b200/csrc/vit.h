@@ -29,3 +29,49 @@ int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bflo
 
 // W fp32 [cout][cin][k][k] -> bf16 core-matrix packs (see conv_aux.cu)
 int pack_conv_weights(const float* W, __nv_bfloat16* out, int cout, int cin, int taps, int dgrad, cudaStream_t st);
+
+// dW[cout][cin][k][k] (fp32, pre-zeroed) += sum_r dY[r,cout]^T X[r+shift,cin]
+int conv_rows_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int cin, int cout,
+                    int taps, const ConvShifts& sh, int impl, cudaStream_t st);
+
+// gemm_simt.cu
+int gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+             long long scm, int M, int N, int K, const float* bias, int relu, int accumulate, int split_k, cudaStream_t st);
+int colsum_f32(const float* X, long long ld, int M, int N, float* out, cudaStream_t st);
+
+// transformer.cu
+int layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* z_out, float* y,
+                  float* mean, float* rstd, int rows, int E, float eps, int group, int out_group, int out_off, cudaStream_t st);
+int layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma, float* dz,
+                  float* dgamma, float* dbeta, int rows, int E, int group, int out_group, int out_off, cudaStream_t st);
+int attention_fwd(const float* q, const float* k, const float* v, float* ctx, float* probs, int B, int S, int E, int H,
+                  cudaStream_t st);
+int attention_bwd(const float* q, const float* k, const float* v, const float* probs, const float* dctx, float* dq,
+                  float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st);
+int act_fwd(const float* pre, float* post, long long n, int mode, cudaStream_t st);
+int act_bwd(const float* dpost, const float* pre, float* dpre, long long n, int mode, cudaStream_t st);
+int tokens_finish(float* tok, const float* reg, const float* proj, const float* pos, int B, int S, int E, cudaStream_t st);
+int tokens_finish_bwd(const float* dtok, float* dreg, float* dproj, float* dpos, int B, int S, int E, cudaStream_t st);
+int pool_tokens(const float* x, float* out, int B, int S, int E, int ld, int use_reg, cudaStream_t st);
+int pool_tokens_bwd(const float* dout, float* dx, int B, int S, int E, int ld, int use_reg, cudaStream_t st);
+
+// bn.cu
+int bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                long long* num_batches, float* mean, float* invstd, float* scale, float* shift, int C, double count, float eps,
+                float momentum, int training, cudaStream_t st);
+int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b,
+             __nv_bfloat16* act, long long rows, long long rows_pad, int P, int C, cudaStream_t st);
+int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P, int C, cudaStream_t st);
+int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* act,
+                const __nv_bfloat16* raw_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a,
+                float* dbeta_a, const __nv_bfloat16* raw_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
+                float* dgamma_b, float* dbeta_b, float* sums, long long rows, long long rows_pad, int P, int C, double count,
+                cudaStream_t st);
+int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad,
+                  int P, cudaStream_t st);
+int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st);
+
+// optim.cu
+int mse_loss(const float* pred, const float* target, int n, float* loss, float* dpred, cudaStream_t st);
+int adamw_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+               long long step, float grad_scale, cudaStream_t st);

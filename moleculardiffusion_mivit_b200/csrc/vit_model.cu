@@ -1,0 +1,471 @@
+// Orchestration of the motion-informed ViT regressor (reference helpers/models.py:278-361
+// GeneralTransformer) forward / backward / training step on the kernels of this library.
+// Parameters live in ONE flat fp32 buffer in the canonical order produced by ParamLayout (the
+// Python module mirrors the order by state_dict key); gradients and AdamW moments use the same
+// offsets, so the optimiser and the data-parallel all-reduce are single passes over 2 MB.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "vit.h"
+#include "../../include/mivit.h"
+
+#define CK(expr)              \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc) return _rc;      \
+  } while (0)
+
+namespace {
+
+constexpr int kGuard = 128;
+constexpr int kMaxLayers = 32;
+
+struct ParamLayout {
+  long off = 0;
+  int count = 0;
+  long sizes[24 + 16 * kMaxLayers + 16];
+  long add(long n) {
+    const long o = off;
+    sizes[count++] = n;
+    off += n;
+    return o;
+  }
+  // embedding
+  long conv0_w = -1, bn0_g = -1, bn0_b = -1;
+  struct RB { long c1_w, bn1_g, bn1_b, c2_w, bn2_g, bn2_b, sk_w, bns_g, bns_b; } rb[2];
+  long fc_w = -1, fc_b = -1, proj_w = -1, proj_b = -1;
+  long norm_g, norm_b, reg = -1, pos = -1;
+  struct Lyr { long q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, n1_g, n1_b, f1_w, f1_b, f2_w, f2_b, n2_g, n2_b; } lyr[kMaxLayers];
+  long tn_g, tn_b, fp0_w = -1, fp0_b = -1, fp2_w = -1, fp2_b = -1, h0_w, h0_b, h3_w, h3_b;
+  int head_in = 0;
+};
+
+int build_layout(const mivit_vit_config* c, ParamLayout& L) {
+  MIVIT_CHECK_ARG(c != nullptr, "config is NULL");
+  MIVIT_CHECK_ARG(c->embedding >= 0 && c->embedding <= 2, "embedding must be 0 (linear), 1 (cnn) or 2 (deepresnet)");
+  MIVIT_CHECK_ARG(c->L >= 1 && c->L <= kMaxLayers, "num_layers out of range");
+  MIVIT_CHECK_ARG(c->E >= 8 && c->E <= 256 && c->E % c->H == 0, "embed_dim must be in [8,256] and divisible by num_heads");
+  MIVIT_CHECK_ARG(c->P >= 1 && c->P <= 100 && c->F >= 1, "bad patch size / frame count");
+  MIVIT_CHECK_ARG(c->F + (c->use_reg ? 1 : 0) <= 128, "more than MAX_TOKENS = 128 tokens");
+  const int E = c->E, HD = c->HD, PP = c->P * c->P;
+  if (c->embedding == 2) {
+    L.conv0_w = L.add(32 * 9); L.bn0_g = L.add(32); L.bn0_b = L.add(32);
+    const int ci[2] = {32, 64}, co[2] = {64, 128};
+    for (int b = 0; b < 2; ++b) {
+      L.rb[b].c1_w = L.add((long)co[b] * ci[b] * 9); L.rb[b].bn1_g = L.add(co[b]); L.rb[b].bn1_b = L.add(co[b]);
+      L.rb[b].c2_w = L.add((long)co[b] * co[b] * 9); L.rb[b].bn2_g = L.add(co[b]); L.rb[b].bn2_b = L.add(co[b]);
+      L.rb[b].sk_w = L.add((long)co[b] * ci[b]); L.rb[b].bns_g = L.add(co[b]); L.rb[b].bns_b = L.add(co[b]);
+    }
+    L.fc_w = L.add((long)E * 128); L.fc_b = L.add(E);
+  } else {
+    L.proj_w = L.add((long)E * PP); L.proj_b = L.add(E);
+  }
+  L.norm_g = L.add(E); L.norm_b = L.add(E);
+  if (c->use_reg) L.reg = L.add(E);
+  if (c->use_pos) L.pos = L.add(128L * E);
+  for (int l = 0; l < c->L; ++l) {
+    auto& y = L.lyr[l];
+    y.q_w = L.add((long)E * E); y.q_b = L.add(E); y.k_w = L.add((long)E * E); y.k_b = L.add(E);
+    y.v_w = L.add((long)E * E); y.v_b = L.add(E); y.o_w = L.add((long)E * E); y.o_b = L.add(E);
+    y.n1_g = L.add(E); y.n1_b = L.add(E);
+    y.f1_w = L.add((long)HD * E); y.f1_b = L.add(HD); y.f2_w = L.add((long)E * HD); y.f2_b = L.add(E);
+    y.n2_g = L.add(E); y.n2_b = L.add(E);
+  }
+  L.tn_g = L.add(E); L.tn_b = L.add(E);
+  if (c->use_feat) {
+    MIVIT_CHECK_ARG(c->feat_dim >= 1, "global_feature_dim must be given with use_global_features");
+    L.fp0_w = L.add((long)E * c->feat_dim); L.fp0_b = L.add(E); L.fp2_w = L.add((long)E * E); L.fp2_b = L.add(E);
+  }
+  L.head_in = (c->use_feat && c->fusion == 1) ? 2 * E : E;
+  L.h0_w = L.add((long)c->head_hidden * L.head_in); L.h0_b = L.add(c->head_hidden);
+  L.h3_w = L.add(c->head_hidden); L.h3_b = L.add(1);
+  return MIVIT_OK;
+}
+
+// ------------------------------------------------------------------- workspace ------------
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct RowsT {  // one pitched-rows bf16 tensor with guards
+  __nv_bfloat16* buf = nullptr;  // allocation start
+  __nv_bfloat16* row0 = nullptr;
+  int C = 0;
+};
+
+struct BnScratch {
+  float *stats, *mi, *ss;  // [2C] each: (sum,sumsq) | (mean,invstd) | (scale,shift)
+  int C;
+};
+
+struct LayerWS {
+  float *q, *k, *v, *ctx, *probs, *ao, *z1, *m1, *r1, *x1, *hpre, *hact, *ff, *z2, *m2, *r2, *x2;
+};
+
+struct Workspace {
+  // deepresnet embedding
+  RowsT raw0, act0, raw1, act1, raw2, raws1, act2, raw3, act3, raw4, raws2, act4;
+  RowsT draw4, draws2, dact3, draw3, dact2m, dact2s, draw2, draws1, dact1, draw1, dact0m, dact0s, draw0;
+  __nv_bfloat16 *wp_c1[2], *wp_c2[2], *wp_sk[2], *wd_c1[2], *wd_c2[2], *wd_sk[2];
+  BnScratch bn[7];
+  float* bn_sums;
+  float *pooled, *dpooled;
+  // tokens
+  float *emb, *m0, *r0, *tok;
+  float *fp_pre, *fp_h, *fp_out;
+  LayerWS lyr[kMaxLayers];
+  float *mf, *rf, *xf, *headin, *hh, *pred_dummy;
+  // backward temporaries
+  float *dxa, *dxb, *dq, *dk, *dv, *dctx, *dh, *dh2, *dheadin, *dhh, *dfp, *dfp_h, *demb;
+  long long rows = 0, rows_pad = 0;
+  size_t bytes = 0;
+};
+
+void take_rows(Bump& b, RowsT& t, int C, long long rows_pad) {
+  t.C = C;
+  t.buf = b.take<__nv_bfloat16>((size_t)(rows_pad + 2 * kGuard) * C);
+  t.row0 = t.buf ? t.buf + (size_t)kGuard * C : nullptr;
+}
+
+void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
+  Bump b{reinterpret_cast<uint8_t*>(base)};
+  const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H;
+  const long long NF = (long long)B * F, T = (long long)B * S;
+  if (c->embedding == 2) {
+    w.rows = NF * (c->P + 1) * (c->P + 1);
+    w.rows_pad = (w.rows + 127) / 128 * 128;
+    const long long rp = w.rows_pad;
+    take_rows(b, w.raw0, 32, rp); take_rows(b, w.act0, 32, rp);
+    take_rows(b, w.raw1, 64, rp); take_rows(b, w.act1, 64, rp); take_rows(b, w.raw2, 64, rp);
+    take_rows(b, w.raws1, 64, rp); take_rows(b, w.act2, 64, rp);
+    take_rows(b, w.raw3, 128, rp); take_rows(b, w.act3, 128, rp); take_rows(b, w.raw4, 128, rp);
+    take_rows(b, w.raws2, 128, rp); take_rows(b, w.act4, 128, rp);
+    take_rows(b, w.draw4, 128, rp); take_rows(b, w.draws2, 128, rp); take_rows(b, w.dact3, 128, rp);
+    take_rows(b, w.draw3, 128, rp); take_rows(b, w.dact2m, 64, rp); take_rows(b, w.dact2s, 64, rp);
+    take_rows(b, w.draw2, 64, rp); take_rows(b, w.draws1, 64, rp); take_rows(b, w.dact1, 64, rp);
+    take_rows(b, w.draw1, 64, rp); take_rows(b, w.dact0m, 32, rp); take_rows(b, w.dact0s, 32, rp);
+    take_rows(b, w.draw0, 32, rp);
+    const int ci[2] = {32, 64}, co[2] = {64, 128};
+    for (int i = 0; i < 2; ++i) {
+      w.wp_c1[i] = b.take<__nv_bfloat16>((size_t)9 * ci[i] * co[i]); w.wd_c1[i] = b.take<__nv_bfloat16>((size_t)9 * ci[i] * co[i]);
+      w.wp_c2[i] = b.take<__nv_bfloat16>((size_t)9 * co[i] * co[i]); w.wd_c2[i] = b.take<__nv_bfloat16>((size_t)9 * co[i] * co[i]);
+      w.wp_sk[i] = b.take<__nv_bfloat16>((size_t)ci[i] * co[i]); w.wd_sk[i] = b.take<__nv_bfloat16>((size_t)ci[i] * co[i]);
+    }
+    const int bc[7] = {32, 64, 64, 64, 128, 128, 128};
+    for (int i = 0; i < 7; ++i) {
+      w.bn[i].C = bc[i];
+      w.bn[i].stats = b.take<float>(2 * bc[i]); w.bn[i].mi = b.take<float>(2 * bc[i]); w.bn[i].ss = b.take<float>(2 * bc[i]);
+    }
+    w.bn_sums = b.take<float>(3 * 128);
+    w.pooled = b.take<float>(NF * 128); w.dpooled = b.take<float>(NF * 128);
+  }
+  w.emb = b.take<float>(NF * E); w.m0 = b.take<float>(NF); w.r0 = b.take<float>(NF);
+  w.tok = b.take<float>(T * E);
+  if (c->use_feat) { w.fp_pre = b.take<float>((size_t)B * E); w.fp_h = b.take<float>((size_t)B * E); w.fp_out = b.take<float>((size_t)B * E); }
+  for (int l = 0; l < c->L; ++l) {
+    LayerWS& y = w.lyr[l];
+    y.q = b.take<float>(T * E); y.k = b.take<float>(T * E); y.v = b.take<float>(T * E); y.ctx = b.take<float>(T * E);
+    y.probs = b.take<float>((size_t)B * H * S * S); y.ao = b.take<float>(T * E);
+    y.z1 = b.take<float>(T * E); y.m1 = b.take<float>(T); y.r1 = b.take<float>(T); y.x1 = b.take<float>(T * E);
+    y.hpre = b.take<float>(T * HD); y.hact = b.take<float>(T * HD); y.ff = b.take<float>(T * E);
+    y.z2 = b.take<float>(T * E); y.m2 = b.take<float>(T); y.r2 = b.take<float>(T); y.x2 = b.take<float>(T * E);
+  }
+  const int hin = (c->use_feat && c->fusion == 1) ? 2 * E : E;
+  w.mf = b.take<float>(T); w.rf = b.take<float>(T); w.xf = b.take<float>(T * E);
+  w.headin = b.take<float>((size_t)B * hin); w.hh = b.take<float>((size_t)B * c->head_hidden);
+  w.dxa = b.take<float>(T * E); w.dxb = b.take<float>(T * E); w.dq = b.take<float>(T * E); w.dk = b.take<float>(T * E);
+  w.dv = b.take<float>(T * E); w.dctx = b.take<float>(T * E); w.dh = b.take<float>(T * HD); w.dh2 = b.take<float>(T * HD);
+  w.dheadin = b.take<float>((size_t)B * hin); w.dhh = b.take<float>((size_t)B * c->head_hidden);
+  w.dfp = b.take<float>((size_t)B * E); w.dfp_h = b.take<float>((size_t)B * E); w.demb = b.take<float>(NF * E);
+  w.bytes = (b.off + 255) & ~(size_t)255;
+}
+
+// Y[M,N] = X[M,K] W[N,K]^T + b
+int linear_fwd(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, int relu, cudaStream_t st) {
+  return gemm_f32(X, K, 1, W, 1, K, Y, N, M, N, K, bias, relu, 0, 1, st);
+}
+// dW[N,K] += dY[M,N]^T X[M,K];  db[N] += colsum(dY);  dX[M,K] (=|+=) dY W
+int linear_bwd(const float* X, const float* W, const float* dY, float* dW, float* db, float* dX, int M, int N, int K,
+               int accumulate_dx, cudaStream_t st) {
+  int split = M / 512;
+  if (split < 1) split = 1;
+  if (split > 64) split = 64;
+  if (split == 1) {
+    CK(gemm_f32(dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, 0, 1, 1, st));
+  } else {
+    CK(gemm_f32(dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, 0, 0, split, st));
+  }
+  if (db) CK(colsum_f32(dY, N, M, N, db, st));
+  if (dX) CK(gemm_f32(dY, N, 1, W, K, 1, dX, K, M, K, N, nullptr, 0, accumulate_dx, 1, st));
+  return MIVIT_OK;
+}
+
+int zero_guards(RowsT& t, long long rows_pad, cudaStream_t st) {
+  MIVIT_CUDA_CHECK(cudaMemsetAsync(t.buf, 0, (size_t)kGuard * t.C * 2, st));
+  MIVIT_CUDA_CHECK(cudaMemsetAsync(t.row0 + (size_t)rows_pad * t.C, 0, (size_t)kGuard * t.C * 2, st));
+  return MIVIT_OK;
+}
+
+struct BnParams { const float *g, *b; float *rm, *rv; long long* nbt; };
+
+int run_bn_finalize(const mivit_vit_config* c, Workspace& w, int i, const float* g, const float* bta, float* bn_running,
+                    long long* nbt, double count, int training, cudaStream_t st) {
+  static const int rm_off[7] = {0, 64, 192, 320, 448, 704, 960};  // [mean C | var C] per layer: 32,64,64,64,128,128,128
+  BnScratch& s = w.bn[i];
+  float* rm = bn_running ? bn_running + rm_off[i] : nullptr;
+  float* rv = rm ? rm + s.C : nullptr;
+  return bn_finalize(s.stats, g, bta, rm, rv, nbt ? nbt + i : nullptr, s.mi, s.mi + s.C, s.ss, s.ss + s.C, s.C, count, c->bn_eps,
+                     c->bn_momentum, training, st);
+}
+
+}  // namespace
+
+extern "C" int mivit_vit_param_sizes(const mivit_vit_config* cfg, int64_t* sizes, int32_t max_count) {
+  ParamLayout L;
+  CK(build_layout(cfg, L));
+  if (sizes != nullptr) {
+    MIVIT_CHECK_ARG(max_count >= L.count, "sizes array too small (%d < %d)", max_count, L.count);
+    for (int i = 0; i < L.count; ++i) sizes[i] = L.sizes[i];
+  }
+  return MIVIT_OK;
+}
+
+extern "C" int32_t mivit_vit_param_count(const mivit_vit_config* cfg) {
+  ParamLayout L;
+  if (build_layout(cfg, L)) return -1;
+  return L.count;
+}
+
+extern "C" int64_t mivit_vit_workspace_bytes(const mivit_vit_config* cfg, int32_t B) {
+  ParamLayout L;
+  if (build_layout(cfg, L) || B < 1) return -1;
+  Workspace w;
+  carve(cfg, B, nullptr, w);
+  return (int64_t)w.bytes;
+}
+
+extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
+                                 const float* params, float* bn_running, int64_t* bn_num_batches, void* workspace,
+                                 float* pred, int32_t training, void* stream) {
+  ParamLayout L;
+  CK(build_layout(c, L));
+  MIVIT_CHECK_ARG(B >= 1 && x && params && workspace && pred, "bad arguments");
+  MIVIT_CHECK_ARG(!c->use_feat || features, "Global features required for %s fusion", c->fusion ? "late" : "early");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve(c, B, workspace, w);
+  const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H, P = c->P;
+  const int NF = B * F, T = B * S;
+  const float* p = params;
+  if (c->embedding == 2) {
+    MIVIT_CHECK_ARG(training || bn_running, "eval-mode BatchNorm needs the running statistics");
+    const long long rows = w.rows, rp = w.rows_pad;
+    const double cnt = (double)NF * P * P;
+    const int impl = c->conv_impl;
+    RowsT* guarded[] = {&w.act0, &w.act1, &w.act2, &w.act3};
+    for (RowsT* t : guarded) CK(zero_guards(*t, rp, st));
+    for (int i = 0; i < 7; ++i) MIVIT_CUDA_CHECK(cudaMemsetAsync(w.bn[i].stats, 0, 2 * w.bn[i].C * sizeof(float), st));
+    const ConvShifts s3 = make_shifts(P, 9, false), s1 = make_shifts(P, 1, false);
+    long long* nbt = (long long*)bn_num_batches;
+    // stem
+    CK(conv0_forward(x, p + L.conv0_w, w.raw0.row0, w.bn[0].stats, rows, rp, P, st));
+    CK(run_bn_finalize(c, w, 0, p + L.bn0_g, p + L.bn0_b, bn_running, nbt, cnt, training, st));
+    CK(bn_apply(w.raw0.row0, w.bn[0].ss, nullptr, nullptr, w.act0.row0, rows, rp, P, 32, st));
+    const int ci[2] = {32, 64}, co[2] = {64, 128};
+    RowsT* in[2] = {&w.act0, &w.act2};
+    RowsT* r1[2] = {&w.raw1, &w.raw3};
+    RowsT* a1[2] = {&w.act1, &w.act3};
+    RowsT* r2[2] = {&w.raw2, &w.raw4};
+    RowsT* rs[2] = {&w.raws1, &w.raws2};
+    RowsT* out[2] = {&w.act2, &w.act4};
+    for (int b = 0; b < 2; ++b) {
+      const auto& R = L.rb[b];
+      const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, is = 3 + 3 * b;
+      CK(pack_conv_weights(p + R.c1_w, w.wp_c1[b], co[b], ci[b], 9, 0, st));
+      CK(pack_conv_weights(p + R.c2_w, w.wp_c2[b], co[b], co[b], 9, 0, st));
+      CK(pack_conv_weights(p + R.sk_w, w.wp_sk[b], co[b], ci[b], 1, 0, st));
+      CK(conv_rows_forward(in[b]->row0, w.wp_c1[b], r1[b]->row0, w.bn[i1].stats, rows, P, ci[b], co[b], 9, s3, impl, st));
+      CK(run_bn_finalize(c, w, i1, p + R.bn1_g, p + R.bn1_b, bn_running, nbt, cnt, training, st));
+      CK(bn_apply(r1[b]->row0, w.bn[i1].ss, nullptr, nullptr, a1[b]->row0, rows, rp, P, co[b], st));
+      CK(conv_rows_forward(a1[b]->row0, w.wp_c2[b], r2[b]->row0, w.bn[i2].stats, rows, P, co[b], co[b], 9, s3, impl, st));
+      CK(conv_rows_forward(in[b]->row0, w.wp_sk[b], rs[b]->row0, w.bn[is].stats, rows, P, ci[b], co[b], 1, s1, impl, st));
+      CK(run_bn_finalize(c, w, i2, p + R.bn2_g, p + R.bn2_b, bn_running, nbt, cnt, training, st));
+      CK(run_bn_finalize(c, w, is, p + R.bns_g, p + R.bns_b, bn_running, nbt, cnt, training, st));
+      CK(bn_apply(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, out[b]->row0, rows, rp, P, co[b], st));
+    }
+    CK(pool_rows(w.act4.row0, w.pooled, NF, P, 128, st));
+    CK(linear_fwd(w.pooled, p + L.fc_w, p + L.fc_b, w.emb, NF, E, 128, 0, st));
+  } else {
+    CK(linear_fwd(x, p + L.proj_w, p + L.proj_b, w.emb, NF, E, P * P, 0, st));
+  }
+  // x = self.norm(x), written straight into the token slots behind the regression token
+  CK(layernorm_fwd(w.emb, nullptr, p + L.norm_g, p + L.norm_b, nullptr, w.tok, w.m0, w.r0, NF, E, c->ln_eps, F, S,
+                   c->use_reg ? 1 : 0, st));
+  if (c->use_feat) {
+    CK(linear_fwd(features, p + L.fp0_w, p + L.fp0_b, w.fp_h, B, E, c->feat_dim, 1, st));
+    CK(linear_fwd(w.fp_h, p + L.fp2_w, p + L.fp2_b, w.fp_out, B, E, E, 0, st));
+  }
+  CK(tokens_finish(w.tok, c->use_reg ? p + L.reg : nullptr, (c->use_feat && c->fusion == 0 && c->use_reg) ? w.fp_out : nullptr,
+                   c->use_pos ? p + L.pos : nullptr, B, S, E, st));
+  const float* xin = w.tok;
+  for (int l = 0; l < c->L; ++l) {
+    const auto& Y = L.lyr[l];
+    LayerWS& y = w.lyr[l];
+    CK(linear_fwd(xin, p + Y.q_w, p + Y.q_b, y.q, T, E, E, 0, st));
+    CK(linear_fwd(xin, p + Y.k_w, p + Y.k_b, y.k, T, E, E, 0, st));
+    CK(linear_fwd(xin, p + Y.v_w, p + Y.v_b, y.v, T, E, E, 0, st));
+    CK(attention_fwd(y.q, y.k, y.v, y.ctx, y.probs, B, S, E, H, st));
+    CK(linear_fwd(y.ctx, p + Y.o_w, p + Y.o_b, y.ao, T, E, E, 0, st));
+    CK(layernorm_fwd(y.ao, xin, p + Y.n1_g, p + Y.n1_b, y.z1, y.x1, y.m1, y.r1, T, E, c->ln_eps, 0, 0, 0, st));
+    CK(linear_fwd(y.x1, p + Y.f1_w, p + Y.f1_b, y.hpre, T, HD, E, 0, st));
+    CK(act_fwd(y.hpre, y.hact, (long long)T * HD, c->activation, st));
+    CK(linear_fwd(y.hact, p + Y.f2_w, p + Y.f2_b, y.ff, T, E, HD, 0, st));
+    CK(layernorm_fwd(y.ff, y.x1, p + Y.n2_g, p + Y.n2_b, y.z2, y.x2, y.m2, y.r2, T, E, c->ln_eps, 0, 0, 0, st));
+    xin = y.x2;
+  }
+  CK(layernorm_fwd(xin, nullptr, p + L.tn_g, p + L.tn_b, nullptr, w.xf, w.mf, w.rf, T, E, c->ln_eps, 0, 0, 0, st));
+  CK(pool_tokens(w.xf, w.headin, B, S, E, L.head_in, c->use_reg, st));
+  if (c->use_feat && c->fusion == 1)
+    MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.headin + E, (size_t)L.head_in * 4, w.fp_out, (size_t)E * 4, (size_t)E * 4, B,
+                                       cudaMemcpyDeviceToDevice, st));
+  CK(linear_fwd(w.headin, p + L.h0_w, p + L.h0_b, w.hh, B, c->head_hidden, L.head_in, 1, st));
+  CK(linear_fwd(w.hh, p + L.h3_w, p + L.h3_b, pred, B, 1, c->head_hidden, 0, st));
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
+                                  const float* dpred, const float* params, float* grads, void* workspace, void* stream) {
+  ParamLayout L;
+  CK(build_layout(c, L));
+  MIVIT_CHECK_ARG(B >= 1 && x && dpred && params && grads && workspace, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve(c, B, workspace, w);
+  const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H, P = c->P;
+  const int NF = B * F, T = B * S, hin = L.head_in, hhid = c->head_hidden;
+  const float* p = params;
+  float* g = grads;
+  MIVIT_CUDA_CHECK(cudaMemsetAsync(g, 0, (size_t)L.off * sizeof(float), st));
+  // head
+  CK(linear_bwd(w.hh, p + L.h3_w, dpred, g + L.h3_w, g + L.h3_b, w.dhh, B, 1, hhid, 0, st));
+  CK(act_bwd(w.dhh, w.hh, w.dhh, (long long)B * hhid, 0, st));
+  CK(linear_bwd(w.headin, p + L.h0_w, w.dhh, g + L.h0_w, g + L.h0_b, w.dheadin, B, hhid, hin, 0, st));
+  const bool late = c->use_feat && c->fusion == 1, early = c->use_feat && c->fusion == 0 && c->use_reg;
+  if (late)
+    MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.dfp, (size_t)E * 4, w.dheadin + E, (size_t)hin * 4, (size_t)E * 4, B,
+                                       cudaMemcpyDeviceToDevice, st));
+  CK(pool_tokens_bwd(w.dheadin, w.dxa, B, S, E, hin, c->use_reg, st));
+  const float* xlast = w.lyr[c->L - 1].x2;
+  CK(layernorm_bwd(w.dxa, xlast, w.mf, w.rf, p + L.tn_g, w.dxb, g + L.tn_g, g + L.tn_b, T, E, 0, 0, 0, st));
+  float* dx = w.dxb;    // gradient w.r.t. the current layer output
+  float* tmp = w.dxa;
+  for (int l = c->L - 1; l >= 0; --l) {
+    const auto& Y = L.lyr[l];
+    LayerWS& y = w.lyr[l];
+    const float* xin = l == 0 ? w.tok : w.lyr[l - 1].x2;
+    // x2 = LN2(x1 + ff)
+    CK(layernorm_bwd(dx, y.z2, y.m2, y.r2, p + Y.n2_g, tmp, g + Y.n2_g, g + Y.n2_b, T, E, 0, 0, 0, st));  // tmp = dz2 = dff = dx1
+    CK(linear_bwd(y.hact, p + Y.f2_w, tmp, g + Y.f2_w, g + Y.f2_b, w.dh, T, E, HD, 0, st));
+    CK(act_bwd(w.dh, y.hpre, w.dh2, (long long)T * HD, c->activation, st));
+    CK(linear_bwd(y.x1, p + Y.f1_w, w.dh2, g + Y.f1_w, g + Y.f1_b, tmp, T, HD, E, 1, st));               // tmp += dhpre W1
+    // x1 = LN1(xin + ao)
+    CK(layernorm_bwd(tmp, y.z1, y.m1, y.r1, p + Y.n1_g, dx, g + Y.n1_g, g + Y.n1_b, T, E, 0, 0, 0, st));   // dx = dz1 = dao = dxin
+    CK(linear_bwd(y.ctx, p + Y.o_w, dx, g + Y.o_w, g + Y.o_b, w.dctx, T, E, E, 0, st));
+    CK(attention_bwd(y.q, y.k, y.v, y.probs, w.dctx, w.dq, w.dk, w.dv, B, S, E, H, st));
+    CK(linear_bwd(xin, p + Y.q_w, w.dq, g + Y.q_w, g + Y.q_b, dx, T, E, E, 1, st));
+    CK(linear_bwd(xin, p + Y.k_w, w.dk, g + Y.k_w, g + Y.k_b, dx, T, E, E, 1, st));
+    CK(linear_bwd(xin, p + Y.v_w, w.dv, g + Y.v_w, g + Y.v_b, dx, T, E, E, 1, st));
+  }
+  // tokens: regression token, positional embedding, early-fusion projection
+  CK(tokens_finish_bwd(dx, c->use_reg ? g + L.reg : nullptr, early ? w.dfp : nullptr, c->use_pos ? g + L.pos : nullptr, B, S, E, st));
+  if (c->use_feat && (late || early)) {
+    CK(linear_bwd(w.fp_h, p + L.fp2_w, w.dfp, g + L.fp2_w, g + L.fp2_b, w.dfp_h, B, E, E, 0, st));
+    CK(act_bwd(w.dfp_h, w.fp_h, w.dfp_h, (long long)B * E, 0, st));
+    CK(linear_bwd(features, p + L.fp0_w, w.dfp_h, g + L.fp0_w, g + L.fp0_b, nullptr, B, E, c->feat_dim, 0, st));
+  }
+  // embedding LayerNorm (dy is read from the token slots)
+  CK(layernorm_bwd(dx, w.emb, w.m0, w.r0, p + L.norm_g, w.demb, g + L.norm_g, g + L.norm_b, NF, E, F, S, c->use_reg ? 1 : 0, st));
+  if (c->embedding != 2) {
+    CK(linear_bwd(x, p + L.proj_w, w.demb, g + L.proj_w, g + L.proj_b, nullptr, NF, E, P * P, 0, st));
+    return MIVIT_OK;
+  }
+  CK(linear_bwd(w.pooled, p + L.fc_w, w.demb, g + L.fc_w, g + L.fc_b, w.dpooled, NF, E, 128, 0, st));
+  const long long rows = w.rows, rp = w.rows_pad;
+  const double cnt = (double)NF * P * P;
+  const int impl = c->conv_impl;
+  RowsT* guarded[] = {&w.draw4, &w.draws2, &w.draw3, &w.draw2, &w.draws1, &w.draw1};
+  for (RowsT* t : guarded) CK(zero_guards(*t, rp, st));
+  const ConvShifts s3 = make_shifts(P, 9, false), s3m = make_shifts(P, 9, true), s1 = make_shifts(P, 1, false);
+  const int ci[2] = {32, 64}, co[2] = {64, 128};
+  RowsT* in[2] = {&w.act0, &w.act2};
+  RowsT* r1[2] = {&w.raw1, &w.raw3};
+  RowsT* a1[2] = {&w.act1, &w.act3};
+  RowsT* r2[2] = {&w.raw2, &w.raw4};
+  RowsT* rs[2] = {&w.raws1, &w.raws2};
+  RowsT* out[2] = {&w.act2, &w.act4};
+  RowsT* d2[2] = {&w.draw2, &w.draw4};      // grad of raw (conv2 output)
+  RowsT* ds[2] = {&w.draws1, &w.draws2};    // grad of raw skip
+  RowsT* da1[2] = {&w.dact1, &w.dact3};     // grad of act1 (conv2 input)
+  RowsT* d1[2] = {&w.draw1, &w.draw3};      // grad of raw1
+  RowsT* dinm[2] = {&w.dact0m, &w.dact2m};  // grad of block input through conv1
+  RowsT* dins[2] = {&w.dact0s, &w.dact2s};  // grad of block input through the skip
+  for (int b = 1; b >= 0; --b) {
+    const auto& R = L.rb[b];
+    const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, is = 3 + 3 * b;
+    CK(pack_conv_weights(p + R.c1_w, w.wd_c1[b], co[b], ci[b], 9, 1, st));
+    CK(pack_conv_weights(p + R.c2_w, w.wd_c2[b], co[b], co[b], 9, 1, st));
+    CK(pack_conv_weights(p + R.sk_w, w.wd_sk[b], co[b], ci[b], 1, 1, st));
+    // out = relu(bn2(raw2) + bns(raws))
+    if (b == 1) {
+      CK(bn_backward(nullptr, nullptr, w.dpooled, out[b]->row0, r2[b]->row0, w.bn[i2].mi, p + R.bn2_g, d2[b]->row0, g + R.bn2_g,
+                     g + R.bn2_b, rs[b]->row0, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g, g + R.bns_b, w.bn_sums, rows, rp,
+                     P, co[b], cnt, st));
+    } else {
+      CK(bn_backward(w.dact2m.row0, w.dact2s.row0, nullptr, out[b]->row0, r2[b]->row0, w.bn[i2].mi, p + R.bn2_g, d2[b]->row0,
+                     g + R.bn2_g, g + R.bn2_b, rs[b]->row0, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g, g + R.bns_b,
+                     w.bn_sums, rows, rp, P, co[b], cnt, st));
+    }
+    CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
+    CK(conv_rows_forward(d2[b]->row0, w.wd_c2[b], da1[b]->row0, nullptr, rows, P, co[b], co[b], 9, s3m, impl, st));
+    CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
+    CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
+    // act1 = relu(bn1(raw1))
+    CK(bn_backward(da1[b]->row0, nullptr, nullptr, a1[b]->row0, r1[b]->row0, w.bn[i1].mi, p + R.bn1_g, d1[b]->row0, g + R.bn1_g,
+                   g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, st));
+    CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
+    CK(conv_rows_forward(d1[b]->row0, w.wd_c1[b], dinm[b]->row0, nullptr, rows, P, co[b], ci[b], 9, s3m, impl, st));
+  }
+  // act0 = relu(bn0(raw0)); upstream = conv1 path + skip path of block 1
+  CK(zero_guards(w.draw0, rp, st));
+  CK(bn_backward(w.dact0m.row0, w.dact0s.row0, nullptr, w.act0.row0, w.raw0.row0, w.bn[0].mi, p + L.bn0_g, w.draw0.row0, g + L.bn0_g,
+                 g + L.bn0_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, 32, cnt, st));
+  CK(conv0_wgrad(x, w.draw0.row0, g + L.conv0_w, rows, P, st));
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_vit_train_step(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
+                                    const float* target, float* params, float* grads, float* adam_m, float* adam_v,
+                                    float* bn_running, int64_t* bn_num_batches, void* workspace, float* pred, float* loss,
+                                    float* dpred, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                    int64_t step, int32_t apply_update, void* stream) {
+  ParamLayout L;
+  CK(build_layout(c, L));
+  MIVIT_CHECK_ARG(target && pred && loss && dpred, "bad arguments");
+  CK(mivit_vit_forward(c, B, x, features, params, bn_running, bn_num_batches, workspace, pred, 1, stream));
+  CK(mse_loss(pred, target, B, loss, dpred, (cudaStream_t)stream));
+  CK(mivit_vit_backward(c, B, x, features, dpred, params, grads, workspace, stream));
+  if (apply_update) {
+    MIVIT_CHECK_ARG(adam_m && adam_v && step >= 1, "optimizer state missing");
+    CK(adamw_flat(params, grads, adam_m, adam_v, L.off, lr, beta1, beta2, eps, weight_decay, step, 1.0f, (cudaStream_t)stream));
+  }
+  return MIVIT_OK;
+}

@@ -1,0 +1,460 @@
+"""Drop-in mirror of the ViT part of the reference's helpers/models.py:
+same class names, constructor signatures, sub-module / state_dict key names and initialisation
+order (so `torch.manual_seed(s)` gives the same random-init weights as the reference), but the
+arithmetic of GeneralTransformer.forward / backward runs in the CUDA library (include/mivit.h:
+mivit_vit_forward / mivit_vit_backward / mivit_vit_train_step).  There is no PyTorch fallback.
+
+  MultiHeadAttention               helpers/models.py:11-59
+  FeedForward                      :61-77
+  TransformerEncoderLayerWithSkip  :81-108
+  Transformer                      :111-141
+  LinearProjectionEmbedding        :146-167
+  CNNEmbedding                     :170-199
+  ResidualBlock / DeepResNetEmbedding  :202-257
+  MLPHead                          :260-276
+  GeneralTransformer               :278-361
+  ImageDataset / ImageFeatureDataset   :781-803
+
+Not supported (raise at construction): dropout > 0 (every reference experiment uses 0.0),
+single_prediction=False, MLPHead activations other than nn.ReLU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.utils.data import Dataset
+
+from . import _lib
+
+MAX_TOKENS = 128  # helpers/models.py:8
+
+__all__ = ["MAX_TOKENS", "MultiHeadAttention", "FeedForward", "TransformerEncoderLayerWithSkip", "Transformer",
+           "LinearProjectionEmbedding", "CNNEmbedding", "ResidualBlock", "DeepResNetEmbedding", "MLPHead",
+           "GeneralTransformer", "ImageDataset", "ImageFeatureDataset", "VitConfig"]
+
+
+class VitConfig(ctypes.Structure):
+    """struct mivit_vit_config (include/mivit.h)."""
+    _fields_ = [("embedding", ctypes.c_int32), ("P", ctypes.c_int32), ("F", ctypes.c_int32), ("E", ctypes.c_int32),
+                ("H", ctypes.c_int32), ("HD", ctypes.c_int32), ("L", ctypes.c_int32), ("activation", ctypes.c_int32),
+                ("use_pos", ctypes.c_int32), ("use_reg", ctypes.c_int32), ("use_feat", ctypes.c_int32),
+                ("fusion", ctypes.c_int32), ("feat_dim", ctypes.c_int32), ("head_hidden", ctypes.c_int32),
+                ("conv_impl", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
+                ("ln_eps", ctypes.c_float)]
+
+
+def _no_direct_forward(self, *a, **k):
+    raise NotImplementedError(
+        "%s is a parameter container in moleculardiffusion_mivit_b200: its arithmetic runs inside "
+        "GeneralTransformer.forward (CUDA library); call the GeneralTransformer." % type(self).__name__)
+
+
+class MultiHeadAttention(nn.Module):
+    def __init__(self, embed_dim, num_heads, dropout=0.0):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim, "embed_dim must be divisible by num_heads"
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.k_proj = nn.Linear(embed_dim, embed_dim)
+        self.v_proj = nn.Linear(embed_dim, embed_dim)
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        self.dropout = nn.Dropout(dropout)
+        nn.init.xavier_uniform_(self.q_proj.weight)
+        nn.init.xavier_uniform_(self.k_proj.weight)
+        nn.init.xavier_uniform_(self.v_proj.weight)
+        nn.init.xavier_uniform_(self.out_proj.weight)
+
+    forward = _no_direct_forward
+
+
+class FeedForward(nn.Module):
+    def __init__(self, embed_dim, hidden_dim, activation_fct, dropout=0.0):
+        super().__init__()
+        self.fc1 = nn.Linear(embed_dim, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, embed_dim)
+        self.dropout = nn.Dropout(dropout)
+        if not callable(activation_fct):
+            raise ValueError("activation_fct must be a callable function from torch.nn.functional or a custom function.")
+        self.activation = activation_fct
+
+    forward = _no_direct_forward
+
+
+class TransformerEncoderLayerWithSkip(nn.Module):
+    def __init__(self, embed_dim, num_heads, hidden_dim, activation_fct, dropout=0.0):
+        super().__init__()
+        self.self_attn = MultiHeadAttention(embed_dim, num_heads, dropout)
+        self.norm1 = nn.LayerNorm(embed_dim)
+        self.norm2 = nn.LayerNorm(embed_dim)
+        self.feed_forward = FeedForward(embed_dim, hidden_dim, activation_fct, dropout)
+        self.dropout = nn.Dropout(dropout)
+
+    forward = _no_direct_forward
+
+
+class Transformer(nn.Module):
+    def __init__(self, embed_dim, num_heads, hidden_dim, num_layers, dropout, use_pos_encoding, activation_fct):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.use_pos_encoding = use_pos_encoding
+        if self.use_pos_encoding:
+            self.pos_embedding = nn.Parameter(torch.randn(1, MAX_TOKENS, embed_dim))
+        self.encoder_layers = nn.ModuleList([
+            TransformerEncoderLayerWithSkip(embed_dim=embed_dim, num_heads=num_heads, hidden_dim=hidden_dim,
+                                            activation_fct=activation_fct, dropout=dropout)
+            for _ in range(num_layers)])
+        self.norm = nn.LayerNorm(embed_dim)
+
+    forward = _no_direct_forward
+
+
+class LinearProjectionEmbedding(nn.Module):
+    def __init__(self, patch_size, embed_dim):
+        super().__init__()
+        self.patch_size = patch_size
+        self.embed_dim = embed_dim
+        self.proj = nn.Linear(patch_size * patch_size, embed_dim)
+
+    forward = _no_direct_forward
+
+
+class CNNEmbedding(nn.Module):
+    def __init__(self, patch_size, embed_dim):
+        super().__init__()
+        self.patch_size = patch_size
+        self.embed_dim = embed_dim
+        self.conv = nn.Conv2d(in_channels=1, out_channels=embed_dim, kernel_size=(patch_size, patch_size))
+
+    forward = _no_direct_forward
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, downsample=False):
+        super().__init__()
+        if downsample:
+            raise NotImplementedError("downsample=True is not used by DeepResNetEmbedding and is not supported")
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1, stride=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(out_channels)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1, stride=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(out_channels)
+        self.skip = nn.Sequential()
+        if in_channels != out_channels or downsample:
+            self.skip = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, bias=False),
+                                      nn.BatchNorm2d(out_channels))
+
+    forward = _no_direct_forward
+
+
+class DeepResNetEmbedding(nn.Module):
+    def __init__(self, patch_size=7, embed_dim=128):
+        super().__init__()
+        self.patch_size = patch_size
+        self.embed_dim = embed_dim
+        self.initial_conv = nn.Conv2d(1, 32, kernel_size=3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(32)
+        self.relu = nn.ReLU(inplace=True)
+        self.res_block1 = ResidualBlock(32, 64)
+        self.res_block2 = ResidualBlock(64, 128)
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(128, embed_dim)
+
+    forward = _no_direct_forward
+
+
+class MLPHead(nn.Module):
+    def __init__(self, input_dim, hidden_dim=128, output_dim=1, dropout=0.0, activation=nn.ReLU):
+        super().__init__()
+        if dropout > 0 or output_dim != 1 or activation is not nn.ReLU:
+            raise NotImplementedError("MLPHead: only dropout=0, output_dim=1, activation=nn.ReLU run on the CUDA path")
+        self.mlp = nn.Sequential(nn.Linear(input_dim, hidden_dim), activation(),
+                                 nn.Dropout(dropout) if dropout > 0 else nn.Identity(),
+                                 nn.Linear(hidden_dim, output_dim))
+
+    forward = _no_direct_forward
+
+
+_ACTIVATIONS = {F.relu: 0, F.gelu: 1, F.leaky_relu: 2}
+_EMBEDDINGS = {LinearProjectionEmbedding: 0, CNNEmbedding: 1, DeepResNetEmbedding: 2}
+_BN_CHANNELS = (32, 64, 64, 64, 128, 128, 128)
+
+
+class _VitFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, features, *params):
+        pred, gen = model._run_forward(x, features, model.training)
+        ctx.model, ctx.gen = model, gen
+        ctx.save_for_backward(x) if features is None else ctx.save_for_backward(x, features)
+        ctx.has_feat = features is not None
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        saved = ctx.saved_tensors
+        x, feats = saved[0], (saved[1] if ctx.has_feat else None)
+        grads = ctx.model._run_backward(x, feats, dpred.contiguous(), ctx.gen)
+        return (None, None, None) + tuple(grads)
+
+
+class GeneralTransformer(nn.Module):
+    def __init__(self, embedding_cls, embed_kwargs, embed_dim, num_heads, hidden_dim, num_layers, mlp_head,
+                 tr_activation_fct, dropout=0, use_pos_encoding=False, use_regression_token=False,
+                 single_prediction=True, use_global_features=False, fusion_type='early', global_feature_dim=None):
+        super().__init__()
+        if dropout != 0:
+            raise NotImplementedError("dropout > 0 is not implemented on the CUDA path (the reference experiments use 0.0)")
+        if not single_prediction:
+            raise NotImplementedError("single_prediction=False (per-frame outputs) is not implemented")
+        if embedding_cls not in _EMBEDDINGS:
+            raise ValueError("embedding_cls must be LinearProjectionEmbedding, CNNEmbedding or DeepResNetEmbedding")
+        if tr_activation_fct not in _ACTIVATIONS:
+            raise ValueError("tr_activation_fct must be F.relu, F.gelu or F.leaky_relu")
+        self.embed_dim = embed_dim
+        self.embedding = embedding_cls(**embed_kwargs)
+        self.norm = nn.LayerNorm(embed_dim)
+        self.use_regression_token = use_regression_token
+        self.single_prediction = single_prediction
+        self.use_global_features = use_global_features
+        self.fusion_type = fusion_type
+        if use_regression_token:
+            self.reg_token = nn.Parameter(torch.randn(1, 1, embed_dim))
+        self.transformer = Transformer(embed_dim, num_heads, hidden_dim, num_layers, dropout,
+                                       use_pos_encoding=use_pos_encoding, activation_fct=tr_activation_fct)
+        if use_global_features:
+            assert global_feature_dim is not None, "Must provide global_feature_dim if using global features"
+            self.feature_projector = nn.Sequential(nn.Linear(global_feature_dim, embed_dim), nn.ReLU(),
+                                                   nn.Linear(embed_dim, embed_dim))
+        if fusion_type == 'late' and use_global_features:
+            self.mlp_head = mlp_head(input_dim=embed_dim * 2)
+        else:
+            self.mlp_head = mlp_head(input_dim=embed_dim)
+        # ---- CUDA-path bookkeeping (not part of the reference surface)
+        self._num_heads, self._hidden_dim, self._num_layers = num_heads, hidden_dim, num_layers
+        self._activation = _ACTIVATIONS[tr_activation_fct]
+        self._use_pos = bool(use_pos_encoding)
+        self._feat_dim = int(global_feature_dim) if use_global_features else 0
+        self._head_hidden = self.mlp_head.mlp[0].out_features
+        self._flat = self._grad_flat = self._bn_flat = self._bn_nbt = None
+        self._ws, self._gen = {}, 0
+        self.conv_impl = 1   # 1 = tcgen05 convolutions; 0 = SIMT cross-check kernels (tests only)
+
+    # ------------------------------------------------------------------ canonical order -----
+    def param_keys(self):
+        """state_dict keys of the parameters in the flat-buffer order of mivit_vit_config."""
+        k = []
+        emb = _EMBEDDINGS[type(self.embedding)]
+        if emb == 2:
+            k += ["embedding.initial_conv.weight", "embedding.bn1.weight", "embedding.bn1.bias"]
+            for b in ("res_block1", "res_block2"):
+                k += ["embedding.%s.%s" % (b, s) for s in ("conv1.weight", "bn1.weight", "bn1.bias", "conv2.weight",
+                                                          "bn2.weight", "bn2.bias", "skip.0.weight", "skip.1.weight",
+                                                          "skip.1.bias")]
+            k += ["embedding.fc.weight", "embedding.fc.bias"]
+        elif emb == 0:
+            k += ["embedding.proj.weight", "embedding.proj.bias"]
+        else:
+            k += ["embedding.conv.weight", "embedding.conv.bias"]
+        k += ["norm.weight", "norm.bias"]
+        if self.use_regression_token:
+            k.append("reg_token")
+        if self._use_pos:
+            k.append("transformer.pos_embedding")
+        for i in range(self._num_layers):
+            p = "transformer.encoder_layers.%d." % i
+            for s in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                k += [p + "self_attn.%s.weight" % s, p + "self_attn.%s.bias" % s]
+            k += [p + "norm1.weight", p + "norm1.bias", p + "feed_forward.fc1.weight", p + "feed_forward.fc1.bias",
+                  p + "feed_forward.fc2.weight", p + "feed_forward.fc2.bias", p + "norm2.weight", p + "norm2.bias"]
+        k += ["transformer.norm.weight", "transformer.norm.bias"]
+        if self.use_global_features:
+            k += ["feature_projector.0.weight", "feature_projector.0.bias", "feature_projector.2.weight",
+                  "feature_projector.2.bias"]
+        k += ["mlp_head.mlp.0.weight", "mlp_head.mlp.0.bias", "mlp_head.mlp.3.weight", "mlp_head.mlp.3.bias"]
+        return k
+
+    def _bn_modules(self):
+        e = self.embedding
+        return [e.bn1, e.res_block1.bn1, e.res_block1.bn2, e.res_block1.skip[1],
+                e.res_block2.bn1, e.res_block2.bn2, e.res_block2.skip[1]]
+
+    def vit_config(self, n_frames):
+        c = VitConfig()
+        c.embedding = _EMBEDDINGS[type(self.embedding)]
+        c.P, c.F, c.E = int(self.embedding.patch_size), int(n_frames), int(self.embed_dim)
+        c.H, c.HD, c.L = int(self._num_heads), int(self._hidden_dim), int(self._num_layers)
+        c.activation, c.use_pos, c.use_reg = self._activation, int(self._use_pos), int(self.use_regression_token)
+        c.use_feat, c.fusion, c.feat_dim = int(self.use_global_features), int(self.fusion_type == 'late'), self._feat_dim
+        c.head_hidden, c.conv_impl = int(self._head_hidden), int(self.conv_impl)
+        c.bn_eps, c.bn_momentum, c.ln_eps = 1e-5, 0.1, 1e-5
+        return c
+
+    # ------------------------------------------------------------------ flat buffers --------
+    def _ensure_flat(self):
+        """(Re)build the flat fp32 CUDA parameter buffer and re-point every Parameter / BatchNorm buffer at a
+        view of it.  Parameter objects keep their identity, so optimizers created earlier stay valid."""
+        dev = _lib.require_cuda()
+        named = dict(self.named_parameters())
+        keys = self.param_keys()
+        assert set(keys) == set(named), "parameter set does not match the canonical layout"
+        ok = self._flat is not None and self._flat.device == dev
+        if ok:
+            off = 0
+            for k in keys:
+                p = named[k]
+                if p.data_ptr() != self._flat.data_ptr() + 4 * off or p.dtype != torch.float32:
+                    ok = False
+                    break
+                off += p.numel()
+        if not ok:
+            cfg = self.vit_config(1)
+            n = _lib.lib().mivit_vit_param_count(ctypes.byref(cfg))
+            if n < 0:
+                raise _lib.MivitError(_lib.lib().mivit_last_error().decode())
+            sizes = (ctypes.c_int64 * n)()
+            _lib.check(_lib.lib().mivit_vit_param_sizes(ctypes.byref(cfg), sizes, n))
+            assert n == len(keys) and [int(s) for s in sizes] == [named[k].numel() for k in keys], \
+                "C-ABI parameter layout does not match the module"
+            total = sum(int(s) for s in sizes)
+            flat = torch.empty(total + 4, dtype=torch.float32, device=dev)
+            off = 0
+            for k in keys:
+                p = named[k]
+                view = flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data.to(device=dev, dtype=torch.float32))
+                p.data = view
+                off += p.numel()
+            self._flat, self._n_params = flat, total
+            self._grad_flat = torch.zeros(total + 4, dtype=torch.float32, device=dev)
+        if _EMBEDDINGS[type(self.embedding)] == 2:
+            bns = self._bn_modules()
+            okb = self._bn_flat is not None and self._bn_flat.device == dev
+            if okb:
+                off = 0
+                for bn in bns:
+                    C = bn.num_features
+                    if bn.running_mean.data_ptr() != self._bn_flat.data_ptr() + 4 * off:
+                        okb = False
+                        break
+                    off += 2 * C
+            if not okb:
+                flat = torch.empty(2 * sum(_BN_CHANNELS), dtype=torch.float32, device=dev)
+                nbt = torch.empty(7, dtype=torch.int64, device=dev)
+                off = 0
+                for i, bn in enumerate(bns):
+                    C = bn.num_features
+                    for name, o in (("running_mean", off), ("running_var", off + C)):
+                        buf = getattr(bn, name)
+                        view = flat[o:o + C]
+                        view.copy_(buf.data.to(device=dev, dtype=torch.float32))
+                        buf.data = view
+                    nv = nbt[i:i + 1].view(())
+                    nv.copy_(bn.num_batches_tracked.data.to(dev))
+                    bn.num_batches_tracked.data = nv
+                    off += 2 * C
+                self._bn_flat, self._bn_nbt = flat, nbt
+        return dev
+
+    def _workspace(self, cfg, B):
+        key = (B, cfg.F, cfg.conv_impl)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = _lib.lib().mivit_vit_workspace_bytes(ctypes.byref(cfg), B)
+            if nbytes < 0:
+                raise _lib.MivitError(_lib.lib().mivit_last_error().decode())
+            self._ws.clear()       # one live workspace: activations of the last forward
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self._flat.device)
+            self._ws[key] = ws
+        return ws
+
+    def _check_inputs(self, x, features):
+        if x.dim() != 4 or x.shape[2] != self.embedding.patch_size or x.shape[3] != self.embedding.patch_size:
+            raise AssertionError("Patch size mismatch")
+        if self.use_global_features:
+            assert features is not None, "Global features required for %s fusion" % self.fusion_type
+        dev = self._flat.device
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        if self.use_global_features:
+            features = features.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            features = None
+        return x, features
+
+    def _run_forward(self, x, features, training):
+        B, Fr = x.shape[0], x.shape[1]
+        cfg = self.vit_config(Fr)
+        ws = self._workspace(cfg, B)
+        pred = torch.empty((B, 1), dtype=torch.float32, device=x.device)
+        is_deep = cfg.embedding == 2
+        _lib.check(_lib.lib().mivit_vit_forward(
+            ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(self._flat),
+            _lib.ptr(self._bn_flat) if is_deep else None, _lib.ptr(self._bn_nbt) if is_deep else None,
+            _lib.ptr(ws), _lib.ptr(pred), int(bool(training)), _lib.current_stream()))
+        self._gen += 1
+        return pred, self._gen
+
+    def _run_backward(self, x, features, dpred, gen):
+        if gen != self._gen:
+            raise RuntimeError("backward() must follow the forward() that produced the output (one live workspace per model)")
+        B, Fr = x.shape[0], x.shape[1]
+        cfg = self.vit_config(Fr)
+        ws = self._workspace(cfg, B)
+        _lib.check(_lib.lib().mivit_vit_backward(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(dpred),
+                                                 _lib.ptr(self._flat), _lib.ptr(self._grad_flat), _lib.ptr(ws),
+                                                 _lib.current_stream()))
+        named = dict(self.named_parameters())
+        grads, off = [], 0
+        for k in self.param_keys():
+            p = named[k]
+            grads.append(self._grad_flat[off:off + p.numel()].view(p.shape).clone())
+            off += p.numel()
+        return grads
+
+    def forward(self, x, features=None):
+        """x: [batch_size, num_images, image_size, image_size]; features: [batch_size, num_features] or None.
+        Returns [batch_size, 1] (CUDA tensor).  Gradients flow to the parameters, not to x."""
+        self._ensure_flat()
+        x, features = self._check_inputs(x, features)
+        named = dict(self.named_parameters())
+        params = [named[k] for k in self.param_keys()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _VitFunction.apply(self, x, features, *params)
+        pred, _ = self._run_forward(x, features, self.training)
+        return pred
+
+    # ------------------------------------------------------------------ fused step ----------
+    def flat_parameters(self):
+        self._ensure_flat()
+        return self._flat[:self._n_params]
+
+    def flat_gradients(self):
+        self._ensure_flat()
+        return self._grad_flat[:self._n_params]
+
+
+class ImageDataset(Dataset):  # helpers/models.py:781-790
+    def __init__(self, images, labels):
+        self.images = images
+        self.labels = labels
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, idx):
+        return self.images[idx], self.labels[idx]
+
+
+class ImageFeatureDataset(Dataset):  # helpers/models.py:793-803
+    def __init__(self, images, features, labels):
+        self.images = images
+        self.features = features
+        self.labels = labels
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, idx):
+        return self.images[idx], self.features[idx], self.labels[idx]

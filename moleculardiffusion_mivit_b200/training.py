@@ -1,0 +1,81 @@
+"""Fused training step of the reference loop body
+(Experiments/PSFNoise/trainModelsPSFNoise.py:182-196: zero_grad, model(x), MSELoss, backward,
+AdamW.step; StepLR(5, 0.9) stepped once per cycle) as ONE C-ABI call on flat buffers, plus the
+data-parallel variant: per-rank generation, one NCCL all-reduce of the 2 MB flat gradient, AdamW
+with grad_scale = 1/world_size.  Nothing here exists in the reference (it is single-process)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from .models import GeneralTransformer
+
+__all__ = ["MiViTTrainer"]
+
+
+class MiViTTrainer:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step_size=5, gamma=0.9,
+                 process_group=None, distributed=None):
+        if not isinstance(model, GeneralTransformer):
+            raise TypeError("MiViTTrainer drives a moleculardiffusion_mivit_b200.models.GeneralTransformer")
+        self.model = model
+        self.base_lr, self.lr = float(lr), float(lr)
+        self.betas, self.eps, self.weight_decay = betas, float(eps), float(weight_decay)
+        self.step_size, self.gamma, self.epoch = int(step_size), float(gamma), 0
+        self.step_count = 0
+        model._ensure_flat()
+        n = model._n_params
+        dev = model._flat.device
+        self.m = torch.zeros(n + 4, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n + 4, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._scratch = {}
+        import torch.distributed as dist
+        self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized())) else None
+        self.group = process_group
+        self.world = self.dist.get_world_size(process_group) if self.dist else 1
+
+    # StepLR(step_size, gamma): lr = base * gamma ** (epoch // step_size), stepped once per cycle
+    def scheduler_step(self):
+        self.epoch += 1
+        self.lr = self.base_lr * self.gamma ** (self.epoch // self.step_size)
+
+    def _buffers(self, B):
+        s = self._scratch.get(B)
+        if s is None:
+            dev = self.model._flat.device
+            s = (torch.empty((B, 1), dtype=torch.float32, device=dev), torch.empty((B, 1), dtype=torch.float32, device=dev))
+            self._scratch = {B: s}
+        return s
+
+    def train_step(self, x, target, features=None):
+        """x: CUDA float32 [B,F,P,P]; target: CUDA float32 [B,1].  Enqueues the whole step on the current
+        stream and returns the (device) loss tensor without synchronising."""
+        model = self.model
+        model._ensure_flat()
+        if not model.training:
+            model.train()
+        x, features = model._check_inputs(x, features)
+        target = target.to(device=x.device, dtype=torch.float32).reshape(-1, 1).contiguous()
+        B, Fr = x.shape[0], x.shape[1]
+        cfg = model.vit_config(Fr)
+        ws = model._workspace(cfg, B)
+        pred, dpred = self._buffers(B)
+        deep = cfg.embedding == 2
+        self.step_count += 1
+        L = _lib.lib()
+        _lib.check(L.mivit_vit_train_step(
+            ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(target), _lib.ptr(model._flat),
+            _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
+            _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None, _lib.ptr(ws),
+            _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
+            self.weight_decay, self.step_count, int(self.world == 1), _lib.current_stream()))
+        model._gen += 1
+        if self.world > 1:
+            g = model._grad_flat[:model._n_params]
+            self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM, group=self.group)
+            _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
+                                          model._n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                          self.step_count, 1.0 / self.world, _lib.current_stream()))
+        self.last_pred = pred
+        return self.loss

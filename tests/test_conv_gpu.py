@@ -101,3 +101,28 @@ def test_conv_tc_matches_simt_large():
     y0, _, s0 = run_conv(x, W, False, 0)
     assert (y1 - y0).abs().max().item() <= 2e-2 * y0.abs().max().item()
     assert torch.allclose(s1, s0, rtol=2e-3, atol=1.0)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("cin,cout,k", [(32, 64, 3), (64, 64, 3), (64, 128, 3), (128, 128, 3), (32, 64, 1), (64, 128, 1)])
+def test_conv_wgrad(impl, cin, cout, k):
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import _lib
+    P, NF = 13, 41
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout + k)
+    x = torch.randn((NF, cin, P, P), device="cuda", generator=g).to(torch.bfloat16).float()
+    dy = torch.randn((NF, cout, P, P), device="cuda", generator=g).to(torch.bfloat16).float()
+    xb, rows = to_rows(x)
+    db, _ = to_rows(dy)
+    dW = torch.zeros((cout, cin, k, k), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().mivit_conv_rows_wgrad(ctypes.c_void_p(xb.data_ptr() + GUARD * cin * 2),
+                                                ctypes.c_void_p(db.data_ptr() + GUARD * cout * 2), _lib.ptr(dW), rows, P, cin,
+                                                cout, k, impl, _lib.current_stream()))
+    torch.cuda.synchronize()
+    W = torch.zeros((cout, cin, k, k), dtype=torch.float64, device="cuda", requires_grad=True)
+    y = F.conv2d(x.double(), W, padding=k // 2)
+    ref, = torch.autograd.grad(y, W, dy.double())
+    ref = ref.float()
+    assert (dW - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 1e-3, (dW - ref).abs().max().item()
