@@ -32,6 +32,18 @@ const char* mivit_last_error(void);
 int64_t mivit_launch_count(void);
 void mivit_reset_launch_count(void);
 
+/* Optional device timing of the tagged hot kernels (CUDA events on the launching stream), used by
+ * bench.py for the roofline object.  total_work = algorithmic FLOPs (convolutions) or bytes
+ * (renderer) summed over the launches. */
+typedef struct mivit_kernel_time {
+  char name[48];
+  int64_t launches;
+  double total_ms;
+  double total_work;
+} mivit_kernel_time;
+void mivit_profile_enable(int32_t on);
+int32_t mivit_profile_read(mivit_kernel_time* out, int32_t max_entries); /* after a stream sync */
+
 /* ------------------------------------------------------------------ renderer ---------- */
 
 /* Scalar set-up that helpers/helpersGeneration.py:225-247 derives from `image_props`. */

@@ -22,6 +22,12 @@ class RenderParams(ctypes.Structure):
     ]
 
 
+class KernelTime(ctypes.Structure):
+    """struct mivit_kernel_time (include/mivit.h)."""
+    _fields_ = [("name", ctypes.c_char * 48), ("launches", ctypes.c_int64), ("total_ms", ctypes.c_double),
+                ("total_work", ctypes.c_double)]
+
+
 class MivitError(RuntimeError):
     pass
 
@@ -35,6 +41,8 @@ def _declare(lib):
         "mivit_last_error": (c.c_char_p, []),
         "mivit_launch_count": (i64, []),
         "mivit_reset_launch_count": (None, []),
+        "mivit_profile_enable": (None, [i32]),
+        "mivit_profile_read": (i32, [c.POINTER(KernelTime), i32]),
         "mivit_render_v1": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, i64, vp]),
         "mivit_render_psfnoise": (i32, [vp, i64, i32, c.POINTER(RenderParams), fp, i32, fp, i32, f32, u64, u64, vp, vp]),
         "mivit_brownian": (i32, [i64, i32, fp, fp, i32, f64, u64, u64, vp, vp, vp]),

@@ -47,3 +47,19 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+
+// optional device timing of tagged launches (capi.cu); work = algorithmic FLOPs or bytes of the launch
+int mivit_prof_tag(const char* name);
+bool mivit_prof_enabled();
+void mivit_prof_begin(int tag, double work, cudaStream_t st);
+void mivit_prof_end(cudaStream_t st);
+struct MivitProfScope {
+  cudaStream_t st;
+  bool on;
+  MivitProfScope(const char* name, double work, cudaStream_t s) : st(s), on(mivit_prof_enabled()) {
+    if (on) mivit_prof_begin(mivit_prof_tag(name), work, st);
+  }
+  ~MivitProfScope() {
+    if (on) mivit_prof_end(st);
+  }
+};

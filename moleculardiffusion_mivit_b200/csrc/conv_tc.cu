@@ -52,6 +52,7 @@ conv_rows_tc_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __
                     __nv_bfloat16* __restrict__ Y, float* __restrict__ stats, long long rows, int n_tiles, int P,
                     int taps, ConvShifts shifts, int halo, int slab_rows) {
   using Cfg = FwdCfg<CIN, COUT>;
+  constexpr int kSwz = (COUT / 8 - 1) < 7 ? (COUT / 8 - 1) : 7;  // XOR swizzle of the 16-byte chunks of a staging row
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slab_bytes = Cfg::kChunks * slab_rows * 16;
@@ -140,7 +141,7 @@ conv_rows_tc_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __
             pw[e] = *reinterpret_cast<uint32_t*>(&h);
           }
           const int chunk = cg * 4 + q;
-          *reinterpret_cast<uint4*>(staging + ((size_t)rl * (COUT / 8) + (chunk ^ (rl & 7))) * 16) = pk;
+          *reinterpret_cast<uint4*>(staging + ((size_t)rl * (COUT / 8) + (chunk ^ (rl & kSwz))) * 16) = pk;
         }
       }
     }
@@ -157,7 +158,7 @@ conv_rows_tc_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __
         float a = 0.f, b = 0.f;
         for (int rr = r0; rr < r1; ++rr) {
           const __nv_bfloat16 h = *reinterpret_cast<const __nv_bfloat16*>(
-              staging + ((size_t)rr * (COUT / 8) + ((col >> 3) ^ (rr & 7))) * 16 + (col & 7) * 2);
+              staging + ((size_t)rr * (COUT / 8) + ((col >> 3) ^ (rr & kSwz))) * 16 + (col & 7) * 2);
           const float f = __bfloat162float(h);
           a += f;
           b = fmaf(f, f, b);
@@ -172,7 +173,7 @@ conv_rows_tc_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __
       constexpr int n16 = kTileM * COUT / 8;
       for (int i = tid; i < n16; i += 128) {
         const int rr = i / (COUT / 8), c = i - rr * (COUT / 8);
-        dst[i] = *reinterpret_cast<const uint4*>(staging + ((size_t)rr * (COUT / 8) + (c ^ (rr & 7))) * 16);
+        dst[i] = *reinterpret_cast<const uint4*>(staging + ((size_t)rr * (COUT / 8) + (c ^ (rr & kSwz))) * 16);
       }
     }
     __syncthreads();  // staging + slab are reused by the next tile
@@ -202,6 +203,10 @@ int launch_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bfloat16* Y
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = n_tiles < sms ? n_tiles : sms;
+  char tag[48];
+  snprintf(tag, sizeof(tag), "conv_rows_tc_%dx%dx%d", CIN, COUT, taps);
+  const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
+  MivitProfScope prof(tag, 2.0 * valid_rows * taps * CIN * COUT, st);
   kern<<<grid, 128, smem, st>>>(X, Wp, Y, stats, rows, n_tiles, P, taps, sh, halo, slab_rows);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();

@@ -137,6 +137,10 @@ int launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, lon
   if (ctas_x > n_stages) ctas_x = n_stages;
   const int spc = (n_stages + ctas_x - 1) / ctas_x;
   ctas_x = (n_stages + spc - 1) / spc;
+  char tag[48];
+  snprintf(tag, sizeof(tag), "conv_wgrad_tc_%dx%dx%d", CIN, COUT, taps);
+  const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
+  MivitProfScope prof(tag, 2.0 * valid_rows * taps * CIN * COUT, st);
   kern<<<dim3(ctas_x, groups), 128, smem, st>>>(X, dY, dW, rows_pad, n_stages, spc, taps, sh, halo, xslab_rows);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();

@@ -354,6 +354,7 @@ extern "C" int mivit_render_v1(const double* traj, int64_t N, int32_t T, const m
   if (smem > 48 * 1024)
     MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long frames = (long long)N * d.F;
+  MivitProfScope prof("render_v1", (double)N * ((double)T * 16.0 + (double)d.F * d.P * d.P * 4.0), (cudaStream_t)stream);
   render_v1_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, out);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();

@@ -14,7 +14,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from oracle import vit_oracle as vo
-from tests.test_oracle_vit import CASES, load_case
+from vit_cases import CASES, load_case
 
 
 def build(name):

@@ -1,0 +1,30 @@
+"""Shared ViT test cases: configs of the golden models and a loader for tests/golden/vit_*.npz."""
+import os
+
+import numpy as np
+import torch
+
+CASES = {
+    "deepcnn_n": dict(embedding="deepresnet", embed_dim=64, num_heads=4, num_layers=6, activation="relu",
+                      use_pos_encoding=False, use_regression_token=True),
+    "linear_s_pos": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="relu",
+                         use_pos_encoding=True, use_regression_token=True),
+    "cnn_s_mean": dict(embedding="cnn", embed_dim=32, num_heads=2, num_layers=3, activation="gelu",
+                       use_pos_encoding=True, use_regression_token=False),
+    "linear_s_feat_early": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="relu",
+                                use_pos_encoding=False, use_regression_token=True, use_global_features=True,
+                                fusion_type="early"),
+    "linear_s_feat_late": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="relu",
+                               use_pos_encoding=False, use_regression_token=True, use_global_features=True,
+                               fusion_type="late"),
+}
+PARAM_COUNTS = {"deepcnn_n": 506081, "linear_s_pos": 36865}   # SURVEY.md section 4 (reference notebooks)
+
+
+def load_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "vit_%s.npz" % name))
+    sd = {k[3:]: torch.tensor(z[k]) for k in z.files if k.startswith("sd/")}
+    feats = torch.tensor(z["features"]) if "features" in z.files else None
+    return z, sd, torch.tensor(z["x"]), torch.tensor(z["target"]), feats
+
+
