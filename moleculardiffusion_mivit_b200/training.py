@@ -9,6 +9,7 @@ import torch
 
 from . import _lib
 from .models import GeneralTransformer
+from .parallel import allreduce_sum_
 
 __all__ = ["MiViTTrainer"]
 
@@ -72,10 +73,9 @@ class MiViTTrainer:
             self.weight_decay, self.step_count, int(self.world == 1), _lib.current_stream()))
         model._gen += 1
         if self.world > 1:
-            g = model._grad_flat[:model._n_params]
-            self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM, group=self.group)
+            scale = allreduce_sum_(model._grad_flat[:model._n_params], self.group)
             _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
                                           model._n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                          self.step_count, 1.0 / self.world, _lib.current_stream()))
+                                          self.step_count, scale, _lib.current_stream()))
         self.last_pred = pred
         return self.loss
