@@ -112,11 +112,17 @@ int mivit_conv_pack_weights(const float* W, void* out_bf16, int32_t cout, int32_
  * (F.conv2d of helpers/models.py:222,225,247 without bias).  mirrored = 1 negates the tap
  * shifts (input gradient with a dgrad weight pack; cin/cout are then those of the GEMM, i.e.
  * swapped).  stats (optional): [2][cout] fp32, per-channel sum and sum of squares of the
- * stored outputs are ADDED (BatchNorm2d batch statistics).  impl: 1 = tcgen05 kernel,
- * 0 = SIMT cross-check kernel. */
+ * stored outputs are ADDED (BatchNorm2d batch statistics).  impl: 1 = pipelined tcgen05 kernel
+ * (product path), 2 = serial tcgen05 kernel, 0 = SIMT cross-check kernel. */
 int mivit_conv_rows(const void* X_row0, const void* Wp, void* Y_row0, float* stats, int64_t rows,
                     int32_t P, int32_t cin, int32_t cout, int32_t ksize, int32_t mirrored, int32_t impl,
                     void* stream);
+
+/* 3x3 convolution + the 1x1 skip convolution of the SAME input in one launch
+ * (ResidualBlock.conv1 and ResidualBlock.skip[0], helpers/models.py:206,216,221-222). */
+int mivit_conv_rows_fused(const void* X_row0, const void* Wp, const void* Wskip, void* Y_row0, void* Yskip_row0,
+                          float* stats, float* stats_skip, int64_t rows, int32_t P, int32_t cin, int32_t cout,
+                          int32_t impl, void* stream);
 
 /* dW (fp32 [cout][cin][k][k], pre-zeroed by the caller) += sum_r dY[r,:]^T X[r + delta_tap,:]
  * (weight gradient of the same convolution).  impl as above. */

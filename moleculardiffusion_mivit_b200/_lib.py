@@ -48,6 +48,7 @@ def _declare(lib):
         "mivit_brownian": (i32, [i64, i32, fp, fp, i32, f64, u64, u64, vp, vp, vp]),
         "mivit_conv_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "mivit_conv_rows": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]),
+        "mivit_conv_rows_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
         "mivit_conv_rows_wgrad": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
         "mivit_vit_param_count": (i32, [vp]),
         "mivit_vit_param_sizes": (i32, [vp, c.POINTER(c.c_int64), i32]),

@@ -68,3 +68,13 @@ extern "C" int mivit_conv_rows_wgrad(const void* X_row0, const void* dY_row0, fl
   return conv_rows_wgrad((const __nv_bfloat16*)X_row0, (const __nv_bfloat16*)dY_row0, dW, rows, P, cin, cout, ksize * ksize, sh,
                          impl, (cudaStream_t)stream);
 }
+
+extern "C" int mivit_conv_rows_fused(const void* X_row0, const void* Wp, const void* Wskip, void* Y_row0, void* Yskip_row0,
+                                     float* stats, float* stats_skip, int64_t rows, int32_t P, int32_t cin, int32_t cout,
+                                     int32_t impl, void* stream) {
+  MIVIT_CHECK_ARG(X_row0 && Wp && Wskip && Y_row0 && Yskip_row0, "NULL pointer");
+  const ConvShifts sh = make_shifts(P, 9, false);
+  return conv_rows_forward_fused((const __nv_bfloat16*)X_row0, (const __nv_bfloat16*)Wp, (const __nv_bfloat16*)Wskip,
+                                 (__nv_bfloat16*)Y_row0, (__nv_bfloat16*)Yskip_row0, stats, stats_skip, rows, P, cin, cout, 9, sh,
+                                 impl, (cudaStream_t)stream);
+}

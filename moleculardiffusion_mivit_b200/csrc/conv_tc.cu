@@ -256,6 +256,11 @@ int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bflo
     MIVIT_LAUNCH_CHECK();
     return MIVIT_OK;
   }
+  if (impl == 1) {  // pipelined kernel; falls through to the serial one if the slab does not fit
+    bool handled = false;
+    const int rc = conv_rows_forward_v2(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);
+    if (rc || handled) return rc;
+  }
 #define MIVIT_FWD_CASE(CI, CO) \
   if (cin == CI && cout == CO) return launch_fwd<CI, CO>(X, Wp, Y, stats, rows, P, taps, sh, st);
   MIVIT_FWD_CASE(32, 64)
@@ -267,4 +272,20 @@ int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bflo
 #undef MIVIT_FWD_CASE
   mivit_set_error("conv_rows_forward: unsupported channel pair %d -> %d", cin, cout);
   return MIVIT_ERR_INVALID;
+}
+
+// conv (taps) + the 1x1 skip convolution of the same input in one launch when the pipelined kernel
+// covers the shape; otherwise two launches.
+int conv_rows_forward_fused(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
+                            __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout,
+                            int taps, const ConvShifts& sh, int impl, cudaStream_t st) {
+  if (impl == 1) {
+    bool handled = false;
+    const int rc = conv_rows_forward_v2(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);
+    if (rc || handled) return rc;
+  }
+  int rc = conv_rows_forward(X, Wp, Y, stats, rows, P, cin, cout, taps, sh, impl, st);
+  if (rc) return rc;
+  const ConvShifts s1 = make_shifts(P, 1, false);
+  return conv_rows_forward(X, Wsk, Ysk, stats_sk, rows, P, cin, cout, 1, s1, impl, st);
 }

@@ -113,7 +113,7 @@ int gemm_f32(const float* A, long long sam, long long sak, const float* B, long 
 
 int colsum_f32(const float* X, long long ld, int M, int N, float* out, cudaStream_t st) {
   if (M <= 0 || N <= 0) return MIVIT_OK;
-  const int rpb = 2048;
+  const int rpb = 128;  // many small CTAs: the reduction is bandwidth-bound and M is 30k+ tokens
   dim3 grid(mivit_ceil_div(N, 32), mivit_ceil_div(M, rpb));
   colsum_kernel<<<grid, 256, 0, st>>>(X, ld, M, N, out, rpb);
   mivit_count_launch();

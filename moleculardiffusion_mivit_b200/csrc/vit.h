@@ -27,6 +27,14 @@ static inline ConvShifts make_shifts(int P, int taps, bool mirrored) {
 int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bfloat16* Y, float* stats, long long rows,
                       int P, int cin, int cout, int taps, const ConvShifts& sh, int impl, cudaStream_t st);
 
+// pipelined / fused variants (conv_tc2.cu); impl: 1 = pipelined tcgen05, 2 = serial tcgen05 (v1), 0 = SIMT
+int conv_rows_forward_v2(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
+                         __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout, int taps,
+                         const ConvShifts& sh, cudaStream_t st, bool* handled);
+int conv_rows_forward_fused(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
+                            __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout,
+                            int taps, const ConvShifts& sh, int impl, cudaStream_t st);
+
 // W fp32 [cout][cin][k][k] -> bf16 core-matrix packs (see conv_aux.cu)
 int pack_conv_weights(const float* W, __nv_bfloat16* out, int cout, int cin, int taps, int dgrad, cudaStream_t st);
 

@@ -196,9 +196,9 @@ int linear_fwd(const float* X, const float* W, const float* bias, float* Y, int 
 // dW[N,K] += dY[M,N]^T X[M,K];  db[N] += colsum(dY);  dX[M,K] (=|+=) dY W
 int linear_bwd(const float* X, const float* W, const float* dY, float* dW, float* db, float* dX, int M, int N, int K,
                int accumulate_dx, cudaStream_t st) {
-  int split = M / 512;
+  int split = M / 128;  // token-dimension split-K: enough CTAs to fill 148 SMs even for 64x64 outputs
   if (split < 1) split = 1;
-  if (split > 64) split = 64;
+  if (split > 296) split = 296;
   if (split == 1) {
     CK(gemm_f32(dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, 0, 1, 1, st));
   } else {
@@ -274,7 +274,7 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
     RowsT* guarded[] = {&w.act0, &w.act1, &w.act2, &w.act3};
     for (RowsT* t : guarded) CK(zero_guards(*t, rp, st));
     for (int i = 0; i < 7; ++i) MIVIT_CUDA_CHECK(cudaMemsetAsync(w.bn[i].stats, 0, 2 * w.bn[i].C * sizeof(float), st));
-    const ConvShifts s3 = make_shifts(P, 9, false), s1 = make_shifts(P, 1, false);
+    const ConvShifts s3 = make_shifts(P, 9, false);
     long long* nbt = (long long*)bn_num_batches;
     // stem
     CK(conv0_forward(x, p + L.conv0_w, w.raw0.row0, w.bn[0].stats, rows, rp, P, st));
@@ -293,11 +293,12 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
       CK(pack_conv_weights(p + R.c1_w, w.wp_c1[b], co[b], ci[b], 9, 0, st));
       CK(pack_conv_weights(p + R.c2_w, w.wp_c2[b], co[b], co[b], 9, 0, st));
       CK(pack_conv_weights(p + R.sk_w, w.wp_sk[b], co[b], ci[b], 1, 0, st));
-      CK(conv_rows_forward(in[b]->row0, w.wp_c1[b], r1[b]->row0, w.bn[i1].stats, rows, P, ci[b], co[b], 9, s3, impl, st));
+      // conv1 (3x3) and the 1x1 skip convolution read the same input: one fused launch
+      CK(conv_rows_forward_fused(in[b]->row0, w.wp_c1[b], w.wp_sk[b], r1[b]->row0, rs[b]->row0, w.bn[i1].stats, w.bn[is].stats,
+                                 rows, P, ci[b], co[b], 9, s3, impl, st));
       CK(run_bn_finalize(c, w, i1, p + R.bn1_g, p + R.bn1_b, bn_running, nbt, cnt, training, st));
       CK(bn_apply(r1[b]->row0, w.bn[i1].ss, nullptr, nullptr, a1[b]->row0, rows, rp, P, co[b], st));
       CK(conv_rows_forward(a1[b]->row0, w.wp_c2[b], r2[b]->row0, w.bn[i2].stats, rows, P, co[b], co[b], 9, s3, impl, st));
-      CK(conv_rows_forward(in[b]->row0, w.wp_sk[b], rs[b]->row0, w.bn[is].stats, rows, P, ci[b], co[b], 1, s1, impl, st));
       CK(run_bn_finalize(c, w, i2, p + R.bn2_g, p + R.bn2_b, bn_running, nbt, cnt, training, st));
       CK(run_bn_finalize(c, w, is, p + R.bns_g, p + R.bns_b, bn_running, nbt, cnt, training, st));
       CK(bn_apply(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, out[b]->row0, rows, rp, P, co[b], st));

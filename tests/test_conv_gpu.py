@@ -53,7 +53,7 @@ def run_conv(x, W, mirrored, impl, want_stats=True):
     return y, padded, stats
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("cin,cout,k", [(32, 64, 3), (64, 64, 3), (64, 128, 3), (128, 128, 3), (32, 64, 1), (64, 128, 1)])
 @pytest.mark.parametrize("P", [9, 13])
 def test_conv_forward(impl, cin, cout, k, P):
@@ -76,8 +76,8 @@ def test_conv_forward(impl, cin, cout, k, P):
     assert torch.allclose(stats[1], (yb * yb).sum(dim=(0, 2, 3)), rtol=2e-3)
 
 
-@pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("cin,cout,k", [(32, 64, 3), (64, 64, 3), (64, 128, 3), (128, 128, 3), (64, 128, 1)])
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("cin,cout,k", [(32, 64, 3), (64, 64, 3), (64, 128, 3), (128, 128, 3), (64, 128, 1), (32, 64, 1)])
 def test_conv_dgrad(impl, cin, cout, k):
     import torch
     import torch.nn.functional as F
@@ -126,3 +126,40 @@ def test_conv_wgrad(impl, cin, cout, k):
     ref, = torch.autograd.grad(y, W, dy.double())
     ref = ref.float()
     assert (dW - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 1e-3, (dW - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 64), (64, 128)])
+@pytest.mark.parametrize("NF", [3, 700])
+def test_conv_fused_skip(cin, cout, NF):
+    """conv1 (3x3) + skip (1x1) of a ResidualBlock in one pipelined launch; NF = 700 gives every
+    persistent CTA several tiles (double-buffer wrap-around, both mbarrier phases)."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import _lib
+    L = _lib.lib()
+    P = 13
+    g = torch.Generator(device="cuda").manual_seed(cin + NF)
+    x = torch.randn((NF, cin, P, P), device="cuda", generator=g).to(torch.bfloat16).float()
+    W = (torch.randn((cout, cin, 3, 3), device="cuda", generator=g) / np.sqrt(cin * 9)).to(torch.bfloat16).float()
+    Ws = (torch.randn((cout, cin, 1, 1), device="cuda", generator=g) / np.sqrt(cin)).to(torch.bfloat16).float()
+    xb, rows = to_rows(x)
+    wp = torch.empty(9 * cin * cout, dtype=torch.bfloat16, device="cuda")
+    ws = torch.empty(cin * cout, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.mivit_conv_pack_weights(_lib.ptr(W), _lib.ptr(wp), cout, cin, 3, 0, _lib.current_stream()))
+    _lib.check(L.mivit_conv_pack_weights(_lib.ptr(Ws), _lib.ptr(ws), cout, cin, 1, 0, _lib.current_stream()))
+    yb = torch.full((xb.shape[0], cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    sb = torch.full((xb.shape[0], cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros((2, 2, cout), dtype=torch.float32, device="cuda")
+    _lib.check(L.mivit_conv_rows_fused(ctypes.c_void_p(xb.data_ptr() + GUARD * cin * 2), _lib.ptr(wp), _lib.ptr(ws),
+                                       ctypes.c_void_p(yb.data_ptr() + GUARD * cout * 2),
+                                       ctypes.c_void_p(sb.data_ptr() + GUARD * cout * 2), _lib.ptr(st[0]), _lib.ptr(st[1]),
+                                       rows, P, cin, cout, 1, _lib.current_stream()))
+    torch.cuda.synchronize()
+    for buf, w, pad, s in ((yb, W, 1, st[0]), (sb, Ws, 0, st[1])):
+        y, padded = from_rows(buf, NF, cout, P)
+        ref = F.conv2d(x.double(), w.double(), padding=pad).float()
+        assert (y - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+        assert torch.all(padded[:, P, :, :] == 0) and torch.all(padded[:, :, P, :] == 0)
+        assert torch.allclose(s[0], y.sum(dim=(0, 2, 3)), rtol=2e-3, atol=0.05 * NF)
+        assert torch.allclose(s[1], (y * y).sum(dim=(0, 2, 3)), rtol=2e-3)
