@@ -9,8 +9,8 @@
 //     epilogue (TMEM -> registers -> bf16 -> global, BatchNorm statistics) of tile k;
 //   * the 1x1 skip convolution of a ResidualBlock (helpers/models.py:216,221) reads the same input
 //     as conv1, so it is fused: a second accumulator fed by the centre tap of the same slab.
-// Warp roles (256 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 MMA issuer,
-// warps 5-7 producers.
+// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4 and 8 MMA
+// issuers (even / odd tiles), warps 5-7 producers.
 #include "common.cuh"
 #include "umma.cuh"
 #include "vit.h"
@@ -57,7 +57,6 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 template <int CIN, int NS, bool SKIP>
 struct Cfg2 {
   static constexpr int kCH = CIN / 8;
-  static constexpr int kWBytes = 9 * CIN * NS * 2;
   static constexpr int kWSkipBytes = SKIP ? CIN * NS * 2 : 0;
   static constexpr int kAccCols = NS * (SKIP ? 2 : 1);
   static constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128
@@ -65,13 +64,14 @@ struct Cfg2 {
   static constexpr int kGroups = NS / 32;
 };
 
-template <int CIN, int NS, bool SKIP>
-__global__ void __launch_bounds__(256, 1)
+template <int CIN, int NS, bool SKIP, int TAPS>
+__global__ void __launch_bounds__(288, 1)
 conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Wp,
                      const __nv_bfloat16* __restrict__ Wsk, __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ Ysk,
-                     float* __restrict__ stats, float* __restrict__ stats_sk, long long rows, int n_tiles, int P, int taps,
+                     float* __restrict__ stats, float* __restrict__ stats_sk, long long rows, int n_tiles, int P,
                      ConvShifts shifts, int halo, int slab_rows, int cout_total, int nsplit) {
   using C = Cfg2<CIN, NS, SKIP>;
+  constexpr int taps = TAPS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slab_bytes = (C::kCH * slab_rows * 16 + 127) & ~127;
@@ -103,13 +103,13 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
   // resident weights of this column slice
   {
     const int per_tap = C::kCH * NS;  // 16-byte units per tap in smem
-    for (int i = tid; i < taps * per_tap; i += 256) {
+    for (int i = tid; i < taps * per_tap; i += 288) {
       const int t = i / per_tap, r = i - t * per_tap, ch = r / NS, n = r - ch * NS;
       const uint4* src = reinterpret_cast<const uint4*>(Wp) + ((size_t)(t * C::kCH + ch) * cout_total + col0 + n);
       reinterpret_cast<uint4*>(wsm)[i] = __ldg(src);
     }
     if (SKIP) {
-      for (int i = tid; i < per_tap; i += 256) {
+      for (int i = tid; i < per_tap; i += 288) {
         const int ch = i / NS, n = i - ch * NS;
         const uint4* src = reinterpret_cast<const uint4*>(Wsk) + ((size_t)ch * cout_total + col0 + n);
         reinterpret_cast<uint4*>(wsk)[i] = __ldg(src);
@@ -122,7 +122,7 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 5) {
+  if (warp >= 5 && warp <= 7) {
     // ===================== producers: row slab of tile k -> slab[k & 1] =====================
     const int pt = (warp - 5) * 32 + lane;
     int k = 0;
@@ -142,41 +142,61 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
       __syncwarp();
       if (lane == 0) mbar_arrive(full + buf);
     }
-  } else if (warp == 4) {
-    // ===================== MMA issuer (whole warp waits, lane 0 issues) =====================
+  } else if (warp == 4 || warp == 8) {
+    // ===================== MMA issuers: warp 4 -> even work items (buffer 0), warp 8 -> odd (buffer 1).
+    // Two issuing threads because one thread's scalar stream (~17 SASS instructions per tcgen05.mma)
+    // is slower than the tensor pipe for N = 64 tiles; their MMAs target different accumulators.
+    // The issue loop is a single thread's scalar instruction stream, so it is kept to ~2 integer
+    // adds per tcgen05.mma: descriptors are (constant high word | start-address low word) and only
+    // the low word is advanced (tap shift: +delta rows, K step: +2 chunks).
     constexpr uint32_t idesc = umma::make_idesc_bf16(kTileM, NS, 0, 0);
-    const uint32_t w_addr = umma::smem_u32(wsm), wsk_addr = umma::smem_u32(wsk);
+    const uint64_t da_base[2] = {umma::make_desc(umma::smem_u32(slab0) + (uint32_t)halo * 16u, (uint32_t)slab_rows * 16u, 128u),
+                                 umma::make_desc(umma::smem_u32(slab1) + (uint32_t)halo * 16u, (uint32_t)slab_rows * 16u, 128u)};
+    const uint64_t db_base = umma::make_desc(umma::smem_u32(wsm), (uint32_t)NS * 16u, 128u);
+    const uint64_t dbsk_base = umma::make_desc(umma::smem_u32(wsk), (uint32_t)NS * 16u, 128u);
+    const uint32_t a_hi = (uint32_t)(da_base[0] >> 32), b_hi = (uint32_t)(db_base >> 32);
+    const uint32_t a_kstep = 2u * (uint32_t)slab_rows;  // two 8-channel chunks per K = 16 step (16-byte units)
+    int dl[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) dl[t] = shifts.d[t];
     int k = 0;
+    const int my_buf = warp == 4 ? 0 : 1;
     for (int tile = cta_in_slice; tile < n_tiles; tile += ctas_per_slice, ++k) {
       const int buf = k & 1;
+      if (buf != my_buf) continue;
       const uint32_t ph = (k >> 1) & 1;
       umma::mbar_wait(full + buf, ph);
       umma::mbar_wait(tempty + buf, ph ^ 1);
       umma::fence_after_sync();
-      if (lane == 0) {
-        const uint32_t slab_addr = umma::smem_u32(buf ? slab1 : slab0);
+      {
+        const uint32_t lead = lane == 0 ? 1u : 0u;
+        const uint32_t a_lo0 = (uint32_t)da_base[buf];
+        const uint32_t b_lo0 = (uint32_t)db_base;
         const uint32_t acc = tmem + (uint32_t)(buf * C::kAccCols);
-        for (int t = 0; t < taps; ++t) {
-          const int delta = shifts.d[t];
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+          uint32_t a_lo = a_lo0 + (uint32_t)dl[t];
 #pragma unroll
           for (int j = 0; j < CIN / 16; ++j) {
-            const uint64_t da = umma::make_desc(slab_addr + (uint32_t)((2 * j) * slab_rows + halo + delta) * 16u,
-                                                (uint32_t)slab_rows * 16u, 128u);
-            const uint64_t db = umma::make_desc(w_addr + (uint32_t)((t * C::kCH + 2 * j) * NS) * 16u, (uint32_t)NS * 16u, 128u);
-            umma::mma_bf16(acc, da, db, idesc, (t > 0 || j > 0) ? 1u : 0u);
+            const uint64_t da = ((uint64_t)a_hi << 32) | a_lo;
+            const uint64_t db = ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)((t * C::kCH + 2 * j) * NS));
+            umma::mma_bf16_lead(acc, da, db, idesc, (t > 0 || j > 0) ? 1u : 0u, lead);
+            a_lo += a_kstep;
           }
         }
         if (SKIP) {
+          uint32_t a_lo = a_lo0;
+          const uint32_t bs_lo0 = (uint32_t)dbsk_base;
 #pragma unroll
           for (int j = 0; j < CIN / 16; ++j) {
-            const uint64_t da = umma::make_desc(slab_addr + (uint32_t)((2 * j) * slab_rows + halo) * 16u,
-                                                (uint32_t)slab_rows * 16u, 128u);
-            const uint64_t db = umma::make_desc(wsk_addr + (uint32_t)((2 * j) * NS) * 16u, (uint32_t)NS * 16u, 128u);
-            umma::mma_bf16(acc + NS, da, db, idesc, j > 0 ? 1u : 0u);
+            const uint64_t da = ((uint64_t)a_hi << 32) | a_lo;
+            const uint64_t db = ((uint64_t)b_hi << 32) | (bs_lo0 + (uint32_t)((2 * j) * NS));
+            umma::mma_bf16_lead(acc + NS, da, db, idesc, j > 0 ? 1u : 0u, lead);
+            a_lo += a_kstep;
           }
         }
-        umma::commit(empty + buf);   // slab may be refilled once these MMAs have read it
-        umma::commit(tfull + buf);   // accumulator ready for the epilogue
+        umma::commit_lead(empty + buf, lead);   // slab may be refilled once these MMAs have read it
+        umma::commit_lead(tfull + buf, lead);   // accumulator ready for the epilogue
       }
       __syncwarp();
     }
@@ -251,11 +271,12 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
   if (warp == 0) umma::tmem_dealloc<C::kTmemCols>(tmem);
 }
 
-template <int CIN, int NS, bool SKIP>
+template <int CIN, int NS, bool SKIP, int TAPS>
 int launch2(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y, __nv_bfloat16* Ysk,
-            float* stats, float* stats_sk, long long rows, int P, int cout_total, int taps, const ConvShifts& sh,
+            float* stats, float* stats_sk, long long rows, int P, int cout_total, const ConvShifts& sh,
             cudaStream_t st, bool* fits) {
   using C = Cfg2<CIN, NS, SKIP>;
+  constexpr int taps = TAPS;
   const int halo = P + 2;
   int slab_rows = kTileM + 2 * halo;
   if ((slab_rows & 1) == 0) ++slab_rows;
@@ -264,7 +285,7 @@ int launch2(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   *fits = smem <= 227 * 1024;
   if (!*fits) return MIVIT_OK;
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: the TMEM budget assumes it
-  auto kern = conv_rows_tc2_kernel<CIN, NS, SKIP>;
+  auto kern = conv_rows_tc2_kernel<CIN, NS, SKIP, TAPS>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (int)((rows + kTileM - 1) / kTileM);
   const int nsplit = cout_total / NS;
@@ -277,7 +298,7 @@ int launch2(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   snprintf(tag, sizeof(tag), "conv_rows_tc_%dx%dx%d%s", CIN, cout_total, taps, SKIP ? "+skip" : "");
   const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
   MivitProfScope prof(tag, 2.0 * valid_rows * (taps + (SKIP ? 1 : 0)) * CIN * cout_total, st);
-  kern<<<per_slice * nsplit, 256, smem, st>>>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, n_tiles, P, taps, sh, halo, slab_rows,
+  kern<<<per_slice * nsplit, 288, smem, st>>>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, n_tiles, P, sh, halo, slab_rows,
                                               cout_total, nsplit);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
@@ -297,7 +318,8 @@ int conv_rows_forward_v2(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const 
   int rc = MIVIT_OK;
 #define V2_CASE(CI, CO, NS_, SK)                                                                                       \
   if (cin == CI && cout == CO && skip == SK) {                                                                         \
-    rc = launch2<CI, NS_, SK>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cout, taps, sh, st, &fits);                \
+    rc = taps == 9 ? launch2<CI, NS_, SK, 9>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cout, sh, st, &fits)        \
+                   : launch2<CI, NS_, SK, 1>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cout, sh, st, &fits);       \
     if (!fits) *handled = false;                                                                                       \
     return rc;                                                                                                         \
   }

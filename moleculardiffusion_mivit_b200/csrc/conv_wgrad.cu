@@ -173,6 +173,11 @@ int conv_rows_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, 
     MIVIT_LAUNCH_CHECK();
     return MIVIT_OK;
   }
+  if (impl == 1) {  // pipelined kernel; falls back to the serial one when the stage does not fit
+    bool handled = false;
+    const int rc = conv_rows_wgrad_v2(X, dY, dW, rows, P, cin, cout, taps, sh, st, &handled);
+    if (rc || handled) return rc;
+  }
 #define MIVIT_WG_CASE(CI, CO) \
   if (cin == CI && cout == CO) return launch_wgrad<CI, CO>(X, dY, dW, rows, P, taps, sh, st);
   MIVIT_WG_CASE(32, 64)
