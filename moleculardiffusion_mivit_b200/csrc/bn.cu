@@ -8,12 +8,43 @@
 
 namespace {
 
-__device__ __forceinline__ bool row_is_valid(long long r, long long rows, int P) {
-  if (r >= rows) return false;
-  const int pitch = P + 1;
-  const int q = (int)(r % (long long)(pitch * pitch));
-  const int y = q / pitch, x = q - y * pitch;
-  return y < P && x < P;
+// Row -> (frame-local index, y, x) needs r mod (P+1)^2 and a division by P+1 for EVERY 16-byte
+// access; 64-bit '%' costs ~100 instructions and made these passes instruction-bound, so both are
+// done with 32-bit multiply-high "magic number" division (Granlund-Montgomery round-up form).
+struct FastDiv {
+  uint32_t d, m, s;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.s = s;
+  f.m = (uint32_t)((((1ull << s) - d) << 32) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return f.s == 0 ? n : (t + ((n - t) >> 1)) >> (f.s - 1);
+}
+struct RowGeom {
+  FastDiv rpf, pitch;
+  uint32_t rows;
+  int P;
+};
+static inline RowGeom make_geom(long long rows, int P) {
+  RowGeom g;
+  g.rpf = make_fastdiv((uint32_t)((P + 1) * (P + 1)));
+  g.pitch = make_fastdiv((uint32_t)(P + 1));
+  g.rows = (uint32_t)rows;
+  g.P = P;
+  return g;
+}
+__device__ __forceinline__ bool row_is_valid(uint32_t r, const RowGeom& g) {
+  if (r >= g.rows) return false;
+  const uint32_t q = r - fast_div(r, g.rpf) * g.rpf.d;
+  const uint32_t y = fast_div(q, g.pitch), x = q - y * g.pitch.d;
+  return y < (uint32_t)g.P && x < (uint32_t)g.P;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -73,15 +104,14 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
 template <int C>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a,
                                                        const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
-                                                       __nv_bfloat16* __restrict__ act, long long rows, long long rows_pad,
-                                                       int P) {
+                                                       __nv_bfloat16* __restrict__ act, RowGeom geo, long long rows_pad) {
   constexpr int CH = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows_pad * CH) return;
   const long long r = idx / CH;
   const int ch = (int)(idx - r * CH);
   float o[8] = {};
-  if (row_is_valid(r, rows, P)) {
+  if (row_is_valid((uint32_t)r, geo)) {
     float a[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
 #pragma unroll
@@ -117,14 +147,15 @@ __global__ void __launch_bounds__(C) pool_rows_kernel(const __nv_bfloat16* __res
 // sums[0][c] = sum g, sums[1][c] = sum g*xhat_a, sums[2][c] = sum g*xhat_b
 template <int C>
 __device__ __forceinline__ bool load_g(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled,
-                                       const __nv_bfloat16* act, long long r, int ch, long long rows, int P, float (&g)[8]) {
-  if (!row_is_valid(r, rows, P)) return false;
+                                       const __nv_bfloat16* act, long long r, int ch, const RowGeom& geo, float (&g)[8]) {
+  if (!row_is_valid((uint32_t)r, geo)) return false;
+  const int P = geo.P;
   constexpr int CH = C / 8;
   const long long idx = r * CH + ch;
   float a[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(act) + idx), a);
   if (dpooled != nullptr) {
-    const long long f = r / ((long long)(P + 1) * (P + 1));
+    const long long f = fast_div((uint32_t)r, geo.rpf);
     const float inv = 1.0f / (float)(P * P);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = a[i] > 0.f ? dpooled[f * C + ch * 8 + i] * inv : 0.f;
@@ -148,16 +179,16 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ act,
                                                             const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mi_a,
                                                             const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mi_b,
-                                                            float* __restrict__ sums, long long rows, int P, int rows_per_block) {
+                                                            float* __restrict__ sums, RowGeom geo, int rows_per_block) {
   constexpr int CH = C / 8;
   constexpr int RL = 256 / CH;  // row lanes
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(rows, r0 + rows_per_block);
+  const long long r1 = min((long long)geo.rows, r0 + rows_per_block);
   float s0[8] = {}, s1[8] = {}, s2[8] = {};
   for (long long r = r0 + rl; r < r1; r += RL) {
     float g[8];
-    if (!load_g<C>(up_a, up_b, dpooled, act, r, ch, rows, P, g)) continue;
+    if (!load_g<C>(up_a, up_b, dpooled, act, r, ch, geo, g)) continue;
     float a[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + r * CH + ch), a);
 #pragma unroll
@@ -197,8 +228,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ gamma_a, __nv_bfloat16* __restrict__ draw_a,
                                                            const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mi_b,
                                                            const float* __restrict__ gamma_b, __nv_bfloat16* __restrict__ draw_b,
-                                                           const float* __restrict__ sums, long long rows, long long rows_pad, int P,
-                                                           float inv_count) {
+                                                           const float* __restrict__ sums, RowGeom geo, long long rows_pad, float inv_count) {
   constexpr int CH = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows_pad * CH) return;
@@ -206,7 +236,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   const int ch = (int)(idx - r * CH);
   float oa[8] = {}, ob[8] = {};
   float g[8];
-  if (load_g<C>(up_a, up_b, dpooled, act, r, ch, rows, P, g)) {
+  if (load_g<C>(up_a, up_b, dpooled, act, r, ch, geo, g)) {
     float a[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
 #pragma unroll
@@ -349,8 +379,9 @@ int bn_finalize(const float* stats, const float* gamma, const float* beta, float
 
 int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b,
              __nv_bfloat16* act, long long rows, long long rows_pad, int P, int C, cudaStream_t st) {
+  MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
   const long long n = rows_pad * (C / 8);
-  BN_DISPATCH_C(C, (bn_apply_kernel<CC><<<mivit_ceil_div(n, 256), 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, rows, rows_pad, P)));
+  BN_DISPATCH_C(C, (bn_apply_kernel<CC><<<mivit_ceil_div(n, 256), 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, make_geom(rows, P), rows_pad)));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -372,12 +403,12 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
   MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
   const int rpb = 4096;
   const int blocks = mivit_ceil_div(rows, rpb);
-  BN_DISPATCH_C(C, (bn_bwd_reduce_kernel<CC><<<blocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, raw_b, mi_b, sums, rows, P, rpb)));
+  BN_DISPATCH_C(C, (bn_bwd_reduce_kernel<CC><<<blocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, raw_b, mi_b, sums, make_geom(rows, P), rpb)));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   const long long n = rows_pad * (C / 8);
   BN_DISPATCH_C(C, (bn_bwd_apply_kernel<CC><<<mivit_ceil_div(n, 256), 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, gamma_a, draw_a,
-                                                                                   raw_b, mi_b, gamma_b, draw_b, sums, rows, rows_pad, P,
+                                                                                   raw_b, mi_b, gamma_b, draw_b, sums, make_geom(rows, P), rows_pad,
                                                                                    (float)(1.0 / count))));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
