@@ -101,31 +101,50 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
 
 // ---------------------------------------------------------------- apply (+relu, +residual) ---
 // act = relu(raw_a*scale_a + shift_a [+ raw_b*scale_b + shift_b]); pad rows -> 0.
-template <int C>
+// Thread = (8-channel chunk, row lane): the per-channel constants are loaded ONCE into registers as
+// float4 and the thread streams kRowsPerThread rows (scalar constant loads per element made the first
+// version LSU-instruction bound at ~45 % of HBM bandwidth).
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+constexpr int kRowsPerCta = 256;
+
+template <int C, bool DUAL>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a,
                                                        const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
                                                        __nv_bfloat16* __restrict__ act, RowGeom geo, long long rows_pad) {
-  constexpr int CH = C / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows_pad * CH) return;
-  const long long r = idx / CH;
-  const int ch = (int)(idx - r * CH);
-  float o[8] = {};
-  if (row_is_valid((uint32_t)r, geo)) {
-    float a[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], ss_a[ch * 8 + i], ss_a[C + ch * 8 + i]);
-    if (raw_b != nullptr) {
-      float b[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += fmaf(b[i], ss_b[ch * 8 + i], ss_b[C + ch * 8 + i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+  constexpr int CH = C / 8, RL = 256 / CH;
+  const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
+  float sa[8], ha[8], sb[8], hb[8];
+  load8f(ss_a + ch * 8, sa);
+  load8f(ss_a + C + ch * 8, ha);
+  if (DUAL) {
+    load8f(ss_b + ch * 8, sb);
+    load8f(ss_b + C + ch * 8, hb);
   }
-  reinterpret_cast<uint4*>(act)[idx] = pack8(o);
+  const long long r0 = (long long)blockIdx.x * kRowsPerCta;
+  const long long r1 = min(rows_pad, r0 + kRowsPerCta);
+#pragma unroll 4
+  for (long long r = r0 + rl; r < r1; r += RL) {
+    const long long idx = r * CH + ch;
+    float o[8] = {};
+    if (row_is_valid((uint32_t)r, geo)) {
+      float a[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], sa[i], ha[i]);
+      if (DUAL) {
+        float b[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += fmaf(b[i], sb[i], hb[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+    }
+    reinterpret_cast<uint4*>(act)[idx] = pack8(o);
+  }
 }
 
 // pooled[f,c] = mean over the P*P valid rows of frame f of act[r,c]   (AdaptiveAvgPool2d(1), :240,254)
@@ -185,7 +204,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min((long long)geo.rows, r0 + rows_per_block);
+  // sum g*xhat = invstd * (sum g*x - mean * sum g): accumulate sum g*x and fix up once at the end
   float s0[8] = {}, s1[8] = {}, s2[8] = {};
+#pragma unroll 2
   for (long long r = r0 + rl; r < r1; r += RL) {
     float g[8];
     if (!load_g<C>(up_a, up_b, dpooled, act, r, ch, geo, g)) continue;
@@ -194,13 +215,26 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       s0[i] += g[i];
-      s1[i] = fmaf(g[i], (a[i] - mi_a[ch * 8 + i]) * mi_a[C + ch * 8 + i], s1[i]);
+      s1[i] = fmaf(g[i], a[i], s1[i]);
     }
     if (raw_b != nullptr) {
       float b[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + r * CH + ch), b);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s2[i] = fmaf(g[i], (b[i] - mi_b[ch * 8 + i]) * mi_b[C + ch * 8 + i], s2[i]);
+      for (int i = 0; i < 8; ++i) s2[i] = fmaf(g[i], b[i], s2[i]);
+    }
+  }
+  {
+    float m[8], iv[8];
+    load8f(mi_a + ch * 8, m);
+    load8f(mi_a + C + ch * 8, iv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = (s1[i] - m[i] * s0[i]) * iv[i];
+    if (raw_b != nullptr) {
+      load8f(mi_b + ch * 8, m);
+      load8f(mi_b + C + ch * 8, iv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s2[i] = (s2[i] - m[i] * s0[i]) * iv[i];
     }
   }
   __shared__ float red[3][RL][C + 1];
@@ -220,56 +254,70 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   }
 }
 
-// draw = gamma*invstd * (g - sum_g/cnt - xhat * sum_gx/cnt); also emits dgamma = sum_gx, dbeta = sum_g
-template <int C>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b,
-                                                           const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ act,
-                                                           const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mi_a,
-                                                           const float* __restrict__ gamma_a, __nv_bfloat16* __restrict__ draw_a,
-                                                           const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mi_b,
-                                                           const float* __restrict__ gamma_b, __nv_bfloat16* __restrict__ draw_b,
-                                                           const float* __restrict__ sums, RowGeom geo, long long rows_pad, float inv_count) {
-  constexpr int CH = C / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows_pad * CH) return;
-  const long long r = idx / CH;
-  const int ch = (int)(idx - r * CH);
-  float oa[8] = {}, ob[8] = {};
-  float g[8];
-  if (load_g<C>(up_a, up_b, dpooled, act, r, ch, geo, g)) {
-    float a[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = ch * 8 + i;
-      const float xh = (a[i] - mi_a[c]) * mi_a[C + c];
-      oa[i] = gamma_a[c] * mi_a[C + c] * (g[i] - sums[c] * inv_count - xh * sums[C + c] * inv_count);
-    }
-    if (raw_b != nullptr) {
-      float b[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = ch * 8 + i;
-        const float xh = (b[i] - mi_b[c]) * mi_b[C + c];
-        ob[i] = gamma_b[c] * mi_b[C + c] * (g[i] - sums[c] * inv_count - xh * sums[2 * C + c] * inv_count);
-      }
-    }
-  }
-  reinterpret_cast<uint4*>(draw_a)[idx] = pack8(oa);
-  if (raw_b != nullptr) reinterpret_cast<uint4*>(draw_b)[idx] = pack8(ob);
-}
-
-// dgamma_a = sums[1], dbeta_a = sums[0]; dgamma_b = sums[2], dbeta_b = sums[0]
-__global__ void bn_param_grads_kernel(const float* __restrict__ sums, float* __restrict__ dgamma_a, float* __restrict__ dbeta_a,
-                                      float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, int C) {
+// draw = gamma*invstd * (g - sum_g/cnt - xhat * sum_gx/cnt)  =  k1*g + k2*raw + k3  with per-channel
+//   k1 = gamma*invstd,  k2 = -k1*invstd*sum_gx/cnt,  k3 = -k1*sum_g/cnt - k2*mean
+// (coef = [k1 | k2 | k3] per BatchNorm, written by bn_bwd_coef_kernel).
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ mi_a, const float* __restrict__ gamma_a,
+                                   const float* __restrict__ mi_b, const float* __restrict__ gamma_b, float* __restrict__ coef_a,
+                                   float* __restrict__ coef_b, float* __restrict__ dgamma_a, float* __restrict__ dbeta_a,
+                                   float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, int C, float inv_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  dgamma_a[c] = sums[C + c];
-  dbeta_a[c] = sums[c];
-  if (dgamma_b) {
+  {
+    const float k1 = gamma_a[c] * mi_a[C + c];
+    const float k2 = -k1 * mi_a[C + c] * sums[C + c] * inv_count;
+    coef_a[c] = k1; coef_a[C + c] = k2; coef_a[2 * C + c] = -k1 * sums[c] * inv_count - k2 * mi_a[c];
+    dgamma_a[c] = sums[C + c];
+    dbeta_a[c] = sums[c];
+  }
+  if (mi_b != nullptr) {
+    const float k1 = gamma_b[c] * mi_b[C + c];
+    const float k2 = -k1 * mi_b[C + c] * sums[2 * C + c] * inv_count;
+    coef_b[c] = k1; coef_b[C + c] = k2; coef_b[2 * C + c] = -k1 * sums[c] * inv_count - k2 * mi_b[c];
     dgamma_b[c] = sums[2 * C + c];
     dbeta_b[c] = sums[c];
+  }
+}
+
+template <int C, bool DUAL>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b,
+                                                           const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ act,
+                                                           const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ coef_a,
+                                                           __nv_bfloat16* __restrict__ draw_a, const __nv_bfloat16* __restrict__ raw_b,
+                                                           const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ draw_b,
+                                                           RowGeom geo, long long rows_pad) {
+  constexpr int CH = C / 8, RL = 256 / CH;
+  const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
+  float a1[8], a2[8], a3[8], b1[8], b2[8], b3[8];
+  load8f(coef_a + ch * 8, a1);
+  load8f(coef_a + C + ch * 8, a2);
+  load8f(coef_a + 2 * C + ch * 8, a3);
+  if (DUAL) {
+    load8f(coef_b + ch * 8, b1);
+    load8f(coef_b + C + ch * 8, b2);
+    load8f(coef_b + 2 * C + ch * 8, b3);
+  }
+  const long long r0 = (long long)blockIdx.x * kRowsPerCta;
+  const long long r1 = min(rows_pad, r0 + kRowsPerCta);
+#pragma unroll 2
+  for (long long r = r0 + rl; r < r1; r += RL) {
+    const long long idx = r * CH + ch;
+    float oa[8] = {}, ob[8] = {};
+    float g[8];
+    if (load_g<C>(up_a, up_b, dpooled, act, r, ch, geo, g)) {
+      float a[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) oa[i] = fmaf(a1[i], g[i], fmaf(a2[i], a[i], a3[i]));
+      if (DUAL) {
+        float b[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ob[i] = fmaf(b1[i], g[i], fmaf(b2[i], b[i], b3[i]));
+      }
+    }
+    reinterpret_cast<uint4*>(draw_a)[idx] = pack8(oa);
+    if (DUAL) reinterpret_cast<uint4*>(draw_b)[idx] = pack8(ob);
   }
 }
 
@@ -380,8 +428,13 @@ int bn_finalize(const float* stats, const float* gamma, const float* beta, float
 int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b,
              __nv_bfloat16* act, long long rows, long long rows_pad, int P, int C, cudaStream_t st) {
   MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
-  const long long n = rows_pad * (C / 8);
-  BN_DISPATCH_C(C, (bn_apply_kernel<CC><<<mivit_ceil_div(n, 256), 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, make_geom(rows, P), rows_pad)));
+  const int blocks = mivit_ceil_div(rows_pad, kRowsPerCta);
+  const RowGeom geo = make_geom(rows, P);
+  if (raw_b != nullptr) {
+    BN_DISPATCH_C(C, (bn_apply_kernel<CC, true><<<blocks, 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, geo, rows_pad)));
+  } else {
+    BN_DISPATCH_C(C, (bn_apply_kernel<CC, false><<<blocks, 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, geo, rows_pad)));
+  }
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -398,21 +451,30 @@ int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P
 int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* act,
                 const __nv_bfloat16* raw_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a,
                 float* dbeta_a, const __nv_bfloat16* raw_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
-                float* dgamma_b, float* dbeta_b, float* sums /*[3][C] scratch*/, long long rows, long long rows_pad, int P, int C,
+                float* dgamma_b, float* dbeta_b, float* sums /*[9][C] scratch: sums | coef_a | coef_b*/, long long rows, long long rows_pad, int P, int C,
                 double count, cudaStream_t st) {
   MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
-  const int rpb = 4096;
+  const int rpb = 2048;
   const int blocks = mivit_ceil_div(rows, rpb);
   BN_DISPATCH_C(C, (bn_bwd_reduce_kernel<CC><<<blocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, raw_b, mi_b, sums, make_geom(rows, P), rpb)));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
-  const long long n = rows_pad * (C / 8);
-  BN_DISPATCH_C(C, (bn_bwd_apply_kernel<CC><<<mivit_ceil_div(n, 256), 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, gamma_a, draw_a,
-                                                                                   raw_b, mi_b, gamma_b, draw_b, sums, make_geom(rows, P), rows_pad,
-                                                                                   (float)(1.0 / count))));
+  // sums -> coefficient form + parameter gradients (C threads), then the streaming pass
+  float* coef_a = sums + 3 * C;
+  float* coef_b = sums + 6 * C;
+  bn_bwd_coef_kernel<<<mivit_ceil_div(C, 128), 128, 0, st>>>(sums, mi_a, gamma_a, raw_b ? mi_b : nullptr, gamma_b, coef_a, coef_b,
+                                                             dgamma_a, dbeta_a, dgamma_b, dbeta_b, C, (float)(1.0 / count));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
-  bn_param_grads_kernel<<<mivit_ceil_div(C, 128), 128, 0, st>>>(sums, dgamma_a, dbeta_a, raw_b ? dgamma_b : nullptr, dbeta_b, C);
+  const int ablocks = mivit_ceil_div(rows_pad, kRowsPerCta);
+  const RowGeom geo = make_geom(rows, P);
+  if (raw_b != nullptr) {
+    BN_DISPATCH_C(C, (bn_bwd_apply_kernel<CC, true><<<ablocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, coef_a, draw_a, raw_b, coef_b,
+                                                                             draw_b, geo, rows_pad)));
+  } else {
+    BN_DISPATCH_C(C, (bn_bwd_apply_kernel<CC, false><<<ablocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, coef_a, draw_a, raw_b, coef_b,
+                                                                              draw_b, geo, rows_pad)));
+  }
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

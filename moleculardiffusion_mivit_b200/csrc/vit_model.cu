@@ -165,7 +165,7 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
       w.bn[i].C = bc[i];
       w.bn[i].stats = b.take<float>(2 * bc[i]); w.bn[i].mi = b.take<float>(2 * bc[i]); w.bn[i].ss = b.take<float>(2 * bc[i]);
     }
-    w.bn_sums = b.take<float>(3 * 128);
+    w.bn_sums = b.take<float>(9 * 128);
     w.pooled = b.take<float>(NF * 128); w.dpooled = b.take<float>(NF * 128);
   }
   w.emb = b.take<float>(NF * E); w.m0 = b.take<float>(NF); w.r0 = b.take<float>(NF);
