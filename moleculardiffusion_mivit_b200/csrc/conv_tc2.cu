@@ -73,7 +73,7 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
   using C = Cfg2<CIN, NS, SKIP>;
   constexpr int taps = TAPS;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int slab_bytes = (C::kCH * slab_rows * 16 + 127) & ~127;
   uint8_t* wsm = smem;                                   // [taps][CH][NS][8]
   uint8_t* wsk = wsm + taps * CIN * NS * 2;              // [CH][NS][8]           (SKIP)
@@ -168,8 +168,7 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
       umma::mbar_wait(full + buf, ph);
       umma::mbar_wait(tempty + buf, ph ^ 1);
       umma::fence_after_sync();
-      {
-        const uint32_t lead = lane == 0 ? 1u : 0u;
+      if (umma::elect_one()) {
         const uint32_t a_lo0 = (uint32_t)da_base[buf];
         const uint32_t b_lo0 = (uint32_t)db_base;
         const uint32_t acc = tmem + (uint32_t)(buf * C::kAccCols);
@@ -180,7 +179,7 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
           for (int j = 0; j < CIN / 16; ++j) {
             const uint64_t da = ((uint64_t)a_hi << 32) | a_lo;
             const uint64_t db = ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)((t * C::kCH + 2 * j) * NS));
-            umma::mma_bf16_lead(acc, da, db, idesc, (t > 0 || j > 0) ? 1u : 0u, lead);
+            umma::mma_bf16(acc, da, db, idesc, (t > 0 || j > 0) ? 1u : 0u);
             a_lo += a_kstep;
           }
         }
@@ -191,12 +190,12 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
           for (int j = 0; j < CIN / 16; ++j) {
             const uint64_t da = ((uint64_t)a_hi << 32) | a_lo;
             const uint64_t db = ((uint64_t)b_hi << 32) | (bs_lo0 + (uint32_t)((2 * j) * NS));
-            umma::mma_bf16_lead(acc + NS, da, db, idesc, j > 0 ? 1u : 0u, lead);
+            umma::mma_bf16(acc + NS, da, db, idesc, j > 0 ? 1u : 0u);
             a_lo += a_kstep;
           }
         }
-        umma::commit_lead(empty + buf, lead);   // slab may be refilled once these MMAs have read it
-        umma::commit_lead(tfull + buf, lead);   // accumulator ready for the epilogue
+        umma::commit(empty + buf);   // slab may be refilled once these MMAs have read it
+        umma::commit(tfull + buf);   // accumulator ready for the epilogue
       }
       __syncwarp();
     }

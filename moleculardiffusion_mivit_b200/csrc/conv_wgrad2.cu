@@ -38,7 +38,7 @@ conv_wgrad_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* 
                       int n_stages, int stages_per_cta, int taps, ConvShifts shifts, int halo, int xslab_rows, int buf_bytes) {
   using C = WgCfg2<CIN, COUT>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   // buffer b: [A slab (dY) | B slab (X)]; the M = 128 over-read of a 64-channel A slab lands in the B slab
   uint8_t* buf0 = smem;
   uint8_t* buf1 = smem + buf_bytes;
@@ -107,21 +107,22 @@ conv_wgrad_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* 
       const uint32_t a_hi = (uint32_t)(da_b[0] >> 32), b_hi = (uint32_t)(db_b[0] >> 32);
       const int dl = shifts.d[tap0 + t];
       const uint32_t acc = tmem + (uint32_t)(t * CIN);
-      const uint32_t lead = lane == 0 ? 1u : 0u;
       int k = 0;
       for (int s = s_begin; s < s_end; ++s, ++k) {
         const int b = k & 1;
         umma::mbar_wait(full + b, (k >> 1) & 1);
         umma::fence_after_sync();
-        const uint32_t a_lo0 = (uint32_t)da_b[b], bt = (uint32_t)db_b[b] + (uint32_t)dl;
+        if (umma::elect_one()) {
+          const uint32_t a_lo0 = (uint32_t)da_b[b], bt = (uint32_t)db_b[b] + (uint32_t)dl;
 #pragma unroll
-        for (int kk = 0; kk < kStageRows / 16; ++kk) {
-          const uint64_t da = ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(kk * 16));
-          const uint64_t db = ((uint64_t)b_hi << 32) | (bt + (uint32_t)(kk * 16));
-          umma::mma_bf16_lead(acc, da, db, idesc, (k > 0 || kk > 0) ? 1u : 0u, lead);
+          for (int kk = 0; kk < kStageRows / 16; ++kk) {
+            const uint64_t da = ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(kk * 16));
+            const uint64_t db = ((uint64_t)b_hi << 32) | (bt + (uint32_t)(kk * 16));
+            umma::mma_bf16(acc, da, db, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma::commit(empty + b);
+          if (s == s_end - 1) umma::commit(done);
         }
-        umma::commit_lead(empty + b, lead);
-        if (s == s_end - 1) umma::commit_lead(done, lead);
         __syncwarp();
       }
     }

@@ -8,6 +8,22 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Warp-uniform warp index: the shuffle makes ptxas treat role branches as warp-uniform, which is what
+// allows the uniform datapath (UIADD3/UMOV + UTCHMMA, ~3 instructions per MMA) inside the issuing role.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// one elected lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layouts --------
 // Units of 16 bytes.  Core matrix = 8 x 16 B = 128 contiguous bytes.
 //   K-major  operand: rows (M/N) 16 B apart inside a core matrix; SBO = stride between 8-row
