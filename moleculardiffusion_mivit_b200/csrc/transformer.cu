@@ -229,6 +229,126 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const float* __restr
   }
 }
 
+// ---- sequence-per-CTA variants (S <= 64): one warp per head, lanes over query rows; 4x the thread
+// utilisation of the (sequence, head)-per-CTA kernels above for S = 31.
+template <int D>
+__global__ void __launch_bounds__(256) attention_fwd_seq_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                const float* __restrict__ v, float* __restrict__ ctx,
+                                                                float* __restrict__ probs, int S, int E, int H, float scale) {
+  extern __shared__ float sm[];
+  float* Ks = sm;            // [S][E]
+  float* Vs = sm + S * E;    // [S][E]
+  const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t base = (size_t)b * S * E;
+  for (int i = threadIdx.x; i < S * E; i += blockDim.x) {
+    Ks[i] = k[base + i];
+    Vs[i] = v[base + i];
+  }
+  __syncthreads();
+  if (h >= H) return;
+  for (int i = lane; i < S; i += 32) {
+    float qi[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) qi[c] = q[base + (size_t)i * E + h * D + c] * scale;
+    float mx = -INFINITY;
+    for (int j = 0; j < S; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a = fmaf(qi[c], Ks[j * E + h * D + c], a);
+      mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a = fmaf(qi[c], Ks[j * E + h * D + c], a);
+      sum += expf(a - mx);
+    }
+    const float inv = 1.0f / sum;
+    float o[D] = {};
+    float* prow = probs + (((size_t)b * H + h) * S + i) * S;
+    for (int j = 0; j < S; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a = fmaf(qi[c], Ks[j * E + h * D + c], a);
+      const float p = expf(a - mx) * inv;
+      prow[j] = p;
+#pragma unroll
+      for (int c = 0; c < D; ++c) o[c] = fmaf(p, Vs[j * E + h * D + c], o[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) ctx[base + (size_t)i * E + h * D + c] = o[c];
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) attention_bwd_seq_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                const float* __restrict__ v, const float* __restrict__ probs,
+                                                                const float* __restrict__ dctx, float* __restrict__ dq,
+                                                                float* __restrict__ dk, float* __restrict__ dv, int S, int E,
+                                                                int H, float scale) {
+  extern __shared__ float sm[];
+  float* Qs = sm;                 // [S][E]
+  float* Ks = Qs + S * E;
+  float* Vs = Ks + S * E;
+  float* Gs = Vs + S * E;         // dctx
+  float* PD = Gs + S * E;         // per head: P [S][S+1] then dS [S][S+1]
+  const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t base = (size_t)b * S * E;
+  for (int i = threadIdx.x; i < S * E; i += blockDim.x) {
+    Qs[i] = q[base + i];
+    Ks[i] = k[base + i];
+    Vs[i] = v[base + i];
+    Gs[i] = dctx[base + i];
+  }
+  float* Ps = PD + (size_t)h * 2 * S * (S + 1);
+  float* Ds = Ps + S * (S + 1);
+  if (h < H)
+    for (int i = lane; i < S * S; i += 32) Ps[(i / S) * (S + 1) + (i % S)] = probs[((size_t)b * H + h) * S * S + i];
+  __syncthreads();
+  if (h >= H) return;
+  const int hc = h * D;
+  for (int i = lane; i < S; i += 32) {
+    float gi[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) gi[c] = Gs[i * E + hc + c];
+    float rowdot = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float dp = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) dp = fmaf(gi[c], Vs[j * E + hc + c], dp);
+      Ds[i * (S + 1) + j] = dp;
+      rowdot = fmaf(dp, Ps[i * (S + 1) + j], rowdot);
+    }
+    float a[D] = {};
+    for (int j = 0; j < S; ++j) {
+      const float ds = Ps[i * (S + 1) + j] * (Ds[i * (S + 1) + j] - rowdot);
+      Ds[i * (S + 1) + j] = ds;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a[c] = fmaf(ds, Ks[j * E + hc + c], a[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) dq[base + (size_t)i * E + hc + c] = a[c] * scale;
+  }
+  __syncwarp();
+  for (int j = lane; j < S; j += 32) {
+    float ak[D] = {}, av[D] = {};
+    for (int i = 0; i < S; ++i) {
+      const float ds = Ds[i * (S + 1) + j], p = Ps[i * (S + 1) + j];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        ak[c] = fmaf(ds, Qs[i * E + hc + c], ak[c]);
+        av[c] = fmaf(p, Gs[i * E + hc + c], av[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      dk[base + (size_t)j * E + hc + c] = ak[c] * scale;
+      dv[base + (size_t)j * E + hc + c] = av[c];
+    }
+  }
+}
+
 // ---------------------------------------------------------------- activations -----------
 __device__ __forceinline__ float act_apply(float x, int mode) {
   if (mode == 0) return fmaxf(x, 0.f);
@@ -264,20 +384,23 @@ __global__ void tokens_finish_kernel(float* __restrict__ tok, const float* __res
   if (pos != nullptr) v += pos[(size_t)s * E + c];
   tok[i] = v;
 }
-// dreg[c] = sum_b dtok[b,0,c]; dproj[b,c] = dtok[b,0,c]; dpos[s,c] = sum_b dtok[b,s,c]
+// dreg[c] += sum_b dtok[b,0,c]; dproj[b,c] = dtok[b,0,c]; dpos[s,c] += sum_b dtok[b,s,c]
+// (gradient buffers are pre-zeroed; blockIdx.y splits the batch, partial sums go through atomics)
 __global__ void tokens_finish_bwd_kernel(const float* __restrict__ dtok, float* __restrict__ dreg, float* __restrict__ dproj,
-                                         float* __restrict__ dpos, int B, int S, int E) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over S*E
-  if (i >= S * E) return;
+                                         float* __restrict__ dpos, int B, int S, int E, int b_chunk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over S*E (or E when only the regression token matters)
+  const int cols = dpos != nullptr ? S * E : E;
+  if (i >= cols) return;
   const int c = i % E, s = i / E;
+  const int b0 = blockIdx.y * b_chunk, b1 = min(B, b0 + b_chunk);
   float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = b0; b < b1; ++b) {
     const float g = dtok[((size_t)b * S + s) * E + c];
     acc += g;
     if (dproj != nullptr && s == 0) dproj[(size_t)b * E + c] = g;
   }
-  if (dpos != nullptr) dpos[i] = acc;
-  if (dreg != nullptr && s == 0) dreg[c] = acc;
+  if (dpos != nullptr) atomicAdd(dpos + i, acc);
+  if (dreg != nullptr && s == 0) atomicAdd(dreg + c, acc);
 }
 
 // out[b,:] = x[b,0,:] (use_reg) or mean_s x[b,s,:]; written at out[b*ld + c]
@@ -347,6 +470,15 @@ int layernorm_bwd(const float* dy, const float* z, const float* mean, const floa
 template <int D>
 static int attention_fwd_d(const float* q, const float* k, const float* v, float* ctx, float* probs, int B, int S, int E,
                            int H, cudaStream_t st) {
+  if (S <= 64 && H <= 8) {
+    const size_t smem = (size_t)2 * S * E * sizeof(float);
+    auto kern = attention_fwd_seq_kernel<D>;
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, 32 * H, smem, st>>>(q, k, v, ctx, probs, S, E, H, 1.0f / sqrtf((float)D));
+    mivit_count_launch();
+    MIVIT_LAUNCH_CHECK();
+    return MIVIT_OK;
+  }
   const size_t smem = (size_t)(2 * S * (D + 1) + S * (S + 1)) * sizeof(float);
   auto kern = attention_fwd_kernel<D>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -358,6 +490,17 @@ static int attention_fwd_d(const float* q, const float* k, const float* v, float
 template <int D>
 static int attention_bwd_d(const float* q, const float* k, const float* v, const float* probs, const float* dctx, float* dq,
                            float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st) {
+  if (S <= 64 && H <= 8) {
+    const size_t smem = (size_t)(4 * S * E + 2 * H * S * (S + 1)) * sizeof(float);
+    if (smem <= 200 * 1024) {
+      auto kern = attention_bwd_seq_kernel<D>;
+      MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<B, 32 * H, smem, st>>>(q, k, v, probs, dctx, dq, dk, dv, S, E, H, 1.0f / sqrtf((float)D));
+      mivit_count_launch();
+      MIVIT_LAUNCH_CHECK();
+      return MIVIT_OK;
+    }
+  }
   const size_t smem = (size_t)(4 * S * (D + 1) + 2 * S * (S + 1)) * sizeof(float);
   auto kern = attention_bwd_kernel<D>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -406,8 +549,12 @@ int tokens_finish(float* tok, const float* reg, const float* proj, const float* 
 }
 int tokens_finish_bwd(const float* dtok, float* dreg, float* dproj, float* dpos, int B, int S, int E, cudaStream_t st) {
   if (dreg == nullptr && dpos == nullptr && dproj == nullptr) return MIVIT_OK;
-  const long long n = (long long)S * E;
-  LAUNCH_1D(tokens_finish_bwd_kernel, n, dtok, dreg, dproj, dpos, B, S, E);
+  const int cols = dpos != nullptr ? S * E : E;
+  const int b_chunk = 32;
+  dim3 grid(mivit_ceil_div(cols, 128), mivit_ceil_div(B, b_chunk));
+  tokens_finish_bwd_kernel<<<grid, 128, 0, st>>>(dtok, dreg, dproj, dpos, B, S, E, b_chunk);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
 }
 int pool_tokens(const float* x, float* out, int B, int S, int E, int ld, int use_reg, cudaStream_t st) {
