@@ -129,6 +129,14 @@ int mivit_conv_rows_fused(const void* X_row0, const void* Wp, const void* Wskip,
 int mivit_conv_rows_wgrad(const void* X_row0, const void* dY_row0, float* dW, int64_t rows, int32_t P,
                           int32_t cin, int32_t cout, int32_t ksize, int32_t impl, void* stream);
 
+/* nn.Linear (helpers/models.py:20-23,64-65,241,268-273) on tcgen05 kind::tf32, fp32 in / fp32 out.
+ *   mode 0: out[M,out_f] = A[M,in_f] W[out_f,in_f]^T + bias (relu)
+ *   mode 1: out[M,in_f] (+)= A[M,out_f] W[out_f,in_f]                (input gradient)
+ *   mode 2: out[out_f,in_f] += A[M,out_f]^T W'[M,in_f]               (weight gradient; W' = layer input)
+ * Fails for shapes outside the tensor-core kernels' range (M >= 512, features multiples of 32, <= 256). */
+int mivit_linear_tf32(int32_t mode, const float* A, const float* W, const float* bias, float* out, int32_t M,
+                      int32_t in_features, int32_t out_features, int32_t relu, int32_t accumulate, void* stream);
+
 /* ---------------------------------------------------------------- ViT -------------------- */
 
 /* Replaces helpers/models.py:278-361 GeneralTransformer (+ its embedding classes :146-257,

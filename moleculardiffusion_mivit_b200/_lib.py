@@ -50,6 +50,7 @@ def _declare(lib):
         "mivit_conv_rows": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]),
         "mivit_conv_rows_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
         "mivit_conv_rows_wgrad": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
+        "mivit_linear_tf32": (i32, [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "mivit_vit_param_count": (i32, [vp]),
         "mivit_vit_param_sizes": (i32, [vp, c.POINTER(c.c_int64), i32]),
         "mivit_vit_workspace_bytes": (i64, [vp, i32]),

@@ -78,3 +78,22 @@ extern "C" int mivit_conv_rows_fused(const void* X_row0, const void* Wp, const v
                                  (__nv_bfloat16*)Y_row0, (__nv_bfloat16*)Yskip_row0, stats, stats_skip, rows, P, cin, cout, 9, sh,
                                  impl, (cudaStream_t)stream);
 }
+
+// nn.Linear building blocks on the tf32 tensor path (tests / ViT).  mode 0: Y = X W^T + b (relu);
+// mode 1: dX (+)= dY W;  mode 2: dW += dY^T X.  Returns an error when the shape is not supported by the
+// tensor-core kernels (the ViT then uses its fp32 SIMT GEMM).
+extern "C" int mivit_linear_tf32(int32_t mode, const float* A, const float* W, const float* bias, float* out, int32_t M,
+                                 int32_t in_features, int32_t out_features, int32_t relu, int32_t accumulate, void* stream) {
+  MIVIT_CHECK_ARG(A && W && out, "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) {
+    MIVIT_CHECK_ARG(linear_tc_supported(M, in_features, out_features), "shape not supported by the tf32 linear kernel");
+    return linear_tc(A, W, bias, out, M, in_features, out_features, 0, relu, 0, st);
+  }
+  if (mode == 1) {
+    MIVIT_CHECK_ARG(linear_tc_supported(M, out_features, in_features), "shape not supported by the tf32 linear kernel");
+    return linear_tc(A, W, nullptr, out, M, out_features, in_features, 1, 0, accumulate, st);
+  }
+  MIVIT_CHECK_ARG(mode == 2 && linear_wgrad_tc_supported(M, out_features, in_features), "shape not supported by the tf32 wgrad kernel");
+  return linear_wgrad_tc(A, W, out, M, out_features, in_features, st);  // A = dY [M,out], W = X [M,in], out = dW [out,in]
+}

@@ -137,6 +137,18 @@ conv_rows_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* _
         const int r = i / C::kCH, c = i - r * C::kCH;
         cp_async16(slab + ((size_t)c * slab_rows + r) * 16, src + i);
       }
+      // L2 prefetch of the slab two work items ahead: only two slabs fit next to the resident weights, so
+      // the cp.async of a slab cannot be issued earlier than one item ahead; pulling the lines into L2
+      // now turns its HBM latency (~1 us) into an L2 hit.
+      {
+        const int tile2 = tile + 2 * ctas_per_slice;
+        if (tile2 < n_tiles) {
+          const char* p2 = reinterpret_cast<const char*>(X + ((long long)tile2 * kTileM - halo) * CIN);
+          const int lines = (slab_rows * CIN * 2 + 127) / 128;
+          for (int i = pt; i < lines; i += kProducerWarps * 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + (size_t)i * 128));
+        }
+      }
       cp_async_wait_all();
       umma::fence_proxy_async();
       __syncwarp();

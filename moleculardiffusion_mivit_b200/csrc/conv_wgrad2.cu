@@ -88,6 +88,13 @@ conv_wgrad_tc2_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* 
         const int r = i / C::kBChunks, c = i - r * C::kBChunks;
         cp_async16w(bslab + ((size_t)c * xslab_rows + r) * 16, srcb + i);
       }
+      if (s + 2 < s_end) {  // L2 prefetch two stages ahead (see conv_tc2.cu)
+        const char* pa = reinterpret_cast<const char*>(dY + (r0 + 2 * kStageRows) * COUT);
+        const char* pb = reinterpret_cast<const char*>(X + (r0 + 2 * kStageRows - halo) * CIN);
+        const int la = kStageRows * COUT * 2 / 128, lb = (xslab_rows * CIN * 2 + 127) / 128;
+        for (int i = pt; i < la + lb; i += kProducerWarps * 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(i < la ? pa + (size_t)i * 128 : pb + (size_t)(i - la) * 128));
+      }
       cp_async_wait_allw();
       umma::fence_proxy_async();
       __syncwarp();

@@ -1,0 +1,342 @@
+// nn.Linear forward / input-gradient / weight-gradient of the transformer stack and heads
+// (reference helpers/models.py:20-23,64-65,241,268-273) on tcgen05 with kind::tf32: the fp32
+// activations and weights are consumed directly as TF32 operands (no conversion pass, no packed
+// copies), accumulators are fp32 in TMEM.  Same machinery as the convolutions (conv_tc2.cu):
+// 128-token row slabs in the no-swizzle core-matrix order [chunk of 4 floats][row][16 B] filled with
+// cp.async, double-buffered slabs and accumulators, resident weights, one elected issuing thread.
+//   forward  Y[M,N]  = X[M,K] W[N,K]^T (+bias)(relu)    W is the K-major  B operand
+//   dgrad    dX[M,N] = dY[M,K] W[K,N]  (+= optional)    W is the MN-major B operand
+//   wgrad    dW[N,K] += dY[M,N]^T X[M,K]                both operands MN-major, rows = reduction
+// These GEMMs are HBM-bound (K, N <= 256 on 30k+ tokens): the point of the tensor path is to get the
+// math out of the way so the kernel streams at memory speed.
+#include "common.cuh"
+#include "umma.cuh"
+#include "vit.h"
+
+namespace {
+
+constexpr int kRows = 128;
+
+__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(mbar)) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ------------------------------------------------------------------ forward / dgrad -------------
+// warps 0-3 epilogue, warp 4 MMA issuer, warps 5-7 producers.
+template <bool BMN>
+__global__ void __launch_bounds__(256, 1)
+linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ Y,
+                 int M, int K, int N, int n_tiles, int relu, int accumulate) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
+  const int kch = K / 4;                       // 16-byte chunks along the reduction dim of A
+  const int slab_bytes = kch * kRows * 16;
+  uint8_t* wsm = smem;                         // K-major: [K/4][N][16B]   MN-major: [N/4][K][16B]
+  uint8_t* slab0 = wsm + (size_t)K * N * 4;
+  uint8_t* slab1 = slab0 + slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slab1 + slab_bytes);
+  uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(full + i, 3);
+      umma::mbar_init(empty + i, 1);
+      umma::mbar_init(tfull + i, 1);
+      umma::mbar_init(tempty + i, 4);
+    }
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  if (!BMN) {  // W[N][K] -> [K/4][N][16B]
+    for (int i = tid; i < kch * N; i += 256) {
+      const int n = i / kch, c = i - n * kch;
+      *reinterpret_cast<uint4*>(wsm + ((size_t)c * N + n) * 16) = __ldg(reinterpret_cast<const uint4*>(W) + i);
+    }
+  } else {     // W[K][N] -> [N/4][K][16B]
+    const int nch = N / 4;
+    for (int i = tid; i < nch * K; i += 256) {
+      const int k = i / nch, c = i - k * nch;
+      *reinterpret_cast<uint4*>(wsm + ((size_t)c * K + k) * 16) = __ldg(reinterpret_cast<const uint4*>(W) + i);
+    }
+  }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int acc_cols = N <= 256 ? 256 : 256;   // two accumulators, 256 columns apart
+
+  if (warp >= 5) {
+    const int pt = (warp - 5) * 32 + lane;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+      const int buf = k & 1;
+      umma::mbar_wait(empty + buf, ((k >> 1) & 1) ^ 1);
+      uint8_t* slab = buf ? slab1 : slab0;
+      const long long m0 = (long long)tile * kRows;
+      const int rows_here = min(kRows, M - (int)m0);
+      const uint4* src = reinterpret_cast<const uint4*>(A + m0 * K);
+      for (int i = pt; i < rows_here * kch; i += 96) {
+        const int r = i / kch, c = i - r * kch;
+        cp16(slab + ((size_t)c * kRows + r) * 16, src + i);
+      }
+      cp_wait_all();
+      umma::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) arrive(full + buf);
+    }
+  } else if (warp == 4) {
+    const uint32_t idesc = idesc_tf32(kRows, N, 0, BMN ? 1 : 0);
+    const uint64_t da_b[2] = {umma::make_desc(umma::smem_u32(slab0), (uint32_t)kRows * 16u, 128u),
+                              umma::make_desc(umma::smem_u32(slab1), (uint32_t)kRows * 16u, 128u)};
+    // K-major B: LBO = chunk stride (N*16), SBO = 128.   MN-major B: LBO = 128 (8-row k groups), SBO = K*16 (n chunks)
+    const uint64_t db0 = BMN ? umma::make_desc(umma::smem_u32(wsm), 128u, (uint32_t)K * 16u)
+                             : umma::make_desc(umma::smem_u32(wsm), (uint32_t)N * 16u, 128u);
+    const uint32_t a_hi = (uint32_t)(da_b[0] >> 32), b_hi = (uint32_t)(db0 >> 32), b_lo0 = (uint32_t)db0;
+    const uint32_t a_step = 2u * kRows;                           // two 4-float chunks per K = 8 step
+    const uint32_t b_step = BMN ? 8u : 2u * (uint32_t)N;          // MN-major: 8 k-rows; K-major: 2 chunks
+    const int ksteps = K / 8;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+      const int buf = k & 1;
+      const uint32_t ph = (k >> 1) & 1;
+      umma::mbar_wait(full + buf, ph);
+      umma::mbar_wait(tempty + buf, ph ^ 1);
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        uint32_t a_lo = (uint32_t)da_b[buf], b_lo = b_lo0;
+        const uint32_t acc = tmem + (uint32_t)(buf * acc_cols);
+        for (int j = 0; j < ksteps; ++j) {
+          mma_tf32(acc, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, j > 0 ? 1u : 0u);
+          a_lo += a_step;
+          b_lo += b_step;
+        }
+        umma::commit(empty + buf);
+        umma::commit(tfull + buf);
+      }
+      __syncwarp();
+    }
+  } else {
+    int k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+      const int buf = k & 1;
+      umma::mbar_wait(tfull + buf, (k >> 1) & 1);
+      umma::fence_after_sync();
+      const long long r = (long long)tile * kRows + warp * 32 + lane;
+      const bool ok = r < M;
+      const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols);
+      float* dst = Y + r * N;
+      const int groups = N / 32;          // N % 32 == 0 on this path
+      for (int g = 0; g < groups; ++g) {
+        float v[32];
+        umma::tmem_ld32(acc + (uint32_t)(g * 32), v);
+        if (g == groups - 1) {
+          umma::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) arrive(tempty + buf);
+        }
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (bias != nullptr) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + g * 32) + q);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            float4* p = reinterpret_cast<float4*>(dst + g * 32) + q;
+            if (accumulate) {
+              const float4 old = *p;
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *p = o;
+          }
+        }
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------ weight gradient -------------
+// warps 0-3 producers + final flush, warp 4 MMA issuer, warps 5-7 producers.
+__global__ void __launch_bounds__(256, 1)
+linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ dW, int M, int N, int K,
+                       int n_stages, int stages_per_cta, int buf_bytes) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
+  const int nch = N / 4, kch = K / 4;
+  const int a_bytes = nch * kRows * 16;
+  uint8_t* buf0 = smem;
+  uint8_t* buf1 = smem + buf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * buf_bytes);
+  uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int s_begin = blockIdx.x * stages_per_cta;
+  const int s_end = min(n_stages, s_begin + stages_per_cta);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(full + i, 7);
+      umma::mbar_init(empty + i, 1);
+    }
+    umma::mbar_init(done, 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp != 4) {
+    const int pt = (warp < 4 ? warp : warp - 1) * 32 + lane;
+    int k = 0;
+    for (int s = s_begin; s < s_end; ++s, ++k) {
+      const int b = k & 1;
+      umma::mbar_wait(empty + b, ((k >> 1) & 1) ^ 1);
+      uint8_t* aslab = b ? buf1 : buf0;
+      uint8_t* bslab = aslab + a_bytes;
+      const long long r0 = (long long)s * kRows;
+      const int rows_here = min(kRows, M - (int)r0);
+      const uint4* srca = reinterpret_cast<const uint4*>(dY + r0 * N);
+      const uint4* srcb = reinterpret_cast<const uint4*>(X + r0 * K);
+      for (int i = pt; i < kRows * nch; i += 224) {
+        const int r = i / nch, c = i - r * nch;
+        uint8_t* d = aslab + ((size_t)c * kRows + r) * 16;
+        if (r < rows_here) cp16(d, srca + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      }
+      for (int i = pt; i < kRows * kch; i += 224) {
+        const int r = i / kch, c = i - r * kch;
+        uint8_t* d = bslab + ((size_t)c * kRows + r) * 16;
+        if (r < rows_here) cp16(d, srcb + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      }
+      cp_wait_all();
+      umma::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) arrive(full + b);
+    }
+  } else {
+    const uint32_t idesc = idesc_tf32(128, K, 1, 1);
+    // MN-major operands: LBO = 128 B (8-row groups of the reduction dim), SBO = chunk stride (128 rows * 16 B)
+    const uint64_t da_b[2] = {umma::make_desc(umma::smem_u32(buf0), 128u, (uint32_t)kRows * 16u),
+                              umma::make_desc(umma::smem_u32(buf1), 128u, (uint32_t)kRows * 16u)};
+    const uint64_t db_b[2] = {umma::make_desc(umma::smem_u32(buf0) + (uint32_t)a_bytes, 128u, (uint32_t)kRows * 16u),
+                              umma::make_desc(umma::smem_u32(buf1) + (uint32_t)a_bytes, 128u, (uint32_t)kRows * 16u)};
+    const uint32_t a_hi = (uint32_t)(da_b[0] >> 32), b_hi = (uint32_t)(db_b[0] >> 32);
+    int k = 0;
+    for (int s = s_begin; s < s_end; ++s, ++k) {
+      const int b = k & 1;
+      umma::mbar_wait(full + b, (k >> 1) & 1);
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        const uint32_t a_lo0 = (uint32_t)da_b[b], b_lo0 = (uint32_t)db_b[b];
+#pragma unroll
+        for (int kk = 0; kk < kRows / 8; ++kk)   // K = 8 rows per tf32 MMA
+          mma_tf32(tmem, ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(kk * 8)), ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)(kk * 8)),
+                   idesc, (k > 0 || kk > 0) ? 1u : 0u);
+        umma::commit(empty + b);
+        if (s == s_end - 1) umma::commit(done);
+      }
+      __syncwarp();
+    }
+  }
+  if (warp < 4 && s_end > s_begin) {
+    umma::mbar_wait(done, 0);
+    umma::fence_after_sync();
+    if (warp * 32 < N) {
+      const int n = warp * 32 + lane;
+      for (int cg = 0; cg < K / 32; ++cg) {
+        float v[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cg * 32), v);
+        if (n < N) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dW + (size_t)n * K + cg * 32 + i, v[i]);
+        }
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<256>(tmem);
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  return sms ? sms : 148;
+}
+
+}  // namespace
+
+bool linear_tc_supported(int M, int K, int N) {
+  return M >= 512 && K % 8 == 0 && N % 32 == 0 && K >= 8 && N >= 32 && N <= 256 && K <= 256 &&
+         (size_t)K * N * 4 + 2 * (size_t)(K / 4) * kRows * 16 + 256 <= 220 * 1024;
+}
+
+// mode 0: Y = A W^T (+bias)(relu), W [N][K].   mode 1: Y (+)= A W, W [K][N].
+int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M, int K, int N, int mode, int relu, int accumulate,
+              cudaStream_t st) {
+  int smem = K * N * 4 + 2 * (K / 4) * kRows * 16 + 256;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  const int n_tiles = (M + kRows - 1) / kRows;
+  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  MivitProfScope prof(mode ? "linear_tc_dgrad" : "linear_tc_fwd", 2.0 * M * K * N, st);
+  if (mode == 0) {
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    linear_tc_kernel<false><<<grid, 256, smem, st>>>(A, W, bias, Y, M, K, N, n_tiles, relu, accumulate);
+  } else {
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    linear_tc_kernel<true><<<grid, 256, smem, st>>>(A, W, bias, Y, M, K, N, n_tiles, relu, accumulate);
+  }
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+bool linear_wgrad_tc_supported(int M, int N, int K) {
+  // N = out_features (rows of dW, <= 128 lanes), K = in_features (TMEM columns)
+  size_t buf = (size_t)(N / 4 + K / 4) * kRows * 16;
+  if (buf < (size_t)32 * kRows * 16) buf = (size_t)32 * kRows * 16;
+  return M >= 512 && N % 4 == 0 && K % 32 == 0 && N >= 16 && N <= 128 && K >= 32 && K <= 256 && 2 * buf + 256 <= 220 * 1024;
+}
+
+// dW[N][K] += dY[M,N]^T X[M,K]   (dW pre-zeroed / holds the value to accumulate onto)
+int linear_wgrad_tc(const float* dY, const float* X, float* dW, int M, int N, int K, cudaStream_t st) {
+  // the M = 128 MMA over-reads the A slab up to 32 chunks: keep that inside the stage buffer
+  int buf_bytes = (N / 4 + K / 4) * kRows * 16;
+  const int need = 32 * kRows * 16;
+  if (buf_bytes < need) buf_bytes = need;
+  int smem = 2 * buf_bytes + 256;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int n_stages = (M + kRows - 1) / kRows;
+  int ctas = n_stages < sm_count() ? n_stages : sm_count();
+  const int spc = (n_stages + ctas - 1) / ctas;
+  ctas = (n_stages + spc - 1) / spc;
+  MivitProfScope prof("linear_tc_wgrad", 2.0 * M * K * N, st);
+  linear_wgrad_tc_kernel<<<ctas, 256, smem, st>>>(dY, X, dW, M, N, K, n_stages, spc, buf_bytes);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}

@@ -86,3 +86,10 @@ int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, lon
 int mse_loss(const float* pred, const float* target, int n, float* loss, float* dpred, cudaStream_t st);
 int adamw_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
                long long step, float grad_scale, cudaStream_t st);
+
+// linear_tc.cu -- tcgen05 kind::tf32 nn.Linear kernels
+bool linear_tc_supported(int M, int K, int N);
+int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M, int K, int N, int mode, int relu, int accumulate,
+              cudaStream_t st);
+bool linear_wgrad_tc_supported(int M, int N, int K);
+int linear_wgrad_tc(const float* dY, const float* X, float* dW, int M, int N, int K, cudaStream_t st);

@@ -189,23 +189,41 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
   w.bytes = (b.off + 255) & ~(size_t)255;
 }
 
+// tensor-core (tf32) nn.Linear kernels are used when the product path is selected (conv_impl == 1) and the
+// shape / alignment allows it; the fp32 SIMT GEMM otherwise (and always for the SIMT cross-check path).
+static thread_local int g_linear_tc = 0;
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // Y[M,N] = X[M,K] W[N,K]^T + b
 int linear_fwd(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, int relu, cudaStream_t st) {
+  if (g_linear_tc && linear_tc_supported(M, K, N) && al16(X) && al16(W) && al16(Y) && (bias == nullptr || al16(bias)))
+    return linear_tc(X, W, bias, Y, M, K, N, 0, relu, 0, st);
   return gemm_f32(X, K, 1, W, 1, K, Y, N, M, N, K, bias, relu, 0, 1, st);
 }
 // dW[N,K] += dY[M,N]^T X[M,K];  db[N] += colsum(dY);  dX[M,K] (=|+=) dY W
 int linear_bwd(const float* X, const float* W, const float* dY, float* dW, float* db, float* dX, int M, int N, int K,
                int accumulate_dx, cudaStream_t st) {
-  int split = M / 128;  // token-dimension split-K: enough CTAs to fill 148 SMs even for 64x64 outputs
-  if (split < 1) split = 1;
-  if (split > 296) split = 296;
-  if (split == 1) {
-    CK(gemm_f32(dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, 0, 1, 1, st));
+  if (g_linear_tc && linear_wgrad_tc_supported(M, N, K) && al16(X) && al16(dY) && al16(dW)) {
+    CK(linear_wgrad_tc(dY, X, dW, M, N, K, st));
   } else {
-    CK(gemm_f32(dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, 0, 0, split, st));
+    int split = M / 128;  // token-dimension split-K: enough CTAs to fill 148 SMs even for 64x64 outputs
+    if (split < 1) split = 1;
+    if (split > 296) split = 296;
+    if (split == 1) {
+      CK(gemm_f32(dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, 0, 1, 1, st));
+    } else {
+      CK(gemm_f32(dY, 1, N, X, K, 1, dW, K, N, K, M, nullptr, 0, 0, split, st));
+    }
   }
   if (db) CK(colsum_f32(dY, N, M, N, db, st));
-  if (dX) CK(gemm_f32(dY, N, 1, W, K, 1, dX, K, M, K, N, nullptr, 0, accumulate_dx, 1, st));
+  if (dX) {
+    // dX[M,K] = dY[M,N] W[N,K]: reduction dim N, output cols K, W is the MN-major operand [N][K]
+    if (g_linear_tc && linear_tc_supported(M, N, K) && al16(dY) && al16(W) && al16(dX)) {
+      CK(linear_tc(dY, W, nullptr, dX, M, N, K, 1, 0, accumulate_dx, st));
+    } else {
+      CK(gemm_f32(dY, N, 1, W, K, 1, dX, K, M, K, N, nullptr, 0, accumulate_dx, 1, st));
+    }
+  }
   return MIVIT_OK;
 }
 
@@ -263,6 +281,7 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
   carve(c, B, workspace, w);
+  g_linear_tc = c->conv_impl == 1;
   const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H, P = c->P;
   const int NF = B * F, T = B * S;
   const float* p = params;
@@ -355,6 +374,7 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
   const int NF = B * F, T = B * S, hin = L.head_in, hhid = c->head_hidden;
   const float* p = params;
   float* g = grads;
+  g_linear_tc = c->conv_impl == 1;
   MIVIT_CUDA_CHECK(cudaMemsetAsync(g, 0, (size_t)L.off * sizeof(float), st));
   // head
   CK(linear_bwd(w.hh, p + L.h3_w, dpred, g + L.h3_w, g + L.h3_b, w.dhh, B, 1, hhid, 0, st));

@@ -154,3 +154,29 @@ def test_second_step_and_launch_count(golden_dir):
     assert n1 > 100 and _lib.lib().mivit_launch_count() == 2 * n1
     assert np.isfinite(l1) and np.isfinite(l2) and l2 < l1          # same batch twice: the loss goes down
     assert int(model.embedding.bn1.num_batches_tracked) == 2
+
+
+@pytest.mark.parametrize("name", ["deepcnn_n", "linear_s_pos"])
+def test_product_path_matches_simt_path_at_batch_64(golden_dir, name):
+    """B = 64 sequences (1984 tokens): large enough for the tf32 tensor-core nn.Linear kernels and
+    multi-tile convolutions.  conv_impl = 1 (tcgen05 everywhere) vs conv_impl = 0 (fp32 SIMT GEMMs, SIMT convs)."""
+    import torch
+    z, sd, x, tgt, feats = load_case(golden_dir, name)
+    g = torch.Generator().manual_seed(3)
+    xb = x.repeat(16, 1, 1, 1) + 0.05 * torch.randn((64,) + tuple(x.shape[1:]), generator=g)
+    tb = torch.rand((64, 1), generator=g)
+    outs = []
+    for impl in (0, 1):
+        model = build(name)
+        model.load_state_dict(sd)
+        model.cuda().train()
+        model.conv_impl = impl
+        pred = model(xb.cuda())
+        ((pred - tb.cuda()) ** 2).mean().backward()
+        outs.append((pred.detach().cpu(), {k: p.grad.cpu() for k, p in model.named_parameters()}))
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-2
+    gmax = max(float(v.norm()) for v in outs[0][1].values())
+    for k in outs[0][1]:
+        a, b = outs[0][1][k], outs[1][1][k]
+        if float(a.norm()) > 1e-4 * gmax:
+            assert relnorm(b, a) < 5e-2, (k, relnorm(b, a))
