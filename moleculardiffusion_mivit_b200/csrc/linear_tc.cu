@@ -7,6 +7,10 @@
 //   forward  Y[M,N]  = X[M,K] W[N,K]^T (+bias)(relu)    W is the K-major  B operand
 //   dgrad    dX[M,N] = dY[M,K] W[K,N]  (+= optional)    W is the MN-major B operand
 //   wgrad    dW[N,K] += dY[M,N]^T X[M,K]                both operands MN-major, rows = reduction
+// MN-major TF32 operands: probed on B200 (scripts/probe_tf32_mn.cu), tcgen05.mma kind::tf32 returns zeros for
+// MN-major operands in every descriptor layout except SWIZZLE_128B_BASE32B (layout type 1), whose address map is
+//   byte(k, mn) = (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + (((mn%32)/8) ^ (k%4))*32 + (mn%8)*4
+// (atoms of 4 reduction rows x 32 MN elements, 32-byte chunks XOR-swizzled by the row).  mn_off() below is that map.
 // These GEMMs are HBM-bound (K, N <= 256 on 30k+ tokens): the point of the tensor path is to get the
 // math out of the way so the kernel streams at memory speed.
 #include "common.cuh"
@@ -23,6 +27,15 @@ __device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(mbar)) : "memory");
+}
+// byte offset of the 16-byte chunk holding MN elements [4j, 4j+4) of reduction row k (SBO = 512: row groups contiguous)
+__device__ __forceinline__ uint32_t mn_off(int k, int j, uint32_t lbo) {
+  const int mn = 4 * j;
+  return (uint32_t)(mn >> 5) * lbo + (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u +
+         (uint32_t)((((mn & 31) >> 3) ^ (k & 3)) << 5) + (uint32_t)((j & 1) << 4);
+}
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return umma::make_desc(smem_addr, lbo_bytes, 512u) | ((uint64_t)1 << 61);   // SWIZZLE_128B_BASE32B
 }
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -48,7 +61,7 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int kch = K / 4;                       // 16-byte chunks along the reduction dim of A
   const int slab_bytes = kch * kRows * 16;
-  uint8_t* wsm = smem;                         // K-major: [K/4][N][16B]   MN-major: [N/4][K][16B]
+  uint8_t* wsm = smem;                         // K-major: [K/4][N][16B]   MN-major: mn_off atoms
   uint8_t* slab0 = wsm + (size_t)K * N * 4;
   uint8_t* slab1 = slab0 + slab_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(slab1 + slab_bytes);
@@ -70,11 +83,11 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
       const int n = i / kch, c = i - n * kch;
       *reinterpret_cast<uint4*>(wsm + ((size_t)c * N + n) * 16) = __ldg(reinterpret_cast<const uint4*>(W) + i);
     }
-  } else {     // W[K][N] -> [N/4][K][16B]
+  } else {     // W[K][N] -> MN-major atoms (mn_off), 32-column groups K*128 bytes apart
     const int nch = N / 4;
     for (int i = tid; i < nch * K; i += 256) {
       const int k = i / nch, c = i - k * nch;
-      *reinterpret_cast<uint4*>(wsm + ((size_t)c * K + k) * 16) = __ldg(reinterpret_cast<const uint4*>(W) + i);
+      *reinterpret_cast<uint4*>(wsm + mn_off(k, c, (uint32_t)K * 128u)) = __ldg(reinterpret_cast<const uint4*>(W) + i);
     }
   }
   umma::fence_proxy_async();
@@ -107,12 +120,12 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
     const uint32_t idesc = idesc_tf32(kRows, N, 0, BMN ? 1 : 0);
     const uint64_t da_b[2] = {umma::make_desc(umma::smem_u32(slab0), (uint32_t)kRows * 16u, 128u),
                               umma::make_desc(umma::smem_u32(slab1), (uint32_t)kRows * 16u, 128u)};
-    // K-major B: LBO = chunk stride (N*16), SBO = 128.   MN-major B: LBO = 128 (8-row k groups), SBO = K*16 (n chunks)
-    const uint64_t db0 = BMN ? umma::make_desc(umma::smem_u32(wsm), 128u, (uint32_t)K * 16u)
+    // K-major B: LBO = chunk stride (N*16), SBO = 128.   MN-major B: SW128_BASE32B atoms, LBO = K*128 (32-column groups)
+    const uint64_t db0 = BMN ? make_desc_mn32(umma::smem_u32(wsm), (uint32_t)K * 128u)
                              : umma::make_desc(umma::smem_u32(wsm), (uint32_t)N * 16u, 128u);
     const uint32_t a_hi = (uint32_t)(da_b[0] >> 32), b_hi = (uint32_t)(db0 >> 32), b_lo0 = (uint32_t)db0;
     const uint32_t a_step = 2u * kRows;                           // two 4-float chunks per K = 8 step
-    const uint32_t b_step = BMN ? 8u : 2u * (uint32_t)N;          // MN-major: 8 k-rows; K-major: 2 chunks
+    const uint32_t b_step = BMN ? 64u : 2u * (uint32_t)N;         // MN-major: 8 k-rows = 1024 B; K-major: 2 chunks
     const int ksteps = K / 8;
     int k = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
@@ -223,12 +236,12 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
       const uint4* srcb = reinterpret_cast<const uint4*>(X + r0 * K);
       for (int i = pt; i < kRows * nch; i += 224) {
         const int r = i / nch, c = i - r * nch;
-        uint8_t* d = aslab + ((size_t)c * kRows + r) * 16;
+        uint8_t* d = aslab + mn_off(r, c, kRows * 128u);
         if (r < rows_here) cp16(d, srca + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
       }
       for (int i = pt; i < kRows * kch; i += 224) {
         const int r = i / kch, c = i - r * kch;
-        uint8_t* d = bslab + ((size_t)c * kRows + r) * 16;
+        uint8_t* d = bslab + mn_off(r, c, kRows * 128u);
         if (r < rows_here) cp16(d, srcb + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
       }
       cp_wait_all();
@@ -238,11 +251,10 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
     }
   } else {
     const uint32_t idesc = idesc_tf32(128, K, 1, 1);
-    // MN-major operands: LBO = 128 B (8-row groups of the reduction dim), SBO = chunk stride (128 rows * 16 B)
-    const uint64_t da_b[2] = {umma::make_desc(umma::smem_u32(buf0), 128u, (uint32_t)kRows * 16u),
-                              umma::make_desc(umma::smem_u32(buf1), 128u, (uint32_t)kRows * 16u)};
-    const uint64_t db_b[2] = {umma::make_desc(umma::smem_u32(buf0) + (uint32_t)a_bytes, 128u, (uint32_t)kRows * 16u),
-                              umma::make_desc(umma::smem_u32(buf1) + (uint32_t)a_bytes, 128u, (uint32_t)kRows * 16u)};
+    // MN-major operands (SW128_BASE32B atoms): 32-channel groups kRows*128 bytes apart, 4-row groups 512 bytes apart
+    const uint64_t da_b[2] = {make_desc_mn32(umma::smem_u32(buf0), kRows * 128u), make_desc_mn32(umma::smem_u32(buf1), kRows * 128u)};
+    const uint64_t db_b[2] = {make_desc_mn32(umma::smem_u32(buf0) + (uint32_t)a_bytes, kRows * 128u),
+                              make_desc_mn32(umma::smem_u32(buf1) + (uint32_t)a_bytes, kRows * 128u)};
     const uint32_t a_hi = (uint32_t)(da_b[0] >> 32), b_hi = (uint32_t)(db_b[0] >> 32);
     int k = 0;
     for (int s = s_begin; s < s_end; ++s, ++k) {
@@ -253,7 +265,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
         const uint32_t a_lo0 = (uint32_t)da_b[b], b_lo0 = (uint32_t)db_b[b];
 #pragma unroll
         for (int kk = 0; kk < kRows / 8; ++kk)   // K = 8 rows per tf32 MMA
-          mma_tf32(tmem, ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(kk * 8)), ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)(kk * 8)),
+          mma_tf32(tmem, ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(kk * 64)), ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)(kk * 64)),
                    idesc, (k > 0 || kk > 0) ? 1u : 0u);
         umma::commit(empty + b);
         if (s == s_end - 1) umma::commit(done);
@@ -318,7 +330,7 @@ bool linear_wgrad_tc_supported(int M, int N, int K) {
   // N = out_features (rows of dW, <= 128 lanes), K = in_features (TMEM columns)
   size_t buf = (size_t)(N / 4 + K / 4) * kRows * 16;
   if (buf < (size_t)32 * kRows * 16) buf = (size_t)32 * kRows * 16;
-  return M >= 512 && N % 4 == 0 && K % 32 == 0 && N >= 16 && N <= 128 && K >= 32 && K <= 256 && 2 * buf + 256 <= 220 * 1024;
+  return M >= 512 && N % 32 == 0 && K % 32 == 0 && N >= 32 && N <= 128 && K >= 32 && K <= 256 && 2 * buf + 256 <= 220 * 1024;
 }
 
 // dW[N][K] += dY[M,N]^T X[M,K]   (dW pre-zeroed / holds the value to accumulate onto)

@@ -28,6 +28,11 @@ def test_linear_forward_and_dgrad(fin, fout, M):
     assert (Y - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 2e-3
     dY = torch.randn((M, fout), device="cuda", generator=g)
     dX = torch.ones((M, fin), device="cuda")
+    if fout > 128:   # the resident weights + two 128-row dY slabs exceed shared memory: the ViT uses its SIMT GEMM there
+        from moleculardiffusion_mivit_b200._lib import MivitError
+        with pytest.raises(MivitError, match="not supported"):
+            call(1, dY, W, None, dX, M, fin, fout, acc=1)
+        return
     call(1, dY, W, None, dX, M, fin, fout, acc=1)
     refd = (dY.double() @ W.double()).float() + 1.0
     assert (dX - refd).abs().max().item() < 2e-3 * refd.abs().max().item() + 2e-3
