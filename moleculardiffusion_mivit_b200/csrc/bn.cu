@@ -102,18 +102,38 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
 // ---------------------------------------------------------------- apply (+relu, +residual) ---
 // act = relu(raw_a*scale_a + shift_a [+ raw_b*scale_b + shift_b]); pad rows -> 0.
 // Thread = (8-channel chunk, row lane): the per-channel constants are loaded ONCE into registers as
-// float4 and the thread streams kRowsPerThread rows (scalar constant loads per element made the first
-// version LSU-instruction bound at ~45 % of HBM bandwidth).
+// float4 and the thread streams rows.  Every iteration issues the 16-byte loads of kU rows
+// unconditionally (pad rows exist in memory) BEFORE any of them is used: the passes are pure HBM
+// streams and need ~40 KB in flight per SM; with loads hidden behind the validity branch they ran at
+// 40-50 % of HBM bandwidth.
 __device__ __forceinline__ void load8f(const float* __restrict__ p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {   // read-once data: do not pollute L1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 constexpr int kRowsPerCta = 256;
+constexpr int kU = 4;   // rows in flight per thread
+
+// pre-activation of the (possibly residual) BatchNorm output: MUST be the same expression in forward and
+// backward -- the backward recomputes the ReLU mask from it instead of reading the activation tensor.
+template <bool DUAL>
+__device__ __forceinline__ void bn_pre(const float (&a)[8], const float (&sa)[8], const float (&ha)[8], const float (&b)[8],
+                                       const float (&sb)[8], const float (&hb)[8], float (&o)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] = fmaf(a[i], sa[i], ha[i]);
+    if (DUAL) o[i] += fmaf(b[i], sb[i], hb[i]);
+  }
+}
 
 template <int C, bool DUAL>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a,
-                                                       const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
-                                                       __nv_bfloat16* __restrict__ act, RowGeom geo, long long rows_pad) {
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a,
+                                                          const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
+                                                          __nv_bfloat16* __restrict__ act, RowGeom geo, long long rows_pad) {
   constexpr int CH = C / 8, RL = 256 / CH;
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
   float sa[8], ha[8], sb[8], hb[8];
@@ -125,25 +145,31 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   }
   const long long r0 = (long long)blockIdx.x * kRowsPerCta;
   const long long r1 = min(rows_pad, r0 + kRowsPerCta);
-#pragma unroll 4
-  for (long long r = r0 + rl; r < r1; r += RL) {
-    const long long idx = r * CH + ch;
-    float o[8] = {};
-    if (row_is_valid((uint32_t)r, geo)) {
-      float a[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
+  for (long long r = r0 + rl; r < r1; r += kU * RL) {
+    uint4 va[kU], vb[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], sa[i], ha[i]);
-      if (DUAL) {
-        float b[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += fmaf(b[i], sb[i], hb[i]);
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr < r1) {
+        va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + rr * CH + ch);
+        if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + rr * CH + ch);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
     }
-    reinterpret_cast<uint4*>(act)[idx] = pack8(o);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr >= r1) break;
+      float o[8] = {};
+      if (row_is_valid((uint32_t)rr, geo)) {
+        float a[8], b[8];
+        unpack8(va[u], a);
+        if (DUAL) unpack8(vb[u], b);
+        bn_pre<DUAL>(a, sa, ha, b, sb, hb, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+      }
+      reinterpret_cast<uint4*>(act)[rr * CH + ch] = pack8(o);
+    }
   }
 }
 
@@ -162,66 +188,80 @@ __global__ void __launch_bounds__(C) pool_rows_kernel(const __nv_bfloat16* __res
 
 // ---------------------------------------------------------------- backward ----------------
 // upstream gradient of the (post-ReLU) activation:
-//   g = (up_a [+ up_b]  |  dpooled[f]/P^2) * 1[act > 0]
+//   g = (up_a [+ up_b]  |  dpooled[f]/P^2) * 1[pre > 0],   pre = bn_pre(raw_a, raw_b) recomputed (the activation
+// tensor is not read: one HBM stream less per pass).  UP: 0 = dpooled, 1 = up_a, 2 = up_a + up_b.
 // sums[0][c] = sum g, sums[1][c] = sum g*xhat_a, sums[2][c] = sum g*xhat_b
-template <int C>
-__device__ __forceinline__ bool load_g(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled,
-                                       const __nv_bfloat16* act, long long r, int ch, const RowGeom& geo, float (&g)[8]) {
-  if (!row_is_valid((uint32_t)r, geo)) return false;
-  const int P = geo.P;
-  constexpr int CH = C / 8;
-  const long long idx = r * CH + ch;
-  float a[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(act) + idx), a);
-  if (dpooled != nullptr) {
-    const long long f = fast_div((uint32_t)r, geo.rpf);
-    const float inv = 1.0f / (float)(P * P);
+template <int C, int UP>
+__device__ __forceinline__ void upstream8(const uint4& ua, const uint4& ub, const float* __restrict__ dpooled, uint32_t r, int ch,
+                                          const RowGeom& geo, float (&u)[8]) {
+  if (UP == 0) {
+    const uint32_t f = fast_div(r, geo.rpf);
+    const float inv = 1.0f / (float)(geo.P * geo.P);
+    load8f(dpooled + (size_t)f * C + ch * 8, u);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = a[i] > 0.f ? dpooled[f * C + ch * 8 + i] * inv : 0.f;
+    for (int i = 0; i < 8; ++i) u[i] *= inv;
   } else {
-    float u[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(up_a) + idx), u);
-    if (up_b != nullptr) {
+    unpack8(ua, u);
+    if (UP == 2) {
       float w[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(up_b) + idx), w);
+      unpack8(ub, w);
 #pragma unroll
       for (int i = 0; i < 8; ++i) u[i] += w[i];
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = a[i] > 0.f ? u[i] : 0.f;
   }
-  return true;
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b,
-                                                            const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ act,
-                                                            const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mi_a,
-                                                            const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mi_b,
-                                                            float* __restrict__ sums, RowGeom geo, int rows_per_block) {
+template <int C, int UP, bool DUAL>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b, const float* __restrict__ dpooled,
+                     const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a, const float* __restrict__ mi_a,
+                     const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b, const float* __restrict__ mi_b,
+                     float* __restrict__ sums, RowGeom geo, int rows_per_block) {
   constexpr int CH = C / 8;
   constexpr int RL = 256 / CH;  // row lanes
+  constexpr int kU = ((DUAL ? 2 : 1) + UP) >= 3 ? 2 : 4;   // 6-8 sixteen-byte loads in flight per thread
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min((long long)geo.rows, r0 + rows_per_block);
+  float sa[8], ha[8], sb[8], hb[8];
+  load8f(ss_a + ch * 8, sa);
+  load8f(ss_a + C + ch * 8, ha);
+  if (DUAL) {
+    load8f(ss_b + ch * 8, sb);
+    load8f(ss_b + C + ch * 8, hb);
+  }
   // sum g*xhat = invstd * (sum g*x - mean * sum g): accumulate sum g*x and fix up once at the end
   float s0[8] = {}, s1[8] = {}, s2[8] = {};
-#pragma unroll 2
-  for (long long r = r0 + rl; r < r1; r += RL) {
-    float g[8];
-    if (!load_g<C>(up_a, up_b, dpooled, act, r, ch, geo, g)) continue;
-    float a[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + r * CH + ch), a);
+  for (long long r = r0 + rl; r < r1; r += kU * RL) {
+    uint4 va[kU], vb[kU], ua[kU], ub[kU];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s0[i] += g[i];
-      s1[i] = fmaf(g[i], a[i], s1[i]);
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr < r1) {
+        const long long idx = rr * CH + ch;
+        va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
+        if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
+        if (UP >= 1) ua[u] = ldg_stream(reinterpret_cast<const uint4*>(up_a) + idx);
+        if (UP == 2) ub[u] = ldg_stream(reinterpret_cast<const uint4*>(up_b) + idx);
+      }
     }
-    if (raw_b != nullptr) {
-      float b[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + r * CH + ch), b);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s2[i] = fmaf(g[i], b[i], s2[i]);
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr >= r1) break;
+      if (!row_is_valid((uint32_t)rr, geo)) continue;
+      float a[8], b[8], pre[8], g[8];
+      unpack8(va[u], a);
+      if (DUAL) unpack8(vb[u], b);
+      bn_pre<DUAL>(a, sa, ha, b, sb, hb, pre);
+      upstream8<C, UP>(ua[u], ub[u], dpooled, (uint32_t)rr, ch, geo, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gi = pre[i] > 0.f ? g[i] : 0.f;
+        s0[i] += gi;
+        s1[i] = fmaf(gi, a[i], s1[i]);
+        if (DUAL) s2[i] = fmaf(gi, b[i], s2[i]);
+      }
     }
   }
   {
@@ -230,24 +270,23 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     load8f(mi_a + C + ch * 8, iv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s1[i] = (s1[i] - m[i] * s0[i]) * iv[i];
-    if (raw_b != nullptr) {
+    if (DUAL) {
       load8f(mi_b + ch * 8, m);
       load8f(mi_b + C + ch * 8, iv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s2[i] = (s2[i] - m[i] * s0[i]) * iv[i];
     }
   }
-  __shared__ float red[3][RL][C + 1];
+  __shared__ float red[DUAL ? 3 : 2][RL][C + 1];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     red[0][rl][ch * 8 + i] = s0[i];
     red[1][rl][ch * 8 + i] = s1[i];
-    red[2][rl][ch * 8 + i] = s2[i];
+    if (DUAL) red[2][rl][ch * 8 + i] = s2[i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+  for (int i = threadIdx.x; i < (DUAL ? 3 : 2) * C; i += 256) {
     const int k = i / C, c = i % C;
-    if (k == 2 && raw_b == nullptr) continue;
     float t = 0.f;
     for (int j = 0; j < RL; ++j) t += red[k][j][c];
     atomicAdd(sums + k * C + c, t);
@@ -279,45 +318,68 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ sums, const float* 
   }
 }
 
-template <int C, bool DUAL>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b,
-                                                           const float* __restrict__ dpooled, const __nv_bfloat16* __restrict__ act,
-                                                           const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ coef_a,
-                                                           __nv_bfloat16* __restrict__ draw_a, const __nv_bfloat16* __restrict__ raw_b,
-                                                           const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ draw_b,
-                                                           RowGeom geo, long long rows_pad) {
+template <int C, int UP, bool DUAL>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b, const float* __restrict__ dpooled,
+                    const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a, const float* __restrict__ coef_a,
+                    __nv_bfloat16* __restrict__ draw_a, const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
+                    const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ draw_b, RowGeom geo, long long rows_pad) {
   constexpr int CH = C / 8, RL = 256 / CH;
+  constexpr int kU = ((DUAL ? 2 : 1) + UP) >= 3 ? 2 : 4;
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
-  float a1[8], a2[8], a3[8], b1[8], b2[8], b3[8];
-  load8f(coef_a + ch * 8, a1);
-  load8f(coef_a + C + ch * 8, a2);
-  load8f(coef_a + 2 * C + ch * 8, a3);
-  if (DUAL) {
-    load8f(coef_b + ch * 8, b1);
-    load8f(coef_b + C + ch * 8, b2);
-    load8f(coef_b + 2 * C + ch * 8, b3);
-  }
   const long long r0 = (long long)blockIdx.x * kRowsPerCta;
   const long long r1 = min(rows_pad, r0 + kRowsPerCta);
-#pragma unroll 2
-  for (long long r = r0 + rl; r < r1; r += RL) {
-    const long long idx = r * CH + ch;
-    float oa[8] = {}, ob[8] = {};
-    float g[8];
-    if (load_g<C>(up_a, up_b, dpooled, act, r, ch, geo, g)) {
-      float a[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(raw_a) + idx), a);
+  for (long long r = r0 + rl; r < r1; r += kU * RL) {
+    uint4 va[kU], vb[kU], ua[kU], ub[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) oa[i] = fmaf(a1[i], g[i], fmaf(a2[i], a[i], a3[i]));
-      if (DUAL) {
-        float b[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(raw_b) + idx), b);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ob[i] = fmaf(b1[i], g[i], fmaf(b2[i], b[i], b3[i]));
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr < r1) {
+        const long long idx = rr * CH + ch;
+        va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
+        if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
+        if (UP >= 1) ua[u] = ldg_stream(reinterpret_cast<const uint4*>(up_a) + idx);
+        if (UP == 2) ub[u] = ldg_stream(reinterpret_cast<const uint4*>(up_b) + idx);
       }
     }
-    reinterpret_cast<uint4*>(draw_a)[idx] = pack8(oa);
-    if (DUAL) reinterpret_cast<uint4*>(draw_b)[idx] = pack8(ob);
+    // per-channel constants are re-read from L1 per batch of rows (keeps the register budget for loads in flight)
+    float sa[8], ha[8], sb[8], hb[8];
+    load8f(ss_a + ch * 8, sa);
+    load8f(ss_a + C + ch * 8, ha);
+    if (DUAL) {
+      load8f(ss_b + ch * 8, sb);
+      load8f(ss_b + C + ch * 8, hb);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr >= r1) break;
+      float oa[8] = {}, ob[8] = {};
+      if (row_is_valid((uint32_t)rr, geo)) {
+        float a[8], b[8], pre[8], g[8];
+        unpack8(va[u], a);
+        if (DUAL) unpack8(vb[u], b);
+        bn_pre<DUAL>(a, sa, ha, b, sb, hb, pre);
+        upstream8<C, UP>(ua[u], ub[u], dpooled, (uint32_t)rr, ch, geo, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = pre[i] > 0.f ? g[i] : 0.f;
+        float k1[8], k2[8], k3[8];
+        load8f(coef_a + ch * 8, k1);
+        load8f(coef_a + C + ch * 8, k2);
+        load8f(coef_a + 2 * C + ch * 8, k3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) oa[i] = fmaf(k1[i], g[i], fmaf(k2[i], a[i], k3[i]));
+        if (DUAL) {
+          load8f(coef_b + ch * 8, k1);
+          load8f(coef_b + C + ch * 8, k2);
+          load8f(coef_b + 2 * C + ch * 8, k3);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ob[i] = fmaf(k1[i], g[i], fmaf(k2[i], b[i], k3[i]));
+        }
+      }
+      reinterpret_cast<uint4*>(draw_a)[rr * CH + ch] = pack8(oa);
+      if (DUAL) reinterpret_cast<uint4*>(draw_b)[rr * CH + ch] = pack8(ob);
+    }
   }
 }
 
@@ -430,6 +492,7 @@ int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16*
   MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
   const int blocks = mivit_ceil_div(rows_pad, kRowsPerCta);
   const RowGeom geo = make_geom(rows, P);
+  MivitProfScope prof("bn_apply", (double)rows_pad * C * 2 * (raw_b ? 3 : 2), st);
   if (raw_b != nullptr) {
     BN_DISPATCH_C(C, (bn_apply_kernel<CC, true><<<blocks, 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, geo, rows_pad)));
   } else {
@@ -448,17 +511,35 @@ int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P
   return MIVIT_OK;
 }
 
-int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* act,
-                const __nv_bfloat16* raw_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a,
-                float* dbeta_a, const __nv_bfloat16* raw_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
-                float* dgamma_b, float* dbeta_b, float* sums /*[9][C] scratch: sums | coef_a | coef_b*/, long long rows, long long rows_pad, int P, int C,
-                double count, cudaStream_t st) {
+#define BN_BWD_LAUNCH(KERN, GRID, ...)                                                                                   \
+  do {                                                                                                                   \
+    const int up_mode = dpooled != nullptr ? 0 : (up_b != nullptr ? 2 : 1);                                             \
+    const bool dual = raw_b != nullptr;                                                                                  \
+    if (up_mode == 0 && dual) { BN_DISPATCH_C(C, (KERN<CC, 0, true><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }              \
+    else if (up_mode == 0) { BN_DISPATCH_C(C, (KERN<CC, 0, false><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                \
+    else if (up_mode == 1 && dual) { BN_DISPATCH_C(C, (KERN<CC, 1, true><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }         \
+    else if (up_mode == 1) { BN_DISPATCH_C(C, (KERN<CC, 1, false><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                \
+    else if (dual) { BN_DISPATCH_C(C, (KERN<CC, 2, true><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                         \
+    else { BN_DISPATCH_C(C, (KERN<CC, 2, false><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                                  \
+  } while (0)
+
+// ss_* = forward (scale | shift) of the BatchNorm(s): the ReLU mask is recomputed from raw, the activation is not read.
+int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* raw_a,
+                const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,
+                const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
+                float* dgamma_b, float* dbeta_b, float* sums /*[9][C] scratch: sums | coef_a | coef_b*/, long long rows,
+                long long rows_pad, int P, int C, double count, cudaStream_t st) {
+  MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
   MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
-  const int rpb = 2048;
+  const int rpb = 1024;
   const int blocks = mivit_ceil_div(rows, rpb);
-  BN_DISPATCH_C(C, (bn_bwd_reduce_kernel<CC><<<blocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, mi_a, raw_b, mi_b, sums, make_geom(rows, P), rpb)));
-  mivit_count_launch();
-  MIVIT_LAUNCH_CHECK();
+  const RowGeom geo = make_geom(rows, P);
+  {
+    MivitProfScope prof("bn_bwd_reduce", (double)rows * C * 2 * ((raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
+    BN_BWD_LAUNCH(bn_bwd_reduce_kernel, blocks, up_a, up_b, dpooled, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, geo, rpb);
+    mivit_count_launch();
+    MIVIT_LAUNCH_CHECK();
+  }
   // sums -> coefficient form + parameter gradients (C threads), then the streaming pass
   float* coef_a = sums + 3 * C;
   float* coef_b = sums + 6 * C;
@@ -467,16 +548,13 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   const int ablocks = mivit_ceil_div(rows_pad, kRowsPerCta);
-  const RowGeom geo = make_geom(rows, P);
-  if (raw_b != nullptr) {
-    BN_DISPATCH_C(C, (bn_bwd_apply_kernel<CC, true><<<ablocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, coef_a, draw_a, raw_b, coef_b,
-                                                                             draw_b, geo, rows_pad)));
-  } else {
-    BN_DISPATCH_C(C, (bn_bwd_apply_kernel<CC, false><<<ablocks, 256, 0, st>>>(up_a, up_b, dpooled, act, raw_a, coef_a, draw_a, raw_b, coef_b,
-                                                                              draw_b, geo, rows_pad)));
+  {
+    MivitProfScope prof("bn_bwd_apply", (double)rows_pad * C * 2 * (2 * (raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
+    BN_BWD_LAUNCH(bn_bwd_apply_kernel, ablocks, up_a, up_b, dpooled, raw_a, ss_a, coef_a, draw_a, raw_b, ss_b, coef_b, draw_b, geo,
+                  rows_pad);
+    mivit_count_launch();
+    MIVIT_LAUNCH_CHECK();
   }
-  mivit_count_launch();
-  MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
 }
 

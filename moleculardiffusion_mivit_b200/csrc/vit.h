@@ -73,9 +73,9 @@ int bn_finalize(const float* stats, const float* gamma, const float* beta, float
 int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b,
              __nv_bfloat16* act, long long rows, long long rows_pad, int P, int C, cudaStream_t st);
 int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P, int C, cudaStream_t st);
-int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* act,
-                const __nv_bfloat16* raw_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a,
-                float* dbeta_a, const __nv_bfloat16* raw_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
+int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* raw_a,
+                const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,
+                const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
                 float* dgamma_b, float* dbeta_b, float* sums, long long rows, long long rows_pad, int P, int C, double count,
                 cudaStream_t st);
 int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad,
