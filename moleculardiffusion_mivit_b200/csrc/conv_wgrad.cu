@@ -175,7 +175,9 @@ int conv_rows_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, 
   }
   if (impl == 1) {  // pipelined kernel; falls back to the serial one when the stage does not fit
     bool handled = false;
-    const int rc = conv_rows_wgrad_v2(X, dY, dW, rows, P, cin, cout, taps, sh, st, &handled);
+    int rc = conv_rows_wgrad_v3(X, dY, dW, rows, P, cin, cout, taps, sh, st, &handled);   // TMA ring + cluster multicast
+    if (rc || handled) return rc;
+    rc = conv_rows_wgrad_v2(X, dY, dW, rows, P, cin, cout, taps, sh, st, &handled);
     if (rc || handled) return rc;
   }
 #define MIVIT_WG_CASE(CI, CO) \

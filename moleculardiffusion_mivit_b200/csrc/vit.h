@@ -45,6 +45,9 @@ int conv_rows_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, 
 int conv_rows_wgrad_v2(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int cin, int cout,
                        int taps, const ConvShifts& sh, cudaStream_t st, bool* handled);
 
+int conv_rows_wgrad_v3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int cin, int cout,
+                       int taps, const ConvShifts& sh, cudaStream_t st, bool* handled);
+
 // gemm_simt.cu
 int gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
              long long scm, int M, int N, int K, const float* bias, int relu, int accumulate, int split_k, cudaStream_t st);

@@ -12,7 +12,8 @@ from moleculardiffusion_mivit_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
 GUARD = 128
-P, NF = 13, 1024 * 30
+import os
+P, NF = 13, int(os.environ.get("NSEQ", "1024")) * 30
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 pit = P + 1
 rows = NF * pit * pit
