@@ -258,7 +258,9 @@ int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bflo
   }
   if (impl == 1) {  // pipelined kernel; falls through to the serial one if the slab does not fit
     bool handled = false;
-    const int rc = conv_rows_forward_v2(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);
+    int rc = conv_rows_forward_v3(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
+    if (rc || handled) return rc;
+    rc = conv_rows_forward_v2(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);
     if (rc || handled) return rc;
   }
 #define MIVIT_FWD_CASE(CI, CO) \
@@ -281,7 +283,9 @@ int conv_rows_forward_fused(const __nv_bfloat16* X, const __nv_bfloat16* Wp, con
                             int taps, const ConvShifts& sh, int impl, cudaStream_t st) {
   if (impl == 1) {
     bool handled = false;
-    const int rc = conv_rows_forward_v2(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);
+    int rc = conv_rows_forward_v3(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
+    if (rc || handled) return rc;
+    rc = conv_rows_forward_v2(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);
     if (rc || handled) return rc;
   }
   int rc = conv_rows_forward(X, Wp, Y, stats, rows, P, cin, cout, taps, sh, impl, st);
