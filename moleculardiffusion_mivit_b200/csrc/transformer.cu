@@ -229,123 +229,150 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const float* __restr
   }
 }
 
-// ---- sequence-per-CTA variants (S <= 64): one warp per head, lanes over query rows; 4x the thread
-// utilisation of the (sequence, head)-per-CTA kernels above for S = 31.
+// ---- sequence-per-CTA variants (S <= 64): one warp per head, lanes over query (forward, dQ) or key (dK, dV)
+// rows.  Flash-attention style bookkeeping: the forward keeps the S scores of a row in registers (one QK^T pass)
+// and stores only the row log-sum-exp L_i (in the first B*H*S floats of `probs`); the backward recomputes
+// P_ij = exp(s_ij - L_i) and uses D_i = dctx_i . ctx_i, so no S x S matrix ever touches shared memory or HBM.
 template <int D>
+__device__ __forceinline__ float dot_row(const float (&a)[D], const float* __restrict__ b) {
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;   // four independent chains
+#pragma unroll
+  for (int c = 0; c < D; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(b + c);
+    p0 = fmaf(a[c], t.x, p0);
+    p1 = fmaf(a[c + 1], t.y, p1);
+    p2 = fmaf(a[c + 2], t.z, p2);
+    p3 = fmaf(a[c + 3], t.w, p3);
+  }
+  return (p0 + p1) + (p2 + p3);
+}
+template <int D>
+__device__ __forceinline__ void axpy_row(float w, const float* __restrict__ b, float (&acc)[D]) {
+#pragma unroll
+  for (int c = 0; c < D; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(b + c);
+    acc[c] = fmaf(w, t.x, acc[c]);
+    acc[c + 1] = fmaf(w, t.y, acc[c + 1]);
+    acc[c + 2] = fmaf(w, t.z, acc[c + 2]);
+    acc[c + 3] = fmaf(w, t.w, acc[c + 3]);
+  }
+}
+template <int D>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&r)[D], float mul) {
+#pragma unroll
+  for (int c = 0; c < D; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + c);
+    r[c] = t.x * mul; r[c + 1] = t.y * mul; r[c + 2] = t.z * mul; r[c + 3] = t.w * mul;
+  }
+}
+template <int D>
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&r)[D], float mul) {
+#pragma unroll
+  for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(p + c) = make_float4(r[c] * mul, r[c + 1] * mul, r[c + 2] * mul, r[c + 3] * mul);
+}
+
+template <int D, int SMAX>
 __global__ void __launch_bounds__(256) attention_fwd_seq_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                 const float* __restrict__ v, float* __restrict__ ctx,
-                                                                float* __restrict__ probs, int S, int E, int H, float scale) {
-  extern __shared__ float sm[];
+                                                                float* __restrict__ lse, int S, int E, int H, float scale) {
+  extern __shared__ __align__(16) float sm[];
   float* Ks = sm;            // [S][E]
   float* Vs = sm + S * E;    // [S][E]
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t base = (size_t)b * S * E;
-  for (int i = threadIdx.x; i < S * E; i += blockDim.x) {
-    Ks[i] = k[base + i];
-    Vs[i] = v[base + i];
+  for (int i = threadIdx.x; i < S * E / 4; i += blockDim.x) {
+    reinterpret_cast<float4*>(Ks)[i] = __ldg(reinterpret_cast<const float4*>(k + base) + i);
+    reinterpret_cast<float4*>(Vs)[i] = __ldg(reinterpret_cast<const float4*>(v + base) + i);
   }
   __syncthreads();
   if (h >= H) return;
+  const int hc = h * D;
   for (int i = lane; i < S; i += 32) {
     float qi[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) qi[c] = q[base + (size_t)i * E + h * D + c] * scale;
+    load_row<D>(q + base + (size_t)i * E + hc, qi, scale);
+    float sc[SMAX];
     float mx = -INFINITY;
-    for (int j = 0; j < S; ++j) {
-      float a = 0.f;
 #pragma unroll
-      for (int c = 0; c < D; ++c) a = fmaf(qi[c], Ks[j * E + h * D + c], a);
-      mx = fmaxf(mx, a);
-    }
+    for (int j = 0; j < SMAX; ++j)
+      if (j < S) {
+        sc[j] = dot_row<D>(qi, Ks + j * E + hc);
+        mx = fmaxf(mx, sc[j]);
+      }
     float sum = 0.f;
-    for (int j = 0; j < S; ++j) {
-      float a = 0.f;
 #pragma unroll
-      for (int c = 0; c < D; ++c) a = fmaf(qi[c], Ks[j * E + h * D + c], a);
-      sum += expf(a - mx);
-    }
-    const float inv = 1.0f / sum;
+    for (int j = 0; j < SMAX; ++j)
+      if (j < S) {
+        sc[j] = expf(sc[j] - mx);
+        sum += sc[j];
+      }
     float o[D] = {};
-    float* prow = probs + (((size_t)b * H + h) * S + i) * S;
-    for (int j = 0; j < S; ++j) {
-      float a = 0.f;
 #pragma unroll
-      for (int c = 0; c < D; ++c) a = fmaf(qi[c], Ks[j * E + h * D + c], a);
-      const float p = expf(a - mx) * inv;
-      prow[j] = p;
-#pragma unroll
-      for (int c = 0; c < D; ++c) o[c] = fmaf(p, Vs[j * E + h * D + c], o[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < D; ++c) ctx[base + (size_t)i * E + h * D + c] = o[c];
+    for (int j = 0; j < SMAX; ++j)
+      if (j < S) axpy_row<D>(sc[j], Vs + j * E + hc, o);
+    store_row<D>(ctx + base + (size_t)i * E + hc, o, 1.0f / sum);
+    lse[((size_t)b * H + h) * S + i] = mx + logf(sum);
   }
 }
 
 template <int D>
 __global__ void __launch_bounds__(256) attention_bwd_seq_kernel(const float* __restrict__ q, const float* __restrict__ k,
-                                                                const float* __restrict__ v, const float* __restrict__ probs,
-                                                                const float* __restrict__ dctx, float* __restrict__ dq,
-                                                                float* __restrict__ dk, float* __restrict__ dv, int S, int E,
-                                                                int H, float scale) {
-  extern __shared__ float sm[];
+                                                                const float* __restrict__ v, const float* __restrict__ lse,
+                                                                const float* __restrict__ ctx, const float* __restrict__ dctx,
+                                                                float* __restrict__ dq, float* __restrict__ dk,
+                                                                float* __restrict__ dv, int S, int E, int H, float scale) {
+  extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                 // [S][E]
   float* Ks = Qs + S * E;
   float* Vs = Ks + S * E;
   float* Gs = Vs + S * E;         // dctx
-  float* PD = Gs + S * E;         // per head: P [S][S+1] then dS [S][S+1]
+  float* Ls = Gs + S * E;         // [H][S] row log-sum-exp
+  float* Dl = Ls + H * S;         // [H][S] D_i = dctx_i . ctx_i
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t base = (size_t)b * S * E;
-  for (int i = threadIdx.x; i < S * E; i += blockDim.x) {
-    Qs[i] = q[base + i];
-    Ks[i] = k[base + i];
-    Vs[i] = v[base + i];
-    Gs[i] = dctx[base + i];
+  for (int i = threadIdx.x; i < S * E / 4; i += blockDim.x) {
+    reinterpret_cast<float4*>(Qs)[i] = __ldg(reinterpret_cast<const float4*>(q + base) + i);
+    reinterpret_cast<float4*>(Ks)[i] = __ldg(reinterpret_cast<const float4*>(k + base) + i);
+    reinterpret_cast<float4*>(Vs)[i] = __ldg(reinterpret_cast<const float4*>(v + base) + i);
+    reinterpret_cast<float4*>(Gs)[i] = __ldg(reinterpret_cast<const float4*>(dctx + base) + i);
   }
-  float* Ps = PD + (size_t)h * 2 * S * (S + 1);
-  float* Ds = Ps + S * (S + 1);
-  if (h < H)
-    for (int i = lane; i < S * S; i += 32) Ps[(i / S) * (S + 1) + (i % S)] = probs[((size_t)b * H + h) * S * S + i];
   __syncthreads();
   if (h >= H) return;
   const int hc = h * D;
+  // pass A (lane = query row i): D_i, then dQ_i = scale * sum_j dS_ij K_j
   for (int i = lane; i < S; i += 32) {
-    float gi[D];
+    float gi[D], qi[D], oi[D];
+    load_row<D>(Gs + i * E + hc, gi, 1.f);
+    load_row<D>(Qs + i * E + hc, qi, scale);
+    load_row<D>(ctx + base + (size_t)i * E + hc, oi, 1.f);
+    float di = 0.f;
 #pragma unroll
-    for (int c = 0; c < D; ++c) gi[c] = Gs[i * E + hc + c];
-    float rowdot = 0.f;
-    for (int j = 0; j < S; ++j) {
-      float dp = 0.f;
-#pragma unroll
-      for (int c = 0; c < D; ++c) dp = fmaf(gi[c], Vs[j * E + hc + c], dp);
-      Ds[i * (S + 1) + j] = dp;
-      rowdot = fmaf(dp, Ps[i * (S + 1) + j], rowdot);
-    }
+    for (int c = 0; c < D; ++c) di = fmaf(gi[c], oi[c], di);
+    const float li = lse[((size_t)b * H + h) * S + i];
+    Ls[h * S + i] = li;
+    Dl[h * S + i] = di;
     float a[D] = {};
     for (int j = 0; j < S; ++j) {
-      const float ds = Ps[i * (S + 1) + j] * (Ds[i * (S + 1) + j] - rowdot);
-      Ds[i * (S + 1) + j] = ds;
-#pragma unroll
-      for (int c = 0; c < D; ++c) a[c] = fmaf(ds, Ks[j * E + hc + c], a[c]);
+      const float p = expf(dot_row<D>(qi, Ks + j * E + hc) - li);
+      const float ds = p * (dot_row<D>(gi, Vs + j * E + hc) - di);
+      axpy_row<D>(ds, Ks + j * E + hc, a);
     }
-#pragma unroll
-    for (int c = 0; c < D; ++c) dq[base + (size_t)i * E + hc + c] = a[c] * scale;
+    store_row<D>(dq + base + (size_t)i * E + hc, a, scale);
   }
   __syncwarp();
+  // pass B (lane = key row j): dK_j = scale * sum_i dS_ij Q_i,  dV_j = sum_i P_ij dctx_i
   for (int j = lane; j < S; j += 32) {
+    float kj[D], vj[D];
+    load_row<D>(Ks + j * E + hc, kj, scale);
+    load_row<D>(Vs + j * E + hc, vj, 1.f);
     float ak[D] = {}, av[D] = {};
     for (int i = 0; i < S; ++i) {
-      const float ds = Ds[i * (S + 1) + j], p = Ps[i * (S + 1) + j];
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        ak[c] = fmaf(ds, Qs[i * E + hc + c], ak[c]);
-        av[c] = fmaf(p, Gs[i * E + hc + c], av[c]);
-      }
+      const float p = expf(dot_row<D>(kj, Qs + i * E + hc) - Ls[h * S + i]);
+      const float ds = p * (dot_row<D>(vj, Gs + i * E + hc) - Dl[h * S + i]);
+      axpy_row<D>(ds, Qs + i * E + hc, ak);
+      axpy_row<D>(p, Gs + i * E + hc, av);
     }
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      dk[base + (size_t)j * E + hc + c] = ak[c] * scale;
-      dv[base + (size_t)j * E + hc + c] = av[c];
-    }
+    store_row<D>(dk + base + (size_t)j * E + hc, ak, scale);
+    store_row<D>(dv + base + (size_t)j * E + hc, av, 1.f);
   }
 }
 
@@ -467,14 +494,26 @@ int layernorm_bwd(const float* dy, const float* z, const float* mean, const floa
   return MIVIT_OK;
 }
 
+// the sequence-per-CTA kernels keep log-sum-exp rows in `probs`; forward and backward must take the same branch
+static bool attention_seq_ok(int S, int E, int H) {
+  return S <= 64 && H <= 8 && E % 4 == 0 && (E / H) % 4 == 0 && (size_t)(4 * S * E + 2 * H * S) * sizeof(float) <= 200 * 1024;
+}
+
 template <int D>
 static int attention_fwd_d(const float* q, const float* k, const float* v, float* ctx, float* probs, int B, int S, int E,
                            int H, cudaStream_t st) {
-  if (S <= 64 && H <= 8) {
+  if (attention_seq_ok(S, E, H)) {
     const size_t smem = (size_t)2 * S * E * sizeof(float);
-    auto kern = attention_fwd_seq_kernel<D>;
-    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, 32 * H, smem, st>>>(q, k, v, ctx, probs, S, E, H, 1.0f / sqrtf((float)D));
+    MivitProfScope prof("attention_fwd", 4.0 * B * H * S * S * D, st);
+    if (S <= 32) {
+      auto kern = attention_fwd_seq_kernel<D, 32>;
+      MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<B, 32 * H, smem, st>>>(q, k, v, ctx, probs, S, E, H, 1.0f / sqrtf((float)D));
+    } else {
+      auto kern = attention_fwd_seq_kernel<D, 64>;
+      MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<B, 32 * H, smem, st>>>(q, k, v, ctx, probs, S, E, H, 1.0f / sqrtf((float)D));
+    }
     mivit_count_launch();
     MIVIT_LAUNCH_CHECK();
     return MIVIT_OK;
@@ -488,18 +527,17 @@ static int attention_fwd_d(const float* q, const float* k, const float* v, float
   return MIVIT_OK;
 }
 template <int D>
-static int attention_bwd_d(const float* q, const float* k, const float* v, const float* probs, const float* dctx, float* dq,
-                           float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st) {
-  if (S <= 64 && H <= 8) {
-    const size_t smem = (size_t)(4 * S * E + 2 * H * S * (S + 1)) * sizeof(float);
-    if (smem <= 200 * 1024) {
-      auto kern = attention_bwd_seq_kernel<D>;
-      MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<B, 32 * H, smem, st>>>(q, k, v, probs, dctx, dq, dk, dv, S, E, H, 1.0f / sqrtf((float)D));
-      mivit_count_launch();
-      MIVIT_LAUNCH_CHECK();
-      return MIVIT_OK;
-    }
+static int attention_bwd_d(const float* q, const float* k, const float* v, const float* probs, const float* ctx, const float* dctx,
+                           float* dq, float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st) {
+  if (attention_seq_ok(S, E, H)) {
+    const size_t smem = (size_t)(4 * S * E + 2 * H * S) * sizeof(float);
+    MivitProfScope prof("attention_bwd", 14.0 * B * H * S * S * D, st);
+    auto kern = attention_bwd_seq_kernel<D>;
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, 32 * H, smem, st>>>(q, k, v, probs, ctx, dctx, dq, dk, dv, S, E, H, 1.0f / sqrtf((float)D));
+    mivit_count_launch();
+    MIVIT_LAUNCH_CHECK();
+    return MIVIT_OK;
   }
   const size_t smem = (size_t)(4 * S * (D + 1) + 2 * S * (S + 1)) * sizeof(float);
   auto kern = attention_bwd_kernel<D>;
@@ -522,13 +560,13 @@ int attention_fwd(const float* q, const float* k, const float* v, float* ctx, fl
     default: mivit_set_error("head_dim %d not supported (8, 16, 32)", E / H); return MIVIT_ERR_INVALID;
   }
 }
-int attention_bwd(const float* q, const float* k, const float* v, const float* probs, const float* dctx, float* dq,
-                  float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st) {
+int attention_bwd(const float* q, const float* k, const float* v, const float* probs, const float* ctx, const float* dctx,
+                  float* dq, float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st) {
   if (B <= 0) return MIVIT_OK;
   switch (E / H) {
-    case 8: return attention_bwd_d<8>(q, k, v, probs, dctx, dq, dk, dv, B, S, E, H, st);
-    case 16: return attention_bwd_d<16>(q, k, v, probs, dctx, dq, dk, dv, B, S, E, H, st);
-    case 32: return attention_bwd_d<32>(q, k, v, probs, dctx, dq, dk, dv, B, S, E, H, st);
+    case 8: return attention_bwd_d<8>(q, k, v, probs, ctx, dctx, dq, dk, dv, B, S, E, H, st);
+    case 16: return attention_bwd_d<16>(q, k, v, probs, ctx, dctx, dq, dk, dv, B, S, E, H, st);
+    case 32: return attention_bwd_d<32>(q, k, v, probs, ctx, dctx, dq, dk, dv, B, S, E, H, st);
     default: mivit_set_error("head_dim %d not supported (8, 16, 32)", E / H); return MIVIT_ERR_INVALID;
   }
 }

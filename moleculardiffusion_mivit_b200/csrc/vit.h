@@ -63,8 +63,8 @@ int layernorm_bwd(const float* dy, const float* z, const float* mean, const floa
                   float* dgamma, float* dbeta, int rows, int E, int group, int out_group, int out_off, cudaStream_t st);
 int attention_fwd(const float* q, const float* k, const float* v, float* ctx, float* probs, int B, int S, int E, int H,
                   cudaStream_t st);
-int attention_bwd(const float* q, const float* k, const float* v, const float* probs, const float* dctx, float* dq,
-                  float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st);
+int attention_bwd(const float* q, const float* k, const float* v, const float* probs, const float* ctx, const float* dctx,
+                  float* dq, float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st);
 int act_fwd(const float* pre, float* post, long long n, int mode, cudaStream_t st);
 int act_bwd(const float* dpost, const float* pre, float* dpre, long long n, int mode, cudaStream_t st);
 int tokens_finish(float* tok, const float* reg, const float* proj, const float* pos, int B, int S, int E, cudaStream_t st);
@@ -78,6 +78,8 @@ int bn_finalize(const float* stats, const float* gamma, const float* beta, float
                 float momentum, int training, cudaStream_t st);
 int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b,
              __nv_bfloat16* act, long long rows, long long rows_pad, int P, int C, cudaStream_t st);
+int bn_apply_pool(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b, float* pooled,
+                  long long n_frames, int P, int C, cudaStream_t st);
 int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P, int C, cudaStream_t st);
 int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* raw_a,
                 const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,

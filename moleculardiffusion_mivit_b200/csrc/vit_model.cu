@@ -113,7 +113,7 @@ struct LayerWS {
 
 struct Workspace {
   // deepresnet embedding
-  RowsT raw0, act0, raw1, act1, raw2, raws1, act2, raw3, act3, raw4, raws2, act4;
+  RowsT raw0, act0, raw1, act1, raw2, raws1, act2, raw3, act3, raw4, raws2;   // the last block output is pooled on the fly
   RowsT draw4, draws2, dact3, draw3, dact2m, dact2s, draw2, draws1, dact1, draw1, dact0m, dact0s, draw0;
   __nv_bfloat16 *wp_c1[2], *wp_c2[2], *wp_sk[2], *wd_c1[2], *wd_c2[2], *wd_sk[2];
   BnScratch bn[7];
@@ -148,7 +148,7 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
     take_rows(b, w.raw1, 64, rp); take_rows(b, w.act1, 64, rp); take_rows(b, w.raw2, 64, rp);
     take_rows(b, w.raws1, 64, rp); take_rows(b, w.act2, 64, rp);
     take_rows(b, w.raw3, 128, rp); take_rows(b, w.act3, 128, rp); take_rows(b, w.raw4, 128, rp);
-    take_rows(b, w.raws2, 128, rp); take_rows(b, w.act4, 128, rp);
+    take_rows(b, w.raws2, 128, rp);
     take_rows(b, w.draw4, 128, rp); take_rows(b, w.draws2, 128, rp); take_rows(b, w.dact3, 128, rp);
     take_rows(b, w.draw3, 128, rp); take_rows(b, w.dact2m, 64, rp); take_rows(b, w.dact2s, 64, rp);
     take_rows(b, w.draw2, 64, rp); take_rows(b, w.draws1, 64, rp); take_rows(b, w.dact1, 64, rp);
@@ -305,7 +305,7 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
     RowsT* a1[2] = {&w.act1, &w.act3};
     RowsT* r2[2] = {&w.raw2, &w.raw4};
     RowsT* rs[2] = {&w.raws1, &w.raws2};
-    RowsT* out[2] = {&w.act2, &w.act4};
+    RowsT* out[2] = {&w.act2, nullptr};
     for (int b = 0; b < 2; ++b) {
       const auto& R = L.rb[b];
       const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, is = 3 + 3 * b;
@@ -320,9 +320,12 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
       CK(conv_rows_forward(a1[b]->row0, w.wp_c2[b], r2[b]->row0, w.bn[i2].stats, rows, P, co[b], co[b], 9, s3, impl, st));
       CK(run_bn_finalize(c, w, i2, p + R.bn2_g, p + R.bn2_b, bn_running, nbt, cnt, training, st));
       CK(run_bn_finalize(c, w, is, p + R.bns_g, p + R.bns_b, bn_running, nbt, cnt, training, st));
-      CK(bn_apply(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, out[b]->row0, rows, rp, P, co[b], st));
+      if (b == 0) {
+        CK(bn_apply(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, out[b]->row0, rows, rp, P, co[b], st));
+      } else {  // last block: its output only feeds the average pool -> fused, the activation is never materialised
+        CK(bn_apply_pool(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, w.pooled, NF, P, co[b], st));
+      }
     }
-    CK(pool_rows(w.act4.row0, w.pooled, NF, P, 128, st));
     CK(linear_fwd(w.pooled, p + L.fc_w, p + L.fc_b, w.emb, NF, E, 128, 0, st));
   } else {
     CK(linear_fwd(x, p + L.proj_w, p + L.proj_b, w.emb, NF, E, P * P, 0, st));
@@ -401,7 +404,7 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
     // x1 = LN1(xin + ao)
     CK(layernorm_bwd(tmp, y.z1, y.m1, y.r1, p + Y.n1_g, dx, g + Y.n1_g, g + Y.n1_b, T, E, 0, 0, 0, st));   // dx = dz1 = dao = dxin
     CK(linear_bwd(y.ctx, p + Y.o_w, dx, g + Y.o_w, g + Y.o_b, w.dctx, T, E, E, 0, st));
-    CK(attention_bwd(y.q, y.k, y.v, y.probs, w.dctx, w.dq, w.dk, w.dv, B, S, E, H, st));
+    CK(attention_bwd(y.q, y.k, y.v, y.probs, y.ctx, w.dctx, w.dq, w.dk, w.dv, B, S, E, H, st));
     CK(linear_bwd(xin, p + Y.q_w, w.dq, g + Y.q_w, g + Y.q_b, dx, T, E, E, 1, st));
     CK(linear_bwd(xin, p + Y.k_w, w.dk, g + Y.k_w, g + Y.k_b, dx, T, E, E, 1, st));
     CK(linear_bwd(xin, p + Y.v_w, w.dv, g + Y.v_w, g + Y.v_b, dx, T, E, E, 1, st));
@@ -432,7 +435,6 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
   RowsT* a1[2] = {&w.act1, &w.act3};
   RowsT* r2[2] = {&w.raw2, &w.raw4};
   RowsT* rs[2] = {&w.raws1, &w.raws2};
-  RowsT* out[2] = {&w.act2, &w.act4};
   RowsT* d2[2] = {&w.draw2, &w.draw4};      // grad of raw (conv2 output)
   RowsT* ds[2] = {&w.draws1, &w.draws2};    // grad of raw skip
   RowsT* da1[2] = {&w.dact1, &w.dact3};     // grad of act1 (conv2 input)
