@@ -132,7 +132,8 @@ int mivit_conv_rows_wgrad(const void* X_row0, const void* dY_row0, float* dW, in
 /* nn.Linear (helpers/models.py:20-23,64-65,241,268-273) on tcgen05 kind::tf32, fp32 in / fp32 out.
  *   mode 0: out[M,out_f] = A[M,in_f] W[out_f,in_f]^T + bias (relu)
  *   mode 1: out[M,in_f] (+)= A[M,out_f] W[out_f,in_f]                (input gradient)
- *   mode 2: out[out_f,in_f] += A[M,out_f]^T W'[M,in_f]               (weight gradient; W' = layer input)
+ *   mode 2: out[out_f,in_f] += A[M,out_f]^T W'[M,in_f]               (weight gradient; W' = layer input;
+ *           when `bias` is not NULL it is the bias GRADIENT: bias[out_f] += column sums of A)
  * Fails for shapes outside the tensor-core kernels' range (M >= 512, features multiples of 32, <= 256). */
 int mivit_linear_tf32(int32_t mode, const float* A, const float* W, const float* bias, float* out, int32_t M,
                       int32_t in_features, int32_t out_features, int32_t relu, int32_t accumulate, void* stream);

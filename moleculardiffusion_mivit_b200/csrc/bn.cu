@@ -442,34 +442,36 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16*
 __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ frames, const float* __restrict__ W0,
                                                         __nv_bfloat16* __restrict__ raw0, float* __restrict__ stats, long long rows,
                                                         long long rows_pad, int P) {
-  __shared__ float w[32 * 9];
   __shared__ float red[2][64][33];
-  for (int i = threadIdx.x; i < 288; i += 256) w[i] = W0[i];
-  __syncthreads();
-  const int pitch = P + 1, rpf = pitch * pitch;
+  const uint32_t pitch = P + 1, rpf = pitch * pitch;
   const int ch = threadIdx.x & 3;  // 4 chunks of 8 channels
+  float w[8][9];                   // this thread's 8 output channels x 9 taps, resident in registers
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[i][t] = __ldg(W0 + (ch * 8 + i) * 9 + t);
   float s0[8] = {}, s1[8] = {};
-  for (long long r = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); r < rows_pad; r += (long long)gridDim.x * 64) {
+  const uint32_t nrows = (uint32_t)rows, nrows_pad = (uint32_t)rows_pad;
+  for (uint32_t r = blockIdx.x * 64u + (threadIdx.x >> 2); r < nrows_pad; r += gridDim.x * 64u) {
     float o[8] = {};
-    if (r < rows) {
-      const long long f = r / rpf;
-      const int q = (int)(r - f * rpf), y = q / pitch, x = q - y * pitch;
-      if (y < P && x < P) {
-        const float* img = frames + f * P * P;
+    if (r < nrows) {
+      const uint32_t f = r / rpf, q = r - f * rpf, y = q / pitch, x = q - y * pitch;
+      if (y < (uint32_t)P && x < (uint32_t)P) {
+        const float* img = frames + (size_t)f * P * P;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
           for (int dx = -1; dx <= 1; ++dx) {
-            const int yy = y + dy, xx = x + dx;
+            const int yy = (int)y + dy, xx = (int)x + dx;
             const float v = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + yy * P + xx) : 0.f;
             const int t = (dy + 1) * 3 + dx + 1;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = fmaf(v, w[(ch * 8 + i) * 9 + t], o[i]);
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(v, w[i][t], o[i]);
           }
       }
     }
     const uint4 pk = pack8(o);
-    reinterpret_cast<uint4*>(raw0)[r * 4 + ch] = pk;
+    reinterpret_cast<uint4*>(raw0)[(size_t)r * 4 + ch] = pk;
     float rb[8];
     unpack8(pk, rb);
 #pragma unroll
@@ -492,16 +494,17 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
   __shared__ float red[288];
   for (int i = threadIdx.x; i < 288; i += 256) red[i] = 0.f;
   __syncthreads();
-  const int pitch = P + 1, rpf = pitch * pitch;
+  const uint32_t pitch = P + 1, rpf = pitch * pitch;
   const int ch = threadIdx.x & 3;
   float acc[8][9] = {};
-  for (long long r = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); r < rows; r += (long long)gridDim.x * 64) {
-    const long long f = r / rpf;
-    const int q = (int)(r - f * rpf), y = q / pitch, x = q - y * pitch;
+  const uint32_t nrows = (uint32_t)rows;
+  for (uint32_t r = blockIdx.x * 64u + (threadIdx.x >> 2); r < nrows; r += gridDim.x * 64u) {
+    const uint32_t f = r / rpf, q = r - f * rpf;
+    const int y = (int)(q / pitch), x = (int)(q - (uint32_t)y * pitch);
     if (y >= P || x >= P) continue;
     float g[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(draw0) + r * 4 + ch), g);
-    const float* img = frames + f * P * P;
+    unpack8(ldg_stream(reinterpret_cast<const uint4*>(draw0) + (size_t)r * 4 + ch), g);
+    const float* img = frames + (size_t)f * P * P;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
@@ -624,6 +627,8 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
 
 int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad, int P,
                   cudaStream_t st) {
+  MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
+  MivitProfScope prof("conv0_fwd", (double)rows_pad * 64, st);
   int blocks = mivit_ceil_div(rows_pad, 64);
   if (blocks > 148 * 8) blocks = 148 * 8;
   conv0_fwd_kernel<<<blocks, 256, 0, st>>>(frames, W0, raw0, stats, rows, rows_pad, P);
@@ -634,6 +639,7 @@ int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, flo
 
 int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st) {
   MIVIT_CUDA_CHECK(cudaMemsetAsync(dW0, 0, 288 * sizeof(float), st));
+  MivitProfScope prof("conv0_wgrad", (double)rows * 64, st);
   int blocks = mivit_ceil_div(rows, 64);
   if (blocks > 148 * 4) blocks = 148 * 4;
   conv0_wgrad_kernel<<<blocks, 256, 0, st>>>(frames, draw0, dW0, rows, P);

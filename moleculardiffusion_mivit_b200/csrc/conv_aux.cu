@@ -80,7 +80,7 @@ extern "C" int mivit_conv_rows_fused(const void* X_row0, const void* Wp, const v
 }
 
 // nn.Linear building blocks on the tf32 tensor path (tests / ViT).  mode 0: Y = X W^T + b (relu);
-// mode 1: dX (+)= dY W;  mode 2: dW += dY^T X.  Returns an error when the shape is not supported by the
+// mode 1: dX (+)= dY W;  mode 2: dW += dY^T X (and, when `bias` is given, bias[out] += column sums of dY).  Returns an error when the shape is not supported by the
 // tensor-core kernels (the ViT then uses its fp32 SIMT GEMM).
 extern "C" int mivit_linear_tf32(int32_t mode, const float* A, const float* W, const float* bias, float* out, int32_t M,
                                  int32_t in_features, int32_t out_features, int32_t relu, int32_t accumulate, void* stream) {
@@ -95,5 +95,5 @@ extern "C" int mivit_linear_tf32(int32_t mode, const float* A, const float* W, c
     return linear_tc(A, W, nullptr, out, M, out_features, in_features, 1, 0, accumulate, st);
   }
   MIVIT_CHECK_ARG(mode == 2 && linear_wgrad_tc_supported(M, out_features, in_features), "shape not supported by the tf32 wgrad kernel");
-  return linear_wgrad_tc(A, W, out, M, out_features, in_features, st);  // A = dY [M,out], W = X [M,in], out = dW [out,in]
+  return linear_wgrad_tc(A, W, out, const_cast<float*>(bias), M, out_features, in_features, st);  // A = dY [M,out], W = X [M,in], out = dW [out,in]
 }

@@ -194,8 +194,8 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
 // ------------------------------------------------------------------ weight gradient -------------
 // warps 0-3 producers + final flush, warp 4 MMA issuer, warps 5-7 producers.
 __global__ void __launch_bounds__(256, 1)
-linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ dW, int M, int N, int K,
-                       int n_stages, int stages_per_cta, int buf_bytes) {
+linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ dW, float* __restrict__ db,
+                       int M, int N, int K, int n_stages, int stages_per_cta, int buf_bytes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int nch = N / 4, kch = K / 4;
@@ -216,7 +216,18 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
     umma::mbar_init(done, 1);
     umma::mbar_fence_init();
   }
-  if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  // bias gradient for free: a 33rd..-th column group of the B operand whose first column is all ones makes accumulator
+  // column K the column sum of dY (db).  The group lives behind the X slab of both stage buffers and is written once.
+  if (db != nullptr) {
+    const int b_bytes = kch * kRows * 16;
+    for (int i = tid; i < 2 * kRows * 8; i += 256) {
+      const int b = i / (kRows * 8), r = (i >> 3) & (kRows - 1), j = i & 7;
+      uint8_t* g = (b ? smem + buf_bytes : smem) + a_bytes + b_bytes;     // one more 32-column group: LBO = kRows*128 after the last
+      *reinterpret_cast<float4*>(g + mn_off(r, j, kRows * 128u)) = make_float4(j == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    }
+    umma::fence_proxy_async();
+  }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -250,7 +261,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
       if (lane == 0) arrive(full + b);
     }
   } else {
-    const uint32_t idesc = idesc_tf32(128, K, 1, 1);
+    const uint32_t idesc = idesc_tf32(128, db != nullptr ? K + 32 : K, 1, 1);
     // MN-major operands (SW128_BASE32B atoms): 32-channel groups kRows*128 bytes apart, 4-row groups 512 bytes apart
     const uint64_t da_b[2] = {make_desc_mn32(umma::smem_u32(buf0), kRows * 128u), make_desc_mn32(umma::smem_u32(buf1), kRows * 128u)};
     const uint64_t db_b[2] = {make_desc_mn32(umma::smem_u32(buf0) + (uint32_t)a_bytes, kRows * 128u),
@@ -286,11 +297,16 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
           for (int i = 0; i < 32; ++i) atomicAdd(dW + (size_t)n * K + cg * 32 + i, v[i]);
         }
       }
+      if (db != nullptr) {
+        float v[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)K, v);
+        if (n < N) atomicAdd(db + n, v[0]);
+      }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc<256>(tmem);
+  if (warp == 0) umma::tmem_dealloc<512>(tmem);
 }
 
 int sm_count() {
@@ -327,16 +343,17 @@ int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M
 }
 
 bool linear_wgrad_tc_supported(int M, int N, int K) {
-  // N = out_features (rows of dW, <= 128 lanes), K = in_features (TMEM columns)
-  size_t buf = (size_t)(N / 4 + K / 4) * kRows * 16;
+  // N = out_features (rows of dW, <= 128 lanes), K = in_features (TMEM columns); + one 32-column group for the bias gradient
+  size_t buf = (size_t)(N / 4 + K / 4 + 8) * kRows * 16;
   if (buf < (size_t)32 * kRows * 16) buf = (size_t)32 * kRows * 16;
-  return M >= 512 && N % 32 == 0 && K % 32 == 0 && N >= 32 && N <= 128 && K >= 32 && K <= 256 && 2 * buf + 256 <= 220 * 1024;
+  return M >= 512 && N % 32 == 0 && K % 32 == 0 && N >= 32 && N <= 128 && K >= 32 && K <= 256 && 2 * buf + 256 <= 227 * 1024;
 }
 
 // dW[N][K] += dY[M,N]^T X[M,K]   (dW pre-zeroed / holds the value to accumulate onto)
-int linear_wgrad_tc(const float* dY, const float* X, float* dW, int M, int N, int K, cudaStream_t st) {
+// db (optional, [N]) += column sums of dY
+int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
   // the M = 128 MMA over-reads the A slab up to 32 chunks: keep that inside the stage buffer
-  int buf_bytes = (N / 4 + K / 4) * kRows * 16;
+  int buf_bytes = (N / 4 + K / 4 + 8) * kRows * 16;
   const int need = 32 * kRows * 16;
   if (buf_bytes < need) buf_bytes = need;
   int smem = 2 * buf_bytes + 256;
@@ -347,7 +364,7 @@ int linear_wgrad_tc(const float* dY, const float* X, float* dW, int M, int N, in
   const int spc = (n_stages + ctas - 1) / ctas;
   ctas = (n_stages + spc - 1) / spc;
   MivitProfScope prof("linear_tc_wgrad", 2.0 * M * K * N, st);
-  linear_wgrad_tc_kernel<<<ctas, 256, smem, st>>>(dY, X, dW, M, N, K, n_stages, spc, buf_bytes);
+  linear_wgrad_tc_kernel<<<ctas, 256, smem, st>>>(dY, X, dW, db, M, N, K, n_stages, spc, buf_bytes);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

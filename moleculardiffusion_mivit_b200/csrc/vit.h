@@ -100,4 +100,4 @@ bool linear_tc_supported(int M, int K, int N);
 int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M, int K, int N, int mode, int relu, int accumulate,
               cudaStream_t st);
 bool linear_wgrad_tc_supported(int M, int N, int K);
-int linear_wgrad_tc(const float* dY, const float* X, float* dW, int M, int N, int K, cudaStream_t st);
+int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st);

@@ -204,7 +204,8 @@ int linear_fwd(const float* X, const float* W, const float* bias, float* Y, int 
 int linear_bwd(const float* X, const float* W, const float* dY, float* dW, float* db, float* dX, int M, int N, int K,
                int accumulate_dx, cudaStream_t st) {
   if (g_linear_tc && linear_wgrad_tc_supported(M, N, K) && al16(X) && al16(dY) && al16(dW)) {
-    CK(linear_wgrad_tc(dY, X, dW, M, N, K, st));
+    CK(linear_wgrad_tc(dY, X, dW, db, M, N, K, st));   // bias gradient rides along as an extra accumulator column
+    db = nullptr;
   } else {
     int split = M / 128;  // token-dimension split-K: enough CTAs to fill 148 SMs even for 64x64 outputs
     if (split < 1) split = 1;
@@ -349,8 +350,12 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
     CK(attention_fwd(y.q, y.k, y.v, y.ctx, y.probs, B, S, E, H, st));
     CK(linear_fwd(y.ctx, p + Y.o_w, p + Y.o_b, y.ao, T, E, E, 0, st));
     CK(layernorm_fwd(y.ao, xin, p + Y.n1_g, p + Y.n1_b, y.z1, y.x1, y.m1, y.r1, T, E, c->ln_eps, 0, 0, 0, st));
-    CK(linear_fwd(y.x1, p + Y.f1_w, p + Y.f1_b, y.hpre, T, HD, E, 0, st));
-    CK(act_fwd(y.hpre, y.hact, (long long)T * HD, c->activation, st));
+    if (c->activation == 0) {   // F.relu: fused into the fc1 epilogue (its gradient only needs the sign, i.e. hact > 0)
+      CK(linear_fwd(y.x1, p + Y.f1_w, p + Y.f1_b, y.hact, T, HD, E, 1, st));
+    } else {
+      CK(linear_fwd(y.x1, p + Y.f1_w, p + Y.f1_b, y.hpre, T, HD, E, 0, st));
+      CK(act_fwd(y.hpre, y.hact, (long long)T * HD, c->activation, st));
+    }
     CK(linear_fwd(y.hact, p + Y.f2_w, p + Y.f2_b, y.ff, T, E, HD, 0, st));
     CK(layernorm_fwd(y.ff, y.x1, p + Y.n2_g, p + Y.n2_b, y.z2, y.x2, y.m2, y.r2, T, E, c->ln_eps, 0, 0, 0, st));
     xin = y.x2;
@@ -399,7 +404,7 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
     // x2 = LN2(x1 + ff)
     CK(layernorm_bwd(dx, y.z2, y.m2, y.r2, p + Y.n2_g, tmp, g + Y.n2_g, g + Y.n2_b, T, E, 0, 0, 0, st));  // tmp = dz2 = dff = dx1
     CK(linear_bwd(y.hact, p + Y.f2_w, tmp, g + Y.f2_w, g + Y.f2_b, w.dh, T, E, HD, 0, st));
-    CK(act_bwd(w.dh, y.hpre, w.dh2, (long long)T * HD, c->activation, st));
+    CK(act_bwd(w.dh, c->activation == 0 ? y.hact : y.hpre, w.dh2, (long long)T * HD, c->activation, st));
     CK(linear_bwd(y.x1, p + Y.f1_w, w.dh2, g + Y.f1_w, g + Y.f1_b, tmp, T, HD, E, 1, st));               // tmp += dhpre W1
     // x1 = LN1(xin + ao)
     CK(layernorm_bwd(tmp, y.z1, y.m1, y.r1, p + Y.n1_g, dx, g + Y.n1_g, g + Y.n1_b, T, E, 0, 0, 0, st));   // dx = dz1 = dao = dxin

@@ -46,6 +46,12 @@ def test_linear_wgrad(fin, fout):
     X = torch.randn((M, fin), device="cuda", generator=g)
     dY = torch.randn((M, fout), device="cuda", generator=g)
     dW = torch.zeros((fout, fin), device="cuda")
-    call(2, dY, X, None, dW, M, fin, fout)
+    db = torch.full((fout,), 2.0, device="cuda")
+    call(2, dY, X, db, dW, M, fin, fout)
     ref = (dY.double().t() @ X.double()).float()
     assert (dW - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 0.3   # sum of 31k tf32 products
+    refb = dY.double().sum(0).float() + 2.0                                      # bias gradient rides along (accumulated)
+    assert (db - refb).abs().max().item() < 2e-3 * refb.abs().max().item() + 0.3
+    dW2 = torch.zeros((fout, fin), device="cuda")
+    call(2, dY, X, None, dW2, M, fin, fout)                                       # without the bias column
+    assert (dW2 - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 0.3
