@@ -294,7 +294,10 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
         umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cg * 32), v);
         if (n < N) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dW + (size_t)n * K + cg * 32 + i, v[i]);
+          for (int i = 0; i < 32; i += 4)   // 16-byte vector reductions: 4x fewer L2 atomic operations
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dW + (size_t)n * K + cg * 32 + i), "f"(v[i]), "f"(v[i + 1]),
+                         "f"(v[i + 2]), "f"(v[i + 3])
+                         : "memory");
         }
       }
       if (db != nullptr) {
