@@ -180,3 +180,58 @@ def test_product_path_matches_simt_path_at_batch_64(golden_dir, name):
         a, b = outs[0][1][k], outs[1][1][k]
         if float(a.norm()) > 1e-4 * gmax:
             assert relnorm(b, a) < 5e-2, (k, relnorm(b, a))
+
+
+# BASELINE.json configs beyond the golden P=9 cases: patch-size sweep 7/9/13/15 (Embeddings experiment), the
+# Framerate frame counts (S = 7 ... 61 tokens), the _s / _n / _b model sizes (trainSettingsEmbeddings.py:152-211)
+# and the bench.py workload itself (P=13, F=30, deepcnn_n).  Weights: the mirror's own random init, shared with the
+# oracle through state_dict; inputs: seeded normalised-image-like noise.
+SWEEP = [
+    # embedding, E, H, HD, L, P, F, B, pos, reg
+    ("deepresnet", 64, 4, 128, 6, 13, 30, 8, False, True),     # bench.py workload
+    ("deepresnet", 32, 2, 64, 3, 7, 20, 5, True, True),        # deepcnn_s, P=7
+    ("deepresnet", 128, 8, 256, 12, 15, 10, 2, True, True),    # deepcnn_b, P=15
+    ("deepresnet", 64, 4, 128, 6, 9, 60, 2, False, True),      # Framerate n=5: 60 frames -> 61 tokens
+    ("deepresnet", 64, 4, 128, 6, 13, 6, 3, False, False),     # Framerate n=50: 6 frames, mean pooling
+    ("linear", 128, 8, 256, 12, 13, 30, 4, True, True),        # linear_b
+    ("cnn", 64, 4, 128, 6, 15, 15, 3, True, True),             # cnn_n, P=15
+]
+
+
+@pytest.mark.parametrize("emb,E,H,HD,Lyr,P,Fr,B,pos,reg", SWEEP)
+def test_config_sweep_matches_oracle(emb, E, H, HD, Lyr, P, Fr, B, pos, reg):
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    torch.manual_seed(P * 1000 + Fr * 10 + B)
+    cls = {"deepresnet": M.DeepResNetEmbedding, "linear": M.LinearProjectionEmbedding, "cnn": M.CNNEmbedding}[emb]
+    model = M.GeneralTransformer(cls, {"patch_size": P, "embed_dim": E}, E, H, HD, Lyr, M.MLPHead, F.relu, 0.0, pos, reg, True)
+    sd = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+    cfg = dict(embedding=emb, embed_dim=E, num_heads=H, num_layers=Lyr, activation="relu", use_pos_encoding=pos,
+               use_regression_token=reg)
+    g = torch.Generator().manual_seed(17)
+    x = 0.1 + 0.25 * torch.randn((B, Fr, P, P), generator=g).abs()
+    tgt = torch.rand((B, 1), generator=g)
+    model.cuda().train()
+    pred = model(x.cuda())
+    loss = F.mse_loss(pred, tgt.cuda())
+    loss.backward()
+    ref_pred, ref_loss, ref_g, _ = vo.loss_and_grads(sd, cfg, x, tgt, None)
+    deep = emb == "deepresnet"
+    ptol = 3e-2 if deep else 2e-4
+    assert (pred.cpu() - ref_pred).abs().max().item() < ptol * max(1.0, ref_pred.abs().max().item())
+    assert abs(loss.item() - float(ref_loss)) < ptol * max(1.0, float(ref_loss))
+    gmax = max(float(v.norm()) for v in ref_g.values())
+    gtol = 8e-2 if deep else 5e-4
+    for k, p in model.named_parameters():
+        r = ref_g[k]
+        if float(r.norm()) < 1e-4 * gmax:
+            assert float(p.grad.cpu().norm()) < 2e-3 * gmax, k
+            continue
+        # Embedding gradients carry the rounding of the bf16-STORED gradient tensors, amplified by the BatchNorm
+        # backward projections (they remove the common mode the rounding was relative to) and averaged over the
+        # B*F*P^2 positions a weight sees: measured 0.14 / 0.10 / 0.05 on initial_conv.weight for B = 2 / 8 / 32
+        # at P=7, F=20 (scripts/diag_grad_error.py; identical for the SIMT and the tcgen05 convolutions), 0.06 at
+        # the bench.py shape (first case).  Tiny batches therefore get a wider bound.
+        tol = 0.16 if (deep and B <= 5 and k.startswith("embedding.")) else gtol
+        assert relnorm(p.grad.cpu(), r) < tol, (k, relnorm(p.grad.cpu(), r))
