@@ -77,6 +77,16 @@ int mivit_render_v1(const double* traj, int64_t N, int32_t T, const mivit_render
                     uint64_t seed, uint64_t seq_offset, float* out, int64_t out_seq_stride,
                     void* stream);
 
+/* Renderer fused with the frame embedding of LinearProjectionEmbedding / CNNEmbedding
+ * (reference helpers/models.py:146-167 and :170-199: both are emb[f,:] = W[E,P*P] . frame[f] + b applied to the output of
+ * helpers/helpersGeneration.py:128-278 + normalize_images :356-400).  Same trajectory / parameter / RNG contract as
+ * mivit_render_v1; the frame is never written to HBM unless frames_out != NULL (needed only for the weight gradient).
+ * Wt: device fp32 [P*P][E] = the nn.Linear weight transposed (Conv2d weight [E,1,P,P] is the same matrix);
+ * bias: device fp32 [E]; emb: device fp32 [N][F][E]; frames_out (optional): [N][..frames_seq_stride..] like render_v1. */
+int mivit_render_embed_linear(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
+                              uint64_t seq_offset, const float* Wt, const float* bias, int32_t E, float* emb,
+                              float* frames_out, int64_t frames_seq_stride, void* stream);
+
 /* Replaces Experiments/PSFNoise/trainSettingsPSFNoise.py:196-309 trajs_to_vid_psf_noise.
  * psf_div[n_psf], noise_frac[n_noise] are HOST arrays (PSF_Settings, Noise_Settings);
  * part_mean_global is the module-level `part_mean` used for the background sigma (:302).

@@ -127,6 +127,44 @@ __device__ __forceinline__ float pixel_signal(const RenderDev& d, const WarpSmem
   return acc;
 }
 
+// spot intensities of the n sub-positions of frame f  (helpersGeneration.py:300)
+__device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, int f, int lane, uint32_t seq) {
+  const int n = d.n;
+  for (int p = lane; p < n; p += 32) {
+    float z = 0.0f, z1;
+    if (!d.mean_noise) {
+      const uint4 r = philox4x32_10((uint32_t)(f * n + p), 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
+      box_muller(r.x, r.y, z, z1);
+    }
+    float I = __fadd_rn(d.imean, __fmul_rn(d.istd, z));
+    if ((double)w.msq[p] * d.inv2s2_d > 745.0) I = __int_as_float(0x7fc00000);  // spot underflows: NaN frame (:305-308)
+    w.inten[p] = I;
+  }
+}
+
+// one output pixel of frame f: signal + clipped Gaussian background, multiplicative Poisson, fused normalisation
+__device__ __forceinline__ float v1_pixel(const RenderDev& d, const WarpSmem& w, int f, int pix, uint32_t seq) {
+  const int P = d.P;
+  const int a = pix / P, b = pix - a * P;
+  float v = d.draw ? pixel_signal(d, w, a, b) : 0.0f;
+  PixelStream st;
+  float zb = 0.0f, z1;
+  if (!d.mean_noise) {
+    st.item = (uint32_t)(f * P * P + pix); st.seq = seq; st.sw = stream_word(MIVIT_STREAM_PIXEL, 0);
+    st.k0 = d.k0; st.k1 = d.k1; st.q = 0;
+    st.cur = philox4x32_10(st.item, 0u, seq, st.sw, d.k0, d.k1);
+    box_muller(st.cur.x, st.cur.y, zb, z1);
+  }
+  const float bg = fminf(fmaxf(__fadd_rn(d.bg_mean, __fmul_rn(d.bg_std, zb)), 0.0f), d.bg_hi);  // :312-313
+  v = __fadd_rn(v, bg);
+  if (d.poisson != -1.0f) {  // :316-317 multiplicative Poisson
+    const float k = d.mean_noise ? d.poisson : poisson_draw(d.poisson, st);
+    v = __fdiv_rn(__fmul_rn(v, k), d.poisson);
+  }
+  if (d.normalize) v = __fdiv_rn(__fsub_rn(v, d.norm_sub), d.norm_div);  // :395
+  return v;
+}
+
 __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict__ traj, long long n_frames_total,
                                                         RenderDev d, float* __restrict__ out) {
   extern __shared__ float smem[];
@@ -143,40 +181,58 @@ __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict
   if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
   __syncwarp();
   if (d.draw) {
-    for (int p = lane; p < n; p += 32) {  // spot intensities (helpersGeneration.py:300)
-      float z = 0.0f, z1;
-      if (!d.mean_noise) {
-        const uint4 r = philox4x32_10((uint32_t)(f * n + p), 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
-        box_muller(r.x, r.y, z, z1);
-      }
-      float I = __fadd_rn(d.imean, __fmul_rn(d.istd, z));
-      if ((double)w.msq[p] * d.inv2s2_d > 745.0) I = __int_as_float(0x7fc00000);  // spot underflows: NaN frame (:305-308)
-      w.inten[p] = I;
-    }
+    v1_intensities(d, w, f, lane, seq);
     __syncwarp();
     axis_table(d, d.inv2s2, lane, w);
     __syncwarp();
   }
   float* dst = out + s * d.out_seq_stride + (long long)f * P * P;
-  for (int pix = lane; pix < P * P; pix += 32) {
-    const int a = pix / P, b = pix - a * P;
-    float v = d.draw ? pixel_signal(d, w, a, b) : 0.0f;
-    PixelStream st;
-    float zb = 0.0f, z1;
-    if (!d.mean_noise) {
-      st.item = (uint32_t)(f * P * P + pix); st.seq = seq; st.sw = stream_word(MIVIT_STREAM_PIXEL, 0);
-      st.k0 = d.k0; st.k1 = d.k1; st.q = 0;
-      st.cur = philox4x32_10(st.item, 0u, seq, st.sw, d.k0, d.k1);
-      box_muller(st.cur.x, st.cur.y, zb, z1);
+  for (int pix = lane; pix < P * P; pix += 32) dst[pix] = v1_pixel(d, w, f, pix, seq);
+}
+
+// Renderer fused with the frame embedding of LinearProjectionEmbedding / CNNEmbedding (helpers/models.py:146-199:
+// both are emb[f,:] = W[E,P*P] . frame[f] + b): the frame lives only in the warp's shared memory, the kernel writes
+// [N,F,E] embeddings (and, optionally, the frames for a later weight gradient).  Persistent CTAs keep W^T
+// ([P*P][E], so that lanes read consecutive output features) resident in shared memory.
+__global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* __restrict__ traj, long long n_frames_total,
+                                                                  RenderDev d, const float* __restrict__ Wt,
+                                                                  const float* __restrict__ bias, int E,
+                                                                  float* __restrict__ emb, float* __restrict__ frames_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int P = d.P, n = d.n, PP = d.P * d.P;
+  float* wts = smem;                                       // [PP][E]
+  const int per_warp = warp_smem_floats(n, P) + PP;
+  float* mine = smem + (size_t)PP * E + (size_t)warp * per_warp;
+  WarpSmem w = carve(mine, n, P);
+  float* px = mine + warp_smem_floats(n, P);               // [PP] rendered frame
+  for (int i = threadIdx.x; i < PP * E; i += blockDim.x) wts[i] = __ldg(Wt + i);
+  __syncthreads();
+  for (long long gf = (long long)blockIdx.x * warps + warp; gf < n_frames_total; gf += (long long)gridDim.x * warps) {
+    const long long s = gf / d.F;
+    const int f = (int)(gf - s * d.F);
+    const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
+    if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
+    __syncwarp();
+    if (d.draw) {
+      v1_intensities(d, w, f, lane, seq);
+      __syncwarp();
+      axis_table(d, d.inv2s2, lane, w);
+      __syncwarp();
     }
-    const float bg = fminf(fmaxf(__fadd_rn(d.bg_mean, __fmul_rn(d.bg_std, zb)), 0.0f), d.bg_hi);  // :312-313
-    v = __fadd_rn(v, bg);
-    if (d.poisson != -1.0f) {  // :316-317 multiplicative Poisson
-      const float k = d.mean_noise ? d.poisson : poisson_draw(d.poisson, st);
-      v = __fdiv_rn(__fmul_rn(v, k), d.poisson);
+    for (int pix = lane; pix < PP; pix += 32) {
+      const float v = v1_pixel(d, w, f, pix, seq);
+      px[pix] = v;
+      if (frames_out != nullptr) frames_out[s * d.out_seq_stride + (long long)f * PP + pix] = v;
     }
-    if (d.normalize) v = __fdiv_rn(__fsub_rn(v, d.norm_sub), d.norm_div);  // :395
-    dst[pix] = v;
+    __syncwarp();
+    for (int e = lane; e < E; e += 32) {
+      float acc = 0.f;
+      for (int pix = 0; pix < PP; ++pix) acc = fmaf(px[pix], wts[pix * E + e], acc);   // same summation order as a K-loop GEMM
+      emb[gf * E + e] = acc + __ldg(bias + e);
+    }
+    __syncwarp();
   }
 }
 
@@ -356,6 +412,41 @@ extern "C" int mivit_render_v1(const double* traj, int64_t N, int32_t T, const m
   const long long frames = (long long)N * d.F;
   MivitProfScope prof("render_v1", (double)N * ((double)T * 16.0 + (double)d.F * d.P * d.P * 4.0), (cudaStream_t)stream);
   render_v1_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, out);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_render_embed_linear(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
+                                         uint64_t seq_offset, const float* Wt, const float* bias, int32_t E, float* emb,
+                                         float* frames_out, int64_t frames_seq_stride, void* stream) {
+  RenderDev d;
+  int rc = fill_dev(prm, T, seed, seq_offset, d);
+  if (rc) return rc;
+  MIVIT_CHECK_ARG(N >= 0 && E >= 1 && E <= 1024, "bad N / embed_dim");
+  if (N == 0) return MIVIT_OK;
+  MIVIT_CHECK_ARG(traj && Wt && bias && emb, "NULL device pointer");
+  d.imean = (float)((double)prm->part_mean / prm->n);
+  d.istd = (float)((double)prm->part_std / prm->n);
+  d.out_seq_stride = frames_seq_stride;
+  const int PP = d.P * d.P;
+  const size_t per_warp = (size_t)(warp_smem_floats(d.n, d.P) + PP) * sizeof(float);
+  const size_t wbytes = (size_t)PP * E * sizeof(float);
+  int warps = 8;
+  while (warps > 1 && wbytes + per_warp * warps > 200 * 1024) warps >>= 1;
+  const size_t smem = wbytes + per_warp * warps;
+  MIVIT_CHECK_ARG(smem <= 220 * 1024, "embedding weight (%d x %d) does not fit shared memory next to the frame tables", E, PP);
+  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_embed_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long frames = (long long)N * d.F;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  int per_sm = (int)((220 * 1024) / smem);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  long long blocks = (long long)sms * per_sm;
+  if (blocks > mivit_ceil_div(frames, warps)) blocks = mivit_ceil_div(frames, warps);
+  MivitProfScope prof("render_embed_linear", (double)N * ((double)T * 16.0 + (double)d.F * E * 4.0), (cudaStream_t)stream);
+  render_embed_linear_kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, Wt, bias, E, emb, frames_out);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["trajectories_to_video", "normalize_images", "brownian_motion", "derive_render_params",
+__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "normalize_images", "brownian_motion", "derive_render_params",
            "DEFAULT_IMAGE_PROPS", "render_device"]
 
 DEFAULT_IMAGE_PROPS = {  # helpers/helpersGeneration.py:205-222
@@ -125,6 +125,52 @@ def trajectories_to_video(trajectories, nPosPerFrame, center=False, image_props=
     if was_host:
         return out.cpu().numpy()
     return out
+
+
+def trajectories_to_embeddings(trajectories, nPosPerFrame, embedding, center=False, image_props={}, *, seed=None, seq_offset=0,
+                               normalize=None, return_frames=False, _mean_noise=False):
+    """Renderer fused with the frame embedding (no reference counterpart as ONE call: it is
+    `embedding(torch.Tensor(normalize_images(trajectories_to_video(...))))` of the training loops,
+    helpers/helpersGeneration.py:128-278,356-400 + helpers/models.py:146-199) for `LinearProjectionEmbedding` /
+    `CNNEmbedding`: returns CUDA float32 [N,F,E]; frames never touch HBM unless return_frames=True.
+    Same side effect (in-place y flip), error text, image_props and RNG streams as trajectories_to_video, so
+    `embedding(trajectories_to_video(..., seed=s))` and `trajectories_to_embeddings(..., seed=s)` see the same frames."""
+    import torch
+    from . import models as _m
+    dev = _lib.require_cuda()
+    if not isinstance(embedding, (_m.LinearProjectionEmbedding, _m.CNNEmbedding)):
+        raise TypeError("the fused render+embed kernel covers LinearProjectionEmbedding and CNNEmbedding "
+                        "(DeepResNetEmbedding needs batch statistics: render, then call the model)")
+    N, T, _ = trajectories.shape
+    trajectories[:, :, 1] *= -1
+    if T % nPosPerFrame != 0:
+        raise Exception("T is not divisble by posPerFrame")
+    prm = derive_render_params(image_props, nPosPerFrame, center, "v1")
+    prm.flip_y = 0
+    prm.mean_noise = int(bool(_mean_noise))
+    if normalize is not None:
+        m, s, mx = normalize
+        den = mx - (m - s)
+        if den == 0:
+            raise ValueError("Denominator in normalization is zero. Check your inputs.")
+        prm.normalize, prm.norm_sub, prm.norm_div = 1, float(m - s), float(den)
+    if isinstance(embedding, _m.LinearProjectionEmbedding):
+        W, b = embedding.proj.weight, embedding.proj.bias
+    else:
+        W, b = embedding.conv.weight, embedding.conv.bias
+    E = W.shape[0]
+    if W.numel() != E * prm.P * prm.P:
+        raise ValueError("embedding patch_size %d does not match output_size %d" % (int(round((W.numel() // E) ** 0.5)), prm.P))
+    Wt = W.detach().to(device=dev, dtype=torch.float32).reshape(E, prm.P * prm.P).t().contiguous()
+    bd = b.detach().to(device=dev, dtype=torch.float32).contiguous()
+    t_dev, _ = _to_device_f64(trajectories, dev)
+    F = T // nPosPerFrame
+    emb = torch.empty((N, F, E), dtype=torch.float32, device=dev)
+    frames = torch.empty((N, F, prm.P, prm.P), dtype=torch.float32, device=dev) if return_frames else None
+    _lib.check(_lib.lib().mivit_render_embed_linear(_lib.ptr(t_dev), N, T, ctypes.byref(prm), _draw_seed(seed), int(seq_offset),
+                                                    _lib.ptr(Wt), _lib.ptr(bd), E, _lib.ptr(emb), _lib.ptr(frames),
+                                                    F * prm.P * prm.P, _lib.current_stream()))
+    return (emb, frames) if return_frames else emb
 
 
 def normalize_images(images, background_mean=None, background_sigma=None, theoretical_max=None, clip_image=False):

@@ -193,3 +193,45 @@ def test_full_size_properties(gen):
     # centred particle: flux conserved up to the part of the PSF that falls outside the 13x13 window
     tot = c1.sum(dim=(2, 3))
     assert (tot > 0).all()
+
+
+# ---- renderer fused with the Linear / CNN frame embedding (north_star (1), BASELINE configs[2]) --------------------
+@pytest.mark.parametrize("kind,P,E,n", [("linear", 9, 64, 10), ("cnn", 9, 32, 10), ("linear", 13, 128, 10), ("cnn", 7, 64, 15),
+                                        ("linear", 15, 32, 30)])
+@pytest.mark.parametrize("noisy", [False, True])
+def test_fused_render_embed_matches_render_then_embed(gold, gen, kind, P, E, n, noisy):
+    """emb = W . frame + b computed inside the render kernel == the reference order of operations
+    (trajectories_to_video -> normalize_images -> embedding, helpers/models.py:160-164 / :188-197) on the SAME frames:
+    noise-free frames are checked against the reference golden pipeline through the unfused renderer, noisy ones use
+    identical Philox streams in both kernels."""
+    import torch
+    from moleculardiffusion_mivit_b200 import models as M
+    inp, _, _ = gold
+    props = dict(C3_PROPS if noisy else CLEAN, output_size=P, upsampling_factor=5)
+    norm = (1420, 290, 6000)
+    torch.manual_seed(P * 100 + E)
+    emb_mod = (M.LinearProjectionEmbedding if kind == "linear" else M.CNNEmbedding)(P, E)
+    t1, t2 = inp["traj30"][:6].copy(), inp["traj30"][:6].copy()
+    frames = gen.trajectories_to_video(t1, n, True, props, seed=11, normalize=norm, _mean_noise=not noisy)
+    emb, fr2 = gen.trajectories_to_embeddings(t2, n, emb_mod, True, props, seed=11, normalize=norm, return_frames=True,
+                                              _mean_noise=not noisy)
+    assert np.array_equal(t1, t2)                                            # same in-place y flip
+    assert emb.shape == (6, 300 // n, E) and emb.dtype == torch.float32 and emb.is_cuda
+    assert np.array_equal(fr2.cpu().numpy(), frames)                         # bit-identical frames (layout + values)
+    W = (emb_mod.proj.weight if kind == "linear" else emb_mod.conv.weight).detach().double().reshape(E, P * P)
+    b = (emb_mod.proj.bias if kind == "linear" else emb_mod.conv.bias).detach().double()
+    ref = torch.from_numpy(frames).double().reshape(6, -1, P * P) @ W.t() + b
+    err = (emb.cpu().double() - ref).abs().max().item()
+    assert err < 1e-5 * max(1.0, ref.abs().max().item()), err                # fp32 dot product of P*P terms
+    only = gen.trajectories_to_embeddings(inp["traj30"][:6].copy(), n, emb_mod, True, props, seed=11, normalize=norm,
+                                          _mean_noise=not noisy)
+    assert torch.equal(only, emb)                                            # frames_out = NULL path
+
+
+def test_fused_render_embed_rejects_deepresnet(gen, gold):
+    from moleculardiffusion_mivit_b200 import models as M
+    inp, _, _ = gold
+    with pytest.raises(TypeError, match="LinearProjectionEmbedding and CNNEmbedding"):
+        gen.trajectories_to_embeddings(inp["traj30"][:1].copy(), 10, M.DeepResNetEmbedding(9, 64), True, C3_PROPS)
+    with pytest.raises(Exception, match="T is not divisble by posPerFrame"):
+        gen.trajectories_to_embeddings(inp["traj30"][:1].copy(), 7, M.LinearProjectionEmbedding(9, 64), True, C3_PROPS)
