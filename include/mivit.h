@@ -108,6 +108,17 @@ int mivit_brownian(int64_t N, int32_t T, const float* group_mean_host, const flo
 
 /* ------------------------------------------------- ViT building blocks (tests / ViT) ---- */
 
+/* Frame-averaged positions (reference helpers/helpersGeneration.py:48-74 average_trajectories_frames):
+ * out[N][T/n][2] = mean over groups of n consecutive sub-positions of traj[N][T][2] (device float64). */
+int mivit_average_frames(const double* traj, int64_t N, int32_t T, int32_t n, double* out, void* stream);
+
+/* The 25 trajectory features the ViT takes as `features` (reference helpers/helpersFeatures.py:448-520
+ * compute_diffusion_features, order of feature_names :7-34; msd :102-132, power-law fit :135-191, efficiency :194-218,
+ * fractal_dim :221-247, gaussianity :250-284, kurtosis :287-324, msd_ratio :327-347, trappedness :350-378,
+ * convex_hull_area :381-402).  traj: device float64 [N][L][2] (already frame-averaged), out: device float64 [N][25],
+ * raw values like the reference's function (NaN / -inf where it returns them; L < 3 gives 25 NaNs).  3 <= L <= 512. */
+int mivit_diffusion_features(const double* traj, int64_t N, int32_t L, double dt, double* out, void* stream);
+
 /* Activation layout of the DeepResNetEmbedding kernels ("pitched rows", bf16, channels last):
  * frame f, pixel (y,x) -> row f*(P+1)^2 + y*(P+1) + x of a [rows, C] matrix; column P of every
  * line and line P of every frame are zero; >= 128 zero guard rows precede row 0 and follow the

@@ -46,6 +46,8 @@ def _declare(lib):
         "mivit_render_v1": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, i64, vp]),
         "mivit_render_embed_linear": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, vp, i32, vp, vp, i64, vp]),
         "mivit_render_psfnoise": (i32, [vp, i64, i32, c.POINTER(RenderParams), fp, i32, fp, i32, f32, u64, u64, vp, vp]),
+        "mivit_average_frames": (i32, [vp, i64, i32, i32, vp, vp]),
+        "mivit_diffusion_features": (i32, [vp, i64, i32, f64, vp, vp]),
         "mivit_brownian": (i32, [i64, i32, fp, fp, i32, f64, u64, u64, vp, vp, vp]),
         "mivit_conv_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "mivit_conv_rows": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]),

@@ -16,7 +16,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "normalize_images", "brownian_motion", "derive_render_params",
+__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "create_video_and_feature_pairs",
+           "average_trajectories_frames", "average_trajs_add_error", "normalize_images", "brownian_motion", "derive_render_params",
            "DEFAULT_IMAGE_PROPS", "render_device"]
 
 DEFAULT_IMAGE_PROPS = {  # helpers/helpersGeneration.py:205-222
@@ -171,6 +172,38 @@ def trajectories_to_embeddings(trajectories, nPosPerFrame, embedding, center=Fal
                                                     _lib.ptr(Wt), _lib.ptr(bd), E, _lib.ptr(emb), _lib.ptr(frames),
                                                     F * prm.P * prm.P, _lib.current_stream()))
     return (emb, frames) if return_frames else emb
+
+
+def average_trajectories_frames(trajectories, nPosFrame):
+    """helpers/helpersGeneration.py:48-74 (device kernel; numpy in, numpy out)."""
+    from . import helpersFeatures as _hf
+    return _hf.average_frames_device(_hf._to_dev(trajectories), nPosFrame).cpu().numpy()
+
+
+def average_trajs_add_error(trajectories, nPosPerFrame, localization_uncertainty):
+    """helpers/helpersGeneration.py:663-672: frame means and frame means + N(mu_loc, sigma_loc) localisation noise
+    (drawn from the global np.random state like the reference)."""
+    avg = average_trajectories_frames(trajectories, nPosPerFrame)
+    mu, sigma = localization_uncertainty
+    return avg, avg + np.random.normal(loc=mu, scale=sigma, size=avg.shape)
+
+
+def create_video_and_feature_pairs(trajectories, nPosPerFrame, center, image_props, localization_uncertainty=(0, 0), dt=1.0, *,
+                                   seed=None):
+    """helpers/helpersGeneration.py:674-719: normalised videos (N,F,P,P) float32, the 25 diffusion features (N,25)
+    float64 of the frame-averaged trajectories, and (trajectories, averaged, averaged + localisation error).
+    As in the reference the features are computed AFTER trajectories_to_video flipped the caller's y axis in place."""
+    from . import helpersFeatures as _hf
+    bg_mean, bg_sigma = image_props["background_intensity"]
+    part_mean, _ = image_props["particle_intensity"]
+    videos = trajectories_to_video(trajectories, nPosPerFrame, center=center, image_props=image_props, seed=seed,
+                                   normalize=(bg_mean, bg_sigma, part_mean + bg_mean))
+    avg_dev = _hf.average_frames_device(_hf._to_dev(trajectories), nPosPerFrame)
+    features = _hf.features_device(avg_dev, dt).cpu().numpy()
+    avg = avg_dev.cpu().numpy()
+    mu, sigma = localization_uncertainty
+    avg_err = avg + np.random.normal(loc=mu, scale=sigma, size=avg.shape)
+    return videos, features, (trajectories, avg, avg_err)
 
 
 def normalize_images(images, background_mean=None, background_sigma=None, theoretical_max=None, clip_image=False):
