@@ -245,15 +245,26 @@ __global__ void __launch_bounds__(C) pool_rows_kernel(const __nv_bfloat16* __res
 //   g = (up_a [+ up_b]  |  dpooled[f]/P^2) * 1[pre > 0],   pre = bn_pre(raw_a, raw_b) recomputed (the activation
 // tensor is not read: one HBM stream less per pass).  UP: 0 = dpooled, 1 = up_a, 2 = up_a + up_b.
 // sums[0][c] = sum g, sums[1][c] = sum g*xhat_a, sums[2][c] = sum g*xhat_b
+// The pooled upstream (UP == 0) is constant over the (P+1)^2 rows of a frame: it is kept in registers and re-read only
+// when the thread's row crosses into another frame (once per ~12 rows), not for every 16-byte chunk.
+struct PooledCache {
+  uint32_t f = 0xffffffffu;
+  float v[8];
+};
 template <int C, int UP>
 __device__ __forceinline__ void upstream8(const uint4& ua, const uint4& ub, const float* __restrict__ dpooled, uint32_t r, int ch,
-                                          const RowGeom& geo, float (&u)[8]) {
+                                          const RowGeom& geo, PooledCache& pc, float (&u)[8]) {
   if (UP == 0) {
     const uint32_t f = fast_div(r, geo.rpf);
-    const float inv = 1.0f / (float)(geo.P * geo.P);
-    load8f(dpooled + (size_t)f * C + ch * 8, u);
+    if (f != pc.f) {
+      const float inv = 1.0f / (float)(geo.P * geo.P);
+      load8f(dpooled + (size_t)f * C + ch * 8, pc.v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] *= inv;
+      for (int i = 0; i < 8; ++i) pc.v[i] *= inv;
+      pc.f = f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = pc.v[i];
   } else {
     unpack8(ua, u);
     if (UP == 2) {
@@ -286,6 +297,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
   }
   // sum g*xhat = invstd * (sum g*x - mean * sum g): accumulate sum g*x and fix up once at the end
   float s0[8] = {}, s1[8] = {}, s2[8] = {};
+  PooledCache pcache;
   for (long long r = r0 + rl; r < r1; r += kU * RL) {
     uint4 va[kU], vb[kU], ua[kU], ub[kU];
 #pragma unroll
@@ -308,7 +320,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
       unpack8(va[u], a);
       if (DUAL) unpack8(vb[u], b);
       bn_pre<DUAL>(a, sa, ha, b, sb, hb, pre);
-      upstream8<C, UP>(ua[u], ub[u], dpooled, (uint32_t)rr, ch, geo, g);
+      upstream8<C, UP>(ua[u], ub[u], dpooled, (uint32_t)rr, ch, geo, pcache, g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float gi = pre[i] > 0.f ? g[i] : 0.f;
@@ -383,6 +395,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16*
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
   const long long r0 = (long long)blockIdx.x * kRowsPerCta;
   const long long r1 = min(rows_pad, r0 + kRowsPerCta);
+  PooledCache pcache;
   for (long long r = r0 + rl; r < r1; r += kU * RL) {
     uint4 va[kU], vb[kU], ua[kU], ub[kU];
 #pragma unroll
@@ -414,7 +427,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16*
         unpack8(va[u], a);
         if (DUAL) unpack8(vb[u], b);
         bn_pre<DUAL>(a, sa, ha, b, sb, hb, pre);
-        upstream8<C, UP>(ua[u], ub[u], dpooled, (uint32_t)rr, ch, geo, g);
+        upstream8<C, UP>(ua[u], ub[u], dpooled, (uint32_t)rr, ch, geo, pcache, g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = pre[i] > 0.f ? g[i] : 0.f;
         float k1[8], k2[8], k3[8];
