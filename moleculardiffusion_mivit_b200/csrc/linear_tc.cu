@@ -51,6 +51,23 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       : "memory");
 }
 
+// TMEM columns are allocated by need (power of two >= 32), not 512: with <= 256 columns and <= 113 KB of shared memory
+// two CTAs share an SM, so the second tile of an SM no longer waits for the first one's load-MMA-store chain (these
+// launches are latency-bound: 12.5 us fixed + 2.5 us per 1024 sequences).
+__device__ __forceinline__ void tmem_alloc_n(uint32_t* slot, int cols) {
+  if (cols <= 64) umma::tmem_alloc<64>(slot);
+  else if (cols <= 128) umma::tmem_alloc<128>(slot);
+  else if (cols <= 256) umma::tmem_alloc<256>(slot);
+  else umma::tmem_alloc<512>(slot);
+}
+__device__ __forceinline__ void tmem_dealloc_n(uint32_t taddr, int cols) {
+  if (cols <= 64) umma::tmem_dealloc<64>(taddr);
+  else if (cols <= 128) umma::tmem_dealloc<128>(taddr);
+  else if (cols <= 256) umma::tmem_dealloc<256>(taddr);
+  else umma::tmem_dealloc<512>(taddr);
+}
+__host__ __device__ inline int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
 // ------------------------------------------------------------------ forward / dgrad -------------
 // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-7 producers.
 template <bool BMN>
@@ -64,7 +81,8 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
   uint8_t* wsm = smem;                         // K-major: [K/4][N][16B]   MN-major: mn_off atoms
   uint8_t* slab0 = wsm + (size_t)K * N * 4;
   uint8_t* slab1 = slab0 + slab_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slab1 + slab_bytes);
+  uint8_t* stage = slab1 + slab_bytes;         // 4 epilogue warps x 4 KB transposition blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 4 * 4096);
   uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
@@ -77,7 +95,8 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
     }
     umma::mbar_fence_init();
   }
-  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  const int acc_cols = pow2_cols(N);            // two accumulators, acc_cols columns apart
+  if (warp == 0) tmem_alloc_n(tmem_slot, 2 * acc_cols);
   if (!BMN) {  // W[N][K] -> [K/4][N][16B]
     for (int i = tid; i < kch * N; i += 256) {
       const int n = i / kch, c = i - n * kch;
@@ -95,7 +114,6 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const int acc_cols = N <= 256 ? 256 : 256;   // two accumulators, 256 columns apart
 
   if (warp >= 5) {
     const int pt = (warp - 5) * 32 + lane;
@@ -153,11 +171,14 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
       const int buf = k & 1;
       umma::mbar_wait(tfull + buf, (k >> 1) & 1);
       umma::fence_after_sync();
-      const long long r = (long long)tile * kRows + warp * 32 + lane;
-      const bool ok = r < M;
+      const long long row0 = (long long)tile * kRows + warp * 32;
       const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols);
-      float* dst = Y + r * N;
       const int groups = N / 32;          // N % 32 == 0 on this path
+      // Each warp transposes its 32 rows x 32 columns through a private, XOR-swizzled 4 KB staging block so that the
+      // global stores are 128 contiguous bytes per row (a thread owns a ROW of the accumulator: storing straight from
+      // registers wrote 16-byte pieces 4*N bytes apart, 32 lines per instruction, and capped the kernel at ~1.1 TB/s).
+      float4* stg = reinterpret_cast<float4*>(stage + warp * 4096);
+      const int c = lane & 7, rsub = lane >> 3;
       for (int g = 0; g < groups; ++g) {
         float v[32];
         umma::tmem_ld32(acc + (uint32_t)(g * 32), v);
@@ -166,15 +187,18 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
           __syncwarp();
           if (lane == 0) arrive(tempty + buf);
         }
-        if (ok) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            if (bias != nullptr) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + g * 32) + q);
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            float4* p = reinterpret_cast<float4*>(dst + g * 32) + q;
+        for (int q = 0; q < 8; ++q) stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(bias + g * 32) + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rsub;
+          if (row0 + row < M) {
+            float4 o = stg[row * 8 + (c ^ (row & 7))];
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            float4* p = reinterpret_cast<float4*>(Y + (row0 + row) * N + g * 32) + c;
             if (accumulate) {
               const float4 old = *p;
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
@@ -183,12 +207,13 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
             *p = o;
           }
         }
+        __syncwarp();
       }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc<512>(tmem);
+  if (warp == 0) tmem_dealloc_n(tmem, 2 * acc_cols);
 }
 
 // ------------------------------------------------------------------ weight gradient -------------
@@ -216,7 +241,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
     umma::mbar_init(done, 1);
     umma::mbar_fence_init();
   }
-  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc_n(tmem_slot, K + 32);
   // bias gradient for free: a 33rd..-th column group of the B operand whose first column is all ones makes accumulator
   // column K the column sum of dY (db).  The group lives behind the X slab of both stage buffers and is written once.
   if (db != nullptr) {
@@ -309,7 +334,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc<512>(tmem);
+  if (warp == 0) tmem_dealloc_n(tmem, K + 32);
 }
 
 int sm_count() {
@@ -322,16 +347,17 @@ int sm_count() {
 
 bool linear_tc_supported(int M, int K, int N) {
   return M >= 512 && K % 8 == 0 && N % 32 == 0 && K >= 8 && N >= 32 && N <= 256 && K <= 256 &&
-         (size_t)K * N * 4 + 2 * (size_t)(K / 4) * kRows * 16 + 256 <= 220 * 1024;
+         (size_t)K * N * 4 + 2 * (size_t)(K / 4) * kRows * 16 + 4 * 4096 + 256 <= 227 * 1024;
 }
 
 // mode 0: Y = A W^T (+bias)(relu), W [N][K].   mode 1: Y (+)= A W, W [K][N].
 int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M, int K, int N, int mode, int relu, int accumulate,
               cudaStream_t st) {
-  int smem = K * N * 4 + 2 * (K / 4) * kRows * 16 + 256;
-  if (smem < 120 * 1024) smem = 120 * 1024;
+  int smem = K * N * 4 + 2 * (K / 4) * kRows * 16 + 4 * 4096 + 256;
+  if (2 * pow2_cols(N) > 256 && smem < 120 * 1024) smem = 120 * 1024;   // 512 TMEM columns: one CTA per SM
   const int n_tiles = (M + kRows - 1) / kRows;
-  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  const int per_sm = (smem <= 113 * 1024 && 2 * pow2_cols(N) <= 256) ? 2 : 1;
+  const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
   MivitProfScope prof(mode ? "linear_tc_dgrad" : "linear_tc_fwd", 2.0 * M * K * N, st);
   if (mode == 0) {
     MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -360,7 +386,7 @@ int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M
   const int need = 32 * kRows * 16;
   if (buf_bytes < need) buf_bytes = need;
   int smem = 2 * buf_bytes + 256;
-  if (smem < 120 * 1024) smem = 120 * 1024;
+  if (K + 32 > 256 && smem < 120 * 1024) smem = 120 * 1024;   // 512 TMEM columns: one CTA per SM
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_stages = (M + kRows - 1) / kRows;
   int ctas = n_stages < sm_count() ? n_stages : sm_count();

@@ -5,7 +5,8 @@ import torch
 sys.path.insert(0, ".")
 from moleculardiffusion_mivit_b200 import _lib  # noqa: E402
 L = _lib.lib()
-M = 1024 * 31
+import os
+M = int(os.environ.get("NSEQ", "1024")) * 31
 REPS = 20
 
 
