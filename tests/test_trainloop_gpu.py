@@ -1,0 +1,60 @@
+"""GPU test (-m gpu) of the experiment-loop mirror (moleculardiffusion_mivit_b200/trainloop.py) of
+Experiments/PSFNoise/trainModelsPSFNoise.py:113-251: batch-size schedule, per-model training over the cycle's data,
+StepLR per cycle, eval-mode validation losses in the reference's dict layout, results file interchange."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PSF, NOISE = [2, 1], [0, 1 / 20]
+PROPS = {"particle_intensity": [5000, 500], "NA": 1.46, "wavelength": 500e-9, "psf_division_factor": 1.3, "resolution": 100e-9,
+         "output_size": 9, "upsampling_factor": 5, "background_intensity": [5000, 0], "poisson_noise": 100, "trajectory_unit": 1200}
+
+
+def make_prediction(model, name, images, eval=True):       # trainSettingsPSFNoise.py:164-172
+    prefix, psf_index, noise_index = name.split("_")
+    return model(images[:, int(psf_index), int(noise_index)])
+
+
+def test_two_cycles_psfnoise_layout(golden_dir, tmp_path):
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M, experiments as X, trainloop as TL
+    torch.manual_seed(0)
+    names = ["tr_0_0", "tr_1_1"]
+    models = {n: M.GeneralTransformer(M.LinearProjectionEmbedding, {"patch_size": 9, "embed_dim": 32}, 32, 2, 64, 2, M.MLPHead,
+                                      F.relu, 0.0, False, True, True).cuda() for n in names}
+    render = lambda t: X.trajs_to_vid_psf_noise(t, 10, center=True, image_props=PROPS, PSF_Settings=PSF, Noise_Settings=NOISE, seed=3)
+    inp = np.load(os.path.join(golden_dir, "render_inputs.npz"))["traj30"]
+    val = [(render(inp[:3].copy()), 1.0), (render(inp[3:6].copy()), 7.0)]
+    assert val[0][0].shape == (3, 2, 2, 30, 9, 9)
+    prefix = str(tmp_path / "training_results_PSFNoise")
+    loop = TL.ExperimentLoop(models, render, make_prediction, val, T=300, N=6, TrainingDs_list=[[1, 1], [10.2, 1]],
+                             adaptive_batch_size=1, seed=1, results_prefix=prefix)
+    w0 = {n: m.state_dict()["mlp_head.mlp.3.weight"].clone() for n, m in models.items()}
+    assert loop.batch_size == 1
+    losses = loop.run(2)
+    assert loop.batch_size == 2                                   # doubled at cycle 1 (adaptive_batch_size = 1)
+    assert len(loop.all_gen_labels) == 2 * (6 + 3) and np.all(loop.all_gen_labels > 0)   # N and N // 2 for the 10.2 group
+    for n in names:
+        assert set(losses[n]) == {"val_1.0", "val_7.0", "val_avg"} and all(len(v) == 2 for v in losses[n].values())
+        assert abs(losses[n]["val_avg"][-1] - 0.5 * (losses[n]["val_1.0"][-1] + losses[n]["val_7.0"][-1])) < 1e-6
+        assert not torch.equal(w0[n], models[n].state_dict()["mlp_head.mlp.3.weight"])          # it trained
+        assert loop.trainers[n].step_count == 9 + 5 and loop.trainers[n].epoch == 2              # ceil(9/1) + ceil(9/2) steps
+    # validation loss = MSE(pred * D_max, D) in eval mode (:206-238)
+    m = models["tr_1_1"].eval()
+    with torch.no_grad():
+        manual = F.mse_loss(m(torch.as_tensor(val[1][0]).float().cuda()[:, 1, 1]) * 10.0, torch.full((3, 1), 7.0, device="cuda")).item()
+    assert abs(manual - losses["tr_1_1"]["val_7.0"][-1]) < 1e-5 * max(1.0, manual)
+    # results files: last cycles (suffix = cycles remaining) and the final one; the reference's key layout
+    for suffix in ("2", "1", ""):
+        assert os.path.exists(prefix + suffix + ".pth")
+    res = torch.load(prefix + ".pth", weights_only=False)
+    assert set(res) == {"validation_losses", "all_labels", "model_weights"} and set(res["model_weights"]) == set(names)
+    ref_keys = set(k[3:] for k in np.load(os.path.join(golden_dir, "vit_linear_s_feat_late.npz")).files if k.startswith("sd/"))
+    mine = set(res["model_weights"]["tr_0_0"])
+    assert {k for k in ref_keys if not k.startswith("feature_projector")} - {"transformer.encoder_layers.2.self_attn.q_proj.weight"} \
+        >= {k for k in mine if "encoder_layers.2" not in k} - set()                                # same naming scheme
+    assert "embedding.proj.weight" in mine and "mlp_head.mlp.3.bias" in mine and "reg_token" in mine
