@@ -48,12 +48,15 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-template <int CIN, int NS, bool SKIP, int TAPS>
+template <int CIN, int NS, bool SKIP, int TAPS, int CIN2 = 0>
 struct Cfg3 {
   static constexpr int kCH = CIN / 8;
   static constexpr int kWBytes = TAPS * CIN * NS * 2;
-  static constexpr int kStageBufs = kWBytes > 128 * 1024 ? 1 : 2;      // 147 KB of resident weights leave room for one
+  static constexpr int kW2Bytes = CIN2 * NS * 2;                     // second input (1x1 path into the same accumulator)
+  static constexpr int kRegions2 = CIN2 / 64;
+  static constexpr int kStageBufs = kWBytes + kW2Bytes > 128 * 1024 ? 1 : 2;      // 147 KB of resident weights leave room for one
   static constexpr int kRegions = CIN >= 64 ? CIN / 64 : 1;          // pipeline units (64-channel regions) per tile
+  static constexpr int kUnits = kRegions + kRegions2;
   static constexpr int kPitch = CIN >= 64 ? 128 : 64;                // bytes per input-tile row
   static constexpr int kKPerRegion = (CIN >= 64 ? 64 : CIN) / 16;    // K = 16 MMAs per tap and region
   static constexpr int kWSkipBytes = SKIP ? CIN * NS * 2 : 0;
@@ -67,20 +70,22 @@ struct Cfg3 {
   static constexpr int kStageBytes = kTileM * kOutPitch;
 };
 
-template <int CIN, int NS, bool SKIP, int TAPS>
+template <int CIN, int NS, bool SKIP, int TAPS, int CIN2>
 __global__ void __launch_bounds__(256, 1)
 conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                     const __grid_constant__ CUtensorMap tmYsk, const __nv_bfloat16* __restrict__ Wp,
-                     const __nv_bfloat16* __restrict__ Wsk, float* __restrict__ stats, float* __restrict__ stats_sk, long long rows,
+                     const __grid_constant__ CUtensorMap tmYsk, const __grid_constant__ CUtensorMap tmX2,
+                     const __nv_bfloat16* __restrict__ Wp, const __nv_bfloat16* __restrict__ Wsk,
+                     const __nv_bfloat16* __restrict__ Wp2, float* __restrict__ stats, float* __restrict__ stats_sk, long long rows,
                      int n_tiles, int P, ConvShifts shifts, int halo, int xslab_rows, int cout_total, int nsplit, int ring, int guard) {
-  using C = Cfg3<CIN, NS, SKIP, TAPS>;
+  using C = Cfg3<CIN, NS, SKIP, TAPS, CIN2>;
   constexpr int taps = TAPS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int unit_bytes = xslab_rows * C::kPitch;
   uint8_t* wsm = smem;                                   // [taps][CH][NS][8]   K-major, no swizzle
   uint8_t* wsk = wsm + taps * CIN * NS * 2;              // [CH][NS][8]         (SKIP)
-  uint8_t* stage0 = wsk + C::kWSkipBytes;                // 2 staged output regions (swizzled [row][kOutPitch])
+  uint8_t* w2sm = wsk + C::kWSkipBytes;                  // [CIN2/8][NS][8]     (second input, 1 tap)
+  uint8_t* stage0 = w2sm + C::kW2Bytes;                  // 1-2 staged output regions (swizzled [row][kOutPitch])
   uint8_t* slab0 = stage0 + C::kStageBufs * C::kStageBytes;   // ring of input units
   uint8_t* tail = slab0 + (size_t)ring * unit_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);    // [kMaxRing] TMA -> MMA
@@ -108,6 +113,7 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tma::prefetch_map(&tmX);
     tma::prefetch_map(&tmY);
     if (SKIP) tma::prefetch_map(&tmYsk);
+    if (CIN2 > 0) tma::prefetch_map(&tmX2);
   }
   if (warp == 0) umma::tmem_alloc<C::kTmemCols>(tmem_slot);
   for (int i = tid; i < C::kOutRegions * 2 * C::kOutW; i += 256) red[i] = 0.f;
@@ -124,6 +130,13 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int ch = i / NS, n = i - ch * NS;
         const uint4* src = reinterpret_cast<const uint4*>(Wsk) + ((size_t)ch * cout_total + col0 + n);
         reinterpret_cast<uint4*>(wsk)[i] = __ldg(src);
+      }
+    }
+    if (CIN2 > 0) {
+      for (int i = tid; i < (CIN2 / 8) * NS; i += 256) {
+        const int ch = i / NS, n = i - ch * NS;
+        const uint4* src = reinterpret_cast<const uint4*>(Wp2) + ((size_t)ch * cout_total + col0 + n);
+        reinterpret_cast<uint4*>(w2sm)[i] = __ldg(src);
       }
     }
   }
@@ -143,14 +156,19 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       for (int tile = cta_in_slice; tile < n_tiles; tile += ctas_per_slice) {
         const int row0 = guard + tile * kTileM - halo;
 #pragma unroll 1
-        for (int rg = 0; rg < C::kRegions; ++rg) {
+        for (int rg = 0; rg < C::kUnits; ++rg) {
           umma::mbar_wait(empty + slot, ph ^ 1);
           uint8_t* slab = slab0 + (size_t)slot * unit_bytes;
-          tma::expect_tx(full + slot, (uint32_t)unit_bytes);
-          for (int b = nh; b < nboxes; b += nsplit) {
+          const bool second = rg >= C::kRegions;            // a region of the second input: 128 rows, no halo
+          const int nb = second ? kTileM / kBoxRows : nboxes;
+          tma::expect_tx(full + slot, (uint32_t)(nb * kBoxRows * C::kPitch));
+          for (int b = nh; b < nb; b += nsplit) {
             uint8_t* dst = slab + (size_t)b * kBoxRows * C::kPitch;
-            if (nsplit == 1) tma::load_tile(dst, &tmX, rg * 64, row0 + b * kBoxRows, full + slot);
-            else tma::load_tile_multicast(dst, &tmX, rg * 64, row0 + b * kBoxRows, full + slot, cmask);
+            const CUtensorMap* tm = second ? &tmX2 : &tmX;
+            const int ch0 = second ? (rg - C::kRegions) * 64 : rg * 64;
+            const int row = (second ? row0 + halo : row0) + b * kBoxRows;
+            if (nsplit == 1) tma::load_tile(dst, tm, ch0, row, full + slot);
+            else tma::load_tile_multicast(dst, tm, ch0, row, full + slot, cmask);
           }
           if (++slot == ring) { slot = 0; ph ^= 1; }
         }
@@ -169,6 +187,7 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint64_t da_base = tma::make_desc_sw(umma::smem_u32(slab0) + (uint32_t)(halo * C::kPitch), 0u, (uint32_t)C::kPitch);
     const uint64_t db_base = umma::make_desc(umma::smem_u32(wsm), (uint32_t)NS * 16u, 128u);
     const uint64_t dbsk_base = umma::make_desc(umma::smem_u32(wsk), (uint32_t)NS * 16u, 128u);
+    const uint64_t db2_base = umma::make_desc(umma::smem_u32(w2sm), (uint32_t)NS * 16u, 128u);
     const uint32_t a_hi = (uint32_t)(da_base >> 32), b_hi = (uint32_t)(db_base >> 32);
     const uint32_t unit_units = (uint32_t)unit_bytes >> 4;
     int dl[TAPS];
@@ -181,8 +200,8 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const uint32_t tph = (k >> 1) & 1;
       const uint32_t acc = tmem + (uint32_t)(my_buf * C::kAccCols);
 #pragma unroll 1
-      for (int rg = 0; rg < C::kRegions; ++rg) {
-        const int u = k * C::kRegions + rg;
+      for (int rg = 0; rg < C::kUnits; ++rg) {
+        const int u = k * C::kUnits + rg;
         const int slot = u % ring;
         const uint32_t ph = (uint32_t)(u / ring) & 1u;
         umma::mbar_wait(full + slot, ph);
@@ -190,29 +209,40 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         umma::fence_after_sync();
         if (umma::elect_one()) {
           const uint32_t a_lo0 = (uint32_t)da_base + (uint32_t)slot * unit_units;
-          const uint32_t b_lo0 = (uint32_t)db_base + (uint32_t)(rg * 8 * NS);
+          if (CIN2 == 0 || rg < C::kRegions) {
+            const uint32_t b_lo0 = (uint32_t)db_base + (uint32_t)(rg * 8 * NS);
 #pragma unroll
-          for (int t = 0; t < TAPS; ++t) {
-            const uint32_t a_t = a_lo0 + (uint32_t)dl[t];
+            for (int t = 0; t < TAPS; ++t) {
+              const uint32_t a_t = a_lo0 + (uint32_t)dl[t];
 #pragma unroll
-            for (int j = 0; j < C::kKPerRegion; ++j) {
-              const uint64_t da = ((uint64_t)a_hi << 32) | (a_t + (uint32_t)(2 * j));
-              const uint64_t db = ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)((t * C::kCH + 2 * j) * NS));
-              umma::mma_bf16(acc, da, db, idesc, (rg > 0 || t > 0 || j > 0) ? 1u : 0u);
+              for (int j = 0; j < C::kKPerRegion; ++j) {
+                const uint64_t da = ((uint64_t)a_hi << 32) | (a_t + (uint32_t)(2 * j));
+                const uint64_t db = ((uint64_t)b_hi << 32) | (b_lo0 + (uint32_t)((t * C::kCH + 2 * j) * NS));
+                umma::mma_bf16(acc, da, db, idesc, (rg > 0 || t > 0 || j > 0) ? 1u : 0u);
+              }
             }
-          }
-          if (SKIP) {
-            const uint32_t bs_lo0 = (uint32_t)dbsk_base + (uint32_t)(rg * 8 * NS);
+            if (SKIP) {
+              const uint32_t bs_lo0 = (uint32_t)dbsk_base + (uint32_t)(rg * 8 * NS);
 #pragma unroll
-            for (int j = 0; j < C::kKPerRegion; ++j) {
-              const uint64_t da = ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(2 * j));
-              const uint64_t db = ((uint64_t)b_hi << 32) | (bs_lo0 + (uint32_t)((2 * j) * NS));
-              umma::mma_bf16(acc + NS, da, db, idesc, (rg > 0 || j > 0) ? 1u : 0u);
+              for (int j = 0; j < C::kKPerRegion; ++j) {
+                const uint64_t da = ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(2 * j));
+                const uint64_t db = ((uint64_t)b_hi << 32) | (bs_lo0 + (uint32_t)((2 * j) * NS));
+                umma::mma_bf16(acc + NS, da, db, idesc, (rg > 0 || j > 0) ? 1u : 0u);
+              }
+            }
+          } else {   // second input: rows [tile, tile+128) sit at the START of the slot (no halo), one tap, same accumulator
+            const uint32_t a2 = a_lo0 - (uint32_t)(halo * (C::kPitch / 16));
+            const uint32_t b2 = (uint32_t)db2_base + (uint32_t)((rg - C::kRegions) * 8 * NS);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t da = ((uint64_t)a_hi << 32) | (a2 + (uint32_t)(2 * j));
+              const uint64_t db = ((uint64_t)b_hi << 32) | (b2 + (uint32_t)((2 * j) * NS));
+              umma::mma_bf16(acc, da, db, idesc, 1u);
             }
           }
           if (nsplit == 1) umma::commit(empty + slot);           // unit may be refilled once these MMAs have read it
           else tma::commit_multicast(empty + slot, cmask);       // ... in both CTAs of the pair
-          if (rg == C::kRegions - 1) umma::commit(tfull + my_buf);  // accumulator ready for the epilogue
+          if (rg == C::kUnits - 1) umma::commit(tfull + my_buf);  // accumulator ready for the epilogue
         }
         __syncwarp();
       }
@@ -329,11 +359,11 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 0) umma::tmem_dealloc<C::kTmemCols>(tmem);
 }
 
-template <int CIN, int NS, bool SKIP, int TAPS>
+template <int CIN, int NS, bool SKIP, int TAPS, int CIN2 = 0>
 int launch3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y, __nv_bfloat16* Ysk,
             float* stats, float* stats_sk, long long rows, int P, int cout_total, const ConvShifts& sh, cudaStream_t st,
-            bool* fits) {
-  using C = Cfg3<CIN, NS, SKIP, TAPS>;
+            bool* fits, const __nv_bfloat16* X2 = nullptr, const __nv_bfloat16* Wp2 = nullptr) {
+  using C = Cfg3<CIN, NS, SKIP, TAPS, CIN2>;
   constexpr int taps = TAPS;
   constexpr int guard = 128;
   const int halo = taps == 1 ? 0 : P + 2;
@@ -341,28 +371,33 @@ int launch3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   *fits = halo <= guard - kBoxRows;
   if (!*fits) return MIVIT_OK;
   const int unit_bytes = xslab_rows * C::kPitch;
-  const int fixed = taps * CIN * NS * 2 + C::kWSkipBytes + C::kStageBufs * C::kStageBytes;
+  const int fixed = taps * CIN * NS * 2 + C::kWSkipBytes + C::kW2Bytes + C::kStageBufs * C::kStageBytes;
   const int tail = (2 * kMaxRing + 4) * 8 + 16 + C::kOutRegions * 2 * C::kOutW * 4 + 64;
   int ring = (227 * 1024 - fixed - tail) / unit_bytes;
   if (ring > kMaxRing) ring = kMaxRing;
-  *fits = ring >= 2 && ring >= C::kRegions;
+  *fits = ring >= 2 && ring >= C::kRegions && (CIN2 == 0 || (ring >= 3 && C::kPitch == 128));
   if (!*fits) return MIVIT_OK;
   int smem = fixed + ring * unit_bytes + tail;
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: the TMEM budget assumes it
-  auto kern = conv_rows_tc3_kernel<CIN, NS, SKIP, TAPS>;
+  auto kern = conv_rows_tc3_kernel<CIN, NS, SKIP, TAPS, CIN2>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long rows_pad = (rows + kTileM - 1) / kTileM * kTileM;
   const int n_tiles = (int)(rows_pad / kTileM);
   const int nsplit = cout_total / NS;
-  CUtensorMap tmX, tmY, tmYsk;
+  CUtensorMap tmX, tmY, tmYsk, tmX2;
   {
     int rc = make_rows_tensor_map_sw(&tmX, X - (size_t)guard * CIN, CIN, rows_pad + 2 * guard, kBoxRows);
     if (rc) return rc;
-    rc = make_rows_tensor_map_sw(&tmY, Y - (size_t)guard * cout_total, cout_total, rows_pad + 2 * guard, kTileM);
+    rc = make_rows_tensor_map_sw(&tmY, Y - (size_t)guard * cout_total, cout_total, rows_pad + 2 * guard, kTileM, C::kOutW);
     if (rc) return rc;
     tmYsk = tmY;
     if (SKIP) {
-      rc = make_rows_tensor_map_sw(&tmYsk, Ysk - (size_t)guard * cout_total, cout_total, rows_pad + 2 * guard, kTileM);
+      rc = make_rows_tensor_map_sw(&tmYsk, Ysk - (size_t)guard * cout_total, cout_total, rows_pad + 2 * guard, kTileM, C::kOutW);
+      if (rc) return rc;
+    }
+    tmX2 = tmX;
+    if (CIN2 > 0) {
+      rc = make_rows_tensor_map_sw(&tmX2, X2 - (size_t)guard * CIN2, CIN2, rows_pad + 2 * guard, kBoxRows);
       if (rc) return rc;
     }
   }
@@ -390,11 +425,11 @@ int launch3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   if (per_slice < 1) per_slice = 1;
   cfg.gridDim = dim3(per_slice * nsplit, 1, 1);
   char tag[48];
-  snprintf(tag, sizeof(tag), "conv_rows_tc_%dx%dx%d%s", CIN, cout_total, taps, SKIP ? "+skip" : "");
+  snprintf(tag, sizeof(tag), "conv_rows_tc_%dx%dx%d%s", CIN, cout_total, taps, SKIP ? "+skip" : CIN2 ? "+in2" : "");
   const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
-  MivitProfScope prof(tag, 2.0 * valid_rows * (taps + (SKIP ? 1 : 0)) * CIN * cout_total, st);
-  MIVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmX, tmY, tmYsk, Wp, Wsk, stats, stats_sk, rows, n_tiles, P, sh, halo, xslab_rows,
-                                      cout_total, nsplit, ring, guard));
+  MivitProfScope prof(tag, 2.0 * valid_rows * ((double)(taps + (SKIP ? 1 : 0)) * CIN + CIN2) * cout_total, st);
+  MIVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmX, tmY, tmYsk, tmX2, Wp, Wsk, Wp2, stats, stats_sk, rows, n_tiles, P, sh, halo,
+                                      xslab_rows, cout_total, nsplit, ring, guard));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -429,4 +464,25 @@ int conv_rows_forward_v3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const 
 #undef V3_CASE
   *handled = false;
   return MIVIT_OK;
+}
+
+// Y = conv3x3(X, Wp) + conv1x1(X2, Wp2): the input gradient of a ResidualBlock's input arrives through conv1 (3x3) and
+// through the skip convolution (1x1) (helpers/models.py:221-226 backwards); one accumulator takes both, so the two
+// partial gradients are never written to HBM and BatchNorm's backward reads one upstream tensor instead of two.
+int conv_rows_forward_dual_v3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* X2, const __nv_bfloat16* Wp2,
+                              __nv_bfloat16* Y, long long rows, int P, int cin, int cin2, int cout, const ConvShifts& sh,
+                              cudaStream_t st, bool* handled) {
+  *handled = true;
+  bool fits = true;
+  int rc = MIVIT_OK;
+  // (128 + 128 -> 64 was measured too: its resident weights force 32-column slices, and N = 32 MMAs re-read the 4 KB A
+  // operand from shared memory every 16 cycles -- 1.42 ms against 0.74 + 0.36 ms for the two separate kernels -- so block 2
+  // keeps the two-kernel path.)
+  if (cin == 64 && cin2 == 64 && cout == 32) {
+    rc = launch3<64, 32, false, 9, 64>(X, Wp, nullptr, Y, nullptr, nullptr, nullptr, rows, P, cout, sh, st, &fits, X2, Wp2);
+  } else {
+    fits = false;
+  }
+  if (!fits) *handled = false;
+  return rc;
 }

@@ -34,13 +34,15 @@ static inline int make_rows_tensor_map(CUtensorMap* tm, const void* base, int C,
 // (scripts/probe_sw128.cu): both tcgen05 K-major (rows = M) and MN-major (rows = K) descriptors read such a tile
 // correctly from a start address shifted by ANY number of rows, with base_offset = 0 (the XOR uses absolute
 // shared-memory address bits), so the 9 convolution taps are 9 start addresses into one tile.
-static inline int make_rows_tensor_map_sw(CUtensorMap* tm, const void* base, int C, long long total_rows, int box_rows) {
+static inline int make_rows_tensor_map_sw(CUtensorMap* tm, const void* base, int C, long long total_rows, int box_rows,
+                                          int box_cols = 0) {
+  if (box_cols <= 0) box_cols = C >= 64 ? 64 : C;   // 64 channels = one 128-byte swizzled row; 32 channels -> SWIZZLE_64B
   const cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)total_rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)C * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)(C >= 64 ? 64 : C), (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                                            CU_TENSOR_MAP_INTERLEAVE_NONE, C >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mivit_set_error("cuTensorMapEncodeTiled failed (%d) for C=%d rows=%lld box=%d", (int)r, C, total_rows, box_rows);
