@@ -15,6 +15,8 @@
 // through a UMMA descriptor whose start address is advanced by delta*16 bytes: 9 taps reuse
 // one slab (no im2col, no 9x re-read).  The same slab order is K-major for forward/dgrad
 // (rows = M) and MN-major for wgrad (rows = K).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "vit.h"
@@ -244,6 +246,16 @@ __global__ void conv_rows_simt_kernel(const __nv_bfloat16* __restrict__ X, const
 
 }  // namespace
 
+// MIVIT_NO_CTA_PAIRS=1 keeps the single-CTA TMA kernels for C_out = 128 (A/B measurements)
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MIVIT_NO_CTA_PAIRS");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bfloat16* Y, float* stats, long long rows,
                       int P, int cin, int cout, int taps, const ConvShifts& sh, int impl, cudaStream_t st) {
   MIVIT_CHECK_ARG(taps == 9 || taps == 1, "taps must be 1 or 9");
@@ -258,7 +270,12 @@ int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bflo
   }
   if (impl == 1) {  // pipelined kernel; falls through to the serial one if the slab does not fit
     bool handled = false;
-    int rc = conv_rows_forward_v3(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
+    int rc = MIVIT_OK;
+    if (use_cta_pairs()) {
+      rc = conv_rows_forward_v4(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);   // CTA pairs
+      if (rc || handled) return rc;
+    }
+    rc = conv_rows_forward_v3(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
     if (rc || handled) return rc;
     rc = conv_rows_forward_v2(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);
     if (rc || handled) return rc;
@@ -283,7 +300,12 @@ int conv_rows_forward_fused(const __nv_bfloat16* X, const __nv_bfloat16* Wp, con
                             int taps, const ConvShifts& sh, int impl, cudaStream_t st) {
   if (impl == 1) {
     bool handled = false;
-    int rc = conv_rows_forward_v3(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
+    int rc = MIVIT_OK;
+    if (use_cta_pairs()) {
+      rc = conv_rows_forward_v4(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);   // CTA pairs
+      if (rc || handled) return rc;
+    }
+    rc = conv_rows_forward_v3(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
     if (rc || handled) return rc;
     rc = conv_rows_forward_v2(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);
     if (rc || handled) return rc;

@@ -34,6 +34,9 @@ int conv_rows_forward_v2(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const 
 int conv_rows_forward_v3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
                          __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout, int taps,
                          const ConvShifts& sh, cudaStream_t st, bool* handled);
+int conv_rows_forward_v4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
+                         __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout, int taps,
+                         const ConvShifts& sh, cudaStream_t st, bool* handled);
 int conv_rows_forward_dual_v3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* X2, const __nv_bfloat16* Wp2,
                               __nv_bfloat16* Y, long long rows, int P, int cin, int cin2, int cout, const ConvShifts& sh,
                               cudaStream_t st, bool* handled);
