@@ -511,28 +511,49 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
   const int ch = threadIdx.x & 3;
   float acc[8][9] = {};
   const uint32_t nrows = (uint32_t)rows;
-  for (uint32_t r = blockIdx.x * 64u + (threadIdx.x >> 2); r < nrows; r += gridDim.x * 64u) {
-    const uint32_t f = r / rpf, q = r - f * rpf;
-    const int y = (int)(q / pitch), x = (int)(q - (uint32_t)y * pitch);
-    if (y >= P || x >= P) continue;
-    float g[8];
-    unpack8(ldg_stream(reinterpret_cast<const uint4*>(draw0) + (size_t)r * 4 + ch), g);
-    const float* img = frames + (size_t)f * P * P;
+  constexpr int U = 4;   // gradient rows in flight per thread (the 16-byte draw0 load is the only HBM access of the loop)
+  const uint32_t stride = gridDim.x * 64u;
+  for (uint32_t r0 = blockIdx.x * 64u + (threadIdx.x >> 2); r0 < nrows; r0 += stride * U) {
+    uint4 gv[U];
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
+    for (int u = 0; u < U; ++u) {
+      const uint32_t r = r0 + u * stride;
+      if (r < nrows) gv[u] = ldg_stream(reinterpret_cast<const uint4*>(draw0) + (size_t)r * 4 + ch);
+    }
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int yy = y + dy, xx = x + dx;
-        const float v = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + yy * P + xx) : 0.f;
-        const int t = (dy + 1) * 3 + dx + 1;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t r = r0 + u * stride;
+      if (r >= nrows) break;
+      const uint32_t f = r / rpf, q = r - f * rpf;
+      const int y = (int)(q / pitch), x = (int)(q - (uint32_t)y * pitch);
+      if (y >= P || x >= P) continue;
+      float g[8];
+      unpack8(gv[u], g);
+      const float* img = frames + (size_t)f * P * P;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i][t] = fmaf(g[i], v, acc[i][t]);
-      }
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int yy = y + dy, xx = x + dx;
+          const float v = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + yy * P + xx) : 0.f;
+          const int t = (dy + 1) * 3 + dx + 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i][t] = fmaf(g[i], v, acc[i][t]);
+        }
+    }
   }
+  // lanes l, l+4, ..., l+28 of a warp hold the same channel chunk: butterfly over them first, so that 4 lanes per warp
+  // (not 32) touch the shared accumulators -- 64-way contended shared atomics were ~75 % of this kernel's time
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(&red[(ch * 8 + i) * 9 + t], acc[i][t]);
+    for (int t = 0; t < 9; ++t) {
+      float v = acc[i][t];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 4) atomicAdd(&red[(ch * 8 + i) * 9 + t], v);
+    }
   __syncthreads();
   for (int i = threadIdx.x; i < 288; i += 256) atomicAdd(dW0 + i, red[i]);
 }
@@ -654,7 +675,7 @@ int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, lon
   MIVIT_CUDA_CHECK(cudaMemsetAsync(dW0, 0, 288 * sizeof(float), st));
   MivitProfScope prof("conv0_wgrad", (double)rows * 64, st);
   int blocks = mivit_ceil_div(rows, 64);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   conv0_wgrad_kernel<<<blocks, 256, 0, st>>>(frames, draw0, dW0, rows, P);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
