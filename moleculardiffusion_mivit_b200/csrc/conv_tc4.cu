@@ -29,8 +29,6 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kBoxRows = 32;
 constexpr int kMaxRing = 8;
-constexpr int NS = 64;     // weight columns resident per CTA
-constexpr int NT = 128;    // accumulator columns per CTA (= C_out)
 
 __device__ __forceinline__ bool row_valid4(long long r, long long rows, int P) {
   if (r < 0 || r >= rows) return false;
@@ -91,28 +89,31 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
-template <int CIN, bool SKIP, int TAPS>
+// NT = C_out = accumulator columns per CTA (128 or 64); NS = NT / 2 = weight columns resident per CTA
+template <int CIN, bool SKIP, int TAPS, int NT>
 struct Cfg4 {
+  static constexpr int NS = NT / 2;
   static constexpr int kCH = CIN / 8;
   static constexpr int kWBytes = TAPS * CIN * NS * 2;
   static constexpr int kWSkipBytes = SKIP ? CIN * NS * 2 : 0;
   static constexpr int kStageBufs = kWBytes + kWSkipBytes > 128 * 1024 ? 1 : 2;
   static constexpr int kRegions = CIN / 64;
   static constexpr int kAccCols = NT * (SKIP ? 2 : 1);
-  static constexpr int kTmemCols = 2 * kAccCols <= 256 ? 256 : 512;
+  static constexpr int kTmemCols = 2 * kAccCols <= 128 ? 128 : 2 * kAccCols <= 256 ? 256 : 512;
   static constexpr int kOutPerAcc = NT / 64;
   static constexpr int kOutRegions = kOutPerAcc * (SKIP ? 2 : 1);
   static constexpr int kStageBytes = kTileM * 128;
 };
 
-template <int CIN, bool SKIP, int TAPS>
+template <int CIN, bool SKIP, int TAPS, int NT>
 __global__ void __launch_bounds__(256, 1)
 conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                      const __grid_constant__ CUtensorMap tmYsk, const __nv_bfloat16* __restrict__ Wp,
                      const __nv_bfloat16* __restrict__ Wsk, float* __restrict__ stats, float* __restrict__ stats_sk, long long rows,
                      int n_tiles, int P, ConvShifts shifts, int halo, int xslab_rows, int ring, int guard) {
-  using C = Cfg4<CIN, SKIP, TAPS>;
+  using C = Cfg4<CIN, SKIP, TAPS, NT>;
   constexpr int taps = TAPS;
+  constexpr int NS = C::NS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int unit_bytes = xslab_rows * 128;
@@ -354,10 +355,10 @@ conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 0) tmem_dealloc_2sm<C::kTmemCols>(tmem);
 }
 
-template <int CIN, bool SKIP, int TAPS>
+template <int CIN, bool SKIP, int TAPS, int NT>
 int launch4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y, __nv_bfloat16* Ysk,
             float* stats, float* stats_sk, long long rows, int P, const ConvShifts& sh, cudaStream_t st, bool* fits) {
-  using C = Cfg4<CIN, SKIP, TAPS>;
+  using C = Cfg4<CIN, SKIP, TAPS, NT>;
   constexpr int taps = TAPS;
   constexpr int guard = 128;
   const int halo = taps == 1 ? 0 : P + 2;
@@ -371,8 +372,9 @@ int launch4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   if (ring > kMaxRing) ring = kMaxRing;
   *fits = ring >= 2 && ring >= C::kRegions;
   if (!*fits) return MIVIT_OK;
-  const int smem = fixed + ring * unit_bytes + tail;   // > 113 KB in every configuration: one CTA per SM
-  auto kern = conv_rows_tc4_kernel<CIN, SKIP, TAPS>;
+  int smem = fixed + ring * unit_bytes + tail;
+  if (smem < 120 * 1024) smem = 120 * 1024;            // one CTA per SM
+  auto kern = conv_rows_tc4_kernel<CIN, SKIP, TAPS, NT>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long rows_pad = (rows + kTileM - 1) / kTileM * kTileM;
   const int n_tiles = (int)(rows_pad / kTileM);
@@ -430,12 +432,16 @@ int conv_rows_forward_v4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const 
   *handled = true;
   bool fits = true;
   int rc = MIVIT_OK;
-  if (cout == 128 && taps == 9 && cin == 128 && !skip) rc = launch4<128, false, 9>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
+  if (cout == 128 && taps == 9 && cin == 128 && !skip) rc = launch4<128, false, 9, 128>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
+  // C_out = 64 on pairs (N = 64 per 256-row MMA, 32 weight columns per CTA) was measured too: 64 -> 64 0.69 ms vs 0.39 ms on
+  // conv_tc3, 128 -> 64 0.76 vs 0.79 ms -- each SM still streams 5 KB per 32 tensor cycles -- so those shapes stay on conv_tc3.
+  else if (cout == 64 && taps == 9 && cin == 128 && !skip && getenv("MIVIT_PAIRS_C64") != nullptr)
+    rc = launch4<128, false, 9, 64>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
   // (64 -> 128 + skip is epilogue-bound -- 256 staged columns per tile -- and measured 1.14 ms on pairs vs 0.99 ms on
   //  conv_tc3's independent half-column CTAs, so it stays there; launch4<64, true, 9> is kept compilable for experiments.)
   else if (cout == 128 && taps == 9 && cin == 64 && skip && getenv("MIVIT_PAIRS_SKIP") != nullptr)
-    rc = launch4<64, true, 9>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
-  else if (cout == 128 && taps == 9 && cin == 64 && !skip) rc = launch4<64, false, 9>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
+    rc = launch4<64, true, 9, 128>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
+  else if (cout == 128 && taps == 9 && cin == 64 && !skip) rc = launch4<64, false, 9, 128>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
   else fits = false;
   if (!fits) *handled = false;
   return rc;
