@@ -31,6 +31,7 @@ const char* mivit_last_error(void);
 /* number of kernels launched by this library since the last reset (bench.py: gpu_launches) */
 int64_t mivit_launch_count(void);
 void mivit_reset_launch_count(void);
+void mivit_add_launch_count(int64_t n); /* kernels launched as nodes of a replayed CUDA graph captured from this library */
 
 /* Optional device timing of the tagged hot kernels (CUDA events on the launching stream), used by
  * bench.py for the roofline object.  total_work = algorithmic FLOPs (convolutions) or bytes

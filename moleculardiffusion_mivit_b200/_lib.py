@@ -41,6 +41,7 @@ def _declare(lib):
         "mivit_last_error": (c.c_char_p, []),
         "mivit_launch_count": (i64, []),
         "mivit_reset_launch_count": (None, []),
+        "mivit_add_launch_count": (None, [i64]),
         "mivit_profile_enable": (None, [i32]),
         "mivit_profile_read": (i32, [c.POINTER(KernelTime), i32]),
         "mivit_render_v1": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, i64, vp]),

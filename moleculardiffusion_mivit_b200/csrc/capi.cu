@@ -21,6 +21,7 @@ extern "C" int mivit_abi_version(void) { return MIVIT_ABI_VERSION; }
 extern "C" const char* mivit_last_error(void) { return g_err; }
 extern "C" int64_t mivit_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" void mivit_reset_launch_count(void) { g_launches.store(0); }
+extern "C" void mivit_add_launch_count(int64_t n) { g_launches.fetch_add((long long)n); }
 
 // ---- optional per-kernel device timing (bench.py roofline): CUDA events around tagged launches ----
 #include <string.h>

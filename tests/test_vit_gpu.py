@@ -235,3 +235,32 @@ def test_config_sweep_matches_oracle(emb, E, H, HD, Lyr, P, Fr, B, pos, reg):
         # the bench.py shape (first case).  Tiny batches therefore get a wider bound.
         tol = 0.16 if (deep and B <= 5 and k.startswith("embedding.")) else gtol
         assert relnorm(p.grad.cpu(), r) < tol, (k, relnorm(p.grad.cpu(), r))
+
+
+def test_cuda_graph_replay_matches_eager_steps(golden_dir):
+    """MiViTTrainer(cuda_graph=True): step 1 runs eagerly, later steps replay the captured forward+loss+backward (different
+    input tensors every step -> staged through the graph's static buffers); weights, BN counters and the launch counter
+    must follow the eager trainer."""
+    import torch
+    from moleculardiffusion_mivit_b200 import _lib
+    from moleculardiffusion_mivit_b200.training import MiViTTrainer
+    z, sd, x, tgt, _ = load_case(golden_dir, "deepcnn_n")
+    g = torch.Generator().manual_seed(5)
+    xs = [(x + 0.02 * torch.randn(x.shape, generator=g)).cuda() for _ in range(4)]
+    ts = [torch.rand(tgt.shape, generator=g).cuda() for _ in range(4)]
+    out = []
+    for graph in (False, True):
+        model = build("deepcnn_n")
+        model.load_state_dict(sd)
+        model.cuda().train()
+        tr = MiViTTrainer(model, lr=1e-4, cuda_graph=graph)
+        _lib.lib().mivit_reset_launch_count()
+        losses = [tr.train_step(a, b).item() for a, b in zip(xs, ts)]
+        out.append((losses, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, _lib.lib().mivit_launch_count()))
+    (l0, s0, n0), (l1, s1, n1) = out
+    assert n0 == n1 and n0 > 400
+    assert np.allclose(l0, l1, rtol=1e-2, atol=1e-5), (l0, l1)   # fp32 atomics reorder sums; AdamW amplifies ~0 gradients
+    assert int(s1["embedding.bn1.num_batches_tracked"]) == 4
+    for k in s0:
+        if s0[k].dtype.is_floating_point:
+            assert torch.allclose(s0[k], s1[k], rtol=5e-2, atol=1e-3), k      # AdamW sign flips of ~0 gradients (atomic order)
