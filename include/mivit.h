@@ -190,6 +190,16 @@ typedef struct mivit_vit_config {
   float bn_eps, bn_momentum, ln_eps;
 } mivit_vit_config;
 
+/* Synchronised BatchNorm for data-parallel training (torch.nn.SyncBatchNorm semantics): the host registers
+ * a SUM all-reduce over its process group (training.py wraps torch.distributed.all_reduce).  While a hook with
+ * world_size > 1 is registered, every TRAINING forward / backward all-reduces the per-channel BatchNorm sums
+ * (<= 384 floats per call, 12 calls per step) through it and uses world_size x the local element count, so the
+ * normalisation, the running statistics and the gradients equal the single-process reference at the same global batch
+ * (per-rank batches must be equal).  fn is called on the calling thread with a DEVICE buffer; it must enqueue the
+ * reduction in order with `stream` and return 0.  fn == NULL unregisters. */
+typedef int (*mivit_allreduce_fn)(void* device_buf, int64_t n_floats, void* stream, void* user);
+void mivit_set_allreduce_hook(mivit_allreduce_fn fn, void* user, int32_t world_size);
+
 int32_t mivit_vit_param_count(const mivit_vit_config* cfg);                 /* -1 on a bad config */
 int mivit_vit_param_sizes(const mivit_vit_config* cfg, int64_t* sizes, int32_t max_count);
 int64_t mivit_vit_workspace_bytes(const mivit_vit_config* cfg, int32_t B);  /* -1 on a bad config */

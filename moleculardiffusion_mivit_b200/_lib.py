@@ -28,6 +28,10 @@ class KernelTime(ctypes.Structure):
                 ("total_work", ctypes.c_double)]
 
 
+# typedef int (*mivit_allreduce_fn)(void* device_buf, int64_t n_floats, void* stream, void* user)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p)
+
+
 class MivitError(RuntimeError):
     pass
 
@@ -42,6 +46,7 @@ def _declare(lib):
         "mivit_launch_count": (i64, []),
         "mivit_reset_launch_count": (None, []),
         "mivit_add_launch_count": (None, [i64]),
+        "mivit_set_allreduce_hook": (None, [ALLREDUCE_FN, vp, i32]),
         "mivit_profile_enable": (None, [i32]),
         "mivit_profile_read": (i32, [c.POINTER(KernelTime), i32]),
         "mivit_render_v1": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, i64, vp]),

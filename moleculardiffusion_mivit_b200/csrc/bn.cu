@@ -147,10 +147,16 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const __nv_bfloat16* _
   const long long r1 = min(rows_pad, r0 + kRowsPerCta);
   for (long long r = r0 + rl; r < r1; r += kU * RL) {
     uint4 va[kU], vb[kU];
+    bool ok[kU];   // pad rows (13.8 % of the rows at P = 13) are not read: their loads are predicated off, not branched around
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long rr = r + u * RL;
-      if (rr < r1) {
+      ok[u] = rr < r1 && row_is_valid((uint32_t)rr, geo);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (ok[u]) {
         va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + rr * CH + ch);
         if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + rr * CH + ch);
       }
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const __nv_bfloat16* _
       const long long rr = r + u * RL;
       if (rr >= r1) break;
       float o[8] = {};
-      if (row_is_valid((uint32_t)rr, geo)) {
+      if (ok[u]) {
         float a[8], b[8];
         unpack8(va[u], a);
         if (DUAL) unpack8(vb[u], b);
@@ -177,53 +183,116 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const __nv_bfloat16* _
 //   pooled[f,c] = mean over the P*P pixels of relu(bn2(raw_a) + bn_skip(raw_b)).
 // The block output is consumed by nothing else (the backward recomputes the ReLU mask from raw), so the
 // [rows,128] activation is never written or re-read: 3 x 1.5 GB of HBM traffic per step less.  One CTA per frame.
+// One WARP per frame (lanes = 16-byte channel chunks x row lanes, no shared memory, no block barrier): the warps of an SM
+// stream independent frames, so the loads of one overlap the shuffles / stores of another.  (One CTA per frame with a
+// shared-memory reduction spent as long in its epilogue as in its loads once the masked sums were added: 0.49 -> 0.98 ms.)
 template <int C>
-__global__ void __launch_bounds__(256) bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a,
-                                                            const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
-                                                            float* __restrict__ pooled, int P) {
-  constexpr int CH = C / 8, RL = 256 / CH;
-  const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
+__global__ void __launch_bounds__(256, 2) bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ ss_a,
+                                                               const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
+                                                               float* __restrict__ pooled, float* __restrict__ fsums, long long n_frames,
+                                                               int P) {
+  constexpr int CH = C / 8, RL = 32 / CH;
+  const int lane = threadIdx.x & 31, ch = lane % CH, rl = lane / CH;
   float sa[8], ha[8], sb[8], hb[8];
   load8f(ss_a + ch * 8, sa);
   load8f(ss_a + C + ch * 8, ha);
   load8f(ss_b + ch * 8, sb);
   load8f(ss_b + C + ch * 8, hb);
   const int pitch = P + 1, PP = P * P;
-  const long long base = (long long)blockIdx.x * pitch * pitch;
-  float acc[8] = {};
+  const float inv_pp = 1.0f / (float)PP;
   constexpr int U = 4;
-  for (int v0 = rl; v0 < PP; v0 += U * RL) {
-    uint4 va[U], vb[U];
+  for (long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); f < n_frames; f += (long long)gridDim.x * 8) {
+    const long long base = f * pitch * pitch;
+    float acc[8] = {}, ma[8] = {}, mb[8] = {};
+    uint32_t npos[4] = {0u, 0u, 0u, 0u};   // two 16-bit counters per word (a lane sees < 65536 pixels of a frame)
+    for (int v0 = rl; v0 < PP; v0 += U * RL) {
+      uint4 va[U], vb[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int v = v0 + u * RL;
-      if (v < PP) {
-        const int y = v / P, x = v - y * P;
-        const long long idx = (base + y * pitch + x) * CH + ch;
-        va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
-        vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
+      for (int u = 0; u < U; ++u) {
+        const int v = v0 + u * RL;
+        if (v < PP) {
+          const int y = v / P, x = v - y * P;
+          const long long idx = (base + y * pitch + x) * CH + ch;
+          va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
+          vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (v0 + u * RL >= PP) break;
+        float a[8], b[8], o[8];
+        unpack8(va[u], a);
+        unpack8(vb[u], b);
+        bn_pre<true>(a, sa, ha, b, sb, hb, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool on = o[i] > 0.f;
+          acc[i] += on ? o[i] : 0.f;
+          npos[i >> 1] += on ? (1u << (16 * (i & 1))) : 0u;
+          ma[i] += on ? a[i] : 0.f;      // per-frame masked sums for the backward of this BatchNorm pair (see below)
+          mb[i] += on ? b[i] : 0.f;
+        }
       }
     }
+    float cnt[8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (v0 + u * RL >= PP) break;
-      float a[8], b[8], o[8];
-      unpack8(va[u], a);
-      unpack8(vb[u], b);
-      bn_pre<true>(a, sa, ha, b, sb, hb, o);
+    for (int i = 0; i < 8; ++i) cnt[i] = (float)((npos[i >> 1] >> (16 * (i & 1))) & 0xffffu);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += fmaxf(o[i], 0.f);
+    for (int o = CH; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        cnt[i] += __shfl_xor_sync(0xffffffffu, cnt[i], o);
+        ma[i] += __shfl_xor_sync(0xffffffffu, ma[i], o);
+        mb[i] += __shfl_xor_sync(0xffffffffu, mb[i], o);
+      }
+    }
+    if (rl == 0) {
+      float4* pd = reinterpret_cast<float4*>(pooled + (size_t)f * C + ch * 8);
+      pd[0] = make_float4(acc[0] * inv_pp, acc[1] * inv_pp, acc[2] * inv_pp, acc[3] * inv_pp);
+      pd[1] = make_float4(acc[4] * inv_pp, acc[5] * inv_pp, acc[6] * inv_pp, acc[7] * inv_pp);
+      if (fsums != nullptr) {
+        float4* q = reinterpret_cast<float4*>(fsums + (size_t)f * 3 * C + ch * 8);
+        q[0] = make_float4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        q[1] = make_float4(cnt[4], cnt[5], cnt[6], cnt[7]);
+        q[C / 4] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+        q[C / 4 + 1] = make_float4(ma[4], ma[5], ma[6], ma[7]);
+        q[C / 2] = make_float4(mb[0], mb[1], mb[2], mb[3]);
+        q[C / 2 + 1] = make_float4(mb[4], mb[5], mb[6], mb[7]);
+      }
     }
   }
-  __shared__ float red[RL][C + 1];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[rl][ch * 8 + i] = acc[i];
+}
+
+// Backward reduction of the LAST BatchNorm pair without a pass over the activations.  Its upstream gradient is the pooled
+// gradient broadcast over the frame, g[r,c] = dpooled[f,c]/P^2 * 1[pre > 0], so
+//   sum_r g = sum_f dp[f,c]/P^2 * n+[f,c],   sum_r g*raw = sum_f dp[f,c]/P^2 * (sum_pix mask*raw)[f,c]
+// and the three per-frame masked sums (n+, sum mask*raw_a, sum mask*raw_b) were written by bn_apply_pool_kernel in the
+// forward ([frames][3][C] floats = 1.5 KB per frame instead of re-reading 2 x 50 KB of raw activations per frame).
+template <int C>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_pooled_kernel(const float* __restrict__ dpooled, const float* __restrict__ fsums,
+                                                                   const float* __restrict__ mi_a, const float* __restrict__ mi_b,
+                                                                   float* __restrict__ sums, long long n_frames, float inv_pp) {
+  constexpr int FL = 256 / C;
+  const int c = threadIdx.x % C, fl = threadIdx.x / C;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (long long f = (long long)blockIdx.x * FL + fl; f < n_frames; f += (long long)gridDim.x * FL) {
+    const float g = __ldg(dpooled + f * C + c) * inv_pp;
+    const float* q = fsums + f * 3 * C + c;
+    s0 = fmaf(g, __ldg(q), s0);
+    s1 = fmaf(g, __ldg(q + C), s1);
+    s2 = fmaf(g, __ldg(q + 2 * C), s2);
+  }
+  s1 = (s1 - mi_a[c] * s0) * mi_a[C + c];
+  s2 = (s2 - mi_b[c] * s0) * mi_b[C + c];
+  __shared__ float red[3][FL][C];
+  red[0][fl][c] = s0; red[1][fl][c] = s1; red[2][fl][c] = s2;
   __syncthreads();
-  if (threadIdx.x < C) {
+  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    const int k = i / C, cc = i - k * C;
     float t = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < RL; ++j) t += red[j][threadIdx.x];
-    pooled[(size_t)blockIdx.x * C + threadIdx.x] = t / (float)PP;
+    for (int j = 0; j < FL; ++j) t += red[k][j][cc];
+    atomicAdd(sums + k * C + cc, t);
   }
 }
 
@@ -300,10 +369,16 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
   PooledCache pcache;
   for (long long r = r0 + rl; r < r1; r += kU * RL) {
     uint4 va[kU], vb[kU], ua[kU], ub[kU];
+    bool ok[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long rr = r + u * RL;
-      if (rr < r1) {
+      ok[u] = rr < r1 && row_is_valid((uint32_t)rr, geo);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (ok[u]) {
         const long long idx = rr * CH + ch;
         va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
         if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
@@ -315,7 +390,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
     for (int u = 0; u < kU; ++u) {
       const long long rr = r + u * RL;
       if (rr >= r1) break;
-      if (!row_is_valid((uint32_t)rr, geo)) continue;
+      if (!ok[u]) continue;
       float a[8], b[8], pre[8], g[8];
       unpack8(va[u], a);
       if (DUAL) unpack8(vb[u], b);
@@ -362,7 +437,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
 // draw = gamma*invstd * (g - sum_g/cnt - xhat * sum_gx/cnt)  =  k1*g + k2*raw + k3  with per-channel
 //   k1 = gamma*invstd,  k2 = -k1*invstd*sum_gx/cnt,  k3 = -k1*sum_g/cnt - k2*mean
 // (coef = [k1 | k2 | k3] per BatchNorm, written by bn_bwd_coef_kernel).
-__global__ void bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ mi_a, const float* __restrict__ gamma_a,
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ sums_local, const float* __restrict__ mi_a,
+                                   const float* __restrict__ gamma_a,
                                    const float* __restrict__ mi_b, const float* __restrict__ gamma_b, float* __restrict__ coef_a,
                                    float* __restrict__ coef_b, float* __restrict__ dgamma_a, float* __restrict__ dbeta_a,
                                    float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, int C, float inv_count) {
@@ -372,18 +448,38 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ sums, const float* 
     const float k1 = gamma_a[c] * mi_a[C + c];
     const float k2 = -k1 * mi_a[C + c] * sums[C + c] * inv_count;
     coef_a[c] = k1; coef_a[C + c] = k2; coef_a[2 * C + c] = -k1 * sums[c] * inv_count - k2 * mi_a[c];
-    dgamma_a[c] = sums[C + c];
-    dbeta_a[c] = sums[c];
+    dgamma_a[c] = sums_local[C + c];
+    dbeta_a[c] = sums_local[c];
   }
   if (mi_b != nullptr) {
     const float k1 = gamma_b[c] * mi_b[C + c];
     const float k2 = -k1 * mi_b[C + c] * sums[2 * C + c] * inv_count;
     coef_b[c] = k1; coef_b[C + c] = k2; coef_b[2 * C + c] = -k1 * sums[c] * inv_count - k2 * mi_b[c];
-    dgamma_b[c] = sums[2 * C + c];
-    dbeta_b[c] = sums[c];
+    dgamma_b[c] = sums_local[2 * C + c];
+    dbeta_b[c] = sums_local[c];
   }
 }
 
+// Half (4 channels = two 32-bit words) of a 16-byte bf16x8 load, and its inverse.
+__device__ __forceinline__ void unpack4(const uint4& v, int h, float (&f)[4]) {
+  const uint32_t w0 = h ? v.z : v.x, w1 = h ? v.w : v.y;
+  f[0] = __uint_as_float(w0 << 16); f[1] = __uint_as_float(w0 & 0xffff0000u);
+  f[2] = __uint_as_float(w1 << 16); f[3] = __uint_as_float(w1 & 0xffff0000u);
+}
+__device__ __forceinline__ void pack4_into(uint4& v, int h, const float (&f)[4]) {
+  const __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&p0), w1 = *reinterpret_cast<const uint32_t*>(&p1);
+  if (h) { v.z = w0; v.w = w1; } else { v.x = w0; v.y = w1; }
+}
+__device__ __forceinline__ void ldg4f(const float* __restrict__ p, float (&v)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+
+// The 10 (20 with the skip BatchNorm) per-channel constants of a thread's 8 channels do not fit in registers next to the
+// rows in flight.  Re-reading them from L1 for EVERY row made this pass L1-bandwidth bound (12-16 LDG.128 of constants per
+// 2-3 LDG.128 of data: 4.6 TB/s); they are now read once per 4-channel half and applied to all kU rows in flight, and the
+// results overwrite the input registers half by half.
 template <int C, int UP, bool DUAL>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b, const float* __restrict__ dpooled,
@@ -395,13 +491,19 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16*
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
   const long long r0 = (long long)blockIdx.x * kRowsPerCta;
   const long long r1 = min(rows_pad, r0 + kRowsPerCta);
-  PooledCache pcache;
+  const float inv_pp = 1.0f / (float)(geo.P * geo.P);
   for (long long r = r0 + rl; r < r1; r += kU * RL) {
     uint4 va[kU], vb[kU], ua[kU], ub[kU];
+    bool ok[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long rr = r + u * RL;
-      if (rr < r1) {
+      ok[u] = rr < r1 && row_is_valid((uint32_t)rr, geo);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (ok[u]) {
         const long long idx = rr * CH + ch;
         va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
         if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
@@ -409,43 +511,80 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16*
         if (UP == 2) ub[u] = ldg_stream(reinterpret_cast<const uint4*>(up_b) + idx);
       }
     }
-    // per-channel constants are re-read from L1 per batch of rows (keeps the register budget for loads in flight)
-    float sa[8], ha[8], sb[8], hb[8];
-    load8f(ss_a + ch * 8, sa);
-    load8f(ss_a + C + ch * 8, ha);
-    if (DUAL) {
-      load8f(ss_b + ch * 8, sb);
-      load8f(ss_b + C + ch * 8, hb);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c0 = ch * 8 + 4 * h;
+      float gg[kU][4];   // masked upstream gradient of the kU rows, this half
+      {
+        float sa[4], ha[4], sb[4], hb[4];
+        ldg4f(ss_a + c0, sa); ldg4f(ss_a + C + c0, ha);
+        if (DUAL) { ldg4f(ss_b + c0, sb); ldg4f(ss_b + C + c0, hb); }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gg[u][j] = 0.f;
+          if (ok[u]) {
+            const uint32_t rr = (uint32_t)(r + u * RL);
+            float a[4], b[4], g[4];
+            unpack4(va[u], h, a);
+            if (DUAL) unpack4(vb[u], h, b);
+            if (UP == 0) {   // pooled upstream: constant over the frame, L1/L2 resident ([frames][C] floats)
+              ldg4f(dpooled + (size_t)fast_div(rr, geo.rpf) * C + c0, g);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) g[j] *= inv_pp;
+            } else {
+              unpack4(ua[u], h, g);
+              if (UP == 2) {
+                float g2[4];
+                unpack4(ub[u], h, g2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[j] += g2[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float pre = fmaf(a[j], sa[j], ha[j]);                 // == bn_pre
+              if (DUAL) pre += fmaf(b[j], sb[j], hb[j]);
+              gg[u][j] = pre > 0.f ? g[j] : 0.f;
+            }
+          }
+        }
+      }
+      {
+        float k1[4], k2[4], k3[4];
+        ldg4f(coef_a + c0, k1); ldg4f(coef_a + C + c0, k2); ldg4f(coef_a + 2 * C + c0, k3);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          float a[4], o[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ok[u]) {
+            unpack4(va[u], h, a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaf(k1[j], gg[u][j], fmaf(k2[j], a[j], k3[j]));
+          }
+          pack4_into(va[u], h, o);
+        }
+      }
+      if (DUAL) {
+        float k1[4], k2[4], k3[4];
+        ldg4f(coef_b + c0, k1); ldg4f(coef_b + C + c0, k2); ldg4f(coef_b + 2 * C + c0, k3);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          float b[4], o[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ok[u]) {
+            unpack4(vb[u], h, b);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaf(k1[j], gg[u][j], fmaf(k2[j], b[j], k3[j]));
+          }
+          pack4_into(vb[u], h, o);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long rr = r + u * RL;
       if (rr >= r1) break;
-      float oa[8] = {}, ob[8] = {};
-      if (row_is_valid((uint32_t)rr, geo)) {
-        float a[8], b[8], pre[8], g[8];
-        unpack8(va[u], a);
-        if (DUAL) unpack8(vb[u], b);
-        bn_pre<DUAL>(a, sa, ha, b, sb, hb, pre);
-        upstream8<C, UP>(ua[u], ub[u], dpooled, (uint32_t)rr, ch, geo, pcache, g);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = pre[i] > 0.f ? g[i] : 0.f;
-        float k1[8], k2[8], k3[8];
-        load8f(coef_a + ch * 8, k1);
-        load8f(coef_a + C + ch * 8, k2);
-        load8f(coef_a + 2 * C + ch * 8, k3);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) oa[i] = fmaf(k1[i], g[i], fmaf(k2[i], a[i], k3[i]));
-        if (DUAL) {
-          load8f(coef_b + ch * 8, k1);
-          load8f(coef_b + C + ch * 8, k2);
-          load8f(coef_b + 2 * C + ch * 8, k3);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ob[i] = fmaf(k1[i], g[i], fmaf(k2[i], b[i], k3[i]));
-        }
-      }
-      reinterpret_cast<uint4*>(draw_a)[rr * CH + ch] = pack8(oa);
-      if (DUAL) reinterpret_cast<uint4*>(draw_b)[rr * CH + ch] = pack8(ob);
+      reinterpret_cast<uint4*>(draw_a)[rr * CH + ch] = va[u];
+      if (DUAL) reinterpret_cast<uint4*>(draw_b)[rr * CH + ch] = vb[u];
     }
   }
 }
@@ -595,10 +734,12 @@ int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16*
 }
 
 int bn_apply_pool(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b, float* pooled,
-                  long long n_frames, int P, int C, cudaStream_t st) {
+                  float* fsums, long long n_frames, int P, int C, cudaStream_t st) {
   if (n_frames <= 0) return MIVIT_OK;
   MivitProfScope prof("bn_apply_pool", (double)n_frames * P * P * C * 2 * 2, st);
-  BN_DISPATCH_C(C, (bn_apply_pool_kernel<CC><<<(unsigned)n_frames, 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, pooled, P)));
+  long long grid = (n_frames + 7) / 8;   // one warp per frame, 8 warps per CTA, grid-stride over the frames
+  if (grid > 148 * 2 * 8) grid = 148 * 2 * 8;
+  BN_DISPATCH_C(C, (bn_apply_pool_kernel<CC><<<(unsigned)grid, 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, pooled, fsums, n_frames, P)));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -628,14 +769,24 @@ int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P
 int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* raw_a,
                 const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,
                 const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
-                float* dgamma_b, float* dbeta_b, float* sums /*[9][C] scratch: sums | coef_a | coef_b*/, long long rows,
-                long long rows_pad, int P, int C, double count, cudaStream_t st) {
+                float* dgamma_b, float* dbeta_b, float* sums /*[12][C] scratch: sums | coef_a | coef_b | local sums*/, long long rows,
+                long long rows_pad, int P, int C, double count, const float* fsums, cudaStream_t st) {
   MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
   MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
   const int rpb = 1024;
   const int blocks = mivit_ceil_div(rows, rpb);
   const RowGeom geo = make_geom(rows, P);
-  {
+  if (dpooled != nullptr && fsums != nullptr && raw_b != nullptr) {
+    const long long n_frames = rows / ((long long)(P + 1) * (P + 1));
+    MivitProfScope prof("bn_bwd_reduce_pooled", (double)n_frames * C * 16, st);
+    const int fl = 256 / C;
+    int grid = (int)((n_frames + fl - 1) / fl);
+    if (grid > 148 * 4) grid = 148 * 4;
+    BN_DISPATCH_C(C, (bn_bwd_reduce_pooled_kernel<CC><<<grid, 256, 0, st>>>(dpooled, fsums, mi_a, mi_b, sums, n_frames,
+                                                                            1.0f / (float)(P * P))));
+    mivit_count_launch();
+    MIVIT_LAUNCH_CHECK();
+  } else {
     MivitProfScope prof("bn_bwd_reduce", (double)rows * C * 2 * ((raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
     BN_BWD_LAUNCH(bn_bwd_reduce_kernel, blocks, up_a, up_b, dpooled, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, geo, rpb);
     mivit_count_launch();
@@ -644,8 +795,16 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
   // sums -> coefficient form + parameter gradients (C threads), then the streaming pass
   float* coef_a = sums + 3 * C;
   float* coef_b = sums + 6 * C;
-  bn_bwd_coef_kernel<<<mivit_ceil_div(C, 128), 128, 0, st>>>(sums, mi_a, gamma_a, raw_b ? mi_b : nullptr, gamma_b, coef_a, coef_b,
-                                                             dgamma_a, dbeta_a, dgamma_b, dbeta_b, C, (float)(1.0 / count));
+  const float* sums_local = sums;
+  if (mivit_bn_sync_world() > 1) {   // synchronised BatchNorm: coefficients from the global sums, dgamma / dbeta from the local ones
+    MIVIT_CUDA_CHECK(cudaMemcpyAsync(sums + 9 * C, sums, 3 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    sums_local = sums + 9 * C;
+    const int rc = mivit_bn_sync(sums, 3 * C, st);
+    if (rc) return rc;
+    count *= mivit_bn_sync_world();
+  }
+  bn_bwd_coef_kernel<<<mivit_ceil_div(C, 128), 128, 0, st>>>(sums, sums_local, mi_a, gamma_a, raw_b ? mi_b : nullptr, gamma_b, coef_a,
+                                                             coef_b, dgamma_a, dbeta_a, dgamma_b, dbeta_b, C, (float)(1.0 / count));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   const int ablocks = mivit_ceil_div(rows_pad, kRowsPerCta);

@@ -78,6 +78,10 @@ int tokens_finish_bwd(const float* dtok, float* dreg, float* dproj, float* dpos,
 int pool_tokens(const float* x, float* out, int B, int S, int E, int ld, int use_reg, cudaStream_t st);
 int pool_tokens_bwd(const float* dout, float* dx, int B, int S, int E, int ld, int use_reg, cudaStream_t st);
 
+// synchronised BatchNorm hook (vit_model.cu): SUM all-reduce of a small device buffer over the data-parallel group
+int mivit_bn_sync_world();                                      // 1 when no hook is registered
+int mivit_bn_sync(float* buf, long long n, cudaStream_t st);
+
 // bn.cu
 int bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                 long long* num_batches, float* mean, float* invstd, float* scale, float* shift, int C, double count, float eps,
@@ -85,13 +89,14 @@ int bn_finalize(const float* stats, const float* gamma, const float* beta, float
 int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b,
              __nv_bfloat16* act, long long rows, long long rows_pad, int P, int C, cudaStream_t st);
 int bn_apply_pool(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b, float* pooled,
-                  long long n_frames, int P, int C, cudaStream_t st);
+                  float* fsums /* [frames][3][C] masked per-frame sums for bn_backward, or NULL */, long long n_frames, int P, int C,
+                  cudaStream_t st);
 int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P, int C, cudaStream_t st);
 int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* raw_a,
                 const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,
                 const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
                 float* dgamma_b, float* dbeta_b, float* sums, long long rows, long long rows_pad, int P, int C, double count,
-                cudaStream_t st);
+                const float* fsums /* with dpooled: per-frame sums of bn_apply_pool replace the reduction pass */, cudaStream_t st);
 int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad,
                   int P, cudaStream_t st);
 int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st);

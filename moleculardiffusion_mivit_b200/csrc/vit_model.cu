@@ -118,7 +118,7 @@ struct Workspace {
   __nv_bfloat16 *wp_c1[2], *wp_c2[2], *wp_sk[2], *wd_c1[2], *wd_c2[2], *wd_sk[2];
   BnScratch bn[7];
   float* bn_sums;
-  float *pooled, *dpooled;
+  float *pooled, *dpooled, *fsums;
   // tokens
   float *emb, *m0, *r0, *tok;
   float *fp_pre, *fp_h, *fp_out;
@@ -165,8 +165,8 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
       w.bn[i].C = bc[i];
       w.bn[i].stats = b.take<float>(2 * bc[i]); w.bn[i].mi = b.take<float>(2 * bc[i]); w.bn[i].ss = b.take<float>(2 * bc[i]);
     }
-    w.bn_sums = b.take<float>(9 * 128);
-    w.pooled = b.take<float>(NF * 128); w.dpooled = b.take<float>(NF * 128);
+    w.bn_sums = b.take<float>(12 * 128);
+    w.pooled = b.take<float>(NF * 128); w.dpooled = b.take<float>(NF * 128); w.fsums = b.take<float>(NF * 3 * 128);
   }
   w.emb = b.take<float>(NF * E); w.m0 = b.take<float>(NF); w.r0 = b.take<float>(NF);
   w.tok = b.take<float>(T * E);
@@ -234,12 +234,23 @@ int zero_guards(RowsT& t, long long rows_pad, cudaStream_t st) {
   return MIVIT_OK;
 }
 
-struct BnParams { const float *g, *b; float *rm, *rv; long long* nbt; };
+// ---- synchronised BatchNorm (data-parallel parity mode) --------------------------------------------------------------
+// The host side (training.py) registers a SUM all-reduce over the data-parallel group; with it, every BatchNorm of a
+// TRAINING forward/backward uses statistics of the GLOBAL batch (torch.nn.SyncBatchNorm semantics): forward all-reduces
+// (sum x, sum x^2) per layer, backward all-reduces (sum g, sum g*xhat); counts are multiplied by the world size (equal
+// per-rank batches).  Parameter gradients keep the LOCAL sums -- the gradient all-reduce adds the ranks up afterwards.
+mivit_allreduce_fn g_ar_fn = nullptr;
+void* g_ar_user = nullptr;
+int g_ar_world = 1;
 
 int run_bn_finalize(const mivit_vit_config* c, Workspace& w, int i, const float* g, const float* bta, float* bn_running,
                     long long* nbt, double count, int training, cudaStream_t st) {
   static const int rm_off[7] = {0, 64, 192, 320, 448, 704, 960};  // [mean C | var C] per layer: 32,64,64,64,128,128,128
   BnScratch& s = w.bn[i];
+  if (training && mivit_bn_sync_world() > 1) {
+    CK(mivit_bn_sync(s.stats, 2 * s.C, st));
+    count *= mivit_bn_sync_world();
+  }
   float* rm = bn_running ? bn_running + rm_off[i] : nullptr;
   float* rv = rm ? rm + s.C : nullptr;
   return bn_finalize(s.stats, g, bta, rm, rv, nbt ? nbt + i : nullptr, s.mi, s.mi + s.C, s.ss, s.ss + s.C, s.C, count, c->bn_eps,
@@ -247,6 +258,22 @@ int run_bn_finalize(const mivit_vit_config* c, Workspace& w, int i, const float*
 }
 
 }  // namespace
+
+int mivit_bn_sync_world() { return g_ar_fn != nullptr ? g_ar_world : 1; }
+int mivit_bn_sync(float* buf, long long n, cudaStream_t st) {
+  if (g_ar_fn == nullptr || g_ar_world <= 1) return MIVIT_OK;
+  const int rc = g_ar_fn(buf, (int64_t)n, (void*)st, g_ar_user);
+  if (rc != 0) {
+    mivit_set_error("the registered all-reduce hook failed (rc = %d)", rc);
+    return MIVIT_ERR_INVALID;
+  }
+  return MIVIT_OK;
+}
+extern "C" void mivit_set_allreduce_hook(mivit_allreduce_fn fn, void* user, int32_t world_size) {
+  g_ar_fn = fn;
+  g_ar_user = user;
+  g_ar_world = fn != nullptr && world_size > 1 ? world_size : 1;
+}
 
 extern "C" int mivit_vit_param_sizes(const mivit_vit_config* cfg, int64_t* sizes, int32_t max_count) {
   ParamLayout L;
@@ -324,7 +351,7 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
       if (b == 0) {
         CK(bn_apply(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, out[b]->row0, rows, rp, P, co[b], st));
       } else {  // last block: its output only feeds the average pool -> fused, the activation is never materialised
-        CK(bn_apply_pool(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, w.pooled, NF, P, co[b], st));
+        CK(bn_apply_pool(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, w.pooled, training ? w.fsums : nullptr, NF, P, co[b], st));
       }
     }
     CK(linear_fwd(w.pooled, p + L.fc_w, p + L.fc_b, w.emb, NF, E, 128, 0, st));
@@ -457,18 +484,18 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
     if (b == 1) {
       CK(bn_backward(nullptr, nullptr, w.dpooled, r2[b]->row0, w.bn[i2].ss, w.bn[i2].mi, p + R.bn2_g, d2[b]->row0, g + R.bn2_g,
                      g + R.bn2_b, rs[b]->row0, w.bn[is].ss, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g, g + R.bns_b,
-                     w.bn_sums, rows, rp, P, co[b], cnt, st));
+                     w.bn_sums, rows, rp, P, co[b], cnt, w.fsums, st));
     } else {
       CK(bn_backward(w.dact2m.row0, fused_in[1] ? nullptr : w.dact2s.row0, nullptr, r2[b]->row0, w.bn[i2].ss, w.bn[i2].mi, p + R.bn2_g, d2[b]->row0,
                      g + R.bn2_g, g + R.bn2_b, rs[b]->row0, w.bn[is].ss, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g,
-                     g + R.bns_b, w.bn_sums, rows, rp, P, co[b], cnt, st));
+                     g + R.bns_b, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, st));
     }
     CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
     CK(conv_rows_forward(d2[b]->row0, w.wd_c2[b], da1[b]->row0, nullptr, rows, P, co[b], co[b], 9, s3m, impl, st));
     CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
     // act1 = relu(bn1(raw1))
     CK(bn_backward(da1[b]->row0, nullptr, nullptr, r1[b]->row0, w.bn[i1].ss, w.bn[i1].mi, p + R.bn1_g, d1[b]->row0, g + R.bn1_g,
-                   g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, st));
+                   g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, st));
     CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
     // gradient of the block input: conv1 path (3x3) + skip path (1x1).  Product path: ONE kernel, one accumulator, one
     // output tensor (dinm); otherwise two convolutions and BatchNorm's backward sums the two tensors.
@@ -487,7 +514,7 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
   // act0 = relu(bn0(raw0)); upstream = conv1 path + skip path of block 1
   CK(zero_guards(w.draw0, rp, st));
   CK(bn_backward(w.dact0m.row0, fused_in[0] ? nullptr : w.dact0s.row0, nullptr, w.raw0.row0, w.bn[0].ss, w.bn[0].mi, p + L.bn0_g, w.draw0.row0, g + L.bn0_g,
-                 g + L.bn0_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, 32, cnt, st));
+                 g + L.bn0_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, 32, cnt, nullptr, st));
   CK(conv0_wgrad(x, w.draw0.row0, g + L.conv0_w, rows, P, st));
   return MIVIT_OK;
 }

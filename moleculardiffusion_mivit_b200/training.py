@@ -16,7 +16,7 @@ __all__ = ["MiViTTrainer"]
 
 class MiViTTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step_size=5, gamma=0.9,
-                 process_group=None, distributed=None, cuda_graph=False):
+                 process_group=None, distributed=None, cuda_graph=False, sync_bn=False):
         if not isinstance(model, GeneralTransformer):
             raise TypeError("MiViTTrainer drives a moleculardiffusion_mivit_b200.models.GeneralTransformer")
         self.model = model
@@ -40,6 +40,28 @@ class MiViTTrainer:
         self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized())) else None
         self.group = process_group
         self.world = self.dist.get_world_size(process_group) if self.dist else 1
+        # sync_bn=True (data-parallel parity mode): BatchNorm statistics and their backward sums are all-reduced
+        # over the group inside the step (include/mivit.h: mivit_set_allreduce_hook), so W ranks with B/W sequences each
+        # reproduce the single-process step on B sequences.  Default is per-rank statistics (stock DDP semantics).
+        self.sync_bn = bool(sync_bn) and self.world > 1
+        self._hook = _lib.ALLREDUCE_FN(self._allreduce_hook) if self.sync_bn else None
+        self._hook_ws = None
+        self._hook_error = None
+
+    def _allreduce_hook(self, buf, n_floats, stream, user):
+        """C callback (mivit_allreduce_fn): SUM all-reduce of n_floats fp32 at device address `buf`, which always lies inside
+        the step's workspace tensor; enqueued by torch.distributed in order with the current stream."""
+        try:
+            ws = self._hook_ws
+            off = int(buf) - ws.data_ptr()
+            if off < 0 or off + 4 * n_floats > ws.numel() * ws.element_size() or off % 4:
+                raise ValueError("all-reduce buffer outside the workspace")
+            view = ws.view(torch.uint8).reshape(-1)[off:off + 4 * n_floats].view(torch.float32)
+            self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
+            return 0
+        except Exception as e:      # an exception must not unwind through the C frames
+            self._hook_error = e
+            return 1
 
     # StepLR(step_size, gamma): lr = base * gamma ** (epoch // step_size), stepped once per cycle
     def scheduler_step(self):
@@ -70,6 +92,8 @@ class MiViTTrainer:
         deep = cfg.embedding == 2
         self.step_count += 1
         L = _lib.lib()
+        if self.sync_bn and deep:
+            return self._sync_bn_step(x, target, features, cfg, B, ws, pred, dpred)
         if self.cuda_graph and self._replay(x, target, features, cfg, B, ws, pred, dpred, deep):
             model._gen += 1
             scale = allreduce_sum_(model._grad_flat[:model._n_params], self.group) if self.world > 1 else 1.0
@@ -90,6 +114,32 @@ class MiViTTrainer:
             _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
                                           model._n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                           self.step_count, scale, _lib.current_stream()))
+        self.last_pred = pred
+        return self.loss
+
+    def _sync_bn_step(self, x, target, features, cfg, B, ws, pred, dpred):
+        """Training step with synchronised BatchNorm: the library calls back into `_allreduce_hook` 12 times per step (7 forward
+        statistics, 5 backward sums); launched kernel by kernel (the collectives are not captured into a graph)."""
+        model = self.model
+        L = _lib.lib()
+        self._hook_ws, self._hook_error = ws, None
+        L.mivit_set_allreduce_hook(self._hook, None, self.world)
+        try:
+            rc = L.mivit_vit_train_step(
+                ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(target), _lib.ptr(model._flat),
+                _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v), _lib.ptr(model._bn_flat), _lib.ptr(model._bn_nbt),
+                _lib.ptr(ws), _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, self.step_count, 0, _lib.current_stream())
+        finally:
+            L.mivit_set_allreduce_hook(_lib.ALLREDUCE_FN(), None, 1)
+        if self._hook_error is not None:
+            raise self._hook_error
+        _lib.check(rc)
+        model._gen += 1
+        scale = allreduce_sum_(model._grad_flat[:model._n_params], self.group)
+        _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
+                                      model._n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                      self.step_count, scale, _lib.current_stream()))
         self.last_pred = pred
         return self.loss
 
