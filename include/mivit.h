@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MIVIT_ABI_VERSION 1
+#define MIVIT_ABI_VERSION 2
 
 int mivit_abi_version(void);
 const char* mivit_last_error(void);
@@ -188,6 +188,15 @@ typedef struct mivit_vit_config {
   int32_t head_hidden; /* MLPHead hidden_dim (128)                                                  */
   int32_t conv_impl;   /* 1 = tcgen05 convolutions (product path), 0 = SIMT cross-check             */
   float bn_eps, bn_momentum, ln_eps;
+  /* ModularTransformer (helpers/models.py:366-593); all four 0 for GeneralTransformer.  With modular != 0 the `features`
+   * argument of forward / backward / train_step is PER FRAME, [B,F,feat_dim] (feat_dim = features_dim), use_feat must be 0,
+   * and the flat parameter order is: image_embedding.* (as `embedding.*` above, with embed_dim - features_dim outputs for
+   * 'concat_features'), feature_embedding.{weight,bias} ('linear') or feature_embedding.{0.weight,0.bias,1.weight,1.bias,
+   * 3.weight,3.bias} ('mlp': Linear, LayerNorm, GELU, Linear), fusion_layer.{weight,bias} ('concat_proj'), then norm.* ... as above. */
+  int32_t modular;     /* 1 = ModularTransformer.forward                                             */
+  int32_t mod_mode;    /* mode: 0 'images_only', 1 'features_only' (x may be NULL), 2 'both'         */
+  int32_t mod_fembed;  /* feature_embedding_type: 0 'linear', 1 'mlp'                                */
+  int32_t mod_fusion;  /* fusion_method: 0 'add', 1 'concat_proj', 2 'concat_features'               */
 } mivit_vit_config;
 
 /* Synchronised BatchNorm for data-parallel training (torch.nn.SyncBatchNorm semantics): the host registers

@@ -397,6 +397,21 @@ __global__ void act_bwd_kernel(const float* __restrict__ dpost, const float* __r
   if (i < n) dpre[i] = dpost[i] * act_grad(pre[i], mode);
 }
 
+// torch.nan_to_num(features, nan=0.0) of ModularTransformer.forward (helpers/models.py:535,550): NaN -> 0,
+// +inf / -inf -> the largest / smallest finite float32 (torch's defaults for posinf / neginf).
+__global__ void nan_to_num_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = in[i];
+  if (v != v) v = 0.f;
+  else if (isinf(v)) v = v > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+  out[i] = v;
+}
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
 // ---------------------------------------------------------------- token assembly --------
 // tokens[b,0,:] = reg (+ proj[b,:]) when use_reg;  tokens[b,s,:] += pos[s,:] when use_pos.
 __global__ void tokens_finish_kernel(float* __restrict__ tok, const float* __restrict__ reg, const float* __restrict__ proj,
@@ -573,6 +588,14 @@ int attention_bwd(const float* q, const float* k, const float* v, const float* p
 
 int act_fwd(const float* pre, float* post, long long n, int mode, cudaStream_t st) {
   LAUNCH_1D(act_fwd_kernel, n, pre, post, n, mode);
+  return MIVIT_OK;
+}
+int nan_to_num_f32(const float* in, float* out, long long n, cudaStream_t st) {
+  LAUNCH_1D(nan_to_num_kernel, n, in, out, n);
+  return MIVIT_OK;
+}
+int add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+  LAUNCH_1D(add_kernel, n, a, b, out, n);
   return MIVIT_OK;
 }
 int act_bwd(const float* dpost, const float* pre, float* dpre, long long n, int mode, cudaStream_t st) {

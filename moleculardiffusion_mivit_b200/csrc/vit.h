@@ -72,6 +72,8 @@ int attention_fwd(const float* q, const float* k, const float* v, float* ctx, fl
 int attention_bwd(const float* q, const float* k, const float* v, const float* probs, const float* ctx, const float* dctx,
                   float* dq, float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st);
 int act_fwd(const float* pre, float* post, long long n, int mode, cudaStream_t st);
+int nan_to_num_f32(const float* in, float* out, long long n, cudaStream_t st);
+int add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st);
 int act_bwd(const float* dpost, const float* pre, float* dpre, long long n, int mode, cudaStream_t st);
 int tokens_finish(float* tok, const float* reg, const float* proj, const float* pos, int B, int S, int E, cudaStream_t st);
 int tokens_finish_bwd(const float* dtok, float* dreg, float* dproj, float* dpos, int B, int S, int E, cudaStream_t st);

@@ -39,7 +39,17 @@ struct ParamLayout {
   struct Lyr { long q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, n1_g, n1_b, f1_w, f1_b, f2_w, f2_b, n2_g, n2_b; } lyr[kMaxLayers];
   long tn_g, tn_b, fp0_w = -1, fp0_b = -1, fp2_w = -1, fp2_b = -1, h0_w, h0_b, h3_w, h3_b;
   int head_in = 0;
+  // ModularTransformer (helpers/models.py:366-593)
+  long fe0_w = -1, fe0_b = -1, feln_g = -1, feln_b = -1, fe3_w = -1, fe3_b = -1, fu_w = -1, fu_b = -1;
+  int E_img = 0;         // output width of the image embedding (embed_dim - features_dim for 'concat_features')
+  bool has_img = true;   // an image embedding exists (everything but 'features_only')
+  bool has_femb = false; // a feature embedding exists ('features_only' / 'both' unless 'concat_features')
 };
+
+// width of the image embedding output
+inline int image_embed_dim(const mivit_vit_config* c) {
+  return (c->modular && c->mod_mode == 2 && c->mod_fusion == 2) ? c->E - c->feat_dim : c->E;
+}
 
 int build_layout(const mivit_vit_config* c, ParamLayout& L) {
   MIVIT_CHECK_ARG(c != nullptr, "config is NULL");
@@ -49,7 +59,23 @@ int build_layout(const mivit_vit_config* c, ParamLayout& L) {
   MIVIT_CHECK_ARG(c->P >= 1 && c->P <= 100 && c->F >= 1, "bad patch size / frame count");
   MIVIT_CHECK_ARG(c->F + (c->use_reg ? 1 : 0) <= 128, "more than MAX_TOKENS = 128 tokens");
   const int E = c->E, HD = c->HD, PP = c->P * c->P;
-  if (c->embedding == 2) {
+  if (c->modular) {
+    MIVIT_CHECK_ARG(c->mod_mode >= 0 && c->mod_mode <= 2, "mode must be one of: 'images_only', 'features_only', 'both'");
+    MIVIT_CHECK_ARG(c->mod_fusion >= 0 && c->mod_fusion <= 2, "fusion_method must be one of: 'add', 'concat_proj', 'concat_features'");
+    MIVIT_CHECK_ARG(c->mod_fembed >= 0 && c->mod_fembed <= 1, "Unknown feature_embedding_type");
+    MIVIT_CHECK_ARG(!c->use_feat, "global features (use_feat) belong to GeneralTransformer, not to ModularTransformer");
+    MIVIT_CHECK_ARG(c->mod_mode == 0 || c->feat_dim >= 1, "features_dim must be provided when using features");
+    MIVIT_CHECK_ARG(image_embed_dim(c) > 0, "embed_dim (%d) must be greater than features_dim (%d) when using 'concat_features' fusion",
+                    c->E, c->feat_dim);
+    MIVIT_CHECK_ARG(!(c->mod_mode != 0 && c->mod_fembed == 1) || 2 * E <= 256, "'mlp' feature embedding needs embed_dim <= 128");
+  }
+  L.E_img = image_embed_dim(c);
+  L.has_img = !c->modular || c->mod_mode != 1;
+  L.has_femb = c->modular && c->mod_mode != 0 && !(c->mod_mode == 2 && c->mod_fusion == 2);
+  const int Ei = L.E_img;
+  if (!L.has_img) {
+    // 'features_only': no image embedding
+  } else if (c->embedding == 2) {
     L.conv0_w = L.add(32 * 9); L.bn0_g = L.add(32); L.bn0_b = L.add(32);
     const int ci[2] = {32, 64}, co[2] = {64, 128};
     for (int b = 0; b < 2; ++b) {
@@ -57,10 +83,20 @@ int build_layout(const mivit_vit_config* c, ParamLayout& L) {
       L.rb[b].c2_w = L.add((long)co[b] * co[b] * 9); L.rb[b].bn2_g = L.add(co[b]); L.rb[b].bn2_b = L.add(co[b]);
       L.rb[b].sk_w = L.add((long)co[b] * ci[b]); L.rb[b].bns_g = L.add(co[b]); L.rb[b].bns_b = L.add(co[b]);
     }
-    L.fc_w = L.add((long)E * 128); L.fc_b = L.add(E);
+    L.fc_w = L.add((long)Ei * 128); L.fc_b = L.add(Ei);
   } else {
-    L.proj_w = L.add((long)E * PP); L.proj_b = L.add(E);
+    L.proj_w = L.add((long)Ei * PP); L.proj_b = L.add(Ei);
   }
+  if (L.has_femb) {
+    const int fd = c->feat_dim;
+    if (c->mod_fembed == 0) {
+      L.fe0_w = L.add((long)E * fd); L.fe0_b = L.add(E);
+    } else {
+      L.fe0_w = L.add(2L * E * fd); L.fe0_b = L.add(2 * E); L.feln_g = L.add(2 * E); L.feln_b = L.add(2 * E);
+      L.fe3_w = L.add((long)E * 2 * E); L.fe3_b = L.add(E);
+    }
+  }
+  if (c->modular && c->mod_mode == 2 && c->mod_fusion == 1) { L.fu_w = L.add((long)E * 2 * E); L.fu_b = L.add(E); }
   L.norm_g = L.add(E); L.norm_b = L.add(E);
   if (c->use_reg) L.reg = L.add(E);
   if (c->use_pos) L.pos = L.add(128L * E);
@@ -122,6 +158,8 @@ struct Workspace {
   // tokens
   float *emb, *m0, *r0, *tok;
   float *fp_pre, *fp_h, *fp_out;
+  // ModularTransformer: image embedding before fusion, cleaned features, feature embedding (+ its MLP internals), concat buffer
+  float *emb_img, *demb_img, *fclean, *femb, *dfemb, *fe_h, *fe_m, *fe_r, *fe_ln, *fe_act, *dfe_a, *dfe_b, *cat, *dcat;
   LayerWS lyr[kMaxLayers];
   float *mf, *rf, *xf, *headin, *hh, *pred_dummy;
   // backward temporaries
@@ -140,7 +178,8 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
   Bump b{reinterpret_cast<uint8_t*>(base)};
   const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H;
   const long long NF = (long long)B * F, T = (long long)B * S;
-  if (c->embedding == 2) {
+  const bool has_img = !c->modular || c->mod_mode != 1;
+  if (c->embedding == 2 && has_img) {
     w.rows = NF * (c->P + 1) * (c->P + 1);
     w.rows_pad = (w.rows + 127) / 128 * 128;
     const long long rp = w.rows_pad;
@@ -170,6 +209,15 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
   }
   w.emb = b.take<float>(NF * E); w.m0 = b.take<float>(NF); w.r0 = b.take<float>(NF);
   w.tok = b.take<float>(T * E);
+  w.emb_img = w.emb;
+  if (c->modular && c->mod_mode != 0) {
+    const int Ei = image_embed_dim(c), fd = c->feat_dim;
+    if (c->mod_mode == 2) { w.emb_img = b.take<float>(NF * Ei); w.demb_img = b.take<float>(NF * Ei); }
+    w.fclean = b.take<float>(NF * fd); w.femb = b.take<float>(NF * E); w.dfemb = b.take<float>(NF * E);
+    w.fe_h = b.take<float>(NF * 2 * E); w.fe_ln = b.take<float>(NF * 2 * E); w.fe_act = b.take<float>(NF * 2 * E);
+    w.dfe_a = b.take<float>(NF * 2 * E); w.dfe_b = b.take<float>(NF * 2 * E); w.fe_m = b.take<float>(NF); w.fe_r = b.take<float>(NF);
+    w.cat = b.take<float>(NF * 2 * E); w.dcat = b.take<float>(NF * 2 * E);
+  }
   if (c->use_feat) { w.fp_pre = b.take<float>((size_t)B * E); w.fp_h = b.take<float>((size_t)B * E); w.fp_out = b.take<float>((size_t)B * E); }
   for (int l = 0; l < c->L; ++l) {
     LayerWS& y = w.lyr[l];
@@ -304,8 +352,12 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
                                  float* pred, int32_t training, void* stream) {
   ParamLayout L;
   CK(build_layout(c, L));
-  MIVIT_CHECK_ARG(B >= 1 && x && params && workspace && pred, "bad arguments");
+  MIVIT_CHECK_ARG(B >= 1 && params && workspace && pred, "bad arguments");
+  MIVIT_CHECK_ARG(x || !L.has_img, c->modular ? (c->mod_mode == 2 ? "Both images and features are required for 'both' mode"
+                                                                   : "Images are required for 'images_only' mode") : "bad arguments");
   MIVIT_CHECK_ARG(!c->use_feat || features, "Global features required for %s fusion", c->fusion ? "late" : "early");
+  MIVIT_CHECK_ARG(!(c->modular && c->mod_mode != 0) || features,
+                  c->mod_mode == 2 ? "Both images and features are required for 'both' mode" : "Features are required for 'features_only' mode");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
   carve(c, B, workspace, w);
@@ -313,7 +365,11 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
   const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H, P = c->P;
   const int NF = B * F, T = B * S;
   const float* p = params;
-  if (c->embedding == 2) {
+  const int Ei = L.E_img;
+  float* emb_img = w.emb_img;   // == w.emb unless ModularTransformer fuses it with a feature embedding
+  if (!L.has_img) {
+    // 'features_only'
+  } else if (c->embedding == 2) {
     MIVIT_CHECK_ARG(training || bn_running, "eval-mode BatchNorm needs the running statistics");
     const long long rows = w.rows, rp = w.rows_pad;
     const double cnt = (double)NF * P * P;
@@ -354,9 +410,36 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
         CK(bn_apply_pool(r2[b]->row0, w.bn[i2].ss, rs[b]->row0, w.bn[is].ss, w.pooled, training ? w.fsums : nullptr, NF, P, co[b], st));
       }
     }
-    CK(linear_fwd(w.pooled, p + L.fc_w, p + L.fc_b, w.emb, NF, E, 128, 0, st));
+    CK(linear_fwd(w.pooled, p + L.fc_w, p + L.fc_b, emb_img, NF, Ei, 128, 0, st));
   } else {
-    CK(linear_fwd(x, p + L.proj_w, p + L.proj_b, w.emb, NF, E, P * P, 0, st));
+    CK(linear_fwd(x, p + L.proj_w, p + L.proj_b, emb_img, NF, Ei, P * P, 0, st));
+  }
+  if (c->modular && c->mod_mode != 0) {   // ModularTransformer.forward, helpers/models.py:528-570
+    const int fd = c->feat_dim;
+    CK(nan_to_num_f32(features, w.fclean, (long long)NF * fd, st));
+    float* femb = c->mod_mode == 1 ? w.emb : w.femb;
+    if (L.has_femb) {
+      if (c->mod_fembed == 0) {
+        CK(linear_fwd(w.fclean, p + L.fe0_w, p + L.fe0_b, femb, NF, E, fd, 0, st));
+      } else {   // Linear(fd, 2E) -> LayerNorm(2E) -> GELU -> Linear(2E, E)
+        CK(linear_fwd(w.fclean, p + L.fe0_w, p + L.fe0_b, w.fe_h, NF, 2 * E, fd, 0, st));
+        CK(layernorm_fwd(w.fe_h, nullptr, p + L.feln_g, p + L.feln_b, nullptr, w.fe_ln, w.fe_m, w.fe_r, NF, 2 * E, c->ln_eps, 0, 0, 0, st));
+        CK(act_fwd(w.fe_ln, w.fe_act, (long long)NF * 2 * E, 1, st));
+        CK(linear_fwd(w.fe_act, p + L.fe3_w, p + L.fe3_b, femb, NF, E, 2 * E, 0, st));
+      }
+    }
+    if (c->mod_mode == 2) {
+      if (c->mod_fusion == 0) {          // 'add'
+        CK(add_f32(emb_img, w.femb, w.emb, (long long)NF * E, st));
+      } else if (c->mod_fusion == 1) {   // 'concat_proj': fusion_layer(cat([image, feature], -1))
+        MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.cat, (size_t)2 * E * 4, emb_img, (size_t)E * 4, (size_t)E * 4, NF, cudaMemcpyDeviceToDevice, st));
+        MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.cat + E, (size_t)2 * E * 4, w.femb, (size_t)E * 4, (size_t)E * 4, NF, cudaMemcpyDeviceToDevice, st));
+        CK(linear_fwd(w.cat, p + L.fu_w, p + L.fu_b, w.emb, NF, E, 2 * E, 0, st));
+      } else {                           // 'concat_features': cat([image (E - fd wide), raw features], -1)
+        MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.emb, (size_t)E * 4, emb_img, (size_t)Ei * 4, (size_t)Ei * 4, NF, cudaMemcpyDeviceToDevice, st));
+        MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.emb + Ei, (size_t)E * 4, w.fclean, (size_t)fd * 4, (size_t)fd * 4, NF, cudaMemcpyDeviceToDevice, st));
+      }
+    }
   }
   // x = self.norm(x), written straight into the token slots behind the regression token
   CK(layernorm_fwd(w.emb, nullptr, p + L.norm_g, p + L.norm_b, nullptr, w.tok, w.m0, w.r0, NF, E, c->ln_eps, F, S,
@@ -401,11 +484,12 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
                                   const float* dpred, const float* params, float* grads, void* workspace, void* stream) {
   ParamLayout L;
   CK(build_layout(c, L));
-  MIVIT_CHECK_ARG(B >= 1 && x && dpred && params && grads && workspace, "bad arguments");
+  MIVIT_CHECK_ARG(B >= 1 && (x || !L.has_img) && dpred && params && grads && workspace, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
   carve(c, B, workspace, w);
   const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H, P = c->P;
+  const int Ei = L.E_img;
   const int NF = B * F, T = B * S, hin = L.head_in, hhid = c->head_hidden;
   const float* p = params;
   float* g = grads;
@@ -450,11 +534,37 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
   }
   // embedding LayerNorm (dy is read from the token slots)
   CK(layernorm_bwd(dx, w.emb, w.m0, w.r0, p + L.norm_g, w.demb, g + L.norm_g, g + L.norm_b, NF, E, F, S, c->use_reg ? 1 : 0, st));
+  const float* d_img = w.demb;   // gradient of the image embedding output [NF, Ei]
+  if (c->modular && c->mod_mode != 0) {   // backward of the ModularTransformer fusion (forward: helpers/models.py:528-570)
+    const int fd = c->feat_dim;
+    const float* d_femb = w.demb;         // 'features_only' and 'add': the fused gradient itself
+    if (c->mod_mode == 2 && c->mod_fusion == 1) {
+      CK(linear_bwd(w.cat, p + L.fu_w, w.demb, g + L.fu_w, g + L.fu_b, w.dcat, NF, E, 2 * E, 0, st));
+      MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.demb_img, (size_t)E * 4, w.dcat, (size_t)2 * E * 4, (size_t)E * 4, NF, cudaMemcpyDeviceToDevice, st));
+      MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.dfemb, (size_t)E * 4, w.dcat + E, (size_t)2 * E * 4, (size_t)E * 4, NF, cudaMemcpyDeviceToDevice, st));
+      d_img = w.demb_img;
+      d_femb = w.dfemb;
+    } else if (c->mod_mode == 2 && c->mod_fusion == 2) {
+      MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.demb_img, (size_t)Ei * 4, w.demb, (size_t)E * 4, (size_t)Ei * 4, NF, cudaMemcpyDeviceToDevice, st));
+      d_img = w.demb_img;
+    }
+    if (L.has_femb) {
+      if (c->mod_fembed == 0) {
+        CK(linear_bwd(w.fclean, p + L.fe0_w, d_femb, g + L.fe0_w, g + L.fe0_b, nullptr, NF, E, fd, 0, st));
+      } else {
+        CK(linear_bwd(w.fe_act, p + L.fe3_w, d_femb, g + L.fe3_w, g + L.fe3_b, w.dfe_a, NF, E, 2 * E, 0, st));
+        CK(act_bwd(w.dfe_a, w.fe_ln, w.dfe_b, (long long)NF * 2 * E, 1, st));
+        CK(layernorm_bwd(w.dfe_b, w.fe_h, w.fe_m, w.fe_r, p + L.feln_g, w.dfe_a, g + L.feln_g, g + L.feln_b, NF, 2 * E, 0, 0, 0, st));
+        CK(linear_bwd(w.fclean, p + L.fe0_w, w.dfe_a, g + L.fe0_w, g + L.fe0_b, nullptr, NF, 2 * E, fd, 0, st));
+      }
+    }
+  }
+  if (!L.has_img) return MIVIT_OK;
   if (c->embedding != 2) {
-    CK(linear_bwd(x, p + L.proj_w, w.demb, g + L.proj_w, g + L.proj_b, nullptr, NF, E, P * P, 0, st));
+    CK(linear_bwd(x, p + L.proj_w, d_img, g + L.proj_w, g + L.proj_b, nullptr, NF, Ei, P * P, 0, st));
     return MIVIT_OK;
   }
-  CK(linear_bwd(w.pooled, p + L.fc_w, w.demb, g + L.fc_w, g + L.fc_b, w.dpooled, NF, E, 128, 0, st));
+  CK(linear_bwd(w.pooled, p + L.fc_w, d_img, g + L.fc_w, g + L.fc_b, w.dpooled, NF, Ei, 128, 0, st));
   const long long rows = w.rows, rp = w.rows_pad;
   const double cnt = (double)NF * P * P;
   const int impl = c->conv_impl;

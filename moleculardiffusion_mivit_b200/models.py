@@ -13,6 +13,8 @@ mivit_vit_forward / mivit_vit_backward / mivit_vit_train_step).  There is no PyT
   ResidualBlock / DeepResNetEmbedding  :202-257
   MLPHead                          :260-276
   GeneralTransformer               :278-361
+  ModularTransformer               :366-593  (per-frame features: 'images_only' | 'features_only' | 'both' with
+                                              'add' | 'concat_proj' | 'concat_features' fusion)
   ImageDataset / ImageFeatureDataset   :781-803
 
 Not supported (raise at construction): dropout > 0 (every reference experiment uses 0.0),
@@ -32,7 +34,7 @@ MAX_TOKENS = 128  # helpers/models.py:8
 
 __all__ = ["MAX_TOKENS", "MultiHeadAttention", "FeedForward", "TransformerEncoderLayerWithSkip", "Transformer",
            "LinearProjectionEmbedding", "CNNEmbedding", "ResidualBlock", "DeepResNetEmbedding", "MLPHead",
-           "GeneralTransformer", "ImageDataset", "ImageFeatureDataset", "VitConfig"]
+           "GeneralTransformer", "ModularTransformer", "ImageDataset", "ImageFeatureDataset", "VitConfig"]
 
 
 class VitConfig(ctypes.Structure):
@@ -42,7 +44,8 @@ class VitConfig(ctypes.Structure):
                 ("use_pos", ctypes.c_int32), ("use_reg", ctypes.c_int32), ("use_feat", ctypes.c_int32),
                 ("fusion", ctypes.c_int32), ("feat_dim", ctypes.c_int32), ("head_hidden", ctypes.c_int32),
                 ("conv_impl", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
-                ("ln_eps", ctypes.c_float)]
+                ("ln_eps", ctypes.c_float), ("modular", ctypes.c_int32), ("mod_mode", ctypes.c_int32),
+                ("mod_fembed", ctypes.c_int32), ("mod_fusion", ctypes.c_int32)]
 
 
 def _no_direct_forward(self, *a, **k):
@@ -188,109 +191,68 @@ class _VitFunction(torch.autograd.Function):
     def forward(ctx, model, x, features, *params):
         pred, gen = model._run_forward(x, features, model.training)
         ctx.model, ctx.gen = model, gen
-        ctx.save_for_backward(x) if features is None else ctx.save_for_backward(x, features)
-        ctx.has_feat = features is not None
+        ctx.has_x, ctx.has_feat = x is not None, features is not None
+        ctx.save_for_backward(*[t for t in (x, features) if t is not None])
         return pred
 
     @staticmethod
     def backward(ctx, dpred):
-        saved = ctx.saved_tensors
-        x, feats = saved[0], (saved[1] if ctx.has_feat else None)
+        saved = list(ctx.saved_tensors)
+        x = saved.pop(0) if ctx.has_x else None
+        feats = saved.pop(0) if ctx.has_feat else None
         grads = ctx.model._run_backward(x, feats, dpred.contiguous(), ctx.gen)
         return (None, None, None) + tuple(grads)
 
 
-class GeneralTransformer(nn.Module):
-    def __init__(self, embedding_cls, embed_kwargs, embed_dim, num_heads, hidden_dim, num_layers, mlp_head,
-                 tr_activation_fct, dropout=0, use_pos_encoding=False, use_regression_token=False,
-                 single_prediction=True, use_global_features=False, fusion_type='early', global_feature_dim=None):
-        super().__init__()
-        if dropout != 0:
-            raise NotImplementedError("dropout > 0 is not implemented on the CUDA path (the reference experiments use 0.0)")
-        if not single_prediction:
-            raise NotImplementedError("single_prediction=False (per-frame outputs) is not implemented")
-        if embedding_cls not in _EMBEDDINGS:
-            raise ValueError("embedding_cls must be LinearProjectionEmbedding, CNNEmbedding or DeepResNetEmbedding")
-        if tr_activation_fct not in _ACTIVATIONS:
-            raise ValueError("tr_activation_fct must be F.relu, F.gelu or F.leaky_relu")
-        self.embed_dim = embed_dim
-        self.embedding = embedding_cls(**embed_kwargs)
-        self.norm = nn.LayerNorm(embed_dim)
-        self.use_regression_token = use_regression_token
-        self.single_prediction = single_prediction
-        self.use_global_features = use_global_features
-        self.fusion_type = fusion_type
-        if use_regression_token:
-            self.reg_token = nn.Parameter(torch.randn(1, 1, embed_dim))
-        self.transformer = Transformer(embed_dim, num_heads, hidden_dim, num_layers, dropout,
-                                       use_pos_encoding=use_pos_encoding, activation_fct=tr_activation_fct)
-        if use_global_features:
-            assert global_feature_dim is not None, "Must provide global_feature_dim if using global features"
-            self.feature_projector = nn.Sequential(nn.Linear(global_feature_dim, embed_dim), nn.ReLU(),
-                                                   nn.Linear(embed_dim, embed_dim))
-        if fusion_type == 'late' and use_global_features:
-            self.mlp_head = mlp_head(input_dim=embed_dim * 2)
-        else:
-            self.mlp_head = mlp_head(input_dim=embed_dim)
-        # ---- CUDA-path bookkeeping (not part of the reference surface)
-        self._num_heads, self._hidden_dim, self._num_layers = num_heads, hidden_dim, num_layers
-        self._activation = _ACTIVATIONS[tr_activation_fct]
-        self._use_pos = bool(use_pos_encoding)
-        self._feat_dim = int(global_feature_dim) if use_global_features else 0
-        self._head_hidden = self.mlp_head.mlp[0].out_features
+def _embedding_keys(prefix, emb):
+    """state_dict keys of an embedding module's parameters in the flat-buffer order of mivit_vit_config."""
+    kind = _EMBEDDINGS[type(emb)]
+    if kind == 2:
+        k = ["initial_conv.weight", "bn1.weight", "bn1.bias"]
+        for b in ("res_block1", "res_block2"):
+            k += ["%s.%s" % (b, s) for s in ("conv1.weight", "bn1.weight", "bn1.bias", "conv2.weight", "bn2.weight", "bn2.bias",
+                                             "skip.0.weight", "skip.1.weight", "skip.1.bias")]
+        k += ["fc.weight", "fc.bias"]
+    elif kind == 0:
+        k = ["proj.weight", "proj.bias"]
+    else:
+        k = ["conv.weight", "conv.bias"]
+    return [prefix + s for s in k]
+
+
+def _transformer_keys(num_layers, use_reg, use_pos):
+    k = ["norm.weight", "norm.bias"]
+    if use_reg:
+        k.append("reg_token")
+    if use_pos:
+        k.append("transformer.pos_embedding")
+    for i in range(num_layers):
+        p = "transformer.encoder_layers.%d." % i
+        for s in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            k += [p + "self_attn.%s.weight" % s, p + "self_attn.%s.bias" % s]
+        k += [p + "norm1.weight", p + "norm1.bias", p + "feed_forward.fc1.weight", p + "feed_forward.fc1.bias",
+              p + "feed_forward.fc2.weight", p + "feed_forward.fc2.bias", p + "norm2.weight", p + "norm2.bias"]
+    return k + ["transformer.norm.weight", "transformer.norm.bias"]
+
+
+class _CudaViT(nn.Module):
+    """Plumbing shared by GeneralTransformer and ModularTransformer: ONE flat fp32 CUDA buffer behind all Parameters (canonical
+    order = param_keys()), the BatchNorm running-statistics buffer, the workspace and the forward / backward calls into the C
+    library.  Subclasses provide param_keys(), vit_config(n_frames), _image_embedding() and _check_inputs()."""
+
+    def _init_cuda_state(self):
         self._flat = self._grad_flat = self._bn_flat = self._bn_nbt = None
         self._ws, self._gen = {}, 0
         self.conv_impl = 1   # 1 = tcgen05 convolutions; 0 = SIMT cross-check kernels (tests only)
 
-    # ------------------------------------------------------------------ canonical order -----
-    def param_keys(self):
-        """state_dict keys of the parameters in the flat-buffer order of mivit_vit_config."""
-        k = []
-        emb = _EMBEDDINGS[type(self.embedding)]
-        if emb == 2:
-            k += ["embedding.initial_conv.weight", "embedding.bn1.weight", "embedding.bn1.bias"]
-            for b in ("res_block1", "res_block2"):
-                k += ["embedding.%s.%s" % (b, s) for s in ("conv1.weight", "bn1.weight", "bn1.bias", "conv2.weight",
-                                                          "bn2.weight", "bn2.bias", "skip.0.weight", "skip.1.weight",
-                                                          "skip.1.bias")]
-            k += ["embedding.fc.weight", "embedding.fc.bias"]
-        elif emb == 0:
-            k += ["embedding.proj.weight", "embedding.proj.bias"]
-        else:
-            k += ["embedding.conv.weight", "embedding.conv.bias"]
-        k += ["norm.weight", "norm.bias"]
-        if self.use_regression_token:
-            k.append("reg_token")
-        if self._use_pos:
-            k.append("transformer.pos_embedding")
-        for i in range(self._num_layers):
-            p = "transformer.encoder_layers.%d." % i
-            for s in ("q_proj", "k_proj", "v_proj", "out_proj"):
-                k += [p + "self_attn.%s.weight" % s, p + "self_attn.%s.bias" % s]
-            k += [p + "norm1.weight", p + "norm1.bias", p + "feed_forward.fc1.weight", p + "feed_forward.fc1.bias",
-                  p + "feed_forward.fc2.weight", p + "feed_forward.fc2.bias", p + "norm2.weight", p + "norm2.bias"]
-        k += ["transformer.norm.weight", "transformer.norm.bias"]
-        if self.use_global_features:
-            k += ["feature_projector.0.weight", "feature_projector.0.bias", "feature_projector.2.weight",
-                  "feature_projector.2.bias"]
-        k += ["mlp_head.mlp.0.weight", "mlp_head.mlp.0.bias", "mlp_head.mlp.3.weight", "mlp_head.mlp.3.bias"]
-        return k
+    def _is_deep(self):
+        emb = self._image_embedding()
+        return emb is not None and _EMBEDDINGS[type(emb)] == 2
 
     def _bn_modules(self):
-        e = self.embedding
+        e = self._image_embedding()
         return [e.bn1, e.res_block1.bn1, e.res_block1.bn2, e.res_block1.skip[1],
                 e.res_block2.bn1, e.res_block2.bn2, e.res_block2.skip[1]]
-
-    def vit_config(self, n_frames):
-        c = VitConfig()
-        c.embedding = _EMBEDDINGS[type(self.embedding)]
-        c.P, c.F, c.E = int(self.embedding.patch_size), int(n_frames), int(self.embed_dim)
-        c.H, c.HD, c.L = int(self._num_heads), int(self._hidden_dim), int(self._num_layers)
-        c.activation, c.use_pos, c.use_reg = self._activation, int(self._use_pos), int(self.use_regression_token)
-        c.use_feat, c.fusion, c.feat_dim = int(self.use_global_features), int(self.fusion_type == 'late'), self._feat_dim
-        c.head_hidden, c.conv_impl = int(self._head_hidden), int(self.conv_impl)
-        c.bn_eps, c.bn_momentum, c.ln_eps = 1e-5, 0.1, 1e-5
-        return c
 
     # ------------------------------------------------------------------ flat buffers --------
     def _ensure_flat(self):
@@ -329,7 +291,7 @@ class GeneralTransformer(nn.Module):
                 off += p.numel()
             self._flat, self._n_params = flat, total
             self._grad_flat = torch.zeros(total + 4, dtype=torch.float32, device=dev)
-        if _EMBEDDINGS[type(self.embedding)] == 2:
+        if self._is_deep():
             bns = self._bn_modules()
             okb = self._bn_flat is not None and self._bn_flat.device == dev
             if okb:
@@ -370,25 +332,17 @@ class GeneralTransformer(nn.Module):
             self._ws[key] = ws
         return ws
 
-    def _check_inputs(self, x, features):
-        if x.dim() != 4 or x.shape[2] != self.embedding.patch_size or x.shape[3] != self.embedding.patch_size:
-            raise AssertionError("Patch size mismatch")
-        if self.use_global_features:
-            assert features is not None, "Global features required for %s fusion" % self.fusion_type
-        dev = self._flat.device
-        x = x.to(device=dev, dtype=torch.float32).contiguous()
-        if self.use_global_features:
-            features = features.to(device=dev, dtype=torch.float32).contiguous()
-        else:
-            features = None
-        return x, features
+    @staticmethod
+    def _batch_frames(x, features):
+        t = x if x is not None else features
+        return int(t.shape[0]), int(t.shape[1])
 
     def _run_forward(self, x, features, training):
-        B, Fr = x.shape[0], x.shape[1]
+        B, Fr = self._batch_frames(x, features)
         cfg = self.vit_config(Fr)
         ws = self._workspace(cfg, B)
-        pred = torch.empty((B, 1), dtype=torch.float32, device=x.device)
-        is_deep = cfg.embedding == 2
+        pred = torch.empty((B, 1), dtype=torch.float32, device=self._flat.device)
+        is_deep = self._is_deep()
         _lib.check(_lib.lib().mivit_vit_forward(
             ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(self._flat),
             _lib.ptr(self._bn_flat) if is_deep else None, _lib.ptr(self._bn_nbt) if is_deep else None,
@@ -399,7 +353,7 @@ class GeneralTransformer(nn.Module):
     def _run_backward(self, x, features, dpred, gen):
         if gen != self._gen:
             raise RuntimeError("backward() must follow the forward() that produced the output (one live workspace per model)")
-        B, Fr = x.shape[0], x.shape[1]
+        B, Fr = self._batch_frames(x, features)
         cfg = self.vit_config(Fr)
         ws = self._workspace(cfg, B)
         _lib.check(_lib.lib().mivit_vit_backward(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(dpred),
@@ -413,11 +367,7 @@ class GeneralTransformer(nn.Module):
             off += p.numel()
         return grads
 
-    def forward(self, x, features=None):
-        """x: [batch_size, num_images, image_size, image_size]; features: [batch_size, num_features] or None.
-        Returns [batch_size, 1] (CUDA tensor).  Gradients flow to the parameters, not to x."""
-        self._ensure_flat()
-        x, features = self._check_inputs(x, features)
+    def _forward_cuda(self, x, features):
         named = dict(self.named_parameters())
         params = [named[k] for k in self.param_keys()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
@@ -433,6 +383,230 @@ class GeneralTransformer(nn.Module):
     def flat_gradients(self):
         self._ensure_flat()
         return self._grad_flat[:self._n_params]
+
+
+class GeneralTransformer(_CudaViT):
+    def __init__(self, embedding_cls, embed_kwargs, embed_dim, num_heads, hidden_dim, num_layers, mlp_head,
+                 tr_activation_fct, dropout=0, use_pos_encoding=False, use_regression_token=False,
+                 single_prediction=True, use_global_features=False, fusion_type='early', global_feature_dim=None):
+        super().__init__()
+        if dropout != 0:
+            raise NotImplementedError("dropout > 0 is not implemented on the CUDA path (the reference experiments use 0.0)")
+        if not single_prediction:
+            raise NotImplementedError("single_prediction=False (per-frame outputs) is not implemented")
+        if embedding_cls not in _EMBEDDINGS:
+            raise ValueError("embedding_cls must be LinearProjectionEmbedding, CNNEmbedding or DeepResNetEmbedding")
+        if tr_activation_fct not in _ACTIVATIONS:
+            raise ValueError("tr_activation_fct must be F.relu, F.gelu or F.leaky_relu")
+        self.embed_dim = embed_dim
+        self.embedding = embedding_cls(**embed_kwargs)
+        self.norm = nn.LayerNorm(embed_dim)
+        self.use_regression_token = use_regression_token
+        self.single_prediction = single_prediction
+        self.use_global_features = use_global_features
+        self.fusion_type = fusion_type
+        if use_regression_token:
+            self.reg_token = nn.Parameter(torch.randn(1, 1, embed_dim))
+        self.transformer = Transformer(embed_dim, num_heads, hidden_dim, num_layers, dropout,
+                                       use_pos_encoding=use_pos_encoding, activation_fct=tr_activation_fct)
+        if use_global_features:
+            assert global_feature_dim is not None, "Must provide global_feature_dim if using global features"
+            self.feature_projector = nn.Sequential(nn.Linear(global_feature_dim, embed_dim), nn.ReLU(),
+                                                   nn.Linear(embed_dim, embed_dim))
+        if fusion_type == 'late' and use_global_features:
+            self.mlp_head = mlp_head(input_dim=embed_dim * 2)
+        else:
+            self.mlp_head = mlp_head(input_dim=embed_dim)
+        # ---- CUDA-path bookkeeping (not part of the reference surface)
+        self._num_heads, self._hidden_dim, self._num_layers = num_heads, hidden_dim, num_layers
+        self._activation = _ACTIVATIONS[tr_activation_fct]
+        self._use_pos = bool(use_pos_encoding)
+        self._feat_dim = int(global_feature_dim) if use_global_features else 0
+        self._head_hidden = self.mlp_head.mlp[0].out_features
+        self._init_cuda_state()
+
+    def _image_embedding(self):
+        return self.embedding
+
+    # ------------------------------------------------------------------ canonical order -----
+    def param_keys(self):
+        """state_dict keys of the parameters in the flat-buffer order of mivit_vit_config."""
+        k = _embedding_keys("embedding.", self.embedding)
+        k += _transformer_keys(self._num_layers, self.use_regression_token, self._use_pos)
+        if self.use_global_features:
+            k += ["feature_projector.0.weight", "feature_projector.0.bias", "feature_projector.2.weight",
+                  "feature_projector.2.bias"]
+        k += ["mlp_head.mlp.0.weight", "mlp_head.mlp.0.bias", "mlp_head.mlp.3.weight", "mlp_head.mlp.3.bias"]
+        return k
+
+    def vit_config(self, n_frames):
+        c = VitConfig()
+        c.embedding = _EMBEDDINGS[type(self.embedding)]
+        c.P, c.F, c.E = int(self.embedding.patch_size), int(n_frames), int(self.embed_dim)
+        c.H, c.HD, c.L = int(self._num_heads), int(self._hidden_dim), int(self._num_layers)
+        c.activation, c.use_pos, c.use_reg = self._activation, int(self._use_pos), int(self.use_regression_token)
+        c.use_feat, c.fusion, c.feat_dim = int(self.use_global_features), int(self.fusion_type == 'late'), self._feat_dim
+        c.head_hidden, c.conv_impl = int(self._head_hidden), int(self.conv_impl)
+        c.bn_eps, c.bn_momentum, c.ln_eps = 1e-5, 0.1, 1e-5
+        return c
+
+    def _check_inputs(self, x, features):
+        if x.dim() != 4 or x.shape[2] != self.embedding.patch_size or x.shape[3] != self.embedding.patch_size:
+            raise AssertionError("Patch size mismatch")
+        if self.use_global_features:
+            assert features is not None, "Global features required for %s fusion" % self.fusion_type
+        dev = self._flat.device
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        if self.use_global_features:
+            features = features.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            features = None
+        return x, features
+
+    def forward(self, x, features=None):
+        """x: [batch_size, num_images, image_size, image_size]; features: [batch_size, num_features] or None.
+        Returns [batch_size, 1] (CUDA tensor).  Gradients flow to the parameters, not to x."""
+        self._ensure_flat()
+        x, features = self._check_inputs(x, features)
+        return self._forward_cuda(x, features)
+
+
+class ModularTransformer(_CudaViT):
+    """helpers/models.py:366-593.  `features` are PER FRAME, [batch_size, num_images, features_dim]; `mlp_head` is a module
+    INSTANCE here (the reference's GeneralTransformer takes the class).  Same constructor errors as the reference."""
+
+    def __init__(self, embed_dim, num_heads, hidden_dim, num_layers, mlp_head, tr_activation_fct, dropout=0,
+                 use_pos_encoding=False, use_regression_token=False, single_prediction=True, mode='images_only',
+                 image_embedding_cls=None, image_embed_kwargs=None, features_dim=None, feature_embedding_type='linear',
+                 fusion_method='add'):
+        super().__init__()
+        if dropout != 0:
+            raise NotImplementedError("dropout > 0 is not implemented on the CUDA path (the reference experiments use 0.0)")
+        if not single_prediction and not use_regression_token:
+            raise NotImplementedError("single_prediction=False (per-frame outputs) is not implemented")
+        if tr_activation_fct not in _ACTIVATIONS:
+            raise ValueError("tr_activation_fct must be F.relu, F.gelu or F.leaky_relu")
+        self.embed_dim = embed_dim
+        self.mode = mode
+        self.use_regression_token = use_regression_token
+        self.single_prediction = single_prediction
+        self.fusion_method = fusion_method
+        self.features_dim = features_dim
+        if mode not in ['images_only', 'features_only', 'both']:
+            raise ValueError("mode must be one of: 'images_only', 'features_only', 'both'")
+        if mode == 'both' and fusion_method not in ['add', 'concat_proj', 'concat_features']:
+            raise ValueError("fusion_method must be one of: 'add', 'concat_proj', 'concat_features'")
+        if mode == 'both' and fusion_method == 'concat_features':
+            image_embed_dim = embed_dim - features_dim
+            if image_embed_dim <= 0:
+                raise ValueError(f"embed_dim ({embed_dim}) must be greater than features_dim ({features_dim}) when using "
+                                 f"'concat_features' fusion")
+            if image_embed_kwargs is None:
+                image_embed_kwargs = {}
+            image_embed_kwargs['embed_dim'] = image_embed_dim      # mutates the caller's dict, like the reference (:427)
+        self.image_embedding = None
+        if mode in ['images_only', 'both']:
+            if image_embedding_cls is None:
+                raise ValueError("image_embedding_cls must be provided when using images")
+            if image_embedding_cls not in _EMBEDDINGS:
+                raise ValueError("image_embedding_cls must be LinearProjectionEmbedding, CNNEmbedding or DeepResNetEmbedding")
+            if image_embed_kwargs is None:
+                image_embed_kwargs = {}
+            self.image_embedding = image_embedding_cls(**image_embed_kwargs)
+        self.feature_embedding = None
+        if mode in ['features_only', 'both'] and fusion_method != 'concat_features':
+            if features_dim is None:
+                raise ValueError("features_dim must be provided when using features")
+            if feature_embedding_type == 'linear':
+                self.feature_embedding = nn.Linear(features_dim, embed_dim)
+            elif feature_embedding_type == 'mlp':
+                self.feature_embedding = nn.Sequential(nn.Linear(features_dim, embed_dim * 2), nn.LayerNorm(embed_dim * 2),
+                                                       nn.GELU(), nn.Linear(embed_dim * 2, embed_dim))
+            else:
+                raise ValueError(f"Unknown feature_embedding_type: {feature_embedding_type}")
+        self.fusion_layer = None
+        if mode == 'both' and fusion_method == 'concat_proj':
+            self.fusion_layer = nn.Linear(embed_dim * 2, embed_dim)
+        self.norm = nn.LayerNorm(embed_dim)
+        if use_regression_token:
+            self.reg_token = nn.Parameter(torch.randn(1, 1, embed_dim))
+        self.transformer = Transformer(embed_dim, num_heads, hidden_dim, num_layers, dropout,
+                                       use_pos_encoding=use_pos_encoding, activation_fct=tr_activation_fct)
+        if not isinstance(mlp_head, MLPHead):
+            raise NotImplementedError("ModularTransformer: mlp_head must be an MLPHead instance on the CUDA path")
+        self.mlp_head = mlp_head
+        # ---- CUDA-path bookkeeping (not part of the reference surface)
+        self._num_heads, self._hidden_dim, self._num_layers = num_heads, hidden_dim, num_layers
+        self._activation = _ACTIVATIONS[tr_activation_fct]
+        self._use_pos = bool(use_pos_encoding)
+        self._fembed_mlp = feature_embedding_type == 'mlp'
+        self._head_hidden = self.mlp_head.mlp[0].out_features
+        self._init_cuda_state()
+
+    def _image_embedding(self):
+        return self.image_embedding
+
+    def param_keys(self):
+        k = _embedding_keys("image_embedding.", self.image_embedding) if self.image_embedding is not None else []
+        if self.feature_embedding is not None:
+            if self._fembed_mlp:
+                k += ["feature_embedding.%s" % s for s in ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias")]
+            else:
+                k += ["feature_embedding.weight", "feature_embedding.bias"]
+        if self.fusion_layer is not None:
+            k += ["fusion_layer.weight", "fusion_layer.bias"]
+        k += _transformer_keys(self._num_layers, self.use_regression_token, self._use_pos)
+        k += ["mlp_head.mlp.0.weight", "mlp_head.mlp.0.bias", "mlp_head.mlp.3.weight", "mlp_head.mlp.3.bias"]
+        return k
+
+    def vit_config(self, n_frames):
+        c = VitConfig()
+        emb = self.image_embedding
+        c.embedding = _EMBEDDINGS[type(emb)] if emb is not None else 0
+        c.P, c.F, c.E = int(emb.patch_size) if emb is not None else 1, int(n_frames), int(self.embed_dim)
+        c.H, c.HD, c.L = int(self._num_heads), int(self._hidden_dim), int(self._num_layers)
+        c.activation, c.use_pos, c.use_reg = self._activation, int(self._use_pos), int(self.use_regression_token)
+        c.use_feat, c.fusion = 0, 0
+        c.feat_dim = int(self.features_dim) if (self.mode != 'images_only' and self.features_dim is not None) else 0
+        c.head_hidden, c.conv_impl = int(self._head_hidden), int(self.conv_impl)
+        c.bn_eps, c.bn_momentum, c.ln_eps = 1e-5, 0.1, 1e-5
+        c.modular = 1
+        c.mod_mode = {'images_only': 0, 'features_only': 1, 'both': 2}[self.mode]
+        c.mod_fembed = int(self._fembed_mlp)
+        c.mod_fusion = {'add': 0, 'concat_proj': 1, 'concat_features': 2}.get(self.fusion_method, 0)
+        return c
+
+    def _check_inputs(self, images, features):
+        if self.mode == 'images_only' and images is None:
+            raise ValueError("Images are required for 'images_only' mode")
+        if self.mode == 'features_only' and features is None:
+            raise ValueError("Features are required for 'features_only' mode")
+        if self.mode == 'both' and (images is None or features is None):
+            raise ValueError("Both images and features are required for 'both' mode")
+        dev = self._flat.device
+        if self.mode == 'features_only':
+            images = None
+        else:
+            ps = self.image_embedding.patch_size
+            if images.dim() != 4 or images.shape[2] != ps or images.shape[3] != ps:
+                raise AssertionError("Patch size mismatch")
+            images = images.to(device=dev, dtype=torch.float32).contiguous()
+        if self.mode == 'images_only':
+            features = None
+        else:
+            if self.mode == 'both' and (images.shape[0] != features.shape[0] or images.shape[1] != features.shape[1]):
+                raise ValueError("Images and features must have the same batch size and sequence length")
+            if features.dim() != 3 or features.shape[2] != self.features_dim:
+                raise ValueError("features must be [batch_size, num_images, features_dim]")
+            features = features.to(device=dev, dtype=torch.float32).contiguous()
+        return images, features
+
+    def forward(self, images=None, features=None):
+        """images: [batch_size, num_images, image_size, image_size] or None; features: [batch_size, num_images, features_dim]
+        or None (NaNs are replaced by zeros).  Returns [batch_size, 1]."""
+        self._ensure_flat()
+        images, features = self._check_inputs(images, features)
+        return self._forward_cuda(images, features)
 
 
 class ImageDataset(Dataset):  # helpers/models.py:781-790

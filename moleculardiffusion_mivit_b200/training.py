@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .models import GeneralTransformer
+from .models import _CudaViT
 from .parallel import allreduce_sum_
 
 __all__ = ["MiViTTrainer"]
@@ -17,8 +17,8 @@ __all__ = ["MiViTTrainer"]
 class MiViTTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step_size=5, gamma=0.9,
                  process_group=None, distributed=None, cuda_graph=False, sync_bn=False):
-        if not isinstance(model, GeneralTransformer):
-            raise TypeError("MiViTTrainer drives a moleculardiffusion_mivit_b200.models.GeneralTransformer")
+        if not isinstance(model, _CudaViT):
+            raise TypeError("MiViTTrainer drives a moleculardiffusion_mivit_b200.models.GeneralTransformer / ModularTransformer")
         self.model = model
         self.base_lr, self.lr = float(lr), float(lr)
         self.betas, self.eps, self.weight_decay = betas, float(eps), float(weight_decay)
@@ -77,19 +77,20 @@ class MiViTTrainer:
         return s
 
     def train_step(self, x, target, features=None):
-        """x: CUDA float32 [B,F,P,P]; target: CUDA float32 [B,1].  Enqueues the whole step on the current
+        """x: CUDA float32 [B,F,P,P] (None for a 'features_only' ModularTransformer); target: CUDA float32 [B,1]; features:
+        [B,feat_dim] (GeneralTransformer) or [B,F,features_dim] (ModularTransformer).  Enqueues the whole step on the current
         stream and returns the (device) loss tensor without synchronising."""
         model = self.model
         model._ensure_flat()
         if not model.training:
             model.train()
         x, features = model._check_inputs(x, features)
-        target = target.to(device=x.device, dtype=torch.float32).reshape(-1, 1).contiguous()
-        B, Fr = x.shape[0], x.shape[1]
+        target = target.to(device=model._flat.device, dtype=torch.float32).reshape(-1, 1).contiguous()
+        B, Fr = model._batch_frames(x, features)
         cfg = model.vit_config(Fr)
         ws = model._workspace(cfg, B)
         pred, dpred = self._buffers(B)
-        deep = cfg.embedding == 2
+        deep = model._is_deep()
         self.step_count += 1
         L = _lib.lib()
         if self.sync_bn and deep:
@@ -147,14 +148,14 @@ class MiViTTrainer:
         """Replays the captured forward + loss + backward for this batch shape; returns False on the first call of a shape
         (that step runs eagerly -- it also performs every lazy initialisation -- and the graph is captured afterwards)."""
         model = self.model
-        key = (B, tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), id(ws))
+        key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), id(ws))
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "pending"
             return False
         L = _lib.lib()
         if ent == "pending":
-            gx, gt = torch.empty_like(x), torch.empty_like(target)
+            gx, gt = (torch.empty_like(x) if x is not None else None), torch.empty_like(target)
             gf = torch.empty_like(features) if features is not None else None
             n0 = L.mivit_launch_count()
             g = torch.cuda.CUDAGraph()
@@ -171,7 +172,8 @@ class MiViTTrainer:
             L.mivit_add_launch_count(-n_cap)          # capturing enqueued nothing: only replays count
             ent = self._graphs[key] = (g, gx, gt, gf, n_cap, cfg)
         g, gx, gt, gf, n_launches, _ = ent
-        gx.copy_(x)
+        if gx is not None:
+            gx.copy_(x)
         gt.copy_(target)
         if gf is not None:
             gf.copy_(features)

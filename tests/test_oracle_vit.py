@@ -43,3 +43,22 @@ def test_train_step(golden_dir, name):
             tol += 2 * 1e-4 * v.numel()
         assert abs(float(v.double().sum()) - ref_sum) < tol, k
         assert abs(float(v.double().abs().sum()) - ref_abs) < tol, k
+
+
+from vit_cases import MODULAR_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(MODULAR_CASES))
+def test_modular_forward_loss_grads(golden_dir, name):
+    """ModularTransformer restatement (oracle.vit_oracle.forward_modular) against the reference nn.Module's outputs."""
+    z, sd, x, tgt, feats = load_case(golden_dir, name)
+    pred, loss, g, _ = vo.loss_and_grads(sd, MODULAR_CASES[name], x, tgt, feats)
+    assert np.abs(pred.numpy() - z["pred"]).max() < 2e-6
+    assert abs(float(loss) - float(z["loss"])) < 1e-6
+    gmax = max(float(z[k]) for k in z.files if k.startswith("gradnorm/"))
+    assert set(g) == set(k[9:] for k in z.files if k.startswith("gradnorm/"))
+    for k in g:
+        assert abs(float(g[k].double().norm()) - float(z["gradnorm/" + k])) < 1e-4 * gmax + 1e-4 * float(z["gradnorm/" + k])
+        if "grad/" + k in z.files:
+            ref = z["grad/" + k]
+            assert np.abs(g[k].numpy() - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-3 * gmax)

@@ -264,3 +264,79 @@ def test_cuda_graph_replay_matches_eager_steps(golden_dir):
     for k in s0:
         if s0[k].dtype.is_floating_point:
             assert torch.allclose(s0[k], s1[k], rtol=5e-2, atol=1e-3), k      # AdamW sign flips of ~0 gradients (atomic order)
+
+
+# ------------------------------------------------------------------ ModularTransformer (helpers/models.py:366-593) ----
+from vit_cases import MODULAR_CASES  # noqa: E402
+
+
+def build_modular(name):
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    c = MODULAR_CASES[name]
+    emb = {"deepresnet": M.DeepResNetEmbedding, "linear": M.LinearProjectionEmbedding, "cnn": M.CNNEmbedding,
+           None: None}[c.get("embedding")]
+    act = {"relu": F.relu, "gelu": F.gelu}[c["activation"]]
+    return M.ModularTransformer(
+        c["embed_dim"], c["num_heads"], c["hidden_dim"], c["num_layers"], M.MLPHead(input_dim=c["embed_dim"]), act, 0.0,
+        c["use_pos_encoding"], c["use_regression_token"], True, c["mode"], emb,
+        {"patch_size": 9, "embed_dim": c["embed_dim"]} if emb is not None else None, c.get("features_dim"),
+        c.get("feature_embedding_type", "linear"), c.get("fusion_method", "add"))
+
+
+@pytest.mark.parametrize("name", list(MODULAR_CASES))
+def test_modular_forward_loss_grads_match_oracle(golden_dir, name):
+    """Every mode / feature embedding / fusion method of ModularTransformer: state_dict keys of the reference, prediction, loss
+    and every gradient against the fp32 oracle from the reference's own random-init weights (per-frame features with NaNs)."""
+    import torch
+    import torch.nn.functional as F
+    z, sd, x, tgt, feats = load_case(golden_dir, name)
+    model = build_modular(name)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd)
+    model.cuda().train()
+    deep = MODULAR_CASES[name].get("embedding") == "deepresnet"
+    pred = model(x.cuda() if x is not None else None, feats.cuda() if feats is not None else None)
+    loss = F.mse_loss(pred, tgt.cuda())
+    loss.backward()
+    ref_pred, ref_loss, ref_g, _ = vo.loss_and_grads(sd, MODULAR_CASES[name], x, tgt, feats)
+    ptol = 3e-2 if deep else 1e-4
+    assert (pred.cpu() - ref_pred).abs().max().item() < ptol * max(1.0, ref_pred.abs().max().item())
+    assert abs(loss.item() - float(z["loss"])) < ptol * max(1.0, float(z["loss"]))
+    gmax = max(float(v.norm()) for v in ref_g.values())
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        r = ref_g[k]
+        if float(r.norm()) < 1e-5 * gmax:
+            assert float(p.grad.cpu().norm()) < 1e-3 * gmax, k
+            continue
+        # B = 4 sequences: the bf16-stored activation gradients of the DeepResNet embedding average over few positions
+        tol = (0.16 if k.startswith("image_embedding.") else 8e-2) if deep else 5e-4
+        assert relnorm(p.grad.cpu(), r) < tol, (k, relnorm(p.grad.cpu(), r))
+
+
+def test_modular_trainer_step_and_errors(golden_dir):
+    """MiViTTrainer drives a ModularTransformer (features-only: no images at all); constructor / input errors of the reference."""
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    from moleculardiffusion_mivit_b200.training import MiViTTrainer
+    z, sd, x, tgt, feats = load_case(golden_dir, "mod_features_only_mlp")
+    model = build_modular("mod_features_only_mlp")
+    model.load_state_dict(sd)
+    model.cuda().train()
+    tr = MiViTTrainer(model, lr=1e-3)
+    l0 = tr.train_step(None, tgt.cuda(), feats.cuda()).item()
+    assert abs(l0 - float(z["loss"])) < 1e-4
+    for _ in range(20):
+        l1 = tr.train_step(None, tgt.cuda(), feats.cuda()).item()
+    assert l1 < l0
+    with pytest.raises(ValueError, match="mode must be one of"):
+        M.ModularTransformer(32, 2, 64, 1, M.MLPHead(32), F.relu, mode="video")
+    with pytest.raises(ValueError, match="must be greater than features_dim"):
+        M.ModularTransformer(8, 2, 16, 1, M.MLPHead(8), F.relu, mode="both", image_embedding_cls=M.LinearProjectionEmbedding,
+                             image_embed_kwargs={"patch_size": 9, "embed_dim": 8}, features_dim=8, fusion_method="concat_features")
+    with pytest.raises(ValueError, match="image_embedding_cls must be provided"):
+        M.ModularTransformer(32, 2, 64, 1, M.MLPHead(32), F.relu, mode="images_only")
+    with pytest.raises(ValueError, match="Features are required"):
+        model(None, None)
