@@ -441,14 +441,20 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ sums, const float* 
                                    const float* __restrict__ gamma_a,
                                    const float* __restrict__ mi_b, const float* __restrict__ gamma_b, float* __restrict__ coef_a,
                                    float* __restrict__ coef_b, float* __restrict__ dgamma_a, float* __restrict__ dbeta_a,
-                                   float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, int C, float inv_count) {
+                                   float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, int C, float inv_count, int raw_sums) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   {
+    // raw_sums: slot 1 holds sum g*x instead of sum g*xhat = invstd * (sum g*x - mean * sum g)
+    float s1 = sums[C + c], s1l = sums_local[C + c];
+    if (raw_sums) {
+      s1 = (s1 - mi_a[c] * sums[c]) * mi_a[C + c];
+      s1l = (s1l - mi_a[c] * sums_local[c]) * mi_a[C + c];
+    }
     const float k1 = gamma_a[c] * mi_a[C + c];
-    const float k2 = -k1 * mi_a[C + c] * sums[C + c] * inv_count;
+    const float k2 = -k1 * mi_a[C + c] * s1 * inv_count;
     coef_a[c] = k1; coef_a[C + c] = k2; coef_a[2 * C + c] = -k1 * sums[c] * inv_count - k2 * mi_a[c];
-    dgamma_a[c] = sums_local[C + c];
+    dgamma_a[c] = s1l;
     dbeta_a[c] = sums_local[c];
   }
   if (mi_b != nullptr) {
@@ -770,13 +776,16 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
                 const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,
                 const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
                 float* dgamma_b, float* dbeta_b, float* sums /*[12][C] scratch: sums | coef_a | coef_b | local sums*/, long long rows,
-                long long rows_pad, int P, int C, double count, const float* fsums, cudaStream_t st) {
+                long long rows_pad, int P, int C, double count, const float* fsums, int presummed, cudaStream_t st) {
   MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
-  MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
+  MIVIT_CHECK_ARG(!presummed || (raw_b == nullptr && dpooled == nullptr), "pre-summed BatchNorm backward is single-input only");
+  if (!presummed) MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
   const int rpb = 1024;
   const int blocks = mivit_ceil_div(rows, rpb);
   const RowGeom geo = make_geom(rows, P);
-  if (dpooled != nullptr && fsums != nullptr && raw_b != nullptr) {
+  if (presummed) {
+    // (sum g, sum g*raw) were accumulated by the epilogue of the convolution that produced g (conv_tc4.cu, BSTAT)
+  } else if (dpooled != nullptr && fsums != nullptr && raw_b != nullptr) {
     const long long n_frames = rows / ((long long)(P + 1) * (P + 1));
     MivitProfScope prof("bn_bwd_reduce_pooled", (double)n_frames * C * 16, st);
     const int fl = 256 / C;
@@ -804,7 +813,8 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
     count *= mivit_bn_sync_world();
   }
   bn_bwd_coef_kernel<<<mivit_ceil_div(C, 128), 128, 0, st>>>(sums, sums_local, mi_a, gamma_a, raw_b ? mi_b : nullptr, gamma_b, coef_a,
-                                                             coef_b, dgamma_a, dbeta_a, dgamma_b, dbeta_b, C, (float)(1.0 / count));
+                                                             coef_b, dgamma_a, dbeta_a, dgamma_b, dbeta_b, C, (float)(1.0 / count),
+                                                             presummed);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   const int ablocks = mivit_ceil_div(rows_pad, kRowsPerCta);

@@ -54,8 +54,12 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Relaxed: the arrival only hands TMEM columns back to the leader's MMA warps, and tcgen05.fence::before_thread_sync /
+// after_thread_sync order the tensor-memory accesses on both sides.  (.release compiled to MEMBAR.ALL.CTA, which also waits
+// for every global load / store the warp has in flight -- with the BatchNorm-backward epilogue that exposed the full DRAM
+// latency of the raw-tile prefetch once per tile: 1.03 -> 1.53 ms per launch, ncu source page of r01_bstat.)
 __device__ __forceinline__ void arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void load_tile_2sm(void* smem_dst, const CUtensorMap* tm, int ch0, int row, uint32_t leader_bar) {
   asm volatile(
@@ -105,12 +109,19 @@ struct Cfg4 {
   static constexpr int kStageBytes = kTileM * 128;
 };
 
-template <int CIN, bool SKIP, int TAPS, int NT>
+// BSTAT (input-gradient launches): the output Y is the gradient g of a ReLU(BatchNorm(raw)) activation, and instead of
+// (sum y, sum y^2) the epilogue accumulates that BatchNorm's backward sums over the masked gradient,
+//   stats[0][c] = sum_r m*g,  stats[1][c] = sum_r m*g*raw,   m = 1[raw*scale + shift > 0]   (bn_ss = scale | shift),
+// from the staged (bf16-rounded, i.e. exactly the stored) g and a raw tile prefetched into registers while the MMAs of the
+// tile are still running.  This removes bn.cu's reduction pass over g and raw (2 x 1.5 GB at 128 channels).
+template <int CIN, bool SKIP, int TAPS, int NT, bool BSTAT>
 __global__ void __launch_bounds__(256, 1)
 conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                      const __grid_constant__ CUtensorMap tmYsk, const __nv_bfloat16* __restrict__ Wp,
                      const __nv_bfloat16* __restrict__ Wsk, float* __restrict__ stats, float* __restrict__ stats_sk, long long rows,
-                     int n_tiles, int P, ConvShifts shifts, int halo, int xslab_rows, int ring, int guard) {
+                     int n_tiles, int P, ConvShifts shifts, int halo, int xslab_rows, int ring, int guard,
+                     const __nv_bfloat16* __restrict__ bn_raw, const float* __restrict__ bn_ss, uint4* __restrict__ y_out) {
+  static_assert(!(BSTAT && SKIP), "BatchNorm-backward sums are for single-output launches");
   using C = Cfg4<CIN, SKIP, TAPS, NT>;
   constexpr int taps = TAPS;
   constexpr int NS = C::NS;
@@ -258,6 +269,27 @@ conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int my_row = warp * 32 + lane;
     const int my_swz = my_row & 7;
     const int sc = tid & 7, sg = tid >> 3;
+    // BSTAT: raw rows of this thread's (8-row group, 16-byte chunk) for the region being processed and for the NEXT one
+    // (prefetched a whole region ahead: one region of epilogue work is ~1000 cycles, about the loaded DRAM latency; a
+    // prefetch issued only at the top of its own region stalled the epilogue and cost 0.4 ms per launch).
+    static_assert(!BSTAT || C::kOutPerAcc == 2, "the raw-tile double buffer assumes two 64-column regions per tile");
+    uint4 rawv[BSTAT ? 2 : 1][BSTAT ? 8 : 1];
+    auto prefetch_raw = [&](int tile_, int q_, uint4 (&dst)[BSTAT ? 8 : 1]) {
+      const uint4* rp = reinterpret_cast<const uint4*>(bn_raw + ((long long)tile_ * kTileM + sg * 8) * NT + q_ * 64 + sc * 8);
+#pragma unroll
+      for (int i = 0; i < (BSTAT ? 8 : 1); ++i) {
+        // A COHERENT load on purpose: ptxas is free to sink a non-coherent (ld.global.nc / __ldg) load below the bar.sync
+        // of the next region to save registers -- it did, which put these loads ~100 instructions before their consumers
+        // instead of a region ahead (ncu source page: the unpack of rawv carried the long-scoreboard stalls).  A weak
+        // ld.global may not move down across a barrier.
+        const uint4* p = rp + (size_t)i * (NT / 8);
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(dst[i].x), "=r"(dst[i].y), "=r"(dst[i].z), "=r"(dst[i].w)
+                     : "l"(p)
+                     : "memory");
+      }
+    };
+    if (BSTAT && pair < n_pair_tiles) prefetch_raw(2 * pair + (int)rank, 0, rawv[0]);
     uint32_t sidx = 0;
     int k = 0;
     for (int pt = pair; pt < n_pair_tiles; pt += n_pairs, ++k) {
@@ -275,7 +307,13 @@ conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
         for (int q = 0; q < C::kOutPerAcc; ++q, ++sidx) {
           uint8_t* stg = stage0 + (sidx % C::kStageBufs) * C::kStageBytes;
-          if (tid == 0) bulk_wait_read4<C::kStageBufs - 1>();
+          if (BSTAT) {
+            if (q == 0) prefetch_raw(tile, 1, rawv[1]);
+            else if (pt + n_pairs < n_pair_tiles) prefetch_raw(2 * (pt + n_pairs) + (int)rank, 0, rawv[0]);
+          }
+          // BSTAT stores Y with plain 16-byte stores from the statistics loop below (no TMA store, hence no generic->async
+          // proxy fence in this path: the fence drained the raw-tile loads in flight and exposed their full DRAM latency)
+          if (!BSTAT && tid == 0) bulk_wait_read4<C::kStageBufs - 1>();
           epi_bar_sync4();
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -300,15 +338,37 @@ conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               *reinterpret_cast<uint4*>(stg + my_row * 128 + ((chunk ^ my_swz) << 4)) = pk;
             }
           }
-          umma::fence_proxy_async();
+          if (!BSTAT) umma::fence_proxy_async();
           epi_bar_sync4();
-          if (tid == 0 && tile < n_tiles) tma_store_tile4(o == 0 ? &tmY : &tmYsk, stg, q * 64, guard + tile * kTileM);
-          if (want_stats) {
+          if (!BSTAT && tid == 0 && tile < n_tiles) tma_store_tile4(o == 0 ? &tmY : &tmYsk, stg, q * 64, guard + tile * kTileM);
+          if (want_stats && (!BSTAT || tile < n_tiles)) {   // (the odd leftover tile reads uninitialised guard rows of raw)
+            float bsa[8], bha[8];   // BatchNorm scale / shift of this thread's 8 channels of region q (L1 resident)
+            if (BSTAT) {
+              const float4* sp = reinterpret_cast<const float4*>(bn_ss + q * 64 + sc * 8);
+              const float4 a0 = __ldg(sp), a1 = __ldg(sp + 1), h0 = __ldg(sp + NT / 4), h1 = __ldg(sp + NT / 4 + 1);
+              bsa[0] = a0.x; bsa[1] = a0.y; bsa[2] = a0.z; bsa[3] = a0.w; bsa[4] = a1.x; bsa[5] = a1.y; bsa[6] = a1.z; bsa[7] = a1.w;
+              bha[0] = h0.x; bha[1] = h0.y; bha[2] = h0.z; bha[3] = h0.w; bha[4] = h1.x; bha[5] = h1.y; bha[6] = h1.z; bha[7] = h1.w;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int row = sg * 8 + i;
               const uint4 u = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sc ^ (row & 7)) << 4));
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              if (BSTAT) {
+                y_out[((long long)tile * kTileM + row) * (NT / 8) + q * 8 + sc] = u;
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rawv[BSTAT ? (q & 1) : 0][BSTAT ? i : 0]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]), r = __bfloat1622float2(rh[e]);
+                  const float gx = fmaf(r.x, bsa[2 * e], bha[2 * e]) > 0.f ? f.x : 0.f;           // == bn.cu bn_pre<false>
+                  const float gy = fmaf(r.y, bsa[2 * e + 1], bha[2 * e + 1]) > 0.f ? f.y : 0.f;
+                  ssum[q][2 * e] += gx;
+                  ssum[q][2 * e + 1] += gy;
+                  ssq[q][2 * e] = fmaf(gx, r.x, ssq[q][2 * e]);
+                  ssq[q][2 * e + 1] = fmaf(gy, r.y, ssq[q][2 * e + 1]);
+                }
+                continue;
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(h[e]);
@@ -355,9 +415,10 @@ conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 0) tmem_dealloc_2sm<C::kTmemCols>(tmem);
 }
 
-template <int CIN, bool SKIP, int TAPS, int NT>
+template <int CIN, bool SKIP, int TAPS, int NT, bool BSTAT = false>
 int launch4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y, __nv_bfloat16* Ysk,
-            float* stats, float* stats_sk, long long rows, int P, const ConvShifts& sh, cudaStream_t st, bool* fits) {
+            float* stats, float* stats_sk, long long rows, int P, const ConvShifts& sh, cudaStream_t st, bool* fits,
+            const __nv_bfloat16* bn_raw = nullptr, const float* bn_ss = nullptr) {
   using C = Cfg4<CIN, SKIP, TAPS, NT>;
   constexpr int taps = TAPS;
   constexpr int guard = 128;
@@ -374,7 +435,7 @@ int launch4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   if (!*fits) return MIVIT_OK;
   int smem = fixed + ring * unit_bytes + tail;
   if (smem < 120 * 1024) smem = 120 * 1024;            // one CTA per SM
-  auto kern = conv_rows_tc4_kernel<CIN, SKIP, TAPS, NT>;
+  auto kern = conv_rows_tc4_kernel<CIN, SKIP, TAPS, NT, BSTAT>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long rows_pad = (rows + kTileM - 1) / kTileM * kTileM;
   const int n_tiles = (int)(rows_pad / kTileM);
@@ -412,11 +473,11 @@ int launch4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   if (pairs < 1) pairs = 1;
   cfg.gridDim = dim3(pairs * 2, 1, 1);
   char tag[48];
-  snprintf(tag, sizeof(tag), "conv_rows_tc_%dx%dx%d%s", CIN, NT, taps, SKIP ? "+skip" : "");
+  snprintf(tag, sizeof(tag), "conv_rows_tc_%dx%dx%d%s", CIN, NT, taps, SKIP ? "+skip" : BSTAT ? "+bnbwd" : "");
   const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
   MivitProfScope prof(tag, 2.0 * valid_rows * (taps + (SKIP ? 1 : 0)) * CIN * NT, st);
   MIVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmX, tmY, tmYsk, Wp, Wsk, stats, stats_sk, rows, n_tiles, P, sh, halo, xslab_rows,
-                                      ring, guard));
+                                      ring, guard, bn_raw, bn_ss, reinterpret_cast<uint4*>(Y)));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -444,5 +505,20 @@ int conv_rows_forward_v4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const 
   else if (cout == 128 && taps == 9 && cin == 64 && !skip) rc = launch4<64, false, 9, 128>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
   else fits = false;
   if (!fits) *handled = false;
+  return rc;
+}
+
+// Input gradient of a 3x3 convolution whose input was act = relu(bn(raw)):  Y = g = dL/dact, and sums[0..C) += sum m*g,
+// sums[C..2C) += sum m*g*raw with m = 1[raw*scale + shift > 0] (ss = scale | shift; sums pre-zeroed by the caller).
+// *handled = false: shape not covered here, nothing was launched.
+int conv_rows_dgrad_bnsums(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bfloat16* Y, const __nv_bfloat16* raw,
+                           const float* ss, float* sums, long long rows, int P, int cin, int cout, const ConvShifts& sh,
+                           cudaStream_t st, bool* handled) {
+  *handled = false;
+  bool fits = false;
+  int rc = MIVIT_OK;
+  if (cin == 128 && cout == 128)
+    rc = launch4<128, false, 9, 128, true>(X, Wp, nullptr, Y, nullptr, sums, nullptr, rows, P, sh, st, &fits, raw, ss);
+  *handled = fits;
   return rc;
 }

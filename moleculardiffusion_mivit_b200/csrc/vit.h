@@ -37,6 +37,9 @@ int conv_rows_forward_v3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const 
 int conv_rows_forward_v4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
                          __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout, int taps,
                          const ConvShifts& sh, cudaStream_t st, bool* handled);
+int conv_rows_dgrad_bnsums(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bfloat16* Y, const __nv_bfloat16* raw,
+                           const float* ss, float* sums, long long rows, int P, int cin, int cout, const ConvShifts& sh,
+                           cudaStream_t st, bool* handled);
 int conv_rows_forward_dual_v3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* X2, const __nv_bfloat16* Wp2,
                               __nv_bfloat16* Y, long long rows, int P, int cin, int cin2, int cout, const ConvShifts& sh,
                               cudaStream_t st, bool* handled);
@@ -98,7 +101,9 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
                 const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,
                 const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, const float* gamma_b, __nv_bfloat16* draw_b,
                 float* dgamma_b, float* dbeta_b, float* sums, long long rows, long long rows_pad, int P, int C, double count,
-                const float* fsums /* with dpooled: per-frame sums of bn_apply_pool replace the reduction pass */, cudaStream_t st);
+                const float* fsums /* with dpooled: per-frame sums of bn_apply_pool replace the reduction pass */,
+                int presummed /* sums already holds (sum g, sum g*raw_a) from conv_rows_dgrad_bnsums: no reduction pass */,
+                cudaStream_t st);
 int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad,
                   int P, cudaStream_t st);
 int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st);

@@ -594,18 +594,25 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
     if (b == 1) {
       CK(bn_backward(nullptr, nullptr, w.dpooled, r2[b]->row0, w.bn[i2].ss, w.bn[i2].mi, p + R.bn2_g, d2[b]->row0, g + R.bn2_g,
                      g + R.bn2_b, rs[b]->row0, w.bn[is].ss, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g, g + R.bns_b,
-                     w.bn_sums, rows, rp, P, co[b], cnt, w.fsums, st));
+                     w.bn_sums, rows, rp, P, co[b], cnt, w.fsums, 0, st));
     } else {
       CK(bn_backward(w.dact2m.row0, fused_in[1] ? nullptr : w.dact2s.row0, nullptr, r2[b]->row0, w.bn[i2].ss, w.bn[i2].mi, p + R.bn2_g, d2[b]->row0,
                      g + R.bn2_g, g + R.bn2_b, rs[b]->row0, w.bn[is].ss, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g,
-                     g + R.bns_b, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, st));
+                     g + R.bns_b, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, 0, st));
     }
     CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
-    CK(conv_rows_forward(d2[b]->row0, w.wd_c2[b], da1[b]->row0, nullptr, rows, P, co[b], co[b], 9, s3m, impl, st));
+    // conv2 input gradient; on the product path its epilogue also accumulates the backward sums of bn1 (no reduction pass)
+    bool bn1_summed = false;
+    if (impl == 1) {
+      MIVIT_CUDA_CHECK(cudaMemsetAsync(w.bn_sums, 0, 3 * co[b] * sizeof(float), st));
+      CK(conv_rows_dgrad_bnsums(d2[b]->row0, w.wd_c2[b], da1[b]->row0, r1[b]->row0, w.bn[i1].ss, w.bn_sums, rows, P, co[b], co[b], s3m,
+                                st, &bn1_summed));
+    }
+    if (!bn1_summed) CK(conv_rows_forward(d2[b]->row0, w.wd_c2[b], da1[b]->row0, nullptr, rows, P, co[b], co[b], 9, s3m, impl, st));
     CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
     // act1 = relu(bn1(raw1))
     CK(bn_backward(da1[b]->row0, nullptr, nullptr, r1[b]->row0, w.bn[i1].ss, w.bn[i1].mi, p + R.bn1_g, d1[b]->row0, g + R.bn1_g,
-                   g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, st));
+                   g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, bn1_summed ? 1 : 0, st));
     CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
     // gradient of the block input: conv1 path (3x3) + skip path (1x1).  Product path: ONE kernel, one accumulator, one
     // output tensor (dinm); otherwise two convolutions and BatchNorm's backward sums the two tensors.
@@ -624,7 +631,7 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
   // act0 = relu(bn0(raw0)); upstream = conv1 path + skip path of block 1
   CK(zero_guards(w.draw0, rp, st));
   CK(bn_backward(w.dact0m.row0, fused_in[0] ? nullptr : w.dact0s.row0, nullptr, w.raw0.row0, w.bn[0].ss, w.bn[0].mi, p + L.bn0_g, w.draw0.row0, g + L.bn0_g,
-                 g + L.bn0_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, 32, cnt, nullptr, st));
+                 g + L.bn0_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, 32, cnt, nullptr, 0, st));
   CK(conv0_wgrad(x, w.draw0.row0, g + L.conv0_w, rows, P, st));
   return MIVIT_OK;
 }
