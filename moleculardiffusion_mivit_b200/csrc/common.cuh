@@ -48,6 +48,33 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Validity (not a pad row / column) of the rows r0, r0 + stride, r0 + 2*stride, ... of the pitched-rows activation layout
+// (conv_tc.cu) without a division per row: r mod (P+1)^2 is carried incrementally and the split into (y, x) is a 32-bit
+// multiply-high (exact: q < 2^16, (P+1) <= 101).  The convolution epilogues call this once per 128-row tile and thread; the
+// 64-bit '%' and the int division they used before were ~45 dependent instructions with two MUFU.RCP on the epilogue's critical path.
+struct RowWalker {
+  long long r, stride;
+  uint32_t q, step, rpf, pitch, magic;
+  __device__ __forceinline__ void init(long long r0, long long stride_, int P) {
+    pitch = (uint32_t)(P + 1);
+    rpf = pitch * pitch;
+    magic = (uint32_t)((0x100000000ull + pitch - 1) / pitch);
+    r = r0;
+    stride = stride_;
+    q = (uint32_t)(r0 % (long long)rpf);
+    step = (uint32_t)(stride_ % (long long)rpf);
+  }
+  __device__ __forceinline__ bool valid(long long rows, int P) const {
+    const uint32_t y = __umulhi(q, magic), x = q - y * pitch;
+    return r < rows && y < (uint32_t)P && x < (uint32_t)P;
+  }
+  __device__ __forceinline__ void next() {
+    r += stride;
+    q += step;
+    if (q >= rpf) q -= rpf;
+  }
+};
+
 // optional device timing of tagged launches (capi.cu); work = algorithmic FLOPs or bytes of the launch
 int mivit_prof_tag(const char* name);
 bool mivit_prof_enabled();

@@ -13,8 +13,16 @@
 //     16-byte stores), one thread writes it out with a TMA store, and the BatchNorm statistics are column sums
 //     read back from the staged tile with a (chunk, 8-row group) thread mapping -- 8 LDS.128 and 128 FMAs per
 //     thread and region, no shuffles, partial sums carried in registers across the CTA's tiles.
-// Warp roles (256 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4 / 5 MMA issuers (even /
-// odd tiles, two accumulators), warp 6 TMA producer, warp 7 idle.
+// Warp roles (256 threads, 384 with two epilogue groups): warps 0-3 epilogue group 0 (TMEM lane quarter = warp id & 3), warps 4 / 5 MMA issuers (even /
+// odd tiles, two accumulators), warp 6 TMA producer, warp 7 idle, warps 8-11 epilogue group 1.
+// Two epilogue groups (even tiles -> group 0, odd tiles -> group 1, each with its own accumulator, staging buffers, named
+// barrier and statistics partials) are used for C_in = 32 only.  With C_out <= 64 per CTA a tile is 1150-1300 cycles of
+// tensor work but ~2450 cycles of epilogue (TMEM read, bf16 pack, staging, TMA store, BatchNorm column sums) for ONE group of
+// four single-issue warps (ncu: tensor pipe 53 % active, the epilogue warps busy 92 % of the time).  Measured with two
+// groups: 32 -> 64 + skip 0.533 -> 0.440 ms, but 64 -> 64 0.369 -> 0.460 ms, 64 -> 128 + skip 0.976 -> 1.212 ms and
+// 64 -> 32 (dual input) 0.352 -> 0.377 ms: at C_in >= 64 the N = 64 MMAs already want more shared-memory bandwidth than the
+// SM has (192 B/cycle, see conv_tc4.cu), and a second group's staging stores, statistics loads and TMA-store reads running
+// concurrently with them take it away from the tensor core.
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
@@ -26,17 +34,11 @@ constexpr int kTileM = 128;
 constexpr int kBoxRows = 32;
 constexpr int kMaxRing = 8;
 
-__device__ __forceinline__ bool row_valid3(long long r, long long rows, int P) {
-  if (r < 0 || r >= rows) return false;
-  const int pitch = P + 1;
-  const int q = (int)(r % (long long)(pitch * pitch));
-  const int y = q / pitch, x = q - y * pitch;
-  return y < P && x < P;
-}
 __device__ __forceinline__ void mbar_arrive3(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(mbar)) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
+
 __device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, const void* smem_src, int ch0, int row) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(ch0), "r"(row),
                "r"(umma::smem_u32(smem_src))
@@ -55,6 +57,8 @@ struct Cfg3 {
   static constexpr int kW2Bytes = CIN2 * NS * 2;                     // second input (1x1 path into the same accumulator)
   static constexpr int kRegions2 = CIN2 / 64;
   static constexpr int kStageBufs = kWBytes + kW2Bytes > 128 * 1024 ? 1 : 2;      // 147 KB of resident weights leave room for one
+  static constexpr int kEpiGroups = CIN <= 32 ? 2 : 1;      // epilogue warp groups (even / odd tiles), see the header comment
+  static constexpr int kThreads = kEpiGroups == 2 ? 384 : 256;
   static constexpr int kRegions = CIN >= 64 ? CIN / 64 : 1;          // pipeline units (64-channel regions) per tile
   static constexpr int kUnits = kRegions + kRegions2;
   static constexpr int kPitch = CIN >= 64 ? 128 : 64;                // bytes per input-tile row
@@ -71,7 +75,7 @@ struct Cfg3 {
 };
 
 template <int CIN, int NS, bool SKIP, int TAPS, int CIN2>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__((Cfg3<CIN, NS, SKIP, TAPS, CIN2>::kThreads), 1)
 conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                      const __grid_constant__ CUtensorMap tmYsk, const __grid_constant__ CUtensorMap tmX2,
                      const __nv_bfloat16* __restrict__ Wp, const __nv_bfloat16* __restrict__ Wsk,
@@ -86,14 +90,14 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint8_t* wsk = wsm + taps * CIN * NS * 2;              // [CH][NS][8]         (SKIP)
   uint8_t* w2sm = wsk + C::kWSkipBytes;                  // [CIN2/8][NS][8]     (second input, 1 tap)
   uint8_t* stage0 = w2sm + C::kW2Bytes;                  // 1-2 staged output regions (swizzled [row][kOutPitch])
-  uint8_t* slab0 = stage0 + C::kStageBufs * C::kStageBytes;   // ring of input units
+  uint8_t* slab0 = stage0 + C::kEpiGroups * C::kStageBufs * C::kStageBytes;   // ring of input units
   uint8_t* tail = slab0 + (size_t)ring * unit_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);    // [kMaxRing] TMA -> MMA
   uint64_t* empty = full + kMaxRing;                     // [kMaxRing] MMA (commit) -> TMA
   uint64_t* tfull = empty + kMaxRing;                    // [2] MMA (commit) -> epilogue
   uint64_t* tempty = tfull + 2;                          // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* red = reinterpret_cast<float*>(tmem_slot + 4);  // [kOutRegions][2][kOutW] statistics of the CTA
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);  // [kEpiGroups][kOutRegions][2][kOutW] statistics of the CTA
 
   const int nh = blockIdx.x % nsplit;                    // output-column slice of this CTA = rank in the cluster
   const int cta_in_slice = blockIdx.x / nsplit, ctas_per_slice = gridDim.x / nsplit;
@@ -116,24 +120,24 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (CIN2 > 0) tma::prefetch_map(&tmX2);
   }
   if (warp == 0) umma::tmem_alloc<C::kTmemCols>(tmem_slot);
-  for (int i = tid; i < C::kOutRegions * 2 * C::kOutW; i += 256) red[i] = 0.f;
+  for (int i = tid; i < C::kEpiGroups * C::kOutRegions * 2 * C::kOutW; i += C::kThreads) red[i] = 0.f;
   // resident weights of this column slice
   {
     const int per_tap = C::kCH * NS;  // 16-byte units per tap in smem
-    for (int i = tid; i < taps * per_tap; i += 256) {
+    for (int i = tid; i < taps * per_tap; i += C::kThreads) {
       const int t = i / per_tap, r = i - t * per_tap, ch = r / NS, n = r - ch * NS;
       const uint4* src = reinterpret_cast<const uint4*>(Wp) + ((size_t)(t * C::kCH + ch) * cout_total + col0 + n);
       reinterpret_cast<uint4*>(wsm)[i] = __ldg(src);
     }
     if (SKIP) {
-      for (int i = tid; i < per_tap; i += 256) {
+      for (int i = tid; i < per_tap; i += C::kThreads) {
         const int ch = i / NS, n = i - ch * NS;
         const uint4* src = reinterpret_cast<const uint4*>(Wsk) + ((size_t)ch * cout_total + col0 + n);
         reinterpret_cast<uint4*>(wsk)[i] = __ldg(src);
       }
     }
     if (CIN2 > 0) {
-      for (int i = tid; i < (CIN2 / 8) * NS; i += 256) {
+      for (int i = tid; i < (CIN2 / 8) * NS; i += C::kThreads) {
         const int ch = i / NS, n = i - ch * NS;
         const uint4* src = reinterpret_cast<const uint4*>(Wp2) + ((size_t)ch * cout_total + col0 + n);
         reinterpret_cast<uint4*>(w2sm)[i] = __ldg(src);
@@ -247,9 +251,13 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         __syncwarp();
       }
     }
-  } else if (warp < 4) {
-    // ===================== epilogue warps 0-3 =====================
-    constexpr int kSwz = C::kOutPitch == 128 ? 7 : 3;
+  } else if (warp < 4 || (warp >= 8 && C::kEpiGroups == 2)) {
+    // ===================== epilogue: group 0 = warps 0-3 (even tiles), group 1 = warps 8-11 (odd tiles) =====================
+    const int grp = warp >= 8 ? 1 : 0;
+    const int ew = warp & 3;                              // TMEM lane quarter of this warp
+    const int etid = ew * 32 + lane;                      // thread index inside the group
+    uint8_t* gstage = stage0 + grp * C::kStageBufs * C::kStageBytes;
+    float* gred = red + grp * C::kOutRegions * 2 * C::kOutW;
     constexpr int kChunks = C::kOutPitch / 16;            // 16-byte chunks per staged row
     constexpr int kRowsPerThread = 128 / (128 / kChunks); // stats: thread = (chunk, row group); rows per group
     float ssum[C::kOutRegions][8], ssq[C::kOutRegions][8];
@@ -257,27 +265,29 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     for (int o = 0; o < C::kOutRegions; ++o)
 #pragma unroll
       for (int i = 0; i < 8; ++i) ssum[o][i] = ssq[o][i] = 0.f;
-    const int my_row = warp * 32 + lane;
+    const int my_row = ew * 32 + lane;
     const int my_swz = C::kOutPitch == 128 ? (my_row & 7) : ((my_row >> 1) & 3);
-    const int sc = tid & (kChunks - 1), sg = tid / kChunks;       // statistics mapping
+    const int sc = etid & (kChunks - 1), sg = etid / kChunks;     // statistics mapping
     uint32_t sidx = 0;
     int k = 0;
-    for (int tile = cta_in_slice; tile < n_tiles; tile += ctas_per_slice, ++k) {
+    RowWalker rw;
+    rw.init((long long)cta_in_slice * kTileM + my_row, (long long)ctas_per_slice * kTileM, P);
+    for (int tile = cta_in_slice; tile < n_tiles; tile += ctas_per_slice, ++k, rw.next()) {
       const int buf = k & 1;
+      if (C::kEpiGroups == 2 && buf != grp) continue;
       umma::mbar_wait(tfull + buf, (k >> 1) & 1);
       umma::fence_after_sync();
-      const long long r = (long long)tile * kTileM + my_row;
-      const bool valid = row_valid3(r, rows, P);
-      const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * C::kAccCols);
+      const bool valid = rw.valid(rows, P);
+      const uint32_t acc = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * C::kAccCols);
 #pragma unroll
       for (int o = 0; o < (SKIP ? 2 : 1); ++o) {
         const bool want_stats = (o == 0 ? stats : stats_sk) != nullptr;
 #pragma unroll
         for (int q = 0; q < C::kOutPerAcc; ++q, ++sidx) {
-          uint8_t* stg = stage0 + (sidx % C::kStageBufs) * C::kStageBytes;
+          uint8_t* stg = gstage + (sidx % C::kStageBufs) * C::kStageBytes;
           // the TMA store that read this staging buffer two regions ago is done; everyone finished its statistics reads
-          if (tid == 0) bulk_wait_read<C::kStageBufs - 1>();
-          epi_bar_sync();
+          if (etid == 0) bulk_wait_read<C::kStageBufs - 1>();
+          epi_bar_sync(grp);
 #pragma unroll
           for (int g = 0; g < C::kOutW / 32; ++g) {
             float v[32];
@@ -302,8 +312,8 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
           }
           umma::fence_proxy_async();   // generic-proxy writes of the staged tile -> visible to the TMA store
-          epi_bar_sync();
-          if (tid == 0) tma_store_tile(o == 0 ? &tmY : &tmYsk, stg, col0 + q * C::kOutW, guard + tile * kTileM);
+          epi_bar_sync(grp);
+          if (etid == 0) tma_store_tile(o == 0 ? &tmY : &tmYsk, stg, col0 + q * C::kOutW, guard + tile * kTileM);
           if (want_stats) {
             // column sums of the STORED (bf16-rounded, pad-masked) values
 #pragma unroll
@@ -325,7 +335,7 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
     }
-    if (tid == 0) bulk_wait_read<0>();   // shared memory stays valid until the last store has read it
+    if (etid == 0) bulk_wait_read<0>();   // shared memory stays valid until the last store has read it
     // CTA-level reduction of the per-thread column sums, then one atomic per channel
     if (k > 0) {
 #pragma unroll
@@ -333,7 +343,7 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if ((o == 0 ? stats : stats_sk) == nullptr) continue;
 #pragma unroll
         for (int q = 0; q < C::kOutPerAcc; ++q) {
-          float* rr = red + (o * C::kOutPerAcc + q) * 2 * C::kOutW;
+          float* rr = gred + (o * C::kOutPerAcc + q) * 2 * C::kOutW;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             atomicAdd(rr + sc * 8 + i, ssum[o * C::kOutPerAcc + q][i]);
@@ -341,14 +351,14 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
         }
       }
-      epi_bar_sync();
+      epi_bar_sync(grp);
 #pragma unroll
       for (int o = 0; o < (SKIP ? 2 : 1); ++o) {
         float* st = o == 0 ? stats : stats_sk;
         if (st == nullptr) continue;
-        for (int i = tid; i < C::kOutPerAcc * 2 * C::kOutW; i += 128) {
+        for (int i = etid; i < C::kOutPerAcc * 2 * C::kOutW; i += 128) {
           const int q = i / (2 * C::kOutW), rem = i - q * 2 * C::kOutW, which = rem / C::kOutW, ch = rem - which * C::kOutW;
-          atomicAdd(st + which * cout_total + col0 + q * C::kOutW + ch, red[(o * C::kOutPerAcc + q) * 2 * C::kOutW + rem]);
+          atomicAdd(st + which * cout_total + col0 + q * C::kOutW + ch, gred[(o * C::kOutPerAcc + q) * 2 * C::kOutW + rem]);
         }
       }
     }
@@ -371,8 +381,8 @@ int launch3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   *fits = halo <= guard - kBoxRows;
   if (!*fits) return MIVIT_OK;
   const int unit_bytes = xslab_rows * C::kPitch;
-  const int fixed = taps * CIN * NS * 2 + C::kWSkipBytes + C::kW2Bytes + C::kStageBufs * C::kStageBytes;
-  const int tail = (2 * kMaxRing + 4) * 8 + 16 + C::kOutRegions * 2 * C::kOutW * 4 + 64;
+  const int fixed = taps * CIN * NS * 2 + C::kWSkipBytes + C::kW2Bytes + C::kEpiGroups * C::kStageBufs * C::kStageBytes;
+  const int tail = (2 * kMaxRing + 4) * 8 + 16 + C::kEpiGroups * C::kOutRegions * 2 * C::kOutW * 4 + 64;
   int ring = (227 * 1024 - fixed - tail) / unit_bytes;
   if (ring > kMaxRing) ring = kMaxRing;
   *fits = ring >= 2 && ring >= C::kRegions && (CIN2 == 0 || (ring >= 3 && C::kPitch == 128));
@@ -405,7 +415,7 @@ int launch3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   int per_slice = sms / nsplit;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(256, 1, 1);
+  cfg.blockDim = dim3(C::kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -30,13 +30,6 @@ constexpr int kTileM = 128;
 constexpr int kBoxRows = 32;
 constexpr int kMaxRing = 8;
 
-__device__ __forceinline__ bool row_valid4(long long r, long long rows, int P) {
-  if (r < 0 || r >= rows) return false;
-  const int pitch = P + 1;
-  const int q = (int)(r % (long long)(pitch * pitch));
-  const int y = q / pitch, x = q - y * pitch;
-  return y < P && x < P;
-}
 __device__ __forceinline__ void epi_bar_sync4() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_tile4(const CUtensorMap* tm, const void* smem_src, int ch0, int row) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(ch0), "r"(row),
@@ -292,13 +285,14 @@ conv_rows_tc4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (BSTAT && pair < n_pair_tiles) prefetch_raw(2 * pair + (int)rank, 0, rawv[0]);
     uint32_t sidx = 0;
     int k = 0;
-    for (int pt = pair; pt < n_pair_tiles; pt += n_pairs, ++k) {
+    RowWalker rw;
+    rw.init((long long)(2 * pair + (int)rank) * kTileM + my_row, (long long)2 * n_pairs * kTileM, P);
+    for (int pt = pair; pt < n_pair_tiles; pt += n_pairs, ++k, rw.next()) {
       const int tile = 2 * pt + (int)rank;
       const int buf = k & 1;
       umma::mbar_wait(tfull + buf, (k >> 1) & 1);
       umma::fence_after_sync();
-      const long long r = (long long)tile * kTileM + my_row;
-      const bool valid = row_valid4(r, rows, P);
+      const bool valid = rw.valid(rows, P);
       const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * C::kAccCols);
       const uint32_t leader_tempty = map_to_rank(umma::smem_u32(tempty + buf), 0);
 #pragma unroll
