@@ -84,6 +84,58 @@ struct PixelStream {
   }
 };
 
+// PTRS set-up and log-pmf table for ONE lambda.  The V1 renderer multiplies every pixel by Poisson(pn)/pn with the same
+// pn (helpersGeneration.py:316-317), so the set-up (sqrt, 2 logs, 3 divisions) is done once per thread instead of once per
+// pixel and the right-hand side of the acceptance test, log pmf(k), comes from a shared-memory table filled with
+// poisson_logpmf itself -- the values, hence every draw, are bit-identical to poisson_draw(lam, st).  ncu (source view,
+// r01_render): the per-pixel set-up and the three logf + log1pf of the slow acceptance path were 28 % of the renderer's
+// instructions, executed by ~10 of 32 lanes (a third of the pixels miss the squeeze test).
+constexpr int kPoissonTable = 256;
+struct PoissonConst {
+  float lam, loglam, b, a, log_invalpha, vr, li, lf;
+  int k0;       // the table holds log pmf(k) for k in [k0, k0 + kPoissonTable)
+  bool ptrs;    // lam >= 10
+};
+__device__ __forceinline__ PoissonConst poisson_setup(float lam) {
+  PoissonConst c;
+  c.lam = lam;
+  c.ptrs = lam >= 10.0f;
+  const float slam = sqrtf(lam);
+  c.loglam = logf(lam);
+  c.b = __fadd_rn(0.931f, __fmul_rn(2.53f, slam));
+  c.a = __fadd_rn(-0.059f, __fmul_rn(0.02483f, c.b));
+  c.log_invalpha = logf(1.1239f + 1.1328f / (c.b - 3.4f));
+  c.vr = 0.9277f - 3.6224f / (c.b - 2.0f);
+  c.li = floorf(lam);
+  c.lf = lam - c.li;
+  c.k0 = lam > 128.0f ? (int)lam - 128 : 0;
+  return c;
+}
+__device__ __forceinline__ void poisson_fill_table(const PoissonConst& c, float* __restrict__ tab, int tid, int nthreads) {
+  for (int i = tid; i < kPoissonTable; i += nthreads) tab[i] = poisson_logpmf((float)(c.k0 + i), c.lam, c.li, c.lf, c.loglam);
+}
+
+__device__ __forceinline__ float poisson_draw(float lam, PixelStream& st);
+
+// poisson_draw(c.lam, st) with the launch-constant pieces taken from c / tab (same arithmetic, same draws)
+__device__ __forceinline__ float poisson_draw_const(const PoissonConst& c, const float* __restrict__ tab, PixelStream& st) {
+  if (!c.ptrs) return poisson_draw(c.lam, st);
+  for (int it = 0; it < 512; ++it) {
+    const float U = u01(st.next()) - 0.5f;
+    const float V = u01(st.next());
+    const float us = 0.5f - fabsf(U);
+    const float d = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(__fmul_rn(2.0f, c.a), us), c.b), U), 0.43f);
+    const float kf = c.li + floorf(c.lf + d);
+    if (us >= 0.07f && V <= c.vr) return kf;
+    if (!(kf >= 0.0f) || !isfinite(kf) || (us < 0.013f && V > us)) continue;
+    const float lhs = logf(V) + c.log_invalpha - logf(c.a / (us * us) + c.b);
+    const int ki = (int)kf - c.k0;
+    const float rhs = (ki >= 0 && ki < kPoissonTable) ? tab[ki] : poisson_logpmf(kf, c.lam, c.li, c.lf, c.loglam);
+    if (lhs <= rhs) return kf;
+  }
+  return c.li;
+}
+
 // numpy's random_poisson (legacy-distributions.c): multiplication method below 10,
 // Hoermann PTRS above, float32.
 __device__ __forceinline__ float poisson_draw(float lam, PixelStream& st) {

@@ -143,7 +143,8 @@ __device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, 
 }
 
 // one output pixel of frame f: signal + clipped Gaussian background, multiplicative Poisson, fused normalisation
-__device__ __forceinline__ float v1_pixel(const RenderDev& d, const WarpSmem& w, int f, int pix, uint32_t seq) {
+__device__ __forceinline__ float v1_pixel(const RenderDev& d, const WarpSmem& w, int f, int pix, uint32_t seq,
+                                          const PoissonConst& pc, const float* __restrict__ ptab) {
   const int P = d.P;
   const int a = pix / P, b = pix - a * P;
   float v = d.draw ? pixel_signal(d, w, a, b) : 0.0f;
@@ -158,7 +159,7 @@ __device__ __forceinline__ float v1_pixel(const RenderDev& d, const WarpSmem& w,
   const float bg = fminf(fmaxf(__fadd_rn(d.bg_mean, __fmul_rn(d.bg_std, zb)), 0.0f), d.bg_hi);  // :312-313
   v = __fadd_rn(v, bg);
   if (d.poisson != -1.0f) {  // :316-317 multiplicative Poisson
-    const float k = d.mean_noise ? d.poisson : poisson_draw(d.poisson, st);
+    const float k = d.mean_noise ? d.poisson : poisson_draw_const(pc, ptab, st);
     v = __fdiv_rn(__fmul_rn(v, k), d.poisson);
   }
   if (d.normalize) v = __fdiv_rn(__fsub_rn(v, d.norm_sub), d.norm_div);  // :395
@@ -171,6 +172,10 @@ __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   WarpSmem w = carve(smem + (size_t)warp * warp_smem_floats(d.n, d.P), d.n, d.P);
+  __shared__ float ptab[kPoissonTable];
+  const PoissonConst pc = poisson_setup(d.poisson);
+  if (d.poisson != -1.0f && !d.mean_noise && pc.ptrs) poisson_fill_table(pc, ptab, threadIdx.x, blockDim.x);
+  __syncthreads();
   const long long gf = (long long)blockIdx.x * warps + warp;  // global frame index
   if (gf >= n_frames_total) return;
   const long long s = gf / d.F;
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict
     __syncwarp();
   }
   float* dst = out + s * d.out_seq_stride + (long long)f * P * P;
-  for (int pix = lane; pix < P * P; pix += 32) dst[pix] = v1_pixel(d, w, f, pix, seq);
+  for (int pix = lane; pix < P * P; pix += 32) dst[pix] = v1_pixel(d, w, f, pix, seq, pc, ptab);
 }
 
 // Renderer fused with the frame embedding of LinearProjectionEmbedding / CNNEmbedding (helpers/models.py:146-199:
@@ -208,6 +213,9 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
   WarpSmem w = carve(mine, n, P);
   float* px = mine + warp_smem_floats(n, P);               // [PP] rendered frame
   for (int i = threadIdx.x; i < PP * E; i += blockDim.x) wts[i] = __ldg(Wt + i);
+  __shared__ float ptab[kPoissonTable];
+  const PoissonConst pc = poisson_setup(d.poisson);
+  if (d.poisson != -1.0f && !d.mean_noise && pc.ptrs) poisson_fill_table(pc, ptab, threadIdx.x, blockDim.x);
   __syncthreads();
   for (long long gf = (long long)blockIdx.x * warps + warp; gf < n_frames_total; gf += (long long)gridDim.x * warps) {
     const long long s = gf / d.F;
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
       __syncwarp();
     }
     for (int pix = lane; pix < PP; pix += 32) {
-      const float v = v1_pixel(d, w, f, pix, seq);
+      const float v = v1_pixel(d, w, f, pix, seq, pc, ptab);
       px[pix] = v;
       if (frames_out != nullptr) frames_out[s * d.out_seq_stride + (long long)f * PP + pix] = v;
     }
