@@ -68,12 +68,27 @@ __device__ __forceinline__ void tmem_dealloc_n(uint32_t taddr, int cols) {
 }
 __host__ __device__ inline int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
+// Up to three independent problems of the same shape in one launch (blockIdx.y): the q / k / v projections of an encoder
+// layer (forward) and their weight gradients.  Each of these launches is a latency chain (load -> MMA -> store) over a single
+// wave of CTAs; three problems in one grid let the load phase of one CTA overlap the epilogue of another on the same SM.
+struct LinBatch {
+  const float* A[3];
+  const float* W[3];
+  const float* bias[3];
+  float* Y[3];
+};
+template <typename T>
+__device__ __forceinline__ T pick3(T const (&a)[3], int z) { return z == 0 ? a[0] : z == 1 ? a[1] : a[2]; }
+
 // ------------------------------------------------------------------ forward / dgrad -------------
 // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-7 producers.
 template <bool BMN>
 __global__ void __launch_bounds__(256, 1)
-linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ Y,
-                 int M, int K, int N, int n_tiles, int relu, int accumulate) {
+linear_tc_kernel(const __grid_constant__ LinBatch batch, int M, int K, int N, int n_tiles, int relu, int accumulate) {
+  const float* __restrict__ A = pick3(batch.A, (int)blockIdx.y);
+  const float* __restrict__ W = pick3(batch.W, (int)blockIdx.y);
+  const float* __restrict__ bias = pick3(batch.bias, (int)blockIdx.y);
+  float* __restrict__ Y = pick3(batch.Y, (int)blockIdx.y);
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int kch = K / 4;                       // 16-byte chunks along the reduction dim of A
@@ -219,8 +234,12 @@ linear_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const
 // ------------------------------------------------------------------ weight gradient -------------
 // warps 0-3 producers + final flush, warp 4 MMA issuer, warps 5-7 producers.
 __global__ void __launch_bounds__(256, 1)
-linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ dW, float* __restrict__ db,
-                       int M, int N, int K, int n_stages, int stages_per_cta, int buf_bytes) {
+linear_wgrad_tc_kernel(const __grid_constant__ LinBatch batch /* A = dY, W = X, Y = dW, bias = db */, int M, int N, int K,
+                       int n_stages, int stages_per_cta, int buf_bytes) {
+  const float* __restrict__ dY = pick3(batch.A, (int)blockIdx.y);
+  const float* __restrict__ X = pick3(batch.W, (int)blockIdx.y);
+  float* __restrict__ dW = pick3(batch.Y, (int)blockIdx.y);
+  float* __restrict__ db = const_cast<float*>(pick3(batch.bias, (int)blockIdx.y));
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int nch = N / 4, kch = K / 4;
@@ -350,25 +369,31 @@ bool linear_tc_supported(int M, int K, int N) {
          (size_t)K * N * 4 + 2 * (size_t)(K / 4) * kRows * 16 + 4 * 4096 + 256 <= 227 * 1024;
 }
 
-// mode 0: Y = A W^T (+bias)(relu), W [N][K].   mode 1: Y (+)= A W, W [K][N].
-int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M, int K, int N, int mode, int relu, int accumulate,
-              cudaStream_t st) {
+// mode 0: Y = A W^T (+bias)(relu), W [N][K].   mode 1: Y (+)= A W, W [K][N].   nb <= 3 problems of the same shape.
+int linear_tc_batched(int nb, const float* const* A, const float* const* W, const float* const* bias, float* const* Y, int M, int K,
+                      int N, int mode, int relu, int accumulate, cudaStream_t st) {
+  LinBatch b = {};
+  for (int i = 0; i < nb; ++i) { b.A[i] = A[i]; b.W[i] = W[i]; b.bias[i] = bias ? bias[i] : nullptr; b.Y[i] = Y[i]; }
   int smem = K * N * 4 + 2 * (K / 4) * kRows * 16 + 4 * 4096 + 256;
   if (2 * pow2_cols(N) > 256 && smem < 120 * 1024) smem = 120 * 1024;   // 512 TMEM columns: one CTA per SM
   const int n_tiles = (M + kRows - 1) / kRows;
   const int per_sm = (smem <= 113 * 1024 && 2 * pow2_cols(N) <= 256) ? 2 : 1;
   const int grid = n_tiles < per_sm * sm_count() ? n_tiles : per_sm * sm_count();
-  MivitProfScope prof(mode ? "linear_tc_dgrad" : "linear_tc_fwd", 2.0 * M * K * N, st);
+  MivitProfScope prof(mode ? "linear_tc_dgrad" : "linear_tc_fwd", 2.0 * M * K * N * nb, st);
   if (mode == 0) {
     MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    linear_tc_kernel<false><<<grid, 256, smem, st>>>(A, W, bias, Y, M, K, N, n_tiles, relu, accumulate);
+    linear_tc_kernel<false><<<dim3(grid, nb), 256, smem, st>>>(b, M, K, N, n_tiles, relu, accumulate);
   } else {
     MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    linear_tc_kernel<true><<<grid, 256, smem, st>>>(A, W, bias, Y, M, K, N, n_tiles, relu, accumulate);
+    linear_tc_kernel<true><<<dim3(grid, nb), 256, smem, st>>>(b, M, K, N, n_tiles, relu, accumulate);
   }
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
+}
+int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M, int K, int N, int mode, int relu, int accumulate,
+              cudaStream_t st) {
+  return linear_tc_batched(1, &A, &W, &bias, &Y, M, K, N, mode, relu, accumulate, st);
 }
 
 bool linear_wgrad_tc_supported(int M, int N, int K) {
@@ -380,7 +405,10 @@ bool linear_wgrad_tc_supported(int M, int N, int K) {
 
 // dW[N][K] += dY[M,N]^T X[M,K]   (dW pre-zeroed / holds the value to accumulate onto)
 // db (optional, [N]) += column sums of dY
-int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
+int linear_wgrad_tc_batched(int nb, const float* const* dY, const float* const* X, float* const* dW, float* const* db, int M, int N,
+                            int K, cudaStream_t st) {
+  LinBatch b = {};
+  for (int i = 0; i < nb; ++i) { b.A[i] = dY[i]; b.W[i] = X[i]; b.Y[i] = dW[i]; b.bias[i] = db ? db[i] : nullptr; }
   // the M = 128 MMA over-reads the A slab up to 32 chunks: keep that inside the stage buffer
   int buf_bytes = (N / 4 + K / 4 + 8) * kRows * 16;
   const int need = 32 * kRows * 16;
@@ -392,9 +420,12 @@ int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M
   int ctas = n_stages < sm_count() ? n_stages : sm_count();
   const int spc = (n_stages + ctas - 1) / ctas;
   ctas = (n_stages + spc - 1) / spc;
-  MivitProfScope prof("linear_tc_wgrad", 2.0 * M * K * N, st);
-  linear_wgrad_tc_kernel<<<ctas, 256, smem, st>>>(dY, X, dW, db, M, N, K, n_stages, spc, buf_bytes);
+  MivitProfScope prof("linear_tc_wgrad", 2.0 * M * K * N * nb, st);
+  linear_wgrad_tc_kernel<<<dim3(ctas, nb), 256, smem, st>>>(b, M, N, K, n_stages, spc, buf_bytes);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
+}
+int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
+  return linear_wgrad_tc_batched(1, &dY, &X, &dW, &db, M, N, K, st);
 }

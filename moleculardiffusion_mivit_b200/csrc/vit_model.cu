@@ -454,9 +454,19 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
   for (int l = 0; l < c->L; ++l) {
     const auto& Y = L.lyr[l];
     LayerWS& y = w.lyr[l];
-    CK(linear_fwd(xin, p + Y.q_w, p + Y.q_b, y.q, T, E, E, 0, st));
-    CK(linear_fwd(xin, p + Y.k_w, p + Y.k_b, y.k, T, E, E, 0, st));
-    CK(linear_fwd(xin, p + Y.v_w, p + Y.v_b, y.v, T, E, E, 0, st));
+    if (g_linear_tc && linear_tc_supported(T, E, E) && al16(xin) && al16(p + Y.q_w) && al16(p + Y.k_w) && al16(p + Y.v_w) &&
+        al16(p + Y.q_b) && al16(p + Y.k_b) && al16(p + Y.v_b) && al16(y.q) && al16(y.k) && al16(y.v)) {
+      // the three projections read the same tokens and are independent: one launch, three problems (linear_tc.cu)
+      const float* As[3] = {xin, xin, xin};
+      const float* Ws[3] = {p + Y.q_w, p + Y.k_w, p + Y.v_w};
+      const float* bs[3] = {p + Y.q_b, p + Y.k_b, p + Y.v_b};
+      float* Ys[3] = {y.q, y.k, y.v};
+      CK(linear_tc_batched(3, As, Ws, bs, Ys, T, E, E, 0, 0, 0, st));
+    } else {
+      CK(linear_fwd(xin, p + Y.q_w, p + Y.q_b, y.q, T, E, E, 0, st));
+      CK(linear_fwd(xin, p + Y.k_w, p + Y.k_b, y.k, T, E, E, 0, st));
+      CK(linear_fwd(xin, p + Y.v_w, p + Y.v_b, y.v, T, E, E, 0, st));
+    }
     CK(attention_fwd(y.q, y.k, y.v, y.ctx, y.probs, B, S, E, H, st));
     CK(linear_fwd(y.ctx, p + Y.o_w, p + Y.o_b, y.ao, T, E, E, 0, st));
     CK(layernorm_fwd(y.ao, xin, p + Y.n1_g, p + Y.n1_b, y.z1, y.x1, y.m1, y.r1, T, E, c->ln_eps, 0, 0, 0, st));
@@ -521,9 +531,23 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
     CK(layernorm_bwd(tmp, y.z1, y.m1, y.r1, p + Y.n1_g, dx, g + Y.n1_g, g + Y.n1_b, T, E, 0, 0, 0, st));   // dx = dz1 = dao = dxin
     CK(linear_bwd(y.ctx, p + Y.o_w, dx, g + Y.o_w, g + Y.o_b, w.dctx, T, E, E, 0, st));
     CK(attention_bwd(y.q, y.k, y.v, y.probs, y.ctx, w.dctx, w.dq, w.dk, w.dv, B, S, E, H, st));
-    CK(linear_bwd(xin, p + Y.q_w, w.dq, g + Y.q_w, g + Y.q_b, dx, T, E, E, 1, st));
-    CK(linear_bwd(xin, p + Y.k_w, w.dk, g + Y.k_w, g + Y.k_b, dx, T, E, E, 1, st));
-    CK(linear_bwd(xin, p + Y.v_w, w.dv, g + Y.v_w, g + Y.v_b, dx, T, E, E, 1, st));
+    if (g_linear_tc && linear_wgrad_tc_supported(T, E, E) && linear_tc_supported(T, E, E) && al16(xin) && al16(w.dq) && al16(w.dk) &&
+        al16(w.dv) && al16(g + Y.q_w) && al16(g + Y.k_w) && al16(g + Y.v_w) && al16(p + Y.q_w) && al16(p + Y.k_w) && al16(p + Y.v_w) &&
+        al16(dx)) {
+      // three weight gradients in one launch; the three input gradients accumulate into dx one after the other
+      const float* dYs[3] = {w.dq, w.dk, w.dv};
+      const float* Xs[3] = {xin, xin, xin};
+      float* dWs[3] = {g + Y.q_w, g + Y.k_w, g + Y.v_w};
+      float* dbs[3] = {g + Y.q_b, g + Y.k_b, g + Y.v_b};
+      CK(linear_wgrad_tc_batched(3, dYs, Xs, dWs, dbs, T, E, E, st));
+      CK(linear_tc(w.dq, p + Y.q_w, nullptr, dx, T, E, E, 1, 0, 1, st));
+      CK(linear_tc(w.dk, p + Y.k_w, nullptr, dx, T, E, E, 1, 0, 1, st));
+      CK(linear_tc(w.dv, p + Y.v_w, nullptr, dx, T, E, E, 1, 0, 1, st));
+    } else {
+      CK(linear_bwd(xin, p + Y.q_w, w.dq, g + Y.q_w, g + Y.q_b, dx, T, E, E, 1, st));
+      CK(linear_bwd(xin, p + Y.k_w, w.dk, g + Y.k_w, g + Y.k_b, dx, T, E, E, 1, st));
+      CK(linear_bwd(xin, p + Y.v_w, w.dv, g + Y.v_w, g + Y.v_b, dx, T, E, E, 1, st));
+    }
   }
   // tokens: regression token, positional embedding, early-fusion projection
   CK(tokens_finish_bwd(dx, c->use_reg ? g + L.reg : nullptr, early ? w.dfp : nullptr, c->use_pos ? g + L.pos : nullptr, B, S, E, st));
