@@ -76,6 +76,7 @@ struct LinBatch {
   const float* W[3];
   const float* bias[3];
   float* Y[3];
+  const float* gate;   // optional [M,N]: Y = gate > 0 ? Y : 0  (backward of a ReLU fused into the dgrad that feeds it)
 };
 template <typename T>
 __device__ __forceinline__ T pick3(T const (&a)[3], int z) { return z == 0 ? a[0] : z == 1 ? a[1] : a[2]; }
@@ -219,6 +220,10 @@ linear_tc_kernel(const __grid_constant__ LinBatch batch, int M, int K, int N, in
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (batch.gate != nullptr) {
+              const float4 gt = __ldg(reinterpret_cast<const float4*>(batch.gate + (row0 + row) * N + g * 32) + c);
+              o.x = gt.x > 0.f ? o.x : 0.f; o.y = gt.y > 0.f ? o.y : 0.f; o.z = gt.z > 0.f ? o.z : 0.f; o.w = gt.w > 0.f ? o.w : 0.f;
+            }
             *p = o;
           }
         }
@@ -371,8 +376,9 @@ bool linear_tc_supported(int M, int K, int N) {
 
 // mode 0: Y = A W^T (+bias)(relu), W [N][K].   mode 1: Y (+)= A W, W [K][N].   nb <= 3 problems of the same shape.
 int linear_tc_batched(int nb, const float* const* A, const float* const* W, const float* const* bias, float* const* Y, int M, int K,
-                      int N, int mode, int relu, int accumulate, cudaStream_t st) {
+                      int N, int mode, int relu, int accumulate, cudaStream_t st, const float* gate) {
   LinBatch b = {};
+  b.gate = gate;
   for (int i = 0; i < nb; ++i) { b.A[i] = A[i]; b.W[i] = W[i]; b.bias[i] = bias ? bias[i] : nullptr; b.Y[i] = Y[i]; }
   int smem = K * N * 4 + 2 * (K / 4) * kRows * 16 + 4 * 4096 + 256;
   if (2 * pow2_cols(N) > 256 && smem < 120 * 1024) smem = 120 * 1024;   // 512 TMEM columns: one CTA per SM
@@ -393,7 +399,7 @@ int linear_tc_batched(int nb, const float* const* A, const float* const* W, cons
 }
 int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M, int K, int N, int mode, int relu, int accumulate,
               cudaStream_t st) {
-  return linear_tc_batched(1, &A, &W, &bias, &Y, M, K, N, mode, relu, accumulate, st);
+  return linear_tc_batched(1, &A, &W, &bias, &Y, M, K, N, mode, relu, accumulate, st, nullptr);
 }
 
 bool linear_wgrad_tc_supported(int M, int N, int K) {

@@ -524,8 +524,16 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
     const float* xin = l == 0 ? w.tok : w.lyr[l - 1].x2;
     // x2 = LN2(x1 + ff)
     CK(layernorm_bwd(dx, y.z2, y.m2, y.r2, p + Y.n2_g, tmp, g + Y.n2_g, g + Y.n2_b, T, E, 0, 0, 0, st));  // tmp = dz2 = dff = dx1
-    CK(linear_bwd(y.hact, p + Y.f2_w, tmp, g + Y.f2_w, g + Y.f2_b, w.dh, T, E, HD, 0, st));
-    CK(act_bwd(w.dh, c->activation == 0 ? y.hact : y.hpre, w.dh2, (long long)T * HD, c->activation, st));
+    if (c->activation == 0 && g_linear_tc && linear_tc_supported(T, E, HD) && al16(tmp) && al16(p + Y.f2_w) && al16(w.dh2) &&
+        al16(y.hact)) {
+      // F.relu: its backward (dh2 = dh * 1[hact > 0]) is a gate in the epilogue of the fc2 input gradient
+      CK(linear_bwd(y.hact, p + Y.f2_w, tmp, g + Y.f2_w, g + Y.f2_b, nullptr, T, E, HD, 0, st));
+      const float* A1 = tmp; const float* W1 = p + Y.f2_w; float* Y1 = w.dh2;
+      CK(linear_tc_batched(1, &A1, &W1, nullptr, &Y1, T, E, HD, 1, 0, 0, st, y.hact));
+    } else {
+      CK(linear_bwd(y.hact, p + Y.f2_w, tmp, g + Y.f2_w, g + Y.f2_b, w.dh, T, E, HD, 0, st));
+      CK(act_bwd(w.dh, c->activation == 0 ? y.hact : y.hpre, w.dh2, (long long)T * HD, c->activation, st));
+    }
     CK(linear_bwd(y.x1, p + Y.f1_w, w.dh2, g + Y.f1_w, g + Y.f1_b, tmp, T, HD, E, 1, st));               // tmp += dhpre W1
     // x1 = LN1(xin + ao)
     CK(layernorm_bwd(tmp, y.z1, y.m1, y.r1, p + Y.n1_g, dx, g + Y.n1_g, g + Y.n1_b, T, E, 0, 0, 0, st));   // dx = dz1 = dao = dxin
