@@ -486,6 +486,18 @@ __device__ __forceinline__ void ldg4f(const float* __restrict__ p, float (&v)[4]
 // rows in flight.  Re-reading them from L1 for EVERY row made this pass L1-bandwidth bound (12-16 LDG.128 of constants per
 // 2-3 LDG.128 of data: 4.6 TB/s); they are now read once per 4-channel half and applied to all kU rows in flight, and the
 // results overwrite the input registers half by half.
+//
+// Loads in flight: registers only hold 8 sixteen-byte loads per thread (64 KB per SM at 2 x 256 threads, and only while the
+// thread is not computing), which left this pass at 5.0-5.6 TB/s.  The inputs now go through a THREAD-PRIVATE ring in shared
+// memory filled with cp.async: slot (stage, row u, stream s) of thread t is ring[((stage*SLOTS + u*NS + s)*256 + t], so a
+// thread only ever reads what it copied itself -- cp.async.wait_group is the only synchronisation, there is no barrier --
+// consecutive threads touch consecutive 16 bytes (no bank conflicts), pad rows are simply not copied, and two iterations
+// (2 x 8 slots x 16 B x 512 threads = 128 KB per SM) are always in flight behind the one being computed.
+constexpr int kApplyStages = 3;
+constexpr int kApplyRowsPerCta = 2048;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 template <int C, int UP, bool DUAL>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b, const float* __restrict__ dpooled,
@@ -493,12 +505,38 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16*
                     __nv_bfloat16* __restrict__ draw_a, const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ ss_b,
                     const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ draw_b, RowGeom geo, long long rows_pad) {
   constexpr int CH = C / 8, RL = 256 / CH;
-  constexpr int kU = ((DUAL ? 2 : 1) + UP) >= 3 ? 2 : 4;
+  constexpr int NS = (DUAL ? 2 : 1) + UP;          // input streams
+  constexpr int kU = NS >= 3 ? 2 : 4;
+  constexpr int SLOTS = kU * NS;
+  extern __shared__ uint4 ring[];                  // [kApplyStages][SLOTS][256]
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
-  const long long r0 = (long long)blockIdx.x * kRowsPerCta;
-  const long long r1 = min(rows_pad, r0 + kRowsPerCta);
+  const long long r0 = (long long)blockIdx.x * kApplyRowsPerCta;
+  const long long r1 = min(rows_pad, r0 + kApplyRowsPerCta);
   const float inv_pp = 1.0f / (float)(geo.P * geo.P);
-  for (long long r = r0 + rl; r < r1; r += kU * RL) {
+  // copies of iteration i (rows r0 + rl + i*kU*RL + u*RL) into stage i % kApplyStages; always commits one group
+  auto issue = [&](int i) {
+    const long long r = r0 + rl + (long long)i * (kU * RL);
+    uint4* stg = ring + (size_t)(i % kApplyStages) * SLOTS * 256 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr < r1 && row_is_valid((uint32_t)rr, geo)) {
+        const long long idx = rr * CH + ch;
+        cp_async16(stg + (u * NS + 0) * 256, reinterpret_cast<const uint4*>(raw_a) + idx);
+        if (DUAL) cp_async16(stg + (u * NS + 1) * 256, reinterpret_cast<const uint4*>(raw_b) + idx);
+        if (UP >= 1) cp_async16(stg + (u * NS + (DUAL ? 2 : 1)) * 256, reinterpret_cast<const uint4*>(up_a) + idx);
+        if (UP == 2) cp_async16(stg + (u * NS + (DUAL ? 3 : 2)) * 256, reinterpret_cast<const uint4*>(up_b) + idx);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int i = 0; i < kApplyStages - 1; ++i) issue(i);
+  int it = 0;
+  for (long long r = r0 + rl; r < r1; r += kU * RL, ++it) {
+    issue(it + kApplyStages - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kApplyStages - 1) : "memory");
+    const uint4* stg = ring + (size_t)(it % kApplyStages) * SLOTS * 256 + threadIdx.x;
     uint4 va[kU], vb[kU], ua[kU], ub[kU];
     bool ok[kU];
 #pragma unroll
@@ -508,13 +546,11 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16*
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const long long rr = r + u * RL;
       if (ok[u]) {
-        const long long idx = rr * CH + ch;
-        va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
-        if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
-        if (UP >= 1) ua[u] = ldg_stream(reinterpret_cast<const uint4*>(up_a) + idx);
-        if (UP == 2) ub[u] = ldg_stream(reinterpret_cast<const uint4*>(up_b) + idx);
+        va[u] = stg[(u * NS + 0) * 256];
+        if (DUAL) vb[u] = stg[(u * NS + 1) * 256];
+        if (UP >= 1) ua[u] = stg[(u * NS + (DUAL ? 2 : 1)) * 256];
+        if (UP == 2) ub[u] = stg[(u * NS + (DUAL ? 3 : 2)) * 256];
       }
     }
 #pragma unroll
@@ -771,6 +807,30 @@ int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P
     else { BN_DISPATCH_C(C, (KERN<CC, 2, false><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                                  \
   } while (0)
 
+// bn_bwd_apply_kernel with its thread-private cp.async ring as dynamic shared memory (48-96 KB: opt-in attribute)
+template <int C, int UP, bool DUAL, typename... Args>
+static int launch_bwd_apply(int grid, cudaStream_t st, Args... args) {
+  constexpr int NS = (DUAL ? 2 : 1) + UP, kU = NS >= 3 ? 2 : 4;
+  constexpr int smem = kApplyStages * kU * NS * 256 * 16;
+  auto kern = bn_bwd_apply_kernel<C, UP, DUAL>;
+  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, 256, smem, st>>>(args...);
+  return MIVIT_OK;
+}
+#define BN_BWD_APPLY_LAUNCH(GRID, ...)                                                                                   \
+  do {                                                                                                                   \
+    const int up_mode = dpooled != nullptr ? 0 : (up_b != nullptr ? 2 : 1);                                             \
+    const bool dual = raw_b != nullptr;                                                                                  \
+    int rc_ = MIVIT_OK;                                                                                                  \
+    if (up_mode == 0 && dual) { BN_DISPATCH_C(C, (rc_ = launch_bwd_apply<CC, 0, true>(GRID, st, __VA_ARGS__))); }        \
+    else if (up_mode == 0) { BN_DISPATCH_C(C, (rc_ = launch_bwd_apply<CC, 0, false>(GRID, st, __VA_ARGS__))); }          \
+    else if (up_mode == 1 && dual) { BN_DISPATCH_C(C, (rc_ = launch_bwd_apply<CC, 1, true>(GRID, st, __VA_ARGS__))); }   \
+    else if (up_mode == 1) { BN_DISPATCH_C(C, (rc_ = launch_bwd_apply<CC, 1, false>(GRID, st, __VA_ARGS__))); }          \
+    else if (dual) { BN_DISPATCH_C(C, (rc_ = launch_bwd_apply<CC, 2, true>(GRID, st, __VA_ARGS__))); }                   \
+    else { BN_DISPATCH_C(C, (rc_ = launch_bwd_apply<CC, 2, false>(GRID, st, __VA_ARGS__))); }                            \
+    if (rc_) return rc_;                                                                                                 \
+  } while (0)
+
 // ss_* = forward (scale | shift) of the BatchNorm(s): the ReLU mask is recomputed from raw, the activation is not read.
 int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const float* dpooled, const __nv_bfloat16* raw_a,
                 const float* ss_a, const float* mi_a, const float* gamma_a, __nv_bfloat16* draw_a, float* dgamma_a, float* dbeta_a,
@@ -817,11 +877,10 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
                                                              presummed);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
-  const int ablocks = mivit_ceil_div(rows_pad, kRowsPerCta);
+  const int ablocks = mivit_ceil_div(rows_pad, kApplyRowsPerCta);
   {
     MivitProfScope prof("bn_bwd_apply", (double)rows_pad * C * 2 * (2 * (raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
-    BN_BWD_LAUNCH(bn_bwd_apply_kernel, ablocks, up_a, up_b, dpooled, raw_a, ss_a, coef_a, draw_a, raw_b, ss_b, coef_b, draw_b, geo,
-                  rows_pad);
+    BN_BWD_APPLY_LAUNCH(ablocks, up_a, up_b, dpooled, raw_a, ss_a, coef_a, draw_a, raw_b, ss_b, coef_b, draw_b, geo, rows_pad);
     mivit_count_launch();
     MIVIT_LAUNCH_CHECK();
   }
