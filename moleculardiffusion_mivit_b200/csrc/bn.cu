@@ -345,6 +345,13 @@ __device__ __forceinline__ void upstream8(const uint4& ua, const uint4& ub, cons
   }
 }
 
+// Thread-private cp.async ring of the two backward passes (see bn_bwd_apply_kernel)
+constexpr int kApplyStages = 3;
+constexpr int kApplyRowsPerCta = 2048;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
 template <int C, int UP, bool DUAL>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b, const float* __restrict__ dpooled,
@@ -353,10 +360,31 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
                      float* __restrict__ sums, RowGeom geo, int rows_per_block) {
   constexpr int CH = C / 8;
   constexpr int RL = 256 / CH;  // row lanes
-  constexpr int kU = ((DUAL ? 2 : 1) + UP) >= 3 ? 2 : 4;   // 6-8 sixteen-byte loads in flight per thread
+  constexpr int NS = (DUAL ? 2 : 1) + UP;
+  constexpr int kU = NS >= 3 ? 2 : 4;
+  constexpr int SLOTS = kU * NS;
+  extern __shared__ uint4 ring[];   // [kApplyStages][SLOTS][256], thread-private slots
   const int ch = threadIdx.x % CH, rl = threadIdx.x / CH;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min((long long)geo.rows, r0 + rows_per_block);
+  auto issue = [&](int i) {
+    const long long r = r0 + rl + (long long)i * (kU * RL);
+    uint4* stg = ring + (size_t)(i % kApplyStages) * SLOTS * 256 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long rr = r + u * RL;
+      if (rr < r1 && row_is_valid((uint32_t)rr, geo)) {
+        const long long idx = rr * CH + ch;
+        cp_async16(stg + (u * NS + 0) * 256, reinterpret_cast<const uint4*>(raw_a) + idx);
+        if (DUAL) cp_async16(stg + (u * NS + 1) * 256, reinterpret_cast<const uint4*>(raw_b) + idx);
+        if (UP >= 1) cp_async16(stg + (u * NS + (DUAL ? 2 : 1)) * 256, reinterpret_cast<const uint4*>(up_a) + idx);
+        if (UP == 2) cp_async16(stg + (u * NS + (DUAL ? 3 : 2)) * 256, reinterpret_cast<const uint4*>(up_b) + idx);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int i = 0; i < kApplyStages - 1; ++i) issue(i);
   float sa[8], ha[8], sb[8], hb[8];
   load8f(ss_a + ch * 8, sa);
   load8f(ss_a + C + ch * 8, ha);
@@ -367,7 +395,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
   // sum g*xhat = invstd * (sum g*x - mean * sum g): accumulate sum g*x and fix up once at the end
   float s0[8] = {}, s1[8] = {}, s2[8] = {};
   PooledCache pcache;
-  for (long long r = r0 + rl; r < r1; r += kU * RL) {
+  int it = 0;
+  for (long long r = r0 + rl; r < r1; r += kU * RL, ++it) {
+    issue(it + kApplyStages - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kApplyStages - 1) : "memory");
+    const uint4* stg = ring + (size_t)(it % kApplyStages) * SLOTS * 256 + threadIdx.x;
     uint4 va[kU], vb[kU], ua[kU], ub[kU];
     bool ok[kU];
 #pragma unroll
@@ -377,13 +409,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const long long rr = r + u * RL;
       if (ok[u]) {
-        const long long idx = rr * CH + ch;
-        va[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_a) + idx);
-        if (DUAL) vb[u] = ldg_stream(reinterpret_cast<const uint4*>(raw_b) + idx);
-        if (UP >= 1) ua[u] = ldg_stream(reinterpret_cast<const uint4*>(up_a) + idx);
-        if (UP == 2) ub[u] = ldg_stream(reinterpret_cast<const uint4*>(up_b) + idx);
+        va[u] = stg[(u * NS + 0) * 256];
+        if (DUAL) vb[u] = stg[(u * NS + 1) * 256];
+        if (UP >= 1) ua[u] = stg[(u * NS + (DUAL ? 2 : 1)) * 256];
+        if (UP == 2) ub[u] = stg[(u * NS + (DUAL ? 3 : 2)) * 256];
       }
     }
 #pragma unroll
@@ -493,11 +523,6 @@ __device__ __forceinline__ void ldg4f(const float* __restrict__ p, float (&v)[4]
 // thread only ever reads what it copied itself -- cp.async.wait_group is the only synchronisation, there is no barrier --
 // consecutive threads touch consecutive 16 bytes (no bank conflicts), pad rows are simply not copied, and two iterations
 // (2 x 8 slots x 16 B x 512 threads = 128 KB per SM) are always in flight behind the one being computed.
-constexpr int kApplyStages = 3;
-constexpr int kApplyRowsPerCta = 2048;
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 template <int C, int UP, bool DUAL>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ up_a, const __nv_bfloat16* __restrict__ up_b, const float* __restrict__ dpooled,
@@ -795,16 +820,28 @@ int pool_rows(const __nv_bfloat16* act, float* pooled, long long n_frames, int P
   return MIVIT_OK;
 }
 
-#define BN_BWD_LAUNCH(KERN, GRID, ...)                                                                                   \
+
+template <int C, int UP, bool DUAL, typename... Args>
+static int launch_bwd_reduce(int grid, cudaStream_t st, Args... args) {
+  constexpr int NS = (DUAL ? 2 : 1) + UP, kU = NS >= 3 ? 2 : 4;
+  constexpr int smem = kApplyStages * kU * NS * 256 * 16;
+  auto kern = bn_bwd_reduce_kernel<C, UP, DUAL>;
+  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, 256, smem, st>>>(args...);
+  return MIVIT_OK;
+}
+#define BN_BWD_REDUCE_LAUNCH(GRID, ...)                                                                                  \
   do {                                                                                                                   \
     const int up_mode = dpooled != nullptr ? 0 : (up_b != nullptr ? 2 : 1);                                             \
     const bool dual = raw_b != nullptr;                                                                                  \
-    if (up_mode == 0 && dual) { BN_DISPATCH_C(C, (KERN<CC, 0, true><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }              \
-    else if (up_mode == 0) { BN_DISPATCH_C(C, (KERN<CC, 0, false><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                \
-    else if (up_mode == 1 && dual) { BN_DISPATCH_C(C, (KERN<CC, 1, true><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }         \
-    else if (up_mode == 1) { BN_DISPATCH_C(C, (KERN<CC, 1, false><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                \
-    else if (dual) { BN_DISPATCH_C(C, (KERN<CC, 2, true><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                         \
-    else { BN_DISPATCH_C(C, (KERN<CC, 2, false><<<GRID, 256, 0, st>>>(__VA_ARGS__))); }                                  \
+    int rc_ = MIVIT_OK;                                                                                                  \
+    if (up_mode == 0 && dual) { BN_DISPATCH_C(C, (rc_ = launch_bwd_reduce<CC, 0, true>(GRID, st, __VA_ARGS__))); }       \
+    else if (up_mode == 0) { BN_DISPATCH_C(C, (rc_ = launch_bwd_reduce<CC, 0, false>(GRID, st, __VA_ARGS__))); }         \
+    else if (up_mode == 1 && dual) { BN_DISPATCH_C(C, (rc_ = launch_bwd_reduce<CC, 1, true>(GRID, st, __VA_ARGS__))); }  \
+    else if (up_mode == 1) { BN_DISPATCH_C(C, (rc_ = launch_bwd_reduce<CC, 1, false>(GRID, st, __VA_ARGS__))); }         \
+    else if (dual) { BN_DISPATCH_C(C, (rc_ = launch_bwd_reduce<CC, 2, true>(GRID, st, __VA_ARGS__))); }                  \
+    else { BN_DISPATCH_C(C, (rc_ = launch_bwd_reduce<CC, 2, false>(GRID, st, __VA_ARGS__))); }                           \
+    if (rc_) return rc_;                                                                                                 \
   } while (0)
 
 // bn_bwd_apply_kernel with its thread-private cp.async ring as dynamic shared memory (48-96 KB: opt-in attribute)
@@ -840,7 +877,7 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
   MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
   MIVIT_CHECK_ARG(!presummed || (raw_b == nullptr && dpooled == nullptr), "pre-summed BatchNorm backward is single-input only");
   if (!presummed) MIVIT_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), st));
-  const int rpb = 1024;
+  const int rpb = kApplyRowsPerCta;
   const int blocks = mivit_ceil_div(rows, rpb);
   const RowGeom geo = make_geom(rows, P);
   if (presummed) {
@@ -857,7 +894,7 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
     MIVIT_LAUNCH_CHECK();
   } else {
     MivitProfScope prof("bn_bwd_reduce", (double)rows * C * 2 * ((raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
-    BN_BWD_LAUNCH(bn_bwd_reduce_kernel, blocks, up_a, up_b, dpooled, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, geo, rpb);
+    BN_BWD_REDUCE_LAUNCH(blocks, up_a, up_b, dpooled, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, geo, rpb);
     mivit_count_launch();
     MIVIT_LAUNCH_CHECK();
   }
