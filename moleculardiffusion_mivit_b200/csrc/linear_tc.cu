@@ -113,6 +113,20 @@ linear_tc_kernel(const __grid_constant__ LinBatch batch, int M, int K, int N, in
   }
   const int acc_cols = pow2_cols(N);            // two accumulators, acc_cols columns apart
   if (warp == 0) tmem_alloc_n(tmem_slot, 2 * acc_cols);
+  // The first tile's cp.async copies go out BEFORE the weights are fetched and the CTA synchronises: at B = 1024 every CTA
+  // has exactly one tile, so the kernel is one latency chain and the two global round trips (weights, tile) used to be serial.
+  // (Both slabs are free at start: no barrier is needed for this copy; the producer loop below only waits for it.)
+  if (warp >= 5 && (int)blockIdx.x < n_tiles) {
+    const int pt = (warp - 5) * 32 + lane;
+    const long long m0 = (long long)blockIdx.x * kRows;
+    const int rows_here = min(kRows, M - (int)m0);
+    const uint4* src = reinterpret_cast<const uint4*>(A + m0 * K);
+    for (int i = pt; i < rows_here * kch; i += 96) {
+      const int r = i / kch, c = i - r * kch;
+      cp16(slab0 + ((size_t)c * kRows + r) * 16, src + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   if (!BMN) {  // W[N][K] -> [K/4][N][16B]
     for (int i = tid; i < kch * N; i += 256) {
       const int n = i / kch, c = i - n * kch;
@@ -136,14 +150,16 @@ linear_tc_kernel(const __grid_constant__ LinBatch batch, int M, int K, int N, in
     int k = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
       const int buf = k & 1;
-      umma::mbar_wait(empty + buf, ((k >> 1) & 1) ^ 1);
-      uint8_t* slab = buf ? slab1 : slab0;
-      const long long m0 = (long long)tile * kRows;
-      const int rows_here = min(kRows, M - (int)m0);
-      const uint4* src = reinterpret_cast<const uint4*>(A + m0 * K);
-      for (int i = pt; i < rows_here * kch; i += 96) {
-        const int r = i / kch, c = i - r * kch;
-        cp16(slab + ((size_t)c * kRows + r) * 16, src + i);
+      if (k > 0) {   // tile 0 was issued in the prologue
+        umma::mbar_wait(empty + buf, ((k >> 1) & 1) ^ 1);
+        uint8_t* slab = buf ? slab1 : slab0;
+        const long long m0 = (long long)tile * kRows;
+        const int rows_here = min(kRows, M - (int)m0);
+        const uint4* src = reinterpret_cast<const uint4*>(A + m0 * K);
+        for (int i = pt; i < rows_here * kch; i += 96) {
+          const int r = i / kch, c = i - r * kch;
+          cp16(slab + ((size_t)c * kRows + r) * 16, src + i);
+        }
       }
       cp_wait_all();
       umma::fence_proxy_async();
