@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import helpersGeneration as _gen
+from .models import _CudaViT
 from .training import MiViTTrainer
 
 __all__ = ["save_results", "single_state", "ExperimentLoop"]
@@ -42,11 +43,36 @@ def single_state(N, T, Ds, seed=None, seq_offset=0):
     return traj, D
 
 
+class _TorchTrainer:
+    """Same interface as MiViTTrainer for models OUTSIDE this package's scope -- the reference experiments train a CNN baseline
+    (helpers/models.py:686 MultiImageResNet, imported from the reference) beside every ViT, with the same criterion, optimiser
+    and schedule (trainSettingsPSFNoise.py:119-120).  Such a model is an ordinary nn.Module and runs on stock PyTorch CUDA."""
+
+    def __init__(self, model, lr=1e-4, step_size=5, gamma=0.9):
+        self.model = model.cuda()
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr)
+        self.sched = torch.optim.lr_scheduler.StepLR(self.opt, step_size=step_size, gamma=gamma)
+        self.criterion = torch.nn.MSELoss()
+
+    def train_step(self, x, target, features=None):
+        self.model.train()
+        self.opt.zero_grad()
+        out = self.model(x) if features is None else self.model(x, features)
+        loss = self.criterion(out, target)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def scheduler_step(self):
+        self.sched.step()
+
+
 class ExperimentLoop:
     def __init__(self, models, render_fn, make_prediction, val_sets, *, T, N=64, traj_div_factor=100, D_max_normalization=10,
                  TrainingDs_list=((1, 1), (3, 1), (5, 1), (7, 1), (9, 1), (10.2, 1)), adaptive_batch_size=20, shuffle=True,
                  lr=1e-4, step_size=5, gamma=0.9, seed=0, results_prefix="training_results_PSFNoise"):
-        """models: {name: GeneralTransformer (CUDA)}; render_fn(trajs numpy (n,T,2)) -> images (numpy or CUDA tensor) with the
+        """models: {name: GeneralTransformer / ModularTransformer of this package (fused CUDA trainer) or any other nn.Module,
+        e.g. the reference's MultiImageResNet baseline (stock PyTorch trainer)}; render_fn(trajs numpy (n,T,2)) -> images (numpy or CUDA tensor) with the
         sequence axis first; make_prediction(model, name, images) -> predictions (the settings files' function, e.g.
         images[:, psf, noise] for PSFNoise); val_sets: [(images, D_value), ...] rendered once (load_validation_data)."""
         self.models, self.render_fn, self.make_prediction = models, render_fn, make_prediction
@@ -55,7 +81,8 @@ class ExperimentLoop:
         self.groups = [list(g) for g in TrainingDs_list]
         self.adaptive, self.shuffle, self.seed = int(adaptive_batch_size), bool(shuffle), int(seed)
         self.batch_size = 1 if self.adaptive != -1 else 16
-        self.trainers = {n: MiViTTrainer(m, lr=lr, step_size=step_size, gamma=gamma) for n, m in models.items()}
+        self.trainers = {n: (MiViTTrainer(m, lr=lr, step_size=step_size, gamma=gamma) if isinstance(m, _CudaViT)
+                             else _TorchTrainer(m, lr=lr, step_size=step_size, gamma=gamma)) for n, m in models.items()}
         self.validation_losses = {n: dict({f"val_{d}": [] for _, d in self.val_sets}, val_avg=[]) for n in models}
         self.all_gen_labels = np.array([])
         self.prefix = results_prefix

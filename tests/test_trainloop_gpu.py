@@ -58,3 +58,36 @@ def test_two_cycles_psfnoise_layout(golden_dir, tmp_path):
     assert {k for k in ref_keys if not k.startswith("feature_projector")} - {"transformer.encoder_layers.2.self_attn.q_proj.weight"} \
         >= {k for k in mine if "encoder_layers.2" not in k} - set()                                # same naming scheme
     assert "embedding.proj.weight" in mine and "mlp_head.mlp.3.bias" in mine and "reg_token" in mine
+
+
+def test_loop_trains_a_foreign_cnn_baseline_beside_the_vit(golden_dir, tmp_path):
+    """The reference experiments train a CNN baseline (MultiImageResNet, out of this package's scope) beside every ViT: any
+    nn.Module that is not one of this package's transformers goes through the stock-PyTorch trainer of the same loop."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M, experiments as X, trainloop as TL
+    torch.manual_seed(0)
+
+    class TinyBaseline(nn.Module):      # stand-in with the baseline's call convention: [B, frames, P, P] -> [B, 1]
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(30, 4, 3, padding=1)
+            self.fc = nn.Linear(4, 1)
+
+        def forward(self, x):
+            return self.fc(F.relu(self.conv(x)).mean(dim=(2, 3)))
+
+    models = {"tr_0_0": M.GeneralTransformer(M.LinearProjectionEmbedding, {"patch_size": 9, "embed_dim": 32}, 32, 2, 64, 2, M.MLPHead,
+                                             F.relu, 0.0, False, True, True).cuda(),
+              "res_0_0": TinyBaseline()}
+    render = lambda t: X.trajs_to_vid_psf_noise(t, 10, center=True, image_props=PROPS, PSF_Settings=PSF, Noise_Settings=NOISE, seed=3)
+    inp = np.load(os.path.join(golden_dir, "render_inputs.npz"))["traj30"]
+    val = [(render(inp[:3].copy()), 1.0)]
+    loop = TL.ExperimentLoop(models, render, make_prediction, val, T=300, N=4, TrainingDs_list=[[1, 1]], adaptive_batch_size=-1,
+                             seed=1, results_prefix=str(tmp_path / "res"))
+    assert isinstance(loop.trainers["res_0_0"], TL._TorchTrainer) and not isinstance(loop.trainers["tr_0_0"], TL._TorchTrainer)
+    w0 = models["res_0_0"].fc.weight.detach().clone()
+    losses = loop.run(1, save=False)
+    assert set(losses) == {"tr_0_0", "res_0_0"} and len(losses["res_0_0"]["val_avg"]) == 1
+    assert not torch.equal(w0, models["res_0_0"].fc.weight.detach())
