@@ -247,7 +247,8 @@ def run_b200(args, rank, world, local_rank):
     torch.manual_seed(0)
     model = M.GeneralTransformer(M.DeepResNetEmbedding, {"patch_size": P, "embed_dim": EMBED}, EMBED, HEADS, HIDDEN, LAYERS,
                                  M.MLPHead, F.relu, 0.0, False, True, True).cuda().train()
-    trainer = MiViTTrainer(model, lr=1e-4, cuda_graph=not args.no_cuda_graph, sync_bn=args.sync_bn)
+    trainer = MiViTTrainer(model, lr=1e-4, cuda_graph=not args.no_cuda_graph, sync_bn=args.sync_bn,
+                           overlap_allreduce=not args.no_overlap)
     prm = derive_render_params(IMAGE_PROPS, NPOS, True)
     den = (BG_MEAN + PART_MEAN) - (BG_MEAN - BG_SIGMA)
     prm.normalize, prm.norm_sub, prm.norm_div = 1, float(BG_MEAN - BG_SIGMA), float(den)
@@ -382,7 +383,10 @@ def run_b200(args, rank, world, local_rank):
                        "batchnorm": "synchronised over the ranks (12 small all-reduces per step)" if trainer.sync_bn
                                     else "per-rank batch statistics (stock DDP semantics)",
                        "launch": "CUDA-graph replay of forward+loss+backward, eager AdamW"
-                                 if (trainer.cuda_graph and not trainer.sync_bn) else "kernel by kernel"},
+                                 if (trainer.cuda_graph and not trainer.sync_bn) else "kernel by kernel",
+                       "allreduce": None if world == 1 else
+                                    ("two buckets, the non-embedding one overlapped with the image-embedding backward"
+                                     if (trainer.overlap_allreduce and not trainer.sync_bn) else "one all-reduce after the backward")},
             "model_tflops": value * FLOPS_PER_SEQ_TRAIN / 1e12 / world, "loss": float(last_loss.item()),
             "roofline": roof, "roofline_render": roof_render, "kernels": kernels, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": int(B * T * 2 * 8 + B * 4),
@@ -427,6 +431,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seqs", type=int, default=32, help="sequences per CPU reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one gradient all-reduce after the whole backward")
     ap.add_argument("--sync-bn", action="store_true", help="N > 1: synchronised BatchNorm (parity mode) instead of per-rank statistics")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the training step kernel by kernel instead of replaying it")
     args = ap.parse_args()

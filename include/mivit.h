@@ -227,6 +227,15 @@ int mivit_vit_backward(const mivit_vit_config* cfg, int32_t B, const float* x, c
                        const float* dpred, const float* params, float* grads, void* workspace,
                        void* stream);
 
+/* The same backward in two parts, for a data-parallel trainer that overlaps the gradient all-reduce with the backward
+ * (SURVEY.md 8e): part 1 = head, encoder layers, tokens, feature paths and the embedding LayerNorm -- afterwards every gradient
+ * at flat offset >= mivit_vit_embedding_param_count(cfg) is final and can be reduced while part 2 = the image embedding
+ * (DeepResNet: 99 % of the FLOPs, ~45 % of the step) runs; part 0 = both (= mivit_vit_backward).  Part 1 zeroes `grads`. */
+int mivit_vit_backward_part(const mivit_vit_config* cfg, int32_t B, const float* x, const float* features,
+                            const float* dpred, const float* params, float* grads, void* workspace,
+                            int32_t part, void* stream);
+int64_t mivit_vit_embedding_param_count(const mivit_vit_config* cfg);   /* floats of the image-embedding block; -1: bad config */
+
 /* nn.MSELoss() (mean) and its gradient w.r.t. pred (Experiments/PSFNoise/trainSettingsPSFNoise.py:31). */
 int mivit_mse_loss(const float* pred, const float* target, int32_t n, float* loss, float* dpred,
                    void* stream);

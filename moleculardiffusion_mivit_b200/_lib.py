@@ -65,6 +65,8 @@ def _declare(lib):
         "mivit_vit_workspace_bytes": (i64, [vp, i32]),
         "mivit_vit_forward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
         "mivit_vit_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "mivit_vit_backward_part": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "mivit_vit_embedding_param_count": (i64, [vp]),
         "mivit_mse_loss": (i32, [vp, vp, i32, vp, vp, vp]),
         "mivit_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]),
         "mivit_vit_train_step": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,

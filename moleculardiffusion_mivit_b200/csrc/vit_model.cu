@@ -490,8 +490,10 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
   return MIVIT_OK;
 }
 
-extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
-                                  const float* dpred, const float* params, float* grads, void* workspace, void* stream) {
+// part: 0 = whole backward; 1 = everything up to (not including) the image embedding -- head, encoder layers, tokens, feature
+// paths, embedding LayerNorm: all gradients behind mivit_vit_embedding_param_count() are final afterwards; 2 = image embedding only.
+static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* x, const float* features, const float* dpred,
+                             const float* params, float* grads, void* workspace, int part, void* stream) {
   ParamLayout L;
   CK(build_layout(c, L));
   MIVIT_CHECK_ARG(B >= 1 && (x || !L.has_img) && dpred && params && grads && workspace, "bad arguments");
@@ -504,6 +506,9 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
   const float* p = params;
   float* g = grads;
   g_linear_tc = c->conv_impl == 1;
+  // gradient of the image embedding output [NF, Ei]: the embedding LayerNorm's input gradient, or its image slice / share
+  const float* d_img = (c->modular && c->mod_mode == 2 && c->mod_fusion != 0) ? w.demb_img : w.demb;
+  auto tokens_part = [&]() -> int {
   MIVIT_CUDA_CHECK(cudaMemsetAsync(g, 0, (size_t)L.off * sizeof(float), st));
   // head
   CK(linear_bwd(w.hh, p + L.h3_w, dpred, g + L.h3_w, g + L.h3_b, w.dhh, B, 1, hhid, 0, st));
@@ -566,7 +571,6 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
   }
   // embedding LayerNorm (dy is read from the token slots)
   CK(layernorm_bwd(dx, w.emb, w.m0, w.r0, p + L.norm_g, w.demb, g + L.norm_g, g + L.norm_b, NF, E, F, S, c->use_reg ? 1 : 0, st));
-  const float* d_img = w.demb;   // gradient of the image embedding output [NF, Ei]
   if (c->modular && c->mod_mode != 0) {   // backward of the ModularTransformer fusion (forward: helpers/models.py:528-570)
     const int fd = c->feat_dim;
     const float* d_femb = w.demb;         // 'features_only' and 'add': the fused gradient itself
@@ -591,7 +595,10 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
       }
     }
   }
-  if (!L.has_img) return MIVIT_OK;
+  return MIVIT_OK;
+  };
+  if (part != 2) CK(tokens_part());
+  if (part == 1 || !L.has_img) return MIVIT_OK;
   if (c->embedding != 2) {
     CK(linear_bwd(x, p + L.proj_w, d_img, g + L.proj_w, g + L.proj_b, nullptr, NF, Ei, P * P, 0, st));
     return MIVIT_OK;
@@ -666,6 +673,23 @@ extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const fl
                  g + L.bn0_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, 32, cnt, nullptr, 0, st));
   CK(conv0_wgrad(x, w.draw0.row0, g + L.conv0_w, rows, P, st));
   return MIVIT_OK;
+}
+
+extern "C" int mivit_vit_backward(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
+                                  const float* dpred, const float* params, float* grads, void* workspace, void* stream) {
+  return vit_backward_impl(c, B, x, features, dpred, params, grads, workspace, 0, stream);
+}
+extern "C" int mivit_vit_backward_part(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
+                                       const float* dpred, const float* params, float* grads, void* workspace, int32_t part,
+                                       void* stream) {
+  MIVIT_CHECK_ARG(part >= 0 && part <= 2, "part must be 0 (all), 1 (tokens) or 2 (image embedding)");
+  return vit_backward_impl(c, B, x, features, dpred, params, grads, workspace, part, stream);
+}
+extern "C" int64_t mivit_vit_embedding_param_count(const mivit_vit_config* c) {
+  ParamLayout L;
+  if (build_layout(c, L)) return -1;
+  // the image-embedding block is the head of the flat buffer; the feature embedding / fusion layer / norm.weight follow it
+  return (int64_t)(L.has_femb ? L.fe0_w : L.fu_w >= 0 ? L.fu_w : L.norm_g);
 }
 
 extern "C" int mivit_vit_train_step(const mivit_vit_config* c, int32_t B, const float* x, const float* features,

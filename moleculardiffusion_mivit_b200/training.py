@@ -16,7 +16,7 @@ __all__ = ["MiViTTrainer"]
 
 class MiViTTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step_size=5, gamma=0.9,
-                 process_group=None, distributed=None, cuda_graph=False, sync_bn=False):
+                 process_group=None, distributed=None, cuda_graph=False, sync_bn=False, overlap_allreduce=True):
         if not isinstance(model, _CudaViT):
             raise TypeError("MiViTTrainer drives a moleculardiffusion_mivit_b200.models.GeneralTransformer / ModularTransformer")
         self.model = model
@@ -47,6 +47,11 @@ class MiViTTrainer:
         self._hook = _lib.ALLREDUCE_FN(self._allreduce_hook) if self.sync_bn else None
         self._hook_ws = None
         self._hook_error = None
+        # overlap_allreduce (data-parallel): the backward is issued in two parts; the gradients of everything but the
+        # image embedding (head, encoder layers, tokens: 42 % of the 2 MB) are all-reduced on the collective's own stream while the
+        # image-embedding backward (~45 % of the step) runs, the embedding's bucket follows, AdamW waits for both.
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self._ne = None
 
     def _allreduce_hook(self, buf, n_floats, stream, user):
         """C callback (mivit_allreduce_fn): SUM all-reduce of n_floats fp32 at device address `buf`, which always lies inside
@@ -95,28 +100,74 @@ class MiViTTrainer:
         L = _lib.lib()
         if self.sync_bn and deep:
             return self._sync_bn_step(x, target, features, cfg, B, ws, pred, dpred)
-        if self.cuda_graph and self._replay(x, target, features, cfg, B, ws, pred, dpred, deep):
-            model._gen += 1
-            scale = allreduce_sum_(model._grad_flat[:model._n_params], self.group) if self.world > 1 else 1.0
-            _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
-                                          model._n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                          self.step_count, scale, _lib.current_stream()))
-            self.last_pred = pred
-            return self.loss
-        _lib.check(L.mivit_vit_train_step(
-            ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(target), _lib.ptr(model._flat),
-            _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
-            _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None, _lib.ptr(ws),
-            _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
-            self.weight_decay, self.step_count, int(self.world == 1), _lib.current_stream()))
+        overlap = self.overlap_allreduce and self.world > 1 and model._image_embedding() is not None
+        ent = self._graph_entry(x, target, features, cfg, B, ws, pred, dpred, deep, overlap) if self.cuda_graph else None
+        n, ne = model._n_params, self._n_embedding(cfg)
+        grad = model._grad_flat
+        if ent is not None:                       # replay the captured forward + loss + backward (one or two graphs)
+            graphs, gx, gt, gf, counts = ent
+            if gx is not None:
+                gx.copy_(x)
+            gt.copy_(target)
+            if gf is not None:
+                gf.copy_(features)
+            handles = []
+            for i, (g, cnt) in enumerate(zip(graphs, counts)):
+                g.replay()
+                L.mivit_add_launch_count(cnt)     # the graph's kernel nodes are launches of this library too
+                if overlap:                       # bucket 1 (everything but the image embedding) goes out while graph 2 runs
+                    part = grad[ne:n] if i == 0 else grad[:ne]
+                    handles.append(self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+        elif overlap:                             # kernel by kernel, same split
+            self._forward_loss_backward_part(1, cfg, B, x, features, target, ws, pred, dpred, deep)
+            handles = [self.dist.all_reduce(grad[ne:n], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)]
+            self._forward_loss_backward_part(2, cfg, B, x, features, target, ws, pred, dpred, deep)
+            handles.append(self.dist.all_reduce(grad[:ne], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            handles = []
+            _lib.check(L.mivit_vit_train_step(
+                ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(target), _lib.ptr(model._flat),
+                _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
+                _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None, _lib.ptr(ws),
+                _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, self.step_count, int(self.world == 1), _lib.current_stream()))
+            if self.world == 1:                   # AdamW ran inside the call
+                model._gen += 1
+                self.last_pred = pred
+                return self.loss
         model._gen += 1
-        if self.world > 1:
-            scale = allreduce_sum_(model._grad_flat[:model._n_params], self.group)
-            _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
-                                          model._n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                          self.step_count, scale, _lib.current_stream()))
+        scale = 1.0
+        if overlap:
+            for h in handles:
+                h.wait()                          # the current stream waits for the reductions; the host does not block
+            scale = 1.0 / self.world
+        elif self.world > 1:
+            scale = allreduce_sum_(grad[:n], self.group)
+        _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(grad), _lib.ptr(self.m), _lib.ptr(self.v), n, self.lr,
+                                      self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, scale,
+                                      _lib.current_stream()))
         self.last_pred = pred
         return self.loss
+
+    def _n_embedding(self, cfg):
+        """floats of the image-embedding block at the head of the flat parameter / gradient buffer"""
+        if self._ne is None:
+            self._ne = int(_lib.lib().mivit_vit_embedding_param_count(ctypes.byref(cfg)))
+        return self._ne
+
+    def _forward_loss_backward_part(self, part, cfg, B, x, features, target, ws, pred, dpred, deep):
+        """part 1: forward, MSE, backward of everything but the image embedding; part 2: backward of the image embedding;
+        part 0: forward, MSE and the whole backward."""
+        model = self.model
+        L = _lib.lib()
+        st = _lib.current_stream()
+        if part != 2:
+            _lib.check(L.mivit_vit_forward(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(model._flat),
+                                           _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None,
+                                           _lib.ptr(ws), _lib.ptr(pred), 1, st))
+            _lib.check(L.mivit_mse_loss(_lib.ptr(pred), _lib.ptr(target), B, _lib.ptr(self.loss), _lib.ptr(dpred), st))
+        _lib.check(L.mivit_vit_backward_part(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(dpred),
+                                             _lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(ws), part, st))
 
     def _sync_bn_step(self, x, target, features, cfg, B, ws, pred, dpred):
         """Training step with synchronised BatchNorm: the library calls back into `_allreduce_hook` 12 times per step (7 forward
@@ -144,39 +195,33 @@ class MiViTTrainer:
         self.last_pred = pred
         return self.loss
 
-    def _replay(self, x, target, features, cfg, B, ws, pred, dpred, deep):
-        """Replays the captured forward + loss + backward for this batch shape; returns False on the first call of a shape
-        (that step runs eagerly -- it also performs every lazy initialisation -- and the graph is captured afterwards)."""
+    def _graph_entry(self, x, target, features, cfg, B, ws, pred, dpred, deep, overlap):
+        """CUDA graphs of forward + loss + backward for this batch shape: one graph, or two when the gradient all-reduce is
+        overlapped (graph 1 ends where the non-embedding gradients are final, graph 2 is the image-embedding backward).
+        Returns None on the first call of a shape: that step runs kernel by kernel -- it also performs every lazy
+        initialisation -- and the graphs are captured on the second call."""
         model = self.model
-        key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), id(ws))
+        key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), id(ws),
+               bool(overlap))
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "pending"
-            return False
+            return None
         L = _lib.lib()
         if ent == "pending":
             gx, gt = (torch.empty_like(x) if x is not None else None), torch.empty_like(target)
             gf = torch.empty_like(features) if features is not None else None
-            n0 = L.mivit_launch_count()
-            g = torch.cuda.CUDAGraph()
+            graphs, counts = [], []
             cap = torch.cuda.Stream()
             cap.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.graph(g, stream=cap):
-                _lib.check(L.mivit_vit_train_step(
-                    ctypes.byref(cfg), B, _lib.ptr(gx), _lib.ptr(gf), _lib.ptr(gt), _lib.ptr(model._flat),
-                    _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
-                    _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None, _lib.ptr(ws),
-                    _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
-                    self.weight_decay, 1, 0, _lib.current_stream()))
-            n_cap = int(L.mivit_launch_count() - n0)
-            L.mivit_add_launch_count(-n_cap)          # capturing enqueued nothing: only replays count
-            ent = self._graphs[key] = (g, gx, gt, gf, n_cap, cfg)
-        g, gx, gt, gf, n_launches, _ = ent
-        if gx is not None:
-            gx.copy_(x)
-        gt.copy_(target)
-        if gf is not None:
-            gf.copy_(features)
-        g.replay()
-        L.mivit_add_launch_count(n_launches)      # the graph's kernel nodes are launches of this library too
-        return True
+            for part in ((1, 2) if overlap else (0,)):
+                n0 = L.mivit_launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap):
+                    self._forward_loss_backward_part(part, cfg, B, gx, gf, gt, ws, pred, dpred, deep)
+                n_cap = int(L.mivit_launch_count() - n0)
+                L.mivit_add_launch_count(-n_cap)          # capturing enqueued nothing: only replays count
+                graphs.append(g)
+                counts.append(n_cap)
+            ent = self._graphs[key] = (graphs, gx, gt, gf, counts)
+        return ent
