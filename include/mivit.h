@@ -88,6 +88,14 @@ int mivit_render_embed_linear(const double* traj, int64_t N, int32_t T, const mi
                               uint64_t seq_offset, const float* Wt, const float* bias, int32_t E, float* emb,
                               float* frames_out, int64_t frames_seq_stride, void* stream);
 
+/* Replaces helpers/helpersGeneration.py:422-540 trajectories_to_video_multiple_settings / trajectory_to_mult_settings (the
+ * Denoising experiments' generator): one intensity per frame, four float32 [N,F,P,P] outputs -- noise free, + clipped Gaussian
+ * background, + Poisson(x*pn)/pn, + Gaussian filter (sigma 0.5, 'nearest' borders) of the Poisson frame.  prm as for
+ * mivit_render_v1 (scale = trajectory_unit*1e-9/resolution, :464; flip_y honoured; normalize ignored). */
+int mivit_render_multi(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
+                       uint64_t seq_offset, float* out_no_noise, float* out_gauss, float* out_poisson,
+                       float* out_filter, void* stream);
+
 /* Replaces Experiments/PSFNoise/trainSettingsPSFNoise.py:196-309 trajs_to_vid_psf_noise.
  * psf_div[n_psf], noise_frac[n_noise] are HOST arrays (PSF_Settings, Noise_Settings);
  * part_mean_global is the module-level `part_mean` used for the background sigma (:302).

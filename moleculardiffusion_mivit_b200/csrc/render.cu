@@ -301,6 +301,87 @@ __global__ void __launch_bounds__(256) render_psfnoise_kernel(const double* __re
   }
 }
 
+// trajectories_to_video_multiple_settings / trajectory_to_mult_settings (helpers/helpersGeneration.py:422-540): one intensity
+// per FRAME shared by its sub-positions (:505,:512) and four outputs per frame -- noise free (:523), + clipped Gaussian
+// background (:524-525), + proper Poisson(x*pn)/pn (:527), + skimage.filters.gaussian(sigma = 0.5) of the Poisson frame (:530),
+// i.e. scipy's separable 5-tap filter with 'nearest' borders: axis 0 then axis 1, float64 accumulation, a float32 image after
+// each axis.  The Poisson frame and the axis-0 result live in the warp's shared memory.
+struct GaussTaps { double w[5]; };
+__global__ void __launch_bounds__(256) render_multi_kernel(const double* __restrict__ traj, long long n_frames_total, RenderDev d,
+                                                           GaussTaps taps, float* __restrict__ out_none, float* __restrict__ out_gauss,
+                                                           float* __restrict__ out_pois, float* __restrict__ out_filt) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int P = d.P, n = d.n, PP = d.P * d.P;
+  const int per_warp = warp_smem_floats(n, P) + 2 * PP;
+  float* mine = smem + (size_t)warp * per_warp;
+  WarpSmem w = carve(mine, n, P);
+  float* fr = mine + warp_smem_floats(n, P);   // [PP] Poisson frame
+  float* t0 = fr + PP;                          // [PP] after the axis-0 pass
+  const long long gf = (long long)blockIdx.x * warps + warp;
+  if (gf >= n_frames_total) return;
+  const long long s = gf / d.F;
+  const int f = (int)(gf - s * d.F);
+  const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
+
+  if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
+  float spot = 0.0f;
+  if (d.draw) {
+    float z = 0.0f, z1;
+    if (!d.mean_noise) {
+      const uint4 r = philox4x32_10((uint32_t)f, 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
+      box_muller(r.x, r.y, z, z1);
+    }
+    spot = __fdiv_rn(__fadd_rn(d.imean, __fmul_rn(d.istd, z)), (float)n);   // :505, :512
+  }
+  __syncwarp();
+  if (d.draw) {
+    for (int p = lane; p < n; p += 32) w.inten[p] = ((double)w.msq[p] * d.inv2s2_d > 745.0) ? __int_as_float(0x7fc00000) : spot;
+    __syncwarp();
+    axis_table(d, d.inv2s2, lane, w);
+    __syncwarp();
+  }
+  const size_t base = (size_t)gf * PP;
+  for (int pix = lane; pix < PP; pix += 32) {
+    const int a = pix / P, b = pix - a * P;
+    const float sig = d.draw ? pixel_signal(d, w, a, b) : 0.0f;
+    PixelStream st;
+    float zb = 0.0f, z1;
+    if (!d.mean_noise) {
+      st.item = (uint32_t)(f * PP + pix); st.seq = seq; st.sw = stream_word(MIVIT_STREAM_PIXEL, 0);
+      st.k0 = d.k0; st.k1 = d.k1; st.q = 0;
+      st.cur = philox4x32_10(st.item, 0u, seq, st.sw, d.k0, d.k1);
+      box_muller(st.cur.x, st.cur.y, zb, z1);
+    }
+    const float bg = fminf(fmaxf(__fadd_rn(d.bg_mean, __fmul_rn(d.bg_std, zb)), 0.0f), d.bg_hi);   // :524-525
+    const float g = __fadd_rn(sig, bg);
+    const float lam = __fmul_rn(g, d.poisson);
+    const float k = d.mean_noise ? lam : poisson_draw(lam, st);
+    const float val = __fdiv_rn(k, d.poisson);                                                       // :527
+    out_none[base + pix] = sig;
+    out_gauss[base + pix] = g;
+    out_pois[base + pix] = val;
+    fr[pix] = val;
+  }
+  __syncwarp();
+  for (int pix = lane; pix < PP; pix += 32) {   // axis 0 (rows), 'nearest' border
+    const int a = pix / P, b = pix - a * P;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = -2; i <= 2; ++i) acc += taps.w[i + 2] * (double)fr[min(max(a + i, 0), P - 1) * P + b];
+    t0[pix] = (float)acc;
+  }
+  __syncwarp();
+  for (int pix = lane; pix < PP; pix += 32) {   // axis 1 (columns)
+    const int a = pix / P, b = pix - a * P;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = -2; j <= 2; ++j) acc += taps.w[j + 2] * (double)t0[a * P + min(max(b + j, 0), P - 1)];
+    out_filt[base + pix] = (float)acc;
+  }
+}
+
 // One warp per sequence: D draw, steps, float64 prefix sum.
 struct DGroups { float mean[16], var[16]; };
 
@@ -455,6 +536,38 @@ extern "C" int mivit_render_embed_linear(const double* traj, int64_t N, int32_t 
   if (blocks > mivit_ceil_div(frames, warps)) blocks = mivit_ceil_div(frames, warps);
   MivitProfScope prof("render_embed_linear", (double)N * ((double)T * 16.0 + (double)d.F * E * 4.0), (cudaStream_t)stream);
   render_embed_linear_kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, Wt, bias, E, emb, frames_out);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_render_multi(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
+                                  uint64_t seq_offset, float* out_no_noise, float* out_gauss, float* out_poisson,
+                                  float* out_filter, void* stream) {
+  RenderDev d;
+  int rc = fill_dev(prm, T, seed, seq_offset, d);
+  if (rc) return rc;
+  MIVIT_CHECK_ARG(N >= 0, "negative N");
+  MIVIT_CHECK_ARG(prm->poisson > 0.0f, "the multiple-settings renderer needs poisson_noise > 0");
+  if (N == 0) return MIVIT_OK;
+  MIVIT_CHECK_ARG(traj && out_no_noise && out_gauss && out_poisson && out_filter, "NULL device pointer");
+  d.imean = prm->part_mean;   // one draw per FRAME, divided by n in the kernel (:505, :512)
+  d.istd = prm->part_std;
+  d.normalize = 0;
+  GaussTaps taps;             // scipy.ndimage.gaussian_filter(sigma = 0.5, truncate = 4.0): radius 2, normalised float64 weights
+  double sum = 0.0;
+  for (int k = -2; k <= 2; ++k) { taps.w[k + 2] = exp(-0.5 / (0.5 * 0.5) * (double)(k * k)); sum += taps.w[k + 2]; }
+  for (int k = 0; k < 5; ++k) taps.w[k] /= sum;
+  const size_t per_warp = (size_t)(warp_smem_floats(d.n, d.P) + 2 * d.P * d.P) * sizeof(float);
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+  MIVIT_CHECK_ARG(per_warp * warps <= 200 * 1024, "nPosPerFrame*output_size too large for shared memory (%zu bytes per frame)", per_warp);
+  const size_t smem = per_warp * warps;
+  if (smem > 48 * 1024)
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long frames = (long long)N * d.F;
+  render_multi_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, taps, out_no_noise,
+                                                                                                  out_gauss, out_poisson, out_filter);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

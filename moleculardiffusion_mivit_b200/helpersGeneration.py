@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "create_video_and_feature_pairs",
+__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "trajectories_to_video_multiple_settings", "create_video_and_feature_pairs",
            "average_trajectories_frames", "average_trajs_add_error", "normalize_images", "brownian_motion", "derive_render_params",
            "DEFAULT_IMAGE_PROPS", "render_device"]
 
@@ -43,13 +43,13 @@ def _draw_seed(seed):
 def derive_render_params(image_props, nPosPerFrame, center, variant="v1"):
     """Host-side scalar set-up of :225-247 (or trainSettingsPSFNoise.py:237-259) -> RenderParams."""
     d = dict(DEFAULT_IMAGE_PROPS)
-    if variant == "psfnoise":
+    if variant in ("psfnoise", "multi"):
         d["poisson_noise"] = 1
     d.update(image_props)
     res, unit = d["resolution"], d["trajectory_unit"]
     if unit == -1:
         scale = 1.0
-    elif variant == "psfnoise":
+    elif variant in ("psfnoise", "multi"):
         scale = unit * 1e-9 / res
     else:
         scale = unit / (res * 1e9)
@@ -172,6 +172,29 @@ def trajectories_to_embeddings(trajectories, nPosPerFrame, embedding, center=Fal
                                                     _lib.ptr(Wt), _lib.ptr(bd), E, _lib.ptr(emb), _lib.ptr(frames),
                                                     F * prm.P * prm.P, _lib.current_stream()))
     return (emb, frames) if return_frames else emb
+
+
+def trajectories_to_video_multiple_settings(trajectories, nPosPerFrame, center=False, image_props={}, *, seed=None, seq_offset=0,
+                                            _mean_noise=False):
+    """helpers/helpersGeneration.py:422-492 (+ trajectory_to_mult_settings :494-540).  (N,T,2) -> four float32 (N,F,P,P) arrays:
+    (no noise, + Gaussian background, + Poisson noise, Gaussian-filtered).  Like the reference it flips the caller's y IN PLACE
+    (:432) and raises after the flip when T is not a multiple of nPosPerFrame; `poisson_noise` defaults to 1 here (:455)."""
+    import torch
+    dev = _lib.require_cuda()
+    N, T, _ = trajectories.shape
+    trajectories[:, :, 1] *= -1
+    if T % nPosPerFrame != 0:
+        raise Exception("T is not divisble by posPerFrame")
+    prm = derive_render_params(image_props, nPosPerFrame, center, "multi")
+    prm.flip_y = 0                      # already applied to the caller's array above
+    prm.mean_noise = int(bool(_mean_noise))
+    t_dev, was_host = _to_device_f64(trajectories, dev)
+    F = T // nPosPerFrame
+    outs = [torch.empty((N, F, prm.P, prm.P), dtype=torch.float32, device=dev) for _ in range(4)]
+    _lib.check(_lib.lib().mivit_render_multi(_lib.ptr(t_dev), N, T, ctypes.byref(prm), _draw_seed(seed), int(seq_offset),
+                                             _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]),
+                                             _lib.current_stream()))
+    return tuple(o.cpu().numpy() for o in outs) if was_host else tuple(outs)
 
 
 def average_trajectories_frames(trajectories, nPosFrame):

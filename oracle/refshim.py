@@ -54,8 +54,17 @@ def install_shims():
         meas.block_reduce = _block_reduce
         filt = types.ModuleType("skimage.filters")
 
-        def _gaussian(*a, **k):
-            raise RuntimeError("skimage is not installed (shim)")
+        def _gaussian(image, sigma=1, *, mode="nearest", cval=0, preserve_range=False, truncate=4.0, channel_axis=None, **k):
+            """skimage.filters.gaussian (absent here, no version pinned by the reference) for a float image: it forwards to
+            scipy.ndimage.gaussian_filter with mode='nearest', truncate=4.0 and an output of the image's own float dtype."""
+            import numpy as np
+            from scipy import ndimage as ndi
+            img = np.asarray(image)
+            if img.dtype.kind != "f":
+                img = img.astype(np.float64)
+            out = np.empty_like(img)
+            ndi.gaussian_filter(img, sigma, output=out, mode=mode, cval=cval, truncate=truncate)
+            return out
 
         filt.gaussian = _gaussian
         ski.measure = meas

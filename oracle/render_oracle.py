@@ -47,15 +47,15 @@ DEFAULT_IMAGE_PROPS = {  # helpersGeneration.py:205-222
 def derive_params(image_props, variant="v1"):
     """Scalar set-up of trajectories_to_video (:225-247) / trajs_to_vid_psf_noise (:237-259)."""
     d = dict(DEFAULT_IMAGE_PROPS)
-    if variant == "psfnoise":
-        d["poisson_noise"] = 1  # trainSettingsPSFNoise.py:232
+    if variant in ("psfnoise", "multi"):
+        d["poisson_noise"] = 1  # trainSettingsPSFNoise.py:232, helpersGeneration.py:455
     d.update(image_props)
     res = d["resolution"]
     unit = d["trajectory_unit"]
     if unit == -1:
         scale = 1.0
-    elif variant == "psfnoise":
-        scale = unit * 1e-9 / res          # trainSettingsPSFNoise.py:241
+    elif variant in ("psfnoise", "multi"):
+        scale = unit * 1e-9 / res          # trainSettingsPSFNoise.py:241, helpersGeneration.py:464
     else:
         scale = unit / (res * 1e9)         # helpersGeneration.py:231
     U = int(d["upsampling_factor"])
@@ -228,6 +228,65 @@ def render_psfnoise(traj, n, center, image_props, psf_settings, noise_settings, 
                 lam = (v * pn).astype(F32)
                 out[s, i, j] = (poisson(lam) / pn).astype(F32)                # :305
     return out
+
+
+def gaussian_filter_nearest(frame, sigma=0.5, truncate=4.0):
+    """scipy.ndimage.gaussian_filter(frame, sigma, mode='nearest', truncate=truncate) on a float32 image, which is what
+    skimage.filters.gaussian(frame, sigma=0.5) runs (helpersGeneration.py:530): radius int(truncate*sigma + 0.5), normalised
+    weights exp(-k^2 / 2 sigma^2) in float64, axis 0 then axis 1, float64 accumulation, float32 result after EACH axis."""
+    r = int(truncate * float(sigma) + 0.5)
+    k = np.arange(-r, r + 1, dtype=np.float64)
+    w = np.exp(-0.5 / (float(sigma) * float(sigma)) * k * k)
+    w /= w.sum()
+    a = np.asarray(frame, dtype=F32)
+    for axis in (0, 1):
+        n = a.shape[axis]
+        acc = np.zeros(a.shape, dtype=np.float64)
+        for i, wk in zip(range(-r, r + 1), w):
+            idx = np.clip(np.arange(n) + i, 0, n - 1)
+            acc += wk * np.take(a, idx, axis=axis).astype(np.float64)
+        a = acc.astype(F32)
+    return a
+
+
+def render_multi(traj, n, center, image_props, noise=None, seq_offset=0, mode="separable", flip_y=True):
+    """trajectories_to_video_multiple_settings / trajectory_to_mult_settings (helpersGeneration.py:422-540): one intensity per
+    FRAME (:505) shared by its sub-positions (:512), four outputs per frame -- noise free (:523), + clipped Gaussian background
+    (:524-525), + proper Poisson(x*pn)/pn (:527), + Gaussian filter sigma 0.5 of the Poisson frame (:530).  Returns four float32
+    (N, F, P, P) arrays.  The reference flips the caller's y in place (:432); `flip_y` applies that sign here."""
+    traj = np.asarray(traj, dtype=np.float64)
+    N, T, _ = traj.shape
+    if T % n != 0:
+        raise Exception("T is not divisble by posPerFrame")
+    prm = derive_params(image_props, "multi")
+    P, U = prm["P"], prm["U"]
+    G = P * U
+    F = T // n
+    noise = noise if noise is not None else MeanNoise()
+    tr = traj.copy()
+    if flip_y:
+        tr[:, :, 1] *= -1
+    tr = tr * prm["scale"]
+    outs = [np.zeros((N, F, P, P), dtype=F32) for _ in range(4)]
+    draw = prm["part_mean"] > 0.0001 and prm["part_std"] > 0.0001
+    pn, bmean, bstd = F32(prm["poisson"]), F32(prm["bg_mean"]), F32(prm["bg_std"])
+    hi = F32(prm["bg_mean"] + 3 * prm["bg_std"])
+    for s in range(N):
+        seq = seq_offset + s
+        zI = noise.intensity_z(seq, F)
+        for f in range(F):
+            xs, ys = _frame_centres(tr[s], f, n, center, U)
+            if draw:
+                If = F32(prm["part_mean"]) + F32(prm["part_std"]) * zI[f]      # :505
+                intens = np.full(n, float(If) / n, dtype=np.float64)          # :512 (a float64 quotient in the reference)
+                outs[0][s, f] = _accumulate_frame(xs, ys, intens, [prm["sigma"]], G, U, mode)[0]
+        zb, poisson = noise.pixel(seq, F * P * P, variant=0)
+        bg = np.clip((bmean + bstd * zb.reshape(F, P, P)).astype(F32), F32(0), hi)
+        outs[1][s] = (outs[0][s] + bg).astype(F32)                             # :524
+        outs[2][s] = (poisson((outs[1][s] * pn).astype(F32)) / pn).astype(F32)  # :527
+        for f in range(F):
+            outs[3][s, f] = gaussian_filter_nearest(outs[2][s, f], 0.5)        # :530
+    return tuple(outs)
 
 
 def normalize_images(images, background_mean=None, background_sigma=None, theoretical_max=None, clip_image=False):

@@ -158,3 +158,33 @@ def test_against_live_reference(gold):
         ref = _quiet(gen.trajectories_to_video, t, 10, True, CLEAN)
     assert np.array_equal(ref, g["v1_p9_center"][2:4])
     assert np.array_equal(ro.render_v1(inp["traj30"][2:4], 10, True, CLEAN, mode="literal"), ref)
+
+
+# ---- trajectories_to_video_multiple_settings (helpersGeneration.py:422-540) -------------------------------
+MULTI_CASES = [("p9_center", slice(0, 3), 10, True, {}), ("p13_nocenter_n15", slice(3, 4), 15, False, {"output_size": 13})]
+
+
+@pytest.mark.parametrize("key,sl,n,center,over", MULTI_CASES)
+def test_multi_settings_oracle_matches_reference_golden(golden_dir, key, sl, n, center, over):
+    inp = np.load(os.path.join(golden_dir, "render_inputs.npz"))["traj30"]
+    g = np.load(os.path.join(golden_dir, "render_multi_golden.npz"))
+    props = dict(C3_PROPS, **over)
+    lit = ro.render_multi(inp[sl], n, center, props, mode="literal")
+    sep = ro.render_multi(inp[sl], n, center, props)
+    for name, a, b in zip(("none", "gauss", "poisson", "filter"), lit, sep):
+        ref = g["%s/%s" % (key, name)]
+        assert a.dtype == np.float32 and a.shape == ref.shape
+        assert np.array_equal(a, ref), name                       # literal restatement: bit exact (filter: scipy's algorithm)
+        assert relmax(b, ref) < 1e-6, name                        # separable closed form
+
+
+def test_multi_settings_noisy_moments_vs_reference(golden_dir):
+    """Philox streams instead of np.random: first / second moments of the four outputs against the reference's own noisy runs."""
+    inp = np.load(os.path.join(golden_dir, "render_inputs.npz"))["traj30"]
+    g = np.load(os.path.join(golden_dir, "render_multi_golden.npz"))
+    runs = [ro.render_multi(inp[:8], 10, True, C3_PROPS, noise=PhiloxNoise(500 + r)) for r in range(6)]
+    for i, name in enumerate(("none", "gauss", "poisson", "filter")):
+        v = np.stack([r[i] for r in runs]).astype(np.float64)
+        assert abs(v.mean() - float(g["noisy/%s_mean" % name])) < 0.02 * float(g["noisy/%s_mean" % name]), name
+        assert abs(v.std() - float(g["noisy/%s_std" % name])) < 0.03 * float(g["noisy/%s_std" % name]), name
+        assert abs(v.std(axis=0).mean() - float(g["noisy/%s_pixstd" % name])) < 0.08 * float(g["noisy/%s_pixstd" % name]), name

@@ -235,3 +235,38 @@ def test_fused_render_embed_rejects_deepresnet(gen, gold):
         gen.trajectories_to_embeddings(inp["traj30"][:1].copy(), 10, M.DeepResNetEmbedding(9, 64), True, C3_PROPS)
     with pytest.raises(Exception, match="T is not divisble by posPerFrame"):
         gen.trajectories_to_embeddings(inp["traj30"][:1].copy(), 7, M.LinearProjectionEmbedding(9, 64), True, C3_PROPS)
+
+
+# ---- trajectories_to_video_multiple_settings (helpersGeneration.py:422-540) -------------------------------
+@pytest.mark.parametrize("key,sl,n,center,over", [("p9_center", slice(0, 3), 10, True, {}),
+                                                   ("p13_nocenter_n15", slice(3, 4), 15, False, {"output_size": 13})])
+def test_multi_settings_noise_free_matches_reference_golden(golden_dir, gold, gen, key, sl, n, center, over):
+    inp, _, _ = gold
+    g = np.load(os.path.join(golden_dir, "render_multi_golden.npz"))
+    t = inp["traj30"][sl].copy()
+    outs = gen.trajectories_to_video_multiple_settings(t, n, center, dict(C3_PROPS, **over), _mean_noise=True)
+    assert np.array_equal(t[:, :, 1], -inp["traj30"][sl][:, :, 1])          # the caller's y is flipped in place (:432)
+    assert len(outs) == 4
+    for name, a in zip(("none", "gauss", "poisson", "filter"), outs):
+        ref = g["%s/%s" % (key, name)]
+        assert a.dtype == np.float32 and a.shape == ref.shape
+        assert relmax(a, ref) < 1e-5, (name, relmax(a, ref))
+        # index / patch layout: the brightest pixel of every frame is where the reference puts it
+        assert (a.reshape(a.shape[0], a.shape[1], -1).argmax(-1) == ref.reshape(ref.shape[0], ref.shape[1], -1).argmax(-1)).mean() > 0.99
+
+
+def test_multi_settings_noisy_matches_philox_oracle_and_errors(gold, gen):
+    inp, _, _ = gold
+    t = inp["traj30"][:3]
+    outs = gen.trajectories_to_video_multiple_settings(t.copy(), 10, True, C3_PROPS, seed=4321, seq_offset=2)
+    orc = ro.render_multi(t, 10, True, C3_PROPS, noise=PhiloxNoise(4321), seq_offset=2)
+    for name, a, b in zip(("none", "gauss", "poisson", "filter"), outs, orc):
+        bad = np.abs(a - b) > 1e-4 * np.abs(b) + 1e-2
+        # same counter streams -> same draws; a Poisson count that differs through an fp tie also moves its 5x5 filter footprint
+        assert bad.mean() < (2e-2 if name == "filter" else 3e-3), (name, bad.mean())
+    # defaults of this variant: poisson_noise = 1 (:455); the T % n check comes after the in-place flip
+    t2 = np.zeros((1, 25, 2))
+    t2[:, :, 1] = 1.0
+    with pytest.raises(Exception, match="T is not divisble by posPerFrame"):
+        gen.trajectories_to_video_multiple_settings(t2, 10, True, C3_PROPS)
+    assert np.all(t2[:, :, 1] == -1.0)
