@@ -96,6 +96,13 @@ int mivit_render_multi(const double* traj, int64_t N, int32_t T, const mivit_ren
                        uint64_t seq_offset, float* out_no_noise, float* out_gauss, float* out_poisson,
                        float* out_filter, void* stream);
 
+/* Replaces helpers/helpersGeneration.py:557-587 richardson_lucy_tv / richardson_lucy_tv_iter_list (with tv_gradient :542-555)
+ * for a batch of P x P frames (P <= 16): images [n_images][P][P] float32 (device), psf_dev [K][K] float64 (device, K odd),
+ * iterations_host[n_iterations] = the reference's `iterations_list` (0-based indices of the iterations whose estimate is kept,
+ * ascending; iterations_list[-1] + 1 iterations run); out [n_images][n_iterations][P][P] float32. */
+int mivit_rl_tv(const float* images, int64_t n_images, int32_t P, const double* psf_dev, int32_t K,
+                const int32_t* iterations_host, int32_t n_iterations, float tv_weight, float* out, void* stream);
+
 /* Replaces Experiments/PSFNoise/trainSettingsPSFNoise.py:196-309 trajs_to_vid_psf_noise.
  * psf_div[n_psf], noise_frac[n_noise] are HOST arrays (PSF_Settings, Noise_Settings);
  * part_mean_global is the module-level `part_mean` used for the background sigma (:302).

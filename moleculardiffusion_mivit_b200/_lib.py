@@ -51,6 +51,7 @@ def _declare(lib):
         "mivit_profile_read": (i32, [c.POINTER(KernelTime), i32]),
         "mivit_render_v1": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, i64, vp]),
         "mivit_render_multi": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, vp, vp, vp, vp]),
+        "mivit_rl_tv": (i32, [vp, i64, i32, vp, i32, c.POINTER(c.c_int32), i32, f32, vp, vp]),
         "mivit_render_embed_linear": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, vp, i32, vp, vp, i64, vp]),
         "mivit_render_psfnoise": (i32, [vp, i64, i32, c.POINTER(RenderParams), fp, i32, fp, i32, f32, u64, u64, vp, vp]),
         "mivit_average_frames": (i32, [vp, i64, i32, i32, vp, vp]),

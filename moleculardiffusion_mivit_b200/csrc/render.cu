@@ -382,6 +382,96 @@ __global__ void __launch_bounds__(256) render_multi_kernel(const double* __restr
   }
 }
 
+// Richardson-Lucy deconvolution with a total-variation step (helpers/helpersGeneration.py:542-587 tv_gradient,
+// richardson_lucy_tv, richardson_lucy_tv_iter_list), one warp per P x P frame, everything in the warp's shared memory.
+// Per iteration (reference order and dtypes): relative_blur = image / (conv(estimate, psf) + 1e-6) in float64,
+// correction = conv(relative_blur, psf mirrored), estimate *= correction (float64 product stored as float32), the TV gradient
+// and its step in float32, clip to [0, 1]; estimates after the listed (0-based) iterations are written out.  conv is scipy's
+// fftconvolve(mode='same') as the direct float64 sum it equals (the reference's FFT of the float32 estimate runs in single
+// precision, so the two agree to ~3e-4 after 11 iterations -- see oracle/render_oracle.py).
+struct RlIters { int it[8]; int n; int last; };
+__global__ void __launch_bounds__(256) rl_tv_kernel(const float* __restrict__ images, long long n_frames, int P, int K,
+                                                    const double* __restrict__ psf, RlIters its, float tv_weight,
+                                                    float* __restrict__ out) {
+  extern __shared__ double sm_d[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int PP = P * P, KK = K * K, c = (K - 1) / 2;
+  double* psf_s = sm_d;                                   // [KK] shared by the CTA
+  double* rb = sm_d + KK + (size_t)warp * PP;             // [PP] relative blur (float64)
+  float* fbase = reinterpret_cast<float*>(sm_d + KK + (size_t)warps * PP) + (size_t)warp * 4 * PP;
+  float *img = fbase, *est = fbase + PP, *dxn = fbase + 2 * PP, *dyn = fbase + 3 * PP;
+  for (int i = threadIdx.x; i < KK; i += blockDim.x) psf_s[i] = psf[i];
+  __syncthreads();
+  const long long fr = (long long)blockIdx.x * warps + warp;
+  if (fr >= n_frames) return;
+  for (int p = lane; p < PP; p += 32) {
+    img[p] = fmaxf(images[fr * PP + p], 1e-6f);           // np.clip(image, 1e-6, None)
+    est[p] = 0.5f;
+  }
+  __syncwarp();
+  for (int iter = 0; iter <= its.last; ++iter) {
+    for (int p = lane; p < PP; p += 32) {                 // image / (estimate (*) psf + 1e-6)
+      const int i = p / P, j = p - i * P;
+      double acc = 0.0;
+      for (int u = 0; u < K; ++u) {
+        const int ii = i + c - u;
+        if (ii < 0 || ii >= P) continue;
+        for (int v = 0; v < K; ++v) {
+          const int jj = j + c - v;
+          if (jj >= 0 && jj < P) acc += (double)est[ii * P + jj] * psf_s[u * K + v];
+        }
+      }
+      rb[p] = (double)img[p] / (acc + 1e-6);
+    }
+    __syncwarp();
+    float e_new[8];                                       // PP <= 256 pixels: up to 8 per lane
+    int cnt = 0;
+    for (int p = lane; p < PP; p += 32, ++cnt) {          // estimate *= relative_blur (*) psf[::-1, ::-1]
+      const int i = p / P, j = p - i * P;
+      double acc = 0.0;
+      for (int u = 0; u < K; ++u) {
+        const int ii = i + c - u;
+        if (ii < 0 || ii >= P) continue;
+        for (int v = 0; v < K; ++v) {
+          const int jj = j + c - v;
+          if (jj >= 0 && jj < P) acc += rb[ii * P + jj] * psf_s[(K - 1 - u) * K + (K - 1 - v)];
+        }
+      }
+      e_new[cnt] = (float)((double)est[p] * acc);
+    }
+    cnt = 0;
+    for (int p = lane; p < PP; p += 32, ++cnt) est[p] = e_new[cnt];
+    __syncwarp();
+    for (int p = lane; p < PP; p += 32) {                 // tv_gradient: normalised forward differences (float32)
+      const int i = p / P, j = p - i * P;
+      const float e = est[p];
+      const float dx = (j + 1 < P) ? __fsub_rn(est[p + 1], e) : 0.0f;      // np.diff(..., append=last column) -> 0
+      const float dy = (i + 1 < P) ? __fsub_rn(est[p + P], e) : 0.0f;
+      const float mag = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), 1e-8f));
+      dxn[p] = __fdiv_rn(dx, mag);
+      dyn[p] = __fdiv_rn(dy, mag);
+    }
+    __syncwarp();
+    cnt = 0;
+    for (int p = lane; p < PP; p += 32, ++cnt) {
+      const int i = p / P, j = p - i * P;
+      float g = 0.0f;
+      if (j + 1 < P) g = __fsub_rn(g, dxn[p]);            // grad[:, :-1] -= dx_norm[:, :-1]
+      if (j >= 1) g = __fadd_rn(g, dxn[p - 1]);           // grad[:, 1:]  += dx_norm[:, :-1]
+      if (i + 1 < P) g = __fsub_rn(g, dyn[p]);            // grad[:-1, :] -= dy_norm[:-1, :]
+      if (i >= 1) g = __fadd_rn(g, dyn[p - P]);           // grad[1:, :]  += dy_norm[:-1, :]
+      const float e = __fsub_rn(est[p], __fmul_rn(tv_weight, g));
+      e_new[cnt] = fminf(fmaxf(e, 0.0f), 1.0f);
+    }
+    cnt = 0;
+    for (int p = lane; p < PP; p += 32, ++cnt) est[p] = e_new[cnt];
+    __syncwarp();
+    for (int k = 0; k < its.n; ++k)
+      if (its.it[k] == iter)
+        for (int p = lane; p < PP; p += 32) out[((size_t)fr * its.n + k) * PP + p] = est[p];
+  }
+}
+
 // One warp per sequence: D draw, steps, float64 prefix sum.
 struct DGroups { float mean[16], var[16]; };
 
@@ -568,6 +658,31 @@ extern "C" int mivit_render_multi(const double* traj, int64_t N, int32_t T, cons
   const long long frames = (long long)N * d.F;
   render_multi_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, taps, out_no_noise,
                                                                                                   out_gauss, out_poisson, out_filter);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+extern "C" int mivit_rl_tv(const float* images, int64_t n_images, int32_t P, const double* psf_dev, int32_t K,
+                           const int32_t* iterations_host, int32_t n_iterations, float tv_weight, float* out, void* stream) {
+  MIVIT_CHECK_ARG(n_images >= 0 && P >= 1 && P <= 16, "Richardson-Lucy/TV frames must be at most 16 x 16");
+  MIVIT_CHECK_ARG(K >= 1 && K % 2 == 1 && K <= 31, "PSF size must be odd and at most 31");
+  MIVIT_CHECK_ARG(iterations_host && n_iterations >= 1 && n_iterations <= 8, "1 to 8 iteration counts");
+  if (n_images == 0) return MIVIT_OK;
+  MIVIT_CHECK_ARG(images && psf_dev && out, "NULL device pointer");
+  RlIters its;
+  its.n = n_iterations;
+  its.last = 0;
+  for (int k = 0; k < n_iterations; ++k) {
+    MIVIT_CHECK_ARG(iterations_host[k] >= 0 && iterations_host[k] <= 10000, "bad iteration index");
+    its.it[k] = iterations_host[k];
+  }
+  its.last = iterations_host[n_iterations - 1];    // the reference runs iterations_list[-1] + 1 iterations (:575)
+  const int warps = 8, PP = P * P;
+  const size_t smem = (size_t)(K * K + warps * PP) * sizeof(double) + (size_t)warps * 4 * PP * sizeof(float);
+  if (smem > 48 * 1024) MIVIT_CUDA_CHECK(cudaFuncSetAttribute(rl_tv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rl_tv_kernel<<<mivit_ceil_div(n_images, warps), warps * 32, smem, (cudaStream_t)stream>>>(images, n_images, P, K, psf_dev, its,
+                                                                                              tv_weight, out);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

@@ -16,7 +16,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "trajectories_to_video_multiple_settings", "create_video_and_feature_pairs",
+__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "trajectories_to_video_multiple_settings", "trajs_to_vid_norm_rl", "create_gaussian_psf", "richardson_lucy_tv",
+           "richardson_lucy_tv_iter_list", "apply_rl_tv_tensor", "apply_rl_tv_tensor_iter_list", "create_video_and_feature_pairs",
            "average_trajectories_frames", "average_trajs_add_error", "normalize_images", "brownian_motion", "derive_render_params",
            "DEFAULT_IMAGE_PROPS", "render_device"]
 
@@ -195,6 +196,119 @@ def trajectories_to_video_multiple_settings(trajectories, nPosPerFrame, center=F
                                              _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]),
                                              _lib.current_stream()))
     return tuple(o.cpu().numpy() for o in outs) if was_host else tuple(outs)
+
+
+def create_gaussian_psf(size=9, sigma=1.3):
+    """helpers/helpersGeneration.py:591-599 (a K x K float64 parameter array; host arithmetic as in the reference)."""
+    if size % 2 == 0:
+        size += 1  # ensure odd size for symmetry
+    ax = np.arange(-size // 2 + 1, size // 2 + 1)
+    x, y = np.meshgrid(ax, ax)
+    psf = np.exp(-(x ** 2 + y ** 2) / (2 * sigma ** 2))
+    psf /= psf.sum()
+    return psf
+
+
+def _rl_tv_device(frames_dev, psf, iterations_list, tv_weight):
+    """frames_dev: CUDA float32 [n, P, P] -> CUDA float32 [n, len(iterations_list), P, P] (include/mivit.h: mivit_rl_tv)."""
+    import torch
+    n, P = int(frames_dev.shape[0]), int(frames_dev.shape[-1])
+    psf = np.ascontiguousarray(psf, dtype=np.float64)
+    if psf.ndim != 2 or psf.shape[0] != psf.shape[1]:
+        raise ValueError("psf must be a square 2-D array")
+    its = np.asarray(list(iterations_list), dtype=np.int32)
+    if its.size == 0 or np.any(np.diff(its) <= 0):
+        raise ValueError("iterations_list must be a non-empty ascending list")
+    psf_dev = torch.from_numpy(psf).to(frames_dev.device)
+    out = torch.empty((n, its.size, P, P), dtype=torch.float32, device=frames_dev.device)
+    _lib.check(_lib.lib().mivit_rl_tv(_lib.ptr(frames_dev), n, P, _lib.ptr(psf_dev), int(psf.shape[0]),
+                                      its.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(its.size), float(tv_weight),
+                                      _lib.ptr(out), _lib.current_stream()))
+    return out
+
+
+def richardson_lucy_tv(image, psf, iterations=20, tv_weight=0.01):
+    """helpers/helpersGeneration.py:557-569: one P x P image -> its estimate after `iterations` iterations (float32)."""
+    import torch
+    dev = _lib.require_cuda()
+    was_host = not torch.is_tensor(image)
+    x = torch.as_tensor(np.asarray(image) if was_host else image).to(device=dev, dtype=torch.float32).contiguous()
+    out = _rl_tv_device(x.reshape(1, x.shape[-2], x.shape[-1]), psf, [int(iterations) - 1], tv_weight)[0, 0]
+    return out.cpu().numpy() if was_host else out
+
+
+def richardson_lucy_tv_iter_list(image, psf, iterations_list, out_array, tv_weight=0.01):
+    """helpers/helpersGeneration.py:571-587: fills out_array[k] with the estimate after iteration iterations_list[k] (0-based)
+    and returns the last estimate."""
+    import torch
+    dev = _lib.require_cuda()
+    x = torch.as_tensor(np.asarray(image)).to(device=dev, dtype=torch.float32).contiguous()
+    out = _rl_tv_device(x.reshape(1, x.shape[-2], x.shape[-1]), psf, iterations_list, tv_weight)[0].cpu().numpy()
+    for k in range(out.shape[0]):
+        out_array[k] = out[k]
+    return out[-1]
+
+
+def apply_rl_tv_tensor(tensor, psf, n_iters=10, tv_weight=0.01):
+    """helpers/helpersGeneration.py:603-614: [B, seq, H, W] torch tensor -> same shape / dtype / device."""
+    import torch
+    dev = _lib.require_cuda()
+    B, seq, H, W = tensor.shape
+    assert H == 9 and W == 9, "Only images of shape 9x9 are supported"
+    x = tensor.detach().to(device=dev, dtype=torch.float32).contiguous().reshape(B * seq, H, W)
+    out = _rl_tv_device(x, psf, [int(n_iters) - 1], tv_weight)[:, 0].reshape(B, seq, H, W)
+    return out.to(dtype=tensor.dtype, device=tensor.device)
+
+
+def apply_rl_tv_tensor_iter_list(tensor, psf, iterations_list=[2, 5, 10], tv_weight=0.01):
+    """helpers/helpersGeneration.py:616-631: [B, seq, H, W] (torch tensor or numpy) -> numpy [B, len(iterations_list), seq, H, W]."""
+    import torch
+    dev = _lib.require_cuda()
+    B, seq, H, W = tensor.shape
+    assert H == 9 and W == 9, "Only images of shape 9x9 are supported"
+    t = tensor.detach() if torch.is_tensor(tensor) else torch.from_numpy(np.ascontiguousarray(tensor))
+    np_dtype = tensor.detach().cpu().numpy().dtype if torch.is_tensor(tensor) else tensor.dtype
+    x = t.to(device=dev, dtype=torch.float32).contiguous().reshape(B * seq, H, W)
+    out = _rl_tv_device(x, psf, iterations_list, tv_weight).reshape(B, seq, len(iterations_list), H, W).permute(0, 2, 1, 3, 4)
+    return out.contiguous().cpu().numpy().astype(np_dtype, copy=False)
+
+
+def trajs_to_vid_norm_rl(trajectories, nPosPerFrame, center, image_props, rl_iterations, poisson_index=2, *, seed=None,
+                         seq_offset=0, _mean_noise=False):
+    """helpers/helpersGeneration.py:635-658 (the Denoising experiments' generator): the four multiple-settings videos stacked
+    to (N, 4, F, P, P), normalised with (bg_mean, bg_sigma, part_mean + bg_mean), plus the Richardson-Lucy/TV estimates
+    (Gaussian PSF, sigma = 1) of the Poisson-noise videos after the iterations in `rl_iterations` ->
+    numpy float32 (N, 4 + len(rl_iterations), F, P, P).  Everything stays on the GPU until the final copy."""
+    import torch
+    bg_mean, bg_sigma = image_props["background_intensity"]
+    part_mean, part_sigma = image_props["particle_intensity"]
+    psf = create_gaussian_psf(sigma=1)
+    was_host = not torch.is_tensor(trajectories)
+    if was_host:      # render from a device copy, keep the reference's in-place y flip of the caller's array (:432)
+        dev = _lib.require_cuda()
+        N, T, _ = trajectories.shape
+        trajectories[:, :, 1] *= -1
+        if T % nPosPerFrame != 0:
+            raise Exception("T is not divisble by posPerFrame")
+        t_dev = torch.from_numpy(np.ascontiguousarray(trajectories, dtype=np.float64)).to(dev)
+        t_dev[:, :, 1] *= -1      # trajectories_to_video_multiple_settings flips once more below
+    else:
+        t_dev = trajectories
+    vids = trajectories_to_video_multiple_settings(t_dev, nPosPerFrame, center=center, image_props=image_props, seed=seed,
+                                                   seq_offset=seq_offset, _mean_noise=_mean_noise)
+    videos = torch.stack(list(vids), dim=1)                                   # (N, 4, F, P, P)
+    lo = bg_mean - bg_sigma
+    den = (part_mean + bg_mean) - lo
+    if den == 0:
+        raise ValueError("Denominator in normalization is zero. Check the input values.")
+    videos = (videos - lo) / den                                              # normalize_images (:389-395), float32
+    to_rl = videos[:, poisson_index]
+    N, F, P = to_rl.shape[0], to_rl.shape[1], to_rl.shape[-1]
+    assert P == 9, "Only images of shape 9x9 are supported"
+    rl = _rl_tv_device(to_rl.contiguous().reshape(N * F, P, P), psf, rl_iterations, 0.01)
+    rl = rl.reshape(N, F, len(rl_iterations), P, P).permute(0, 2, 1, 3, 4)
+    out = torch.cat([videos, rl], dim=1)
+    return out.cpu().numpy() if was_host else out
 
 
 def average_trajectories_frames(trajectories, nPosFrame):

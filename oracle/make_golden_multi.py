@@ -45,6 +45,11 @@ def main():
         rec["noisy/%s_pixstd" % name] = v.std(axis=0).mean()       # run-to-run spread per pixel = the noise itself
     rec["noisy/repeats"] = R
     np.savez_compressed(os.path.join(OUT, "render_multi_golden.npz"), **rec)
+    # trajs_to_vid_norm_rl (:635-658): normalised four outputs + Richardson-Lucy/TV estimates after iterations 2, 5, 10
+    with _Deterministic(), contextlib.redirect_stdout(io.StringIO()):
+        rl = gen.trajs_to_vid_norm_rl(inp[:2].copy(), 10, True, dict(C3_PROPS), [2, 5, 10])
+    assert rl.shape == (2, 7, 30, 9, 9) and rl.dtype == np.float32
+    np.savez_compressed(os.path.join(OUT, "render_norm_rl_golden.npz"), out=rl)
     print({k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in rec.items()})
 
 

@@ -188,3 +188,18 @@ def test_multi_settings_noisy_moments_vs_reference(golden_dir):
         assert abs(v.mean() - float(g["noisy/%s_mean" % name])) < 0.02 * float(g["noisy/%s_mean" % name]), name
         assert abs(v.std() - float(g["noisy/%s_std" % name])) < 0.03 * float(g["noisy/%s_std" % name]), name
         assert abs(v.std(axis=0).mean() - float(g["noisy/%s_pixstd" % name])) < 0.08 * float(g["noisy/%s_pixstd" % name]), name
+
+
+def test_norm_rl_oracle_matches_reference_golden(golden_dir):
+    """trajs_to_vid_norm_rl (helpersGeneration.py:635-658): with the reference's own fftconvolve the restatement is bit exact;
+    with the direct float64 sum (what the CUDA kernel computes) the Richardson-Lucy/TV channels agree to the single-precision
+    noise of scipy's FFT of the float32 estimate, amplified over 3 / 6 / 11 iterations."""
+    inp = np.load(os.path.join(golden_dir, "render_inputs.npz"))["traj30"][:2]
+    ref = np.load(os.path.join(golden_dir, "render_norm_rl_golden.npz"))["out"]
+    lit = ro.render_norm_rl(inp, 10, True, C3_PROPS, [2, 5, 10], mode="literal", conv="fft")
+    assert lit.shape == ref.shape == (2, 7, 30, 9, 9) and lit.dtype == np.float32
+    assert np.array_equal(lit, ref)
+    direct = ro.render_norm_rl(inp, 10, True, C3_PROPS, [2, 5, 10])
+    assert relmax(direct[:, :4], ref[:, :4]) < 1e-6
+    for k, tol in ((4, 1e-4), (5, 5e-4), (6, 1.5e-3)):
+        assert np.abs(direct[:, k] - ref[:, k]).max() < tol, (k, np.abs(direct[:, k] - ref[:, k]).max())

@@ -270,3 +270,47 @@ def test_multi_settings_noisy_matches_philox_oracle_and_errors(gold, gen):
     with pytest.raises(Exception, match="T is not divisble by posPerFrame"):
         gen.trajectories_to_video_multiple_settings(t2, 10, True, C3_PROPS)
     assert np.all(t2[:, :, 1] == -1.0)
+
+
+def test_norm_rl_matches_reference_golden_and_oracle(golden_dir, gold, gen):
+    """trajs_to_vid_norm_rl (helpersGeneration.py:635-658): normalised four outputs + Richardson-Lucy/TV estimates."""
+    inp, _, _ = gold
+    ref = np.load(os.path.join(golden_dir, "render_norm_rl_golden.npz"))["out"]
+    t = inp["traj30"][:2].copy()
+    out = gen.trajs_to_vid_norm_rl(t, 10, True, C3_PROPS, [2, 5, 10], _mean_noise=True)
+    assert np.array_equal(t[:, :, 1], -inp["traj30"][:2][:, :, 1])              # the in-place y flip of the inner call
+    assert out.shape == ref.shape == (2, 7, 30, 9, 9) and out.dtype == np.float32
+    assert relmax(out[:, :4], ref[:, :4]) < 1e-5
+    # The multiplicative RL update amplifies 1e-7-level differences of its INPUT (float32 renderer vs float64 reference frames,
+    # and the reference's own single-precision FFT) by ~10x every few iterations: bounds per kept iteration (3, 6, 11 iterations).
+    # The kernel's arithmetic itself is checked on identical inputs in test_rl_tv_helpers_match_oracle.
+    orc = ro.render_norm_rl(inp["traj30"][:2], 10, True, C3_PROPS, [2, 5, 10])   # direct float64 convolution, like the kernel
+    for k, tol in ((4, 2e-4), (5, 6e-4), (6, 2e-3)):
+        assert np.abs(out[:, k] - orc[:, k]).max() < tol, (k, np.abs(out[:, k] - orc[:, k]).max())
+        assert np.abs(out[:, k] - ref[:, k]).max() < tol, (k, np.abs(out[:, k] - ref[:, k]).max())
+        assert np.abs(out[:, k] - ref[:, k]).mean() < 2e-6, (k, np.abs(out[:, k] - ref[:, k]).mean())
+
+
+def test_rl_tv_helpers_match_oracle(gen):
+    import torch
+    rng = np.random.default_rng(3)
+    imgs = rng.uniform(0.0, 1.2, size=(3, 4, 9, 9)).astype(np.float32)
+    imgs[0, 0, 2, 3] = -0.5                                                      # clipped to 1e-6 (:558)
+    psf = gen.create_gaussian_psf(sigma=1)
+    assert psf.shape == (9, 9) and abs(psf.sum() - 1.0) < 1e-12 and np.allclose(psf, ro.create_gaussian_psf(sigma=1), rtol=0, atol=0)
+    got = gen.apply_rl_tv_tensor_iter_list(imgs, psf, [0, 3, 7])
+    assert got.shape == (3, 3, 4, 9, 9) and got.dtype == np.float32
+    for b in range(3):
+        for s in range(4):
+            want = ro.richardson_lucy_tv_iter_list(imgs[b, s], psf, [0, 3, 7])
+            for k in range(3):
+                assert np.abs(got[b, k, s] - want[k]).max() < 5e-5, (b, s, k, np.abs(got[b, k, s] - want[k]).max())
+    one = gen.richardson_lucy_tv(imgs[1, 2], psf, iterations=4)                  # 4 iterations = list index 3
+    assert np.abs(one - got[1, 1, 2]).max() == 0.0
+    outs = np.zeros((2, 9, 9), np.float32)
+    last = gen.richardson_lucy_tv_iter_list(imgs[1, 2], psf, [3, 7], outs)
+    assert np.array_equal(outs[0], got[1, 1, 2]) and np.array_equal(last, got[1, 2, 2])
+    tens = gen.apply_rl_tv_tensor(torch.from_numpy(imgs), psf, n_iters=8)
+    assert tuple(tens.shape) == (3, 4, 9, 9) and np.array_equal(tens.numpy(), got[:, 2])
+    with pytest.raises(AssertionError, match="9x9"):
+        gen.apply_rl_tv_tensor(torch.zeros(1, 1, 8, 8), psf)
