@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "trajectories_to_video_multiple_settings", "trajs_to_vid_norm_rl", "create_gaussian_psf", "richardson_lucy_tv",
+__all__ = ["trajectories_to_video", "trajectories_to_embeddings", "trajectories_to_video_multiple_settings", "trajs_to_vid_norm_rl", "generateTrajAndVideosBrownian", "create_gaussian_psf", "richardson_lucy_tv",
            "richardson_lucy_tv_iter_list", "apply_rl_tv_tensor", "apply_rl_tv_tensor_iter_list", "create_video_and_feature_pairs",
            "average_trajectories_frames", "average_trajs_add_error", "normalize_images", "brownian_motion", "derive_render_params",
            "DEFAULT_IMAGE_PROPS", "render_device"]
@@ -196,6 +196,18 @@ def trajectories_to_video_multiple_settings(trajectories, nPosPerFrame, center=F
                                              _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]),
                                              _lib.current_stream()))
     return tuple(o.cpu().numpy() for o in outs) if was_host else tuple(outs)
+
+
+def generateTrajAndVideosBrownian(Ds, nPart, nImages, nPosPerFrame, optics_props, *, seed=None, seq_offset=0):
+    """helpers/helpersGeneration.py:402-417: nPart Brownian trajectories with D ~ N(Ds[0], Ds[1]) (the andi_datasets
+    `single_state(L=0, alphas=1)` call, replaced by this package's device generator: statistical contract only, see
+    oracle/trajectory_oracle.py) rendered with trajectories_to_video(center=True).  Returns (videos (N,F,P,P) float32 numpy,
+    D (N,) float32 numpy) -- the reference's `labels[:, 0, 1]`."""
+    T = int(nImages) * int(nPosPerFrame)
+    s = _draw_seed(seed)
+    trajs, D = brownian_motion(nPart, T, 1, [Ds[0]], 1.0, seed=s, seq_offset=seq_offset, D_var=Ds[1], return_D=True)
+    videos = trajectories_to_video(trajs, nPosPerFrame, True, optics_props, seed=s, seq_offset=seq_offset)
+    return videos, D
 
 
 def create_gaussian_psf(size=9, sigma=1.3):

@@ -36,6 +36,7 @@ class MiViTTrainer:
         # because its bias corrections change every step.
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
+        self._graph_ws = self._graph_flat = None
         import torch.distributed as dist
         self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized())) else None
         self.group = process_group
@@ -78,7 +79,10 @@ class MiViTTrainer:
         if s is None:
             dev = self.model._flat.device
             s = (torch.empty((B, 1), dtype=torch.float32, device=dev), torch.empty((B, 1), dtype=torch.float32, device=dev))
-            self._scratch = {B: s}
+            if self.cuda_graph:
+                self._scratch[B] = s      # captured graphs hold these addresses: keep every size alive
+            else:
+                self._scratch = {B: s}
         return s
 
     def train_step(self, x, target, features=None):
@@ -201,8 +205,12 @@ class MiViTTrainer:
         Returns None on the first call of a shape: that step runs kernel by kernel -- it also performs every lazy
         initialisation -- and the graphs are captured on the second call."""
         model = self.model
-        key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), id(ws),
-               bool(overlap))
+        if self._graph_ws is not ws or self._graph_flat is not model._flat:
+            # the model keeps ONE live workspace: a new batch shape replaced it (or the parameters moved), and every captured
+            # graph points into the old buffers
+            self._graphs.clear()
+            self._graph_ws, self._graph_flat = ws, model._flat
+        key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), bool(overlap))
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "pending"

@@ -314,3 +314,13 @@ def test_rl_tv_helpers_match_oracle(gen):
     assert tuple(tens.shape) == (3, 4, 9, 9) and np.array_equal(tens.numpy(), got[:, 2])
     with pytest.raises(AssertionError, match="9x9"):
         gen.apply_rl_tv_tensor(torch.zeros(1, 1, 8, 8), psf)
+
+
+def test_generate_traj_and_videos_brownian(gen):
+    """helpersGeneration.py:402-417: trajectories from the device Brownian source (D ~ N(mean, var)) rendered centred."""
+    vids, D = gen.generateTrajAndVideosBrownian([5.0, 1.0], 64, 30, 10, C3_PROPS, seed=11)
+    assert vids.shape == (64, 30, 9, 9) and vids.dtype == np.float32 and D.shape == (64,)
+    assert np.all(D > 0) and abs(float(D.mean()) - 5.0) < 0.5 and 0.5 < float(D.std()) < 1.6
+    assert np.isfinite(vids).all() and float(vids.mean()) > 1420.0     # background + particle
+    vids2, D2 = gen.generateTrajAndVideosBrownian([5.0, 1.0], 64, 30, 10, C3_PROPS, seed=11)
+    assert np.array_equal(vids, vids2) and np.array_equal(D, D2)       # counter-based streams: reproducible

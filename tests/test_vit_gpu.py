@@ -340,3 +340,23 @@ def test_modular_trainer_step_and_errors(golden_dir):
         M.ModularTransformer(32, 2, 64, 1, M.MLPHead(32), F.relu, mode="images_only")
     with pytest.raises(ValueError, match="Features are required"):
         model(None, None)
+
+
+def test_cuda_graph_survives_batch_shape_changes(golden_dir):
+    """The model keeps one live workspace: a different batch size replaces it, so graphs captured for the old shape must be
+    dropped and re-captured (B = 4, 4, 4, 2, 2, 2, 4, 4, 4 -- the experiment loop's trailing partial batches do this)."""
+    import torch
+    from moleculardiffusion_mivit_b200.training import MiViTTrainer
+    z, sd, x, tgt, _ = load_case(golden_dir, "deepcnn_n")
+    g = torch.Generator().manual_seed(9)
+    sizes = [4, 4, 4, 2, 2, 2, 4, 4, 4]
+    xs = [(x[:b] + 0.02 * torch.randn(x[:b].shape, generator=g)).cuda() for b in sizes]
+    ts = [torch.rand((b, 1), generator=g).cuda() for b in sizes]
+    losses = []
+    for graph in (False, True):
+        model = build("deepcnn_n")
+        model.load_state_dict(sd)
+        model.cuda().train()
+        tr = MiViTTrainer(model, lr=1e-4, cuda_graph=graph)
+        losses.append([tr.train_step(a, b).item() for a, b in zip(xs, ts)])
+    assert np.allclose(losses[0], losses[1], rtol=2e-2, atol=1e-5), losses
