@@ -318,9 +318,10 @@ def test_rl_tv_helpers_match_oracle(gen):
 
 def test_generate_traj_and_videos_brownian(gen):
     """helpersGeneration.py:402-417: trajectories from the device Brownian source (D ~ N(mean, var)) rendered centred."""
-    vids, D = gen.generateTrajAndVideosBrownian([5.0, 1.0], 64, 30, 10, C3_PROPS, seed=11)
+    props = dict(C3_PROPS, trajectory_unit=100)     # 1 trajectory unit = 1 pixel: D = 0.05 px^2 per sub-step stays in the 9 px frame
+    vids, D = gen.generateTrajAndVideosBrownian([0.05, 1e-4], 64, 30, 10, props, seed=11)
     assert vids.shape == (64, 30, 9, 9) and vids.dtype == np.float32 and D.shape == (64,)
-    assert np.all(D > 0) and abs(float(D.mean()) - 5.0) < 0.5 and 0.5 < float(D.std()) < 1.6
+    assert np.all(D > 0) and abs(float(D.mean()) - 0.05) < 0.01 and 0.004 < float(D.std()) < 0.02
     assert np.isfinite(vids).all() and float(vids.mean()) > 1420.0     # background + particle
-    vids2, D2 = gen.generateTrajAndVideosBrownian([5.0, 1.0], 64, 30, 10, C3_PROPS, seed=11)
+    vids2, D2 = gen.generateTrajAndVideosBrownian([0.05, 1e-4], 64, 30, 10, props, seed=11)
     assert np.array_equal(vids, vids2) and np.array_equal(D, D2)       # counter-based streams: reproducible
