@@ -23,6 +23,8 @@
 // 64 -> 32 (dual input) 0.352 -> 0.377 ms: at C_in >= 64 the N = 64 MMAs already want more shared-memory bandwidth than the
 // SM has (192 B/cycle, see conv_tc4.cu), and a second group's staging stores, statistics loads and TMA-store reads running
 // concurrently with them take it away from the tensor core.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
@@ -80,7 +82,8 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                      const __grid_constant__ CUtensorMap tmYsk, const __grid_constant__ CUtensorMap tmX2,
                      const __nv_bfloat16* __restrict__ Wp, const __nv_bfloat16* __restrict__ Wsk,
                      const __nv_bfloat16* __restrict__ Wp2, float* __restrict__ stats, float* __restrict__ stats_sk, long long rows,
-                     int n_tiles, int P, ConvShifts shifts, int halo, int xslab_rows, int cout_total, int nsplit, int ring, int guard) {
+                     int n_tiles, int P, ConvShifts shifts, int halo, int xslab_rows, int cout_total, int nsplit, int ring, int guard,
+                     __nv_bfloat16* __restrict__ Yp, __nv_bfloat16* __restrict__ Yskp, int use_tma_store) {
   using C = Cfg3<CIN, NS, SKIP, TAPS, CIN2>;
   constexpr int taps = TAPS;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -286,7 +289,7 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int q = 0; q < C::kOutPerAcc; ++q, ++sidx) {
           uint8_t* stg = gstage + (sidx % C::kStageBufs) * C::kStageBytes;
           // the TMA store that read this staging buffer two regions ago is done; everyone finished its statistics reads
-          if (etid == 0) bulk_wait_read<C::kStageBufs - 1>();
+          if (use_tma_store && etid == 0) bulk_wait_read<C::kStageBufs - 1>();
           epi_bar_sync(grp);
 #pragma unroll
           for (int g = 0; g < C::kOutW / 32; ++g) {
@@ -311,16 +314,28 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               *reinterpret_cast<uint4*>(stg + my_row * C::kOutPitch + ((chunk ^ my_swz) << 4)) = pk;
             }
           }
-          umma::fence_proxy_async();   // generic-proxy writes of the staged tile -> visible to the TMA store
-          epi_bar_sync(grp);
-          if (etid == 0) tma_store_tile(o == 0 ? &tmY : &tmYsk, stg, col0 + q * C::kOutW, guard + tile * kTileM);
-          if (want_stats) {
+          if (use_tma_store) {
+            umma::fence_proxy_async();   // generic-proxy writes of the staged tile -> visible to the TMA store
+            epi_bar_sync(grp);
+            if (etid == 0) tma_store_tile(o == 0 ? &tmY : &tmYsk, stg, col0 + q * C::kOutW, guard + tile * kTileM);
+          } else {
+            epi_bar_sync(grp);
+          }
+          // MIVIT_DIRECT_STORE=1 (experiment): the tile leaves through plain 16-byte stores from the loop that reads it back for the statistics (every
+          // thread: one chunk of kRowsPerThread rows, 8 lanes = one 128-byte row segment).  A TMA store is one request per
+          // 128-byte ROW on the unit that also feeds the operand ring (~1 row per 6-8 cycles per SM): with
+          // C_out <= 64 per CTA the 128-256 stored rows per tile outnumbered the 80-160 loaded ones and set the tile time.
+          if (want_stats || !use_tma_store) {
+            uint4* yout = reinterpret_cast<uint4*>(o == 0 ? Yp : Yskp) +
+                          (((long long)tile * kTileM + sg * kRowsPerThread) * cout_total + col0 + q * C::kOutW) / 8 + sc;
             // column sums of the STORED (bf16-rounded, pad-masked) values
 #pragma unroll
             for (int i = 0; i < kRowsPerThread; ++i) {
               const int row = sg * kRowsPerThread + i;
               const int sw = C::kOutPitch == 128 ? (row & 7) : ((row >> 1) & 3);
               const uint4 u = *reinterpret_cast<const uint4*>(stg + row * C::kOutPitch + ((sc ^ sw) << 4));
+              if (!use_tma_store) yout[(size_t)i * (cout_total / 8)] = u;
+              if (!want_stats) continue;
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -335,7 +350,7 @@ conv_rows_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
     }
-    if (etid == 0) bulk_wait_read<0>();   // shared memory stays valid until the last store has read it
+    if (use_tma_store && etid == 0) bulk_wait_read<0>();   // shared memory stays valid until the last store has read it
     // CTA-level reduction of the per-thread column sums, then one atomic per channel
     if (k > 0) {
 #pragma unroll
@@ -438,8 +453,9 @@ int launch3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16
   snprintf(tag, sizeof(tag), "conv_rows_tc_%dx%dx%d%s", CIN, cout_total, taps, SKIP ? "+skip" : CIN2 ? "+in2" : "");
   const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
   MivitProfScope prof(tag, 2.0 * valid_rows * ((double)(taps + (SKIP ? 1 : 0)) * CIN + CIN2) * cout_total, st);
+  static const int use_tma_store = getenv("MIVIT_DIRECT_STORE") != nullptr ? 0 : 1;   // A/B switch, see the epilogue
   MIVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmX, tmY, tmYsk, tmX2, Wp, Wsk, Wp2, stats, stats_sk, rows, n_tiles, P, sh, halo,
-                                      xslab_rows, cout_total, nsplit, ring, guard));
+                                      xslab_rows, cout_total, nsplit, ring, guard, Y, Ysk, use_tma_store));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
