@@ -360,3 +360,38 @@ def test_cuda_graph_survives_batch_shape_changes(golden_dir):
         tr = MiViTTrainer(model, lr=1e-4, cuda_graph=graph)
         losses.append([tr.train_step(a, b).item() for a, b in zip(xs, ts)])
     assert np.allclose(losses[0], losses[1], rtol=2e-2, atol=1e-5), losses
+
+
+def test_edge_sizes_long_sequences_single_sample_and_empty_render():
+    """Edge cases: MAX_TOKENS-long sequences (127 frames + regression token: the attention falls back from the
+    sequence-per-CTA kernels, S > 64), a single-sequence batch, and an empty trajectory batch through the renderer."""
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    from moleculardiffusion_mivit_b200.helpersGeneration import trajectories_to_video
+    torch.manual_seed(5)
+    cfg = dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=2, activation="relu", use_pos_encoding=True,
+               use_regression_token=True)
+    model = M.GeneralTransformer(M.LinearProjectionEmbedding, {"patch_size": 9, "embed_dim": 32}, 32, 2, 64, 2, M.MLPHead, F.relu,
+                                 0.0, True, True, True)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.cuda().train()
+    for B, Fr in ((2, 127), (1, 30)):
+        x = torch.randn(B, Fr, 9, 9)
+        tgt = torch.rand(B, 1)
+        model.zero_grad()
+        pred = model(x.cuda())
+        loss = F.mse_loss(pred, tgt.cuda())
+        loss.backward()
+        ref_pred, ref_loss, ref_g, _ = vo.loss_and_grads(sd, cfg, x, tgt, None)
+        assert (pred.cpu() - ref_pred).abs().max().item() < 2e-3 * max(1.0, ref_pred.abs().max().item()), (B, Fr)
+        gmax = max(float(v.norm()) for v in ref_g.values())
+        for k, p in model.named_parameters():
+            r = ref_g[k]
+            if float(r.norm()) < 1e-5 * gmax:
+                continue
+            assert relnorm(p.grad.cpu(), r) < 5e-3, (B, Fr, k, relnorm(p.grad.cpu(), r))
+    with pytest.raises(Exception):
+        model(torch.randn(1, 128, 9, 9).cuda())          # 129 tokens > MAX_TOKENS
+    out = trajectories_to_video(np.zeros((0, 300, 2)), 10, True, {"output_size": 9})
+    assert out.shape == (0, 30, 9, 9) and out.dtype == np.float32
