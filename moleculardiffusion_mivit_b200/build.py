@@ -51,7 +51,9 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s" % src)
         with open(os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".ptxas.log"), "w") as f:
             f.write(out)
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+    # no -lcuda: the one driver entry point (cuTensorMapEncodeTiled) is resolved at run time (csrc/tma.cuh), so the library
+    # loads on a machine without a driver
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

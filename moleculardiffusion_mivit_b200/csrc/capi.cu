@@ -3,6 +3,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "tma.cuh"
 #include "../../include/mivit.h"
 
 static thread_local char g_err[1024] = "";
@@ -16,6 +17,22 @@ void mivit_set_error(const char* fmt, ...) {
 }
 
 void mivit_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+mivit_tensor_map_encode_fn mivit_tensor_map_encoder() {
+  static mivit_tensor_map_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<mivit_tensor_map_encode_fn>(p);
+    else
+      (void)cudaGetLastError();
+    tried = true;
+  }
+  if (fn == nullptr) mivit_set_error("cuTensorMapEncodeTiled is not available (no CUDA driver on this machine?)");
+  return fn;
+}
 
 extern "C" int mivit_abi_version(void) { return MIVIT_ABI_VERSION; }
 extern "C" const char* mivit_last_error(void) { return g_err; }

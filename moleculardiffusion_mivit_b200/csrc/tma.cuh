@@ -12,6 +12,14 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+// cuTensorMapEncodeTiled is the only driver-API entry point this library needs.  It is resolved through the runtime
+// (cudaGetDriverEntryPoint, capi.cu) instead of linking libcuda, so libmivit_b200.so loads -- and its ABI version / symbol table
+// can be checked -- on a machine without a driver (the build container); it fails loudly at the first launch there.
+typedef CUresult (*mivit_tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+mivit_tensor_map_encode_fn mivit_tensor_map_encoder();   // nullptr (and mivit_last_error set) when the driver is not available
+
 // base = first guard row (row0 - guard_rows*C); total_rows includes both guards.  box = box_chunks x box_rows (<= 256) x 16 B.
 static inline int make_rows_tensor_map(CUtensorMap* tm, const void* base, int C, long long total_rows, int box_rows,
                                        int box_chunks) {
@@ -19,7 +27,9 @@ static inline int make_rows_tensor_map(CUtensorMap* tm, const void* base, int C,
   const cuuint64_t gstride[2] = {(cuuint64_t)C * 2, 16};   // bytes, dims 1..2
   const cuuint32_t box[3] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+  mivit_tensor_map_encode_fn encode = mivit_tensor_map_encoder();
+  if (encode == nullptr) return MIVIT_ERR_CUDA;
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -41,7 +51,9 @@ static inline int make_rows_tensor_map_sw(CUtensorMap* tm, const void* base, int
   const cuuint64_t gstride[1] = {(cuuint64_t)C * 2};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  mivit_tensor_map_encode_fn encode = mivit_tensor_map_encoder();
+  if (encode == nullptr) return MIVIT_ERR_CUDA;
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -43,3 +43,20 @@ def test_abi_version_matches_header():
     ver = int(re.search(r"#define\s+MIVIT_ABI_VERSION\s+(\d+)", src).group(1))
     entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
     assert "mivit_abi_version() == %d" % ver in entry
+
+
+def test_library_loads_without_a_driver_and_reports_its_abi_version():
+    """The library links only the CUDA runtime (the one driver entry point it needs is resolved at run time), so it must
+    dlopen on a machine without libcuda, answer mivit_abi_version() and expose every declared entry point -- no compute call."""
+    import ctypes
+    if _build.needs_build():
+        _build.build()
+    lib = ctypes.CDLL(_build.LIB)
+    src = open(os.path.join(ROOT, "include", "mivit.h")).read()
+    ver = int(re.search(r"#define\s+MIVIT_ABI_VERSION\s+(\d+)", src).group(1))
+    lib.mivit_abi_version.restype = ctypes.c_int
+    assert lib.mivit_abi_version() == ver
+    for name in _declared():
+        assert hasattr(lib, name), name
+    lib.mivit_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.mivit_last_error(), bytes)
