@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MIVIT_ABI_VERSION 2
+#define MIVIT_ABI_VERSION 3
 
 int mivit_abi_version(void);
 const char* mivit_last_error(void);
@@ -87,6 +87,18 @@ int mivit_render_v1(const double* traj, int64_t N, int32_t T, const mivit_render
 int mivit_render_embed_linear(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
                               uint64_t seq_offset, const float* Wt, const float* bias, int32_t E, float* emb,
                               float* frames_out, int64_t frames_seq_stride, void* stream);
+
+/* Weight gradient of that fused layer with the frames RE-RENDERED from the trajectories (same parameters / seed / seq_offset
+ * as the forward call, hence bit-identical frames): dW[E][P*P] += sum_frames demb[frame][:] (x) frame, db[E] += sum_frames
+ * demb[frame][:] (the backward of helpers/models.py:160-164 / :188-197 w.r.t. proj.weight / conv.weight and the bias).
+ * demb: device fp32 [N][F][E]; dW, db: device fp32, ACCUMULATED into (zero them first); db may be NULL.  P <= 16, E <= 256. */
+int mivit_render_embed_linear_wgrad(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
+                                    uint64_t seq_offset, const float* demb, int32_t E, float* dW, float* db, void* stream);
+
+/* Host-only helper (no GPU needed): the 256-entry alias table the V1 renderer draws its multiplicative Poisson(pn) factor from
+ * (helpers/helpersGeneration.py:316-317; layout in csrc/philox.cuh): entries_host[j] = alias << 24 | threshold(24 bit),
+ * k = *k0_host + (accepted ? j : alias).  Returns non-zero when lam is outside (0, 380] (the renderer then uses PTRS). */
+int mivit_poisson_alias_table(double lam, uint32_t* entries_host, int32_t* k0_host);
 
 /* Replaces helpers/helpersGeneration.py:422-540 trajectories_to_video_multiple_settings / trajectory_to_mult_settings (the
  * Denoising experiments' generator): one intensity per frame, four float32 [N,F,P,P] outputs -- noise free, + clipped Gaussian
@@ -212,6 +224,8 @@ typedef struct mivit_vit_config {
   int32_t mod_mode;    /* mode: 0 'images_only', 1 'features_only' (x may be NULL), 2 'both'         */
   int32_t mod_fembed;  /* feature_embedding_type: 0 'linear', 1 'mlp'                                */
   int32_t mod_fusion;  /* fusion_method: 0 'add', 1 'concat_proj', 2 'concat_features'               */
+  int32_t per_frame;   /* ModularTransformer(use_regression_token=False, single_prediction=False): the MLP head runs on every
+                        * token and pred / dpred / target are [B*F,1] (helpers/models.py:585-593); needs use_reg = use_feat = 0 */
 } mivit_vit_config;
 
 /* Synchronised BatchNorm for data-parallel training (torch.nn.SyncBatchNorm semantics): the host registers
@@ -250,6 +264,39 @@ int mivit_vit_backward_part(const mivit_vit_config* cfg, int32_t B, const float*
                             const float* dpred, const float* params, float* grads, void* workspace,
                             int32_t part, void* stream);
 int64_t mivit_vit_embedding_param_count(const mivit_vit_config* cfg);   /* floats of the image-embedding block; -1: bad config */
+
+/* rows of pred / dpred / target: B, or B*F for per_frame configurations */
+int32_t mivit_vit_pred_rows(const mivit_vit_config* cfg, int32_t B);
+
+/* The same forward / backward / training step starting from the TRAJECTORIES (BASELINE north_star (1): "fused with the
+ * patch/temporal embedding so frames never round-trip HBM").  Replaces `model(torch.Tensor(normalize_images(
+ * trajectories_to_video(trajs, ...))))` of the training loops (helpers/helpersGeneration.py:128-278,356-400 feeding
+ * helpers/models.py:146-199,328-361).  traj: device float64 [B,T,2] (the caller applies the in-place y flip of :197), prm /
+ * seed / seq_offset as for mivit_render_v1 (prm->normalize selects the fused normalize_images), T / prm->n == cfg->F.
+ *   LinearProjectionEmbedding / CNNEmbedding: the forward runs mivit_render_embed_linear on the model's own weights and the
+ *     backward mivit_render_embed_linear_wgrad (frames re-rendered, bit-identical); `frames` may be NULL, no frame reaches HBM.
+ *   DeepResNetEmbedding: BatchNorm needs the statistics of all frames before any can be consumed, so they are rendered into
+ *     `frames` (device fp32 [B,F,P,P], required) and the usual path runs; the backward reads them again for initial_conv.
+ * seq_offset_dev (optional, may be NULL): DEVICE uint64 added to seq_offset when the kernels run -- a captured CUDA graph
+ * advances the global sequence ids by updating it between replays.
+ * The backward entry must be given the same traj / prm / seed / seq_offset as the forward that filled `workspace`. */
+int mivit_vit_forward_traj(const mivit_vit_config* cfg, int32_t B, const double* traj, int32_t T,
+                           const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset, const uint64_t* seq_offset_dev,
+                           float* frames,
+                           const float* features, const float* params, float* bn_running, int64_t* bn_num_batches,
+                           void* workspace, float* pred, int32_t training, void* stream);
+int mivit_vit_backward_traj(const mivit_vit_config* cfg, int32_t B, const double* traj, int32_t T,
+                            const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset, const uint64_t* seq_offset_dev,
+                            float* frames,
+                            const float* features, const float* dpred, const float* params, float* grads, void* workspace,
+                            int32_t part, void* stream);
+int mivit_vit_train_step_traj(const mivit_vit_config* cfg, int32_t B, const double* traj, int32_t T,
+                              const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset, const uint64_t* seq_offset_dev,
+                              float* frames,
+                              const float* features, const float* target, float* params, float* grads, float* adam_m,
+                              float* adam_v, float* bn_running, int64_t* bn_num_batches, void* workspace, float* pred,
+                              float* loss, float* dpred, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              int64_t step, int32_t apply_update, void* stream);
 
 /* nn.MSELoss() (mean) and its gradient w.r.t. pred (Experiments/PSFNoise/trainSettingsPSFNoise.py:31). */
 int mivit_mse_loss(const float* pred, const float* target, int32_t n, float* loss, float* dpred,

@@ -53,6 +53,8 @@ def _declare(lib):
         "mivit_render_multi": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, vp, vp, vp, vp]),
         "mivit_rl_tv": (i32, [vp, i64, i32, vp, i32, c.POINTER(c.c_int32), i32, f32, vp, vp]),
         "mivit_render_embed_linear": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, vp, i32, vp, vp, i64, vp]),
+        "mivit_render_embed_linear_wgrad": (i32, [vp, i64, i32, c.POINTER(RenderParams), u64, u64, vp, i32, vp, vp, vp]),
+        "mivit_poisson_alias_table": (i32, [f64, c.POINTER(c.c_uint32), c.POINTER(i32)]),
         "mivit_render_psfnoise": (i32, [vp, i64, i32, c.POINTER(RenderParams), fp, i32, fp, i32, f32, u64, u64, vp, vp]),
         "mivit_average_frames": (i32, [vp, i64, i32, i32, vp, vp]),
         "mivit_diffusion_features": (i32, [vp, i64, i32, f64, vp, vp]),
@@ -69,6 +71,11 @@ def _declare(lib):
         "mivit_vit_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
         "mivit_vit_backward_part": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
         "mivit_vit_embedding_param_count": (i64, [vp]),
+        "mivit_vit_pred_rows": (i32, [vp, i32]),
+        "mivit_vit_forward_traj": (i32, [vp, i32, vp, i32, c.POINTER(RenderParams), u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "mivit_vit_backward_traj": (i32, [vp, i32, vp, i32, c.POINTER(RenderParams), u64, u64, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "mivit_vit_train_step_traj": (i32, [vp, i32, vp, i32, c.POINTER(RenderParams), u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                            vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i64, i32, vp]),
         "mivit_mse_loss": (i32, [vp, vp, i32, vp, vp, vp]),
         "mivit_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]),
         "mivit_vit_train_step": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,

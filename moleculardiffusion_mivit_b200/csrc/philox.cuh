@@ -49,6 +49,50 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, 
   z1 = r * c;
 }
 
+// ---- V1 renderer noise layout ("pair" layout, round 2) ----------------------------------------------------------------
+// The V1 renderer (helpers/helpersGeneration.py:312-317) needs ONE standard normal (background) and ONE Poisson(pn) draw with
+// a launch-constant pn per pixel.  One Philox4x32-10 block therefore serves a PAIR of horizontally adjacent pixels:
+//     counter = (frame * pairs_per_frame + row * ceil(P/2) + pair_in_row, 0, seq_id, PIXEL stream)
+//     words x,y -> Box-Muller (angle shifted to (-pi, pi]) -> z for the left / right pixel
+//     word  z   -> Poisson draw of the left pixel, word w -> of the right pixel, through an alias table (Walker / Vose):
+//                  j = word >> 24, accept k0 + j if (word & 0xFFFFFF) < thresh[j], else k0 + alias[j].
+// The table (256 entries, built on the host in float64 by mivit_poisson_alias_table, restated in oracle/noise.py) covers
+// k in [k0, k0 + 256) and is exact up to the 2^-24 threshold quantisation and the mass outside +-6.5 sigma (< 1e-10);
+// it applies for pn <= 380.  Larger pn fall back to the PTRS sampler on the pixel's own uniform stream (blocks >= 1).
+constexpr int kAliasEntries = 256;
+constexpr float kAliasMaxLambda = 380.0f;
+struct AliasTable {
+  uint32_t e[kAliasEntries];   // alias index << 24 | threshold (24 bits)
+  int k0;
+  int valid;
+};
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// two words -> two standard normals, MUFU only: r = sqrt(-2 ln u), angle in (-pi, pi]
+__device__ __forceinline__ void box_muller_fast(uint32_t xa, uint32_t xb, float& z0, float& z1) {
+  const float u = u01(xa);
+  const float th = (u01(xb) - 0.5f) * 6.2831853071795860f;
+  const float r = sqrtf(-1.3862943611198906f * fast_lg2(u));   // -2 ln 2 * log2(u)
+  z0 = r * __sinf(th);
+  z1 = r * __cosf(th);
+}
+
+__device__ __forceinline__ float alias_draw(const uint32_t* __restrict__ tab, int k0, uint32_t word) {
+  const uint32_t ent = tab[word >> 24];
+  const uint32_t j = (word & 0xFFFFFFu) < (ent & 0xFFFFFFu) ? (word >> 24) : (ent >> 24);
+  return (float)(k0 + (int)j);
+}
+
 __constant__ float kLogFact[16] = {
     0.0f, 0.0f, 0.693147180559945f, 1.791759469228055f, 3.178053830347946f, 4.787491742782046f,
     6.579251212010101f, 8.525161361065415f, 10.604602902745251f, 12.801827480081469f,

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "../../include/mivit.h"
+#include "vit.h"
 
 namespace {
 
@@ -34,8 +35,12 @@ struct RenderDev {
   float inv2s2, step;
   uint32_t k0, k1;
   unsigned long long seq_offset;
+  const unsigned long long* seq_off_dev;   // optional DEVICE counter added to seq_offset (lets a captured CUDA graph advance the ids)
   long long out_seq_stride;
 };
+__device__ __forceinline__ uint32_t global_seq(const RenderDev& d, long long s) {
+  return (uint32_t)(d.seq_offset + (d.seq_off_dev != nullptr ? *d.seq_off_dev : 0ull) + (unsigned long long)s);
+}
 
 struct PsfNoiseDev {
   int n_psf, n_noise;
@@ -127,6 +132,16 @@ __device__ __forceinline__ float pixel_signal(const RenderDev& d, const WarpSmem
   return acc;
 }
 
+// ---- V1 renderer (trajectories_to_video): shared per-frame device code of render_v1_kernel, the fused render->embedding
+// kernel and its weight-gradient twin.  Noise layout: "pair" layout of philox.cuh.
+struct V1Noise {
+  const uint32_t* alias;   // shared-memory copy of the alias table (valid when use_alias)
+  int k0;
+  bool use_alias;
+  PoissonConst pc;         // PTRS fall-back for pn > kAliasMaxLambda
+  const float* ptab;
+};
+
 // spot intensities of the n sub-positions of frame f  (helpersGeneration.py:300)
 __device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, int f, int lane, uint32_t seq) {
   const int n = d.n;
@@ -142,65 +157,144 @@ __device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, 
   }
 }
 
-// one output pixel of frame f: signal + clipped Gaussian background, multiplicative Poisson, fused normalisation
-__device__ __forceinline__ float v1_pixel(const RenderDev& d, const WarpSmem& w, int f, int pix, uint32_t seq,
-                                          const PoissonConst& pc, const float* __restrict__ ptab) {
-  const int P = d.P;
-  const int a = pix / P, b = pix - a * P;
-  float v = d.draw ? pixel_signal(d, w, a, b) : 0.0f;
-  PixelStream st;
-  float zb = 0.0f, z1;
-  if (!d.mean_noise) {
-    st.item = (uint32_t)(f * P * P + pix); st.seq = seq; st.sw = stream_word(MIVIT_STREAM_PIXEL, 0);
-    st.k0 = d.k0; st.k1 = d.k1; st.q = 0;
-    st.cur = philox4x32_10(st.item, 0u, seq, st.sw, d.k0, d.k1);
-    box_muller(st.cur.x, st.cur.y, zb, z1);
+// axis table of the V1 kernels: tab[p][0][b] = block mean of the x profile, tab[p][1][a] = I_p * block mean of the y profile
+// (the intensity is folded into the row factor, so a pixel costs one FMA per sub-position); exps on the MUFU (ex2.approx)
+__device__ __forceinline__ void axis_table_v1(const RenderDev& d, int lane, WarpSmem& w) {
+  const int P = d.P, U = d.U, n = d.n;
+  const int entries = 2 * n * P;
+  const float c2 = -d.inv2s2 * 1.4426950408889634f;   // exp(-t/2s^2) = 2^(t * c2)
+  const float invU = 1.0f / (float)U;
+  for (int e = lane; e < entries; e += 32) {
+    const int p = e / (2 * P);
+    const int r = e - p * 2 * P;
+    const int axis = r >= P ? 1 : 0;
+    const int b = r - axis * P;
+    const int idx = axis * n + p;
+    const int jc = w.jc[idx];
+    const float twoc0 = 2.0f * w.c0[idx];
+    float acc = 0.0f;
+    for (int u = 0; u < U; ++u) {
+      const float k = (float)(b * U + u - jc) * d.step;
+      acc += fast_ex2(k * (k - twoc0) * c2);
+    }
+    acc *= invU;
+    if (axis) acc *= w.inten[p];
+    w.tab[(p * 2 + axis) * P + b] = acc;
   }
-  const float bg = fminf(fmaxf(__fadd_rn(d.bg_mean, __fmul_rn(d.bg_std, zb)), 0.0f), d.bg_hi);  // :312-313
-  v = __fadd_rn(v, bg);
-  if (d.poisson != -1.0f) {  // :316-317 multiplicative Poisson
-    const float k = d.mean_noise ? d.poisson : poisson_draw_const(pc, ptab, st);
-    v = __fdiv_rn(__fmul_rn(v, k), d.poisson);
+}
+
+// One frame: every lane walks the frame's pixel PAIRS (row a, columns b0 = 2*pr, b0 + 1), computes signal + clipped Gaussian
+// background (:312-313), multiplicative Poisson (:316-317), fused normalisation (:395) and hands (pixel index, value) to `sink`.
+template <typename Sink>
+__device__ __forceinline__ void v1_frame_pixels(const RenderDev& d, const WarpSmem& w, int f, int lane, uint32_t seq,
+                                                const V1Noise& nz, Sink&& sink) {
+  const int P = d.P, n = d.n;
+  const int ppr = (P + 1) >> 1;              // pairs per row
+  const int pairs = ppr * P;
+  const float inv_pn = d.poisson != -1.0f ? 1.0f / d.poisson : 1.0f;
+  for (int q = lane; q < pairs; q += 32) {
+    const int a = q / ppr, b0 = (q - a * ppr) * 2;
+    const bool two = b0 + 1 < P;
+    float v0 = 0.0f, v1 = 0.0f;
+    if (d.draw) {
+      const float* ty = w.tab + P + a;        // tab[p][1][a]
+      const float* tx = w.tab + b0;           // tab[p][0][b0]
+      if (two) {
+#pragma unroll 2
+        for (int p = 0; p < n; ++p) {
+          const float t = ty[p * 2 * P];
+          v0 = fmaf(t, tx[p * 2 * P], v0);
+          v1 = fmaf(t, tx[p * 2 * P + 1], v1);
+        }
+      } else {
+        for (int p = 0; p < n; ++p) v0 = fmaf(ty[p * 2 * P], tx[p * 2 * P], v0);
+      }
+    }
+    float z0 = 0.0f, z1 = 0.0f, k0f = d.poisson, k1f = d.poisson;
+    if (!d.mean_noise) {
+      const uint4 r = philox4x32_10((uint32_t)(f * pairs + q), 0u, seq, stream_word(MIVIT_STREAM_PIXEL, 0), d.k0, d.k1);
+      box_muller_fast(r.x, r.y, z0, z1);
+      if (d.poisson != -1.0f) {
+        if (nz.use_alias) {
+          k0f = alias_draw(nz.alias, nz.k0, r.z);
+          k1f = alias_draw(nz.alias, nz.k0, r.w);
+        } else {  // PTRS on the pixel's own uniform stream: blocks 1, 2, ... of item = pixel index
+          PixelStream st;
+          st.seq = seq; st.sw = stream_word(MIVIT_STREAM_PIXEL, 0); st.k0 = d.k0; st.k1 = d.k1;
+          st.item = (uint32_t)(f * P * P + a * P + b0); st.q = 2;
+          k0f = poisson_draw_const(nz.pc, nz.ptab, st);
+          if (two) { st.item += 1u; st.q = 2; k1f = poisson_draw_const(nz.pc, nz.ptab, st); }
+        }
+      }
+    }
+    v0 += fminf(fmaxf(fmaf(d.bg_std, z0, d.bg_mean), 0.0f), d.bg_hi);
+    v1 += fminf(fmaxf(fmaf(d.bg_std, z1, d.bg_mean), 0.0f), d.bg_hi);
+    if (d.poisson != -1.0f) { v0 = v0 * k0f * inv_pn; v1 = v1 * k1f * inv_pn; }
+    if (d.normalize) { v0 = __fdiv_rn(__fsub_rn(v0, d.norm_sub), d.norm_div); v1 = __fdiv_rn(__fsub_rn(v1, d.norm_sub), d.norm_div); }
+    const int pix = a * P + b0;
+    sink(pix, v0);
+    if (two) sink(pix + 1, v1);
   }
-  if (d.normalize) v = __fdiv_rn(__fsub_rn(v, d.norm_sub), d.norm_div);  // :395
-  return v;
+}
+
+// per-CTA noise set-up: alias table (kernel parameter -> shared memory) or the PTRS log-pmf table
+__device__ __forceinline__ V1Noise v1_noise_setup(const RenderDev& d, const AliasTable& at, uint32_t* alias_s, float* ptab) {
+  V1Noise nz;
+  nz.use_alias = at.valid != 0;
+  nz.alias = alias_s;
+  nz.k0 = at.k0;
+  nz.ptab = ptab;
+  nz.pc = poisson_setup(d.poisson);
+  if (d.poisson != -1.0f && !d.mean_noise) {
+    if (nz.use_alias) {
+      for (int i = threadIdx.x; i < kAliasEntries; i += blockDim.x) alias_s[i] = at.e[i];
+    } else if (nz.pc.ptrs) {
+      poisson_fill_table(nz.pc, ptab, threadIdx.x, blockDim.x);
+    }
+  }
+  return nz;
+}
+
+__device__ __forceinline__ void v1_frame_tables(const RenderDev& d, const double* __restrict__ traj, long long s, int f, int lane,
+                                                uint32_t seq, WarpSmem& w) {
+  if (!d.draw) return;
+  frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
+  __syncwarp();
+  v1_intensities(d, w, f, lane, seq);
+  __syncwarp();
+  axis_table_v1(d, lane, w);
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict__ traj, long long n_frames_total,
-                                                        RenderDev d, float* __restrict__ out) {
+                                                        RenderDev d, const __grid_constant__ AliasTable at,
+                                                        float* __restrict__ out) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   WarpSmem w = carve(smem + (size_t)warp * warp_smem_floats(d.n, d.P), d.n, d.P);
   __shared__ float ptab[kPoissonTable];
-  const PoissonConst pc = poisson_setup(d.poisson);
-  if (d.poisson != -1.0f && !d.mean_noise && pc.ptrs) poisson_fill_table(pc, ptab, threadIdx.x, blockDim.x);
+  __shared__ uint32_t alias_s[kAliasEntries];
+  const V1Noise nz = v1_noise_setup(d, at, alias_s, ptab);
   __syncthreads();
   const long long gf = (long long)blockIdx.x * warps + warp;  // global frame index
   if (gf >= n_frames_total) return;
   const long long s = gf / d.F;
   const int f = (int)(gf - s * d.F);
-  const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
-  const int P = d.P, n = d.n;
-
-  if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
-  __syncwarp();
-  if (d.draw) {
-    v1_intensities(d, w, f, lane, seq);
-    __syncwarp();
-    axis_table(d, d.inv2s2, lane, w);
-    __syncwarp();
-  }
-  float* dst = out + s * d.out_seq_stride + (long long)f * P * P;
-  for (int pix = lane; pix < P * P; pix += 32) dst[pix] = v1_pixel(d, w, f, pix, seq, pc, ptab);
+  const uint32_t seq = global_seq(d, s);
+  v1_frame_tables(d, traj, s, f, lane, seq, w);
+  float* dst = out + s * d.out_seq_stride + (long long)f * d.P * d.P;
+  v1_frame_pixels(d, w, f, lane, seq, nz, [&](int pix, float v) { dst[pix] = v; });
 }
 
 // Renderer fused with the frame embedding of LinearProjectionEmbedding / CNNEmbedding (helpers/models.py:146-199:
 // both are emb[f,:] = W[E,P*P] . frame[f] + b): the frame lives only in the warp's shared memory, the kernel writes
-// [N,F,E] embeddings (and, optionally, the frames for a later weight gradient).  Persistent CTAs keep W^T
-// ([P*P][E], so that lanes read consecutive output features) resident in shared memory.
+// [N,F,E] embeddings (and, optionally, the frames).  Persistent CTAs keep W^T ([P*P][E], so that lanes read consecutive
+// output features) resident in shared memory; w_transposed = 0 takes the nn.Linear layout [E][P*P] (the flat parameter
+// buffer of the ViT) and transposes while staging.
 __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* __restrict__ traj, long long n_frames_total,
-                                                                  RenderDev d, const float* __restrict__ Wt,
+                                                                  RenderDev d, const __grid_constant__ AliasTable at,
+                                                                  const float* __restrict__ W, int w_transposed,
                                                                   const float* __restrict__ bias, int E,
                                                                   float* __restrict__ emb, float* __restrict__ frames_out) {
   extern __shared__ float smem[];
@@ -212,28 +306,25 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
   float* mine = smem + (size_t)PP * E + (size_t)warp * per_warp;
   WarpSmem w = carve(mine, n, P);
   float* px = mine + warp_smem_floats(n, P);               // [PP] rendered frame
-  for (int i = threadIdx.x; i < PP * E; i += blockDim.x) wts[i] = __ldg(Wt + i);
+  if (w_transposed) {
+    for (int i = threadIdx.x; i < PP * E; i += blockDim.x) wts[i] = __ldg(W + i);
+  } else {
+    for (int i = threadIdx.x; i < PP * E; i += blockDim.x) { const int e = i / PP, pix = i - e * PP; wts[pix * E + e] = __ldg(W + i); }
+  }
   __shared__ float ptab[kPoissonTable];
-  const PoissonConst pc = poisson_setup(d.poisson);
-  if (d.poisson != -1.0f && !d.mean_noise && pc.ptrs) poisson_fill_table(pc, ptab, threadIdx.x, blockDim.x);
+  __shared__ uint32_t alias_s[kAliasEntries];
+  const V1Noise nz = v1_noise_setup(d, at, alias_s, ptab);
   __syncthreads();
   for (long long gf = (long long)blockIdx.x * warps + warp; gf < n_frames_total; gf += (long long)gridDim.x * warps) {
     const long long s = gf / d.F;
     const int f = (int)(gf - s * d.F);
-    const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
-    if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
-    __syncwarp();
-    if (d.draw) {
-      v1_intensities(d, w, f, lane, seq);
-      __syncwarp();
-      axis_table(d, d.inv2s2, lane, w);
-      __syncwarp();
-    }
-    for (int pix = lane; pix < PP; pix += 32) {
-      const float v = v1_pixel(d, w, f, pix, seq, pc, ptab);
+    const uint32_t seq = global_seq(d, s);
+    v1_frame_tables(d, traj, s, f, lane, seq, w);
+    float* fo = frames_out != nullptr ? frames_out + s * d.out_seq_stride + (long long)f * PP : nullptr;
+    v1_frame_pixels(d, w, f, lane, seq, nz, [&](int pix, float v) {
       px[pix] = v;
-      if (frames_out != nullptr) frames_out[s * d.out_seq_stride + (long long)f * PP + pix] = v;
-    }
+      if (fo != nullptr) fo[pix] = v;
+    });
     __syncwarp();
     for (int e = lane; e < E; e += 32) {
       float acc = 0.f;
@@ -241,6 +332,80 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
       emb[gf * E + e] = acc + __ldg(bias + e);
     }
     __syncwarp();
+  }
+}
+
+// Weight gradient of the fused render->embedding layer: dW[e][pix] += sum_frames demb[frame][e] * frame[pix],
+// db[e] += sum_frames demb[frame][e], with the frames RE-RENDERED from the trajectories (same Philox streams, hence
+// bit-identical to the forward's frames) instead of being stored: the frames of a Linear / CNN-embedding ViT never exist
+// in HBM, forward or backward.  A CTA renders 8 frames (one per warp) into shared memory, then all 256 threads update
+// their register tile of dW: warp w owns EPW consecutive output features, lane l the pixels l, l + 32, ...
+template <int EPW, int PJ>
+__global__ void __launch_bounds__(256) render_embed_wgrad_kernel(const double* __restrict__ traj, long long n_frames_total,
+                                                                 RenderDev d, const __grid_constant__ AliasTable at,
+                                                                 const float* __restrict__ demb, int E,
+                                                                 float* __restrict__ dW, float* __restrict__ db) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = d.P, n = d.n, PP = d.P * d.P;
+  const int per_warp = warp_smem_floats(n, P) + PP;
+  float* mine = smem + (size_t)warp * per_warp;
+  WarpSmem w = carve(mine, n, P);
+  float* px = mine + warp_smem_floats(n, P);               // [PP] rendered frame of this warp
+  float* dsh = smem + (size_t)8 * per_warp;                // [8][E] demb rows of the CTA's 8 frames
+  __shared__ float ptab[kPoissonTable];
+  __shared__ uint32_t alias_s[kAliasEntries];
+  const V1Noise nz = v1_noise_setup(d, at, alias_s, ptab);
+  float acc[EPW][PJ];
+  float bacc = 0.0f;                                       // lane 0..EPW-1 of every warp: bias gradient of feature warp*EPW+lane
+#pragma unroll
+  for (int i = 0; i < EPW; ++i)
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) acc[i][j] = 0.0f;
+  __syncthreads();
+  const int e0 = warp * EPW;
+  for (long long g0 = (long long)blockIdx.x * 8; g0 < n_frames_total; g0 += (long long)gridDim.x * 8) {
+    const long long gf = g0 + warp;
+    const bool live = gf < n_frames_total;
+    if (live) {
+      const long long s = gf / d.F;
+      const int f = (int)(gf - s * d.F);
+      const uint32_t seq = global_seq(d, s);
+      v1_frame_tables(d, traj, s, f, lane, seq, w);
+      v1_frame_pixels(d, w, f, lane, seq, nz, [&](int pix, float v) { px[pix] = v; });
+      for (int e = lane; e < E; e += 32) dsh[warp * E + e] = __ldg(demb + gf * E + e);
+    } else {
+      for (int pix = lane; pix < PP; pix += 32) px[pix] = 0.0f;
+      for (int e = lane; e < E; e += 32) dsh[warp * E + e] = 0.0f;
+    }
+    __syncthreads();
+    if (e0 < E) {
+#pragma unroll 1
+      for (int fr = 0; fr < 8; ++fr) {
+        const float* pf = smem + (size_t)fr * per_warp + warp_smem_floats(n, P);
+        float pv[PJ];
+#pragma unroll
+        for (int j = 0; j < PJ; ++j) { const int pix = lane + 32 * j; pv[j] = pix < PP ? pf[pix] : 0.0f; }
+#pragma unroll
+        for (int i = 0; i < EPW; ++i) {
+          const float g = e0 + i < E ? dsh[fr * E + e0 + i] : 0.0f;
+#pragma unroll
+          for (int j = 0; j < PJ; ++j) acc[i][j] = fmaf(g, pv[j], acc[i][j]);
+        }
+        if (lane < EPW && e0 + lane < E) bacc += dsh[fr * E + e0 + lane];
+      }
+    }
+    __syncthreads();
+  }
+  if (e0 < E) {
+#pragma unroll
+    for (int i = 0; i < EPW; ++i)
+#pragma unroll
+      for (int j = 0; j < PJ; ++j) {
+        const int pix = lane + 32 * j;
+        if (pix < PP && e0 + i < E) atomicAdd(dW + (size_t)(e0 + i) * PP + pix, acc[i][j]);
+      }
+    if (lane < EPW && e0 + lane < E && db != nullptr) atomicAdd(db + e0 + lane, bacc);
   }
 }
 
@@ -254,7 +419,7 @@ __global__ void __launch_bounds__(256) render_psfnoise_kernel(const double* __re
   if (gf >= n_frames_total) return;
   const long long s = gf / d.F;
   const int f = (int)(gf - s * d.F);
-  const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
+  const uint32_t seq = global_seq(d, s);
   const int P = d.P, n = d.n, PP = d.P * d.P;
 
   if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
@@ -323,7 +488,7 @@ __global__ void __launch_bounds__(256) render_multi_kernel(const double* __restr
   if (gf >= n_frames_total) return;
   const long long s = gf / d.F;
   const int f = (int)(gf - s * d.F);
-  const uint32_t seq = (uint32_t)(d.seq_offset + (unsigned long long)s);
+  const uint32_t seq = global_seq(d, s);
 
   if (d.draw) frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
   float spot = 0.0f;
@@ -530,6 +695,47 @@ __global__ void __launch_bounds__(128) brownian_kernel(long long N, int T, DGrou
   }
 }
 
+// Alias table (Walker / Vose) of Poisson(lam) restricted to k in [k0, k0 + 256), float64 on the host; oracle/noise.py restates
+// it operation by operation.  pmf by the recurrence p(k+1) = p(k) lam / (k+1) from the mode (no lgamma: identical in C and numpy).
+void build_alias_table(double lam, AliasTable& at) {
+  at.valid = 0;
+  at.k0 = 0;
+  for (int i = 0; i < kAliasEntries; ++i) at.e[i] = 0;
+  if (!(lam > 0.0) || lam > (double)kAliasMaxLambda) return;
+  const int K = kAliasEntries;
+  const int mode = (int)floor(lam);
+  const int k0 = mode > K / 2 ? mode - K / 2 : 0;
+  double p[kAliasEntries];
+  p[mode - k0] = 1.0;
+  for (int k = mode; k + 1 < k0 + K; ++k) p[k + 1 - k0] = p[k - k0] * lam / (double)(k + 1);
+  for (int k = mode; k - 1 >= k0; --k) p[k - 1 - k0] = p[k - k0] * (double)k / lam;
+  double sum = 0.0;
+  for (int i = 0; i < K; ++i) sum += p[i];
+  double sc[kAliasEntries], prob[kAliasEntries];
+  int alias[kAliasEntries], small[kAliasEntries], large[kAliasEntries], ns = 0, nl = 0;
+  for (int i = 0; i < K; ++i) {
+    sc[i] = p[i] / sum * (double)K;
+    prob[i] = 1.0;
+    alias[i] = i;
+    if (sc[i] < 1.0) small[ns++] = i; else large[nl++] = i;
+  }
+  while (ns > 0 && nl > 0) {
+    const int sm = small[--ns], lg = large[--nl];
+    prob[sm] = sc[sm];
+    alias[sm] = lg;
+    sc[lg] = (sc[lg] + sc[sm]) - 1.0;
+    if (sc[lg] < 1.0) small[ns++] = lg; else large[nl++] = lg;
+  }
+  for (int i = 0; i < K; ++i) {
+    double t = floor(prob[i] * 16777216.0 + 0.5);
+    if (t > 16777215.0) t = 16777215.0;
+    if (t < 0.0) t = 0.0;
+    at.e[i] = ((uint32_t)alias[i] << 24) | (uint32_t)t;
+  }
+  at.k0 = k0;
+  at.valid = 1;
+}
+
 int fill_dev(const mivit_render_params* prm, int T, uint64_t seed, uint64_t seq_offset, RenderDev& d) {
   MIVIT_CHECK_ARG(prm != nullptr, "render params are NULL");
   MIVIT_CHECK_ARG(prm->P >= 1 && prm->P <= 128, "output_size %d out of range [1,128]", prm->P);
@@ -556,6 +762,7 @@ int fill_dev(const mivit_render_params* prm, int T, uint64_t seed, uint64_t seq_
   d.mean_noise = prm->mean_noise;
   d.k0 = (uint32_t)(seed & 0xFFFFFFFFull); d.k1 = (uint32_t)(seed >> 32);
   d.seq_offset = seq_offset;
+  d.seq_off_dev = nullptr;
   return MIVIT_OK;
 }
 
@@ -573,9 +780,15 @@ int pick_warps(int n, int P, int* warps, size_t* smem) {
 
 extern "C" int mivit_render_v1(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
                                uint64_t seq_offset, float* out, int64_t out_seq_stride, void* stream) {
+  return render_v1_launch(traj, N, T, prm, seed, seq_offset, nullptr, out, out_seq_stride, (cudaStream_t)stream);
+}
+
+int render_v1_launch(const double* traj, long long N, int T, const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset,
+                     const uint64_t* seq_off_dev, float* out, long long out_seq_stride, cudaStream_t stream) {
   RenderDev d;
   int rc = fill_dev(prm, T, seed, seq_offset, d);
   if (rc) return rc;
+  d.seq_off_dev = reinterpret_cast<const unsigned long long*>(seq_off_dev);
   MIVIT_CHECK_ARG(N >= 0, "negative N");
   if (N == 0) return MIVIT_OK;
   MIVIT_CHECK_ARG(traj && out, "NULL device pointer");
@@ -590,21 +803,25 @@ extern "C" int mivit_render_v1(const double* traj, int64_t N, int32_t T, const m
     MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long frames = (long long)N * d.F;
   MivitProfScope prof("render_v1", (double)N * ((double)T * 16.0 + (double)d.F * d.P * d.P * 4.0), (cudaStream_t)stream);
-  render_v1_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, out);
+  AliasTable at;
+  build_alias_table(d.mean_noise || d.poisson == -1.0f ? 0.0 : (double)d.poisson, at);
+  render_v1_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, at, out);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
 }
 
-extern "C" int mivit_render_embed_linear(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
-                                         uint64_t seq_offset, const float* Wt, const float* bias, int32_t E, float* emb,
-                                         float* frames_out, int64_t frames_seq_stride, void* stream) {
+// shared launcher of the fused render -> embedding kernel (C ABI below; vit_model.cu for the from-trajectories training step)
+int render_embed_linear_launch(const double* traj, long long N, int T, const mivit_render_params* prm, uint64_t seed,
+                               uint64_t seq_offset, const uint64_t* seq_off_dev, const float* W, int w_transposed, const float* bias,
+                               int E, float* emb, float* frames_out, long long frames_seq_stride, cudaStream_t st) {
   RenderDev d;
   int rc = fill_dev(prm, T, seed, seq_offset, d);
   if (rc) return rc;
+  d.seq_off_dev = reinterpret_cast<const unsigned long long*>(seq_off_dev);
   MIVIT_CHECK_ARG(N >= 0 && E >= 1 && E <= 1024, "bad N / embed_dim");
   if (N == 0) return MIVIT_OK;
-  MIVIT_CHECK_ARG(traj && Wt && bias && emb, "NULL device pointer");
+  MIVIT_CHECK_ARG(traj && W && bias && emb, "NULL device pointer");
   d.imean = (float)((double)prm->part_mean / prm->n);
   d.istd = (float)((double)prm->part_std / prm->n);
   d.out_seq_stride = frames_seq_stride;
@@ -624,11 +841,92 @@ extern "C" int mivit_render_embed_linear(const double* traj, int64_t N, int32_t 
   if (per_sm > 4) per_sm = 4;
   long long blocks = (long long)sms * per_sm;
   if (blocks > mivit_ceil_div(frames, warps)) blocks = mivit_ceil_div(frames, warps);
-  MivitProfScope prof("render_embed_linear", (double)N * ((double)T * 16.0 + (double)d.F * E * 4.0), (cudaStream_t)stream);
-  render_embed_linear_kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, Wt, bias, E, emb, frames_out);
+  AliasTable at;
+  build_alias_table(d.mean_noise || d.poisson == -1.0f ? 0.0 : (double)d.poisson, at);
+  MivitProfScope prof("render_embed_linear", (double)N * ((double)T * 16.0 + (double)d.F * E * 4.0), st);
+  render_embed_linear_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(traj, frames, d, at, W, w_transposed, bias, E, emb, frames_out);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
+}
+
+template <int EPW, int PJ>
+static int wgrad_launch_t(const double* traj, long long frames, const RenderDev& d, const AliasTable& at, const float* demb, int E,
+                          float* dW, float* db, cudaStream_t st) {
+  const size_t per_warp = (size_t)(warp_smem_floats(d.n, d.P) + d.P * d.P) * sizeof(float);
+  const size_t smem = per_warp * 8 + (size_t)8 * E * sizeof(float);
+  MIVIT_CHECK_ARG(smem <= 200 * 1024, "nPosPerFrame*output_size too large for shared memory (%zu bytes per frame)", per_warp);
+  if (smem > 48 * 1024)
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_embed_wgrad_kernel<EPW, PJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  long long blocks = (long long)sms * 2;
+  if (blocks > mivit_ceil_div(frames, 8)) blocks = mivit_ceil_div(frames, 8);
+  render_embed_wgrad_kernel<EPW, PJ><<<(unsigned)blocks, 256, smem, st>>>(traj, frames, d, at, demb, E, dW, db);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+// dW [E][P*P] and db [E] are ACCUMULATED into (the caller zeroes them)
+int render_embed_wgrad_launch(const double* traj, long long N, int T, const mivit_render_params* prm, uint64_t seed,
+                              uint64_t seq_offset, const uint64_t* seq_off_dev, const float* demb, int E, float* dW, float* db,
+                              cudaStream_t st) {
+  RenderDev d;
+  int rc = fill_dev(prm, T, seed, seq_offset, d);
+  if (rc) return rc;
+  d.seq_off_dev = reinterpret_cast<const unsigned long long*>(seq_off_dev);
+  MIVIT_CHECK_ARG(N >= 0 && E >= 1 && E <= 256, "bad N / embed_dim (the fused weight gradient covers embed_dim <= 256)");
+  MIVIT_CHECK_ARG(d.P <= 16, "the fused weight gradient covers output_size <= 16");
+  if (N == 0) return MIVIT_OK;
+  MIVIT_CHECK_ARG(traj && demb && dW, "NULL device pointer");
+  d.imean = (float)((double)prm->part_mean / prm->n);
+  d.istd = (float)((double)prm->part_std / prm->n);
+  d.out_seq_stride = 0;
+  const long long frames = (long long)N * d.F;
+  AliasTable at;
+  build_alias_table(d.mean_noise || d.poisson == -1.0f ? 0.0 : (double)d.poisson, at);
+  const int epw = (E + 7) / 8, pj = (d.P * d.P + 31) / 32;
+  MivitProfScope prof("render_embed_wgrad", (double)N * ((double)T * 16.0 + (double)d.F * E * 4.0), st);
+#define MIVIT_WG(EPW_, PJ_) return wgrad_launch_t<EPW_, PJ_>(traj, frames, d, at, demb, E, dW, db, st)
+#define MIVIT_WG_E(PJ_)                                  \
+  do {                                                   \
+    if (epw <= 4) MIVIT_WG(4, PJ_);                      \
+    if (epw <= 8) MIVIT_WG(8, PJ_);                      \
+    if (epw <= 16) MIVIT_WG(16, PJ_);                    \
+    MIVIT_WG(32, PJ_);                                   \
+  } while (0)
+  if (pj <= 2) MIVIT_WG_E(2);
+  if (pj <= 3) MIVIT_WG_E(3);
+  if (pj <= 6) MIVIT_WG_E(6);
+  if (epw <= 16) { if (epw <= 4) MIVIT_WG(4, 8); if (epw <= 8) MIVIT_WG(8, 8); MIVIT_WG(16, 8); }
+  // E > 128 with P > 13: two passes over feature halves would be needed; not a configuration of the reference
+  mivit_set_error("fused embedding weight gradient: embed_dim %d with output_size %d is not supported", E, d.P);
+  return MIVIT_ERR_INVALID;
+#undef MIVIT_WG_E
+#undef MIVIT_WG
+}
+
+extern "C" int mivit_render_embed_linear(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,
+                                         uint64_t seq_offset, const float* Wt, const float* bias, int32_t E, float* emb,
+                                         float* frames_out, int64_t frames_seq_stride, void* stream) {
+  return render_embed_linear_launch(traj, N, T, prm, seed, seq_offset, nullptr, Wt, 1, bias, E, emb, frames_out, frames_seq_stride,
+                                    (cudaStream_t)stream);
+}
+
+extern "C" int mivit_render_embed_linear_wgrad(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm,
+                                               uint64_t seed, uint64_t seq_offset, const float* demb, int32_t E, float* dW,
+                                               float* db, void* stream) {
+  return render_embed_wgrad_launch(traj, N, T, prm, seed, seq_offset, nullptr, demb, E, dW, db, (cudaStream_t)stream);
+}
+
+extern "C" int mivit_poisson_alias_table(double lam, uint32_t* entries_host, int32_t* k0_host) {
+  MIVIT_CHECK_ARG(entries_host && k0_host, "NULL pointer");
+  AliasTable at;
+  build_alias_table(lam, at);
+  for (int i = 0; i < kAliasEntries; ++i) entries_host[i] = at.e[i];
+  *k0_host = at.k0;
+  return at.valid ? MIVIT_OK : MIVIT_ERR_INVALID;
 }
 
 extern "C" int mivit_render_multi(const double* traj, int64_t N, int32_t T, const mivit_render_params* prm, uint64_t seed,

@@ -108,6 +108,18 @@ int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, flo
                   int P, cudaStream_t st);
 int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st);
 
+// render.cu -- renderer fused with the Linear / CNN frame embedding and its re-rendering weight gradient
+struct mivit_render_params;
+// seq_off_dev: optional DEVICE counter added to seq_offset (a captured CUDA graph advances the global sequence ids through it)
+int render_v1_launch(const double* traj, long long N, int T, const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset,
+                     const uint64_t* seq_off_dev, float* out, long long out_seq_stride, cudaStream_t stream);
+int render_embed_linear_launch(const double* traj, long long N, int T, const mivit_render_params* prm, uint64_t seed,
+                               uint64_t seq_offset, const uint64_t* seq_off_dev, const float* W, int w_transposed, const float* bias,
+                               int E, float* emb, float* frames_out, long long frames_seq_stride, cudaStream_t st);
+int render_embed_wgrad_launch(const double* traj, long long N, int T, const mivit_render_params* prm, uint64_t seed,
+                              uint64_t seq_offset, const uint64_t* seq_off_dev, const float* demb, int E, float* dW, float* db,
+                              cudaStream_t st);
+
 // optim.cu
 int mse_loss(const float* pred, const float* target, int n, float* loss, float* dpred, cudaStream_t st);
 int adamw_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,

@@ -69,6 +69,8 @@ int build_layout(const mivit_vit_config* c, ParamLayout& L) {
                     c->E, c->feat_dim);
     MIVIT_CHECK_ARG(!(c->mod_mode != 0 && c->mod_fembed == 1) || 2 * E <= 256, "'mlp' feature embedding needs embed_dim <= 128");
   }
+  MIVIT_CHECK_ARG(!c->per_frame || (!c->use_reg && !c->use_feat),
+                  "per-frame outputs (single_prediction=False) need use_regression_token=False and no global features");
   L.E_img = image_embed_dim(c);
   L.has_img = !c->modular || c->mod_mode != 1;
   L.has_femb = c->modular && c->mod_mode != 0 && !(c->mod_mode == 2 && c->mod_fusion == 2);
@@ -141,6 +143,17 @@ struct RowsT {  // one pitched-rows bf16 tensor with guards
 struct BnScratch {
   float *stats, *mi, *ss;  // [2C] each: (sum,sumsq) | (mean,invstd) | (scale,shift)
   int C;
+};
+
+// image source of the from-trajectories entry points: the frames are rendered inside the call (Linear / CNN embedding: fused
+// with the embedding, they never exist in HBM; DeepResNet: rendered into `frames`, [B,F,P,P])
+struct TrajSrc {
+  const double* traj;
+  int T;
+  const mivit_render_params* prm;
+  uint64_t seed, seq_offset;
+  const uint64_t* seq_off_dev;
+  float* frames;
 };
 
 struct LayerWS {
@@ -228,11 +241,12 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
     y.z2 = b.take<float>(T * E); y.m2 = b.take<float>(T); y.r2 = b.take<float>(T); y.x2 = b.take<float>(T * E);
   }
   const int hin = (c->use_feat && c->fusion == 1) ? 2 * E : E;
+  const long long HR = c->per_frame ? T : B;   // rows the MLP head runs on: every token (ModularTransformer, single_prediction=False) or one per sequence
   w.mf = b.take<float>(T); w.rf = b.take<float>(T); w.xf = b.take<float>(T * E);
-  w.headin = b.take<float>((size_t)B * hin); w.hh = b.take<float>((size_t)B * c->head_hidden);
+  w.headin = b.take<float>((size_t)B * hin); w.hh = b.take<float>((size_t)HR * c->head_hidden);
   w.dxa = b.take<float>(T * E); w.dxb = b.take<float>(T * E); w.dq = b.take<float>(T * E); w.dk = b.take<float>(T * E);
   w.dv = b.take<float>(T * E); w.dctx = b.take<float>(T * E); w.dh = b.take<float>(T * HD); w.dh2 = b.take<float>(T * HD);
-  w.dheadin = b.take<float>((size_t)B * hin); w.dhh = b.take<float>((size_t)B * c->head_hidden);
+  w.dheadin = b.take<float>((size_t)B * hin); w.dhh = b.take<float>((size_t)HR * c->head_hidden);
   w.dfp = b.take<float>((size_t)B * E); w.dfp_h = b.take<float>((size_t)B * E); w.demb = b.take<float>(NF * E);
   w.bytes = (b.off + 255) & ~(size_t)255;
 }
@@ -347,12 +361,32 @@ extern "C" int64_t mivit_vit_workspace_bytes(const mivit_vit_config* cfg, int32_
   return (int64_t)w.bytes;
 }
 
-extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
-                                 const float* params, float* bn_running, int64_t* bn_num_batches, void* workspace,
-                                 float* pred, int32_t training, void* stream) {
+static int check_src(const mivit_vit_config* c, const ParamLayout& L, const TrajSrc* src) {
+  MIVIT_CHECK_ARG(L.has_img, "a 'features_only' ModularTransformer has no image path to render for");
+  MIVIT_CHECK_ARG(src->traj && src->prm, "NULL trajectory / render parameters");
+  MIVIT_CHECK_ARG(src->prm->P == c->P, "output_size %d does not match the model's patch_size %d", src->prm->P, c->P);
+  MIVIT_CHECK_ARG(src->prm->n >= 1 && src->T % src->prm->n == 0, "T is not divisble by posPerFrame");
+  MIVIT_CHECK_ARG(src->T / src->prm->n == c->F, "the trajectories give %d frames, the configuration says %d", src->T / src->prm->n, c->F);
+  MIVIT_CHECK_ARG(c->embedding != 2 || src->frames, "the DeepResNet embedding needs a [B,F,P,P] frame buffer (batch statistics)");
+  return MIVIT_OK;
+}
+
+static int vit_forward_impl(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
+                            const float* params, float* bn_running, int64_t* bn_num_batches, void* workspace,
+                            float* pred, int32_t training, void* stream, const TrajSrc* src) {
   ParamLayout L;
   CK(build_layout(c, L));
   MIVIT_CHECK_ARG(B >= 1 && params && workspace && pred, "bad arguments");
+  if (src != nullptr) {
+    CK(check_src(c, L, src));
+    if (c->embedding == 2) {   // batch statistics need every frame of the batch: render to HBM (20 KB per sequence), then as usual
+      CK(render_v1_launch(src->traj, B, src->T, src->prm, src->seed, src->seq_offset, src->seq_off_dev, src->frames,
+                          (long long)c->F * c->P * c->P, (cudaStream_t)stream));
+      x = src->frames;
+    } else {
+      x = reinterpret_cast<const float*>(src->traj);   // non-NULL marker; the fused kernel reads the trajectories
+    }
+  }
   MIVIT_CHECK_ARG(x || !L.has_img, c->modular ? (c->mod_mode == 2 ? "Both images and features are required for 'both' mode"
                                                                    : "Images are required for 'images_only' mode") : "bad arguments");
   MIVIT_CHECK_ARG(!c->use_feat || features, "Global features required for %s fusion", c->fusion ? "late" : "early");
@@ -411,6 +445,10 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
       }
     }
     CK(linear_fwd(w.pooled, p + L.fc_w, p + L.fc_b, emb_img, NF, Ei, 128, 0, st));
+  } else if (src != nullptr) {
+    // renderer fused with the frame embedding: emb = W . frame + b straight from the trajectories, frames never reach HBM
+    CK(render_embed_linear_launch(src->traj, B, src->T, src->prm, src->seed, src->seq_offset, src->seq_off_dev, p + L.proj_w, 0,
+                                  p + L.proj_b, Ei, emb_img, nullptr, 0, st));
   } else {
     CK(linear_fwd(x, p + L.proj_w, p + L.proj_b, emb_img, NF, Ei, P * P, 0, st));
   }
@@ -481,6 +519,11 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
     xin = y.x2;
   }
   CK(layernorm_fwd(xin, nullptr, p + L.tn_g, p + L.tn_b, nullptr, w.xf, w.mf, w.rf, T, E, c->ln_eps, 0, 0, 0, st));
+  if (c->per_frame) {   // ModularTransformer, no regression token, single_prediction=False: the head sees every token (:585-593)
+    CK(linear_fwd(w.xf, p + L.h0_w, p + L.h0_b, w.hh, T, c->head_hidden, E, 1, st));
+    CK(linear_fwd(w.hh, p + L.h3_w, p + L.h3_b, pred, T, 1, c->head_hidden, 0, st));
+    return MIVIT_OK;
+  }
   CK(pool_tokens(w.xf, w.headin, B, S, E, L.head_in, c->use_reg, st));
   if (c->use_feat && c->fusion == 1)
     MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.headin + E, (size_t)L.head_in * 4, w.fp_out, (size_t)E * 4, (size_t)E * 4, B,
@@ -490,12 +533,31 @@ extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const flo
   return MIVIT_OK;
 }
 
+extern "C" int mivit_vit_forward(const mivit_vit_config* c, int32_t B, const float* x, const float* features,
+                                 const float* params, float* bn_running, int64_t* bn_num_batches, void* workspace,
+                                 float* pred, int32_t training, void* stream) {
+  return vit_forward_impl(c, B, x, features, params, bn_running, bn_num_batches, workspace, pred, training, stream, nullptr);
+}
+
+extern "C" int mivit_vit_forward_traj(const mivit_vit_config* c, int32_t B, const double* traj, int32_t T,
+                                      const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset,
+                                      const uint64_t* seq_offset_dev, float* frames,
+                                      const float* features, const float* params, float* bn_running, int64_t* bn_num_batches,
+                                      void* workspace, float* pred, int32_t training, void* stream) {
+  const TrajSrc src{traj, T, prm, seed, seq_offset, seq_offset_dev, frames};
+  return vit_forward_impl(c, B, nullptr, features, params, bn_running, bn_num_batches, workspace, pred, training, stream, &src);
+}
+
 // part: 0 = whole backward; 1 = everything up to (not including) the image embedding -- head, encoder layers, tokens, feature
 // paths, embedding LayerNorm: all gradients behind mivit_vit_embedding_param_count() are final afterwards; 2 = image embedding only.
 static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* x, const float* features, const float* dpred,
-                             const float* params, float* grads, void* workspace, int part, void* stream) {
+                             const float* params, float* grads, void* workspace, int part, void* stream, const TrajSrc* src = nullptr) {
   ParamLayout L;
   CK(build_layout(c, L));
+  if (src != nullptr) {
+    CK(check_src(c, L, src));
+    x = c->embedding == 2 ? src->frames : reinterpret_cast<const float*>(src->traj);
+  }
   MIVIT_CHECK_ARG(B >= 1 && (x || !L.has_img) && dpred && params && grads && workspace, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
@@ -511,14 +573,19 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
   auto tokens_part = [&]() -> int {
   MIVIT_CUDA_CHECK(cudaMemsetAsync(g, 0, (size_t)L.off * sizeof(float), st));
   // head
-  CK(linear_bwd(w.hh, p + L.h3_w, dpred, g + L.h3_w, g + L.h3_b, w.dhh, B, 1, hhid, 0, st));
-  CK(act_bwd(w.dhh, w.hh, w.dhh, (long long)B * hhid, 0, st));
-  CK(linear_bwd(w.headin, p + L.h0_w, w.dhh, g + L.h0_w, g + L.h0_b, w.dheadin, B, hhid, hin, 0, st));
+  const int HR = c->per_frame ? T : B;
+  CK(linear_bwd(w.hh, p + L.h3_w, dpred, g + L.h3_w, g + L.h3_b, w.dhh, HR, 1, hhid, 0, st));
+  CK(act_bwd(w.dhh, w.hh, w.dhh, (long long)HR * hhid, 0, st));
   const bool late = c->use_feat && c->fusion == 1, early = c->use_feat && c->fusion == 0 && c->use_reg;
-  if (late)
-    MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.dfp, (size_t)E * 4, w.dheadin + E, (size_t)hin * 4, (size_t)E * 4, B,
-                                       cudaMemcpyDeviceToDevice, st));
-  CK(pool_tokens_bwd(w.dheadin, w.dxa, B, S, E, hin, c->use_reg, st));
+  if (c->per_frame) {   // the head read every token of the final LayerNorm's output: its input gradient IS d(xf)
+    CK(linear_bwd(w.xf, p + L.h0_w, w.dhh, g + L.h0_w, g + L.h0_b, w.dxa, T, hhid, E, 0, st));
+  } else {
+    CK(linear_bwd(w.headin, p + L.h0_w, w.dhh, g + L.h0_w, g + L.h0_b, w.dheadin, B, hhid, hin, 0, st));
+    if (late)
+      MIVIT_CUDA_CHECK(cudaMemcpy2DAsync(w.dfp, (size_t)E * 4, w.dheadin + E, (size_t)hin * 4, (size_t)E * 4, B,
+                                         cudaMemcpyDeviceToDevice, st));
+    CK(pool_tokens_bwd(w.dheadin, w.dxa, B, S, E, hin, c->use_reg, st));
+  }
   const float* xlast = w.lyr[c->L - 1].x2;
   CK(layernorm_bwd(w.dxa, xlast, w.mf, w.rf, p + L.tn_g, w.dxb, g + L.tn_g, g + L.tn_b, T, E, 0, 0, 0, st));
   float* dx = w.dxb;    // gradient w.r.t. the current layer output
@@ -600,7 +667,11 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
   if (part != 2) CK(tokens_part());
   if (part == 1 || !L.has_img) return MIVIT_OK;
   if (c->embedding != 2) {
-    CK(linear_bwd(x, p + L.proj_w, d_img, g + L.proj_w, g + L.proj_b, nullptr, NF, Ei, P * P, 0, st));
+    if (src != nullptr)   // frames re-rendered from the trajectories inside the weight-gradient kernel (bit-identical to the forward's)
+      CK(render_embed_wgrad_launch(src->traj, B, src->T, src->prm, src->seed, src->seq_offset, src->seq_off_dev, d_img, Ei,
+                                   g + L.proj_w, g + L.proj_b, st));
+    else
+      CK(linear_bwd(x, p + L.proj_w, d_img, g + L.proj_w, g + L.proj_b, nullptr, NF, Ei, P * P, 0, st));
     return MIVIT_OK;
   }
   CK(linear_bwd(w.pooled, p + L.fc_w, d_img, g + L.fc_w, g + L.fc_b, w.dpooled, NF, Ei, 128, 0, st));
@@ -685,6 +756,15 @@ extern "C" int mivit_vit_backward_part(const mivit_vit_config* c, int32_t B, con
   MIVIT_CHECK_ARG(part >= 0 && part <= 2, "part must be 0 (all), 1 (tokens) or 2 (image embedding)");
   return vit_backward_impl(c, B, x, features, dpred, params, grads, workspace, part, stream);
 }
+extern "C" int mivit_vit_backward_traj(const mivit_vit_config* c, int32_t B, const double* traj, int32_t T,
+                                       const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset,
+                                       const uint64_t* seq_offset_dev, float* frames,
+                                       const float* features, const float* dpred, const float* params, float* grads,
+                                       void* workspace, int32_t part, void* stream) {
+  MIVIT_CHECK_ARG(part >= 0 && part <= 2, "part must be 0 (all), 1 (tokens) or 2 (image embedding)");
+  const TrajSrc src{traj, T, prm, seed, seq_offset, seq_offset_dev, frames};
+  return vit_backward_impl(c, B, nullptr, features, dpred, params, grads, workspace, part, stream, &src);
+}
 extern "C" int64_t mivit_vit_embedding_param_count(const mivit_vit_config* c) {
   ParamLayout L;
   if (build_layout(c, L)) return -1;
@@ -701,8 +781,37 @@ extern "C" int mivit_vit_train_step(const mivit_vit_config* c, int32_t B, const 
   CK(build_layout(c, L));
   MIVIT_CHECK_ARG(target && pred && loss && dpred, "bad arguments");
   CK(mivit_vit_forward(c, B, x, features, params, bn_running, bn_num_batches, workspace, pred, 1, stream));
-  CK(mse_loss(pred, target, B, loss, dpred, (cudaStream_t)stream));
+  CK(mse_loss(pred, target, mivit_vit_pred_rows(c, B), loss, dpred, (cudaStream_t)stream));
   CK(mivit_vit_backward(c, B, x, features, dpred, params, grads, workspace, stream));
+  if (apply_update) {
+    MIVIT_CHECK_ARG(adam_m && adam_v && step >= 1, "optimizer state missing");
+    CK(adamw_flat(params, grads, adam_m, adam_v, L.off, lr, beta1, beta2, eps, weight_decay, step, 1.0f, (cudaStream_t)stream));
+  }
+  return MIVIT_OK;
+}
+
+extern "C" int32_t mivit_vit_pred_rows(const mivit_vit_config* c, int32_t B) {
+  return c->per_frame ? B * (c->F + (c->use_reg ? 1 : 0)) : B;
+}
+
+// The reference loop body starting from the TRAJECTORIES: render (helpers/helpersGeneration.py:128-278 + normalize_images
+// :356-400), model forward, MSE, backward, AdamW -- for the Linear / CNN embeddings the frames exist only inside the fused
+// render->embedding kernel (forward) and its re-rendering weight-gradient twin (backward).
+extern "C" int mivit_vit_train_step_traj(const mivit_vit_config* c, int32_t B, const double* traj, int32_t T,
+                                         const mivit_render_params* prm, uint64_t seed, uint64_t seq_offset,
+                                         const uint64_t* seq_offset_dev, float* frames,
+                                         const float* features, const float* target, float* params, float* grads, float* adam_m,
+                                         float* adam_v, float* bn_running, int64_t* bn_num_batches, void* workspace, float* pred,
+                                         float* loss, float* dpred, float lr, float beta1, float beta2, float eps,
+                                         float weight_decay, int64_t step, int32_t apply_update, void* stream) {
+  ParamLayout L;
+  CK(build_layout(c, L));
+  MIVIT_CHECK_ARG(target && pred && loss && dpred, "bad arguments");
+  CK(mivit_vit_forward_traj(c, B, traj, T, prm, seed, seq_offset, seq_offset_dev, frames, features, params, bn_running,
+                            bn_num_batches, workspace, pred, 1, stream));
+  CK(mse_loss(pred, target, mivit_vit_pred_rows(c, B), loss, dpred, (cudaStream_t)stream));
+  CK(mivit_vit_backward_traj(c, B, traj, T, prm, seed, seq_offset, seq_offset_dev, frames, features, dpred, params, grads, workspace,
+                             0, stream));
   if (apply_update) {
     MIVIT_CHECK_ARG(adam_m && adam_v && step >= 1, "optimizer state missing");
     CK(adamw_flat(params, grads, adam_m, adam_v, L.off, lr, beta1, beta2, eps, weight_decay, step, 1.0f, (cudaStream_t)stream));

@@ -17,8 +17,13 @@ mivit_vit_forward / mivit_vit_backward / mivit_vit_train_step).  There is no PyT
                                               'add' | 'concat_proj' | 'concat_features' fusion)
   ImageDataset / ImageFeatureDataset   :781-803
 
-Not supported (raise at construction): dropout > 0 (every reference experiment uses 0.0),
-single_prediction=False, MLPHead activations other than nn.ReLU.
+Not supported (raise at construction): dropout > 0 (every reference experiment uses 0.0), MLPHead activations other
+than nn.ReLU.  `single_prediction=False` is stored and ignored by GeneralTransformer exactly like the reference does
+(helpers/models.py:303, forward :328-361); ModularTransformer without a regression token then returns per-frame
+predictions [B, F, 1] (:585-593).
+
+Additions (no reference counterpart as ONE call): `forward_from_trajectories` -- the training loops'
+`model(torch.Tensor(normalize_images(trajectories_to_video(trajs, ...))))` with the renderer fused into the frame embedding.
 """
 import ctypes
 
@@ -34,7 +39,7 @@ MAX_TOKENS = 128  # helpers/models.py:8
 
 __all__ = ["MAX_TOKENS", "MultiHeadAttention", "FeedForward", "TransformerEncoderLayerWithSkip", "Transformer",
            "LinearProjectionEmbedding", "CNNEmbedding", "ResidualBlock", "DeepResNetEmbedding", "MLPHead",
-           "GeneralTransformer", "ModularTransformer", "ImageDataset", "ImageFeatureDataset", "VitConfig"]
+           "GeneralTransformer", "ModularTransformer", "ImageDataset", "ImageFeatureDataset", "VitConfig", "TrajectorySource"]
 
 
 class VitConfig(ctypes.Structure):
@@ -45,7 +50,7 @@ class VitConfig(ctypes.Structure):
                 ("fusion", ctypes.c_int32), ("feat_dim", ctypes.c_int32), ("head_hidden", ctypes.c_int32),
                 ("conv_impl", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
                 ("ln_eps", ctypes.c_float), ("modular", ctypes.c_int32), ("mod_mode", ctypes.c_int32),
-                ("mod_fembed", ctypes.c_int32), ("mod_fusion", ctypes.c_int32)]
+                ("mod_fembed", ctypes.c_int32), ("mod_fusion", ctypes.c_int32), ("per_frame", ctypes.c_int32)]
 
 
 def _no_direct_forward(self, *a, **k):
@@ -188,9 +193,15 @@ _BN_CHANNELS = (32, 64, 64, 64, 128, 128, 128)
 
 class _VitFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, x, features, *params):
-        pred, gen = model._run_forward(x, features, model.training)
-        ctx.model, ctx.gen = model, gen
+    def forward(ctx, model, x, features, src, *params):
+        if not model.training and model._is_deep():
+            # mivit_vit_backward implements the BATCH-statistics BatchNorm backward only; with running statistics
+            # (eval mode) its gradients would be wrong, so refuse instead of returning them silently
+            raise NotImplementedError(
+                "backward through a DeepResNetEmbedding model in eval() mode is not implemented on the CUDA path "
+                "(BatchNorm backward uses batch statistics): call model.train(), or wrap the call in torch.no_grad()")
+        pred, gen = model._run_forward(x, features, model.training, src)
+        ctx.model, ctx.gen, ctx.src = model, gen, src
         ctx.has_x, ctx.has_feat = x is not None, features is not None
         ctx.save_for_backward(*[t for t in (x, features) if t is not None])
         return pred
@@ -200,8 +211,24 @@ class _VitFunction(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         x = saved.pop(0) if ctx.has_x else None
         feats = saved.pop(0) if ctx.has_feat else None
-        grads = ctx.model._run_backward(x, feats, dpred.contiguous(), ctx.gen)
-        return (None, None, None) + tuple(grads)
+        grads = ctx.model._run_backward(x, feats, dpred.contiguous(), ctx.gen, ctx.src)
+        return (None, None, None, None) + tuple(grads)
+
+
+class TrajectorySource:
+    """Image source of the from-trajectories entry points (include/mivit.h: mivit_vit_*_traj): device float64 trajectories
+    [B,T,2] (y already flipped), the renderer's scalar parameters, the Philox seed and the global id of sequence 0, an optional
+    DEVICE uint64 counter added to that id (graph replay), and -- DeepResNet only -- the [B,F,P,P] frame buffer."""
+
+    def __init__(self, traj, prm, seed, seq_offset=0, seq_offset_dev=None, frames=None):
+        self.traj, self.prm, self.seed, self.seq_offset = traj, prm, int(seed), int(seq_offset)
+        self.seq_offset_dev, self.frames = seq_offset_dev, frames
+        self.B, self.T = int(traj.shape[0]), int(traj.shape[1])
+        self.F = self.T // int(prm.n)
+
+    def args(self):
+        return (_lib.ptr(self.traj), self.T, ctypes.byref(self.prm), self.seed, self.seq_offset, _lib.ptr(self.seq_offset_dev),
+                _lib.ptr(self.frames))
 
 
 def _embedding_keys(prefix, emb):
@@ -337,28 +364,44 @@ class _CudaViT(nn.Module):
         t = x if x is not None else features
         return int(t.shape[0]), int(t.shape[1])
 
-    def _run_forward(self, x, features, training):
-        B, Fr = self._batch_frames(x, features)
+    def _pred_shape(self, cfg, B):
+        """[B,1], or [B,F,1] for per-frame outputs (ModularTransformer, single_prediction=False, no regression token)."""
+        return (B, cfg.F, 1) if cfg.per_frame else (B, 1)
+
+    def _run_forward(self, x, features, training, src=None):
+        B, Fr = (src.B, src.F) if src is not None else self._batch_frames(x, features)
         cfg = self.vit_config(Fr)
         ws = self._workspace(cfg, B)
-        pred = torch.empty((B, 1), dtype=torch.float32, device=self._flat.device)
+        pred = torch.empty(self._pred_shape(cfg, B), dtype=torch.float32, device=self._flat.device)
         is_deep = self._is_deep()
-        _lib.check(_lib.lib().mivit_vit_forward(
-            ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(self._flat),
-            _lib.ptr(self._bn_flat) if is_deep else None, _lib.ptr(self._bn_nbt) if is_deep else None,
-            _lib.ptr(ws), _lib.ptr(pred), int(bool(training)), _lib.current_stream()))
+        bn = (_lib.ptr(self._bn_flat) if is_deep else None, _lib.ptr(self._bn_nbt) if is_deep else None)
+        if src is not None:
+            if is_deep and src.frames is None:
+                src.frames = torch.empty((B, Fr, cfg.P, cfg.P), dtype=torch.float32, device=self._flat.device)
+            _lib.check(_lib.lib().mivit_vit_forward_traj(
+                ctypes.byref(cfg), B, *src.args(), _lib.ptr(features), _lib.ptr(self._flat), bn[0], bn[1],
+                _lib.ptr(ws), _lib.ptr(pred), int(bool(training)), _lib.current_stream()))
+        else:
+            _lib.check(_lib.lib().mivit_vit_forward(
+                ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(self._flat), bn[0], bn[1],
+                _lib.ptr(ws), _lib.ptr(pred), int(bool(training)), _lib.current_stream()))
         self._gen += 1
         return pred, self._gen
 
-    def _run_backward(self, x, features, dpred, gen):
+    def _run_backward(self, x, features, dpred, gen, src=None):
         if gen != self._gen:
             raise RuntimeError("backward() must follow the forward() that produced the output (one live workspace per model)")
-        B, Fr = self._batch_frames(x, features)
+        B, Fr = (src.B, src.F) if src is not None else self._batch_frames(x, features)
         cfg = self.vit_config(Fr)
         ws = self._workspace(cfg, B)
-        _lib.check(_lib.lib().mivit_vit_backward(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(dpred),
-                                                 _lib.ptr(self._flat), _lib.ptr(self._grad_flat), _lib.ptr(ws),
-                                                 _lib.current_stream()))
+        if src is not None:
+            _lib.check(_lib.lib().mivit_vit_backward_traj(ctypes.byref(cfg), B, *src.args(), _lib.ptr(features), _lib.ptr(dpred),
+                                                          _lib.ptr(self._flat), _lib.ptr(self._grad_flat), _lib.ptr(ws), 0,
+                                                          _lib.current_stream()))
+        else:
+            _lib.check(_lib.lib().mivit_vit_backward(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(dpred),
+                                                     _lib.ptr(self._flat), _lib.ptr(self._grad_flat), _lib.ptr(ws),
+                                                     _lib.current_stream()))
         named = dict(self.named_parameters())
         grads, off = [], 0
         for k in self.param_keys():
@@ -367,13 +410,55 @@ class _CudaViT(nn.Module):
             off += p.numel()
         return grads
 
-    def _forward_cuda(self, x, features):
+    def _forward_cuda(self, x, features, src=None):
         named = dict(self.named_parameters())
         params = [named[k] for k in self.param_keys()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _VitFunction.apply(self, x, features, *params)
-        pred, _ = self._run_forward(x, features, self.training)
+            return _VitFunction.apply(self, x, features, src, *params)
+        pred, _ = self._run_forward(x, features, self.training, src)
         return pred
+
+    def trajectory_source(self, trajectories, nPosPerFrame, center=False, image_props={}, *, seed=None, seq_offset=0,
+                          normalize=None, seq_offset_dev=None, _mean_noise=False):
+        """Argument handling of trajectories_to_video (helpers/helpersGeneration.py:194-247: in-place y flip of the caller's
+        array, the T % nPosPerFrame check after it, image_props defaults) -> TrajectorySource on this model's device.
+        normalize=(background_mean, background_sigma, theoretical_max) fuses normalize_images (:389-395)."""
+        from . import helpersGeneration as _g
+        dev = self._ensure_flat()
+        trajectories[:, :, 1] *= -1
+        if trajectories.shape[1] % nPosPerFrame != 0:
+            raise Exception("T is not divisble by posPerFrame")
+        prm = _g.derive_render_params(image_props, nPosPerFrame, center, "v1")
+        prm.flip_y = 0                      # already applied to the caller's array
+        prm.mean_noise = int(bool(_mean_noise))
+        if normalize is not None:
+            m, sg, mx = normalize
+            den = mx - (m - sg)
+            if den == 0:
+                raise ValueError("Denominator in normalization is zero. Check your inputs.")
+            prm.normalize, prm.norm_sub, prm.norm_div = 1, float(m - sg), float(den)
+        emb = self._image_embedding()
+        if emb is None:
+            raise ValueError("this model has no image embedding to render for")
+        if prm.P != emb.patch_size:
+            raise AssertionError("Patch size mismatch")
+        t_dev, _ = _g._to_device_f64(trajectories, dev)
+        return TrajectorySource(t_dev, prm, _g._draw_seed(seed), seq_offset, seq_offset_dev)
+
+    def forward_from_trajectories(self, trajectories, nPosPerFrame, center=False, image_props={}, features=None, *, seed=None,
+                                  seq_offset=0, normalize=None, _mean_noise=False):
+        """`self(torch.Tensor(normalize_images(trajectories_to_video(trajectories, nPosPerFrame, center, image_props))), features)`
+        of the reference training loops (Experiments/Embeddings/trainModelsEmbeddings.py:150-186) as ONE call into the CUDA
+        library: for LinearProjectionEmbedding / CNNEmbedding the renderer is fused with the frame embedding and the frames never
+        reach HBM, forward or backward (the weight gradient re-renders them from the same Philox streams); DeepResNetEmbedding
+        renders into a frame buffer first (BatchNorm needs all frames).  Same side effect (in-place y flip), errors and noise
+        streams as trajectories_to_video(..., seed=seed, seq_offset=seq_offset, normalize=normalize).  Differentiable w.r.t. the
+        parameters."""
+        self._ensure_flat()
+        src = self.trajectory_source(trajectories, nPosPerFrame, center, image_props, seed=seed, seq_offset=seq_offset,
+                                     normalize=normalize, _mean_noise=_mean_noise)
+        features = self._check_features_only(features, src.B, src.F)
+        return self._forward_cuda(None, features, src)
 
     # ------------------------------------------------------------------ fused step ----------
     def flat_parameters(self):
@@ -392,8 +477,6 @@ class GeneralTransformer(_CudaViT):
         super().__init__()
         if dropout != 0:
             raise NotImplementedError("dropout > 0 is not implemented on the CUDA path (the reference experiments use 0.0)")
-        if not single_prediction:
-            raise NotImplementedError("single_prediction=False (per-frame outputs) is not implemented")
         if embedding_cls not in _EMBEDDINGS:
             raise ValueError("embedding_cls must be LinearProjectionEmbedding, CNNEmbedding or DeepResNetEmbedding")
         if tr_activation_fct not in _ACTIVATIONS:
@@ -450,18 +533,17 @@ class GeneralTransformer(_CudaViT):
         c.bn_eps, c.bn_momentum, c.ln_eps = 1e-5, 0.1, 1e-5
         return c
 
+    def _check_features_only(self, features, B, Fr):
+        if self.use_global_features:
+            assert features is not None, "Global features required for %s fusion" % self.fusion_type
+            return features.to(device=self._flat.device, dtype=torch.float32).contiguous()
+        return None
+
     def _check_inputs(self, x, features):
         if x.dim() != 4 or x.shape[2] != self.embedding.patch_size or x.shape[3] != self.embedding.patch_size:
             raise AssertionError("Patch size mismatch")
-        if self.use_global_features:
-            assert features is not None, "Global features required for %s fusion" % self.fusion_type
-        dev = self._flat.device
-        x = x.to(device=dev, dtype=torch.float32).contiguous()
-        if self.use_global_features:
-            features = features.to(device=dev, dtype=torch.float32).contiguous()
-        else:
-            features = None
-        return x, features
+        x = x.to(device=self._flat.device, dtype=torch.float32).contiguous()
+        return x, self._check_features_only(features, x.shape[0], x.shape[1])
 
     def forward(self, x, features=None):
         """x: [batch_size, num_images, image_size, image_size]; features: [batch_size, num_features] or None.
@@ -482,8 +564,6 @@ class ModularTransformer(_CudaViT):
         super().__init__()
         if dropout != 0:
             raise NotImplementedError("dropout > 0 is not implemented on the CUDA path (the reference experiments use 0.0)")
-        if not single_prediction and not use_regression_token:
-            raise NotImplementedError("single_prediction=False (per-frame outputs) is not implemented")
         if tr_activation_fct not in _ACTIVATIONS:
             raise ValueError("tr_activation_fct must be F.relu, F.gelu or F.leaky_relu")
         self.embed_dim = embed_dim
@@ -574,7 +654,20 @@ class ModularTransformer(_CudaViT):
         c.mod_mode = {'images_only': 0, 'features_only': 1, 'both': 2}[self.mode]
         c.mod_fembed = int(self._fembed_mlp)
         c.mod_fusion = {'add': 0, 'concat_proj': 1, 'concat_features': 2}.get(self.fusion_method, 0)
+        # helpers/models.py:585-593: without a regression token and with single_prediction=False the head sees every token
+        c.per_frame = int(not self.use_regression_token and not self.single_prediction)
         return c
+
+    def _check_features_only(self, features, B, Fr):
+        if self.mode == 'images_only':
+            return None
+        if features is None:
+            raise ValueError("Both images and features are required for 'both' mode")
+        if features.dim() != 3 or features.shape[2] != self.features_dim:
+            raise ValueError("features must be [batch_size, num_images, features_dim]")
+        if features.shape[0] != B or features.shape[1] != Fr:
+            raise ValueError("Images and features must have the same batch size and sequence length")
+        return features.to(device=self._flat.device, dtype=torch.float32).contiguous()
 
     def _check_inputs(self, images, features):
         if self.mode == 'images_only' and images is None:
@@ -603,7 +696,8 @@ class ModularTransformer(_CudaViT):
 
     def forward(self, images=None, features=None):
         """images: [batch_size, num_images, image_size, image_size] or None; features: [batch_size, num_images, features_dim]
-        or None (NaNs are replaced by zeros).  Returns [batch_size, 1]."""
+        or None (NaNs are replaced by zeros).  Returns [batch_size, 1], or [batch_size, num_images, 1] for
+        use_regression_token=False, single_prediction=False."""
         self._ensure_flat()
         images, features = self._check_inputs(images, features)
         return self._forward_cuda(images, features)

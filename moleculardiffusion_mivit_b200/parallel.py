@@ -38,3 +38,14 @@ def allreduce_sum_(flat, group=None):
     if world > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / world
+
+
+def broadcast_state_(tensors, group=None, src=0):
+    """Rank `src`'s copy of every tensor replaces the other ranks' (what DistributedDataParallel does with parameters and buffers
+    at construction): ranks built from different seeds or checkpoints start the data-parallel run from identical state."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+        return
+    root = dist.get_global_rank(group, src) if group is not None else src
+    for t in tensors:
+        dist.broadcast(t, src=root, group=group)

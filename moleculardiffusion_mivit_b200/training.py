@@ -8,8 +8,8 @@ import ctypes
 import torch
 
 from . import _lib
-from .models import _CudaViT
-from .parallel import allreduce_sum_
+from .models import _CudaViT, TrajectorySource
+from .parallel import allreduce_sum_, broadcast_state_
 
 __all__ = ["MiViTTrainer"]
 
@@ -53,6 +53,15 @@ class MiViTTrainer:
         # image-embedding backward (~45 % of the step) runs, the embedding's bucket follows, AdamW waits for both.
         self.overlap_allreduce = bool(overlap_allreduce)
         self._ne = None
+        if any(not p.requires_grad for p in model.parameters()):
+            # the fused AdamW walks the whole flat buffer; torch.optim.AdamW would skip frozen parameters
+            raise NotImplementedError("MiViTTrainer updates every parameter: requires_grad=False parameters are not supported")
+        if self.world > 1:
+            # like DistributedDataParallel: every rank starts from rank 0's parameters, BatchNorm statistics and (zero) moments
+            bufs = [model._flat]
+            if model._is_deep():
+                bufs += [model._bn_flat, model._bn_nbt]
+            broadcast_state_(bufs, self.group)
 
     def _allreduce_hook(self, buf, n_floats, stream, user):
         """C callback (mivit_allreduce_fn): SUM all-reduce of n_floats fp32 at device address `buf`, which always lies inside
@@ -74,44 +83,73 @@ class MiViTTrainer:
         self.epoch += 1
         self.lr = self.base_lr * self.gamma ** (self.epoch // self.step_size)
 
-    def _buffers(self, B):
-        s = self._scratch.get(B)
+    def _buffers(self, rows):
+        s = self._scratch.get(rows)
         if s is None:
             dev = self.model._flat.device
-            s = (torch.empty((B, 1), dtype=torch.float32, device=dev), torch.empty((B, 1), dtype=torch.float32, device=dev))
+            s = (torch.empty((rows, 1), dtype=torch.float32, device=dev), torch.empty((rows, 1), dtype=torch.float32, device=dev))
             if self.cuda_graph:
-                self._scratch[B] = s      # captured graphs hold these addresses: keep every size alive
+                self._scratch[rows] = s      # captured graphs hold these addresses: keep every size alive
             else:
-                self._scratch = {B: s}
+                self._scratch = {rows: s}
         return s
 
     def train_step(self, x, target, features=None):
-        """x: CUDA float32 [B,F,P,P] (None for a 'features_only' ModularTransformer); target: CUDA float32 [B,1]; features:
-        [B,feat_dim] (GeneralTransformer) or [B,F,features_dim] (ModularTransformer).  Enqueues the whole step on the current
-        stream and returns the (device) loss tensor without synchronising."""
+        """x: CUDA float32 [B,F,P,P] (None for a 'features_only' ModularTransformer); target: CUDA float32 [B,1] ([B,F,1] for a
+        per-frame ModularTransformer); features: [B,feat_dim] (GeneralTransformer) or [B,F,features_dim] (ModularTransformer).
+        Enqueues the whole step on the current stream and returns the (device) loss tensor without synchronising.  The returned
+        tensor is the trainer's ONE loss buffer (every step overwrites it): read it (`.item()`) or `.clone()` it before the next
+        step if the values are collected."""
         model = self.model
         model._ensure_flat()
         if not model.training:
             model.train()
         x, features = model._check_inputs(x, features)
-        target = target.to(device=model._flat.device, dtype=torch.float32).reshape(-1, 1).contiguous()
         B, Fr = model._batch_frames(x, features)
+        return self._step(x, None, target, features, B, Fr)
+
+    def train_step_from_trajectories(self, src, target, features=None):
+        """The same step starting from TRAJECTORIES (BASELINE north_star (1), include/mivit.h: mivit_vit_train_step_traj): `src` is a
+        models.TrajectorySource (model.trajectory_source(trajs, nPosPerFrame, center, image_props, seed=..., normalize=...) applies
+        the reference's argument handling, or build one around a device-resident float64 [B,T,2] tensor).  Linear / CNN embeddings:
+        the frames exist only inside the fused render->embedding kernel and its re-rendering weight-gradient twin; DeepResNet: they
+        are rendered into src.frames first."""
+        model = self.model
+        model._ensure_flat()
+        if not model.training:
+            model.train()
+        if not isinstance(src, TrajectorySource):
+            raise TypeError("src must be a models.TrajectorySource (see GeneralTransformer.trajectory_source)")
+        features = model._check_features_only(features, src.B, src.F)
+        return self._step(None, src, target, features, src.B, src.F)
+
+    def _step(self, x, src, target, features, B, Fr):
+        model = self.model
         cfg = model.vit_config(Fr)
         ws = model._workspace(cfg, B)
-        pred, dpred = self._buffers(B)
+        rows = B * Fr if cfg.per_frame else B
+        target = target.to(device=model._flat.device, dtype=torch.float32).reshape(-1, 1).contiguous()
+        if target.shape[0] != rows:
+            raise ValueError("target has %d rows, the model predicts %d" % (target.shape[0], rows))
+        pred, dpred = self._buffers(rows)
         deep = model._is_deep()
+        if src is not None and deep and src.frames is None:
+            src.frames = self._frames_buffer(B, Fr, cfg.P)
         self.step_count += 1
         L = _lib.lib()
         if self.sync_bn and deep:
-            return self._sync_bn_step(x, target, features, cfg, B, ws, pred, dpred)
+            return self._sync_bn_step(x, src, target, features, cfg, B, ws, pred, dpred)
         overlap = self.overlap_allreduce and self.world > 1 and model._image_embedding() is not None
-        ent = self._graph_entry(x, target, features, cfg, B, ws, pred, dpred, deep, overlap) if self.cuda_graph else None
+        ent = self._graph_entry(x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap) if self.cuda_graph else None
         n, ne = model._n_params, self._n_embedding(cfg)
         grad = model._grad_flat
         if ent is not None:                       # replay the captured forward + loss + backward (one or two graphs)
-            graphs, gx, gt, gf, counts = ent
+            graphs, gx, gt, gf, counts, gsrc = ent
             if gx is not None:
                 gx.copy_(x)
+            if gsrc is not None:                  # trajectories and the global sequence id go through the graph's static buffers
+                gsrc.traj.copy_(src.traj)
+                gsrc.seq_offset_dev.fill_(src.seq_offset)
             gt.copy_(target)
             if gf is not None:
                 gf.copy_(features)
@@ -123,18 +161,13 @@ class MiViTTrainer:
                     part = grad[ne:n] if i == 0 else grad[:ne]
                     handles.append(self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
         elif overlap:                             # kernel by kernel, same split
-            self._forward_loss_backward_part(1, cfg, B, x, features, target, ws, pred, dpred, deep)
+            self._forward_loss_backward_part(1, cfg, B, x, src, features, target, ws, pred, dpred, deep)
             handles = [self.dist.all_reduce(grad[ne:n], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)]
-            self._forward_loss_backward_part(2, cfg, B, x, features, target, ws, pred, dpred, deep)
+            self._forward_loss_backward_part(2, cfg, B, x, src, features, target, ws, pred, dpred, deep)
             handles.append(self.dist.all_reduce(grad[:ne], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
             handles = []
-            _lib.check(L.mivit_vit_train_step(
-                ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(target), _lib.ptr(model._flat),
-                _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
-                _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None, _lib.ptr(ws),
-                _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
-                self.weight_decay, self.step_count, int(self.world == 1), _lib.current_stream()))
+            self._fused_step_call(cfg, B, x, src, features, target, ws, pred, dpred, deep, int(self.world == 1))
             if self.world == 1:                   # AdamW ran inside the call
                 model._gen += 1
                 self.last_pred = pred
@@ -159,21 +192,49 @@ class MiViTTrainer:
             self._ne = int(_lib.lib().mivit_vit_embedding_param_count(ctypes.byref(cfg)))
         return self._ne
 
-    def _forward_loss_backward_part(self, part, cfg, B, x, features, target, ws, pred, dpred, deep):
+    def _frames_buffer(self, B, Fr, P):
+        key = ("frames", B, Fr, P)
+        buf = self._scratch.get(key)
+        if buf is None:
+            buf = self._scratch[key] = torch.empty((B, Fr, P, P), dtype=torch.float32, device=self.model._flat.device)
+        return buf
+
+    def _fused_step_call(self, cfg, B, x, src, features, target, ws, pred, dpred, deep, apply_update):
+        """ONE C-ABI call: forward, MSE, backward (+ AdamW) -- mivit_vit_train_step or its from-trajectories twin."""
+        model = self.model
+        L = _lib.lib()
+        tail = (_lib.ptr(features), _lib.ptr(target), _lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m),
+                _lib.ptr(self.v), _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None, _lib.ptr(ws),
+                _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, self.step_count, int(apply_update), _lib.current_stream())
+        if src is not None:
+            return _lib.check(L.mivit_vit_train_step_traj(ctypes.byref(cfg), B, *src.args(), *tail))
+        return _lib.check(L.mivit_vit_train_step(ctypes.byref(cfg), B, _lib.ptr(x), *tail))
+
+    def _forward_loss_backward_part(self, part, cfg, B, x, src, features, target, ws, pred, dpred, deep):
         """part 1: forward, MSE, backward of everything but the image embedding; part 2: backward of the image embedding;
         part 0: forward, MSE and the whole backward."""
         model = self.model
         L = _lib.lib()
         st = _lib.current_stream()
+        rows = pred.shape[0]
+        bn = (_lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None)
         if part != 2:
-            _lib.check(L.mivit_vit_forward(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(model._flat),
-                                           _lib.ptr(model._bn_flat) if deep else None, _lib.ptr(model._bn_nbt) if deep else None,
-                                           _lib.ptr(ws), _lib.ptr(pred), 1, st))
-            _lib.check(L.mivit_mse_loss(_lib.ptr(pred), _lib.ptr(target), B, _lib.ptr(self.loss), _lib.ptr(dpred), st))
-        _lib.check(L.mivit_vit_backward_part(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(dpred),
-                                             _lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(ws), part, st))
+            if src is not None:
+                _lib.check(L.mivit_vit_forward_traj(ctypes.byref(cfg), B, *src.args(), _lib.ptr(features), _lib.ptr(model._flat),
+                                                    bn[0], bn[1], _lib.ptr(ws), _lib.ptr(pred), 1, st))
+            else:
+                _lib.check(L.mivit_vit_forward(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(model._flat),
+                                               bn[0], bn[1], _lib.ptr(ws), _lib.ptr(pred), 1, st))
+            _lib.check(L.mivit_mse_loss(_lib.ptr(pred), _lib.ptr(target), rows, _lib.ptr(self.loss), _lib.ptr(dpred), st))
+        if src is not None:
+            _lib.check(L.mivit_vit_backward_traj(ctypes.byref(cfg), B, *src.args(), _lib.ptr(features), _lib.ptr(dpred),
+                                                 _lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(ws), part, st))
+        else:
+            _lib.check(L.mivit_vit_backward_part(ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(dpred),
+                                                 _lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(ws), part, st))
 
-    def _sync_bn_step(self, x, target, features, cfg, B, ws, pred, dpred):
+    def _sync_bn_step(self, x, src, target, features, cfg, B, ws, pred, dpred):
         """Training step with synchronised BatchNorm: the library calls back into `_allreduce_hook` 12 times per step (7 forward
         statistics, 5 backward sums); launched kernel by kernel (the collectives are not captured into a graph)."""
         model = self.model
@@ -181,16 +242,11 @@ class MiViTTrainer:
         self._hook_ws, self._hook_error = ws, None
         L.mivit_set_allreduce_hook(self._hook, None, self.world)
         try:
-            rc = L.mivit_vit_train_step(
-                ctypes.byref(cfg), B, _lib.ptr(x), _lib.ptr(features), _lib.ptr(target), _lib.ptr(model._flat),
-                _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v), _lib.ptr(model._bn_flat), _lib.ptr(model._bn_nbt),
-                _lib.ptr(ws), _lib.ptr(pred), _lib.ptr(self.loss), _lib.ptr(dpred), self.lr, self.betas[0], self.betas[1], self.eps,
-                self.weight_decay, self.step_count, 0, _lib.current_stream())
+            self._fused_step_call(cfg, B, x, src, features, target, ws, pred, dpred, True, 0)
         finally:
             L.mivit_set_allreduce_hook(_lib.ALLREDUCE_FN(), None, 1)
-        if self._hook_error is not None:
-            raise self._hook_error
-        _lib.check(rc)
+            if self._hook_error is not None:
+                raise self._hook_error
         model._gen += 1
         scale = allreduce_sum_(model._grad_flat[:model._n_params], self.group)
         _lib.check(L.mivit_adamw_step(_lib.ptr(model._flat), _lib.ptr(model._grad_flat), _lib.ptr(self.m), _lib.ptr(self.v),
@@ -199,7 +255,7 @@ class MiViTTrainer:
         self.last_pred = pred
         return self.loss
 
-    def _graph_entry(self, x, target, features, cfg, B, ws, pred, dpred, deep, overlap):
+    def _graph_entry(self, x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap):
         """CUDA graphs of forward + loss + backward for this batch shape: one graph, or two when the gradient all-reduce is
         overlapped (graph 1 ends where the non-embedding gradients are final, graph 2 is the image-embedding backward).
         Returns None on the first call of a shape: that step runs kernel by kernel -- it also performs every lazy
@@ -210,7 +266,8 @@ class MiViTTrainer:
             # graph points into the old buffers
             self._graphs.clear()
             self._graph_ws, self._graph_flat = ws, model._flat
-        key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), bool(overlap))
+        key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), bool(overlap),
+               None if src is None else (src.T, bytes(src.prm), src.seed), pred.shape[0])   # render scalars are captured by value
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "pending"
@@ -219,6 +276,10 @@ class MiViTTrainer:
         if ent == "pending":
             gx, gt = (torch.empty_like(x) if x is not None else None), torch.empty_like(target)
             gf = torch.empty_like(features) if features is not None else None
+            gsrc = None
+            if src is not None:
+                gsrc = TrajectorySource(torch.empty_like(src.traj), src.prm, src.seed, 0,
+                                        torch.zeros(1, dtype=torch.int64, device=src.traj.device), src.frames)
             graphs, counts = [], []
             cap = torch.cuda.Stream()
             cap.wait_stream(torch.cuda.current_stream())
@@ -226,10 +287,10 @@ class MiViTTrainer:
                 n0 = L.mivit_launch_count()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=cap):
-                    self._forward_loss_backward_part(part, cfg, B, gx, gf, gt, ws, pred, dpred, deep)
+                    self._forward_loss_backward_part(part, cfg, B, gx, gsrc, gf, gt, ws, pred, dpred, deep)
                 n_cap = int(L.mivit_launch_count() - n0)
                 L.mivit_add_launch_count(-n_cap)          # capturing enqueued nothing: only replays count
                 graphs.append(g)
                 counts.append(n_cap)
-            ent = self._graphs[key] = (graphs, gx, gt, gf, counts)
+            ent = self._graphs[key] = (graphs, gx, gt, gf, counts, gsrc)
         return ent

@@ -13,9 +13,16 @@ What is kept from the reference, line by line:
     `validation_losses[name]["val_<D>" | "val_avg"]`;
   * `save_results` writes {"validation_losses", "all_labels", "model_weights": {name: state_dict}} with torch.save for the
     last five cycles (suffix = cycles remaining, :241-242) and at the end (:251) -- files load into the reference's models.
+ImagesFeatures variant (Experiments/ImagesFeatures/trainModelsImagesFeatures.py:155-203): when `render_fn` returns
+(videos, features) -- e.g. a wrapper of create_video_and_feature_pairs -- the features travel with the videos through the
+shuffle and every model is called the way that trainer calls it: "im_resnet" -> model(images), "ft_mlp" -> model(features),
+names without "ft" -> model(images, None), the rest -> model(images, features) (:187-199); validation sets are then
+(images, features, D) triples (make_prediction_tuple, :226).
 What changes: trajectories come from the device Brownian generator (`mivit_brownian`; the reference calls the third-party
 andi_datasets `models_phenom().single_state(N, L=0, T, Ds=[mean, var], alphas=1)`, statistically equivalent),
 the optimiser step is the fused `MiViTTrainer.train_step`, and everything stays on the GPU between rendering and training."""
+import inspect
+
 import numpy as np
 import torch
 
@@ -57,7 +64,10 @@ class _TorchTrainer:
     def train_step(self, x, target, features=None):
         self.model.train()
         self.opt.zero_grad()
-        out = self.model(x) if features is None else self.model(x, features)
+        if x is None:
+            out = self.model(features)
+        else:
+            out = self.model(x) if features is None else self.model(x, features)
         loss = self.criterion(out, target)
         loss.backward()
         self.opt.step()
@@ -71,40 +81,69 @@ class ExperimentLoop:
     def __init__(self, models, render_fn, make_prediction, val_sets, *, T, N=64, traj_div_factor=100, D_max_normalization=10,
                  TrainingDs_list=((1, 1), (3, 1), (5, 1), (7, 1), (9, 1), (10.2, 1)), adaptive_batch_size=20, shuffle=True,
                  lr=1e-4, step_size=5, gamma=0.9, seed=0, results_prefix="training_results_PSFNoise"):
-        """models: {name: GeneralTransformer / ModularTransformer of this package (fused CUDA trainer) or any other nn.Module,
-        e.g. the reference's MultiImageResNet baseline (stock PyTorch trainer)}; render_fn(trajs numpy (n,T,2)) -> images (numpy or CUDA tensor) with the
-        sequence axis first; make_prediction(model, name, images) -> predictions (the settings files' function, e.g.
-        images[:, psf, noise] for PSFNoise); val_sets: [(images, D_value), ...] rendered once (load_validation_data)."""
+        """models: {name: GeneralTransformer / ModularTransformer / CNN baseline of this package (fused CUDA trainers) or any other
+        nn.Module (stock PyTorch trainer)}; render_fn(trajs numpy (n,T,2)[, seq_offset=global id of trajs[0]][, seed=...]) -> images
+        (numpy or CUDA tensor, sequence axis first) or (images, features); make_prediction(model, name, images[, features]) ->
+        predictions (the settings files' function, e.g. images[:, psf, noise] for PSFNoise); val_sets: [(images, D_value), ...] or
+        [(images, features, D_value), ...] rendered once (load_validation_data).
+        Noise streams: the renderer keys them by (seed, global sequence id); render_fn is handed the global id of its first
+        trajectory (and the loop's seed) whenever its signature accepts `seq_offset` (`seed`), so every D group and every cycle
+        draws fresh noise like the reference does -- a render_fn that takes neither must vary its seed itself."""
         self.models, self.render_fn, self.make_prediction = models, render_fn, make_prediction
-        self.val_sets = [(torch.as_tensor(v).float().cuda(), float(d)) for v, d in val_sets]
+        self.val_sets = []
+        for vs in val_sets:
+            feats = torch.as_tensor(vs[1]).float().cuda() if len(vs) == 3 else None
+            self.val_sets.append((torch.as_tensor(vs[0]).float().cuda(), feats, float(vs[-1])))
+        try:
+            prm = inspect.signature(render_fn).parameters
+            anykw = any(p.kind == p.VAR_KEYWORD for p in prm.values())
+            self._render_kw = {k for k in ("seq_offset", "seed") if anykw or k in prm}
+        except (TypeError, ValueError):
+            self._render_kw = set()
         self.T, self.N, self.div, self.Dmax = int(T), int(N), float(traj_div_factor), float(D_max_normalization)
         self.groups = [list(g) for g in TrainingDs_list]
         self.adaptive, self.shuffle, self.seed = int(adaptive_batch_size), bool(shuffle), int(seed)
         self.batch_size = 1 if self.adaptive != -1 else 16
-        self.trainers = {n: (MiViTTrainer(m, lr=lr, step_size=step_size, gamma=gamma) if isinstance(m, _CudaViT)
-                             else _TorchTrainer(m, lr=lr, step_size=step_size, gamma=gamma)) for n, m in models.items()}
-        self.validation_losses = {n: dict({f"val_{d}": [] for _, d in self.val_sets}, val_avg=[]) for n in models}
+        self.trainers = {n: self._make_trainer(m, lr, step_size, gamma) for n, m in models.items()}
+        self.validation_losses = {n: dict({f"val_{d}": [] for _, _, d in self.val_sets}, val_avg=[]) for n in models}
         self.all_gen_labels = np.array([])
         self.prefix = results_prefix
         self._generated = 0
         self._gen = torch.Generator(device="cuda").manual_seed(self.seed)
 
+    @staticmethod
+    def _make_trainer(m, lr, step_size, gamma):
+        if isinstance(m, _CudaViT):
+            return MiViTTrainer(m, lr=lr, step_size=step_size, gamma=gamma)
+        return _TorchTrainer(m, lr=lr, step_size=step_size, gamma=gamma)
+
     # -- one dataset refresh (:121-173) ---------------------------------------------------------------------------
     def generate(self):
-        videos, labels = [], []
+        videos, feats, labels = [], [], []
         for g in self.groups:
             n = self.N if g[0] != 10.2 else self.N // 2
-            trajs, D = single_state(n, self.T, g, seed=self.seed, seq_offset=self._generated)
+            first_id = self._generated
+            trajs, D = single_state(n, self.T, g, seed=self.seed, seq_offset=first_id)
             self._generated += n
             self.all_gen_labels = np.append(self.all_gen_labels, D)
-            videos.append(torch.as_tensor(self.render_fn(trajs / self.div)).float().cuda())
+            kw = {}
+            if "seq_offset" in self._render_kw:
+                kw["seq_offset"] = first_id
+            if "seed" in self._render_kw:
+                kw["seed"] = self.seed
+            out = self.render_fn(trajs / self.div, **kw)
+            if isinstance(out, (tuple, list)):                 # ImagesFeatures: (videos, features[, ...])
+                feats.append(torch.as_tensor(out[1]).float().cuda())
+                out = out[0]
+            videos.append(torch.as_tensor(out).float().cuda())
             labels.append(torch.from_numpy(D / self.Dmax))
-        return torch.cat(videos, 0), torch.cat(labels, 0).float().unsqueeze(-1).cuda()
+        return (torch.cat(videos, 0), torch.cat(feats, 0) if feats else None,
+                torch.cat(labels, 0).float().unsqueeze(-1).cuda())
 
     def train_cycle(self, cycle):
         if self.adaptive != -1 and cycle != 0 and cycle % self.adaptive == 0:
             self.batch_size *= 2
-        videos, labels = self.generate()
+        videos, feats, labels = self.generate()
         n = videos.shape[0]
         order = torch.randperm(n, device="cuda", generator=self._gen) if self.shuffle else torch.arange(n, device="cuda")
         last = {}
@@ -113,14 +152,21 @@ class ExperimentLoop:
             tr = self.trainers[name]
             for i in range(0, n, self.batch_size):
                 idx = order[i:i + self.batch_size]
-                x = self._select(model, name, videos[idx])
-                last[name] = tr.train_step(x, labels[idx])
+                x, f = self._select(model, name, videos[idx], feats[idx] if feats is not None else None)
+                last[name] = tr.train_step(x, labels[idx], f).clone()
             tr.scheduler_step()
         return {k: float(v.item()) for k, v in last.items()}
 
-    def _select(self, model, name, images):
-        """The settings files' make_prediction both slices the image stack and calls the model; the fused trainer needs the
-        slice only, so the model call is intercepted."""
+    def _select(self, model, name, images, features=None):
+        """What the model is called with.  Image-only experiments: the settings files' make_prediction both slices the image
+        stack and calls the model; the fused trainer needs the slice only, so the model call is intercepted.  With features
+        (ImagesFeatures) the trainer's own rule applies (trainModelsImagesFeatures.py:187-199)."""
+        if features is not None:
+            if name == "im_resnet":
+                return images.contiguous(), None
+            if name == "ft_mlp":
+                return None, features.contiguous()
+            return images.contiguous(), (features.contiguous() if "ft" in name else None)
         box = {}
 
         class _Probe:
@@ -132,16 +178,19 @@ class ExperimentLoop:
                 return self_inner
 
         self.make_prediction(_Probe(), name, images)
-        return box["x"].contiguous()
+        return box["x"].contiguous(), None
 
     def validate(self):
         for name, model in self.models.items():
             model.eval()
             with torch.no_grad():
                 losses = []
-                for vid, d in self.val_sets:
+                for vid, vfeat, d in self.val_sets:
                     label = torch.full((vid.shape[0], 1), d, device="cuda")
-                    pred = self.make_prediction(model, name, vid) * self.Dmax
+                    if vfeat is not None:
+                        pred = self.make_prediction(model, name, vid, vfeat) * self.Dmax
+                    else:
+                        pred = self.make_prediction(model, name, vid) * self.Dmax
                     loss = torch.nn.functional.mse_loss(pred, label).item()
                     self.validation_losses[name][f"val_{d}"].append(loss)
                     losses.append(loss)

@@ -103,6 +103,59 @@ def poisson_from_uniform_words(lam, word_fn, max_rounds=64):
     return out.astype(F32)
 
 
+ALIAS_ENTRIES = 256
+ALIAS_MAX_LAMBDA = 380.0
+
+
+def poisson_alias_table(lam):
+    """Walker / Vose alias table of Poisson(lam) on k in [k0, k0 + 256): the float64 construction of csrc/render.cu
+    build_alias_table restated operation by operation (pmf by the recurrence p(k+1) = p(k) lam / (k+1) from the mode).
+    Returns (entries uint32[256] = alias << 24 | threshold(24 bit), k0) or None when lam is outside (0, 380]."""
+    lam = float(lam)
+    if not (lam > 0.0) or lam > ALIAS_MAX_LAMBDA:
+        return None
+    K = ALIAS_ENTRIES
+    mode = int(math.floor(lam))
+    k0 = mode - K // 2 if mode > K // 2 else 0
+    p = [0.0] * K
+    p[mode - k0] = 1.0
+    for k in range(mode, k0 + K - 1):
+        p[k + 1 - k0] = p[k - k0] * lam / float(k + 1)
+    for k in range(mode, k0, -1):
+        p[k - 1 - k0] = p[k - k0] * float(k) / lam
+    total = 0.0
+    for i in range(K):
+        total += p[i]
+    sc = [0.0] * K
+    prob = [1.0] * K
+    alias = list(range(K))
+    small, large = [], []
+    for i in range(K):
+        sc[i] = p[i] / total * float(K)
+        (small if sc[i] < 1.0 else large).append(i)
+    while small and large:
+        sm, lg = small.pop(), large.pop()
+        prob[sm] = sc[sm]
+        alias[sm] = lg
+        sc[lg] = (sc[lg] + sc[sm]) - 1.0
+        (small if sc[lg] < 1.0 else large).append(lg)
+    ent = np.zeros(K, dtype=np.uint32)
+    for i in range(K):
+        t = math.floor(prob[i] * 16777216.0 + 0.5)
+        t = min(max(t, 0.0), 16777215.0)
+        ent[i] = (alias[i] << 24) | int(t)
+    return ent, k0
+
+
+def alias_draw(table, words):
+    ent, k0 = table
+    words = np.asarray(words, dtype=np.uint32)
+    j = (words >> np.uint32(24)).astype(np.int64)
+    e = ent[j]
+    acc = (words & np.uint32(0xFFFFFF)) < (e & np.uint32(0xFFFFFF))
+    return (k0 + np.where(acc, j, (e >> np.uint32(24)).astype(np.int64))).astype(F32)
+
+
 class PhiloxNoise:
     """Counter streams of the CUDA renderer."""
 
@@ -139,6 +192,42 @@ class PhiloxNoise:
 
         return z, poisson
 
+    def pixel_v1(self, seq, F, P, lam):
+        """"Pair" layout of the V1 renderer (csrc/philox.cuh): one Philox block per pair of horizontally adjacent pixels --
+        words x,y -> the two background normals (Box-Muller, angle in (-pi, pi]), words z,w -> the two Poisson(lam) draws
+        through the alias table (PTRS on the pixel's own blocks >= 1 when lam > 380).  Returns (z[F,P,P], k[F,P,P] or None)."""
+        ppr = (P + 1) // 2
+        pairs = ppr * P
+        item = np.arange(F * pairs, dtype=np.uint32)
+        w = self._words(item, np.uint32(0), np.uint32(seq), px.STREAM_PIXEL)
+        u = px.u01(w[0])
+        th = ((px.u01(w[1]) - F32(0.5)) * F32(6.2831853071795860)).astype(F32)
+        r = np.sqrt((F32(-1.3862943611198906) * np.log2(u).astype(F32)).astype(F32)).astype(F32)
+        zl, zr = (r * np.sin(th)).astype(F32), (r * np.cos(th)).astype(F32)
+        z = np.zeros((F, P, 2 * ppr), dtype=F32)
+        z[:, :, 0::2] = zl.reshape(F, P, ppr)
+        z[:, :, 1::2] = zr.reshape(F, P, ppr)
+        z = z[:, :, :P]
+        if lam is None or lam == -1:
+            return z, None
+        table = poisson_alias_table(lam)
+        if table is not None:
+            k = np.zeros((F, P, 2 * ppr), dtype=F32)
+            k[:, :, 0::2] = alias_draw(table, w[2]).reshape(F, P, ppr)
+            k[:, :, 1::2] = alias_draw(table, w[3]).reshape(F, P, ppr)
+            return z, k[:, :, :P]
+        pit = np.arange(F * P * P, dtype=np.uint32)
+        cache = {}
+
+        def word_fn(q):            # PixelStream with q starting at 2: blocks 1, 2, ... of item = pixel
+            blk = 1 + q // 4
+            if blk not in cache:
+                cache[blk] = self._words(pit, np.uint32(blk), np.uint32(seq), px.STREAM_PIXEL)
+            return cache[blk][q % 4]
+
+        k = poisson_from_uniform_words(np.full(F * P * P, lam, dtype=F32), word_fn)
+        return z, k.reshape(F, P, P)
+
 
 class NumpyNoise:
     """What the reference does: independent numpy draws (statistical parity only)."""
@@ -157,6 +246,12 @@ class NumpyNoise:
 
         return z, poisson
 
+    def pixel_v1(self, seq, F, P, lam):
+        z = self.rng.standard_normal((F, P, P)).astype(F32)
+        if lam is None or lam == -1:
+            return z, None
+        return z, self.rng.poisson(float(lam), (F, P, P)).astype(F32)
+
 
 class MeanNoise:
     """Every draw returns its mean: z = 0 and Poisson(lam) -> lam."""
@@ -169,3 +264,9 @@ class MeanNoise:
             return np.asarray(lam, dtype=F32)
 
         return np.zeros(n_pixels, dtype=F32), poisson
+
+    def pixel_v1(self, seq, F, P, lam):
+        z = np.zeros((F, P, P), dtype=F32)
+        if lam is None or lam == -1:
+            return z, None
+        return z, np.full((F, P, P), lam, dtype=F32)

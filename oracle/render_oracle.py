@@ -162,8 +162,7 @@ def render_v1(traj, n, center, image_props, noise=None, seq_offset=0, mode="sepa
     for s in range(N):
         seq = seq_offset + s
         zI = noise.intensity_z(seq, F * n).reshape(F, n)
-        zb, poisson = noise.pixel(seq, F * P * P)
-        zb = zb.reshape(F, P, P)
+        zb, kpois = noise.pixel_v1(seq, F, P, prm["poisson"])
         for f in range(F):
             xs, ys = _frame_centres(tr[s], f, n, center, U)
             if draw:
@@ -175,8 +174,7 @@ def render_v1(traj, n, center, image_props, noise=None, seq_offset=0, mode="sepa
             out[s, f] = (lr + bg).astype(F32)
         if prm["poisson"] != -1:                                                  # :316-317 (multiplicative)
             pn = F32(prm["poisson"])
-            k = poisson(np.full((F, P, P), pn, dtype=F32))
-            out[s] = ((out[s] * k).astype(F32) / pn).astype(F32)
+            out[s] = ((out[s] * kpois).astype(F32) * (F32(1.0) / pn)).astype(F32)
     return out
 
 
