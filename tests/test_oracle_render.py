@@ -148,6 +148,71 @@ def test_poisson_sampler_chi_square():
     assert abs(k.var() / 1.5e6 - 1) < 0.03
 
 
+def test_alias_table_matches_the_library_and_the_poisson_pmf():
+    """V1 renderer noise (round 2): one uniform word per pixel through a 256-entry alias table.  The numpy restatement of the
+    table must equal the C library's (host-only entry point, no GPU) bit for bit, and draws from it must follow Poisson(lam)."""
+    import ctypes
+    from scipy import stats
+    from moleculardiffusion_mivit_b200 import _lib
+    from oracle.noise import alias_draw, poisson_alias_table
+    L = _lib.lib()
+    rng = np.random.default_rng(9)
+    for lam in (100.0, 0.3, 5.0, 50.0, 129.0, 150.5, 379.9):
+        ent, k0 = (ctypes.c_uint32 * 256)(), ctypes.c_int32()
+        assert L.mivit_poisson_alias_table(lam, ent, ctypes.byref(k0)) == 0
+        tab = poisson_alias_table(lam)
+        assert np.array_equal(np.frombuffer(ent, dtype=np.uint32), tab[0]) and k0.value == tab[1], lam
+        n = 400000
+        k = alias_draw(tab, rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)).astype(np.int64)
+        lo, hi = int(stats.poisson.ppf(1e-4, lam)), int(stats.poisson.ppf(1 - 1e-4, lam))
+        obs = np.array([(k == i).sum() for i in range(lo, hi + 1)], dtype=np.float64)
+        exp = stats.poisson.pmf(np.arange(lo, hi + 1), lam) * n
+        keep = exp > 20
+        chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+        assert chi2 < stats.chi2.ppf(1 - 1e-4, max(keep.sum() - 1, 1)), (lam, chi2)
+    ent, k0 = (ctypes.c_uint32 * 256)(), ctypes.c_int32()
+    assert L.mivit_poisson_alias_table(500.0, ent, ctypes.byref(k0)) != 0 and poisson_alias_table(500.0) is None   # PTRS regime
+    assert poisson_alias_table(-1.0) is None
+    # exact table mass: sum over entries of the accept / alias probabilities reproduces the pmf to the 2^-24 quantisation
+    ent_np, k0v = poisson_alias_table(100.0)
+    pm = np.zeros(256)
+    thr = (ent_np & 0xFFFFFF).astype(np.float64) / 2.0 ** 24
+    np.add.at(pm, np.arange(256), thr / 256)
+    np.add.at(pm, (ent_np >> 24).astype(np.int64), (1 - thr) / 256)
+    assert np.abs(pm - stats.poisson.pmf(k0v + np.arange(256), 100.0)).max() < 1e-7
+
+
+def test_pair_layout_streams_are_independent_normals_and_poissons():
+    """PhiloxNoise.pixel_v1: every pixel gets its own normal and its own Poisson draw (no value shared inside a pair), also when
+    P is odd (the last pair of a row has one pixel) and in the PTRS regime (lam > 380)."""
+    z, k = PhiloxNoise(3).pixel_v1(7, 40, 13, 100.0)
+    assert z.shape == k.shape == (40, 13, 13)
+    assert abs(z.mean()) < 0.03 and abs(z.std() - 1) < 0.03
+    assert abs(np.corrcoef(z[:, :, 0:12:2].ravel(), z[:, :, 1:13:2].ravel())[0, 1]) < 0.04     # left / right of a pair
+    assert abs(k.mean() - 100) < 0.4 and abs(k.var() / 100 - 1) < 0.06
+    assert abs(np.corrcoef(k[:, :, 0:12:2].ravel(), k[:, :, 1:13:2].ravel())[0, 1]) < 0.04
+    assert abs(np.corrcoef(z.ravel(), k.ravel())[0, 1]) < 0.04
+    z2, k2 = PhiloxNoise(3).pixel_v1(7, 6, 9, 1000.0)
+    assert abs(k2.mean() - 1000) < 8 and abs(k2.var() / 1000 - 1) < 0.2
+    z3, k3 = PhiloxNoise(3).pixel_v1(7, 6, 9, -1)
+    assert k3 is None and z3.shape == (6, 9, 9)
+
+
+@pytest.mark.parametrize("source", ["philox", "numpy"])
+def test_noisy_p13_framerate_statistics(golden_dir, gold, source):
+    """The props bench.py renders (Framerate experiment, P = 13, n = 10): moments, per-pixel means and KS against statistics of
+    the reference's own np.random path (oracle/make_golden_r2.py)."""
+    inp, _, _ = gold
+    st = np.load(os.path.join(golden_dir, "render_noise_stats_p13.npz"))
+    outs = [ro.render_v1(inp["traj30"], 10, True, FRAMERATE_PROPS, noise=PhiloxNoise(2000 + r) if source == "philox" else NumpyNoise(50 + r))
+            for r in range(4)]
+    v = np.stack(outs).astype(np.float64)
+    assert abs(v.mean() - st["mean"]) / st["mean"] < 3e-3
+    assert abs(v.std() - st["std"]) / st["std"] < 1e-2
+    assert np.abs(v.mean(axis=(0, 1, 2)) - st["pix_mean"]).max() / st["pix_mean"].max() < 1.5e-2
+    assert _ks_from_quantiles(v, st["quantiles"]) < 0.01
+
+
 @pytest.mark.skipif(not refshim.reference_available(), reason="reference checkout not present")
 def test_against_live_reference(gold):
     inp, g, _ = gold

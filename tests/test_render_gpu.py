@@ -115,6 +115,40 @@ def test_noisy_v1_statistics_vs_reference(gold, gen):
     assert ks < 5e-3, ks
 
 
+def test_noisy_p13_framerate_statistics_vs_reference(golden_dir, gold, gen):
+    """The props bench.py renders (Framerate experiment, P = 13, n = 10): first / second moments, per-pixel maps and the KS
+    statistic of the CUDA renderer against the reference's own np.random statistics (oracle/make_golden_r2.py)."""
+    inp, _, _ = gold
+    st = np.load(os.path.join(golden_dir, "render_noise_stats_p13.npz"))
+    v = np.stack([gen.trajectories_to_video(inp["traj30"].copy(), 10, True, FRAMERATE_PROPS, seed=900 + r)
+                  for r in range(24)]).astype(np.float64)
+    assert abs(v.mean() - st["mean"]) / st["mean"] < 2e-3
+    assert abs(v.std() - st["std"]) / st["std"] < 5e-3
+    assert np.abs(v.mean(axis=(0, 1, 2)) - st["pix_mean"]).max() / st["pix_mean"].max() < 6e-3
+    assert np.abs(v.std(axis=(0, 1, 2)) / st["pix_std"] - 1).max() < 8e-2
+    q = np.linspace(0, 1, len(st["quantiles"]))
+    srt = np.sort(v.ravel())
+    ks = np.abs(np.searchsorted(srt, st["quantiles"], side="right") / srt.size - q).max()
+    assert ks < 5e-3, ks
+    orc = ro.render_v1(inp["traj30"][:2], 10, True, FRAMERATE_PROPS, noise=PhiloxNoise(900))
+    out = gen.trajectories_to_video(inp["traj30"][:2].copy(), 10, True, FRAMERATE_PROPS, seed=900)
+    bad = np.abs(out - orc) > 1e-4 * np.abs(orc) + 1e-2
+    assert bad.mean() < 2e-3, bad.mean()                                  # odd P: the last pair of every row holds one pixel
+
+
+def test_large_lambda_falls_back_to_ptrs(gold, gen):
+    """poisson_noise > 380 is outside the alias table: PTRS on the pixel's own uniform stream, same draws as the oracle."""
+    inp, _, _ = gold
+    props = dict(C3_PROPS, poisson_noise=1000)
+    out = gen.trajectories_to_video(inp["traj30"][:2].copy(), 10, True, props, seed=31)
+    orc = ro.render_v1(inp["traj30"][:2], 10, True, props, noise=PhiloxNoise(31))
+    bad = np.abs(out - orc) > 1e-4 * np.abs(orc) + 1e-2
+    assert bad.mean() < 3e-3, bad.mean()
+    clean = gen.trajectories_to_video(inp["traj30"][:2].copy(), 10, True, dict(props, poisson_noise=-1), seed=31)
+    r = (out / clean).ravel()
+    assert abs(r.mean() - 1) < 2e-3 and abs(r.std() - 1 / np.sqrt(1000)) < 2e-3
+
+
 def test_psfnoise(gold, exp):
     inp, g, st = gold
     t = inp["traj20"][:1]
@@ -226,6 +260,36 @@ def test_fused_render_embed_matches_render_then_embed(gold, gen, kind, P, E, n, 
     only = gen.trajectories_to_embeddings(inp["traj30"][:6].copy(), n, emb_mod, True, props, seed=11, normalize=norm,
                                           _mean_noise=not noisy)
     assert torch.equal(only, emb)                                            # frames_out = NULL path
+
+
+@pytest.mark.parametrize("P,E,n,noisy", [(9, 64, 10, True), (13, 64, 10, True), (13, 128, 10, False), (7, 32, 15, True), (15, 39, 30, True)])
+def test_fused_embed_weight_gradient_rerenders_identical_frames(gold, gen, P, E, n, noisy):
+    """mivit_render_embed_linear_wgrad: dW = sum_frames demb (x) frame and db = sum_frames demb with the frames re-rendered inside
+    the kernel, against the same products formed from the frames the forward kernel can write out."""
+    import ctypes
+    import torch
+    from moleculardiffusion_mivit_b200 import _lib, models as M
+    from moleculardiffusion_mivit_b200.helpersGeneration import derive_render_params
+    inp, _, _ = gold
+    props = dict(C3_PROPS if noisy else CLEAN, output_size=P)
+    emb_mod = M.LinearProjectionEmbedding(P, E)
+    t = inp["traj30"].copy()
+    emb, frames = gen.trajectories_to_embeddings(t, n, emb_mod, True, props, seed=77, seq_offset=3, normalize=(1420, 290, 6000),
+                                                 return_frames=True, _mean_noise=not noisy)
+    N, Fr = frames.shape[0], frames.shape[1]
+    demb = torch.randn(N, Fr, E, generator=torch.Generator().manual_seed(4)).cuda()
+    prm = derive_render_params(props, n, True)
+    prm.flip_y, prm.mean_noise = 0, int(not noisy)
+    prm.normalize, prm.norm_sub, prm.norm_div = 1, 1130.0, 4870.0
+    tdev = torch.from_numpy(t).cuda()                                     # already flipped by the call above
+    dW = torch.zeros(E, P * P, device="cuda")
+    db = torch.zeros(E, device="cuda")
+    _lib.check(_lib.lib().mivit_render_embed_linear_wgrad(_lib.ptr(tdev), N, 300, ctypes.byref(prm), 77, 3, _lib.ptr(demb), E,
+                                                          _lib.ptr(dW), _lib.ptr(db), _lib.current_stream()))
+    ref_dW = demb.double().reshape(-1, E).t() @ frames.double().reshape(-1, P * P)
+    ref_db = demb.double().sum(dim=(0, 1))
+    assert (dW.double() - ref_dW).abs().max().item() < 2e-5 * ref_dW.abs().max().item()
+    assert (db.double() - ref_db).abs().max().item() < 2e-5 * ref_db.abs().max().item()
 
 
 def test_fused_render_embed_rejects_deepresnet(gen, gold):

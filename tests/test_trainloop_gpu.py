@@ -91,3 +91,45 @@ def test_loop_trains_a_foreign_cnn_baseline_beside_the_vit(golden_dir, tmp_path)
     losses = loop.run(1, save=False)
     assert set(losses) == {"tr_0_0", "res_0_0"} and len(losses["res_0_0"]["val_avg"]) == 1
     assert not torch.equal(w0, models["res_0_0"].fc.weight.detach())
+
+
+def test_cycles_draw_fresh_noise_and_features_travel_with_the_videos(golden_dir, tmp_path):
+    """(1) render_fn is handed the global id of its first trajectory, so the noise streams differ between D groups and cycles even
+    with a fixed seed (the reference draws fresh np.random noise every cycle); (2) the ImagesFeatures loop
+    (trainModelsImagesFeatures.py:155-203): render_fn returns (videos, features), models whose name contains "ft" get the
+    features, the others None; validation sets are (images, features, D) triples."""
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M, helpersGeneration as G, trainloop as TL
+    props = {"particle_intensity": [4580, 500], "NA": 1.46, "wavelength": 500e-9, "psf_division_factor": 1.3, "resolution": 100e-9,
+             "output_size": 9, "upsampling_factor": 5, "background_intensity": [1420, 290], "poisson_noise": 100, "trajectory_unit": 1200}
+    seen = []
+
+    def render(trajs, seq_offset=0, seed=None):
+        vids = G.trajectories_to_video(trajs.copy(), 10, True, props, seed=seed, seq_offset=seq_offset, normalize=(1420, 290, 6000))
+        feats = G.create_video_and_feature_pairs(trajs.copy(), 10, True, props, dt=1.0, seed=seed)[1]
+        feats = np.nan_to_num(feats, nan=0.0, posinf=0.0, neginf=0.0)
+        seen.append((seq_offset, vids.copy()))
+        return vids, feats
+
+    def make_prediction(model, name, images, features, *a, **k):          # trainSettingsImagesFeatures.py:303-341
+        with torch.no_grad():
+            return model(images, features if "ft" in name else None)
+
+    torch.manual_seed(0)
+    mk = lambda ft: M.GeneralTransformer(M.LinearProjectionEmbedding, {"patch_size": 9, "embed_dim": 32}, 32, 2, 64, 2, M.MLPHead, F.relu,
+                                         0.0, False, True, True, ft, "late", 25 if ft else None).cuda()
+    models = {"im_tr": mk(False), "im_ft_late_tr": mk(True)}
+    inp = np.load(os.path.join(golden_dir, "render_inputs.npz"))["traj30"]
+    v0, f0 = render(inp[:3].copy(), seq_offset=10 ** 6, seed=1)
+    seen.clear()
+    loop = TL.ExperimentLoop(models, render, make_prediction, [(v0, f0, 7.0)], T=300, N=4, TrainingDs_list=[[3, 1], [7, 1]],
+                             adaptive_batch_size=-1, seed=1, results_prefix=str(tmp_path / "res"))
+    w0 = models["im_ft_late_tr"].state_dict()["feature_projector.0.weight"].clone()
+    losses = loop.run(2, save=False)
+    assert [s for s, _ in seen] == [0, 4, 8, 12]                          # global ids: 2 groups x 2 cycles x N = 4
+    assert not np.array_equal(seen[0][1], seen[2][1])                     # cycle 2 sees new trajectories AND new noise
+    bg = [v[:, :, 0, 0] for _, v in seen]                                 # a corner pixel is background + noise only
+    assert not np.allclose(bg[0], bg[2]) and not np.allclose(bg[0], bg[1])
+    assert set(losses) == {"im_tr", "im_ft_late_tr"} and len(losses["im_tr"]["val_7.0"]) == 2
+    assert not torch.equal(w0, models["im_ft_late_tr"].state_dict()["feature_projector.0.weight"])   # the features were used

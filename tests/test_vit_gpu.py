@@ -279,7 +279,7 @@ def build_modular(name):
     act = {"relu": F.relu, "gelu": F.gelu}[c["activation"]]
     return M.ModularTransformer(
         c["embed_dim"], c["num_heads"], c["hidden_dim"], c["num_layers"], M.MLPHead(input_dim=c["embed_dim"]), act, 0.0,
-        c["use_pos_encoding"], c["use_regression_token"], True, c["mode"], emb,
+        c["use_pos_encoding"], c["use_regression_token"], c.get("single_prediction", True), c["mode"], emb,
         {"patch_size": 9, "embed_dim": c["embed_dim"]} if emb is not None else None, c.get("features_dim"),
         c.get("feature_embedding_type", "linear"), c.get("fusion_method", "add"))
 
@@ -395,3 +395,178 @@ def test_edge_sizes_long_sequences_single_sample_and_empty_render():
         model(torch.randn(1, 128, 9, 9).cuda())          # 129 tokens > MAX_TOKENS
     out = trajectories_to_video(np.zeros((0, 300, 2)), 10, True, {"output_size": 9})
     assert out.shape == (0, 30, 9, 9) and out.dtype == np.float32
+
+
+# ------------------------------------------------------------------ round 2: product shapes, curves, per-frame, trajectories ----
+BENCH_PROPS = {"particle_intensity": [4580, 500], "NA": 1.46, "wavelength": 500e-9, "psf_division_factor": 1.3, "resolution": 100e-9,
+               "output_size": 13, "upsampling_factor": 5, "background_intensity": [1420, 290], "poisson_noise": 100,
+               "trajectory_unit": 1200}
+
+
+def _bench_frames(B, P=13, Fr=30, seed=3):
+    """Frames of the bench.py workload: device Brownian trajectories (D groups of the training loops) rendered by the CUDA
+    renderer with the Framerate experiment's image_props, normalised."""
+    from moleculardiffusion_mivit_b200.helpersGeneration import brownian_motion, derive_render_params, render_device
+    traj, D = brownian_motion(B, Fr, 10, [1, 3, 5, 7, 9, 10.2], 1.0, seed=seed, D_var=1.0, div=100.0, return_device=True, return_D=True)
+    prm = derive_render_params(dict(BENCH_PROPS, output_size=P), 10, True)
+    prm.normalize, prm.norm_sub, prm.norm_div = 1, 1420.0 - 290.0, 6000.0 - 1130.0
+    return render_device(traj, prm, seed=seed), (D / 10.0).view(-1, 1)
+
+
+def _deep_model(P, feat=None, seed=1):
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    torch.manual_seed(seed)
+    model = M.GeneralTransformer(M.DeepResNetEmbedding, {"patch_size": P, "embed_dim": 64}, 64, 4, 128, 6, M.MLPHead, F.relu, 0.0,
+                                 False, True, True, feat is not None, feat or "early", 25 if feat else None)
+    cfg = dict(embedding="deepresnet", embed_dim=64, num_heads=4, num_layers=6, activation="relu", use_pos_encoding=False,
+               use_regression_token=True, use_global_features=feat is not None, fusion_type=feat or "early")
+    return model, cfg, {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+
+
+def _check_against_oracle(model, cfg, sd, x, tgt, feats, ptol, gtol, emb_gtol=None):
+    import torch.nn.functional as F
+    model.cuda().train()
+    pred = model(x, feats) if feats is not None else model(x)
+    loss = F.mse_loss(pred, tgt)
+    loss.backward()
+    ref_pred, ref_loss, ref_g, _ = vo.loss_and_grads(sd, cfg, x.cpu(), tgt.cpu(), feats.cpu() if feats is not None else None)
+    assert (pred.cpu() - ref_pred).abs().max().item() < ptol * max(1.0, ref_pred.abs().max().item())
+    assert abs(loss.item() - float(ref_loss)) < ptol * max(1.0, float(ref_loss))
+    gmax = max(float(v.norm()) for v in ref_g.values())
+    worst = {}
+    for k, p in model.named_parameters():
+        r = ref_g[k]
+        if float(r.norm()) < 1e-4 * gmax:
+            assert float(p.grad.cpu().norm()) < 2e-3 * gmax, k
+            continue
+        e = relnorm(p.grad.cpu(), r)
+        grp = "embedding" if k.startswith("embedding.") else "rest"
+        if e > worst.get(grp, ("", 0.0))[1]:
+            worst[grp] = (k, e)
+    assert worst.get("rest", ("", 0.0))[1] < gtol, worst
+    assert worst.get("embedding", ("", 0.0))[1] < (emb_gtol or gtol), worst
+    return worst
+
+
+@pytest.mark.parametrize("feat", [None, "early", "late"])
+def test_product_shape_B32_matches_oracle(feat):
+    """deepcnn_n at P=13, F=30, B=32 (992 tokens >= 512): the tf32 tcgen05 nn.Linear kernels, the batched q/k/v launch, the ReLU-gate
+    dgrad, the CTA-pair 128->128 convolution with the BatchNorm-backward sums in its epilogue and multi-tile persistence are all
+    live and compared with the fp32 oracle -- also with the 25-feature early / late fusion of the ImagesFeatures experiment
+    (trainSettingsImagesFeatures.py:112-188)."""
+    import torch
+    model, cfg, sd = _deep_model(13, feat)
+    x, tgt = _bench_frames(32)
+    feats = torch.randn(32, 25, generator=torch.Generator().manual_seed(2)).cuda() if feat else None
+    _check_against_oracle(model, cfg, sd, x, tgt, feats, 3e-2, 5e-2, 8e-2)
+
+
+def test_bench_shape_B1024_matches_oracle():
+    """The bench.py shape itself (B = 1024 sequences of 30 frames of 13 x 13): forward, loss and every gradient against the fp32
+    oracle on the same rendered frames (the CPU oracle needs ~20-30 s on the box's cores)."""
+    model, cfg, sd = _deep_model(13)
+    x, tgt = _bench_frames(1024)
+    _check_against_oracle(model, cfg, sd, x, tgt, None, 3e-2, 5e-2, 8e-2)
+
+
+def test_thirty_step_training_curve_follows_oracle():
+    """30 AdamW steps on a fixed batch of 16 rendered sequences, CUDA trainer vs oracle/vit_oracle.train_step from shared weights:
+    the per-step loss stays within 2 % (+1e-4 absolute) of the oracle's the whole way."""
+    import torch
+    from moleculardiffusion_mivit_b200.training import MiViTTrainer
+    model, cfg, sd = _deep_model(9)
+    x, tgt = _bench_frames(16, P=9)
+    model.cuda().train()
+    tr = MiViTTrainer(model, lr=1e-3)
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    st = vo.new_opt_state(ref_sd)
+    xc, tc = x.cpu(), tgt.cpu()
+    mine, ref = [], []
+    for _ in range(30):
+        mine.append(tr.train_step(x, tgt).item())
+        ref.append(vo.train_step(ref_sd, st, cfg, xc, tc, None, lr=1e-3))
+    mine, ref = np.array(mine), np.array(ref)
+    assert ref[-1] < 0.5 * ref[0]                                        # it does train
+    assert np.all(np.abs(mine - ref) < 2e-2 * ref + 1e-4), (mine, ref)
+
+
+def test_eval_mode_backward_is_refused_and_single_prediction_flag_is_ignored(golden_dir):
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    z, sd, x, tgt, _ = load_case(golden_dir, "deepcnn_n")
+    # helpers/models.py:303 stores single_prediction and forward (:328-361) never reads it
+    model = M.GeneralTransformer(M.DeepResNetEmbedding, {"patch_size": 9, "embed_dim": 64}, 64, 4, 128, 6, M.MLPHead, F.relu, 0.0,
+                                 False, True, False)
+    assert model.single_prediction is False
+    model.load_state_dict(sd)
+    model.cuda().train()
+    ref = build("deepcnn_n")
+    ref.load_state_dict(sd)
+    ref.cuda().train()
+    assert torch.equal(model(x.cuda()), ref(x.cuda()))
+    model.eval()
+    with pytest.raises(NotImplementedError, match="eval"):
+        model(x.cuda())                                                   # grad enabled + eval-mode BatchNorm: no silent wrong gradients
+    with torch.no_grad():
+        assert model(x.cuda()).shape == (4, 1)
+
+
+@pytest.mark.parametrize("kind,P,E", [("linear", 9, 32), ("cnn", 13, 64), ("deepresnet", 9, 64)])
+def test_forward_and_train_step_from_trajectories(golden_dir, kind, P, E):
+    """north_star (1): `model(normalize_images(trajectories_to_video(trajs)))` as one call.  The fused path must give the prediction
+    and the gradients of render-then-model on the SAME noisy frames (identical Philox streams); for Linear / CNN embeddings the
+    embedding weight gradient comes from re-rendered frames.  Then the trainer's from-trajectories step (eager and CUDA-graph
+    replay with a device-side sequence counter) follows the render-then-train_step trainer step for step."""
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    from moleculardiffusion_mivit_b200.helpersGeneration import trajectories_to_video
+    from moleculardiffusion_mivit_b200.training import MiViTTrainer
+    inp = np.load(os.path.join(golden_dir, "render_inputs.npz"))["traj30"]
+    props = dict(BENCH_PROPS, output_size=P)
+    norm = (1420, 290, 6000)
+    cls = {"linear": M.LinearProjectionEmbedding, "cnn": M.CNNEmbedding, "deepresnet": M.DeepResNetEmbedding}[kind]
+
+    def make():
+        torch.manual_seed(P + E)
+        return M.GeneralTransformer(cls, {"patch_size": P, "embed_dim": E}, E, 4, 2 * E, 2, M.MLPHead, F.relu, 0.0, True, True, True).cuda().train()
+
+    tgt = torch.rand(8, 1, generator=torch.Generator().manual_seed(1)).cuda()
+    a, b = make(), make()
+    t1, t2 = inp.copy(), inp.copy()
+    frames = torch.from_numpy(trajectories_to_video(t1, 10, True, props, seed=21, seq_offset=40, normalize=norm)).cuda()
+    pa = a(frames)
+    F.mse_loss(pa, tgt).backward()
+    pb = b.forward_from_trajectories(t2, 10, True, props, seed=21, seq_offset=40, normalize=norm)
+    F.mse_loss(pb, tgt).backward()
+    assert np.array_equal(t1, t2) and np.array_equal(t1[:, :, 1], -inp[:, :, 1])          # same in-place y flip
+    assert (pa - pb).abs().max().item() < 1e-5 * max(1.0, pa.abs().max().item())
+    for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        n = float(p.grad.norm())
+        assert float((p.grad - q.grad).norm()) <= (2e-3 if kind == "deepresnet" else 2e-5) * max(n, 1e-6) + 1e-7, k
+    with pytest.raises(Exception, match="T is not divisble by posPerFrame"):
+        b.forward_from_trajectories(inp[:, :295].copy(), 10, True, props)
+    with pytest.raises(AssertionError, match="Patch size mismatch"):
+        b.forward_from_trajectories(inp.copy(), 10, True, dict(props, output_size=P + 2))
+    # trainer: render-then-step vs from-trajectories (eager, then graph replay), fresh noise every step through seq_offset
+    runs = []
+    for mode in ("frames", "traj", "traj_graph"):
+        m = make()
+        tr = MiViTTrainer(m, lr=1e-3, cuda_graph=(mode == "traj_graph"))
+        losses = []
+        for step in range(4):
+            t = inp.copy()
+            if mode == "frames":
+                fr = torch.from_numpy(trajectories_to_video(t, 10, True, props, seed=5, seq_offset=8 * step, normalize=norm)).cuda()
+                losses.append(tr.train_step(fr, tgt).item())
+            else:
+                src = m.trajectory_source(t, 10, True, props, seed=5, seq_offset=8 * step, normalize=norm)
+                losses.append(tr.train_step_from_trajectories(src, tgt).item())
+        runs.append(losses)
+    assert len(set(runs[0])) == 4                                         # different noise every step
+    tol = 2e-2 if kind == "deepresnet" else 1e-4
+    assert np.allclose(runs[0], runs[1], rtol=tol, atol=1e-6), runs
+    assert np.allclose(runs[0], runs[2], rtol=tol, atol=1e-6), runs

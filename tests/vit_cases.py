@@ -17,6 +17,13 @@ CASES = {
     "linear_s_feat_late": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="relu",
                                use_pos_encoding=False, use_regression_token=True, use_global_features=True,
                                fusion_type="late"),
+    # round 2 (oracle/make_golden_r2.py): the ImagesFeatures models (trainSettingsImagesFeatures.py:112-188) and F.leaky_relu
+    "deepcnn_n_feat_early": dict(embedding="deepresnet", embed_dim=64, num_heads=4, num_layers=6, activation="relu",
+                                 use_pos_encoding=False, use_regression_token=True, use_global_features=True, fusion_type="early"),
+    "deepcnn_n_feat_late": dict(embedding="deepresnet", embed_dim=64, num_heads=4, num_layers=6, activation="relu",
+                                use_pos_encoding=False, use_regression_token=True, use_global_features=True, fusion_type="late"),
+    "linear_s_leaky": dict(embedding="linear", embed_dim=32, num_heads=2, num_layers=3, activation="leaky_relu",
+                           use_pos_encoding=True, use_regression_token=True),
 }
 # ModularTransformer (helpers/models.py:366-593) goldens: tests/golden/vit_mod_*.npz (oracle/make_golden_modular.py)
 MODULAR_CASES = {
@@ -34,8 +41,13 @@ MODULAR_CASES = {
     "mod_both_concatfeat_cnn": dict(modular=True, mode="both", embedding="cnn", embed_dim=32, num_heads=2, num_layers=2,
                                     hidden_dim=64, activation="gelu", use_pos_encoding=False, use_regression_token=True,
                                     features_dim=7, feature_embedding_type="linear", fusion_method="concat_features"),
+    # per-frame outputs: no regression token, single_prediction=False (helpers/models.py:585-593); target / pred are [B, F, 1]
+    "mod_perframe": dict(modular=True, mode="images_only", embedding="linear", embed_dim=32, num_heads=2, num_layers=2,
+                         hidden_dim=64, activation="relu", use_pos_encoding=True, use_regression_token=False,
+                         single_prediction=False),
 }
-PARAM_COUNTS = {"deepcnn_n": 506081, "linear_s_pos": 36865}   # SURVEY.md section 4 (reference notebooks)
+PARAM_COUNTS = {"deepcnn_n": 506081, "linear_s_pos": 36865,    # SURVEY.md section 4 (reference notebooks)
+                "deepcnn_n_feat_early": 511905, "deepcnn_n_feat_late": 520097}
 
 
 def load_case(golden_dir, name):
