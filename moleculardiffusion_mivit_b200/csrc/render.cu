@@ -26,12 +26,12 @@ namespace {
 constexpr int kMaxVariants = 8;
 
 struct RenderDev {
-  double scale, ysign, inv2s2_d, step_d;
+  double scale, ysign, inv2s2_d, step_d, inv_step_d, inv_n;
   int P, U, n, center, draw, G, limit, T, F;
   float imean, istd;  // per-sub-position intensity mean/std (V1) or per-frame (PSFNoise)
   float bg_mean, bg_std, bg_hi, poisson;
   int normalize, mean_noise;
-  float norm_sub, norm_div;
+  float norm_sub, norm_div, inv_norm_div;
   float inv2s2, step;
   uint32_t k0, k1;
   unsigned long long seq_offset;
@@ -79,14 +79,15 @@ __device__ __forceinline__ void frame_centres(const RenderDev& d, const double* 
       mx += seg[2 * p] * d.scale;
       my += seg[2 * p + 1] * d.scale * d.ysign;
     }
-    mx /= (double)d.n;
-    my /= (double)d.n;
+    mx *= d.inv_n;   // (a reciprocal multiply instead of np.mean's division: 1 ulp of float64, no double-division subroutine)
+    my *= d.inv_n;
   }
   for (int p = lane; p < d.n; p += 32) {
     const double cx = (seg[2 * p] * d.scale - mx) * (double)d.U;
     const double cy = (seg[2 * p + 1] * d.scale * d.ysign - my) * (double)d.U;
-    int jx = (int)fmin(fmax(rint((cx + d.limit) / d.step_d), 0.0), (double)(d.G - 1));
-    int jy = (int)fmin(fmax(rint((cy + d.limit) / d.step_d), 0.0), (double)(d.G - 1));
+    // nearest grid node: any node gives a correct (node, offset) pair, the nearest one keeps the float32 offset small
+    int jx = (int)fmin(fmax(rint((cx + d.limit) * d.inv_step_d), 0.0), (double)(d.G - 1));
+    int jy = (int)fmin(fmax(rint((cy + d.limit) * d.inv_step_d), 0.0), (double)(d.G - 1));
     const double ox = cx - (-(double)d.limit + jx * d.step_d);
     const double oy = cy - (-(double)d.limit + jy * d.step_d);
     w.jc[p] = jx;
@@ -142,14 +143,27 @@ struct V1Noise {
   const float* ptab;
 };
 
+// Compile-time frame geometry of the common configurations (0 = read the value from RenderDev at run time): with P, U and n
+// known the table / pixel loops unroll, the index divisions vanish and shared-memory offsets become immediates.  ncu on the
+// first round-2 version (runtime geometry): 3270 warp instructions per 13 x 13 frame, a third of them address arithmetic.
+#define TU_OR(G, dflt) (G::kU ? G::kU : (dflt))
+template <int TP, int TU, int TN>
+struct Geo {
+  static constexpr int kU = TU;
+  __device__ __forceinline__ static int P(const RenderDev& d) { return TP ? TP : d.P; }
+  __device__ __forceinline__ static int U(const RenderDev& d) { return TU ? TU : d.U; }
+  __device__ __forceinline__ static int n(const RenderDev& d) { return TN ? TN : d.n; }
+};
+
 // spot intensities of the n sub-positions of frame f  (helpersGeneration.py:300)
+template <class G>
 __device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, int f, int lane, uint32_t seq) {
-  const int n = d.n;
+  const int n = G::n(d);
   for (int p = lane; p < n; p += 32) {
     float z = 0.0f, z1;
     if (!d.mean_noise) {
       const uint4 r = philox4x32_10((uint32_t)(f * n + p), 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
-      box_muller(r.x, r.y, z, z1);
+      box_muller_fast(r.x, r.y, z, z1);
     }
     float I = __fadd_rn(d.imean, __fmul_rn(d.istd, z));
     if ((double)w.msq[p] * d.inv2s2_d > 745.0) I = __int_as_float(0x7fc00000);  // spot underflows: NaN frame (:305-308)
@@ -159,8 +173,9 @@ __device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, 
 
 // axis table of the V1 kernels: tab[p][0][b] = block mean of the x profile, tab[p][1][a] = I_p * block mean of the y profile
 // (the intensity is folded into the row factor, so a pixel costs one FMA per sub-position); exps on the MUFU (ex2.approx)
+template <class G>
 __device__ __forceinline__ void axis_table_v1(const RenderDev& d, int lane, WarpSmem& w) {
-  const int P = d.P, U = d.U, n = d.n;
+  const int P = G::P(d), U = G::U(d), n = G::n(d);
   const int entries = 2 * n * P;
   const float c2 = -d.inv2s2 * 1.4426950408889634f;   // exp(-t/2s^2) = 2^(t * c2)
   const float invU = 1.0f / (float)U;
@@ -170,25 +185,34 @@ __device__ __forceinline__ void axis_table_v1(const RenderDev& d, int lane, Warp
     const int axis = r >= P ? 1 : 0;
     const int b = r - axis * P;
     const int idx = axis * n + p;
-    const int jc = w.jc[idx];
     const float twoc0 = 2.0f * w.c0[idx];
+    const float kb = (float)(b * U - w.jc[idx]) * d.step;
     float acc = 0.0f;
-    for (int u = 0; u < U; ++u) {
-      const float k = (float)(b * U + u - jc) * d.step;
+#pragma unroll
+    for (int u = 0; u < (TU_OR(G, 8)); ++u) {
+      if (u < U) {
+        const float k = kb + (float)u * d.step;
+        acc += fast_ex2(k * (k - twoc0) * c2);
+      }
+    }
+    for (int u = TU_OR(G, 8); u < U; ++u) {   // generic geometry with an upsampling factor beyond 8: rolled remainder
+      const float k = kb + (float)u * d.step;
       acc += fast_ex2(k * (k - twoc0) * c2);
     }
     acc *= invU;
     if (axis) acc *= w.inten[p];
-    w.tab[(p * 2 + axis) * P + b] = acc;
+    w.tab[e] = acc;                 // (p * 2 + axis) * P + b == e
   }
 }
 
 // One frame: every lane walks the frame's pixel PAIRS (row a, columns b0 = 2*pr, b0 + 1), computes signal + clipped Gaussian
 // background (:312-313), multiplicative Poisson (:316-317), fused normalisation (:395) and hands (pixel index, value) to `sink`.
-template <typename Sink>
+// No divergent branch on the one-pixel pair that ends a row of odd length: its second column index is clamped and only the
+// sink call is predicated.
+template <class G, typename Sink>
 __device__ __forceinline__ void v1_frame_pixels(const RenderDev& d, const WarpSmem& w, int f, int lane, uint32_t seq,
                                                 const V1Noise& nz, Sink&& sink) {
-  const int P = d.P, n = d.n;
+  const int P = G::P(d), n = G::n(d);
   const int ppr = (P + 1) >> 1;              // pairs per row
   const int pairs = ppr * P;
   const float inv_pn = d.poisson != -1.0f ? 1.0f / d.poisson : 1.0f;
@@ -197,17 +221,14 @@ __device__ __forceinline__ void v1_frame_pixels(const RenderDev& d, const WarpSm
     const bool two = b0 + 1 < P;
     float v0 = 0.0f, v1 = 0.0f;
     if (d.draw) {
-      const float* ty = w.tab + P + a;        // tab[p][1][a]
-      const float* tx = w.tab + b0;           // tab[p][0][b0]
-      if (two) {
-#pragma unroll 2
-        for (int p = 0; p < n; ++p) {
-          const float t = ty[p * 2 * P];
-          v0 = fmaf(t, tx[p * 2 * P], v0);
-          v1 = fmaf(t, tx[p * 2 * P + 1], v1);
-        }
-      } else {
-        for (int p = 0; p < n; ++p) v0 = fmaf(ty[p * 2 * P], tx[p * 2 * P], v0);
+      const float* ty = w.tab + P + a;                    // tab[p][1][a]
+      const float* tx0 = w.tab + b0;                      // tab[p][0][b0]
+      const float* tx1 = w.tab + (two ? b0 + 1 : b0);
+#pragma unroll 10
+      for (int p = 0; p < n; ++p) {
+        const float t = ty[p * 2 * P];
+        v0 = fmaf(t, tx0[p * 2 * P], v0);
+        v1 = fmaf(t, tx1[p * 2 * P], v1);
       }
     }
     float z0 = 0.0f, z1 = 0.0f, k0f = d.poisson, k1f = d.poisson;
@@ -230,7 +251,7 @@ __device__ __forceinline__ void v1_frame_pixels(const RenderDev& d, const WarpSm
     v0 += fminf(fmaxf(fmaf(d.bg_std, z0, d.bg_mean), 0.0f), d.bg_hi);
     v1 += fminf(fmaxf(fmaf(d.bg_std, z1, d.bg_mean), 0.0f), d.bg_hi);
     if (d.poisson != -1.0f) { v0 = v0 * k0f * inv_pn; v1 = v1 * k1f * inv_pn; }
-    if (d.normalize) { v0 = __fdiv_rn(__fsub_rn(v0, d.norm_sub), d.norm_div); v1 = __fdiv_rn(__fsub_rn(v1, d.norm_sub), d.norm_div); }
+    if (d.normalize) { v0 = (v0 - d.norm_sub) * d.inv_norm_div; v1 = (v1 - d.norm_sub) * d.inv_norm_div; }
     const int pix = a * P + b0;
     sink(pix, v0);
     if (two) sink(pix + 1, v1);
@@ -255,24 +276,27 @@ __device__ __forceinline__ V1Noise v1_noise_setup(const RenderDev& d, const Alia
   return nz;
 }
 
+template <class G>
 __device__ __forceinline__ void v1_frame_tables(const RenderDev& d, const double* __restrict__ traj, long long s, int f, int lane,
                                                 uint32_t seq, WarpSmem& w) {
   if (!d.draw) return;
   frame_centres(d, traj + (size_t)s * d.T * 2, f, lane, w);
   __syncwarp();
-  v1_intensities(d, w, f, lane, seq);
+  v1_intensities<G>(d, w, f, lane, seq);
   __syncwarp();
-  axis_table_v1(d, lane, w);
+  axis_table_v1<G>(d, lane, w);
   __syncwarp();
 }
 
+template <int TP, int TU, int TN>
 __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict__ traj, long long n_frames_total,
                                                         RenderDev d, const __grid_constant__ AliasTable at,
                                                         float* __restrict__ out) {
+  using G = Geo<TP, TU, TN>;
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
-  WarpSmem w = carve(smem + (size_t)warp * warp_smem_floats(d.n, d.P), d.n, d.P);
+  WarpSmem w = carve(smem + (size_t)warp * warp_smem_floats(G::n(d), G::P(d)), G::n(d), G::P(d));
   __shared__ float ptab[kPoissonTable];
   __shared__ uint32_t alias_s[kAliasEntries];
   const V1Noise nz = v1_noise_setup(d, at, alias_s, ptab);
@@ -282,9 +306,9 @@ __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict
   const long long s = gf / d.F;
   const int f = (int)(gf - s * d.F);
   const uint32_t seq = global_seq(d, s);
-  v1_frame_tables(d, traj, s, f, lane, seq, w);
-  float* dst = out + s * d.out_seq_stride + (long long)f * d.P * d.P;
-  v1_frame_pixels(d, w, f, lane, seq, nz, [&](int pix, float v) { dst[pix] = v; });
+  v1_frame_tables<G>(d, traj, s, f, lane, seq, w);
+  float* dst = out + s * d.out_seq_stride + (long long)f * G::P(d) * G::P(d);
+  v1_frame_pixels<G>(d, w, f, lane, seq, nz, [&](int pix, float v) { dst[pix] = v; });
 }
 
 // Renderer fused with the frame embedding of LinearProjectionEmbedding / CNNEmbedding (helpers/models.py:146-199:
@@ -292,15 +316,17 @@ __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict
 // [N,F,E] embeddings (and, optionally, the frames).  Persistent CTAs keep W^T ([P*P][E], so that lanes read consecutive
 // output features) resident in shared memory; w_transposed = 0 takes the nn.Linear layout [E][P*P] (the flat parameter
 // buffer of the ViT) and transposes while staging.
+template <int TP, int TU, int TN>
 __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* __restrict__ traj, long long n_frames_total,
                                                                   RenderDev d, const __grid_constant__ AliasTable at,
                                                                   const float* __restrict__ W, int w_transposed,
                                                                   const float* __restrict__ bias, int E,
                                                                   float* __restrict__ emb, float* __restrict__ frames_out) {
+  using G = Geo<TP, TU, TN>;
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
-  const int P = d.P, n = d.n, PP = d.P * d.P;
+  const int P = G::P(d), n = G::n(d), PP = P * P;
   float* wts = smem;                                       // [PP][E]
   const int per_warp = warp_smem_floats(n, P) + PP;
   float* mine = smem + (size_t)PP * E + (size_t)warp * per_warp;
@@ -319,9 +345,9 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
     const long long s = gf / d.F;
     const int f = (int)(gf - s * d.F);
     const uint32_t seq = global_seq(d, s);
-    v1_frame_tables(d, traj, s, f, lane, seq, w);
+    v1_frame_tables<G>(d, traj, s, f, lane, seq, w);
     float* fo = frames_out != nullptr ? frames_out + s * d.out_seq_stride + (long long)f * PP : nullptr;
-    v1_frame_pixels(d, w, f, lane, seq, nz, [&](int pix, float v) {
+    v1_frame_pixels<G>(d, w, f, lane, seq, nz, [&](int pix, float v) {
       px[pix] = v;
       if (fo != nullptr) fo[pix] = v;
     });
@@ -371,8 +397,8 @@ __global__ void __launch_bounds__(256) render_embed_wgrad_kernel(const double* _
       const long long s = gf / d.F;
       const int f = (int)(gf - s * d.F);
       const uint32_t seq = global_seq(d, s);
-      v1_frame_tables(d, traj, s, f, lane, seq, w);
-      v1_frame_pixels(d, w, f, lane, seq, nz, [&](int pix, float v) { px[pix] = v; });
+      v1_frame_tables<Geo<0, 0, 0>>(d, traj, s, f, lane, seq, w);
+      v1_frame_pixels<Geo<0, 0, 0>>(d, w, f, lane, seq, nz, [&](int pix, float v) { px[pix] = v; });
       for (int e = lane; e < E; e += 32) dsh[warp * E + e] = __ldg(demb + gf * E + e);
     } else {
       for (int pix = lane; pix < PP; pix += 32) px[pix] = 0.0f;
@@ -751,6 +777,8 @@ int fill_dev(const mivit_render_params* prm, int T, uint64_t seed, uint64_t seq_
   d.step_d = d.G > 1 ? 2.0 * d.limit / (double)(d.G - 1) : 1.0;
   if (d.step_d == 0.0) d.step_d = 1.0;
   d.step = (float)d.step_d;
+  d.inv_step_d = 1.0 / d.step_d;
+  d.inv_n = 1.0 / (double)prm->n;
   d.inv2s2_d = 1.0 / (2.0 * prm->sigma_hr * prm->sigma_hr);
   d.inv2s2 = (float)d.inv2s2_d;
   d.T = T; d.F = T / prm->n;
@@ -759,6 +787,7 @@ int fill_dev(const mivit_render_params* prm, int T, uint64_t seed, uint64_t seq_
   d.bg_hi = (float)((double)prm->bg_mean + 3.0 * (double)prm->bg_std);
   d.poisson = prm->poisson;
   d.normalize = prm->normalize; d.norm_sub = prm->norm_sub; d.norm_div = prm->norm_div;
+  d.inv_norm_div = prm->norm_div != 0.0f ? 1.0f / prm->norm_div : 0.0f;
   d.mean_noise = prm->mean_noise;
   d.k0 = (uint32_t)(seed & 0xFFFFFFFFull); d.k1 = (uint32_t)(seed >> 32);
   d.seq_offset = seq_offset;
@@ -799,13 +828,25 @@ int render_v1_launch(const double* traj, long long N, int T, const mivit_render_
   int warps; size_t smem;
   rc = pick_warps(d.n, d.P, &warps, &smem);
   if (rc) return rc;
-  if (smem > 48 * 1024)
-    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long frames = (long long)N * d.F;
   MivitProfScope prof("render_v1", (double)N * ((double)T * 16.0 + (double)d.F * d.P * d.P * 4.0), (cudaStream_t)stream);
   AliasTable at;
   build_alias_table(d.mean_noise || d.poisson == -1.0f ? 0.0 : (double)d.poisson, at);
-  render_v1_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, at, out);
+  // compile-time geometry for the reference's experiment configurations (U = 5; P = 9 / 13 / 7 / 15; n = 10 or any)
+#define MIVIT_V1(TP, TU, TN)                                                                                                    \
+  do {                                                                                                                          \
+    if (smem > 48 * 1024)                                                                                                       \
+      MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_v1_kernel<TP, TU, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    render_v1_kernel<TP, TU, TN><<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, at, out); \
+  } while (0)
+  if (d.U == 5 && d.P == 13 && d.n == 10) MIVIT_V1(13, 5, 10);
+  else if (d.U == 5 && d.P == 9 && d.n == 10) MIVIT_V1(9, 5, 10);
+  else if (d.U == 5 && d.P == 13) MIVIT_V1(13, 5, 0);
+  else if (d.U == 5 && d.P == 9) MIVIT_V1(9, 5, 0);
+  else if (d.U == 5 && d.P == 7) MIVIT_V1(7, 5, 0);
+  else if (d.U == 5 && d.P == 15) MIVIT_V1(15, 5, 0);
+  else MIVIT_V1(0, 0, 0);
+#undef MIVIT_V1
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -832,7 +873,6 @@ int render_embed_linear_launch(const double* traj, long long N, int T, const miv
   while (warps > 1 && wbytes + per_warp * warps > 200 * 1024) warps >>= 1;
   const size_t smem = wbytes + per_warp * warps;
   MIVIT_CHECK_ARG(smem <= 220 * 1024, "embedding weight (%d x %d) does not fit shared memory next to the frame tables", E, PP);
-  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_embed_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long frames = (long long)N * d.F;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -844,7 +884,18 @@ int render_embed_linear_launch(const double* traj, long long N, int T, const miv
   AliasTable at;
   build_alias_table(d.mean_noise || d.poisson == -1.0f ? 0.0 : (double)d.poisson, at);
   MivitProfScope prof("render_embed_linear", (double)N * ((double)T * 16.0 + (double)d.F * E * 4.0), st);
-  render_embed_linear_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(traj, frames, d, at, W, w_transposed, bias, E, emb, frames_out);
+#define MIVIT_EMB(TP, TU, TN)                                                                                                   \
+  do {                                                                                                                          \
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_embed_linear_kernel<TP, TU, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    render_embed_linear_kernel<TP, TU, TN><<<(unsigned)blocks, warps * 32, smem, st>>>(traj, frames, d, at, W, w_transposed, bias, E, emb, \
+                                                                                       frames_out);                           \
+  } while (0)
+  if (d.U == 5 && d.P == 13 && d.n == 10) MIVIT_EMB(13, 5, 10);
+  else if (d.U == 5 && d.P == 9 && d.n == 10) MIVIT_EMB(9, 5, 10);
+  else if (d.U == 5 && d.P == 7 && d.n == 10) MIVIT_EMB(7, 5, 10);
+  else if (d.U == 5 && d.P == 15 && d.n == 10) MIVIT_EMB(15, 5, 10);
+  else MIVIT_EMB(0, 0, 0);
+#undef MIVIT_EMB
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

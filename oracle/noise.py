@@ -165,10 +165,13 @@ class PhiloxNoise:
     def _words(self, item, block, seq, stream, variant=0):
         return px.philox4x32_10(item, block, seq, px.stream_word(stream, variant), self.k0, self.k1)
 
-    def intensity_z(self, seq, n_items):
-        """One standard normal per item (V1: item = frame*n+p; PSFNoise: item = frame)."""
+    def intensity_z(self, seq, n_items, v1=False):
+        """One standard normal per item (V1: item = frame*n+p; PSFNoise: item = frame).  v1=True: the V1 renderer's Box-Muller
+        with the angle in (-pi, pi] (csrc/philox.cuh box_muller_fast)."""
         item = np.arange(n_items, dtype=np.uint32)
         w = self._words(item, np.uint32(0), np.uint32(seq), px.STREAM_INTENSITY)
+        if v1:
+            return px.box_muller_shifted(w[0], w[1])[0]
         z, _ = px.box_muller(w[0], w[1])
         return z
 
@@ -200,10 +203,7 @@ class PhiloxNoise:
         pairs = ppr * P
         item = np.arange(F * pairs, dtype=np.uint32)
         w = self._words(item, np.uint32(0), np.uint32(seq), px.STREAM_PIXEL)
-        u = px.u01(w[0])
-        th = ((px.u01(w[1]) - F32(0.5)) * F32(6.2831853071795860)).astype(F32)
-        r = np.sqrt((F32(-1.3862943611198906) * np.log2(u).astype(F32)).astype(F32)).astype(F32)
-        zl, zr = (r * np.sin(th)).astype(F32), (r * np.cos(th)).astype(F32)
+        zl, zr = px.box_muller_shifted(w[0], w[1])
         z = np.zeros((F, P, 2 * ppr), dtype=F32)
         z[:, :, 0::2] = zl.reshape(F, P, ppr)
         z[:, :, 1::2] = zr.reshape(F, P, ppr)
@@ -235,7 +235,7 @@ class NumpyNoise:
     def __init__(self, seed=None):
         self.rng = np.random.default_rng(seed)
 
-    def intensity_z(self, seq, n_items):
+    def intensity_z(self, seq, n_items, v1=False):
         return self.rng.standard_normal(n_items).astype(F32)
 
     def pixel(self, seq, n_pixels, variant=0):
@@ -256,7 +256,7 @@ class NumpyNoise:
 class MeanNoise:
     """Every draw returns its mean: z = 0 and Poisson(lam) -> lam."""
 
-    def intensity_z(self, seq, n_items):
+    def intensity_z(self, seq, n_items, v1=False):
         return np.zeros(n_items, dtype=F32)
 
     def pixel(self, seq, n_pixels, variant=0):

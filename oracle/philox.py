@@ -68,6 +68,14 @@ def box_muller(xa, xb):
     return (r * np.sin(v)).astype(np.float32), (r * np.cos(v)).astype(np.float32)
 
 
+def box_muller_shifted(xa, xb):
+    """box_muller_fast of philox.cuh: r = sqrt(-2 ln 2 * log2(u)), angle (v - 1/2) * 2 pi in (-pi, pi]."""
+    u = u01(xa)
+    th = ((u01(xb) - np.float32(0.5)) * np.float32(6.2831853071795860)).astype(np.float32)
+    r = np.sqrt((np.float32(-1.3862943611198906) * np.log2(u).astype(np.float32)).astype(np.float32)).astype(np.float32)
+    return (r * np.sin(th)).astype(np.float32), (r * np.cos(th)).astype(np.float32)
+
+
 def seed_key(seed):
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32)

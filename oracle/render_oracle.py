@@ -161,7 +161,7 @@ def render_v1(traj, n, center, image_props, noise=None, seq_offset=0, mode="sepa
     hi = F32(prm["bg_mean"] + 3 * prm["bg_std"])
     for s in range(N):
         seq = seq_offset + s
-        zI = noise.intensity_z(seq, F * n).reshape(F, n)
+        zI = noise.intensity_z(seq, F * n, v1=True).reshape(F, n)
         zb, kpois = noise.pixel_v1(seq, F, P, prm["poisson"])
         for f in range(F):
             xs, ys = _frame_centres(tr[s], f, n, center, U)
