@@ -277,8 +277,6 @@ int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bflo
     }
     rc = conv_rows_forward_v3(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
     if (rc || handled) return rc;
-    rc = conv_rows_forward_v2(X, Wp, nullptr, Y, nullptr, stats, nullptr, rows, P, cin, cout, taps, sh, st, &handled);
-    if (rc || handled) return rc;
   }
 #define MIVIT_FWD_CASE(CI, CO) \
   if (cin == CI && cout == CO) return launch_fwd<CI, CO>(X, Wp, Y, stats, rows, P, taps, sh, st);
@@ -306,8 +304,6 @@ int conv_rows_forward_fused(const __nv_bfloat16* X, const __nv_bfloat16* Wp, con
       if (rc || handled) return rc;
     }
     rc = conv_rows_forward_v3(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);   // TMA
-    if (rc || handled) return rc;
-    rc = conv_rows_forward_v2(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, cin, cout, taps, sh, st, &handled);
     if (rc || handled) return rc;
   }
   int rc = conv_rows_forward(X, Wp, Y, stats, rows, P, cin, cout, taps, sh, impl, st);

@@ -177,8 +177,6 @@ int conv_rows_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, 
     bool handled = false;
     int rc = conv_rows_wgrad_v3(X, dY, dW, rows, P, cin, cout, taps, sh, st, &handled);   // TMA ring + cluster multicast
     if (rc || handled) return rc;
-    rc = conv_rows_wgrad_v2(X, dY, dW, rows, P, cin, cout, taps, sh, st, &handled);
-    if (rc || handled) return rc;
   }
 #define MIVIT_WG_CASE(CI, CO) \
   if (cin == CI && cout == CO) return launch_wgrad<CI, CO>(X, dY, dW, rows, P, taps, sh, st);

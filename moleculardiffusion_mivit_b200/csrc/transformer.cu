@@ -514,6 +514,11 @@ static bool attention_seq_ok(int S, int E, int H) {
   return S <= 64 && H <= 8 && E % 4 == 0 && (E / H) % 4 == 0 && (size_t)(4 * S * E + 2 * H * S) * sizeof(float) <= 200 * 1024;
 }
 
+// floats the `probs` buffer of one layer needs: row log-sum-exps for the sequence-per-CTA kernels, the full S x S matrices otherwise
+size_t attention_probs_floats(int B, int S, int E, int H) {
+  return attention_seq_ok(S, E, H) ? (size_t)B * H * S : (size_t)B * H * S * S;
+}
+
 template <int D>
 static int attention_fwd_d(const float* q, const float* k, const float* v, float* ctx, float* probs, int B, int S, int E,
                            int H, cudaStream_t st) {

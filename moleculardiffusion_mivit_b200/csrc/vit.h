@@ -27,10 +27,7 @@ static inline ConvShifts make_shifts(int P, int taps, bool mirrored) {
 int conv_rows_forward(const __nv_bfloat16* X, const __nv_bfloat16* Wp, __nv_bfloat16* Y, float* stats, long long rows,
                       int P, int cin, int cout, int taps, const ConvShifts& sh, int impl, cudaStream_t st);
 
-// pipelined / fused variants (conv_tc2.cu); impl: 1 = pipelined tcgen05, 2 = serial tcgen05 (v1), 0 = SIMT
-int conv_rows_forward_v2(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
-                         __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout, int taps,
-                         const ConvShifts& sh, cudaStream_t st, bool* handled);
+// pipelined / fused variants (conv_tc3.cu: TMA ring; conv_tc4.cu: CTA pairs); impl: 1 = pipelined tcgen05, 2 = serial tcgen05, 0 = SIMT
 int conv_rows_forward_v3(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const __nv_bfloat16* Wsk, __nv_bfloat16* Y,
                          __nv_bfloat16* Ysk, float* stats, float* stats_sk, long long rows, int P, int cin, int cout, int taps,
                          const ConvShifts& sh, cudaStream_t st, bool* handled);
@@ -54,9 +51,6 @@ int pack_conv_weights(const float* W, __nv_bfloat16* out, int cout, int cin, int
 int conv_rows_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int cin, int cout,
                     int taps, const ConvShifts& sh, int impl, cudaStream_t st);
 
-int conv_rows_wgrad_v2(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int cin, int cout,
-                       int taps, const ConvShifts& sh, cudaStream_t st, bool* handled);
-
 int conv_rows_wgrad_v3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int cin, int cout,
                        int taps, const ConvShifts& sh, cudaStream_t st, bool* handled);
 
@@ -74,6 +68,7 @@ int attention_fwd(const float* q, const float* k, const float* v, float* ctx, fl
                   cudaStream_t st);
 int attention_bwd(const float* q, const float* k, const float* v, const float* probs, const float* ctx, const float* dctx,
                   float* dq, float* dk, float* dv, int B, int S, int E, int H, cudaStream_t st);
+size_t attention_probs_floats(int B, int S, int E, int H);   // size of the per-layer `probs` buffer (log-sum-exp rows, or S x S)
 int act_fwd(const float* pre, float* post, long long n, int mode, cudaStream_t st);
 int nan_to_num_f32(const float* in, float* out, long long n, cudaStream_t st);
 int add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st);

@@ -235,7 +235,7 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
   for (int l = 0; l < c->L; ++l) {
     LayerWS& y = w.lyr[l];
     y.q = b.take<float>(T * E); y.k = b.take<float>(T * E); y.v = b.take<float>(T * E); y.ctx = b.take<float>(T * E);
-    y.probs = b.take<float>((size_t)B * H * S * S); y.ao = b.take<float>(T * E);
+    y.probs = b.take<float>(attention_probs_floats(B, S, E, H)); y.ao = b.take<float>(T * E);
     y.z1 = b.take<float>(T * E); y.m1 = b.take<float>(T); y.r1 = b.take<float>(T); y.x1 = b.take<float>(T * E);
     y.hpre = b.take<float>(T * HD); y.hact = b.take<float>(T * HD); y.ff = b.take<float>(T * E);
     y.z2 = b.take<float>(T * E); y.m2 = b.take<float>(T); y.r2 = b.take<float>(T); y.x2 = b.take<float>(T * E);
