@@ -1,21 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the MiViT hot path on B200.
+"""bench.py -- benchmarks of the MiViT hot path on B200.
 
-Metric (BASELINE.json): synthetic sequences/sec of  render + ViT train step.
-Workload (BASELINE.json configs[1], "Framerate experiment: 30-frame sequences with full ViT
-training step on 1 B200"): per step and per GPU, B Brownian trajectories (T=300 sub-steps, D groups
-of trainModelsFramerate.py:45) are generated on the device, rendered to 30 frames of 13x13 pixels
-with the Framerate experiment's image_props (n=10 sub-positions per frame, background + Poisson
-noise, fused normalisation), and pushed through one full training step (forward, MSE, backward,
-AdamW lr=1e-4) of the DeepResNet-embedding ViT (E64/H4/HD128/L6, regression token, no pos-enc,
-506 081 parameters).
+Metric (BASELINE.json): synthetic sequences/sec of  render + ViT train step;  render GB/s.
 
-    python bench.py --gpus 1 --steps 20 --warmup 5
-    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --gpus 1 --steps 20 --warmup 5                       # headline: BASELINE configs[1]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W   # configs[4]
     python bench.py --impl reference ...     # the reference algorithm on the host CPU cores (oracle port)
+    python bench.py --config psfnoise_render | embeddings_linear_n | embeddings_cnn_n | embeddings_deepcnn_n | imagesfeatures
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same metric
-through the public host-buffer API (pinned H2D of the trajectories, D2H of the loss every step).
+Workloads (`--config`; `config.workload` of the JSON line names the one that ran):
+  framerate (default, BASELINE configs[1] "Framerate experiment: 30-frame sequences with full ViT training step on 1 B200"; with
+      --gpus N it is configs[4], the data-parallel run): per step and per GPU, B Brownian trajectories (T=300 sub-steps, D groups of
+      trainModelsFramerate.py:45) are generated on the device, rendered to 30 frames of 13x13 pixels with the Framerate
+      experiment's image_props (n=10 sub-positions per frame, background + Poisson noise, fused normalisation), and pushed
+      through one full training step (forward, MSE, backward, AdamW lr=1e-4) of the DeepResNet-embedding ViT (E64/H4/HD128/L6,
+      regression token, no pos-enc, 506 081 parameters).
+  psfnoise_render (configs[0]): trajs_to_vid_psf_noise of trainSettingsPSFNoise.py (T=200 -> 5 PSF x 6 noise x 20 frames of 9x9,
+      197.6 KB per trajectory) + eval-mode ViT forward + MSE on each of the 30 variants (trainModelsPSFNoise.py:206-238).
+  embeddings_{linear,cnn,deepcnn}_n (configs[2]): the Embeddings experiment's models (P=9, F=30, pos-enc on) trained FROM THE
+      TRAJECTORIES: renderer fused with the frame embedding, frames re-rendered for the embedding's weight gradient
+      (12 480 algorithmic bytes per sequence for linear / cnn); deepcnn renders to a frame buffer first.
+  imagesfeatures (configs[3]): P=9, F=30 DeepResNet ViT + the 25 trajectory features (late fusion), features computed on the GPU
+      from the frame-averaged trajectories (create_video_and_feature_pairs, helpersGeneration.py:674-719).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same metric through the public host-buffer
+API (pinned H2D of the trajectories, D2H of the loss every step).
 """
 import argparse
 import json
@@ -28,20 +37,54 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# ---- workload: Experiments/Framerate/trainSettingsFramerate.py (image_props :62-81, model :40-46)
-P, NPOS, NFRAMES = 13, 10, 30
-T = NPOS * NFRAMES
-BG_MEAN, BG_SIGMA = 1420, 290
-PART_MEAN, PART_STD = 6000 - BG_MEAN, 500
-IMAGE_PROPS = {"particle_intensity": [PART_MEAN, PART_STD], "NA": 1.46, "wavelength": 500e-9, "psf_division_factor": 1.3,
-               "resolution": 100e-9, "output_size": P, "upsampling_factor": 5, "background_intensity": [BG_MEAN, BG_SIGMA],
-               "poisson_noise": 100, "trajectory_unit": 1200}
 D_GROUPS = [1, 3, 5, 7, 9, 10.2]          # TrainingDs_list means (variance 1), trainModelsFramerate.py:45
 D_MAX = 10.0
-EMBED, HEADS, HIDDEN, LAYERS = 64, 4, 128, 6
-# algorithmic work per sequence
-FLOPS_PER_SEQ_TRAIN = 8.773e9             # P13 F30 deepcnn_n: 2 924.4 MF forward x 3
-RENDER_BYTES_PER_SEQ = T * 2 * 8 + NFRAMES * P * P * 4
+BG_MEAN, BG_SIGMA = 1420, 290
+PART_MEAN, PART_STD = 6000 - BG_MEAN, 500
+
+
+def _props(P, **over):
+    d = {"particle_intensity": [PART_MEAN, PART_STD], "NA": 1.46, "wavelength": 500e-9, "psf_division_factor": 1.3,
+         "resolution": 100e-9, "output_size": P, "upsampling_factor": 5, "background_intensity": [BG_MEAN, BG_SIGMA],
+         "poisson_noise": 100, "trajectory_unit": 1200}
+    d.update(over)
+    return d
+
+
+def _model_cfg(embedding, size="n", **over):
+    E, H, HD, L = {"s": (32, 2, 64, 3), "n": (64, 4, 128, 6), "b": (128, 8, 256, 12)}[size]
+    d = dict(embedding=embedding, embed_dim=E, num_heads=H, hidden_dim=HD, num_layers=L, activation="relu",
+             use_pos_encoding=False, use_regression_token=True)
+    d.update(over)
+    return d
+
+
+# name -> workload description.  flops_per_seq: algorithmic training FLOPs, render_bytes_per_seq: 8d too.
+WORKLOADS = {
+    "framerate": dict(kind="train", P=13, npos=10, frames=30, props=_props(13), model=_model_cfg("deepresnet"),
+                      flops_per_seq=8.773e9, from_traj=False, batch=1024,
+                      text="framerate_P13_F30_deepcnn_n (BASELINE configs[1]): on-device Brownian T=300 -> render 30x13x13 (n=10, "
+                           "bg+Poisson noise, normalised) -> DeepResNet-ViT E64/H4/HD128/L6 fwd+MSE+bwd+AdamW"),
+    "psfnoise_render": dict(kind="psfnoise", P=9, npos=10, frames=20, batch=256,
+                            props=_props(9, particle_intensity=[5000, 500], background_intensity=[5000, 0]),
+                            psf=[2, 1.75, 1.5, 1.25, 1], noise=[0, 1 / 50, 1 / 25, 1 / 20, 1 / 10, 1 / 5],
+                            model=_model_cfg("deepresnet"), flops_per_seq=30 * 939.2e6,
+                            text="psfnoise_render (BASELINE configs[0]): on-device Brownian T=200 -> trajs_to_vid_psf_noise 5 PSF x 6 "
+                                 "noise x 20 frames of 9x9 (197.6 KB per trajectory) -> eval-mode DeepResNet-ViT forward + MSE on each "
+                                 "of the 30 variants"),
+    "imagesfeatures": dict(kind="train", P=9, npos=10, frames=30, props=_props(9), batch=1024, from_traj=False, features=True,
+                           model=_model_cfg("deepresnet", use_global_features=True, fusion_type="late"), flops_per_seq=4.227e9,
+                           text="imagesfeatures_P9_F30_deepcnn_n_late (BASELINE configs[3]): on-device Brownian T=300 -> render 30x9x9 "
+                                "+ 25 trajectory features on the GPU -> DeepResNet-ViT with late feature fusion fwd+MSE+bwd+AdamW"),
+}
+for _emb, _fl in (("linear", 0.042e9), ("cnn", 0.042e9), ("deepresnet", 4.227e9)):
+    _nm = "embeddings_%s_n" % ("deepcnn" if _emb == "deepresnet" else _emb)
+    WORKLOADS[_nm] = dict(kind="train", P=9, npos=10, frames=30, props=_props(9), batch=1024 if _emb == "deepresnet" else 4096,
+                          model=_model_cfg(_emb, use_pos_encoding=True), flops_per_seq=_fl, from_traj=True,
+                          text="%s_P9_F30 (BASELINE configs[2]): on-device Brownian T=300 -> training step FROM THE TRAJECTORIES (%s) "
+                               "-> ViT E64/H4/HD128/L6 + pos-enc fwd+MSE+bwd+AdamW" % (
+                                   _nm, "renderer fused with the frame embedding; frames re-rendered for its weight gradient, never "
+                                   "in HBM" if _emb != "deepresnet" else "rendered into a frame buffer: BatchNorm needs all frames"))
 
 
 def load_peaks():
@@ -97,129 +140,126 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------ reference arm
 def _render_slice(args):
     """Worker of the process pool: the literal numpy renderer on a slice of the step's trajectories."""
-    traj, seed = args
+    traj, seed, name = args
     from oracle import render_oracle as ro
     from oracle.noise import NumpyNoise
-    vid = ro.render_v1(traj, NPOS, True, IMAGE_PROPS, noise=NumpyNoise(seed), mode="literal")
+    w = WORKLOADS[name]
+    if w["kind"] == "psfnoise":
+        return ro.render_psfnoise(traj, w["npos"], True, w["props"], w["psf"], w["noise"], noise=NumpyNoise(seed), mode="literal")
+    vid = ro.render_v1(traj, w["npos"], True, w["props"], noise=NumpyNoise(seed), mode="literal")
     vid, _ = ro.normalize_images(vid, BG_MEAN, BG_SIGMA, BG_MEAN + PART_MEAN)
     return vid
 
 
-def cpu_reference_step(n_seq, state, pool=None):
-    """One bounded sample of the reference algorithm on the host: the literal numpy renderer
-    (oracle/render_oracle.py) + normalisation + one fp32 PyTorch training step (oracle/vit_oracle.py, torch
+def cpu_reference_step(name, n_seq, state, pool=None):
+    """One bounded sample of the reference algorithm on the host: the literal numpy renderer (oracle/render_oracle.py) +
+    normalisation (+ the 25 features, oracle/features_oracle.py) + the fp32 PyTorch model step (oracle/vit_oracle.py, torch
     intra-op threads = all cores).  pool = None: the renderer runs in ONE process, as the reference does (its
-    use_multiprocessing branch raises TypeError); with a process pool the sequences of the step are rendered on all
-    cores.  Returns (t_render, t_train)."""
+    use_multiprocessing branch raises TypeError); with a process pool the sequences of the step are rendered on all cores.
+    Returns (t_render, t_model)."""
     import numpy as np
     import torch
     from oracle import vit_oracle as vo
     from oracle.trajectory_oracle import brownian_oracle
+    w = WORKLOADS[name]
+    T = w["npos"] * w["frames"]
     traj, D = brownian_oracle(n_seq, T, D_GROUPS, [1.0] * len(D_GROUPS), 100.0, seed=state["step"], seq_offset=0)
     t0 = time.perf_counter()
     if pool is None:
-        vid = _render_slice((traj, state["step"]))
+        vid = _render_slice((traj, state["step"], name))
     else:
         parts = np.array_split(np.arange(n_seq), min(n_seq, pool._processes))
-        vid = np.concatenate(pool.map(_render_slice, [(traj[p], state["step"] * 1000 + i) for i, p in enumerate(parts)]))
+        vid = np.concatenate(pool.map(_render_slice, [(traj[p], state["step"] * 1000 + i, name) for i, p in enumerate(parts)]))
+    feats = None
+    if w.get("features"):
+        from oracle import features_oracle as fo
+        flipped = traj.copy()
+        flipped[:, :, 1] *= -1                              # create_video_and_feature_pairs sees the flipped trajectories
+        feats = torch.from_numpy(np.nan_to_num(fo.features_batch(fo.average_frames(flipped, w["npos"]), 1.0), nan=0.0, posinf=0.0,
+                                               neginf=0.0).astype(np.float32))
     t1 = time.perf_counter()
-    x = torch.from_numpy(np.ascontiguousarray(vid))
     y = torch.from_numpy((D / D_MAX).astype(np.float32)).unsqueeze(-1)
-    vo.train_step(state["sd"], state["opt"], state["cfg"], x, y)
+    if w["kind"] == "psfnoise":
+        with torch.no_grad():
+            for i in range(vid.shape[1]):
+                for j in range(vid.shape[2]):
+                    pred = vo.forward(state["sd"], state["cfg"], torch.from_numpy(np.ascontiguousarray(vid[:, i, j])), training=False)
+                    torch.nn.functional.mse_loss(pred * D_MAX, y * D_MAX)
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(vid))
+        vo.train_step(state["sd"], state["opt"], state["cfg"], x, y, feats)
     t2 = time.perf_counter()
     state["step"] += 1
     return t1 - t0, t2 - t1
 
 
-def cpu_reference_state():
+def _build_model(w, device=None):
+    """Random-init model of the workload through this package's mirror classes (same constructors / init order as the reference)."""
     import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    m = w["model"]
+    cls = {"deepresnet": M.DeepResNetEmbedding, "linear": M.LinearProjectionEmbedding, "cnn": M.CNNEmbedding}[m["embedding"]]
+    torch.manual_seed(0)
+    return M.GeneralTransformer(cls, {"patch_size": w["P"], "embed_dim": m["embed_dim"]}, m["embed_dim"], m["num_heads"],
+                                m["hidden_dim"], m["num_layers"], M.MLPHead, F.relu, 0.0, m["use_pos_encoding"],
+                                m["use_regression_token"], True, m.get("use_global_features", False), m.get("fusion_type", "early"),
+                                25 if m.get("use_global_features") else None)
+
+
+def cpu_reference_state(name):
+    """Random-init weights of the workload's architecture (the mirror module's constructor only builds torch parameters on the
+    host; nothing of the CUDA library runs) shared with the oracle through the state dict."""
     from oracle import vit_oracle as vo
-    import torch.nn as nn
-    torch.manual_seed(0)
-    cfg = dict(embedding="deepresnet", embed_dim=EMBED, num_heads=HEADS, num_layers=LAYERS, activation="relu",
-               use_pos_encoding=False, use_regression_token=True)
-    sd = _random_state_dict()
-    return {"sd": sd, "opt": vo.new_opt_state(sd), "cfg": cfg, "step": 0}
+    w = WORKLOADS[name]
+    sd = {k: v.detach().clone() for k, v in _build_model(w).state_dict().items()}
+    return {"sd": sd, "opt": vo.new_opt_state(sd), "cfg": dict(w["model"]), "step": 0}
 
 
-def _random_state_dict():
-    """Random-init weights of the reference architecture via plain torch modules (host side, CPU)."""
-    import torch
-    import torch.nn as nn
-    torch.manual_seed(0)
-    sd = {}
-
-    def lin(pre, o, i):
-        m = nn.Linear(i, o)
-        sd[pre + ".weight"], sd[pre + ".bias"] = m.weight.detach().clone(), m.bias.detach().clone()
-
-    def bn(pre, c):
-        sd[pre + ".weight"], sd[pre + ".bias"] = torch.ones(c), torch.zeros(c)
-        sd[pre + ".running_mean"], sd[pre + ".running_var"] = torch.zeros(c), torch.ones(c)
-        sd[pre + ".num_batches_tracked"] = torch.tensor(0)
-
-    def conv(key, o, i, k):
-        sd[key] = nn.Conv2d(i, o, k, bias=False).weight.detach().clone()
-
-    conv("embedding.initial_conv.weight", 32, 1, 3); bn("embedding.bn1", 32)
-    for b, (ci, co) in (("res_block1", (32, 64)), ("res_block2", (64, 128))):
-        conv("embedding.%s.conv1.weight" % b, co, ci, 3); bn("embedding.%s.bn1" % b, co)
-        conv("embedding.%s.conv2.weight" % b, co, co, 3); bn("embedding.%s.bn2" % b, co)
-        conv("embedding.%s.skip.0.weight" % b, co, ci, 1); bn("embedding.%s.skip.1" % b, co)
-    lin("embedding.fc", EMBED, 128)
-    sd["norm.weight"], sd["norm.bias"] = torch.ones(EMBED), torch.zeros(EMBED)
-    sd["reg_token"] = torch.randn(1, 1, EMBED)
-    for l in range(LAYERS):
-        p = "transformer.encoder_layers.%d." % l
-        for s in ("q_proj", "k_proj", "v_proj", "out_proj"):
-            lin(p + "self_attn." + s, EMBED, EMBED)
-        for nrm in ("norm1", "norm2"):
-            sd[p + nrm + ".weight"], sd[p + nrm + ".bias"] = torch.ones(EMBED), torch.zeros(EMBED)
-        lin(p + "feed_forward.fc1", HIDDEN, EMBED); lin(p + "feed_forward.fc2", EMBED, HIDDEN)
-    sd["transformer.norm.weight"], sd["transformer.norm.bias"] = torch.ones(EMBED), torch.zeros(EMBED)
-    lin("mlp_head.mlp.0", 128, EMBED); lin("mlp_head.mlp.3", 1, 128)
-    return sd
-
-
-def run_reference(args, rank):
-    """Reference arm: the reference algorithm on ALL host cores -- the renderer sharded over a process pool (one
-    process per core, each running the literal per-sequence loop), the training step with torch using every core.
-    The as-written figure (renderer in one process, like the reference's own loop) is reported beside it."""
-    if rank != 0:
-        return
+def _cpu_baseline(name, n_seq, reps, warm):
     import multiprocessing as mp
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_seq = args.cpu_seqs
-    st = cpu_reference_state()
-    a, b = cpu_reference_step(n_seq, st)                       # as written: single-process renderer
+    st = cpu_reference_state(name)
+    a, b = cpu_reference_step(name, n_seq, st)                     # as written: single-process renderer
     as_written = n_seq / (a + b)
     pool = mp.get_context("fork").Pool(cores)
     try:
-        for _ in range(max(args.warmup, 1) if args.steps < 10 else 2):
-            cpu_reference_step(n_seq, st, pool)
+        for _ in range(warm):
+            cpu_reference_step(name, n_seq, st, pool)
         t0 = time.perf_counter()
         tr = tt = 0.0
-        for _ in range(args.steps):
-            a, b = cpu_reference_step(n_seq, st, pool)
+        for _ in range(reps):
+            a, b = cpu_reference_step(name, n_seq, st, pool)
             tr += a; tt += b
         el = time.perf_counter() - t0
     finally:
         pool.close()
-    val = n_seq * args.steps / (tr + tt)
-    line = {"impl": "reference", "metric": "synthetic sequences/sec (render+ViT train step)", "value": val, "unit": "sequences/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tr + tt) / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "framerate_P13_F30_deepcnn_n (BASELINE configs[1])", "batch_per_step": n_seq},
-            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port",
-                             "as_written_value": as_written,
-                             "sample": "%d steps x %d sequences: literal numpy renderer sharded over %d processes + fp32 torch "
-                                       "train step (%d intra-op threads); render %.1f ms/seq, train %.1f ms/seq; as written "
-                                       "(renderer in one process, like the reference's loop): %.1f sequences/s" %
-                                       (args.steps, n_seq, cores, cores, 1e3 * tr / (n_seq * args.steps),
-                                        1e3 * tt / (n_seq * args.steps), as_written)},
-            "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    val = n_seq * reps / (tr + tt)
+    w = WORKLOADS[name]
+    what = "eval forward + MSE on 30 variants" if w["kind"] == "psfnoise" else "fp32 torch train step"
+    sample = ("%d steps x %d sequences of the same workload: literal numpy renderer sharded over %d processes %.1f ms/seq + %s "
+              "(%d intra-op threads) %.1f ms/seq; as written (renderer in one process, like the reference's loop): %.1f sequences/s" %
+              (reps, n_seq, cores, 1e3 * tr / (n_seq * reps), what, cores, 1e3 * tt / (n_seq * reps), as_written))
+    return {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port", "as_written_value": as_written, "sample": sample}, \
+        1e3 * (tr + tt) / reps, el
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference algorithm on ALL host cores -- the renderer sharded over a process pool (one process per core,
+    each running the literal per-sequence loop), the model step with torch using every core.  The as-written figure (renderer in
+    one process, like the reference's own loop) is reported beside it."""
+    if rank != 0:
+        return
+    w = WORKLOADS[args.config]
+    n_seq = args.cpu_seqs if w["kind"] != "psfnoise" else max(4, args.cpu_seqs // 4)
+    cb, ms, el = _cpu_baseline(args.config, n_seq, args.steps, max(args.warmup, 1) if args.steps < 10 else 2)
+    line = {"impl": "reference", "metric": "synthetic sequences/sec (render+ViT train step)", "value": cb["value"], "unit": "sequences/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["text"].split(":")[0], "batch_per_step": n_seq}, "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": el}
     print(json.dumps(line))
 
@@ -229,12 +269,15 @@ def run_b200(args, rank, world, local_rank):
     import ctypes
     import numpy as np
     import torch
-    import torch.nn.functional as F
     import torch.distributed as dist
-    from moleculardiffusion_mivit_b200 import _lib, models as M
-    from moleculardiffusion_mivit_b200.helpersGeneration import brownian_motion, derive_render_params, render_device
+    from moleculardiffusion_mivit_b200 import _lib, experiments as X, helpersFeatures as HF
+    from moleculardiffusion_mivit_b200.helpersGeneration import derive_render_params, render_device
+    from moleculardiffusion_mivit_b200.models import TrajectorySource
     from moleculardiffusion_mivit_b200.training import MiViTTrainer
 
+    w = WORKLOADS[args.config]
+    P, NPOS, NFRAMES = w["P"], w["npos"], w["frames"]
+    T = NPOS * NFRAMES
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -243,15 +286,20 @@ def run_b200(args, rank, world, local_rank):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    B = args.batch
-    torch.manual_seed(0)
-    model = M.GeneralTransformer(M.DeepResNetEmbedding, {"patch_size": P, "embed_dim": EMBED}, EMBED, HEADS, HIDDEN, LAYERS,
-                                 M.MLPHead, F.relu, 0.0, False, True, True).cuda().train()
-    trainer = MiViTTrainer(model, lr=1e-4, cuda_graph=not args.no_cuda_graph, sync_bn=args.sync_bn,
-                           overlap_allreduce=not args.no_overlap)
-    prm = derive_render_params(IMAGE_PROPS, NPOS, True)
-    den = (BG_MEAN + PART_MEAN) - (BG_MEAN - BG_SIGMA)
-    prm.normalize, prm.norm_sub, prm.norm_div = 1, float(BG_MEAN - BG_SIGMA), float(den)
+    B = args.batch if args.batch > 0 else w["batch"]
+    model = _build_model(w).cuda()
+    psf_mode = w["kind"] == "psfnoise"
+    trainer = None
+    if psf_mode:
+        model.eval()
+    else:
+        model.train()
+        trainer = MiViTTrainer(model, lr=1e-4, cuda_graph=not args.no_cuda_graph, sync_bn=args.sync_bn,
+                               overlap_allreduce=not args.no_overlap, fused_allreduce=not args.nccl_allreduce)
+    prm = derive_render_params(w["props"], NPOS, True)
+    if not psf_mode:
+        den = (BG_MEAN + PART_MEAN) - (BG_MEAN - BG_SIGMA)
+        prm.normalize, prm.norm_sub, prm.norm_div = 1, float(BG_MEAN - BG_SIGMA), float(den)
     gm = np.asarray(D_GROUPS, dtype=np.float32)
     gv = np.ones(len(D_GROUPS), dtype=np.float32)
     fp = ctypes.POINTER(ctypes.c_float)
@@ -261,16 +309,42 @@ def run_b200(args, rank, world, local_rank):
     labels = torch.empty((B, 1), dtype=torch.float32, device=dev)
     step_no = [0]
 
-    def device_step():
-        """generate -> render (+normalise) -> train step, all enqueued on the current stream."""
+    def next_offset():
         off = (step_no[0] * world + rank) * B      # global sequence ids: the data set is sharding invariant
         step_no[0] += 1
-        st = _lib.current_stream()
+        return off
+
+    def gen_trajectories(off):
         _lib.check(L.mivit_brownian(B, T, gm.ctypes.data_as(fp), gv.ctypes.data_as(fp), len(gm), 100.0, args.seed, off,
-                                    _lib.ptr(traj), _lib.ptr(Dd), st))
-        render_device(traj, prm, args.seed, seq_offset=off, out=frames, out_seq_stride=NFRAMES * P * P)
+                                    _lib.ptr(traj), _lib.ptr(Dd), _lib.current_stream()))
         torch.div(Dd.view(B, 1), D_MAX, out=labels)
-        return trainer.train_step(frames, labels)
+
+    def consume(off):
+        """render + model step from the device-resident trajectories / labels of this step"""
+        if psf_mode:
+            vids = X.trajs_to_vid_psf_noise(traj, NPOS, True, w["props"], w["psf"], w["noise"], seed=args.seed, seq_offset=off)
+            tot = torch.zeros((), device=dev)
+            with torch.no_grad():
+                for i in range(vids.shape[1]):
+                    for j in range(vids.shape[2]):
+                        pred = model(vids[:, i, j])
+                        tot += torch.nn.functional.mse_loss(pred * D_MAX, labels * D_MAX)
+            return tot
+        if w.get("from_traj"):
+            return trainer.train_step_from_trajectories(TrajectorySource(traj, prm, args.seed, off), labels)
+        render_device(traj, prm, args.seed, seq_offset=off, out=frames, out_seq_stride=NFRAMES * P * P)
+        feats = None
+        if w.get("features"):      # create_video_and_feature_pairs: features of the frame-averaged (y-flipped) trajectories
+            flipped = traj * torch.tensor([1.0, -1.0], dtype=torch.float64, device=dev)
+            feats = torch.nan_to_num(HF.features_device(HF.average_frames_device(flipped, NPOS), 1.0), nan=0.0, posinf=0.0,
+                                     neginf=0.0).float()
+        return trainer.train_step(frames, labels, feats)
+
+    def device_step():
+        """generate -> render -> model step, all enqueued on the current stream."""
+        off = next_offset()
+        gen_trajectories(off)
+        return consume(off)
 
     # host-buffer path (public API): pinned trajectories + labels in, loss out, every step
     h_traj = torch.empty((B, T, 2), dtype=torch.float64).pin_memory()
@@ -280,12 +354,10 @@ def run_b200(args, rank, world, local_rank):
     h_traj.copy_(traj.cpu()); h_lab.copy_(labels.cpu())
 
     def e2e_step():
-        off = (step_no[0] * world + rank) * B
-        step_no[0] += 1
+        off = next_offset()
         traj.copy_(h_traj, non_blocking=True)
         labels.copy_(h_lab, non_blocking=True)
-        render_device(traj, prm, args.seed, seq_offset=off, out=frames, out_seq_stride=NFRAMES * P * P)
-        return float(trainer.train_step(frames, labels).item())      # D2H read of the loss = sync point
+        return float(consume(off).item())                              # D2H read of the loss = sync point
 
     def barrier():
         torch.cuda.synchronize()
@@ -324,11 +396,13 @@ def run_b200(args, rank, world, local_rank):
     value = world * B * args.steps / (ms * 1e-3)
     # instrumented pass of the SAME step, launched kernel by kernel with CUDA events around every tagged launch on the
     # launching stream: per-kernel durations for the roofline (event records cannot live inside a replayed graph)
-    graph_mode = trainer.cuda_graph
-    trainer.cuda_graph = False
+    if trainer is not None:
+        graph_mode = trainer.cuda_graph
+        trainer.cuda_graph = False
     device_step()
     ms_prof, _, _, _ = timed(device_step, args.steps, profile=True)
-    trainer.cuda_graph = graph_mode
+    if trainer is not None:
+        trainer.cuda_graph = graph_mode
     kt = (_lib.KernelTime * 64)()
     nk = L.mivit_profile_read(kt, 64)
     kernels = [{"name": kt[i].name.decode(), "launches": int(kt[i].launches), "ms": kt[i].total_ms, "work": kt[i].total_work}
@@ -344,9 +418,24 @@ def run_b200(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    convs = [k for k in kernels if k["name"].startswith("conv_")]
+    step_ms = ms_prof / args.steps
+    by_name = {k["name"]: k for k in kernels}
+
+    def group(prefixes):
+        ks = [k for k in kernels if any(k["name"].startswith(p) for p in prefixes)]
+        return sum(k["ms"] for k in ks) / args.steps, sum(k["work"] for k in ks) / args.steps
+
+    def hbm_roof(k, note):
+        gbs = k["work"] / (k["ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": k["name"], "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"], "traffic": None, "avg_launch_ms": k["ms"] / k["launches"],
+                "share_of_step": k["ms"] / ms_prof, "peak_source": peaks["source"], "note": note}
+
+    render_note = ("instruction-issue bound (Philox + Box-Muller + alias-table Poisson per pixel pair, 2 n P U exps per frame), "
+                   "not HBM-bound: see DESIGN.md section 2")
     roof = None
-    if convs:
+    convs = [k for k in kernels if k["name"].startswith("conv_")]
+    if convs and not psf_mode:
         top = max(convs, key=lambda k: k["ms"])
         ach = top["work"] / (top["ms"] * 1e-3) / 1e12
         traffic = None
@@ -354,6 +443,9 @@ def run_b200(args, rank, world, local_rank):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get(top["name"])
+        conv_ms, conv_work = group(["conv_"])
+        bn_ms, bn_bytes = group(["bn_"])
+        tr_ms, _ = group(["linear_tc", "attention", "layernorm", "encoder_"])
         roof = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"],
                 "peak_burst": peaks.get("bf16_tflops_burst"),
@@ -361,61 +453,47 @@ def run_b200(args, rank, world, local_rank):
                 "note": "frac > 1 means the kernel beats the cuBLAS bf16 GEMM figure measured under sustained load; "
                         "frac_of_burst is against the cuBLAS burst figure",
                 "avg_launch_ms": top["ms"] / top["launches"], "share_of_step": top["ms"] / ms_prof,
-                "all_convs_tflops": sum(k["work"] for k in convs) / (sum(k["ms"] for k in convs) * 1e-3) / 1e12,
-                "all_convs_share_of_step": sum(k["ms"] for k in convs) / ms_prof,
+                "all_convs_tflops": conv_work / (conv_ms * 1e-3) / 1e12, "all_convs_share_of_step": conv_ms / step_ms,
+                # the other groups of the step, so the line cannot hide a regression outside the convolutions
+                "groups_ms_per_step": {"convolutions": conv_ms, "batchnorm_streams": bn_ms, "transformer_tagged": tr_ms,
+                                       "render": group(["render_"])[0], "step_instrumented": step_ms},
+                "batchnorm_streams": {"ms_per_step": bn_ms, "share_of_step": bn_ms / step_ms,
+                                      "gbs_nominal": bn_bytes / (bn_ms * 1e-3) / 1e9 if bn_ms else None,
+                                      "note": "HBM streams; nominal bytes count the pad rows whose loads are predicated off, "
+                                              "DRAM bytes from ncu are in profiles/"},
+                "whole_step": {"model_tflops": value * w["flops_per_seq"] / 1e12 / world,
+                               "frac_of_sustained": value * w["flops_per_seq"] / 1e12 / world / peaks["bf16_tflops"],
+                               "frac_of_burst": (value * w["flops_per_seq"] / 1e12 / world / peaks["bf16_tflops_burst"])
+                               if peaks.get("bf16_tflops_burst") else None},
                 "timed_in": "instrumented pass (kernel-by-kernel launches with CUDA events), %.3f ms/step; the headline step "
-                            "replays the same kernels as a CUDA graph" % (ms_prof / args.steps)}
-    rnd = [k for k in kernels if k["name"] == "render_v1"]
-    roof_render = None
-    if rnd:
-        gbs = rnd[0]["work"] / (rnd[0]["ms"] * 1e-3) / 1e9
-        roof_render = {"bound": "hbm", "kernel": "render_v1", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                       "frac": gbs / peaks["hbm_gbs"], "traffic": None, "avg_launch_ms": rnd[0]["ms"] / rnd[0]["launches"],
-                       "note": "ALU/RNG-bound (Philox + Poisson per pixel), not HBM-bound: see DESIGN.md"}
-    line = {"metric": "synthetic sequences/sec (render+ViT train step)", "value": value, "unit": "sequences/s", "n_gpus": world,
+                            "replays the same kernels as a CUDA graph" % step_ms}
+    rk = by_name.get("render_v1") or by_name.get("render_embed_linear") or by_name.get("render_psfnoise")
+    roof_render = hbm_roof(rk, render_note) if rk else None
+    if roof is None:
+        roof = roof_render          # render-dominated workloads: the renderer is the kernel the line is about
+    cfg = {"workload": w["text"], "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+           "l2": ("activation working set %.1f GB per step >> 126 MB L2 (no flush needed)" %
+                  (L.mivit_vit_workspace_bytes(ctypes.byref(model.vit_config(NFRAMES)), B) / 1e9)) if not psf_mode else
+                 "rendered variants %.0f MB per step > 126 MB L2 (no flush needed)" % (B * 30 * NFRAMES * P * P * 4 / 1e6)}
+    if trainer is not None:
+        cfg.update({
+            "batchnorm": ("synchronised over the ranks (12 small in-graph all-reduces per step)" if trainer.sync_bn
+                          else "per-rank batch statistics (stock DDP semantics)") if model._is_deep() else "none (no BatchNorm)",
+            "launch": trainer.launch_description(),
+            "allreduce": None if world == 1 else trainer.allreduce_description()})
+    line = {"metric": "synthetic sequences/sec (render+ViT train step)" if not psf_mode else
+                      "synthetic sequences/sec (PSFNoise render + ViT forward+loss on 30 variants)",
+            "value": value, "unit": "sequences/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "framerate_P13_F30_deepcnn_n (BASELINE configs[1]): on-device Brownian T=300 -> render 30x13x13 "
-                                   "(n=10, bg+Poisson noise, normalised) -> DeepResNet-ViT E64/H4/HD128/L6 fwd+MSE+bwd+AdamW",
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "l2": "activation working set %.1f GB per step >> 126 MB L2 (no flush needed)" %
-                             (L.mivit_vit_workspace_bytes(ctypes.byref(model.vit_config(NFRAMES)), B) / 1e9),
-                       "batchnorm": "synchronised over the ranks (12 small all-reduces per step)" if trainer.sync_bn
-                                    else "per-rank batch statistics (stock DDP semantics)",
-                       "launch": "CUDA-graph replay of forward+loss+backward, eager AdamW"
-                                 if (trainer.cuda_graph and not trainer.sync_bn) else "kernel by kernel",
-                       "allreduce": None if world == 1 else
-                                    ("two buckets, the non-embedding one overlapped with the image-embedding backward"
-                                     if (trainer.overlap_allreduce and not trainer.sync_bn) else "one all-reduce after the backward")},
-            "model_tflops": value * FLOPS_PER_SEQ_TRAIN / 1e12 / world, "loss": float(last_loss.item()),
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if model._is_deep() else "tf32", "data": "synthetic",
+            "config": cfg, "model_tflops": value * w["flops_per_seq"] / 1e12 / world, "loss": float(last_loss.item()),
             "roofline": roof, "roofline_render": roof_render, "kernels": kernels, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": int(B * T * 2 * 8 + B * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches}
     if world == 1 and not args.no_cpu_baseline:
-        import multiprocessing as mp
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        st = cpu_reference_state()
-        a, b = cpu_reference_step(args.cpu_seqs, st)
-        as_written = args.cpu_seqs / (a + b)
-        pool = mp.get_context("fork").Pool(cores)
-        try:
-            cpu_reference_step(args.cpu_seqs, st, pool)
-            tr = tt = 0.0
-            reps = 3
-            for _ in range(reps):
-                a, b = cpu_reference_step(args.cpu_seqs, st, pool)
-                tr += a; tt += b
-        finally:
-            pool.close()
-        cval = args.cpu_seqs * reps / (tr + tt)
-        line["cpu_baseline"] = {"value": cval, "unit": "sequences/s", "cores": cores, "kind": "port", "as_written_value": as_written,
-                                "sample": "%d steps x %d sequences of the same workload: literal numpy renderer sharded over %d "
-                                          "processes %.1f ms/seq + fp32 torch train step (%d threads) %.1f ms/seq; as written "
-                                          "(renderer in one process): %.1f sequences/s" %
-                                          (reps, args.cpu_seqs, cores, 1e3 * tr / (args.cpu_seqs * reps), cores,
-                                           1e3 * tt / (args.cpu_seqs * reps), as_written)}
+        n_seq = args.cpu_seqs if not psf_mode else max(4, args.cpu_seqs // 4)
+        line["cpu_baseline"], _, _ = _cpu_baseline(args.config, n_seq, 3, 1)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -427,13 +505,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU per step")
+    ap.add_argument("--config", default="framerate", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (0: the workload's default, 1024 for the headline)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seqs", type=int, default=32, help="sequences per CPU reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: one gradient all-reduce after the whole backward")
     ap.add_argument("--sync-bn", action="store_true", help="N > 1: synchronised BatchNorm (parity mode) instead of per-rank statistics")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the training step kernel by kernel instead of replaying it")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N > 1: NCCL all-reduce + separate AdamW instead of the fused peer-memory all-reduce + AdamW kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1070,6 +1070,7 @@ extern "C" int mivit_render_psfnoise(const double* traj, int64_t N, int32_t T, c
   if (smem > 48 * 1024)
     MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_psfnoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long frames = (long long)N * d.F;
+  MivitProfScope prof("render_psfnoise", (double)N * ((double)T * 16.0 + (double)n_psf * n_noise * d.F * d.P * d.P * 4.0), (cudaStream_t)stream);
   render_psfnoise_kernel<<<mivit_ceil_div(frames, warps), warps * 32, smem, (cudaStream_t)stream>>>(traj, frames, d, v, out);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();

@@ -16,7 +16,8 @@ __all__ = ["MiViTTrainer"]
 
 class MiViTTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step_size=5, gamma=0.9,
-                 process_group=None, distributed=None, cuda_graph=False, sync_bn=False, overlap_allreduce=True):
+                 process_group=None, distributed=None, cuda_graph=False, sync_bn=False, overlap_allreduce=True,
+                 fused_allreduce=True):
         if not isinstance(model, _CudaViT):
             raise TypeError("MiViTTrainer drives a moleculardiffusion_mivit_b200.models.GeneralTransformer / ModularTransformer")
         self.model = model
@@ -52,6 +53,7 @@ class MiViTTrainer:
         # image embedding (head, encoder layers, tokens: 42 % of the 2 MB) are all-reduced on the collective's own stream while the
         # image-embedding backward (~45 % of the step) runs, the embedding's bucket follows, AdamW waits for both.
         self.overlap_allreduce = bool(overlap_allreduce)
+        self.fused_allreduce = bool(fused_allreduce)
         self._ne = None
         if any(not p.requires_grad for p in model.parameters()):
             # the fused AdamW walks the whole flat buffer; torch.optim.AdamW would skip frozen parameters
@@ -77,6 +79,20 @@ class MiViTTrainer:
         except Exception as e:      # an exception must not unwind through the C frames
             self._hook_error = e
             return 1
+
+    def launch_description(self):
+        if self.sync_bn and self.model._is_deep():
+            return "kernel by kernel (synchronised BatchNorm)"
+        return "CUDA-graph replay of forward+loss+backward, eager AdamW" if self.cuda_graph else "kernel by kernel"
+
+    def allreduce_description(self):
+        if self.world == 1:
+            return None
+        if self.sync_bn and self.model._is_deep():
+            return "one NCCL all-reduce after the backward"
+        if self.overlap_allreduce and self.model._image_embedding() is not None:
+            return "NCCL, two buckets, the non-embedding one overlapped with the image-embedding backward"
+        return "one NCCL all-reduce after the backward"
 
     # StepLR(step_size, gamma): lr = base * gamma ** (epoch // step_size), stepped once per cycle
     def scheduler_step(self):
