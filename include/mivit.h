@@ -238,6 +238,40 @@ typedef struct mivit_vit_config {
 typedef int (*mivit_allreduce_fn)(void* device_buf, int64_t n_floats, void* stream, void* user);
 void mivit_set_allreduce_hook(mivit_allreduce_fn fn, void* user, int32_t world_size);
 
+/* -------------------------------------------------- data-parallel exchange over NVLink peer memory (csrc/peer_comm.cu) ----
+ * The reference is single-process; these entry points implement SURVEY.md section 8e without NCCL on the data path: every rank
+ * owns a SEGMENT -- header (flags, counters, AdamW step, lr) | small-exchange slots | the model's flat gradient buffer --
+ * allocated by mivit_comm_alloc, exported as a 64-byte CUDA IPC handle, mapped by its peers with mivit_comm_ipc_open (the host
+ * exchanges the handles, e.g. with torch.distributed.all_gather_object).  All ranks must enqueue the same exchanges in the same
+ * order.  Up to 8 ranks (one NVSwitch domain). */
+typedef struct mivit_peer_comm {
+  int32_t rank, world;
+  void* segment[8];     /* segment base pointers AS MAPPED IN THIS PROCESS; segment[rank] is the rank's own */
+} mivit_peer_comm;
+int64_t mivit_comm_segment_bytes(int64_t n_grad_floats);     /* segment size for a flat gradient of n floats */
+int64_t mivit_comm_grad_offset_bytes(void);                  /* the gradient buffer starts this far into the segment */
+int mivit_comm_alloc(int64_t bytes, void** segment);         /* cudaMalloc + zero (the one allocation this library makes) */
+int mivit_comm_free(void* segment);
+int mivit_comm_ipc_handle(void* segment, uint8_t* handle64);
+int mivit_comm_ipc_open(const uint8_t* handle64, void** segment);
+int mivit_comm_ipc_close(void* segment);
+/* AdamW's learning rate and 1-based step count live in the segment (a replayed CUDA graph reads them there) */
+int mivit_comm_set_lr(const mivit_peer_comm* comm, float lr, void* stream);
+int mivit_comm_set_step(const mivit_peer_comm* comm, int64_t steps_done, void* stream);
+/* Gradient all-reduce FUSED with torch.optim.AdamW (Experiments/PSFNoise/trainSettingsPSFNoise.py:119) on flat offsets
+ * [lo, hi) (lo % 4 == 0): g = sum over ranks (rank order) of the peers' gradient replicas, read straight from peer memory;
+ * p, m, v updated with grad_scale = 1 / world, lr and step from the segment.  advance_step != 0 on the LAST bucket of a step.
+ * grad_sum (optional, local, same offsets): receives the reduced gradient.  bucket in [0,4): exchanges that may be in flight
+ * concurrently need different buckets.  One kernel, no host synchronisation, capturable into a CUDA graph. */
+int mivit_allreduce_adamw(const mivit_peer_comm* comm, int32_t bucket, int64_t lo, int64_t hi, float* p, float* m, float* v,
+                          float beta1, float beta2, float eps, float weight_decay, int32_t advance_step, float* grad_sum,
+                          void* stream);
+/* In-place SUM all-reduce of n <= 512 floats at `buf` (local); `call` in [0,32) names the exchange within a step. */
+int mivit_allreduce_small(const mivit_peer_comm* comm, int32_t call, float* buf, int32_t n, void* stream);
+/* While set (non-NULL, world > 1) the synchronised-BatchNorm reductions of mivit_vit_forward / backward go through the peer
+ * segments (mivit_allreduce_small) instead of the host hook of mivit_set_allreduce_hook: plain kernels, capturable. */
+int mivit_set_bn_sync_comm(const mivit_peer_comm* comm);
+
 int32_t mivit_vit_param_count(const mivit_vit_config* cfg);                 /* -1 on a bad config */
 int mivit_vit_param_sizes(const mivit_vit_config* cfg, int64_t* sizes, int32_t max_count);
 int64_t mivit_vit_workspace_bytes(const mivit_vit_config* cfg, int32_t B);  /* -1 on a bad config */

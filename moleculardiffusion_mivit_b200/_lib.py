@@ -32,6 +32,11 @@ class KernelTime(ctypes.Structure):
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p)
 
 
+class PeerComm(ctypes.Structure):
+    """struct mivit_peer_comm (include/mivit.h)."""
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("segment", ctypes.c_void_p * 8)]
+
+
 class MivitError(RuntimeError):
     pass
 
@@ -64,6 +69,18 @@ def _declare(lib):
         "mivit_conv_rows_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
         "mivit_conv_rows_wgrad": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
         "mivit_linear_tf32": (i32, [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "mivit_comm_segment_bytes": (i64, [i64]),
+        "mivit_comm_grad_offset_bytes": (i64, []),
+        "mivit_comm_alloc": (i32, [i64, c.POINTER(vp)]),
+        "mivit_comm_free": (i32, [vp]),
+        "mivit_comm_ipc_handle": (i32, [vp, c.POINTER(c.c_uint8)]),
+        "mivit_comm_ipc_open": (i32, [c.POINTER(c.c_uint8), c.POINTER(vp)]),
+        "mivit_comm_ipc_close": (i32, [vp]),
+        "mivit_comm_set_lr": (i32, [c.POINTER(PeerComm), f32, vp]),
+        "mivit_comm_set_step": (i32, [c.POINTER(PeerComm), i64, vp]),
+        "mivit_allreduce_adamw": (i32, [c.POINTER(PeerComm), i32, i64, i64, vp, vp, vp, f32, f32, f32, f32, i32, vp, vp]),
+        "mivit_allreduce_small": (i32, [c.POINTER(PeerComm), i32, vp, i32, vp]),
+        "mivit_set_bn_sync_comm": (i32, [c.POINTER(PeerComm)]),
         "mivit_vit_param_count": (i32, [vp]),
         "mivit_vit_param_sizes": (i32, [vp, c.POINTER(c.c_int64), i32]),
         "mivit_vit_workspace_bytes": (i64, [vp, i32]),

@@ -82,6 +82,12 @@ int pool_tokens_bwd(const float* dout, float* dx, int B, int S, int E, int ld, i
 int mivit_bn_sync_world();                                      // 1 when no hook is registered
 int mivit_bn_sync(float* buf, long long n, cudaStream_t st);
 
+// peer_comm.cu: synchronised BatchNorm through the peer segments (plain kernels instead of the host hook)
+bool mivit_bn_peer_active();
+int mivit_bn_peer_world();
+void mivit_bn_peer_begin_step();
+int mivit_bn_peer_sync(float* buf, long long n, cudaStream_t st);
+
 // bn.cu
 int bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                 long long* num_batches, float* mean, float* invstd, float* scale, float* shift, int C, double count, float eps,

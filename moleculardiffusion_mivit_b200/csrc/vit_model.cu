@@ -321,8 +321,9 @@ int run_bn_finalize(const mivit_vit_config* c, Workspace& w, int i, const float*
 
 }  // namespace
 
-int mivit_bn_sync_world() { return g_ar_fn != nullptr ? g_ar_world : 1; }
+int mivit_bn_sync_world() { return mivit_bn_peer_active() ? mivit_bn_peer_world() : g_ar_fn != nullptr ? g_ar_world : 1; }
 int mivit_bn_sync(float* buf, long long n, cudaStream_t st) {
+  if (mivit_bn_peer_active()) return mivit_bn_peer_sync(buf, n, st);
   if (g_ar_fn == nullptr || g_ar_world <= 1) return MIVIT_OK;
   const int rc = g_ar_fn(buf, (int64_t)n, (void*)st, g_ar_user);
   if (rc != 0) {
@@ -396,6 +397,7 @@ static int vit_forward_impl(const mivit_vit_config* c, int32_t B, const float* x
   Workspace w;
   carve(c, B, workspace, w);
   g_linear_tc = c->conv_impl == 1;
+  if (training) mivit_bn_peer_begin_step();   // small-exchange call indices restart with every training forward
   const int E = c->E, HD = c->HD, F = c->F, S = F + (c->use_reg ? 1 : 0), H = c->H, P = c->P;
   const int NF = B * F, T = B * S;
   const float* p = params;

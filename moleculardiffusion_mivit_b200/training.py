@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from .models import _CudaViT, TrajectorySource
-from .parallel import allreduce_sum_, broadcast_state_
+from .parallel import PeerCommunicator, allreduce_sum_, broadcast_state_
 
 __all__ = ["MiViTTrainer"]
 
@@ -58,12 +58,23 @@ class MiViTTrainer:
         if any(not p.requires_grad for p in model.parameters()):
             # the fused AdamW walks the whole flat buffer; torch.optim.AdamW would skip frozen parameters
             raise NotImplementedError("MiViTTrainer updates every parameter: requires_grad=False parameters are not supported")
+        self.comm = None
+        self._side = None
         if self.world > 1:
             # like DistributedDataParallel: every rank starts from rank 0's parameters, BatchNorm statistics and (zero) moments
             bufs = [model._flat]
             if model._is_deep():
                 bufs += [model._bn_flat, model._bn_nbt]
             broadcast_state_(bufs, self.group)
+            if self.fused_allreduce:
+                # peer-memory data path (csrc/peer_comm.cu): the model's flat gradient buffer moves into this rank's segment, the
+                # gradient all-reduce + AdamW become one kernel per bucket and -- being ordinary kernels -- part of the step's graph
+                self.comm = PeerCommunicator(n + 4, self.group)
+                model._grad_flat = self.comm.grad[:n + 4]
+                self._gsum = torch.zeros(n + 4, dtype=torch.float32, device=dev)
+                self._side = torch.cuda.Stream()
+                self.comm.set_lr(self.lr)
+                self.comm.set_step(self.step_count)
 
     def _allreduce_hook(self, buf, n_floats, stream, user):
         """C callback (mivit_allreduce_fn): SUM all-reduce of n_floats fp32 at device address `buf`, which always lies inside
@@ -81,13 +92,20 @@ class MiViTTrainer:
             return 1
 
     def launch_description(self):
+        if self.comm is not None:
+            return ("ONE CUDA-graph replay per step: forward+loss+backward+peer-memory all-reduce+AdamW" if self.cuda_graph
+                    else "kernel by kernel")
         if self.sync_bn and self.model._is_deep():
-            return "kernel by kernel (synchronised BatchNorm)"
+            return "kernel by kernel (synchronised BatchNorm through the host all-reduce hook)"
         return "CUDA-graph replay of forward+loss+backward, eager AdamW" if self.cuda_graph else "kernel by kernel"
 
     def allreduce_description(self):
         if self.world == 1:
             return None
+        if self.comm is not None:
+            two = self.overlap_allreduce and self.model._image_embedding() is not None
+            return ("fused peer-memory all-reduce + AdamW kernel (no NCCL on the data path), " +
+                    ("two buckets, the non-embedding one overlapped with the image-embedding backward" if two else "one bucket"))
         if self.sync_bn and self.model._is_deep():
             return "one NCCL all-reduce after the backward"
         if self.overlap_allreduce and self.model._image_embedding() is not None:
@@ -98,6 +116,13 @@ class MiViTTrainer:
     def scheduler_step(self):
         self.epoch += 1
         self.lr = self.base_lr * self.gamma ** (self.epoch // self.step_size)
+        if self.comm is not None:
+            self.comm.set_lr(self.lr)        # the fused all-reduce + AdamW kernel reads lr from the segment (graph replays too)
+
+    def reduced_gradient(self):
+        """The all-reduced SUM of the per-rank gradients of the last step, [n_params] (data-parallel runs)."""
+        n = self.model._n_params
+        return self._gsum[:n] if self.comm is not None else self.model._grad_flat[:n]
 
     def _buffers(self, rows):
         s = self._scratch.get(rows)
@@ -153,9 +178,11 @@ class MiViTTrainer:
             src.frames = self._frames_buffer(B, Fr, cfg.P)
         self.step_count += 1
         L = _lib.lib()
+        overlap = self.overlap_allreduce and self.world > 1 and model._image_embedding() is not None
+        if self.comm is not None:
+            return self._fused_dp_step(x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap)
         if self.sync_bn and deep:
             return self._sync_bn_step(x, src, target, features, cfg, B, ws, pred, dpred)
-        overlap = self.overlap_allreduce and self.world > 1 and model._image_embedding() is not None
         ent = self._graph_entry(x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap) if self.cuda_graph else None
         n, ne = model._n_params, self._n_embedding(cfg)
         grad = model._grad_flat
@@ -201,6 +228,60 @@ class MiViTTrainer:
                                       _lib.current_stream()))
         self.last_pred = pred
         return self.loss
+
+    # ---- data-parallel step on the peer-memory path: everything is a kernel of this library, so the whole step is one graph ----
+    def _fused_dp_step(self, x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap):
+        model = self.model
+        L = _lib.lib()
+        bn_sync = self.sync_bn and deep
+        if bn_sync:
+            _lib.check(L.mivit_set_bn_sync_comm(self.comm.ref()))
+        try:
+            ent = self._graph_entry(x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap, fused=True) if self.cuda_graph else None
+            if ent is not None:
+                graphs, gx, gt, gf, counts, gsrc = ent
+                if gx is not None:
+                    gx.copy_(x)
+                if gsrc is not None:
+                    gsrc.traj.copy_(src.traj)
+                    gsrc.seq_offset_dev.fill_(src.seq_offset)
+                gt.copy_(target)
+                if gf is not None:
+                    gf.copy_(features)
+                graphs[0].replay()
+                L.mivit_add_launch_count(counts[0])
+            else:
+                self._fused_dp_body(cfg, B, x, src, features, target, ws, pred, dpred, deep, overlap)
+        finally:
+            if bn_sync:
+                L.mivit_set_bn_sync_comm(None)
+        model._gen += 1
+        self.last_pred = pred
+        return self.loss
+
+    def _allreduce_adamw(self, bucket, lo, hi, advance):
+        model = self.model
+        _lib.check(_lib.lib().mivit_allreduce_adamw(self.comm.ref(), bucket, lo, hi, _lib.ptr(model._flat), _lib.ptr(self.m),
+                                                    _lib.ptr(self.v), self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                                    int(advance), _lib.ptr(self._gsum), _lib.current_stream()))
+
+    def _fused_dp_body(self, cfg, B, x, src, features, target, ws, pred, dpred, deep, overlap):
+        """forward, MSE, backward and the fused all-reduce + AdamW kernels; with `overlap` the bucket of everything but the image
+        embedding goes out on a side stream while the image-embedding backward runs (fork / join by events, capturable)."""
+        n = self.model._n_params
+        if not overlap:
+            self._forward_loss_backward_part(0, cfg, B, x, src, features, target, ws, pred, dpred, deep)
+            self._allreduce_adamw(0, 0, n, True)
+            return
+        ne4 = (self._n_embedding(cfg) + 3) // 4 * 4      # bucket boundary on a 16-byte boundary (the late bucket takes the slack)
+        cur = torch.cuda.current_stream()
+        self._forward_loss_backward_part(1, cfg, B, x, src, features, target, ws, pred, dpred, deep)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self._allreduce_adamw(0, ne4, n, False)
+        self._forward_loss_backward_part(2, cfg, B, x, src, features, target, ws, pred, dpred, deep)
+        cur.wait_stream(self._side)                       # bucket 0 is complete (and read the step count) before bucket 1 advances it
+        self._allreduce_adamw(1, 0, ne4, True)
 
     def _n_embedding(self, cfg):
         """floats of the image-embedding block at the head of the flat parameter / gradient buffer"""
@@ -271,7 +352,7 @@ class MiViTTrainer:
         self.last_pred = pred
         return self.loss
 
-    def _graph_entry(self, x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap):
+    def _graph_entry(self, x, src, target, features, cfg, B, ws, pred, dpred, deep, overlap, fused=False):
         """CUDA graphs of forward + loss + backward for this batch shape: one graph, or two when the gradient all-reduce is
         overlapped (graph 1 ends where the non-embedding gradients are final, graph 2 is the image-embedding backward).
         Returns None on the first call of a shape: that step runs kernel by kernel -- it also performs every lazy
@@ -283,7 +364,8 @@ class MiViTTrainer:
             self._graphs.clear()
             self._graph_ws, self._graph_flat = ws, model._flat
         key = (B, None if x is None else tuple(x.shape[1:]), None if features is None else tuple(features.shape[1:]), bool(overlap),
-               None if src is None else (src.T, bytes(src.prm), src.seed), pred.shape[0])   # render scalars are captured by value
+               None if src is None else (src.T, bytes(src.prm), src.seed), pred.shape[0], bool(fused),
+               bool(self.sync_bn))   # render scalars are captured by value
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "pending"
@@ -299,7 +381,16 @@ class MiViTTrainer:
             graphs, counts = [], []
             cap = torch.cuda.Stream()
             cap.wait_stream(torch.cuda.current_stream())
-            for part in ((1, 2) if overlap else (0,)):
+            if fused:       # the whole data-parallel step, collectives included, is one graph
+                n0 = L.mivit_launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap):
+                    self._fused_dp_body(cfg, B, gx, gsrc, gf, gt, ws, pred, dpred, deep, overlap)
+                n_cap = int(L.mivit_launch_count() - n0)
+                L.mivit_add_launch_count(-n_cap)
+                graphs.append(g)
+                counts.append(n_cap)
+            for part in (() if fused else (1, 2) if overlap else (0,)):
                 n0 = L.mivit_launch_count()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=cap):

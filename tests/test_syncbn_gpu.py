@@ -33,21 +33,21 @@ def _batch():
     return sd, torch.cat([x, x2]).contiguous(), torch.cat([tgt, t2]).contiguous()
 
 
-def _step(sd, x, tgt, sync_bn):
+def _step(sd, x, tgt, sync_bn, fused=False, graph=False, steps=1):
     import torch
     from test_vit_gpu import build
     from moleculardiffusion_mivit_b200.training import MiViTTrainer
     model = build(NAME)
     model.load_state_dict(sd)
     model.cuda().train()
-    tr = MiViTTrainer(model, lr=1e-4, sync_bn=sync_bn)
-    loss = tr.train_step(x.cuda(), tgt.cuda())
+    tr = MiViTTrainer(model, lr=1e-4 if steps == 1 else 0.0, sync_bn=sync_bn, fused_allreduce=fused, cuda_graph=graph)
+    for _ in range(steps):       # (lr = 0 for the multi-step graph variant: every step sees the same weights)
+        loss = tr.train_step(x.cuda(), tgt.cuda())
     torch.cuda.synchronize()
-    n = model._n_params
-    return tr, float(loss.item()), model._grad_flat[:n].detach().cpu().clone(), model._bn_flat.detach().cpu().clone()
+    return tr, float(loss.item()), tr.reduced_gradient().detach().cpu().clone(), model._bn_flat.detach().cpu().clone()
 
 
-def _worker(rank, world, port, backend, out_dir):
+def _worker(rank, world, port, backend, out_dir, mode):
     import torch
     import torch.distributed as dist
     from moleculardiffusion_mivit_b200.parallel import shard_slices
@@ -56,25 +56,30 @@ def _worker(rank, world, port, backend, out_dir):
     dist.init_process_group(backend, rank=rank, world_size=world)
     sd, x, tgt = _batch()
     sl = shard_slices(x.shape[0], world)[rank]
-    tr, loss, grad, bn = _step(sd, x[sl], tgt[sl], True)
-    assert tr.sync_bn and tr.world == world
-    # grad_flat holds the all-reduced SUM of the per-rank mean-loss gradients; AdamW applied 1/W
+    # "hook": statistics through the host all-reduce callback (torch.distributed), kernel by kernel; "peer": through the peer
+    # segments (plain kernels); "peer_graph": the same captured -- step 1 runs eagerly, steps 2 and 3 replay ONE graph that
+    # contains the 12 small all-reduces and the fused gradient all-reduce + AdamW
+    tr, loss, grad, bn = _step(sd, x[sl], tgt[sl], True, fused=mode != "hook", graph=mode == "peer_graph",
+                               steps=3 if mode == "peer_graph" else 1)
+    assert tr.sync_bn and tr.world == world and (tr.comm is not None) == (mode != "hook")
+    # the reduced gradient is the SUM of the per-rank mean-loss gradients; AdamW applied 1/W
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), loss=loss, grad=(grad / world).numpy(), bn=bn.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_sync_bn_step_equals_single_process(tmp_path):
+@pytest.mark.parametrize("mode", ["hook", "peer", "peer_graph"])
+def test_two_rank_sync_bn_step_equals_single_process(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
     backend = os.environ.get("MIVIT_TEST_BACKEND", "gloo")
     if backend == "nccl" and torch.cuda.device_count() < 2:
         pytest.skip("nccl needs two GPUs")
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), backend, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), backend, str(tmp_path), mode), nprocs=world, join=True)
     r = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % i)) for i in range(world)]
     sd, x, tgt = _batch()
-    _, loss, grad, bn = _step(sd, x, tgt, False)
+    _, loss, grad, bn = _step(sd, x, tgt, False, steps=3 if mode == "peer_graph" else 1)
     # same all-reduced gradient and the same (global) running statistics on both ranks
     assert np.array_equal(r[0]["grad"], r[1]["grad"])
     assert np.allclose(r[0]["bn"], r[1]["bn"], rtol=0, atol=0)
