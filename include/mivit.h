@@ -332,6 +332,41 @@ int mivit_vit_train_step_traj(const mivit_vit_config* cfg, int32_t B, const doub
                               float* loss, float* dpred, float lr, float beta1, float beta2, float eps, float weight_decay,
                               int64_t step, int32_t apply_update, void* stream);
 
+/* ------------------------------------------------- CNN baselines ----------------
+ * Replaces helpers/models.py:600-772: BasicBlock, LightResNet, MultiImageResNet (ext_dim == 0) and LightImagesFeaturesResNet /
+ * MultiImageFeatureResNet (ext_dim > 0) with num_blocks = [1,1,1] -- the ResNet every reference experiment trains beside its
+ * ViTs (Experiments/PSFNoise/trainSettingsPSFNoise.py:114, trainSettingsImagesFeatures.py:170-173).  fp32, train-mode BatchNorm.
+ * Flat parameter order (= state_dict order): resnet.conv1.weight, resnet.bn1.{weight,bias}, resnet.layer1.0.{conv1.weight,
+ * bn1.weight, bn1.bias, conv2.weight, bn2.weight, bn2.bias}, resnet.layer{2,3}.0.{the same six, shortcut.0.weight,
+ * shortcut.1.weight, shortcut.1.bias}, resnet.fc1.{weight,bias}, then resnet.fc2.{weight,bias} (MultiImageResNet) or
+ * mlp.0.{weight,bias}, mlp.2.{weight,bias} (MultiImageFeatureResNet).  BatchNorm running statistics: flat [mean C | var C] for
+ * bn1, layer1.0.{bn1,bn2}, layer2.0.{bn1,bn2,shortcut.1}, layer3.0.{bn1,bn2,shortcut.1} (1344 floats) + int64[9] counters. */
+typedef struct mivit_resnet_config {
+  int32_t P, F;              /* image size, frames per sequence                                                   */
+  int32_t feature_size;      /* LightResNet feature_size (64)                                                     */
+  int32_t ext_dim;           /* 0: MultiImageResNet; > 0: MultiImageFeatureResNet with external_dim features      */
+  int32_t hidden;            /* MultiImageFeatureResNet hidden_size (128); ignored when ext_dim == 0              */
+  int32_t single_prediction; /* MultiImageResNet: mean of the per-frame predictions [B,1] (1) or all of them [B,F,1] */
+  int32_t activation;        /* 0 = nn.ReLU (the only one on the CUDA path)                                       */
+  float bn_eps, bn_momentum;
+} mivit_resnet_config;
+int32_t mivit_resnet_param_count(const mivit_resnet_config* cfg);
+int mivit_resnet_param_sizes(const mivit_resnet_config* cfg, int64_t* sizes, int32_t max_count);
+int64_t mivit_resnet_workspace_bytes(const mivit_resnet_config* cfg, int32_t B);
+int32_t mivit_resnet_pred_rows(const mivit_resnet_config* cfg, int32_t B);
+/* x: [B,F,P,P] fp32; ext: [B,ext_dim] or NULL; pred: [pred_rows,1].  Same conventions as mivit_vit_forward / backward /
+ * train_step (grads is overwritten; the backward follows the forward that last used `workspace`). */
+int mivit_resnet_forward(const mivit_resnet_config* cfg, int32_t B, const float* x, const float* ext, const float* params,
+                         float* bn_running, int64_t* bn_num_batches, void* workspace, float* pred, int32_t training,
+                         void* stream);
+int mivit_resnet_backward(const mivit_resnet_config* cfg, int32_t B, const float* x, const float* ext, const float* dpred,
+                          const float* params, float* grads, void* workspace, void* stream);
+int mivit_resnet_train_step(const mivit_resnet_config* cfg, int32_t B, const float* x, const float* ext, const float* target,
+                            float* params, float* grads, float* adam_m, float* adam_v, float* bn_running,
+                            int64_t* bn_num_batches, void* workspace, float* pred, float* loss, float* dpred, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, int64_t step, int32_t apply_update,
+                            void* stream);
+
 /* nn.MSELoss() (mean) and its gradient w.r.t. pred (Experiments/PSFNoise/trainSettingsPSFNoise.py:31). */
 int mivit_mse_loss(const float* pred, const float* target, int32_t n, float* loss, float* dpred,
                    void* stream);

@@ -32,6 +32,13 @@ class KernelTime(ctypes.Structure):
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p)
 
 
+class ResnetConfig(ctypes.Structure):
+    """struct mivit_resnet_config (include/mivit.h)."""
+    _fields_ = [("P", ctypes.c_int32), ("F", ctypes.c_int32), ("feature_size", ctypes.c_int32), ("ext_dim", ctypes.c_int32),
+                ("hidden", ctypes.c_int32), ("single_prediction", ctypes.c_int32), ("activation", ctypes.c_int32),
+                ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float)]
+
+
 class PeerComm(ctypes.Structure):
     """struct mivit_peer_comm (include/mivit.h)."""
     _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("segment", ctypes.c_void_p * 8)]
@@ -93,6 +100,14 @@ def _declare(lib):
         "mivit_vit_backward_traj": (i32, [vp, i32, vp, i32, c.POINTER(RenderParams), u64, u64, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
         "mivit_vit_train_step_traj": (i32, [vp, i32, vp, i32, c.POINTER(RenderParams), u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                             vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i64, i32, vp]),
+        "mivit_resnet_param_count": (i32, [vp]),
+        "mivit_resnet_param_sizes": (i32, [vp, c.POINTER(c.c_int64), i32]),
+        "mivit_resnet_workspace_bytes": (i64, [vp, i32]),
+        "mivit_resnet_pred_rows": (i32, [vp, i32]),
+        "mivit_resnet_forward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "mivit_resnet_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "mivit_resnet_train_step": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                          f32, f32, f32, f32, f32, i64, i32, vp]),
         "mivit_mse_loss": (i32, [vp, vp, i32, vp, vp, vp]),
         "mivit_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]),
         "mivit_vit_train_step": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,

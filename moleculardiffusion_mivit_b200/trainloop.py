@@ -51,9 +51,10 @@ def single_state(N, T, Ds, seed=None, seq_offset=0):
 
 
 class _TorchTrainer:
-    """Same interface as MiViTTrainer for models OUTSIDE this package's scope -- the reference experiments train a CNN baseline
-    (helpers/models.py:686 MultiImageResNet, imported from the reference) beside every ViT, with the same criterion, optimiser
-    and schedule (trainSettingsPSFNoise.py:119-120).  Such a model is an ordinary nn.Module and runs on stock PyTorch CUDA."""
+    """Same interface as MiViTTrainer for models OUTSIDE this package (e.g. the ImagesFeatures experiment's feature-only MLP
+    `ft_mlp`, an nn.Sequential): same criterion, optimiser and schedule (trainSettingsPSFNoise.py:119-120) on stock PyTorch CUDA.
+    The reference's own models -- the ViTs and the CNN baselines MultiImageResNet / MultiImageFeatureResNet -- have CUDA-library
+    trainers (training.MiViTTrainer, baselines.CnnTrainer)."""
 
     def __init__(self, model, lr=1e-4, step_size=5, gamma=0.9):
         self.model = model.cuda()
@@ -113,8 +114,11 @@ class ExperimentLoop:
 
     @staticmethod
     def _make_trainer(m, lr, step_size, gamma):
+        from .baselines import CnnTrainer, _CudaResNet
         if isinstance(m, _CudaViT):
             return MiViTTrainer(m, lr=lr, step_size=step_size, gamma=gamma)
+        if isinstance(m, _CudaResNet):        # the experiments' CNN baseline (helpers/models.py:686 MultiImageResNet & co.)
+            return CnnTrainer(m, lr=lr, step_size=step_size, gamma=gamma)
         return _TorchTrainer(m, lr=lr, step_size=step_size, gamma=gamma)
 
     # -- one dataset refresh (:121-173) ---------------------------------------------------------------------------
