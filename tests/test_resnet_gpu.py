@@ -73,8 +73,8 @@ def test_fused_train_step_and_eval_mode(golden_dir, name):
         upd, upd_ref = msd[k].cpu() - sd[k], want - sd[k]
         assert (msd[k].cpu() - want).abs().max().item() <= 2.1e-4, k              # first AdamW step: |update| ~ lr
         if float(gr.norm()) > 1e-5 * gmax:
-            agree = (torch.sign(upd) == torch.sign(upd_ref)).float().mean().item()
-            assert agree > 0.995, (k, agree)
+            differ = int((torch.sign(upd) != torch.sign(upd_ref)).sum())          # near-zero gradients may flip sign (fp32 order)
+            assert differ <= max(2, 0.005 * upd.numel()), (k, differ, upd.numel())
     assert int(model.resnet.bn1.num_batches_tracked) == 1
     # eval mode: running statistics; the reference semantics for inference, and gradients are refused
     ref_sd = dict(sd)
