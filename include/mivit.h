@@ -262,10 +262,11 @@ int mivit_comm_set_step(const mivit_peer_comm* comm, int64_t steps_done, void* s
  * [lo, hi) (lo % 4 == 0): g = sum over ranks (rank order) of the peers' gradient replicas, read straight from peer memory;
  * p, m, v updated with grad_scale = 1 / world, lr and step from the segment.  advance_step != 0 on the LAST bucket of a step.
  * grad_sum (optional, local, same offsets): receives the reduced gradient.  bucket in [0,4): exchanges that may be in flight
- * concurrently need different buckets.  One kernel, no host synchronisation, capturable into a CUDA graph. */
+ * concurrently need different buckets.  max_ctas: 0 = one CTA per SM; an exchange that overlaps other kernels should ask for
+ * a few dozen (it is latency bound).  One kernel, no host synchronisation, capturable into a CUDA graph. */
 int mivit_allreduce_adamw(const mivit_peer_comm* comm, int32_t bucket, int64_t lo, int64_t hi, float* p, float* m, float* v,
                           float beta1, float beta2, float eps, float weight_decay, int32_t advance_step, float* grad_sum,
-                          void* stream);
+                          int32_t max_ctas, void* stream);
 /* In-place SUM all-reduce of n <= 512 floats at `buf` (local); `call` in [0,32) names the exchange within a step. */
 int mivit_allreduce_small(const mivit_peer_comm* comm, int32_t call, float* buf, int32_t n, void* stream);
 /* While set (non-NULL, world > 1) the synchronised-BatchNorm reductions of mivit_vit_forward / backward go through the peer

@@ -85,7 +85,7 @@ def _declare(lib):
         "mivit_comm_ipc_close": (i32, [vp]),
         "mivit_comm_set_lr": (i32, [c.POINTER(PeerComm), f32, vp]),
         "mivit_comm_set_step": (i32, [c.POINTER(PeerComm), i64, vp]),
-        "mivit_allreduce_adamw": (i32, [c.POINTER(PeerComm), i32, i64, i64, vp, vp, vp, f32, f32, f32, f32, i32, vp, vp]),
+        "mivit_allreduce_adamw": (i32, [c.POINTER(PeerComm), i32, i64, i64, vp, vp, vp, f32, f32, f32, f32, i32, vp, i32, vp]),
         "mivit_allreduce_small": (i32, [c.POINTER(PeerComm), i32, vp, i32, vp]),
         "mivit_set_bn_sync_comm": (i32, [c.POINTER(PeerComm)]),
         "mivit_vit_param_count": (i32, [vp]),

@@ -272,7 +272,7 @@ extern "C" int mivit_comm_set_step(const mivit_peer_comm* c, int64_t step, void*
 
 extern "C" int mivit_allreduce_adamw(const mivit_peer_comm* c, int32_t bucket, int64_t lo, int64_t hi, float* p, float* m, float* v,
                                      float beta1, float beta2, float eps, float weight_decay, int32_t advance_step, float* grad_sum,
-                                     void* stream) {
+                                     int32_t max_ctas, void* stream) {
   Peers pr;
   int rc = to_peers(c, pr);
   if (rc) return rc;
@@ -283,7 +283,8 @@ extern "C" int mivit_allreduce_adamw(const mivit_peer_comm* c, int32_t bucket, i
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   long long blocks = ((hi4 - lo) / 4 + 255) / 256;
-  if (blocks > sms) blocks = sms;             // one co-resident wave: every CTA spins on the start barrier
+  if (blocks > sms) blocks = sms;             // at most one CTA per SM: every CTA spins on the start barrier
+  if (max_ctas > 0 && blocks > max_ctas) blocks = max_ctas;   // an exchange overlapped with compute leaves the SMs to the compute
   if (blocks < 1) blocks = 1;
   MivitProfScope prof("allreduce_adamw", (double)(hi4 - lo) * 4.0 * (pr.world + 6), (cudaStream_t)stream);
   allreduce_adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pr, bucket, lo, hi4, p, m, v, beta1, beta2, eps,

@@ -259,11 +259,11 @@ class MiViTTrainer:
         self.last_pred = pred
         return self.loss
 
-    def _allreduce_adamw(self, bucket, lo, hi, advance):
+    def _allreduce_adamw(self, bucket, lo, hi, advance, max_ctas=0):
         model = self.model
         _lib.check(_lib.lib().mivit_allreduce_adamw(self.comm.ref(), bucket, lo, hi, _lib.ptr(model._flat), _lib.ptr(self.m),
                                                     _lib.ptr(self.v), self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                                    int(advance), _lib.ptr(self._gsum), _lib.current_stream()))
+                                                    int(advance), _lib.ptr(self._gsum), int(max_ctas), _lib.current_stream()))
 
     def _fused_dp_body(self, cfg, B, x, src, features, target, ws, pred, dpred, deep, overlap):
         """forward, MSE, backward and the fused all-reduce + AdamW kernels; with `overlap` the bucket of everything but the image
@@ -278,7 +278,7 @@ class MiViTTrainer:
         self._forward_loss_backward_part(1, cfg, B, x, src, features, target, ws, pred, dpred, deep)
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            self._allreduce_adamw(0, ne4, n, False)
+            self._allreduce_adamw(0, ne4, n, False, max_ctas=24)     # shares the GPU with the image-embedding backward
         self._forward_loss_backward_part(2, cfg, B, x, src, features, target, ws, pred, dpred, deep)
         cur.wait_stream(self._side)                       # bucket 0 is complete (and read the step count) before bucket 1 advances it
         self._allreduce_adamw(1, 0, ne4, True)
