@@ -463,7 +463,9 @@ def test_product_shape_B32_matches_oracle(feat):
     model, cfg, sd = _deep_model(13, feat)
     x, tgt = _bench_frames(32)
     feats = torch.randn(32, 25, generator=torch.Generator().manual_seed(2)).cuda() if feat else None
-    _check_against_oracle(model, cfg, sd, x, tgt, feats, 3e-2, 5e-2, 8e-2)
+    # measured (profiles/r02_parity.md): embedding gradients <= 1.5e-2, transformer / head <= 3.7e-2 (tf32 q/k projections); the
+    # feature projector sees the 32 per-sample dpred errors un-averaged (5.4e-2 with late fusion) -> 8e-2 with features
+    _check_against_oracle(model, cfg, sd, x, tgt, feats, 3e-2, 8e-2 if feat else 5e-2, 3e-2)
 
 
 def test_bench_shape_B1024_matches_oracle():
@@ -471,7 +473,7 @@ def test_bench_shape_B1024_matches_oracle():
     oracle on the same rendered frames (the CPU oracle needs ~20-30 s on the box's cores)."""
     model, cfg, sd = _deep_model(13)
     x, tgt = _bench_frames(1024)
-    _check_against_oracle(model, cfg, sd, x, tgt, None, 3e-2, 5e-2, 8e-2)
+    _check_against_oracle(model, cfg, sd, x, tgt, None, 3e-2, 5e-2, 3e-2)
 
 
 def test_thirty_step_training_curve_follows_oracle():
