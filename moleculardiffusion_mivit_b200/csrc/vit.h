@@ -78,6 +78,16 @@ int tokens_finish_bwd(const float* dtok, float* dreg, float* dproj, float* dpos,
 int pool_tokens(const float* x, float* out, int B, int S, int E, int ld, int use_reg, cudaStream_t st);
 int pool_tokens_bwd(const float* dout, float* dx, int B, int S, int E, int ld, int use_reg, cudaStream_t st);
 
+// encoder_fused.cu -- one encoder layer (q/k/v, attention, out-proj + LN, FFN + LN) as one persistent tcgen05 kernel
+struct EncoderLayerIO {
+  const float* x;   // [B*S, E] layer input
+  const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo, *g1, *be1, *w1, *bf1, *w2, *bf2, *g2, *be2;
+  // everything the backward reads: [B*S, E] tensors, hact [B*S, HD], lse [B, H, S], LayerNorm row statistics [B*S]
+  float *q, *k, *v, *ctx, *lse, *z1, *m1, *r1, *x1, *hact, *z2, *m2, *r2, *x2;
+};
+bool encoder_fused_supported(int B, int S, int E, int HD, int H);
+int encoder_layer_fwd(const EncoderLayerIO& io, int B, int S, int E, int HD, int H, float ln_eps, cudaStream_t st);
+
 // synchronised BatchNorm hook (vit_model.cu): SUM all-reduce of a small device buffer over the data-parallel group
 int mivit_bn_sync_world();                                      // 1 when no hook is registered
 int mivit_bn_sync(float* buf, long long n, cudaStream_t st);

@@ -4,6 +4,7 @@
 // Python module mirrors the order by state_dict key); gradients and AdamW moments use the same
 // offsets, so the optimiser and the data-parallel all-reduce are single passes over 2 MB.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -491,9 +492,22 @@ static int vit_forward_impl(const mivit_vit_config* c, int32_t B, const float* x
   CK(tokens_finish(w.tok, c->use_reg ? p + L.reg : nullptr, (c->use_feat && c->fusion == 0 && c->use_reg) ? w.fp_out : nullptr,
                    c->use_pos ? p + L.pos : nullptr, B, S, E, st));
   const float* xin = w.tok;
+  const bool fused_layers = g_linear_tc && c->activation == 0 && encoder_fused_supported(B, S, E, HD, H) && !getenv("MIVIT_NO_FUSED_ENCODER");
   for (int l = 0; l < c->L; ++l) {
     const auto& Y = L.lyr[l];
     LayerWS& y = w.lyr[l];
+    if (fused_layers) {   // the whole layer in one persistent kernel (encoder_fused.cu); writes what the backward below reads
+      EncoderLayerIO io;
+      io.x = xin;
+      io.wq = p + Y.q_w; io.bq = p + Y.q_b; io.wk = p + Y.k_w; io.bk = p + Y.k_b; io.wv = p + Y.v_w; io.bv = p + Y.v_b;
+      io.wo = p + Y.o_w; io.bo = p + Y.o_b; io.g1 = p + Y.n1_g; io.be1 = p + Y.n1_b; io.w1 = p + Y.f1_w; io.bf1 = p + Y.f1_b;
+      io.w2 = p + Y.f2_w; io.bf2 = p + Y.f2_b; io.g2 = p + Y.n2_g; io.be2 = p + Y.n2_b;
+      io.q = y.q; io.k = y.k; io.v = y.v; io.ctx = y.ctx; io.lse = y.probs; io.z1 = y.z1; io.m1 = y.m1; io.r1 = y.r1; io.x1 = y.x1;
+      io.hact = y.hact; io.z2 = y.z2; io.m2 = y.m2; io.r2 = y.r2; io.x2 = y.x2;
+      CK(encoder_layer_fwd(io, B, S, E, HD, H, c->ln_eps, st));
+      xin = y.x2;
+      continue;
+    }
     if (g_linear_tc && linear_tc_supported(T, E, E) && al16(xin) && al16(p + Y.q_w) && al16(p + Y.k_w) && al16(p + Y.v_w) &&
         al16(p + Y.q_b) && al16(p + Y.k_b) && al16(p + Y.v_b) && al16(y.q) && al16(y.k) && al16(y.v)) {
       // the three projections read the same tokens and are independent: one launch, three problems (linear_tc.cu)

@@ -576,3 +576,48 @@ def test_forward_and_train_step_from_trajectories(golden_dir, kind, P, E):
     tol = 2e-2 if kind == "deepresnet" else 1e-4
     assert np.allclose(runs[0], runs[1], rtol=tol, atol=1e-6), runs
     assert np.allclose(runs[0], runs[2], rtol=tol, atol=1e-6), runs
+
+
+@pytest.mark.parametrize("emb,E,H,HD,Lyr,P,Fr,B,pos,reg", [
+    ("linear", 64, 4, 128, 6, 9, 30, 40, True, True),          # S = 31: four sequences per 128-row tile, last tile partial
+    ("linear", 64, 4, 128, 2, 9, 60, 12, False, True),         # S = 61: two sequences per tile, two key passes per lane
+    ("cnn", 32, 2, 64, 3, 9, 20, 30, True, False),             # _s size: E = 32, mean pooling, S = 20 (six sequences per tile)
+    ("linear", 64, 4, 128, 2, 9, 63, 9, False, True),          # S = 64: the largest fused shape, two sequences per tile
+])
+def test_fused_encoder_layer_matches_unfused_path_and_oracle(emb, E, H, HD, Lyr, P, Fr, B, pos, reg):
+    """csrc/encoder_fused.cu: the persistent per-layer kernel (tf32 tcgen05 GEMMs chained through shared memory / TMEM, in-register
+    softmax and LayerNorm) against the unfused kernels (MIVIT_NO_FUSED_ENCODER=1) -- prediction and every gradient, i.e. every
+    tensor the fused forward hands to the backward -- and against the fp32 oracle within tf32 tolerance."""
+    import torch
+    import torch.nn.functional as F
+    from moleculardiffusion_mivit_b200 import models as M
+    torch.manual_seed(E + Fr)
+    cls = {"linear": M.LinearProjectionEmbedding, "cnn": M.CNNEmbedding}[emb]
+    model = M.GeneralTransformer(cls, {"patch_size": P, "embed_dim": E}, E, H, HD, Lyr, M.MLPHead, F.relu, 0.0, pos, reg, True)
+    sd = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+    cfg = dict(embedding=emb, embed_dim=E, num_heads=H, num_layers=Lyr, activation="relu", use_pos_encoding=pos, use_regression_token=reg)
+    g = torch.Generator().manual_seed(5)
+    x = 0.1 + 0.25 * torch.randn((B, Fr, P, P), generator=g).abs()
+    tgt = torch.rand((B, 1), generator=g)
+    model.cuda().train()
+    outs = []
+    for no_fused in ("1", ""):
+        if no_fused:
+            os.environ["MIVIT_NO_FUSED_ENCODER"] = no_fused
+        else:
+            os.environ.pop("MIVIT_NO_FUSED_ENCODER", None)
+        model.zero_grad()
+        pred = model(x.cuda())
+        F.mse_loss(pred, tgt.cuda()).backward()
+        outs.append((pred.detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()}))
+    (p0, g0), (p1, g1) = outs
+    assert (p0 - p1).abs().max().item() < 2e-3 * max(1.0, p0.abs().max().item())        # both tf32; different summation order
+    gmax = max(float(v.norm()) for v in g0.values())
+    for k in g0:
+        if float(g0[k].norm()) > 1e-4 * gmax:
+            assert relnorm(g1[k], g0[k]) < 2e-2, (k, relnorm(g1[k], g0[k]))
+    ref_pred, _, ref_g, _ = vo.loss_and_grads(sd, cfg, x, tgt, None)
+    assert (p1 - ref_pred).abs().max().item() < 5e-3 * max(1.0, ref_pred.abs().max().item())
+    for k in g1:
+        if float(ref_g[k].norm()) > 1e-4 * gmax:
+            assert relnorm(g1[k], ref_g[k]) < 5e-2, (k, relnorm(g1[k], ref_g[k]))
