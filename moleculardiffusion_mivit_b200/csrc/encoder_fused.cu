@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
   constexpr int ROW_BYTES = kRows * LD * 4;
   constexpr int HS_BYTES = HD * 512;        // [HD/4][128][16 B]
   static_assert(HS_BYTES <= 2 * ROW_BYTES, "the hidden tile aliases the k / v tiles");
-  static_assert(HD % 64 == 0 && E % 32 == 0 && D % 4 == 0, "tile shapes");
+  static_assert(HD % E == 0 && E % 32 == 0 && D % 4 == 0, "tile shapes");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Xs = smem;                                   // A operand: x, then ctx, then x1
   uint8_t* Wa = Xs + XS_BYTES;                          // W_qkv, then W_1
@@ -327,13 +327,13 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
     umma::fence_after_sync();
     __syncthreads();               // staging tiles consumed: Hs (aliases Ks / Vs) may be written
 #pragma unroll 1
-    for (int half = 0; half < HD / 64; ++half) {            // 64 hidden columns at a time: A operand + staged copy to HBM
+    for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: A operand + staged copy to HBM
       if (warp < 4) {
         const int r = warp * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int c0 = half * 64 + g * 32;
+        for (int g = 0; g < E / 32; ++g) {
+          const int c0 = chunk * E + g * 32;
           float v[32];
           umma::tmem_ld32(trow + (uint32_t)c0, v);
 #pragma unroll
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
         }
       }
       __syncthreads();
-      copy_out(Qs, LD, a.hact, row0, nrows, 64, HD, half * 64, tid);
+      copy_out(Qs, LD, a.hact, row0, nrows, E, HD, chunk * E, tid);
       __syncthreads();
     }
     if (warp < 4) umma::fence_before_sync();
