@@ -49,17 +49,20 @@ struct EncArgs {
   float ln_eps;
 };
 
+constexpr int kThreads = 512;   // 16 warps: warp w reads TMEM lane quarter w & 3 and owns column slice w >> 2 of every epilogue
+
 // nn.Linear weight W[N][K] (row-major) -> K-major B operand [K/4][N][16 B]; all threads, cp.async
-__device__ __forceinline__ void load_w_kmajor(uint8_t* dst, const float* __restrict__ W, int N, int K, int n_off, int n_total, int tid) {
-  const int kch = K / 4;
+template <int N, int K>
+__device__ __forceinline__ void load_w_kmajor(uint8_t* dst, const float* __restrict__ W, int n_off, int n_total, int tid) {
+  constexpr int kch = K / 4;
   const uint4* src = reinterpret_cast<const uint4*>(W);
-  for (int i = tid; i < N * kch; i += 256) {
-    const int n = i / kch, c = i - n * kch;
+  for (int i = tid; i < N * kch; i += kThreads) {
+    const int n = i / kch, c = i % kch;
     cp16(dst + ((size_t)c * n_total + n_off + n) * 16, src + i);
   }
 }
 
-// D[128 x N] (TMEM columns [col0, col0 + N)) = A[128 x K] (K-major slab `a`) * B (K-major [K/4][N][16 B])
+// D[128 x N] (TMEM columns [0, N)) = A[128 x K] (K-major slab `a`) * B (K-major [K/4][N][16 B])
 __device__ __forceinline__ void issue_gemm(uint32_t tmem, const uint8_t* a, const uint8_t* b, int N, int K, uint64_t* bar) {
   const uint32_t idesc = idesc_tf32(kRows, N);
   const uint64_t da = umma::make_desc(umma::smem_u32(a), (uint32_t)kRows * 16u, 128u);
@@ -76,11 +79,12 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem, const uint8_t* a, cons
 
 // coalesced copy of a row-major staging tile [nrows][W] (row stride ld floats) to global rows [row0, row0 + nrows) of width gw
 // at column offset gc
+template <int W>
 __device__ __forceinline__ void copy_out(const float* __restrict__ stg, int ld, float* __restrict__ g, long long row0, int nrows,
-                                         int W, int gw, int gc, int tid) {
-  const int w4 = W / 4;
-  for (int i = tid; i < nrows * w4; i += 256) {
-    const int r = i / w4, c = i - r * w4;
+                                         int gw, int gc, int tid) {
+  constexpr int w4 = W / 4;
+  for (int i = tid; i < nrows * w4; i += kThreads) {
+    const int r = i / w4, c = i % w4;
     *reinterpret_cast<float4*>(g + (row0 + r) * gw + gc + 4 * c) = *reinterpret_cast<const float4*>(stg + (size_t)r * ld + 4 * c);
   }
 }
@@ -96,24 +100,46 @@ __device__ __forceinline__ float dot16(const float (&a)[D], const float* __restr
   return (p0 + p1) + (p2 + p3);
 }
 
-// LayerNorm of one token row held in registers: v[] = z on entry, normalised output on exit
+// LayerNorm over a token row whose E columns are split into 16-column slices over E/16 threads (one per column-slice warp):
+// partial sums go through shared memory `red` ([128 rows][4 slices]), two passes (mean, then centred sum of squares) like the
+// one-warp-per-token kernel.  v[] = z on entry, the normalised output on exit.  Every thread of the CTA must call it.
 template <int E>
-__device__ __forceinline__ void layernorm_row(float (&v)[E], const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                              float& mean, float& rstd) {
+__device__ __forceinline__ void layernorm_sliced(float (&v)[16], bool active, int r, int sl, float* __restrict__ red,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                 float& mean, float& rstd) {
+  constexpr int NS = E / 16;
   float s = 0.f;
+  if (active) {
 #pragma unroll
-  for (int c = 0; c < E; ++c) s += v[c];
+    for (int c = 0; c < 16; ++c) s += v[c];
+    red[r * 4 + sl] = s;
+  }
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s += red[r * 4 + k];
   mean = s / (float)E;
+  __syncthreads();
   float q = 0.f;
+  if (active) {
 #pragma unroll
-  for (int c = 0; c < E; ++c) { const float d = v[c] - mean; q = fmaf(d, d, q); }
+    for (int c = 0; c < 16; ++c) { const float d = v[c] - mean; q = fmaf(d, d, q); }
+    red[r * 4 + sl] = q;
+  }
+  __syncthreads();
+  q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) q += red[r * 4 + k];
   rstd = rsqrtf(q / (float)E + eps);
+  __syncthreads();
+  if (active) {
 #pragma unroll
-  for (int c = 0; c < E; ++c) v[c] = (v[c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    for (int c = 0; c < 16; ++c) v[c] = (v[c] - mean) * rstd * __ldg(gamma + sl * 16 + c) + __ldg(beta + sl * 16 + c);
+  }
 }
 
 template <int E, int HD, int NH, int SMAX>
-__global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_constant__ EncArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __grid_constant__ EncArgs a) {
   constexpr int D = E / NH;                 // head dim (16 in every reference configuration)
   constexpr int LD = E + 4;                 // row stride of the row-major tiles (floats): 16-byte aligned rows, spread banks
   constexpr int XS_BYTES = E * 512;         // [E/4][128][16 B]
@@ -121,8 +147,9 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
   constexpr int WB_BYTES = (E * E > HD * E ? E * E : HD * E) * 4;
   constexpr int ROW_BYTES = kRows * LD * 4;
   constexpr int HS_BYTES = HD * 512;        // [HD/4][128][16 B]
+  constexpr int NS = E / 16;                // active column slices of an E-wide epilogue
   static_assert(HS_BYTES <= 2 * ROW_BYTES, "the hidden tile aliases the k / v tiles");
-  static_assert(HD % E == 0 && E % 32 == 0 && D % 4 == 0, "tile shapes");
+  static_assert(HD % E == 0 && E % 32 == 0 && D % 4 == 0 && NS <= 4, "tile shapes");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Xs = smem;                                   // A operand: x, then ctx, then x1
   uint8_t* Wa = Xs + XS_BYTES;                          // W_qkv, then W_1
@@ -131,9 +158,12 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
   float* Ks = Qs + kRows * LD;
   float* Vs = Ks + kRows * LD;
   uint8_t* Hs = reinterpret_cast<uint8_t*>(Ks);         // A operand: relu(h) (aliases k, v)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(Qs) + 3 * ROW_BYTES);
+  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(Qs) + 3 * ROW_BYTES);   // [128][4] LayerNorm partial sums
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + kRows * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
+  const int qd = warp & 3, sl = warp >> 2;              // TMEM lane quarter, column slice
+  const int r = qd * 32 + lane;                         // token row of this thread in every epilogue
   const int S = a.S;
 
   if (tid == 0) {
@@ -145,6 +175,7 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
   uint32_t parity = 0;
   const float scale = rsqrtf((float)D);
 
@@ -153,19 +184,20 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
     const int nseq = min(a.spt, a.B - seq0);
     const long long row0 = (long long)seq0 * S;
     const int nrows = nseq * S;
+    const bool live = r < nrows;
     // ---- x tile + W_qkv (-> Wa) + W_o (-> Wb)
     {
       constexpr int kch = E / 4;
       const uint4* src = reinterpret_cast<const uint4*>(a.x + row0 * E);
-      for (int i = tid; i < kRows * kch; i += 256) {
-        const int r = i / kch, c = i - r * kch;
-        uint8_t* d = Xs + ((size_t)c * kRows + r) * 16;
-        if (r < nrows) cp16(d, src + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < kRows * kch; i += kThreads) {
+        const int rr = i / kch, c = i % kch;
+        uint8_t* d = Xs + ((size_t)c * kRows + rr) * 16;
+        if (rr < nrows) cp16(d, src + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
       }
-      load_w_kmajor(Wa, a.wq, E, E, 0, 3 * E, tid);
-      load_w_kmajor(Wa, a.wk, E, E, E, 3 * E, tid);
-      load_w_kmajor(Wa, a.wv, E, E, 2 * E, 3 * E, tid);
-      load_w_kmajor(Wb, a.wo, E, E, 0, E, tid);
+      load_w_kmajor<E, E>(Wa, a.wq, 0, 3 * E, tid);
+      load_w_kmajor<E, E>(Wa, a.wk, E, 3 * E, tid);
+      load_w_kmajor<E, E>(Wa, a.wv, 2 * E, 3 * E, tid);
+      load_w_kmajor<E, E>(Wb, a.wo, 0, E, tid);
       cp_wait_all();
       umma::fence_proxy_async();
     }
@@ -180,33 +212,29 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     // W_1 -> Wa (free now), in flight during the q/k/v epilogue and the attention
-    load_w_kmajor(Wa, a.w1, HD, E, 0, HD, tid);
+    load_w_kmajor<HD, E>(Wa, a.w1, 0, HD, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    if (warp < 4) {
-      const int r = warp * 32 + lane;
-      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-      for (int g = 0; g < 3 * E / 32; ++g) {
-        float v[32];
-        umma::tmem_ld32(trow + (uint32_t)(g * 32), v);
-        const int which = (g * 32) / E, c0 = (g * 32) % E;
-        const float* bias = which == 0 ? a.bq : which == 1 ? a.bk : a.bv;
-        float* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + (size_t)r * LD + c0;
+    for (int g = sl; g < 3 * E / 16; g += 4) {            // 16-column groups of [q | k | v], dealt over the four column slices
+      float v[16];
+      umma::tmem_ld16(trow + (uint32_t)(g * 16), v);
+      const int which = (g * 16) / E, c0 = (g * 16) % E;
+      const float* bias = which == 0 ? a.bq : which == 1 ? a.bk : a.bv;
+      float* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + (size_t)r * LD + c0;
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + c));
-          *reinterpret_cast<float4*>(dst + c) = make_float4(v[c] + bb.x, v[c + 1] + bb.y, v[c + 2] + bb.z, v[c + 3] + bb.w);
-        }
+      for (int c = 0; c < 16; c += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + c));
+        *reinterpret_cast<float4*>(dst + c) = make_float4(v[c] + bb.x, v[c + 1] + bb.y, v[c + 2] + bb.z, v[c + 3] + bb.w);
       }
-      umma::fence_before_sync();
     }
+    umma::fence_before_sync();
     __syncthreads();
-    // ---- q, k, v to HBM (the backward reads them) and the attention, one (sequence, head) per warp pass
-    copy_out(Qs, LD, a.q, row0, nrows, E, E, 0, tid);
-    copy_out(Ks, LD, a.k, row0, nrows, E, E, 0, tid);
-    copy_out(Vs, LD, a.v, row0, nrows, E, E, 0, tid);
-    for (int pair = warp; pair < nseq * NH; pair += 8) {
-      const int sq = pair / NH, h = pair - sq * NH, hc = h * D;
+    // ---- q, k, v to HBM (the backward reads them) and the attention: one (sequence, head) per warp
+    copy_out<E>(Qs, LD, a.q, row0, nrows, E, 0, tid);
+    copy_out<E>(Ks, LD, a.k, row0, nrows, E, 0, tid);
+    copy_out<E>(Vs, LD, a.v, row0, nrows, E, 0, tid);
+    for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
+      const int sq = pair / NH, h = pair % NH, hc = h * D;
       const float* Kb = Ks + (size_t)sq * S * LD + hc;
       const float* Vb = Vs + (size_t)sq * S * LD + hc;
       for (int i = lane; i < S; i += 32) {
@@ -261,55 +289,51 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
       if (umma::elect_one()) issue_gemm(tmem, Xs, Wb, E, E, bar);
       __syncwarp();
     }
-    for (int i = tid; i < nrows * (E / 4); i += 256) {      // Xs (core layout) -> Qs rows; lanes walk rows: conflict-free reads
-      const int c = i / nrows, r = i - c * nrows;
-      *reinterpret_cast<float4*>(Qs + (size_t)r * LD + 4 * c) = *reinterpret_cast<const float4*>(Xs + ((size_t)c * kRows + r) * 16);
+    for (int i = tid; i < kRows * (E / 4); i += kThreads) {   // Xs (core layout) -> Qs rows; lanes walk rows: conflict-free reads
+      const int c = i / kRows, rr = i % kRows;
+      *reinterpret_cast<float4*>(Qs + (size_t)rr * LD + 4 * c) = *reinterpret_cast<const float4*>(Xs + ((size_t)c * kRows + rr) * 16);
     }
     __syncthreads();
-    copy_out(Qs, LD, a.ctx, row0, nrows, E, E, 0, tid);
+    copy_out<E>(Qs, LD, a.ctx, row0, nrows, E, 0, tid);
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     __syncthreads();               // ctx staging consumed, W_o consumed: Wb and Qs / Ks are free
-    load_w_kmajor(Wb, a.w2, E, HD, 0, E, tid);              // W_2 -> Wb, in flight during LayerNorm 1 and fc1
+    load_w_kmajor<E, HD>(Wb, a.w2, 0, E, tid);              // W_2 -> Wb, in flight during LayerNorm 1 and fc1
     asm volatile("cp.async.commit_group;" ::: "memory");
-    float x1row[E];                // the token row of x1 stays in registers for the second residual (epilogue threads)
-    if (warp < 4) {
-      const int r = warp * 32 + lane;
-      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    float x1v[16];                 // this thread's 16 columns of the x1 row stay in registers for the second residual
+    const bool act = sl < NS;
+    {
+      float v[16];
+      if (act) {
+        umma::tmem_ld16(trow + (uint32_t)(sl * 16), v);
+        if (live) {
+          const float4* xr = reinterpret_cast<const float4*>(a.x + (row0 + r) * E + sl * 16);
 #pragma unroll
-      for (int g = 0; g < E / 32; ++g) {
-        float v[32];
-        umma::tmem_ld32(trow + (uint32_t)(g * 32), v);
+          for (int c = 0; c < 16; c += 4) {
+            const float4 xx = __ldg(xr + c / 4), bb = __ldg(reinterpret_cast<const float4*>(a.bo + sl * 16 + c));
+            v[c] += xx.x + bb.x; v[c + 1] += xx.y + bb.y; v[c + 2] += xx.z + bb.z; v[c + 3] += xx.w + bb.w;
+          }
+        } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) x1row[g * 32 + c] = v[c];
+          for (int c = 0; c < 16; ++c) v[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c += 4)          // z1 -> staging (Qs)
+          *reinterpret_cast<float4*>(Qs + (size_t)r * LD + sl * 16 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
       }
       umma::fence_before_sync();
-      if (r < nrows) {
-        const float4* xr = reinterpret_cast<const float4*>(a.x + (row0 + r) * E);
-#pragma unroll
-        for (int c = 0; c < E; c += 4) {
-          const float4 xx = __ldg(xr + c / 4), bb = __ldg(reinterpret_cast<const float4*>(a.bo + c));
-          x1row[c] += xx.x + bb.x; x1row[c + 1] += xx.y + bb.y; x1row[c + 2] += xx.z + bb.z; x1row[c + 3] += xx.w + bb.w;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < E; ++c) x1row[c] = 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < E; c += 4)           // z1 -> staging (Qs)
-        *reinterpret_cast<float4*>(Qs + (size_t)r * LD + c) = make_float4(x1row[c], x1row[c + 1], x1row[c + 2], x1row[c + 3]);
       float mean, rstd;
-      layernorm_row<E>(x1row, a.g1, a.be1, a.ln_eps, mean, rstd);
-      if (r < nrows) { a.m1[row0 + r] = mean; a.r1[row0 + r] = rstd; }
-      else {
+      layernorm_sliced<E>(v, act, r, sl, red, a.g1, a.be1, a.ln_eps, mean, rstd);
+      if (act) {
+        if (live && sl == 0) { a.m1[row0 + r] = mean; a.r1[row0 + r] = rstd; }
 #pragma unroll
-        for (int c = 0; c < E; ++c) x1row[c] = 0.f;
-      }
+        for (int c = 0; c < 16; ++c) x1v[c] = live ? v[c] : 0.f;
 #pragma unroll
-      for (int c = 0; c < E; c += 4) {         // x1 -> A operand (Xs) and staging (Ks)
-        const float4 t = make_float4(x1row[c], x1row[c + 1], x1row[c + 2], x1row[c + 3]);
-        *reinterpret_cast<float4*>(Xs + ((size_t)(c / 4) * kRows + r) * 16) = t;
-        *reinterpret_cast<float4*>(Ks + (size_t)r * LD + c) = t;
+        for (int c = 0; c < 16; c += 4) {        // x1 -> A operand (Xs) and staging (Ks)
+          const float4 t = make_float4(x1v[c], x1v[c + 1], x1v[c + 2], x1v[c + 3]);
+          *reinterpret_cast<float4*>(Xs + ((size_t)((sl * 16 + c) / 4) * kRows + r) * 16) = t;
+          *reinterpret_cast<float4*>(Ks + (size_t)r * LD + sl * 16 + c) = t;
+        }
       }
     }
     umma::fence_proxy_async();
@@ -321,40 +345,34 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
       if (umma::elect_one()) issue_gemm(tmem, Xs, Wa, HD, E, bar);
       __syncwarp();
     }
-    copy_out(Qs, LD, a.z1, row0, nrows, E, E, 0, tid);
-    copy_out(Ks, LD, a.x1, row0, nrows, E, E, 0, tid);
+    copy_out<E>(Qs, LD, a.z1, row0, nrows, E, 0, tid);
+    copy_out<E>(Ks, LD, a.x1, row0, nrows, E, 0, tid);
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     __syncthreads();               // staging tiles consumed: Hs (aliases Ks / Vs) may be written
 #pragma unroll 1
     for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: A operand + staged copy to HBM
-      if (warp < 4) {
-        const int r = warp * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+      if (act) {
+        const int c0 = chunk * E + sl * 16;
+        float v[16];
+        umma::tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
-        for (int g = 0; g < E / 32; ++g) {
-          const int c0 = chunk * E + g * 32;
-          float v[32];
-          umma::tmem_ld32(trow + (uint32_t)c0, v);
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bf1 + c0 + c));
-            float4 t = make_float4(fmaxf(v[c] + bb.x, 0.f), fmaxf(v[c + 1] + bb.y, 0.f), fmaxf(v[c + 2] + bb.z, 0.f),
-                                   fmaxf(v[c + 3] + bb.w, 0.f));
-            if (r >= nrows) t = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(Hs + ((size_t)((c0 + c) / 4) * kRows + r) * 16) = t;
-            *reinterpret_cast<float4*>(Qs + (size_t)r * LD + g * 32 + c) = t;
-          }
+        for (int c = 0; c < 16; c += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bf1 + c0 + c));
+          float4 t = make_float4(fmaxf(v[c] + bb.x, 0.f), fmaxf(v[c + 1] + bb.y, 0.f), fmaxf(v[c + 2] + bb.z, 0.f),
+                                 fmaxf(v[c + 3] + bb.w, 0.f));
+          if (!live) t = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(Hs + ((size_t)((c0 + c) / 4) * kRows + r) * 16) = t;
+          *reinterpret_cast<float4*>(Qs + (size_t)r * LD + sl * 16 + c) = t;
         }
       }
       __syncthreads();
-      copy_out(Qs, LD, a.hact, row0, nrows, E, HD, chunk * E, tid);
+      copy_out<E>(Qs, LD, a.hact, row0, nrows, HD, chunk * E, tid);
       __syncthreads();
     }
-    if (warp < 4) umma::fence_before_sync();
+    umma::fence_before_sync();
     cp_wait_all();                 // W_2 has landed
     umma::fence_proxy_async();
-    umma::fence_before_sync();
     __syncthreads();
     // ---- x2 = LN2(x1 + h W_2^T + b)
     if (warp == 4) {
@@ -364,35 +382,33 @@ __global__ void __launch_bounds__(256, 1) encoder_layer_fwd_kernel(const __grid_
     }
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
-    if (warp < 4) {
-      const int r = warp * 32 + lane;
-      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-      float z[E];
+    {
+      float z[16];
+      if (act) {
+        umma::tmem_ld16(trow + (uint32_t)(sl * 16), z);
 #pragma unroll
-      for (int g = 0; g < E / 32; ++g) {
-        float v[32];
-        umma::tmem_ld32(trow + (uint32_t)(g * 32), v);
+        for (int c = 0; c < 16; c += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bf2 + sl * 16 + c));
+          z[c] += x1v[c] + bb.x; z[c + 1] += x1v[c + 1] + bb.y; z[c + 2] += x1v[c + 2] + bb.z; z[c + 3] += x1v[c + 3] + bb.w;
+        }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) z[g * 32 + c] = v[c];
+        for (int c = 0; c < 16; c += 4)
+          *reinterpret_cast<float4*>(Qs + (size_t)r * LD + sl * 16 + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
       }
       umma::fence_before_sync();
-#pragma unroll
-      for (int c = 0; c < E; c += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bf2 + c));
-        z[c] += x1row[c] + bb.x; z[c + 1] += x1row[c + 1] + bb.y; z[c + 2] += x1row[c + 2] + bb.z; z[c + 3] += x1row[c + 3] + bb.w;
-      }
-#pragma unroll
-      for (int c = 0; c < E; c += 4) *reinterpret_cast<float4*>(Qs + (size_t)r * LD + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
       float mean, rstd;
-      layernorm_row<E>(z, a.g2, a.be2, a.ln_eps, mean, rstd);
-      if (r < nrows) { a.m2[row0 + r] = mean; a.r2[row0 + r] = rstd; }
-      // Ks aliases Hs, which the fc2 MMA has finished reading (its commit was waited for above)
+      layernorm_sliced<E>(z, act, r, sl, red, a.g2, a.be2, a.ln_eps, mean, rstd);
+      if (act) {
+        if (live && sl == 0) { a.m2[row0 + r] = mean; a.r2[row0 + r] = rstd; }
+        // Ks aliases Hs, which the fc2 MMA has finished reading (its commit was waited for above)
 #pragma unroll
-      for (int c = 0; c < E; c += 4) *reinterpret_cast<float4*>(Ks + (size_t)r * LD + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
+        for (int c = 0; c < 16; c += 4)
+          *reinterpret_cast<float4*>(Ks + (size_t)r * LD + sl * 16 + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
+      }
     }
     __syncthreads();
-    copy_out(Qs, LD, a.z2, row0, nrows, E, E, 0, tid);
-    copy_out(Ks, LD, a.x2, row0, nrows, E, E, 0, tid);
+    copy_out<E>(Qs, LD, a.z2, row0, nrows, E, 0, tid);
+    copy_out<E>(Ks, LD, a.x2, row0, nrows, E, 0, tid);
     umma::fence_before_sync();
     __syncthreads();               // the next tile overwrites every buffer
   }
@@ -411,13 +427,13 @@ template <int E, int HD, int NH, int SMAX>
 int launch_fwd(const EncArgs& a, cudaStream_t st) {
   constexpr int LD = E + 4;
   constexpr int WA = (3 * E * E > E * HD ? 3 * E * E : E * HD) * 4, WB = (E * E > HD * E ? E * E : HD * E) * 4;
-  const int smem = E * 512 + WA + WB + 3 * kRows * LD * 4 + 64;
+  const int smem = E * 512 + WA + WB + 3 * kRows * LD * 4 + kRows * 4 * 4 + 64;
   auto kern = encoder_layer_fwd_kernel<E, HD, NH, SMAX>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   const double T = (double)a.B * a.S;
   MivitProfScope prof("encoder_layer_fwd", 2.0 * T * (4.0 * E * E + 2.0 * E * HD) + 4.0 * a.B * NH * (double)a.S * a.S * (E / NH), st);
-  kern<<<grid, 256, smem, st>>>(a);
+  kern<<<grid, kThreads, smem, st>>>(a);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
