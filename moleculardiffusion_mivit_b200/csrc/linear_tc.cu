@@ -68,18 +68,18 @@ __device__ __forceinline__ void tmem_dealloc_n(uint32_t taddr, int cols) {
 }
 __host__ __device__ inline int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
-// Up to three independent problems of the same shape in one launch (blockIdx.y): the q / k / v projections of an encoder
+// Up to four independent problems of the same shape in one launch (blockIdx.y): the q / k / v projections of an encoder
 // layer (forward) and their weight gradients.  Each of these launches is a latency chain (load -> MMA -> store) over a single
 // wave of CTAs; three problems in one grid let the load phase of one CTA overlap the epilogue of another on the same SM.
 struct LinBatch {
-  const float* A[3];
-  const float* W[3];
-  const float* bias[3];
-  float* Y[3];
+  const float* A[4];
+  const float* W[4];
+  const float* bias[4];
+  float* Y[4];
   const float* gate;   // optional [M,N]: Y = gate > 0 ? Y : 0  (backward of a ReLU fused into the dgrad that feeds it)
 };
 template <typename T>
-__device__ __forceinline__ T pick3(T const (&a)[3], int z) { return z == 0 ? a[0] : z == 1 ? a[1] : a[2]; }
+__device__ __forceinline__ T pick3(T const (&a)[4], int z) { return z == 0 ? a[0] : z == 1 ? a[1] : z == 2 ? a[2] : a[3]; }
 
 // ------------------------------------------------------------------ forward / dgrad -------------
 // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-7 producers.
@@ -231,6 +231,10 @@ linear_tc_kernel(const __grid_constant__ LinBatch batch, int M, int K, int N, in
             float4 o = stg[row * 8 + (c ^ (row & 7))];
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             float4* p = reinterpret_cast<float4*>(Y + (row0 + row) * N + g * 32) + c;
+            if (accumulate == 2) {   // several problems of the launch add into the SAME output (dx += dq Wq + dk Wk + dv Wv)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+              continue;
+            }
             if (accumulate) {
               const float4 old = *p;
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
@@ -390,7 +394,7 @@ bool linear_tc_supported(int M, int K, int N) {
          (size_t)K * N * 4 + 2 * (size_t)(K / 4) * kRows * 16 + 4 * 4096 + 256 <= 227 * 1024;
 }
 
-// mode 0: Y = A W^T (+bias)(relu), W [N][K].   mode 1: Y (+)= A W, W [K][N].   nb <= 3 problems of the same shape.
+// mode 0: Y = A W^T (+bias)(relu), W [N][K].   mode 1: Y (+)= A W, W [K][N].   nb <= 4 problems of the same shape; accumulate = 2 adds with vector atomics (problems may share Y).
 int linear_tc_batched(int nb, const float* const* A, const float* const* W, const float* const* bias, float* const* Y, int M, int K,
                       int N, int mode, int relu, int accumulate, cudaStream_t st, const float* gate) {
   LinBatch b = {};

@@ -142,7 +142,7 @@ int linear_tc(const float* A, const float* W, const float* bias, float* Y, int M
               cudaStream_t st);
 int linear_tc_batched(int nb, const float* const* A, const float* const* W, const float* const* bias, float* const* Y, int M, int K,
                       int N, int mode, int relu, int accumulate, cudaStream_t st,
-                      const float* gate = nullptr);   // nb <= 3 problems of one shape, one launch; gate: Y = gate > 0 ? Y : 0
+                      const float* gate = nullptr);   // nb <= 4 problems of one shape, one launch; gate: Y = gate > 0 ? Y : 0; accumulate 2: atomic add (problems may share Y)
 int linear_wgrad_tc_batched(int nb, const float* const* dY, const float* const* X, float* const* dW, float* const* db, int M, int N,
                             int K, cudaStream_t st);
 bool linear_wgrad_tc_supported(int M, int N, int K);

@@ -625,21 +625,27 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
     CK(linear_bwd(y.x1, p + Y.f1_w, w.dh2, g + Y.f1_w, g + Y.f1_b, tmp, T, HD, E, 1, st));               // tmp += dhpre W1
     // x1 = LN1(xin + ao)
     CK(layernorm_bwd(tmp, y.z1, y.m1, y.r1, p + Y.n1_g, dx, g + Y.n1_g, g + Y.n1_b, T, E, 0, 0, 0, st));   // dx = dz1 = dao = dxin
-    CK(linear_bwd(y.ctx, p + Y.o_w, dx, g + Y.o_w, g + Y.o_b, w.dctx, T, E, E, 0, st));
-    CK(attention_bwd(y.q, y.k, y.v, y.probs, y.ctx, w.dctx, w.dq, w.dk, w.dv, B, S, E, H, st));
-    if (g_linear_tc && linear_wgrad_tc_supported(T, E, E) && linear_tc_supported(T, E, E) && al16(xin) && al16(w.dq) && al16(w.dk) &&
-        al16(w.dv) && al16(g + Y.q_w) && al16(g + Y.k_w) && al16(g + Y.v_w) && al16(p + Y.q_w) && al16(p + Y.k_w) && al16(p + Y.v_w) &&
-        al16(dx)) {
-      // three weight gradients in one launch; the three input gradients accumulate into dx one after the other
-      const float* dYs[3] = {w.dq, w.dk, w.dv};
-      const float* Xs[3] = {xin, xin, xin};
-      float* dWs[3] = {g + Y.q_w, g + Y.k_w, g + Y.v_w};
-      float* dbs[3] = {g + Y.q_b, g + Y.k_b, g + Y.v_b};
-      CK(linear_wgrad_tc_batched(3, dYs, Xs, dWs, dbs, T, E, E, st));
-      CK(linear_tc(w.dq, p + Y.q_w, nullptr, dx, T, E, E, 1, 0, 1, st));
-      CK(linear_tc(w.dk, p + Y.k_w, nullptr, dx, T, E, E, 1, 0, 1, st));
-      CK(linear_tc(w.dv, p + Y.v_w, nullptr, dx, T, E, E, 1, 0, 1, st));
+    const bool tc_attn = g_linear_tc && linear_wgrad_tc_supported(T, E, E) && linear_tc_supported(T, E, E) && al16(xin) && al16(w.dq) &&
+                         al16(w.dk) && al16(w.dv) && al16(g + Y.q_w) && al16(g + Y.k_w) && al16(g + Y.v_w) && al16(g + Y.o_w) &&
+                         al16(p + Y.q_w) && al16(p + Y.k_w) && al16(p + Y.v_w) && al16(p + Y.o_w) && al16(dx) && al16(y.ctx) &&
+                         al16(w.dctx);
+    if (tc_attn) {
+      CK(linear_tc(dx, p + Y.o_w, nullptr, w.dctx, T, E, E, 1, 0, 0, st));                 // dctx = dz1 W_o
+      CK(attention_bwd(y.q, y.k, y.v, y.probs, y.ctx, w.dctx, w.dq, w.dk, w.dv, B, S, E, H, st));
+      // the four E x E weight gradients of the attention block (q, k, v, out) in one launch ...
+      const float* dYs[4] = {w.dq, w.dk, w.dv, dx};
+      const float* Xs[4] = {xin, xin, xin, y.ctx};
+      float* dWs[4] = {g + Y.q_w, g + Y.k_w, g + Y.v_w, g + Y.o_w};
+      float* dbs[4] = {g + Y.q_b, g + Y.k_b, g + Y.v_b, g + Y.o_b};
+      CK(linear_wgrad_tc_batched(4, dYs, Xs, dWs, dbs, T, E, E, st));
+      // ... and the three input gradients in one launch, added onto dx (= dz1, the residual path) with vector atomics
+      const float* As[3] = {w.dq, w.dk, w.dv};
+      const float* Ws[3] = {p + Y.q_w, p + Y.k_w, p + Y.v_w};
+      float* Ys[3] = {dx, dx, dx};
+      CK(linear_tc_batched(3, As, Ws, nullptr, Ys, T, E, E, 1, 0, 2, st));
     } else {
+      CK(linear_bwd(y.ctx, p + Y.o_w, dx, g + Y.o_w, g + Y.o_b, w.dctx, T, E, E, 0, st));
+      CK(attention_bwd(y.q, y.k, y.v, y.probs, y.ctx, w.dctx, w.dq, w.dk, w.dv, B, S, E, H, st));
       CK(linear_bwd(xin, p + Y.q_w, w.dq, g + Y.q_w, g + Y.q_b, dx, T, E, E, 1, st));
       CK(linear_bwd(xin, p + Y.k_w, w.dk, g + Y.k_w, g + Y.k_b, dx, T, E, E, 1, st));
       CK(linear_bwd(xin, p + Y.v_w, w.dv, g + Y.v_w, g + Y.v_b, dx, T, E, E, 1, st));
