@@ -1,0 +1,654 @@
+// Input-gradient half of the backward of one post-norm encoder layer as ONE persistent kernel (reference
+// helpers/models.py:81-108 TransformerEncoderLayerWithSkip, differentiated by autograd there):
+//   dz2  = LN2'(dy)                                   thread = token row, 16-column slices, cross-slice sums in shared memory
+//   dh2  = (dz2 W_2) * 1[relu(h) > 0]                 tcgen05 kind::tf32, M = 128 tokens, N = HD
+//   dz1  = LN1'(dz2 + dh2 W_1)                        tcgen05, N = E; residual from registers
+//   dctx = dz1 W_o                                    tcgen05, N = E
+//   dq, dk, dv = attention'(q, k, v, lse, ctx, dctx)  one (sequence, head) per warp, flash style (P recomputed from the row
+//                                                     log-sum-exps), operands and results in shared memory
+//   dx   = dz1 + dq W_q + dk W_k + dv W_v             three tcgen05 chains into one accumulator
+// The unfused path runs this as 9 launches per layer (two LayerNorm backwards, four tf32 GEMM launches, the attention
+// backward, ...), each a 10-19 us latency chain over ~2.5 us of HBM traffic.  Here a CTA owns a tile of 128 token rows =
+// floor(128 / S) whole sequences and keeps it on chip; what the weight-gradient GEMMs need (dz2, dh2, dz1, dq, dk, dv) is
+// written once, coalesced, through an XOR-swizzled row-major staging tile.  The weight gradients stay in linear_tc.cu: their
+// reduction runs over ALL tokens, so they are separate (batched) launches behind this kernel.
+//
+// The input-gradient GEMMs multiply by W (not W^T); instead of an MN-major B operand the (tiny) weights are transposed once
+// per step by pack_kernel, so every GEMM here is the same K-major x K-major form as the forward kernel (encoder_fused.cu).
+#include "common.cuh"
+#include "umma.cuh"
+#include "vit.h"
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kThreads = 512;   // 16 warps: warp w reads TMEM lane quarter w & 3 and owns column slice w >> 2 of every epilogue
+
+__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct BwdArgs {
+  const float* dy;   // [T, E] gradient of the layer output
+  float* dx;         // [T, E] gradient of the layer input (may alias dy: a tile reads its dy rows before it writes them)
+  const float *z2, *m2, *r2, *hact, *z1, *m1, *r1, *q, *k, *v, *lse, *ctx;
+  const float *g2, *g1;                     // LayerNorm weights
+  const float *w2t, *w1t, *wot, *wqkvt;     // transposed weights (pack_kernel)
+  float *dz2, *dh2, *dz1, *dq, *dk, *dv;    // operands of the weight-gradient launches
+  float *dg2, *db2, *dg1, *db1;             // LayerNorm parameter gradients (accumulated with atomics)
+  int B, S, spt, n_tiles;
+};
+
+// row-major source Wsrc[N][K] -> K-major B operand [K/4][N][16 B]; all threads, cp.async
+template <int N, int K>
+__device__ __forceinline__ void load_w_kmajor(uint8_t* dst, const float* __restrict__ W, int tid) {
+  constexpr int kch = K / 4;
+  const uint4* src = reinterpret_cast<const uint4*>(W);
+  for (int i = tid; i < N * kch; i += kThreads) {
+    const int n = i / kch, c = i % kch;
+    cp16(dst + ((size_t)c * N + n) * 16, src + i);
+  }
+}
+
+// D[128 x N] (TMEM columns from `tmem`) (+)= A[128 x K] (K-major slab) * B (K-major [..][N][16 B], chunk stride N * 16)
+__device__ __forceinline__ void issue_chain(uint32_t tmem, const uint8_t* a, const uint8_t* b, int N, int K, bool first) {
+  const uint32_t idesc = idesc_tf32(kRows, N);
+  const uint64_t da = umma::make_desc(umma::smem_u32(a), (uint32_t)kRows * 16u, 128u);
+  const uint64_t db = umma::make_desc(umma::smem_u32(b), (uint32_t)N * 16u, 128u);
+  uint32_t a_lo = (uint32_t)da, b_lo = (uint32_t)db;
+  const uint32_t a_hi = (uint32_t)(da >> 32), b_hi = (uint32_t)(db >> 32);
+  for (int j = 0; j < K / 8; ++j) {
+    mma_tf32(tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, (first && j == 0) ? 0u : 1u);
+    a_lo += 2u * kRows;          // two 4-float chunks per K = 8 step
+    b_lo += 2u * (uint32_t)N;
+  }
+}
+
+// XOR-swizzled row-major tile [128][CH x 16 B]: the 64-byte group g = c / 4 of row r (one head's 16 floats) lives at group
+// position g ^ (r & (CH / 4 - 1)); the four chunks of a group stay in order, so a head block is 64 contiguous bytes and the
+// attention loops address it with ONE computed offset + immediates (a per-chunk XOR cost 18 % of the kernel's instructions).
+// Lanes holding consecutive rows and the same chunk spread over CH / 4 bank groups (8-way instead of 32-way conflicts; a padded
+// layout would not fit in shared memory).
+template <int CH>
+__device__ __forceinline__ uint32_t rm_off(int r, int c) {
+  return (uint32_t)r * (CH * 16) + (uint32_t)((((c >> 2) ^ (r & (CH / 4 - 1))) << 6) | ((c & 3) << 4));
+}
+// byte offset of head block h (64 bytes) of row r
+template <int CH>
+__device__ __forceinline__ uint32_t head_off(int r, int h) {
+  return (uint32_t)r * (CH * 16) + (uint32_t)((h ^ (r & (CH / 4 - 1))) << 6);
+}
+template <int CH>
+__device__ __forceinline__ float4 rm_ld(const uint8_t* tile, int r, int c) {
+  return *reinterpret_cast<const float4*>(tile + rm_off<CH>(r, c));
+}
+template <int CH>
+__device__ __forceinline__ void rm_st(uint8_t* tile, int r, int c, float4 v) {
+  *reinterpret_cast<float4*>(tile + rm_off<CH>(r, c)) = v;
+}
+
+// swizzled tile -> global rows [row0, row0 + nrows) of a [.., gw] matrix at column offset gc (coalesced 16-byte stores)
+template <int CH>
+__device__ __forceinline__ void copy_out(const uint8_t* tile, float* __restrict__ g, long long row0, int nrows, int gw, int gc, int tid) {
+  for (int i = tid; i < nrows * CH; i += kThreads) {
+    const int r = i / CH, c = i % CH;
+    *reinterpret_cast<float4*>(g + (row0 + r) * gw + gc + 4 * c) = rm_ld<CH>(tile, r, c);
+  }
+}
+// global rows -> swizzled tile (cp.async; rows past nrows are zero)
+template <int CH>
+__device__ __forceinline__ void fill_tile(uint8_t* tile, const float* __restrict__ g, long long row0, int nrows, int tid) {
+  const uint4* src = reinterpret_cast<const uint4*>(g + row0 * (CH * 4));
+  for (int i = tid; i < kRows * CH; i += kThreads) {
+    const int r = i / CH, c = i % CH;
+    uint8_t* d = tile + rm_off<CH>(r, c);
+    if (r < nrows) cp16(d, src + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+  }
+}
+// swizzled row-major tile -> K-major A slab [CH][128][16 B]; lanes walk rows (conflict-free on both sides)
+template <int CH>
+__device__ __forceinline__ void tile_to_slab(const uint8_t* tile, uint8_t* slab, int tid) {
+  for (int i = tid; i < kRows * CH; i += kThreads) {
+    const int c = i / kRows, r = i % kRows;
+    *reinterpret_cast<float4*>(slab + ((size_t)c * kRows + r) * 16) = rm_ld<CH>(tile, r, c);
+  }
+}
+
+// 32 values per lane -> lane l returns the sum over the warp's lanes of value l (31 shuffles instead of 160)
+template <int N>
+__device__ __forceinline__ void tr_step(float (&v)[32], int lane) {
+  const bool up = (lane & N) != 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float keep = up ? v[i + N] : v[i];
+    const float send = up ? v[i] : v[i + N];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, N);
+  }
+}
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+  tr_step<16>(v, lane); tr_step<8>(v, lane); tr_step<4>(v, lane); tr_step<2>(v, lane); tr_step<1>(v, lane);
+  return v[0];
+}
+
+// 16 floats of a head block (64 contiguous bytes at blk)
+template <int D>
+__device__ __forceinline__ void ld_head(const uint8_t* blk, float (&o)[D], float mul) {
+#pragma unroll
+  for (int j = 0; j < D / 4; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(blk + 16 * j);
+    o[4 * j] = t.x * mul; o[4 * j + 1] = t.y * mul; o[4 * j + 2] = t.z * mul; o[4 * j + 3] = t.w * mul;
+  }
+}
+template <int D>
+__device__ __forceinline__ void st_head(uint8_t* blk, const float (&o)[D], float mul) {
+#pragma unroll
+  for (int j = 0; j < D / 4; ++j)
+    *reinterpret_cast<float4*>(blk + 16 * j) = make_float4(o[4 * j] * mul, o[4 * j + 1] * mul, o[4 * j + 2] * mul, o[4 * j + 3] * mul);
+}
+
+// LayerNorm backward of a token row whose E columns are split into 16-column slices over the column-slice warps.
+// On entry dyv = upstream gradient, zv = the saved pre-norm sum; on exit dz = the input gradient (0 for dead rows: rs = 0),
+// and the row's contributions to dgamma / dbeta have been added to acc[0 .. E) / acc[E .. 2E).  Every thread must call it.
+template <int E>
+__device__ __forceinline__ void layernorm_bwd_sliced(const float (&dyv)[16], const float (&zv)[16], float m, float rs, bool act,
+                                                     int r, int sl, int lane, float* __restrict__ red,
+                                                     const float* __restrict__ gamma, float* __restrict__ acc, float (&dz)[16]) {
+  constexpr int NS = E / 16;
+  float xh[16], g[16];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    xh[c] = (zv[c] - m) * rs;
+    g[c] = act ? dyv[c] * __ldg(gamma + sl * 16 + c) : 0.f;
+    s1 += g[c];
+    s2 = fmaf(g[c], xh[c], s2);
+  }
+  if (act) { red[r * 4 + sl] = s1; red[kRows * 4 + r * 4 + sl] = s2; }
+  __syncthreads();
+  s1 = s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) { s1 += red[r * 4 + k]; s2 += red[kRows * 4 + r * 4 + k]; }
+  s1 *= 1.0f / (float)E;
+  s2 *= 1.0f / (float)E;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) dz[c] = rs * (g[c] - s1 - xh[c] * s2);
+  float pv[32];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { pv[c] = dyv[c] * xh[c]; pv[16 + c] = dyv[c]; }
+  const float tot = warp_transpose_reduce(pv, lane);
+  if (act) atomicAdd(acc + (lane >> 4) * E + sl * 16 + (lane & 15), tot);
+}
+
+template <int E, int HD, int NH, int SMAX>
+__global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __grid_constant__ BwdArgs a) {
+  constexpr int D = E / NH;                 // head dim (16)
+  constexpr int CH = E / 4;                 // 16-byte chunks of an E-wide row
+  constexpr int NS = E / 16;                // active column slices of an E-wide epilogue
+  constexpr int RPL = SMAX / 32;            // sequence rows per lane in the attention passes
+  constexpr int TILE = kRows * E * 4;       // bytes of an E-wide tile (swizzled row-major, or a K-major slab)
+  constexpr int WA_BYTES = (3 * E * E > E * HD + E * E ? 3 * E * E : E * HD + E * E) * 4;
+  constexpr int WB_BYTES = E * HD * 4;
+  constexpr int C1 = 0, C2 = HD, C3 = HD + E, C4 = 0;   // TMEM columns of the four accumulators
+  static_assert(HD == 2 * E && D == 16 && NS <= 4 && (CH & (CH - 1)) == 0 && CH >= 8, "tile shapes");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Wa = smem;                         // [W_2^T | W_o^T], then [W_q^T | W_k^T | W_v^T]
+  uint8_t* Wb = Wa + WA_BYTES;                // W_1^T (resident over the CTA's tiles)
+  uint8_t* R0 = Wb + WB_BYTES;                // dz2 slab -> dz1 slab -> q tile (dk on exit) -> dv slab
+  uint8_t* R1 = R0 + TILE;                    // dh2 slab (R1, R2) -> k tile (dq on exit) -> dk slab
+  uint8_t* R2 = R1 + TILE;                    //                   -> v tile (dv on exit) -> dx staging
+  uint8_t* R3 = R2 + TILE;                    // staging tile -> dctx tile -> dq slab
+  float* red = reinterpret_cast<float*>(R3 + TILE);      // [2][128][4] LayerNorm partial sums
+  float* lnacc = red + 2 * kRows * 4;                    // [LN1 | LN2][dgamma | dbeta][E]
+  float* lsdl = lnacc + 4 * E;                           // [16 warps][L | D][SMAX]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lsdl + 16 * 2 * SMAX);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
+  const int qd = warp & 3, sl = warp >> 2;
+  const int r = qd * 32 + lane;               // token row of this thread in every epilogue
+  const bool act = sl < NS;
+  const int S = a.S;
+
+  if (tid == 0) {
+    umma::mbar_init(bar, 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc<HD + 2 * E>(tmem_slot);
+  for (int i = tid; i < 4 * E; i += kThreads) lnacc[i] = 0.f;
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
+  uint32_t parity = 0;
+  const float scale = rsqrtf((float)D);
+  bool wa_ready = false;       // [W_2^T | W_o^T] of the next tile already requested
+
+  load_w_kmajor<E, HD>(Wb, a.w1t, tid);
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int seq0 = tile * a.spt;
+    const int nseq = min(a.spt, a.B - seq0);
+    const long long row0 = (long long)seq0 * S;
+    const int nrows = nseq * S;
+    const bool live = act && r < nrows;
+    if (!wa_ready) {
+      load_w_kmajor<HD, E>(Wa, a.w2t, tid);
+      load_w_kmajor<E, E>(Wa + E * HD * 4, a.wot, tid);
+    }
+    cp_commit();
+    // ---- dz2 = LN2'(dy)
+    float dz2v[16];
+    {
+      float dyv[16], zv[16];
+      float m = 0.f, rs = 0.f;
+      if (live) {
+        const float4* dp = reinterpret_cast<const float4*>(a.dy + (row0 + r) * E + sl * 16);
+        const float4* zp = reinterpret_cast<const float4*>(a.z2 + (row0 + r) * E + sl * 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 d4 = dp[c], z4 = __ldg(zp + c);
+          dyv[4 * c] = d4.x; dyv[4 * c + 1] = d4.y; dyv[4 * c + 2] = d4.z; dyv[4 * c + 3] = d4.w;
+          zv[4 * c] = z4.x; zv[4 * c + 1] = z4.y; zv[4 * c + 2] = z4.z; zv[4 * c + 3] = z4.w;
+        }
+        m = __ldg(a.m2 + row0 + r);
+        rs = __ldg(a.r2 + row0 + r);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dyv[c] = zv[c] = 0.f;
+      }
+      layernorm_bwd_sliced<E>(dyv, zv, m, rs, act, r, sl, lane, red, a.g2, lnacc + 2 * E, dz2v);
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 t = make_float4(dz2v[4 * c], dz2v[4 * c + 1], dz2v[4 * c + 2], dz2v[4 * c + 3]);
+          *reinterpret_cast<float4*>(R0 + ((size_t)(sl * 4 + c) * kRows + r) * 16) = t;
+          rm_st<CH>(R3, r, sl * 4 + c, t);
+        }
+      }
+    }
+    cp_wait_all();                 // the weights have landed
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- dh = dz2 W_2 ; dz2 to HBM meanwhile
+    if (warp == 4) {
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        issue_chain(tmem + C1, R0, Wa, HD, E, true);
+        umma::commit(bar);
+      }
+      __syncwarp();
+    }
+    copy_out<CH>(R3, a.dz2, row0, nrows, E, 0, tid);
+    umma::mbar_wait(bar, parity); parity ^= 1;
+    umma::fence_after_sync();
+    __syncthreads();               // staging tile consumed
+#pragma unroll 1
+    for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: ReLU gate, A operand, staged copy to HBM
+      if (act) {
+        const int c0 = chunk * E + sl * 16;
+        float v[16];
+        umma::tmem_ld16(trow + (uint32_t)(C1 + c0), v);
+        const float4* hp = reinterpret_cast<const float4*>(a.hact + (row0 + r) * HD + c0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) {
+            const float4 h4 = __ldg(hp + c);
+            t = make_float4(h4.x > 0.f ? v[4 * c] : 0.f, h4.y > 0.f ? v[4 * c + 1] : 0.f, h4.z > 0.f ? v[4 * c + 2] : 0.f,
+                            h4.w > 0.f ? v[4 * c + 3] : 0.f);
+          }
+          *reinterpret_cast<float4*>(R1 + ((size_t)(c0 / 4 + c) * kRows + r) * 16) = t;
+          rm_st<CH>(R3, r, sl * 4 + c, t);
+        }
+      }
+      __syncthreads();
+      copy_out<CH>(R3, a.dh2, row0, nrows, HD, chunk * E, tid);
+      __syncthreads();
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- d(x1) = dz2 + dh2 W_1 ; dz1 = LN1'(d(x1))
+    if (warp == 4) {
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        issue_chain(tmem + C2, R1, Wb, E, HD, true);
+        umma::commit(bar);
+      }
+      __syncwarp();
+    }
+    float dz1v[16];
+    {
+      float zv[16];
+      float m = 0.f, rs = 0.f;
+      if (live) {
+        const float4* zp = reinterpret_cast<const float4*>(a.z1 + (row0 + r) * E + sl * 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 z4 = __ldg(zp + c);
+          zv[4 * c] = z4.x; zv[4 * c + 1] = z4.y; zv[4 * c + 2] = z4.z; zv[4 * c + 3] = z4.w;
+        }
+        m = __ldg(a.m1 + row0 + r);
+        rs = __ldg(a.r1 + row0 + r);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) zv[c] = 0.f;
+      }
+      umma::mbar_wait(bar, parity); parity ^= 1;
+      umma::fence_after_sync();
+      // the dh2 slab is consumed: k and v tiles of the attention backward land in its place
+      fill_tile<CH>(R1, a.k, row0, nrows, tid);
+      fill_tile<CH>(R2, a.v, row0, nrows, tid);
+      cp_commit();
+      float dyv[16];
+      if (act) {
+        umma::tmem_ld16(trow + (uint32_t)(C2 + sl * 16), dyv);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dyv[c] = live ? dyv[c] + dz2v[c] : 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dyv[c] = 0.f;
+      }
+      layernorm_bwd_sliced<E>(dyv, zv, m, rs, act, r, sl, lane, red, a.g1, lnacc, dz1v);
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 t = make_float4(dz1v[4 * c], dz1v[4 * c + 1], dz1v[4 * c + 2], dz1v[4 * c + 3]);
+          *reinterpret_cast<float4*>(R0 + ((size_t)(sl * 4 + c) * kRows + r) * 16) = t;
+          rm_st<CH>(R3, r, sl * 4 + c, t);
+        }
+      }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- dctx = dz1 W_o ; dz1 to HBM meanwhile
+    if (warp == 4) {
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        issue_chain(tmem + C3, R0, Wa + E * HD * 4, E, E, true);
+        umma::commit(bar);
+      }
+      __syncwarp();
+    }
+    copy_out<CH>(R3, a.dz1, row0, nrows, E, 0, tid);
+    umma::mbar_wait(bar, parity); parity ^= 1;
+    umma::fence_after_sync();
+    __syncthreads();               // staging consumed; the dz1 slab and [W_2^T | W_o^T] are consumed too
+    fill_tile<CH>(R0, a.q, row0, nrows, tid);
+    load_w_kmajor<E, 3 * E>(Wa, a.wqkvt, tid);
+    cp_commit();
+    if (act) {                     // dctx -> swizzled row-major tile
+      float v[16];
+      umma::tmem_ld16(trow + (uint32_t)(C3 + sl * 16), v);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        rm_st<CH>(R3, r, sl * 4 + c, live ? make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    cp_wait_all();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- attention backward: one (sequence, head) per warp.  Results replace dead operands of the same (sequence, head)
+    //      block: dq -> k tile, dk -> q tile, dv -> v tile.
+    {
+      float* Ls = lsdl + warp * 2 * SMAX;
+      float* Dl = Ls + SMAX;
+      for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
+        const int sq = pair / NH, h = pair % NH, rb = sq * S;
+        // pass A (lane = query row i): D_i = dctx_i . ctx_i, dQ_i = scale * sum_j dS_ij K_j
+        float dqv[RPL][D];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+          const int i = lane + 32 * rr;
+          if (i < S) {
+            float gi[D], qi[D];
+            const uint32_t oi = head_off<CH>(rb + i, h);
+            ld_head<D>(R3 + oi, gi, 1.f);
+            ld_head<D>(R0 + oi, qi, scale);
+            float di = 0.f;
+            const float4* op = reinterpret_cast<const float4*>(a.ctx + (row0 + rb + i) * E + h * D);
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+              const float4 o4 = __ldg(op + c);
+              di = fmaf(gi[4 * c], o4.x, di); di = fmaf(gi[4 * c + 1], o4.y, di);
+              di = fmaf(gi[4 * c + 2], o4.z, di); di = fmaf(gi[4 * c + 3], o4.w, di);
+            }
+            const float li = __ldg(a.lse + ((size_t)(seq0 + sq) * NH + h) * S + i);
+            Ls[i] = li;
+            Dl[i] = di;
+            float acc[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] = 0.f;
+            for (int j = 0; j < S; ++j) {
+              float kj[D], vj[D];
+              const uint32_t oj = head_off<CH>(rb + j, h);
+              ld_head<D>(R1 + oj, kj, 1.f);
+              ld_head<D>(R2 + oj, vj, 1.f);
+              float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+              for (int c = 0; c < D; c += 2) {
+                s0 = fmaf(qi[c], kj[c], s0); s1 = fmaf(qi[c + 1], kj[c + 1], s1);
+                p0 = fmaf(gi[c], vj[c], p0); p1 = fmaf(gi[c + 1], vj[c + 1], p1);
+              }
+              const float p = __expf((s0 + s1) - li);
+              const float ds = p * ((p0 + p1) - di);
+#pragma unroll
+              for (int c = 0; c < D; ++c) acc[c] = fmaf(ds, kj[c], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) dqv[rr][c] = acc[c] * scale;
+          }
+        }
+        __syncwarp();
+        // pass B (lane = key row j): dK_j = scale * sum_i dS_ij Q_i,  dV_j = sum_i P_ij dctx_i
+        float kjs[RPL][D], vjs[RPL][D];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+          const int j = lane + 32 * rr;
+          if (j < S) {
+            const uint32_t oj = head_off<CH>(rb + j, h);
+            ld_head<D>(R1 + oj, kjs[rr], scale);
+            ld_head<D>(R2 + oj, vjs[rr], 1.f);
+          }
+        }
+        __syncwarp();              // every lane holds its k / v rows: the k block is dead, dq moves in
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+          const int i = lane + 32 * rr;
+          if (i < S) st_head<D>(R1 + head_off<CH>(rb + i, h), dqv[rr], 1.f);
+        }
+        float dkv[RPL][D];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+          const int j = lane + 32 * rr;
+          if (j < S) {
+            float ak[D], av[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) ak[c] = av[c] = 0.f;
+            for (int i = 0; i < S; ++i) {
+              float qi[D], gi[D];
+              const uint32_t oi = head_off<CH>(rb + i, h);
+              ld_head<D>(R0 + oi, qi, 1.f);
+              ld_head<D>(R3 + oi, gi, 1.f);
+              float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+              for (int c = 0; c < D; c += 2) {
+                s0 = fmaf(kjs[rr][c], qi[c], s0); s1 = fmaf(kjs[rr][c + 1], qi[c + 1], s1);
+                p0 = fmaf(vjs[rr][c], gi[c], p0); p1 = fmaf(vjs[rr][c + 1], gi[c + 1], p1);
+              }
+              const float p = __expf((s0 + s1) - Ls[i]);
+              const float ds = p * ((p0 + p1) - Dl[i]);
+#pragma unroll
+              for (int c = 0; c < D; ++c) { ak[c] = fmaf(ds, qi[c], ak[c]); av[c] = fmaf(p, gi[c], av[c]); }
+            }
+            st_head<D>(R2 + head_off<CH>(rb + j, h), av, 1.f);      // the v block is dead since the loads above
+#pragma unroll
+            for (int c = 0; c < D; ++c) dkv[rr][c] = ak[c] * scale;
+          }
+        }
+        __syncwarp();              // every lane is done with the q block: dk moves in
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+          const int j = lane + 32 * rr;
+          if (j < S) st_head<D>(R0 + head_off<CH>(rb + j, h), dkv[rr], 1.f);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- dq / dk / dv to HBM and into K-major slabs (each slab replaces a tile that has just been consumed)
+    copy_out<CH>(R1, a.dq, row0, nrows, E, 0, tid);
+    tile_to_slab<CH>(R1, R3, tid);          // dq slab <- dctx tile's place
+    __syncthreads();
+    copy_out<CH>(R0, a.dk, row0, nrows, E, 0, tid);
+    tile_to_slab<CH>(R0, R1, tid);          // dk slab <- dq tile's place
+    __syncthreads();
+    copy_out<CH>(R2, a.dv, row0, nrows, E, 0, tid);
+    tile_to_slab<CH>(R2, R0, tid);          // dv slab <- dk tile's place
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- dx = dz1 + dq W_q + dk W_k + dv W_v
+    if (warp == 4) {
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        issue_chain(tmem + C4, R3, Wa, E, E, true);
+        issue_chain(tmem + C4, R1, Wa + (size_t)(E / 4) * E * 16, E, E, false);
+        issue_chain(tmem + C4, R0, Wa + (size_t)2 * (E / 4) * E * 16, E, E, false);
+        umma::commit(bar);
+      }
+      __syncwarp();
+    }
+    umma::mbar_wait(bar, parity); parity ^= 1;
+    umma::fence_after_sync();
+    wa_ready = tile + (int)gridDim.x < a.n_tiles;
+    if (wa_ready) {                // the next tile's first weights, in flight during this epilogue
+      load_w_kmajor<HD, E>(Wa, a.w2t, tid);
+      load_w_kmajor<E, E>(Wa + E * HD * 4, a.wot, tid);
+    }
+    if (act) {
+      float v[16];
+      umma::tmem_ld16(trow + (uint32_t)(C4 + sl * 16), v);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        rm_st<CH>(R2, r, sl * 4 + c, make_float4(v[4 * c] + dz1v[4 * c], v[4 * c + 1] + dz1v[4 * c + 1], v[4 * c + 2] + dz1v[4 * c + 2],
+                                                 v[4 * c + 3] + dz1v[4 * c + 3]));
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    copy_out<CH>(R2, a.dx, row0, nrows, E, 0, tid);
+    __syncthreads();               // the next tile overwrites every buffer
+  }
+  cp_wait_all();
+  umma::fence_before_sync();
+  __syncthreads();
+  for (int i = tid; i < 4 * E; i += kThreads) {
+    float* dst = i < E ? a.dg1 + i : i < 2 * E ? a.db1 + (i - E) : i < 3 * E ? a.dg2 + (i - 2 * E) : a.db2 + (i - 3 * E);
+    atomicAdd(dst, lnacc[i]);
+  }
+  if (warp == 0) umma::tmem_dealloc<HD + 2 * E>(tmem);
+}
+
+// transposed weights of every layer, one launch: out[l] = [W_2^T (HD x E) | W_1^T (E x HD) | W_o^T (E x E) | W_qkv^T (E x 3E)]
+struct PackArgs {
+  long long off[kEncMaxLayers][6];   // offsets of q_w, k_w, v_w, o_w, f1_w, f2_w in the flat parameter buffer
+};
+__global__ void pack_kernel(const float* __restrict__ params, const __grid_constant__ PackArgs pa, float* __restrict__ out, int E, int HD) {
+  const int l = blockIdx.y;
+  const size_t per = (size_t)2 * E * HD + 4 * (size_t)E * E;
+  float* o = out + l * per;
+  const float* wq = params + pa.off[l][0];
+  const float* wk = params + pa.off[l][1];
+  const float* wv = params + pa.off[l][2];
+  const float* wo = params + pa.off[l][3];
+  const float* w1 = params + pa.off[l][4];   // [HD][E]
+  const float* w2 = params + pa.off[l][5];   // [E][HD]
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)per; i += gridDim.x * blockDim.x) {
+    int j = i;
+    float v;
+    if (j < E * HD) {                        // W_2^T [h][e]
+      const int h = j / E, e = j % E;
+      v = w2[(size_t)e * HD + h];
+    } else if ((j -= E * HD) < E * HD) {     // W_1^T [e][h]
+      const int e = j / HD, h = j % HD;
+      v = w1[(size_t)h * E + e];
+    } else if ((j -= E * HD) < E * E) {      // W_o^T [i][o]
+      const int ii = j / E, oo = j % E;
+      v = wo[(size_t)oo * E + ii];
+    } else {                                 // [W_q^T | W_k^T | W_v^T]  [i][w * E + o]
+      j -= E * E;
+      const int ii = j / (3 * E), rem = j % (3 * E), w = rem / E, oo = rem % E;
+      const float* ww = w == 0 ? wq : w == 1 ? wk : wv;
+      v = ww[(size_t)oo * E + ii];
+    }
+    o[i] = v;
+  }
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  return sms ? sms : 148;
+}
+
+template <int E, int HD, int NH, int SMAX>
+int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+  constexpr int WA = (3 * E * E > E * HD + E * E ? 3 * E * E : E * HD + E * E) * 4, WB = E * HD * 4;
+  const int smem = WA + WB + 4 * kRows * E * 4 + 2 * kRows * 4 * 4 + 4 * E * 4 + 16 * 2 * SMAX * 4 + 64;
+  auto kern = encoder_layer_bwd_kernel<E, HD, NH, SMAX>;
+  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  const double T = (double)a.B * a.S;
+  MivitProfScope prof("encoder_layer_bwd", 2.0 * T * (4.0 * E * E + 2.0 * E * HD) + 10.0 * a.B * NH * (double)a.S * a.S * (E / NH), st);
+  kern<<<grid, kThreads, smem, st>>>(a);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+}  // namespace
+
+size_t encoder_bwd_packed_floats(int E, int HD) { return (size_t)2 * E * HD + 4 * (size_t)E * E; }
+
+int encoder_pack_bwd_weights(const float* params, const long long (*offs)[6], int L, int E, int HD, float* out, cudaStream_t st) {
+  MIVIT_CHECK_ARG(L >= 1 && L <= kEncMaxLayers, "fused encoder backward: more than %d layers", kEncMaxLayers);
+  PackArgs pa;
+  for (int l = 0; l < L; ++l)
+    for (int i = 0; i < 6; ++i) pa.off[l][i] = offs[l][i];
+  pack_kernel<<<dim3(8, L), 256, 0, st>>>(params, pa, out, E, HD);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+int encoder_layer_bwd(const EncoderLayerBwdIO& io, int B, int S, int E, int HD, int H, cudaStream_t st) {
+  MIVIT_CHECK_ARG(encoder_fused_supported(B, S, E, HD, H), "fused encoder layer: unsupported shape");
+  BwdArgs a;
+  a.dy = io.dy; a.dx = io.dx;
+  a.z2 = io.z2; a.m2 = io.m2; a.r2 = io.r2; a.hact = io.hact; a.z1 = io.z1; a.m1 = io.m1; a.r1 = io.r1;
+  a.q = io.q; a.k = io.k; a.v = io.v; a.lse = io.lse; a.ctx = io.ctx;
+  a.g2 = io.g2; a.g1 = io.g1;
+  a.w2t = io.packed;
+  a.w1t = a.w2t + (size_t)E * HD;
+  a.wot = a.w1t + (size_t)E * HD;
+  a.wqkvt = a.wot + (size_t)E * E;
+  a.dz2 = io.dz2; a.dh2 = io.dh2; a.dz1 = io.dz1; a.dq = io.dq; a.dk = io.dk; a.dv = io.dv;
+  a.dg2 = io.dg2; a.db2 = io.db2; a.dg1 = io.dg1; a.db1 = io.db1;
+  a.B = B; a.S = S; a.spt = kRows / S; a.n_tiles = (B + a.spt - 1) / a.spt;
+  if (E == 64) return S <= 32 ? launch_bwd<64, 128, 4, 32>(a, st) : launch_bwd<64, 128, 4, 64>(a, st);
+  return S <= 32 ? launch_bwd<32, 64, 2, 32>(a, st) : launch_bwd<32, 64, 2, 64>(a, st);
+}

@@ -88,6 +88,23 @@ struct EncoderLayerIO {
 bool encoder_fused_supported(int B, int S, int E, int HD, int H);
 int encoder_layer_fwd(const EncoderLayerIO& io, int B, int S, int E, int HD, int H, float ln_eps, cudaStream_t st);
 
+// encoder_fused_bwd.cu -- the input-gradient half of a layer's backward as one persistent kernel (the weight gradients reduce
+// over all tokens and stay batched launches of linear_tc.cu)
+constexpr int kEncMaxLayers = 16;
+struct EncoderLayerBwdIO {
+  const float* dy;   // [B*S, E] gradient of the layer output
+  float* dx;         // [B*S, E] gradient of the layer input (may alias dy)
+  const float *z2, *m2, *r2, *hact, *z1, *m1, *r1, *q, *k, *v, *lse, *ctx;   // written by the forward
+  const float *g2, *g1;          // LayerNorm weights (norm2, norm1)
+  const float* packed;           // this layer's block of encoder_pack_bwd_weights
+  float *dz2, *dh2, *dz1, *dq, *dk, *dv;   // [B*S, E] ([B*S, HD] for dh2): the dY operands of the weight-gradient launches
+  float *dg2, *db2, *dg1, *db1;  // LayerNorm parameter gradients, accumulated
+};
+size_t encoder_bwd_packed_floats(int E, int HD);   // floats per layer of the packed (transposed) weights
+int encoder_pack_bwd_weights(const float* params, const long long (*offs)[6] /* q, k, v, o, f1, f2 weight offsets per layer */, int L,
+                             int E, int HD, float* out, cudaStream_t st);
+int encoder_layer_bwd(const EncoderLayerBwdIO& io, int B, int S, int E, int HD, int H, cudaStream_t st);
+
 // synchronised BatchNorm hook (vit_model.cu): SUM all-reduce of a small device buffer over the data-parallel group
 int mivit_bn_sync_world();                                      // 1 when no hook is registered
 int mivit_bn_sync(float* buf, long long n, cudaStream_t st);

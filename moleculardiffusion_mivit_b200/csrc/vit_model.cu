@@ -178,6 +178,7 @@ struct Workspace {
   float *mf, *rf, *xf, *headin, *hh, *pred_dummy;
   // backward temporaries
   float *dxa, *dxb, *dq, *dk, *dv, *dctx, *dh, *dh2, *dheadin, *dhh, *dfp, *dfp_h, *demb;
+  float* enc_wt;   // transposed encoder weights of the fused layer backward (encoder_fused_bwd.cu)
   long long rows = 0, rows_pad = 0;
   size_t bytes = 0;
 };
@@ -202,11 +203,25 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
     take_rows(b, w.raws1, 64, rp); take_rows(b, w.act2, 64, rp);
     take_rows(b, w.raw3, 128, rp); take_rows(b, w.act3, 128, rp); take_rows(b, w.raw4, 128, rp);
     take_rows(b, w.raws2, 128, rp);
-    take_rows(b, w.draw4, 128, rp); take_rows(b, w.draws2, 128, rp); take_rows(b, w.dact3, 128, rp);
-    take_rows(b, w.draw3, 128, rp); take_rows(b, w.dact2m, 64, rp); take_rows(b, w.dact2s, 64, rp);
-    take_rows(b, w.draw2, 64, rp); take_rows(b, w.draws1, 64, rp); take_rows(b, w.dact1, 64, rp);
-    take_rows(b, w.draw1, 64, rp); take_rows(b, w.dact0m, 32, rp); take_rows(b, w.dact0s, 32, rp);
-    take_rows(b, w.draw0, 32, rp);
+    // The 13 gradient tensors of the embedding backward live in THREE slots (two of 128 channels, one of 64): a tensor moves
+    // into a slot when the previous occupant has been consumed (order of vit_backward_impl; 31 -> 10 units of 0.39 GB at
+    // B = 1024).  Guards are zeroed right before each tensor's producer runs (zero_guards): they overlay the dead occupant's rows.
+    RowsT slotA, slotB, slotD;
+    take_rows(b, slotA, 128, rp); take_rows(b, slotB, 128, rp); take_rows(b, slotD, 64, rp);
+    auto sub = [&](RowsT& t, const RowsT& sl, int C, int part) {
+      t.C = C;
+      t.buf = sl.buf ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(sl.buf) + (size_t)part * (rp + 2 * kGuard) * C * 2) : nullptr;
+      t.row0 = t.buf ? t.buf + (size_t)kGuard * C : nullptr;
+    };
+    sub(w.draw4, slotA, 128, 0); sub(w.draws2, slotB, 128, 0);
+    sub(w.dact2s, slotD, 64, 0);                                  // block 2's skip dgrad runs first ...
+    sub(w.dact3, slotB, 128, 0);                                  // ... so draws2 is consumed when conv2's dgrad writes dact3
+    sub(w.draw3, slotA, 128, 0);                                  // draw4: consumed by conv2's wgrad / dgrad
+    sub(w.dact2m, slotB, 64, 0);                                  // dact3: consumed by bn1's backward
+    sub(w.draw2, slotA, 64, 0); sub(w.draws1, slotA, 64, 1);      // draw3: consumed by conv1's wgrad / dgrad
+    sub(w.dact1, slotB, 64, 0); sub(w.draw1, slotB, 64, 1);       // dact2m (and dact2s): consumed by block 1's bn2 / skip-bn backward
+    sub(w.dact0m, slotD, 32, 0); sub(w.dact0s, slotD, 32, 1);
+    sub(w.draw0, slotA, 32, 0);                                   // draw2: consumed by block 1's conv2 wgrad / dgrad
     const int ci[2] = {32, 64}, co[2] = {64, 128};
     for (int i = 0; i < 2; ++i) {
       w.wp_c1[i] = b.take<__nv_bfloat16>((size_t)9 * ci[i] * co[i]); w.wd_c1[i] = b.take<__nv_bfloat16>((size_t)9 * ci[i] * co[i]);
@@ -249,6 +264,7 @@ void carve(const mivit_vit_config* c, int B, void* base, Workspace& w) {
   w.dv = b.take<float>(T * E); w.dctx = b.take<float>(T * E); w.dh = b.take<float>(T * HD); w.dh2 = b.take<float>(T * HD);
   w.dheadin = b.take<float>((size_t)B * hin); w.dhh = b.take<float>((size_t)HR * c->head_hidden);
   w.dfp = b.take<float>((size_t)B * E); w.dfp_h = b.take<float>((size_t)B * E); w.demb = b.take<float>(NF * E);
+  w.enc_wt = b.take<float>((size_t)c->L * encoder_bwd_packed_floats(E, HD));
   w.bytes = (b.off + 255) & ~(size_t)255;
 }
 
@@ -606,10 +622,46 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
   CK(layernorm_bwd(w.dxa, xlast, w.mf, w.rf, p + L.tn_g, w.dxb, g + L.tn_g, g + L.tn_b, T, E, 0, 0, 0, st));
   float* dx = w.dxb;    // gradient w.r.t. the current layer output
   float* tmp = w.dxa;
+  // one persistent kernel per layer for the whole input-gradient chain (encoder_fused_bwd.cu) + three weight-gradient launches
+  bool fused_bwd = g_linear_tc && c->activation == 0 && encoder_fused_supported(B, S, E, HD, H) && c->L <= kEncMaxLayers &&
+                   linear_wgrad_tc_supported(T, E, E) && linear_wgrad_tc_supported(T, E, HD) && linear_wgrad_tc_supported(T, HD, E) &&
+                   !getenv("MIVIT_NO_FUSED_ENCODER_BWD");
+  for (int l = 0; fused_bwd && l < c->L; ++l) {   // the weight-gradient flushes are 16-byte vector reductions
+    const auto& Y = L.lyr[l];
+    fused_bwd = al16(g + Y.q_w) && al16(g + Y.k_w) && al16(g + Y.v_w) && al16(g + Y.o_w) && al16(g + Y.f1_w) && al16(g + Y.f2_w);
+  }
+  if (fused_bwd) {
+    long long offs[kEncMaxLayers][6];
+    for (int l = 0; l < c->L; ++l) {
+      const auto& Y = L.lyr[l];
+      const long long o[6] = {Y.q_w, Y.k_w, Y.v_w, Y.o_w, Y.f1_w, Y.f2_w};
+      for (int i = 0; i < 6; ++i) offs[l][i] = o[i];
+    }
+    CK(encoder_pack_bwd_weights(p, offs, c->L, E, HD, w.enc_wt, st));
+  }
   for (int l = c->L - 1; l >= 0; --l) {
     const auto& Y = L.lyr[l];
     LayerWS& y = w.lyr[l];
     const float* xin = l == 0 ? w.tok : w.lyr[l - 1].x2;
+    if (fused_bwd) {
+      EncoderLayerBwdIO io;
+      io.dy = dx; io.dx = dx;
+      io.z2 = y.z2; io.m2 = y.m2; io.r2 = y.r2; io.hact = y.hact; io.z1 = y.z1; io.m1 = y.m1; io.r1 = y.r1;
+      io.q = y.q; io.k = y.k; io.v = y.v; io.lse = y.probs; io.ctx = y.ctx;
+      io.g2 = p + Y.n2_g; io.g1 = p + Y.n1_g;
+      io.packed = w.enc_wt + (size_t)l * encoder_bwd_packed_floats(E, HD);
+      io.dz2 = tmp; io.dh2 = w.dh2; io.dz1 = w.dctx; io.dq = w.dq; io.dk = w.dk; io.dv = w.dv;
+      io.dg2 = g + Y.n2_g; io.db2 = g + Y.n2_b; io.dg1 = g + Y.n1_g; io.db1 = g + Y.n1_b;
+      CK(encoder_layer_bwd(io, B, S, E, HD, H, st));
+      const float* dYs[4] = {w.dq, w.dk, w.dv, w.dctx};
+      const float* Xs[4] = {xin, xin, xin, y.ctx};
+      float* dWs[4] = {g + Y.q_w, g + Y.k_w, g + Y.v_w, g + Y.o_w};
+      float* dbs[4] = {g + Y.q_b, g + Y.k_b, g + Y.v_b, g + Y.o_b};
+      CK(linear_wgrad_tc_batched(4, dYs, Xs, dWs, dbs, T, E, E, st));
+      CK(linear_wgrad_tc(tmp, y.hact, g + Y.f2_w, g + Y.f2_b, T, E, HD, st));
+      CK(linear_wgrad_tc(w.dh2, y.x1, g + Y.f1_w, g + Y.f1_b, T, HD, E, st));
+      continue;
+    }
     // x2 = LN2(x1 + ff)
     CK(layernorm_bwd(dx, y.z2, y.m2, y.r2, p + Y.n2_g, tmp, g + Y.n2_g, g + Y.n2_b, T, E, 0, 0, 0, st));  // tmp = dz2 = dff = dx1
     if (c->activation == 0 && g_linear_tc && linear_tc_supported(T, E, HD) && al16(tmp) && al16(p + Y.f2_w) && al16(w.dh2) &&
@@ -700,8 +752,6 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
   const long long rows = w.rows, rp = w.rows_pad;
   const double cnt = (double)NF * P * P;
   const int impl = c->conv_impl;
-  RowsT* guarded[] = {&w.draw4, &w.draws2, &w.draw3, &w.draw2, &w.draws1, &w.draw1};
-  for (RowsT* t : guarded) CK(zero_guards(*t, rp, st));
   const ConvShifts s3 = make_shifts(P, 9, false), s3m = make_shifts(P, 9, true), s1 = make_shifts(P, 1, false);
   const int ci[2] = {32, 64}, co[2] = {64, 128};
   RowsT* in[2] = {&w.act0, &w.act2};
@@ -723,6 +773,9 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
     CK(pack_conv_weights(p + R.c2_w, w.wd_c2[b], co[b], co[b], 9, 1, st));
     CK(pack_conv_weights(p + R.sk_w, w.wd_sk[b], co[b], ci[b], 1, 1, st));
     // out = relu(bn2(raw2) + bns(raws))
+    // (the gradient tensors share three slots, see carve(): guards are zeroed when a tensor moves in, i.e. before its producer)
+    CK(zero_guards(*d2[b], rp, st));
+    CK(zero_guards(*ds[b], rp, st));
     if (b == 1) {
       CK(bn_backward(nullptr, nullptr, w.dpooled, r2[b]->row0, w.bn[i2].ss, w.bn[i2].mi, p + R.bn2_g, d2[b]->row0, g + R.bn2_g,
                      g + R.bn2_b, rs[b]->row0, w.bn[is].ss, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g, g + R.bns_b,
@@ -732,6 +785,12 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
                      g + R.bn2_g, g + R.bn2_b, rs[b]->row0, w.bn[is].ss, w.bn[is].mi, p + R.bns_g, ds[b]->row0, g + R.bns_g,
                      g + R.bns_b, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, 0, st));
     }
+    // The skip path first: its gradient tensor leaves its slot before conv2's input gradient needs one (carve()).  Block 1 on
+    // the product path keeps it for the ONE kernel that accumulates the conv1 (3x3) and skip (1x1) input gradients into one
+    // accumulator and one output tensor (dinm); otherwise two convolutions, and BatchNorm's backward sums the two tensors.
+    CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
+    const bool try_dual = impl == 1 && b == 0;   // (block 2: the resident weights would force 32-column slices, measured slower)
+    if (!try_dual) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
     CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
     // conv2 input gradient; on the product path its epilogue also accumulates the backward sums of bn1 (no reduction pass)
     bool bn1_summed = false;
@@ -741,24 +800,20 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
                                 st, &bn1_summed));
     }
     if (!bn1_summed) CK(conv_rows_forward(d2[b]->row0, w.wd_c2[b], da1[b]->row0, nullptr, rows, P, co[b], co[b], 9, s3m, impl, st));
-    CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
     // act1 = relu(bn1(raw1))
+    CK(zero_guards(*d1[b], rp, st));
     CK(bn_backward(da1[b]->row0, nullptr, nullptr, r1[b]->row0, w.bn[i1].ss, w.bn[i1].mi, p + R.bn1_g, d1[b]->row0, g + R.bn1_g,
                    g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, bn1_summed ? 1 : 0, st));
     CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
-    // gradient of the block input: conv1 path (3x3) + skip path (1x1).  Product path: ONE kernel, one accumulator, one
-    // output tensor (dinm); otherwise two convolutions and BatchNorm's backward sums the two tensors.
     fused_in[b] = false;
-    if (impl == 1) {
+    if (try_dual) {
       bool handled = false;
       CK(conv_rows_forward_dual_v3(d1[b]->row0, w.wd_c1[b], ds[b]->row0, w.wd_sk[b], dinm[b]->row0, rows, P, co[b], co[b], ci[b], s3m,
                                    st, &handled));
       fused_in[b] = handled;
+      if (!handled) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
     }
-    if (!fused_in[b]) {
-      CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
-      CK(conv_rows_forward(d1[b]->row0, w.wd_c1[b], dinm[b]->row0, nullptr, rows, P, co[b], ci[b], 9, s3m, impl, st));
-    }
+    if (!fused_in[b]) CK(conv_rows_forward(d1[b]->row0, w.wd_c1[b], dinm[b]->row0, nullptr, rows, P, co[b], ci[b], 9, s3m, impl, st));
   }
   // act0 = relu(bn0(raw0)); upstream = conv1 path + skip path of block 1
   CK(zero_guards(w.draw0, rp, st));

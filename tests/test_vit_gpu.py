@@ -585,9 +585,10 @@ def test_forward_and_train_step_from_trajectories(golden_dir, kind, P, E):
     ("linear", 64, 4, 128, 2, 9, 63, 9, False, True),          # S = 64: the largest fused shape, two sequences per tile
 ])
 def test_fused_encoder_layer_matches_unfused_path_and_oracle(emb, E, H, HD, Lyr, P, Fr, B, pos, reg):
-    """csrc/encoder_fused.cu: the persistent per-layer kernel (tf32 tcgen05 GEMMs chained through shared memory / TMEM, in-register
-    softmax and LayerNorm) against the unfused kernels (MIVIT_NO_FUSED_ENCODER=1) -- prediction and every gradient, i.e. every
-    tensor the fused forward hands to the backward -- and against the fp32 oracle within tf32 tolerance."""
+    """csrc/encoder_fused.cu / encoder_fused_bwd.cu: the persistent per-layer kernels (tf32 tcgen05 GEMMs chained through shared
+    memory / TMEM, in-register softmax and LayerNorm and their backwards) against the unfused kernels (MIVIT_NO_FUSED_ENCODER=1,
+    MIVIT_NO_FUSED_ENCODER_BWD=1), in every forward / backward combination -- prediction and every gradient, i.e. every tensor the
+    fused forward hands to either backward -- and against the fp32 oracle within tf32 tolerance."""
     import torch
     import torch.nn.functional as F
     from moleculardiffusion_mivit_b200 import models as M
@@ -601,21 +602,27 @@ def test_fused_encoder_layer_matches_unfused_path_and_oracle(emb, E, H, HD, Lyr,
     tgt = torch.rand((B, 1), generator=g)
     model.cuda().train()
     outs = []
-    for no_fused in ("1", ""):
-        if no_fused:
-            os.environ["MIVIT_NO_FUSED_ENCODER"] = no_fused
-        else:
-            os.environ.pop("MIVIT_NO_FUSED_ENCODER", None)
+    # (forward, backward) kernels: unfused / unfused, fused / unfused, fused / fused (csrc/encoder_fused_bwd.cu), unfused / fused
+    for no_fwd, no_bwd in (("1", "1"), ("", "1"), ("", ""), ("1", "")):
+        for var, val in (("MIVIT_NO_FUSED_ENCODER", no_fwd), ("MIVIT_NO_FUSED_ENCODER_BWD", no_bwd)):
+            if val:
+                os.environ[var] = val
+            else:
+                os.environ.pop(var, None)
         model.zero_grad()
         pred = model(x.cuda())
         F.mse_loss(pred, tgt.cuda()).backward()
         outs.append((pred.detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()}))
-    (p0, g0), (p1, g1) = outs
-    assert (p0 - p1).abs().max().item() < 2e-3 * max(1.0, p0.abs().max().item())        # both tf32; different summation order
+    os.environ.pop("MIVIT_NO_FUSED_ENCODER", None)
+    os.environ.pop("MIVIT_NO_FUSED_ENCODER_BWD", None)
+    (p0, g0) = outs[0]
     gmax = max(float(v.norm()) for v in g0.values())
-    for k in g0:
-        if float(g0[k].norm()) > 1e-4 * gmax:
-            assert relnorm(g1[k], g0[k]) < 2e-2, (k, relnorm(g1[k], g0[k]))
+    for p1, g1 in outs[1:]:
+        assert (p0 - p1).abs().max().item() < 2e-3 * max(1.0, p0.abs().max().item())        # both tf32; different summation order
+        for k in g0:
+            if float(g0[k].norm()) > 1e-4 * gmax:
+                assert relnorm(g1[k], g0[k]) < 2e-2, (k, relnorm(g1[k], g0[k]))
+    p1, g1 = outs[2]
     ref_pred, _, ref_g, _ = vo.loss_and_grads(sd, cfg, x, tgt, None)
     assert (p1 - ref_pred).abs().max().item() < 5e-3 * max(1.0, ref_pred.abs().max().item())
     for k in g1:
