@@ -458,9 +458,11 @@ def run_b200(args, rank, world, local_rank):
                 "groups_ms_per_step": {"convolutions": conv_ms, "batchnorm_streams": bn_ms, "transformer_tagged": tr_ms,
                                        "render": group(["render_"])[0], "step_instrumented": step_ms},
                 "batchnorm_streams": {"ms_per_step": bn_ms, "share_of_step": bn_ms / step_ms,
-                                      "gbs_nominal": bn_bytes / (bn_ms * 1e-3) / 1e9 if bn_ms else None,
-                                      "note": "HBM streams; nominal bytes count the pad rows whose loads are predicated off, "
-                                              "DRAM bytes from ncu are in profiles/"},
+                                      "gbs_algorithmic": bn_bytes / (bn_ms * 1e-3) / 1e9 if bn_ms else None,
+                                      "frac_of_hbm_peak": (bn_bytes / (bn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if bn_ms else None,
+                                      "note": "HBM streams; algorithmic bytes = valid pixels x channels x 2 B x tensors touched "
+                                              "(pad rows of the pitched layout excluded); DRAM bytes per kernel from ncu are in "
+                                              "profiles/r02_ncu_bn.md"},
                 "whole_step": {"model_tflops": value * w["flops_per_seq"] / 1e12 / world,
                                "frac_of_sustained": value * w["flops_per_seq"] / 1e12 / world / peaks["bf16_tflops"],
                                "frac_of_burst": (value * w["flops_per_seq"] / 1e12 / world / peaks["bf16_tflops_burst"])

@@ -818,7 +818,10 @@ int bn_apply(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16*
   MIVIT_CHECK_ARG(rows_pad < (1ll << 31), "too many activation rows for one launch (%lld)", rows_pad);
   const int blocks = mivit_ceil_div(rows_pad, kRowsPerCta);
   const RowGeom geo = make_geom(rows, P);
-  MivitProfScope prof("bn_apply", (double)rows_pad * C * 2 * (raw_b ? 3 : 2), st);
+  // work = ALGORITHMIC bytes: the valid pixels only (the loads of the pad rows, (P+1)^2 / P^2 - 1 = 16 % of the rows at P = 13,
+  // are predicated off; their zero stores still reach DRAM -- the ncu figures are in profiles/r02_ncu_bn.md)
+  const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
+  MivitProfScope prof("bn_apply", valid_rows * C * 2 * (raw_b ? 3 : 2), st);
   if (raw_b != nullptr) {
     BN_DISPATCH_C(C, (bn_apply_kernel<CC, true><<<blocks, 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, act, geo, rows_pad)));
   } else {
@@ -922,7 +925,7 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
     mivit_count_launch();
     MIVIT_LAUNCH_CHECK();
   } else {
-    MivitProfScope prof("bn_bwd_reduce", (double)rows * C * 2 * ((raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
+    MivitProfScope prof("bn_bwd_reduce", (double)rows * P * P / ((double)(P + 1) * (P + 1)) * C * 2 * ((raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
     BN_BWD_REDUCE_LAUNCH(blocks, up_a, up_b, dpooled, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, geo, rpb);
     mivit_count_launch();
     MIVIT_LAUNCH_CHECK();
@@ -945,7 +948,7 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
   MIVIT_LAUNCH_CHECK();
   const int ablocks = mivit_ceil_div(rows_pad, kApplyRowsPerCta);
   {
-    MivitProfScope prof("bn_bwd_apply", (double)rows_pad * C * 2 * (2 * (raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
+    MivitProfScope prof("bn_bwd_apply", (double)rows * P * P / ((double)(P + 1) * (P + 1)) * C * 2 * (2 * (raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
     BN_BWD_APPLY_LAUNCH(ablocks, up_a, up_b, dpooled, raw_a, ss_a, coef_a, draw_a, raw_b, ss_b, coef_b, draw_b, geo, rows_pad);
     mivit_count_launch();
     MIVIT_LAUNCH_CHECK();

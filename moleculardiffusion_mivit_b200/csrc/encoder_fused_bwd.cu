@@ -78,19 +78,14 @@ __device__ __forceinline__ void issue_chain(uint32_t tmem, const uint8_t* a, con
   }
 }
 
-// XOR-swizzled row-major tile [128][CH x 16 B]: the 64-byte group g = c / 4 of row r (one head's 16 floats) lives at group
-// position g ^ (r & (CH / 4 - 1)); the four chunks of a group stay in order, so a head block is 64 contiguous bytes and the
-// attention loops address it with ONE computed offset + immediates (a per-chunk XOR cost 18 % of the kernel's instructions).
-// Lanes holding consecutive rows and the same chunk spread over CH / 4 bank groups (8-way instead of 32-way conflicts; a padded
-// layout would not fit in shared memory).
+// XOR-swizzled row-major tile [128][CH x 16 B]: chunk c of row r lives at position c ^ (r & (CH - 1)).  A warp whose lanes
+// hold 32 consecutive rows and the same chunk index hits every bank group once (a padded layout would not fit here).
+// (Measured alternative: swizzling whole 64-byte head blocks, so that the attention loops address a block with one computed
+// offset + immediates, executes 7 % fewer instructions but pays 8-way instead of no bank conflicts on every thread-per-row
+// access: 121.5 vs 106.9 us per launch under ncu, profiles/r02_ncu_encoder_bwd.md.)
 template <int CH>
 __device__ __forceinline__ uint32_t rm_off(int r, int c) {
-  return (uint32_t)r * (CH * 16) + (uint32_t)((((c >> 2) ^ (r & (CH / 4 - 1))) << 6) | ((c & 3) << 4));
-}
-// byte offset of head block h (64 bytes) of row r
-template <int CH>
-__device__ __forceinline__ uint32_t head_off(int r, int h) {
-  return (uint32_t)r * (CH * 16) + (uint32_t)((h ^ (r & (CH / 4 - 1))) << 6);
+  return (uint32_t)r * (CH * 16) + (uint32_t)((c ^ (r & (CH - 1))) << 4);
 }
 template <int CH>
 __device__ __forceinline__ float4 rm_ld(const uint8_t* tile, int r, int c) {
@@ -144,20 +139,20 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
-// 16 floats of a head block (64 contiguous bytes at blk)
-template <int D>
-__device__ __forceinline__ void ld_head(const uint8_t* blk, float (&o)[D], float mul) {
+// 16 floats of a row's head block (4 chunks from chunk c0) of a swizzled tile
+template <int CH, int D>
+__device__ __forceinline__ void ld_head(const uint8_t* tile, int row, int c0, float (&o)[D], float mul) {
 #pragma unroll
   for (int j = 0; j < D / 4; ++j) {
-    const float4 t = *reinterpret_cast<const float4*>(blk + 16 * j);
+    const float4 t = rm_ld<CH>(tile, row, c0 + j);
     o[4 * j] = t.x * mul; o[4 * j + 1] = t.y * mul; o[4 * j + 2] = t.z * mul; o[4 * j + 3] = t.w * mul;
   }
 }
-template <int D>
-__device__ __forceinline__ void st_head(uint8_t* blk, const float (&o)[D], float mul) {
+template <int CH, int D>
+__device__ __forceinline__ void st_head(uint8_t* tile, int row, int c0, const float (&o)[D], float mul) {
 #pragma unroll
   for (int j = 0; j < D / 4; ++j)
-    *reinterpret_cast<float4*>(blk + 16 * j) = make_float4(o[4 * j] * mul, o[4 * j + 1] * mul, o[4 * j + 2] * mul, o[4 * j + 3] * mul);
+    rm_st<CH>(tile, row, c0 + j, make_float4(o[4 * j] * mul, o[4 * j + 1] * mul, o[4 * j + 2] * mul, o[4 * j + 3] * mul));
 }
 
 // LayerNorm backward of a token row whose E columns are split into 16-column slices over the column-slice warps.
@@ -408,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       float* Ls = lsdl + warp * 2 * SMAX;
       float* Dl = Ls + SMAX;
       for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
-        const int sq = pair / NH, h = pair % NH, rb = sq * S;
+        const int sq = pair / NH, h = pair % NH, c0 = h * (D / 4), rb = sq * S;
         // pass A (lane = query row i): D_i = dctx_i . ctx_i, dQ_i = scale * sum_j dS_ij K_j
         float dqv[RPL][D];
 #pragma unroll
@@ -416,9 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
           const int i = lane + 32 * rr;
           if (i < S) {
             float gi[D], qi[D];
-            const uint32_t oi = head_off<CH>(rb + i, h);
-            ld_head<D>(R3 + oi, gi, 1.f);
-            ld_head<D>(R0 + oi, qi, scale);
+            ld_head<CH, D>(R3, rb + i, c0, gi, 1.f);
+            ld_head<CH, D>(R0, rb + i, c0, qi, scale);
             float di = 0.f;
             const float4* op = reinterpret_cast<const float4*>(a.ctx + (row0 + rb + i) * E + h * D);
 #pragma unroll
@@ -435,9 +429,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
             for (int c = 0; c < D; ++c) acc[c] = 0.f;
             for (int j = 0; j < S; ++j) {
               float kj[D], vj[D];
-              const uint32_t oj = head_off<CH>(rb + j, h);
-              ld_head<D>(R1 + oj, kj, 1.f);
-              ld_head<D>(R2 + oj, vj, 1.f);
+              ld_head<CH, D>(R1, rb + j, c0, kj, 1.f);
+              ld_head<CH, D>(R2, rb + j, c0, vj, 1.f);
               float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
 #pragma unroll
               for (int c = 0; c < D; c += 2) {
@@ -460,16 +453,15 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
         for (int rr = 0; rr < RPL; ++rr) {
           const int j = lane + 32 * rr;
           if (j < S) {
-            const uint32_t oj = head_off<CH>(rb + j, h);
-            ld_head<D>(R1 + oj, kjs[rr], scale);
-            ld_head<D>(R2 + oj, vjs[rr], 1.f);
+            ld_head<CH, D>(R1, rb + j, c0, kjs[rr], scale);
+            ld_head<CH, D>(R2, rb + j, c0, vjs[rr], 1.f);
           }
         }
         __syncwarp();              // every lane holds its k / v rows: the k block is dead, dq moves in
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) {
           const int i = lane + 32 * rr;
-          if (i < S) st_head<D>(R1 + head_off<CH>(rb + i, h), dqv[rr], 1.f);
+          if (i < S) st_head<CH, D>(R1, rb + i, c0, dqv[rr], 1.f);
         }
         float dkv[RPL][D];
 #pragma unroll
@@ -481,9 +473,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
             for (int c = 0; c < D; ++c) ak[c] = av[c] = 0.f;
             for (int i = 0; i < S; ++i) {
               float qi[D], gi[D];
-              const uint32_t oi = head_off<CH>(rb + i, h);
-              ld_head<D>(R0 + oi, qi, 1.f);
-              ld_head<D>(R3 + oi, gi, 1.f);
+              ld_head<CH, D>(R0, rb + i, c0, qi, 1.f);
+              ld_head<CH, D>(R3, rb + i, c0, gi, 1.f);
               float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
 #pragma unroll
               for (int c = 0; c < D; c += 2) {
@@ -495,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
 #pragma unroll
               for (int c = 0; c < D; ++c) { ak[c] = fmaf(ds, qi[c], ak[c]); av[c] = fmaf(p, gi[c], av[c]); }
             }
-            st_head<D>(R2 + head_off<CH>(rb + j, h), av, 1.f);      // the v block is dead since the loads above
+            st_head<CH, D>(R2, rb + j, c0, av, 1.f);      // the v block is dead since the loads above
 #pragma unroll
             for (int c = 0; c < D; ++c) dkv[rr][c] = ak[c] * scale;
           }
@@ -504,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) {
           const int j = lane + 32 * rr;
-          if (j < S) st_head<D>(R0 + head_off<CH>(rb + j, h), dkv[rr], 1.f);
+          if (j < S) st_head<CH, D>(R0, rb + j, c0, dkv[rr], 1.f);
         }
         __syncwarp();
       }
