@@ -139,6 +139,156 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// ---- warp-level tensor-core pieces of the attention backward (S <= 32): mma.sync m16n8k8 tf32 --------------------------------
+// Fragment layouts (PTX ISA, m16n8k8 .tf32; gid = lane / 4, tig = lane % 4):
+//   A 16x8 (row):  a0 = (gid, tig)      a1 = (gid + 8, tig)      a2 = (gid, tig + 4)      a3 = (gid + 8, tig + 4)
+//   B  8x8 (col):  b0 = (k = tig, n = gid)                       b1 = (k = tig + 4, n = gid)
+//   C 16x8:        c0 = (gid, 2 tig)    c1 = (gid, 2 tig + 1)    c2 = (gid + 8, 2 tig)    c3 = (gid + 8, 2 tig + 1)
+__device__ __forceinline__ void mma_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// 3xTF32 split: x = hi + lo with hi exactly representable in tf32 (the score GEMMs must reproduce the forward's fp32 scores:
+// P_ij = exp(s_ij - L_i) is only normalised if s_ij matches the s_ij the log-sum-exp L_i was computed from)
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// element (row, col) of a swizzled row-major tile; rows past the tile are clamped (finite data: a masked 0 * NaN would poison the MMA)
+template <int CH>
+__device__ __forceinline__ float tile_el(const uint8_t* tile, int row, int col) {
+  row = min(row, kRows - 1);
+  return *reinterpret_cast<const float*>(tile + rm_off<CH>(row, col >> 2) + ((col & 3) << 2));
+}
+// K-major A slab [CH][128][16 B] straight from global rows (cp.async; rows past nrows are zero)
+template <int CH>
+__device__ __forceinline__ void fill_slab(uint8_t* slab, const float* __restrict__ g, long long row0, int nrows, int tid) {
+  const uint4* src = reinterpret_cast<const uint4*>(g + row0 * (CH * 4));
+  for (int i = tid; i < kRows * CH; i += kThreads) {
+    const int r = i / CH, c = i % CH;
+    uint8_t* d = slab + ((size_t)c * kRows + r) * 16;
+    if (r < nrows) cp16(d, src + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// Attention backward of ONE (sequence, head) on one warp with tensor-core MMAs (S <= 32, head dim 16).  Q / K / V / dctx are
+// the swizzled tiles Qt / Kt / Vt / Gt (rows rb .. rb + S of the CTA's tile, columns hc .. hc + 16); Ls / Dl = this warp's row
+// log-sum-exps and D_i = dctx_i . ctx_i (entries >= S are 0).  Two orientations, each in two halves of 16 rows:
+//   rows = queries i:  s = (scale Q) K^T (3xTF32), dP = G V^T  ->  dS = P (dP - D)  ->  dQ = scale dS K
+//   rows = keys j:     s^T = (scale K) Q^T,        dP^T = V G^T ->  P^T, dS^T        ->  dV = P^T G,  dK = scale dS^T Q
+// The C fragments of the first stage are the A fragments of the second with the reduction index permuted inside each group of 8
+// (slot tig <-> token 2 tig, slot tig + 4 <-> token 2 tig + 1); the B fragments of the second stage are loaded with the same
+// permutation, so nothing moves between lanes.  Results go straight to HBM (the weight-gradient launches read them there; the
+// CTA reads them back from L2 as K-major slabs for the q/k/v input-gradient GEMM).
+template <int E, int CH>
+__device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8_t* Kt, const uint8_t* Vt, const uint8_t* Gt,
+                                                  const float* Ls, const float* Dl, int rb, int hc, int S, float scale, int lane,
+                                                  float* __restrict__ gdq, float* __restrict__ gdk, float* __restrict__ gdv) {
+  const int gid = lane >> 2, tig = lane & 3;
+  constexpr float kLog2e = 1.4426950408889634f;   // P = 2^(s log2e - L log2e): Ls holds L log2e, the scaled operand carries log2e
+  const float sl2 = scale * kLog2e;
+#pragma unroll 1
+  for (int orient = 0; orient < 2; ++orient) {
+    // orient 0: rows = queries (A operands Q, G; B operands K, V; second stage B = K -> dQ)
+    // orient 1: rows = keys    (A operands K, V; B operands Q, G; second stage B = G -> dV and B = Q -> dK)
+    const uint8_t* A1 = orient == 0 ? Qt : Kt;     // scaled, 3xTF32
+    const uint8_t* A2 = orient == 0 ? Gt : Vt;
+    const uint8_t* B1 = orient == 0 ? Kt : Qt;     // 3xTF32
+    const uint8_t* B2 = orient == 0 ? Vt : Gt;
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = mt * 16 + gid, r1 = r0 + 8;                    // this lane's two rows (of the orientation)
+      uint32_t ah[2][4], al[2][4], a2[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int ca = hc + ks * 8 + tig, cb = ca + 4;
+        tf32_split(tile_el<CH>(A1, rb + r0, ca) * sl2, ah[ks][0], al[ks][0]);
+        tf32_split(tile_el<CH>(A1, rb + r1, ca) * sl2, ah[ks][1], al[ks][1]);
+        tf32_split(tile_el<CH>(A1, rb + r0, cb) * sl2, ah[ks][2], al[ks][2]);
+        tf32_split(tile_el<CH>(A1, rb + r1, cb) * sl2, ah[ks][3], al[ks][3]);
+        a2[ks][0] = tf32_rna(tile_el<CH>(A2, rb + r0, ca));
+        a2[ks][1] = tf32_rna(tile_el<CH>(A2, rb + r1, ca));
+        a2[ks][2] = tf32_rna(tile_el<CH>(A2, rb + r0, cb));
+        a2[ks][3] = tf32_rna(tile_el<CH>(A2, rb + r1, cb));
+      }
+      // orientation 0: L, D belong to the rows; orientation 1: to the columns
+      const float Lr0 = Ls[r0], Lr1 = Ls[r1], Dr0 = Dl[r0], Dr1 = Dl[r1];
+      uint32_t pa[4][4], da[4][4];     // second-stage A fragments: P (orientation 1 only) and dS, one k-step per first-stage n-tile
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int cr = rb + nt * 8 + gid;                            // row of the B-operand tiles
+        uint32_t bh[2][2], bl[2][2], b2[2][2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int ca = hc + ks * 8 + tig;
+          tf32_split(tile_el<CH>(B1, cr, ca), bh[ks][0], bl[ks][0]);
+          tf32_split(tile_el<CH>(B1, cr, ca + 4), bh[ks][1], bl[ks][1]);
+          b2[ks][0] = tf32_rna(tile_el<CH>(B2, cr, ca));
+          b2[ks][1] = tf32_rna(tile_el<CH>(B2, cr, ca + 4));
+        }
+        float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          mma_16x8x8(sc, al[ks], bh[ks]);
+          mma_16x8x8(sc, ah[ks], bl[ks]);
+          mma_16x8x8(sc, ah[ks], bh[ks]);
+          mma_16x8x8(dp, a2[ks], b2[ks]);
+        }
+        const int c0 = nt * 8 + 2 * tig, c1 = c0 + 1;               // this lane's two columns
+        float L00, L01, L10, L11, D00, D01, D10, D11;               // (row r0 | r1, column c0 | c1)
+        if (orient == 0) {
+          L00 = L01 = Lr0; L10 = L11 = Lr1; D00 = D01 = Dr0; D10 = D11 = Dr1;
+        } else {
+          L00 = L10 = Ls[c0]; L01 = L11 = Ls[c1]; D00 = D10 = Dl[c0]; D01 = D11 = Dl[c1];
+        }
+        const bool v00 = r0 < S && c0 < S, v01 = r0 < S && c1 < S, v10 = r1 < S && c0 < S, v11 = r1 < S && c1 < S;
+        const float p00 = v00 ? exp2f(sc[0] - L00) : 0.f, p01 = v01 ? exp2f(sc[1] - L01) : 0.f;
+        const float p10 = v10 ? exp2f(sc[2] - L10) : 0.f, p11 = v11 ? exp2f(sc[3] - L11) : 0.f;
+        const float d00 = v00 ? p00 * (dp[0] - D00) : 0.f, d01 = v01 ? p01 * (dp[1] - D01) : 0.f;
+        const float d10 = v10 ? p10 * (dp[2] - D10) : 0.f, d11 = v11 ? p11 * (dp[3] - D11) : 0.f;
+        // A fragment of k-step nt: slot tig <- column c0, slot tig + 4 <- column c1
+        da[nt][0] = tf32_rna(d00); da[nt][1] = tf32_rna(d10); da[nt][2] = tf32_rna(d01); da[nt][3] = tf32_rna(d11);
+        if (orient == 1) { pa[nt][0] = tf32_rna(p00); pa[nt][1] = tf32_rna(p10); pa[nt][2] = tf32_rna(p01); pa[nt][3] = tf32_rna(p11); }
+      }
+      float o1[2][4] = {}, o2[2][4] = {};     // orientation 0: o1 = dQ;  orientation 1: o1 = dK, o2 = dV
+      const uint8_t* S1 = orient == 0 ? Kt : Qt;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int ta = rb + ks * 8 + 2 * tig, tb = ta + 1;            // tokens behind slots tig and tig + 4
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int col = hc + nt * 8 + gid;
+          uint32_t b[2] = {tf32_rna(tile_el<CH>(S1, ta, col)), tf32_rna(tile_el<CH>(S1, tb, col))};
+          mma_16x8x8(o1[nt], da[ks], b);
+          if (orient == 1) {
+            uint32_t bg[2] = {tf32_rna(tile_el<CH>(Gt, ta, col)), tf32_rna(tile_el<CH>(Gt, tb, col))};
+            mma_16x8x8(o2[nt], pa[ks], bg);
+          }
+        }
+      }
+      float* g1 = orient == 0 ? gdq : gdk;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = hc + nt * 8 + 2 * tig;
+        if (r0 < S) {
+          *reinterpret_cast<float2*>(g1 + (size_t)(rb + r0) * E + col) = make_float2(o1[nt][0] * scale, o1[nt][1] * scale);
+          if (orient == 1) *reinterpret_cast<float2*>(gdv + (size_t)(rb + r0) * E + col) = make_float2(o2[nt][0], o2[nt][1]);
+        }
+        if (r1 < S) {
+          *reinterpret_cast<float2*>(g1 + (size_t)(rb + r1) * E + col) = make_float2(o1[nt][2] * scale, o1[nt][3] * scale);
+          if (orient == 1) *reinterpret_cast<float2*>(gdv + (size_t)(rb + r1) * E + col) = make_float2(o2[nt][2], o2[nt][3]);
+        }
+      }
+    }
+  }
+}
+
 // 16 floats of a row's head block (4 chunks from chunk c0) of a swizzled tile
 template <int CH, int D>
 __device__ __forceinline__ void ld_head(const uint8_t* tile, int row, int c0, float (&o)[D], float mul) {
@@ -288,24 +438,28 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       __syncwarp();
     }
     copy_out<CH>(R3, a.dz2, row0, nrows, E, 0, tid);
+    // the ReLU gate (sign of the stored relu(h)) of this thread's columns of both hidden chunks: in flight during the MMA
+    float4 gate[HD / E][4];
+#pragma unroll
+    for (int chunk = 0; chunk < HD / E; ++chunk)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        gate[chunk][c] = live ? __ldg(reinterpret_cast<const float4*>(a.hact + (row0 + r) * HD + chunk * E + sl * 16) + c)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     __syncthreads();               // staging tile consumed
-#pragma unroll 1
+#pragma unroll
     for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: ReLU gate, A operand, staged copy to HBM
       if (act) {
         const int c0 = chunk * E + sl * 16;
         float v[16];
         umma::tmem_ld16(trow + (uint32_t)(C1 + c0), v);
-        const float4* hp = reinterpret_cast<const float4*>(a.hact + (row0 + r) * HD + c0);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) {
-            const float4 h4 = __ldg(hp + c);
-            t = make_float4(h4.x > 0.f ? v[4 * c] : 0.f, h4.y > 0.f ? v[4 * c + 1] : 0.f, h4.z > 0.f ? v[4 * c + 2] : 0.f,
-                            h4.w > 0.f ? v[4 * c + 3] : 0.f);
-          }
+          const float4 h4 = gate[chunk][c];
+          const float4 t = make_float4(h4.x > 0.f ? v[4 * c] : 0.f, h4.y > 0.f ? v[4 * c + 1] : 0.f, h4.z > 0.f ? v[4 * c + 2] : 0.f,
+                                       h4.w > 0.f ? v[4 * c + 3] : 0.f);
           *reinterpret_cast<float4*>(R1 + ((size_t)(c0 / 4 + c) * kRows + r) * 16) = t;
           rm_st<CH>(R3, r, sl * 4 + c, t);
         }
@@ -397,122 +551,159 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     cp_wait_all();
     umma::fence_before_sync();
     __syncthreads();
-    // ---- attention backward: one (sequence, head) per warp.  Results replace dead operands of the same (sequence, head)
-    //      block: dq -> k tile, dk -> q tile, dv -> v tile.
-    {
+    if constexpr (SMAX == 32) {
+      // ---- attention backward on warp-level tensor-core MMAs: one (sequence, head) per warp (attention_bwd_mma above)
       float* Ls = lsdl + warp * 2 * SMAX;
       float* Dl = Ls + SMAX;
       for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
-        const int sq = pair / NH, h = pair % NH, c0 = h * (D / 4), rb = sq * S;
-        // pass A (lane = query row i): D_i = dctx_i . ctx_i, dQ_i = scale * sum_j dS_ij K_j
-        float dqv[RPL][D];
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-          const int i = lane + 32 * rr;
-          if (i < S) {
-            float gi[D], qi[D];
-            ld_head<CH, D>(R3, rb + i, c0, gi, 1.f);
-            ld_head<CH, D>(R0, rb + i, c0, qi, scale);
-            float di = 0.f;
-            const float4* op = reinterpret_cast<const float4*>(a.ctx + (row0 + rb + i) * E + h * D);
+        const int sq = pair / NH, h = pair % NH, rb = sq * S;
+        {   // D_i = dctx_i . ctx_i and the row log-sum-exp, lane = query row
+          float di = 0.f, li = 0.f;
+          if (lane < S) {
+            float gi[D];
+            ld_head<CH, D>(R3, rb + lane, h * (D / 4), gi, 1.f);
+            const float4* op = reinterpret_cast<const float4*>(a.ctx + (row0 + rb + lane) * E + h * D);
 #pragma unroll
             for (int c = 0; c < D / 4; ++c) {
               const float4 o4 = __ldg(op + c);
               di = fmaf(gi[4 * c], o4.x, di); di = fmaf(gi[4 * c + 1], o4.y, di);
               di = fmaf(gi[4 * c + 2], o4.z, di); di = fmaf(gi[4 * c + 3], o4.w, di);
             }
-            const float li = __ldg(a.lse + ((size_t)(seq0 + sq) * NH + h) * S + i);
-            Ls[i] = li;
-            Dl[i] = di;
-            float acc[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) acc[c] = 0.f;
-            for (int j = 0; j < S; ++j) {
-              float kj[D], vj[D];
-              ld_head<CH, D>(R1, rb + j, c0, kj, 1.f);
-              ld_head<CH, D>(R2, rb + j, c0, vj, 1.f);
-              float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
-#pragma unroll
-              for (int c = 0; c < D; c += 2) {
-                s0 = fmaf(qi[c], kj[c], s0); s1 = fmaf(qi[c + 1], kj[c + 1], s1);
-                p0 = fmaf(gi[c], vj[c], p0); p1 = fmaf(gi[c + 1], vj[c + 1], p1);
-              }
-              const float p = __expf((s0 + s1) - li);
-              const float ds = p * ((p0 + p1) - di);
-#pragma unroll
-              for (int c = 0; c < D; ++c) acc[c] = fmaf(ds, kj[c], acc[c]);
-            }
-#pragma unroll
-            for (int c = 0; c < D; ++c) dqv[rr][c] = acc[c] * scale;
+            li = __ldg(a.lse + ((size_t)(seq0 + sq) * NH + h) * S + lane);
           }
+          Ls[lane] = li * 1.4426950408889634f;   // attention_bwd_mma works in base 2
+          Dl[lane] = di;
         }
         __syncwarp();
-        // pass B (lane = key row j): dK_j = scale * sum_i dS_ij Q_i,  dV_j = sum_i P_ij dctx_i
-        float kjs[RPL][D], vjs[RPL][D];
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-          const int j = lane + 32 * rr;
-          if (j < S) {
-            ld_head<CH, D>(R1, rb + j, c0, kjs[rr], scale);
-            ld_head<CH, D>(R2, rb + j, c0, vjs[rr], 1.f);
-          }
-        }
-        __syncwarp();              // every lane holds its k / v rows: the k block is dead, dq moves in
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-          const int i = lane + 32 * rr;
-          if (i < S) st_head<CH, D>(R1, rb + i, c0, dqv[rr], 1.f);
-        }
-        float dkv[RPL][D];
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-          const int j = lane + 32 * rr;
-          if (j < S) {
-            float ak[D], av[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) ak[c] = av[c] = 0.f;
-            for (int i = 0; i < S; ++i) {
-              float qi[D], gi[D];
-              ld_head<CH, D>(R0, rb + i, c0, qi, 1.f);
-              ld_head<CH, D>(R3, rb + i, c0, gi, 1.f);
-              float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
-#pragma unroll
-              for (int c = 0; c < D; c += 2) {
-                s0 = fmaf(kjs[rr][c], qi[c], s0); s1 = fmaf(kjs[rr][c + 1], qi[c + 1], s1);
-                p0 = fmaf(vjs[rr][c], gi[c], p0); p1 = fmaf(vjs[rr][c + 1], gi[c + 1], p1);
-              }
-              const float p = __expf((s0 + s1) - Ls[i]);
-              const float ds = p * ((p0 + p1) - Dl[i]);
-#pragma unroll
-              for (int c = 0; c < D; ++c) { ak[c] = fmaf(ds, qi[c], ak[c]); av[c] = fmaf(p, gi[c], av[c]); }
-            }
-            st_head<CH, D>(R2, rb + j, c0, av, 1.f);      // the v block is dead since the loads above
-#pragma unroll
-            for (int c = 0; c < D; ++c) dkv[rr][c] = ak[c] * scale;
-          }
-        }
-        __syncwarp();              // every lane is done with the q block: dk moves in
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) {
-          const int j = lane + 32 * rr;
-          if (j < S) st_head<CH, D>(R0, rb + j, c0, dkv[rr], 1.f);
-        }
+        attention_bwd_mma<E, CH>(R0, R1, R2, R3, Ls, Dl, rb, h * D, S, scale, lane, a.dq + row0 * E, a.dk + row0 * E, a.dv + row0 * E);
         __syncwarp();
       }
+      __syncthreads();             // dq / dk / dv of the tile are in HBM / L2; every tile is dead
+      fill_slab<CH>(R3, a.dq, row0, nrows, tid);
+      fill_slab<CH>(R1, a.dk, row0, nrows, tid);
+      fill_slab<CH>(R0, a.dv, row0, nrows, tid);
+      cp_wait_all();
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
+    } else {
+      // ---- attention backward: one (sequence, head) per warp.  Results replace dead operands of the same (sequence, head)
+      //      block: dq -> k tile, dk -> q tile, dv -> v tile.
+      {
+        float* Ls = lsdl + warp * 2 * SMAX;
+        float* Dl = Ls + SMAX;
+        for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
+          const int sq = pair / NH, h = pair % NH, c0 = h * (D / 4), rb = sq * S;
+          // pass A (lane = query row i): D_i = dctx_i . ctx_i, dQ_i = scale * sum_j dS_ij K_j
+          float dqv[RPL][D];
+#pragma unroll
+          for (int rr = 0; rr < RPL; ++rr) {
+            const int i = lane + 32 * rr;
+            if (i < S) {
+              float gi[D], qi[D];
+              ld_head<CH, D>(R3, rb + i, c0, gi, 1.f);
+              ld_head<CH, D>(R0, rb + i, c0, qi, scale);
+              float di = 0.f;
+              const float4* op = reinterpret_cast<const float4*>(a.ctx + (row0 + rb + i) * E + h * D);
+#pragma unroll
+              for (int c = 0; c < D / 4; ++c) {
+                const float4 o4 = __ldg(op + c);
+                di = fmaf(gi[4 * c], o4.x, di); di = fmaf(gi[4 * c + 1], o4.y, di);
+                di = fmaf(gi[4 * c + 2], o4.z, di); di = fmaf(gi[4 * c + 3], o4.w, di);
+              }
+              const float li = __ldg(a.lse + ((size_t)(seq0 + sq) * NH + h) * S + i);
+              Ls[i] = li;
+              Dl[i] = di;
+              float acc[D];
+#pragma unroll
+              for (int c = 0; c < D; ++c) acc[c] = 0.f;
+              for (int j = 0; j < S; ++j) {
+                float kj[D], vj[D];
+                ld_head<CH, D>(R1, rb + j, c0, kj, 1.f);
+                ld_head<CH, D>(R2, rb + j, c0, vj, 1.f);
+                float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; c += 2) {
+                  s0 = fmaf(qi[c], kj[c], s0); s1 = fmaf(qi[c + 1], kj[c + 1], s1);
+                  p0 = fmaf(gi[c], vj[c], p0); p1 = fmaf(gi[c + 1], vj[c + 1], p1);
+                }
+                const float p = __expf((s0 + s1) - li);
+                const float ds = p * ((p0 + p1) - di);
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[c] = fmaf(ds, kj[c], acc[c]);
+              }
+#pragma unroll
+              for (int c = 0; c < D; ++c) dqv[rr][c] = acc[c] * scale;
+            }
+          }
+          __syncwarp();
+          // pass B (lane = key row j): dK_j = scale * sum_i dS_ij Q_i,  dV_j = sum_i P_ij dctx_i
+          float kjs[RPL][D], vjs[RPL][D];
+#pragma unroll
+          for (int rr = 0; rr < RPL; ++rr) {
+            const int j = lane + 32 * rr;
+            if (j < S) {
+              ld_head<CH, D>(R1, rb + j, c0, kjs[rr], scale);
+              ld_head<CH, D>(R2, rb + j, c0, vjs[rr], 1.f);
+            }
+          }
+          __syncwarp();              // every lane holds its k / v rows: the k block is dead, dq moves in
+#pragma unroll
+          for (int rr = 0; rr < RPL; ++rr) {
+            const int i = lane + 32 * rr;
+            if (i < S) st_head<CH, D>(R1, rb + i, c0, dqv[rr], 1.f);
+          }
+          float dkv[RPL][D];
+#pragma unroll
+          for (int rr = 0; rr < RPL; ++rr) {
+            const int j = lane + 32 * rr;
+            if (j < S) {
+              float ak[D], av[D];
+#pragma unroll
+              for (int c = 0; c < D; ++c) ak[c] = av[c] = 0.f;
+              for (int i = 0; i < S; ++i) {
+                float qi[D], gi[D];
+                ld_head<CH, D>(R0, rb + i, c0, qi, 1.f);
+                ld_head<CH, D>(R3, rb + i, c0, gi, 1.f);
+                float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; c += 2) {
+                  s0 = fmaf(kjs[rr][c], qi[c], s0); s1 = fmaf(kjs[rr][c + 1], qi[c + 1], s1);
+                  p0 = fmaf(vjs[rr][c], gi[c], p0); p1 = fmaf(vjs[rr][c + 1], gi[c + 1], p1);
+                }
+                const float p = __expf((s0 + s1) - Ls[i]);
+                const float ds = p * ((p0 + p1) - Dl[i]);
+#pragma unroll
+                for (int c = 0; c < D; ++c) { ak[c] = fmaf(ds, qi[c], ak[c]); av[c] = fmaf(p, gi[c], av[c]); }
+              }
+              st_head<CH, D>(R2, rb + j, c0, av, 1.f);      // the v block is dead since the loads above
+#pragma unroll
+              for (int c = 0; c < D; ++c) dkv[rr][c] = ak[c] * scale;
+            }
+          }
+          __syncwarp();              // every lane is done with the q block: dk moves in
+#pragma unroll
+          for (int rr = 0; rr < RPL; ++rr) {
+            const int j = lane + 32 * rr;
+            if (j < S) st_head<CH, D>(R0, rb + j, c0, dkv[rr], 1.f);
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      // ---- dq / dk / dv to HBM and into K-major slabs (each slab replaces a tile that has just been consumed)
+      copy_out<CH>(R1, a.dq, row0, nrows, E, 0, tid);
+      tile_to_slab<CH>(R1, R3, tid);          // dq slab <- dctx tile's place
+      __syncthreads();
+      copy_out<CH>(R0, a.dk, row0, nrows, E, 0, tid);
+      tile_to_slab<CH>(R0, R1, tid);          // dk slab <- dq tile's place
+      __syncthreads();
+      copy_out<CH>(R2, a.dv, row0, nrows, E, 0, tid);
+      tile_to_slab<CH>(R2, R0, tid);          // dv slab <- dk tile's place
+      umma::fence_proxy_async();
+      umma::fence_before_sync();
+      __syncthreads();
     }
-    __syncthreads();
-    // ---- dq / dk / dv to HBM and into K-major slabs (each slab replaces a tile that has just been consumed)
-    copy_out<CH>(R1, a.dq, row0, nrows, E, 0, tid);
-    tile_to_slab<CH>(R1, R3, tid);          // dq slab <- dctx tile's place
-    __syncthreads();
-    copy_out<CH>(R0, a.dk, row0, nrows, E, 0, tid);
-    tile_to_slab<CH>(R0, R1, tid);          // dk slab <- dq tile's place
-    __syncthreads();
-    copy_out<CH>(R2, a.dv, row0, nrows, E, 0, tid);
-    tile_to_slab<CH>(R2, R0, tid);          // dv slab <- dk tile's place
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
     // ---- dx = dz1 + dq W_q + dk W_k + dv W_v
     if (warp == 4) {
       umma::fence_after_sync();
