@@ -258,13 +258,8 @@ linear_tc_kernel(const __grid_constant__ LinBatch batch, int M, int K, int N, in
 
 // ------------------------------------------------------------------ weight gradient -------------
 // warps 0-3 producers + final flush, warp 4 MMA issuer, warps 5-7 producers.
-__global__ void __launch_bounds__(256, 1)
-linear_wgrad_tc_kernel(const __grid_constant__ LinBatch batch /* A = dY, W = X, Y = dW, bias = db */, int M, int N, int K,
-                       int n_stages, int stages_per_cta, int buf_bytes) {
-  const float* __restrict__ dY = pick3(batch.A, (int)blockIdx.y);
-  const float* __restrict__ X = pick3(batch.W, (int)blockIdx.y);
-  float* __restrict__ dW = pick3(batch.Y, (int)blockIdx.y);
-  float* __restrict__ db = const_cast<float*>(pick3(batch.bias, (int)blockIdx.y));
+__device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ dW,
+                                           float* __restrict__ db, int M, int N, int K, int s_begin, int s_end, int buf_bytes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int nch = N / 4, kch = K / 4;
@@ -274,8 +269,6 @@ linear_wgrad_tc_kernel(const __grid_constant__ LinBatch batch /* A = dY, W = X, 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * buf_bytes);
   uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  const int s_begin = blockIdx.x * stages_per_cta;
-  const int s_end = min(n_stages, s_begin + stages_per_cta);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -381,6 +374,38 @@ linear_wgrad_tc_kernel(const __grid_constant__ LinBatch batch /* A = dY, W = X, 
   if (warp == 0) tmem_dealloc_n(tmem, K + 32);
 }
 
+__global__ void __launch_bounds__(256, 1)
+linear_wgrad_tc_kernel(const __grid_constant__ LinBatch batch /* A = dY, W = X, Y = dW, bias = db */, int M, int N, int K,
+                       int n_stages, int stages_per_cta, int buf_bytes) {
+  const int s_begin = blockIdx.x * stages_per_cta;
+  wgrad_body(pick3(batch.A, (int)blockIdx.y), pick3(batch.W, (int)blockIdx.y), pick3(batch.Y, (int)blockIdx.y),
+             const_cast<float*>(pick3(batch.bias, (int)blockIdx.y)), M, N, K, s_begin, min(n_stages, s_begin + stages_per_cta), buf_bytes);
+}
+
+// Several weight gradients of DIFFERENT shapes over the same M rows in one launch (the six nn.Linear layers of an encoder layer):
+// the CTAs of the grid are dealt to the problems in proportion to their bytes per row, each CTA owns a contiguous row range of
+// ONE problem and flushes its accumulator once -- ~148 flushes per layer instead of one per 256 rows and problem, and one
+// launch instead of three.
+constexpr int kMaxMulti = 6;
+struct WgradMulti {
+  const float* dY[kMaxMulti];
+  const float* X[kMaxMulti];
+  float* dW[kMaxMulti];
+  float* db[kMaxMulti];
+  int N[kMaxMulti], K[kMaxMulti], spc[kMaxMulti];
+  int cta0[kMaxMulti + 1];
+  int nb;
+};
+__global__ void __launch_bounds__(256, 1) linear_wgrad_multi_kernel(const __grid_constant__ WgradMulti mp, int M, int n_stages, int buf_bytes) {
+  int pidx = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxMulti; ++i)
+    if (i < mp.nb && (int)blockIdx.x >= mp.cta0[i]) pidx = i;
+  const int local = (int)blockIdx.x - mp.cta0[pidx];
+  const int s_begin = local * mp.spc[pidx];
+  wgrad_body(mp.dY[pidx], mp.X[pidx], mp.dW[pidx], mp.db[pidx], M, mp.N[pidx], mp.K[pidx], s_begin, min(n_stages, s_begin + mp.spc[pidx]), buf_bytes);
+}
+
 int sm_count() {
   static int sms = 0;
   if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -454,4 +479,55 @@ int linear_wgrad_tc_batched(int nb, const float* const* dY, const float* const* 
 }
 int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
   return linear_wgrad_tc_batched(1, &dY, &X, &dW, &db, M, N, K, st);
+}
+
+// nb <= 6 weight gradients dW_i[N_i][K_i] += dY_i[M,N_i]^T X_i[M,K_i] (+ bias gradients) over the same M rows in ONE launch
+bool linear_wgrad_tc_multi_supported(int nb, int M, const int* N, const int* K) {
+  if (nb < 1 || nb > kMaxMulti) return false;
+  size_t buf = 0;
+  for (int i = 0; i < nb; ++i) {
+    if (!linear_wgrad_tc_supported(M, N[i], K[i])) return false;
+    size_t b = (size_t)(N[i] / 4 + K[i] / 4 + 8) * kRows * 16;
+    if (b < (size_t)32 * kRows * 16) b = (size_t)32 * kRows * 16;
+    if (b > buf) buf = b;
+  }
+  return 2 * buf + 256 <= 227 * 1024;
+}
+int linear_wgrad_tc_multi(int nb, const float* const* dY, const float* const* X, float* const* dW, float* const* db, int M, const int* N,
+                          const int* K, cudaStream_t st) {
+  MIVIT_CHECK_ARG(linear_wgrad_tc_multi_supported(nb, M, N, K), "batched weight gradient: unsupported shapes");
+  WgradMulti mp = {};
+  mp.nb = nb;
+  int buf_bytes = 32 * kRows * 16;
+  double bytes_total = 0, flops = 0;
+  for (int i = 0; i < nb; ++i) {
+    mp.dY[i] = dY[i]; mp.X[i] = X[i]; mp.dW[i] = dW[i]; mp.db[i] = db ? db[i] : nullptr; mp.N[i] = N[i]; mp.K[i] = K[i];
+    const int b = (N[i] / 4 + K[i] / 4 + 8) * kRows * 16;
+    if (b > buf_bytes) buf_bytes = b;
+    bytes_total += N[i] + K[i];
+    flops += 2.0 * M * N[i] * K[i];
+  }
+  const int n_stages = (M + kRows - 1) / kRows;
+  const int sms = sm_count();
+  int used = 0;
+  for (int i = 0; i < nb; ++i) {
+    // CTAs in proportion to the bytes a row of the problem moves, at least one, at most one per stage
+    int c = (int)((double)sms * (N[i] + K[i]) / bytes_total);
+    if (c < 1) c = 1;
+    if (c > n_stages) c = n_stages;
+    const int spc = (n_stages + c - 1) / c;
+    c = (n_stages + spc - 1) / spc;
+    mp.spc[i] = spc;
+    mp.cta0[i] = used;
+    used += c;
+  }
+  mp.cta0[nb] = used;
+  for (int i = nb + 1; i <= kMaxMulti; ++i) mp.cta0[i] = used;
+  const int smem = 2 * buf_bytes + 256;
+  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  MivitProfScope prof("linear_tc_wgrad", flops, st);
+  linear_wgrad_multi_kernel<<<used, 256, smem, st>>>(mp, M, n_stages, buf_bytes);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
 }

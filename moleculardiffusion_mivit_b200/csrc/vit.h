@@ -163,4 +163,8 @@ int linear_tc_batched(int nb, const float* const* A, const float* const* W, cons
 int linear_wgrad_tc_batched(int nb, const float* const* dY, const float* const* X, float* const* dW, float* const* db, int M, int N,
                             int K, cudaStream_t st);
 bool linear_wgrad_tc_supported(int M, int N, int K);
+// nb <= 6 weight gradients of different shapes over the same M rows in one launch (CTAs dealt to the problems by bytes per row)
+bool linear_wgrad_tc_multi_supported(int nb, int M, const int* N, const int* K);
+int linear_wgrad_tc_multi(int nb, const float* const* dY, const float* const* X, float* const* dW, float* const* db, int M, const int* N,
+                          const int* K, cudaStream_t st);
 int linear_wgrad_tc(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st);

@@ -653,13 +653,19 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
       io.dz2 = tmp; io.dh2 = w.dh2; io.dz1 = w.dctx; io.dq = w.dq; io.dk = w.dk; io.dv = w.dv;
       io.dg2 = g + Y.n2_g; io.db2 = g + Y.n2_b; io.dg1 = g + Y.n1_g; io.db1 = g + Y.n1_b;
       CK(encoder_layer_bwd(io, B, S, E, HD, H, st));
-      const float* dYs[4] = {w.dq, w.dk, w.dv, w.dctx};
-      const float* Xs[4] = {xin, xin, xin, y.ctx};
-      float* dWs[4] = {g + Y.q_w, g + Y.k_w, g + Y.v_w, g + Y.o_w};
-      float* dbs[4] = {g + Y.q_b, g + Y.k_b, g + Y.v_b, g + Y.o_b};
-      CK(linear_wgrad_tc_batched(4, dYs, Xs, dWs, dbs, T, E, E, st));
-      CK(linear_wgrad_tc(tmp, y.hact, g + Y.f2_w, g + Y.f2_b, T, E, HD, st));
-      CK(linear_wgrad_tc(w.dh2, y.x1, g + Y.f1_w, g + Y.f1_b, T, HD, E, st));
+      // the six weight (and bias) gradients of the layer: one launch
+      const float* dYs[6] = {w.dq, w.dk, w.dv, w.dctx, tmp, w.dh2};
+      const float* Xs[6] = {xin, xin, xin, y.ctx, y.hact, y.x1};
+      float* dWs[6] = {g + Y.q_w, g + Y.k_w, g + Y.v_w, g + Y.o_w, g + Y.f2_w, g + Y.f1_w};
+      float* dbs[6] = {g + Y.q_b, g + Y.k_b, g + Y.v_b, g + Y.o_b, g + Y.f2_b, g + Y.f1_b};
+      const int Ns[6] = {E, E, E, E, E, HD}, Ks[6] = {E, E, E, E, HD, E};
+      if (linear_wgrad_tc_multi_supported(6, T, Ns, Ks) && !getenv("MIVIT_NO_WGRAD_MULTI")) {
+        CK(linear_wgrad_tc_multi(6, dYs, Xs, dWs, dbs, T, Ns, Ks, st));
+      } else {
+        CK(linear_wgrad_tc_batched(4, dYs, Xs, dWs, dbs, T, E, E, st));
+        CK(linear_wgrad_tc(tmp, y.hact, g + Y.f2_w, g + Y.f2_b, T, E, HD, st));
+        CK(linear_wgrad_tc(w.dh2, y.x1, g + Y.f1_w, g + Y.f1_b, T, HD, E, st));
+      }
       continue;
     }
     // x2 = LN2(x1 + ff)
