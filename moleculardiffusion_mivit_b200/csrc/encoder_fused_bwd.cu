@@ -204,7 +204,9 @@ __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
       const int r0 = mt * 16 + gid, r1 = r0 + 8;                    // this lane's two rows (of the orientation)
-      uint32_t ah[2][4], al[2][4], a2[2][4];
+      // both first-stage products in 3xTF32: dS = P (dP - D) cancels (dP_ij ~ D_i for diffuse attention), so a plain tf32 dP
+      // (1e-3 relative) showed up as 9 % on the last layer's q_proj gradient against the fp32 oracle
+      uint32_t ah[2][4], al[2][4], a2h[2][4], a2l[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         const int ca = hc + ks * 8 + tig, cb = ca + 4;
@@ -212,10 +214,10 @@ __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8
         tf32_split(tile_el<CH>(A1, rb + r1, ca) * sl2, ah[ks][1], al[ks][1]);
         tf32_split(tile_el<CH>(A1, rb + r0, cb) * sl2, ah[ks][2], al[ks][2]);
         tf32_split(tile_el<CH>(A1, rb + r1, cb) * sl2, ah[ks][3], al[ks][3]);
-        a2[ks][0] = tf32_rna(tile_el<CH>(A2, rb + r0, ca));
-        a2[ks][1] = tf32_rna(tile_el<CH>(A2, rb + r1, ca));
-        a2[ks][2] = tf32_rna(tile_el<CH>(A2, rb + r0, cb));
-        a2[ks][3] = tf32_rna(tile_el<CH>(A2, rb + r1, cb));
+        tf32_split(tile_el<CH>(A2, rb + r0, ca), a2h[ks][0], a2l[ks][0]);
+        tf32_split(tile_el<CH>(A2, rb + r1, ca), a2h[ks][1], a2l[ks][1]);
+        tf32_split(tile_el<CH>(A2, rb + r0, cb), a2h[ks][2], a2l[ks][2]);
+        tf32_split(tile_el<CH>(A2, rb + r1, cb), a2h[ks][3], a2l[ks][3]);
       }
       // orientation 0: L, D belong to the rows; orientation 1: to the columns
       const float Lr0 = Ls[r0], Lr1 = Ls[r1], Dr0 = Dl[r0], Dr1 = Dl[r1];
@@ -223,14 +225,14 @@ __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int cr = rb + nt * 8 + gid;                            // row of the B-operand tiles
-        uint32_t bh[2][2], bl[2][2], b2[2][2];
+        uint32_t bh[2][2], bl[2][2], b2h[2][2], b2l[2][2];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const int ca = hc + ks * 8 + tig;
           tf32_split(tile_el<CH>(B1, cr, ca), bh[ks][0], bl[ks][0]);
           tf32_split(tile_el<CH>(B1, cr, ca + 4), bh[ks][1], bl[ks][1]);
-          b2[ks][0] = tf32_rna(tile_el<CH>(B2, cr, ca));
-          b2[ks][1] = tf32_rna(tile_el<CH>(B2, cr, ca + 4));
+          tf32_split(tile_el<CH>(B2, cr, ca), b2h[ks][0], b2l[ks][0]);
+          tf32_split(tile_el<CH>(B2, cr, ca + 4), b2h[ks][1], b2l[ks][1]);
         }
         float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -238,7 +240,9 @@ __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8
           mma_16x8x8(sc, al[ks], bh[ks]);
           mma_16x8x8(sc, ah[ks], bl[ks]);
           mma_16x8x8(sc, ah[ks], bh[ks]);
-          mma_16x8x8(dp, a2[ks], b2[ks]);
+          mma_16x8x8(dp, a2l[ks], b2h[ks]);
+          mma_16x8x8(dp, a2h[ks], b2l[ks]);
+          mma_16x8x8(dp, a2h[ks], b2h[ks]);
         }
         const int c0 = nt * 8 + 2 * tig, c1 = c0 + 1;               // this lane's two columns
         float L00, L01, L10, L11, D00, D01, D10, D11;               // (row r0 | r1, column c0 | c1)
@@ -725,10 +729,13 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     if (act) {
       float v[16];
       umma::tmem_ld16(trow + (uint32_t)(C4 + sl * 16), v);
+      // the residual dz1: this CTA wrote the rows above (L2); re-reading them frees 16 registers across the attention phase
+      const float4* zp = reinterpret_cast<const float4*>(a.dz1 + (row0 + r) * E + sl * 16);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        rm_st<CH>(R2, r, sl * 4 + c, make_float4(v[4 * c] + dz1v[4 * c], v[4 * c + 1] + dz1v[4 * c + 1], v[4 * c + 2] + dz1v[4 * c + 2],
-                                                 v[4 * c + 3] + dz1v[4 * c + 3]));
+      for (int c = 0; c < 4; ++c) {
+        const float4 z4 = live ? __ldcg(zp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rm_st<CH>(R2, r, sl * 4 + c, make_float4(v[4 * c] + z4.x, v[4 * c + 1] + z4.y, v[4 * c + 2] + z4.z, v[4 * c + 3] + z4.w));
+      }
     }
     umma::fence_before_sync();
     __syncthreads();
