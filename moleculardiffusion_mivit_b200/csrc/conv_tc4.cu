@@ -493,7 +493,11 @@ int conv_rows_forward_v4(const __nv_bfloat16* X, const __nv_bfloat16* Wp, const 
   else if (cout == 64 && taps == 9 && cin == 128 && !skip && getenv("MIVIT_PAIRS_C64") != nullptr)
     rc = launch4<128, false, 9, 64>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
   // (64 -> 128 + skip is epilogue-bound -- 256 staged columns per tile -- and measured 1.14 ms on pairs vs 0.99 ms on
-  //  conv_tc3's independent half-column CTAs, so it stays there; launch4<64, true, 9> is kept compilable for experiments.)
+  //  conv_tc3's independent half-column CTAs, so it stays there; launch4<64, true, 9> is kept compilable for experiments.
+  //  Round 2: a SECOND epilogue group on pairs (warps 8-11, alternate tiles, own staging tiles / barrier / bulk groups) changed
+  //  nothing -- 1.066 vs 1.023 ms with one group, 0.733 vs 0.734 ms without the statistics loop -- and ncu then shows both groups
+  //  waiting for the accumulator 25 % of the time: the tile is bounded by shared-memory traffic (operand reads 243 KB + staging
+  //  writes / TMA-store reads / statistics reads 192 KB per 128-row tile and SM), not by epilogue issue slots.)
   else if (cout == 128 && taps == 9 && cin == 64 && skip && getenv("MIVIT_PAIRS_SKIP") != nullptr)
     rc = launch4<64, true, 9, 128>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
   else if (cout == 128 && taps == 9 && cin == 64 && !skip) rc = launch4<64, false, 9, 128>(X, Wp, Wsk, Y, Ysk, stats, stats_sk, rows, P, sh, st, &fits);
