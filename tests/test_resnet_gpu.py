@@ -48,7 +48,13 @@ def test_forward_loss_grads_match_oracle(golden_dir, name):
         if float(r.norm()) < 1e-6 * gmax:
             assert float(p.grad.cpu().norm()) < 1e-4 * gmax, k
             continue
-        assert relnorm(p.grad.cpu(), r) < 2e-4, (k, relnorm(p.grad.cpu(), r))
+        # fp32 on both sides: summation-order noise (measured <= 1.1e-5).  The BatchNorm statistics are accumulated with atomics, so
+        # the forward differs from run to run in the last bit, and in resnet_ft_p9 ONE pre-activation of layer2's 3x3 output sits
+        # within that bit of zero: in ~25 % of the runs its ReLU mask differs from the CPU oracle's and the BatchNorm affine
+        # gradients of that layer (sums over few pixels) move by 1.0e-3 (scripts/diag_resnet_flaky.py; poisoning the workspace
+        # with NaN changes nothing, i.e. no uninitialised read).  Weight gradients move by < 2e-5 in those runs.
+        tol = 3e-3 if (".bn" in k or "shortcut.1" in k) else 2e-4
+        assert relnorm(p.grad.cpu(), r) < tol, (k, relnorm(p.grad.cpu(), r))
     msd = model.state_dict()
     for k, v in ref_stats.items():
         assert torch.allclose(msd[k].cpu().float(), v.float(), rtol=1e-4, atol=1e-6), k
