@@ -6,17 +6,19 @@
 // each for ~2.5 us of HBM traffic: a fixed latency chain per launch (barrier / TMEM set-up, weight fetch, tile fetch, MMA, TMEM
 // read, transposed store).  Here a CTA owns a tile of 128 token rows = floor(128 / S) whole sequences and walks the layer with
 // the tile resident on chip:
-//   x tile  --cp.async-->  shared memory (K-major core-matrix order, the tcgen05 A operand)
+//   x tile  --TMA-->  shared memory ([row][128 B] SWIZZLE_128B boxes of 32 floats, the tcgen05 K-major A operand)
 //   [q|k|v] = x W_qkv^T    ONE tcgen05.mma chain (kind::tf32, M = 128, N = 3E) -> TMEM -> +bias -> shared memory (row-major)
 //   attention              per (sequence, head) on one warp, flash style in registers (S <= 64, d = 16) -> ctx written straight
 //                          into the A-operand layout, row log-sum-exps to HBM
 //   ao = ctx W_o^T         tcgen05 -> TMEM -> epilogue with thread = token row: + bias + residual, LayerNorm in registers
 //   h  = relu(x1 W_1^T)    tcgen05 -> TMEM -> +bias, ReLU -> shared memory (A layout)
 //   x2 = LN2(x1 + h W_2^T) tcgen05 -> TMEM -> epilogue: + bias + residual, LayerNorm -> HBM
-// Weights are fetched by cp.async into two alternating buffers one phase ahead.  Everything the (unfused) backward reads is
+// Weights arrive by TMA (one box per 32-float slice of the reduction dimension, SWIZZLE_128B) in two alternating buffers, one
+// phase ahead; activations produced on chip (ctx, x1, relu(h)) are written by the threads in the no-swizzle core-matrix order.  Everything the (unfused) backward reads is
 // written once, coalesced through a shared-memory staging tile: q, k, v, ctx, z1, x1, relu(h), z2, x2 and the LayerNorm / softmax
 // row statistics.  Same arithmetic as the unfused path (tf32 products, fp32 accumulation / softmax / LayerNorm).
 #include "common.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 #include "vit.h"
 
@@ -24,10 +26,6 @@ namespace {
 
 constexpr int kRows = 128;
 
-__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -51,28 +49,28 @@ struct EncArgs {
 
 constexpr int kThreads = 512;   // 16 warps: warp w reads TMEM lane quarter w & 3 and owns column slice w >> 2 of every epilogue
 
-// nn.Linear weight W[N][K] (row-major) -> K-major B operand [K/4][N][16 B]; all threads, cp.async
-template <int N, int K>
-__device__ __forceinline__ void load_w_kmajor(uint8_t* dst, const float* __restrict__ W, int n_off, int n_total, int tid) {
-  constexpr int kch = K / 4;
-  const uint4* src = reinterpret_cast<const uint4*>(W);
-  for (int i = tid; i < N * kch; i += kThreads) {
-    const int n = i / kch, c = i % kch;
-    cp16(dst + ((size_t)c * n_total + n_off + n) * 16, src + i);
-  }
-}
+struct EncMaps {   // fp32 SWIZZLE_128B tensor maps (tma.cuh: make_f32_tensor_map_sw), boxes of 32 floats x rows
+  CUtensorMap x;                       // [T, E], 128-row boxes
+  CUtensorMap wq, wk, wv, wo;          // [E, E], E-row boxes
+  CUtensorMap w1;                      // [HD, E], HD-row boxes
+  CUtensorMap w2;                      // [E, HD], E-row boxes
+};
 
-// D[128 x N] (TMEM columns [0, N)) = A[128 x K] (K-major slab `a`) * B (K-major [K/4][N][16 B])
+// D[128 x N] (TMEM columns [0, N)) = A[128 x K] * B^T.  B = TMA-loaded weights: K / 32 boxes of [N rows][128 B] SWIZZLE_128B
+// (8 reduction elements = 32 B per MMA inside the 128-byte atom).  A = the same layout (A_SW: the TMA-loaded x tile, boxes of
+// [128 rows][128 B]) or the no-swizzle core-matrix slab [K/4][128][16 B] the epilogues write.
+template <bool A_SW>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem, const uint8_t* a, const uint8_t* b, int N, int K, uint64_t* bar) {
   const uint32_t idesc = idesc_tf32(kRows, N);
-  const uint64_t da = umma::make_desc(umma::smem_u32(a), (uint32_t)kRows * 16u, 128u);
-  const uint64_t db = umma::make_desc(umma::smem_u32(b), (uint32_t)N * 16u, 128u);
-  uint32_t a_lo = (uint32_t)da, b_lo = (uint32_t)db;
+  const uint64_t da = A_SW ? tma::make_desc_sw(umma::smem_u32(a), 0u, 128u) : umma::make_desc(umma::smem_u32(a), (uint32_t)kRows * 16u, 128u);
+  const uint64_t db = tma::make_desc_sw(umma::smem_u32(b), 0u, 128u);
+  const uint32_t a_lo0 = (uint32_t)da, b_lo0 = (uint32_t)db;
   const uint32_t a_hi = (uint32_t)(da >> 32), b_hi = (uint32_t)(db >> 32);
-  for (int j = 0; j < K / 8; ++j) {
-    mma_tf32(tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, j > 0 ? 1u : 0u);
-    a_lo += 2u * kRows;          // two 4-float chunks per K = 8 step
-    b_lo += 2u * (uint32_t)N;
+  for (int ks = 0; ks < K / 8; ++ks) {
+    const uint32_t kb = (uint32_t)(ks >> 2), j = (uint32_t)(ks & 3);
+    const uint32_t a_lo = A_SW ? a_lo0 + kb * (uint32_t)(kRows * 8) + 2u * j : a_lo0 + (uint32_t)ks * 2u * kRows;   // 16-byte units
+    const uint32_t b_lo = b_lo0 + kb * (uint32_t)(N * 8) + 2u * j;
+    mma_tf32(tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, ks > 0 ? 1u : 0u);
   }
   umma::commit(bar);
 }
@@ -139,7 +137,7 @@ __device__ __forceinline__ void layernorm_sliced(float (&v)[16], bool active, in
 }
 
 template <int E, int HD, int NH, int SMAX>
-__global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __grid_constant__ EncArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __grid_constant__ EncArgs a, const __grid_constant__ EncMaps tm) {
   constexpr int D = E / NH;                 // head dim (16 in every reference configuration)
   constexpr int LD = E + 4;                 // row stride of the row-major tiles (floats): 16-byte aligned rows, spread banks
   constexpr int XS_BYTES = E * 512;         // [E/4][128][16 B]
@@ -159,8 +157,9 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
   float* Vs = Ks + kRows * LD;
   uint8_t* Hs = reinterpret_cast<uint8_t*>(Ks);         // A operand: relu(h) (aliases k, v)
   float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(Qs) + 3 * ROW_BYTES);   // [128][4] LayerNorm partial sums
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + kRows * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + kRows * 4);     // MMA completion
+  uint64_t* lbar = bar + 1;                                          // [3] TMA completion: x + W_qkv + W_o | W_1 | W_2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 3);
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int qd = warp & 3, sl = warp >> 2;              // TMEM lane quarter, column slice
   const int r = qd * 32 + lane;                         // token row of this thread in every epilogue
@@ -168,7 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
 
   if (tid == 0) {
     umma::mbar_init(bar, 1);
+    for (int i = 0; i < 3; ++i) umma::mbar_init(lbar + i, 1);
     umma::mbar_fence_init();
+    tma::prefetch_map(&tm.x); tma::prefetch_map(&tm.wq); tma::prefetch_map(&tm.wk); tma::prefetch_map(&tm.wv);
+    tma::prefetch_map(&tm.wo); tma::prefetch_map(&tm.w1); tma::prefetch_map(&tm.w2);
   }
   if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
   umma::fence_before_sync();
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
-  uint32_t parity = 0;
+  uint32_t parity = 0, lpar = 0;   // lpar: phase of the three load barriers (each completes once per tile)
   const float scale = rsqrtf((float)D);
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -185,35 +187,34 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
     const long long row0 = (long long)seq0 * S;
     const int nrows = nseq * S;
     const bool live = r < nrows;
-    // ---- x tile + W_qkv (-> Wa) + W_o (-> Wb)
-    {
-      constexpr int kch = E / 4;
-      const uint4* src = reinterpret_cast<const uint4*>(a.x + row0 * E);
-      for (int i = tid; i < kRows * kch; i += kThreads) {
-        const int rr = i / kch, c = i % kch;
-        uint8_t* d = Xs + ((size_t)c * kRows + rr) * 16;
-        if (rr < nrows) cp16(d, src + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+    // ---- x tile + W_qkv (-> Wa) + W_o (-> Wb): 10 TMA boxes, one elected thread.  (Rows of the tile past nrows hold the next
+    //      tile's tokens, or zeros past the end of the tensor: every epilogue masks them with `live`.)
+    if (tid == 0) {
+      tma::expect_tx(lbar, (uint32_t)(XS_BYTES + 4 * E * E * 4));
+#pragma unroll
+      for (int kb = 0; kb < E / 32; ++kb) {
+        tma::load_tile(Xs + (size_t)kb * kRows * 128, &tm.x, kb * 32, (int)row0, lbar);
+        tma::load_tile(Wa + ((size_t)kb * 3 * E) * 128, &tm.wq, kb * 32, 0, lbar);
+        tma::load_tile(Wa + ((size_t)kb * 3 * E + E) * 128, &tm.wk, kb * 32, 0, lbar);
+        tma::load_tile(Wa + ((size_t)kb * 3 * E + 2 * E) * 128, &tm.wv, kb * 32, 0, lbar);
+        tma::load_tile(Wb + (size_t)kb * E * 128, &tm.wo, kb * 32, 0, lbar);
       }
-      load_w_kmajor<E, E>(Wa, a.wq, 0, 3 * E, tid);
-      load_w_kmajor<E, E>(Wa, a.wk, E, 3 * E, tid);
-      load_w_kmajor<E, E>(Wa, a.wv, 2 * E, 3 * E, tid);
-      load_w_kmajor<E, E>(Wb, a.wo, 0, E, tid);
-      cp_wait_all();
-      umma::fence_proxy_async();
     }
-    umma::fence_before_sync();
-    __syncthreads();
     // ---- [q | k | v] = x W_qkv^T
     if (warp == 4) {
+      umma::mbar_wait(lbar, lpar);
       umma::fence_after_sync();
-      if (umma::elect_one()) issue_gemm(tmem, Xs, Wa, 3 * E, E, bar);
+      if (umma::elect_one()) issue_gemm<true>(tmem, Xs, Wa, 3 * E, E, bar);
       __syncwarp();
     }
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     // W_1 -> Wa (free now), in flight during the q/k/v epilogue and the attention
-    load_w_kmajor<HD, E>(Wa, a.w1, 0, HD, tid);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0) {
+      tma::expect_tx(lbar + 1, (uint32_t)(HD * E * 4));
+#pragma unroll
+      for (int kb = 0; kb < E / 32; ++kb) tma::load_tile(Wa + (size_t)kb * HD * 128, &tm.w1, kb * 32, 0, lbar + 1);
+    }
 #pragma unroll 1
     for (int g = sl; g < 3 * E / 16; g += 4) {            // 16-column groups of [q | k | v], dealt over the four column slices
       float v[16];
@@ -279,14 +280,13 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
         a.lse[((size_t)(seq0 + sq) * NH + h) * S + i] = mx + logf(sum);
       }
     }
-    cp_wait_all();                 // W_1 has landed
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     // ---- ao = ctx W_o^T ; ctx to HBM meanwhile (staged row-major through Qs)
     if (warp == 4) {
       umma::fence_after_sync();
-      if (umma::elect_one()) issue_gemm(tmem, Xs, Wb, E, E, bar);
+      if (umma::elect_one()) issue_gemm<false>(tmem, Xs, Wb, E, E, bar);
       __syncwarp();
     }
     for (int i = tid; i < kRows * (E / 4); i += kThreads) {   // Xs (core layout) -> Qs rows; lanes walk rows: conflict-free reads
@@ -298,8 +298,11 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     __syncthreads();               // ctx staging consumed, W_o consumed: Wb and Qs / Ks are free
-    load_w_kmajor<E, HD>(Wb, a.w2, 0, E, tid);              // W_2 -> Wb, in flight during LayerNorm 1 and fc1
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0) {                // W_2 -> Wb, in flight during LayerNorm 1 and fc1
+      tma::expect_tx(lbar + 2, (uint32_t)(HD * E * 4));
+#pragma unroll
+      for (int kb = 0; kb < HD / 32; ++kb) tma::load_tile(Wb + (size_t)kb * E * 128, &tm.w2, kb * 32, 0, lbar + 2);
+    }
     float x1v[16];                 // this thread's 16 columns of the x1 row stay in registers for the second residual
     const bool act = sl < NS;
     {
@@ -341,8 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
     __syncthreads();
     // ---- h = relu(x1 W_1^T + b) ; z1, x1 to HBM meanwhile
     if (warp == 4) {
+      umma::mbar_wait(lbar + 1, lpar);   // W_1 has landed
       umma::fence_after_sync();
-      if (umma::elect_one()) issue_gemm(tmem, Xs, Wa, HD, E, bar);
+      if (umma::elect_one()) issue_gemm<false>(tmem, Xs, Wa, HD, E, bar);
       __syncwarp();
     }
     copy_out<E>(Qs, LD, a.z1, row0, nrows, E, 0, tid);
@@ -371,13 +375,13 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
       __syncthreads();
     }
     umma::fence_before_sync();
-    cp_wait_all();                 // W_2 has landed
     umma::fence_proxy_async();
     __syncthreads();
     // ---- x2 = LN2(x1 + h W_2^T + b)
     if (warp == 4) {
+      umma::mbar_wait(lbar + 2, lpar);   // W_2 has landed
       umma::fence_after_sync();
-      if (umma::elect_one()) issue_gemm(tmem, Hs, Wb, E, HD, bar);
+      if (umma::elect_one()) issue_gemm<false>(tmem, Hs, Wb, E, HD, bar);
       __syncwarp();
     }
     umma::mbar_wait(bar, parity); parity ^= 1;
@@ -411,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
     copy_out<E>(Ks, LD, a.x2, row0, nrows, E, 0, tid);
     umma::fence_before_sync();
     __syncthreads();               // the next tile overwrites every buffer
+    lpar ^= 1;
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -432,8 +437,19 @@ int launch_fwd(const EncArgs& a, cudaStream_t st) {
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   const double T = (double)a.B * a.S;
+  EncMaps tm;
+  {
+    int rc = make_f32_tensor_map_sw(&tm.x, a.x, E, (long long)a.B * a.S, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.wq, a.wq, E, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.wk, a.wk, E, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.wv, a.wv, E, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.wo, a.wo, E, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.w1, a.w1, E, HD, HD);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.w2, a.w2, HD, E, E);
+    if (rc) return rc;
+  }
   MivitProfScope prof("encoder_layer_fwd", 2.0 * T * (4.0 * E * E + 2.0 * E * HD) + 4.0 * a.B * NH * (double)a.S * a.S * (E / NH), st);
-  kern<<<grid, kThreads, smem, st>>>(a);
+  kern<<<grid, kThreads, smem, st>>>(a, tm);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

@@ -63,6 +63,26 @@ static inline int make_rows_tensor_map_sw(CUtensorMap* tm, const void* base, int
   return MIVIT_OK;
 }
 
+// fp32 row-major matrix [rows][cols] for the tf32 kernels: one box = {32 floats = 128 B, box_rows rows} lands as a [row][128 B]
+// SWIZZLE_128B tile, which tcgen05 kind::tf32 reads as a K-major operand (8 reduction elements = 32 B per MMA: the descriptor
+// start address advances by 32 B inside the 128-byte atom, then to the next box).  Rows past `rows` read as zeros.
+static inline int make_f32_tensor_map_sw(CUtensorMap* tm, const void* base, int cols, long long rows, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  mivit_tensor_map_encode_fn encode = mivit_tensor_map_encoder();
+  if (encode == nullptr) return MIVIT_ERR_CUDA;
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mivit_set_error("cuTensorMapEncodeTiled failed (%d) for fp32 cols=%d rows=%lld box=%d", (int)r, cols, rows, box_rows);
+    return MIVIT_ERR_CUDA;
+  }
+  return MIVIT_OK;
+}
+
 namespace tma {
 
 // UMMA shared-memory descriptor for a swizzled row tile (pitch 128 -> SWIZZLE_128B, pitch 64 -> SWIZZLE_64B)

@@ -508,7 +508,11 @@ static int vit_forward_impl(const mivit_vit_config* c, int32_t B, const float* x
   CK(tokens_finish(w.tok, c->use_reg ? p + L.reg : nullptr, (c->use_feat && c->fusion == 0 && c->use_reg) ? w.fp_out : nullptr,
                    c->use_pos ? p + L.pos : nullptr, B, S, E, st));
   const float* xin = w.tok;
-  const bool fused_layers = g_linear_tc && c->activation == 0 && encoder_fused_supported(B, S, E, HD, H) && !getenv("MIVIT_NO_FUSED_ENCODER");
+  bool fused_layers = g_linear_tc && c->activation == 0 && encoder_fused_supported(B, S, E, HD, H) && !getenv("MIVIT_NO_FUSED_ENCODER");
+  for (int l = 0; fused_layers && l < c->L; ++l) {   // TMA reads the weights in place: 16-byte aligned matrices
+    const auto& Y = L.lyr[l];
+    fused_layers = al16(p + Y.q_w) && al16(p + Y.k_w) && al16(p + Y.v_w) && al16(p + Y.o_w) && al16(p + Y.f1_w) && al16(p + Y.f2_w);
+  }
   for (int l = 0; l < c->L; ++l) {
     const auto& Y = L.lyr[l];
     LayerWS& y = w.lyr[l];
