@@ -15,7 +15,10 @@
 //
 // The input-gradient GEMMs multiply by W (not W^T); instead of an MN-major B operand the (tiny) weights are transposed once
 // per step by pack_kernel, so every GEMM here is the same K-major x K-major form as the forward kernel (encoder_fused.cu).
+// Weights (and, for S <= 32, the dq / dk / dv slabs) are staged by TMA: fp32 boxes of 32 reduction elements x rows that land as
+// [row][128 B] SWIZZLE_128B tiles, completion on mbarriers; A operands produced on chip stay in the no-swizzle core-matrix order.
 #include "common.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 #include "vit.h"
 
@@ -53,28 +56,28 @@ struct BwdArgs {
   int B, S, spt, n_tiles;
 };
 
-// row-major source Wsrc[N][K] -> K-major B operand [K/4][N][16 B]; all threads, cp.async
-template <int N, int K>
-__device__ __forceinline__ void load_w_kmajor(uint8_t* dst, const float* __restrict__ W, int tid) {
-  constexpr int kch = K / 4;
-  const uint4* src = reinterpret_cast<const uint4*>(W);
-  for (int i = tid; i < N * kch; i += kThreads) {
-    const int n = i / kch, c = i % kch;
-    cp16(dst + ((size_t)c * N + n) * 16, src + i);
-  }
-}
+struct BwdMaps {   // fp32 SWIZZLE_128B tensor maps (tma.cuh: make_f32_tensor_map_sw), boxes of 32 floats x rows
+  CUtensorMap w2t;           // [HD, E],  HD-row boxes
+  CUtensorMap wot;           // [E, E],   E-row boxes
+  CUtensorMap w1t;           // [E, HD],  E-row boxes
+  CUtensorMap wqkvt;         // [E, 3E],  E-row boxes
+  CUtensorMap dq, dk, dv;    // [T, E],   128-row boxes (read back as A slabs, S <= 32)
+};
 
-// D[128 x N] (TMEM columns from `tmem`) (+)= A[128 x K] (K-major slab) * B (K-major [..][N][16 B], chunk stride N * 16)
+// D[128 x N] (TMEM columns from `tmem`) (+)= A[128 x K] * B^T.  B = TMA-loaded weights: K / 32 boxes of [N rows][128 B]
+// SWIZZLE_128B; A = the same layout (A_SW: boxes of [128 rows][128 B]) or the no-swizzle core-matrix slab [K/4][128][16 B].
+template <bool A_SW>
 __device__ __forceinline__ void issue_chain(uint32_t tmem, const uint8_t* a, const uint8_t* b, int N, int K, bool first) {
   const uint32_t idesc = idesc_tf32(kRows, N);
-  const uint64_t da = umma::make_desc(umma::smem_u32(a), (uint32_t)kRows * 16u, 128u);
-  const uint64_t db = umma::make_desc(umma::smem_u32(b), (uint32_t)N * 16u, 128u);
-  uint32_t a_lo = (uint32_t)da, b_lo = (uint32_t)db;
+  const uint64_t da = A_SW ? tma::make_desc_sw(umma::smem_u32(a), 0u, 128u) : umma::make_desc(umma::smem_u32(a), (uint32_t)kRows * 16u, 128u);
+  const uint64_t db = tma::make_desc_sw(umma::smem_u32(b), 0u, 128u);
+  const uint32_t a_lo0 = (uint32_t)da, b_lo0 = (uint32_t)db;
   const uint32_t a_hi = (uint32_t)(da >> 32), b_hi = (uint32_t)(db >> 32);
-  for (int j = 0; j < K / 8; ++j) {
-    mma_tf32(tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, (first && j == 0) ? 0u : 1u);
-    a_lo += 2u * kRows;          // two 4-float chunks per K = 8 step
-    b_lo += 2u * (uint32_t)N;
+  for (int ks = 0; ks < K / 8; ++ks) {
+    const uint32_t kb = (uint32_t)(ks >> 2), j = (uint32_t)(ks & 3);
+    const uint32_t a_lo = A_SW ? a_lo0 + kb * (uint32_t)(kRows * 8) + 2u * j : a_lo0 + (uint32_t)ks * 2u * kRows;   // 16-byte units
+    const uint32_t b_lo = b_lo0 + kb * (uint32_t)(N * 8) + 2u * j;
+    mma_tf32(tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, (first && ks == 0) ? 0u : 1u);
   }
 }
 
@@ -166,17 +169,6 @@ __device__ __forceinline__ float tile_el(const uint8_t* tile, int row, int col) 
   row = min(row, kRows - 1);
   return *reinterpret_cast<const float*>(tile + rm_off<CH>(row, col >> 2) + ((col & 3) << 2));
 }
-// K-major A slab [CH][128][16 B] straight from global rows (cp.async; rows past nrows are zero)
-template <int CH>
-__device__ __forceinline__ void fill_slab(uint8_t* slab, const float* __restrict__ g, long long row0, int nrows, int tid) {
-  const uint4* src = reinterpret_cast<const uint4*>(g + row0 * (CH * 4));
-  for (int i = tid; i < kRows * CH; i += kThreads) {
-    const int r = i / CH, c = i % CH;
-    uint8_t* d = slab + ((size_t)c * kRows + r) * 16;
-    if (r < nrows) cp16(d, src + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-  }
-}
-
 // Attention backward of ONE (sequence, head) on one warp with tensor-core MMAs (S <= 32, head dim 16).  Q / K / V / dctx are
 // the swizzled tiles Qt / Kt / Vt / Gt (rows rb .. rb + S of the CTA's tile, columns hc .. hc + 16); Ls / Dl = this warp's row
 // log-sum-exps and D_i = dctx_i . ctx_i (entries >= S are 0).  Two orientations, each in two halves of 16 rows:
@@ -343,7 +335,7 @@ __device__ __forceinline__ void layernorm_bwd_sliced(const float (&dyv)[16], con
 }
 
 template <int E, int HD, int NH, int SMAX>
-__global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __grid_constant__ BwdArgs a, const __grid_constant__ BwdMaps tm) {
   constexpr int D = E / NH;                 // head dim (16)
   constexpr int CH = E / 4;                 // 16-byte chunks of an E-wide row
   constexpr int NS = E / 16;                // active column slices of an E-wide epilogue
@@ -363,8 +355,9 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
   float* red = reinterpret_cast<float*>(R3 + TILE);      // [2][128][4] LayerNorm partial sums
   float* lnacc = red + 2 * kRows * 4;                    // [LN1 | LN2][dgamma | dbeta][E]
   float* lsdl = lnacc + 4 * E;                           // [16 warps][L | D][SMAX]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(lsdl + 16 * 2 * SMAX);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lsdl + 16 * 2 * SMAX);   // MMA completion
+  uint64_t* lbar = bar + 1;              // [4] TMA completion: W_2^T + W_o^T | W_1^T (once) | W_qkv^T | dq, dk, dv slabs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 4);
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int qd = warp & 3, sl = warp >> 2;
   const int r = qd * 32 + lane;               // token row of this thread in every epilogue
@@ -373,7 +366,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
 
   if (tid == 0) {
     umma::mbar_init(bar, 1);
+    for (int i = 0; i < 4; ++i) umma::mbar_init(lbar + i, 1);
     umma::mbar_fence_init();
+    tma::prefetch_map(&tm.w2t); tma::prefetch_map(&tm.wot); tma::prefetch_map(&tm.w1t); tma::prefetch_map(&tm.wqkvt);
+    tma::prefetch_map(&tm.dq); tma::prefetch_map(&tm.dk); tma::prefetch_map(&tm.dv);
   }
   if (warp == 0) umma::tmem_alloc<HD + 2 * E>(tmem_slot);
   for (int i = tid; i < 4 * E; i += kThreads) lnacc[i] = 0.f;
@@ -382,22 +378,31 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
-  uint32_t parity = 0;
+  uint32_t parity = 0, lpar = 0;   // lpar: phase of the per-tile load barriers (each completes once per tile)
   const float scale = rsqrtf((float)D);
   bool wa_ready = false;       // [W_2^T | W_o^T] of the next tile already requested
-
-  load_w_kmajor<E, HD>(Wb, a.w1t, tid);
+  bool w1_waited = false;      // W_1^T is loaded once and stays resident
+  // one elected thread issues every TMA load; the MMA warp waits for them
+  auto load_wa_first = [&]() {   // [W_2^T | W_o^T] -> Wa
+    tma::expect_tx(lbar, (uint32_t)((E * HD + E * E) * 4));
+#pragma unroll
+    for (int kb = 0; kb < E / 32; ++kb) {
+      tma::load_tile(Wa + (size_t)kb * HD * 128, &tm.w2t, kb * 32, 0, lbar);
+      tma::load_tile(Wa + E * HD * 4 + (size_t)kb * E * 128, &tm.wot, kb * 32, 0, lbar);
+    }
+  };
+  if (tid == 0 && (int)blockIdx.x < a.n_tiles) {
+    tma::expect_tx(lbar + 1, (uint32_t)(E * HD * 4));
+#pragma unroll
+    for (int kb = 0; kb < HD / 32; ++kb) tma::load_tile(Wb + (size_t)kb * E * 128, &tm.w1t, kb * 32, 0, lbar + 1);
+  }
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int seq0 = tile * a.spt;
     const int nseq = min(a.spt, a.B - seq0);
     const long long row0 = (long long)seq0 * S;
     const int nrows = nseq * S;
     const bool live = act && r < nrows;
-    if (!wa_ready) {
-      load_w_kmajor<HD, E>(Wa, a.w2t, tid);
-      load_w_kmajor<E, E>(Wa + E * HD * 4, a.wot, tid);
-    }
-    cp_commit();
+    if (!wa_ready && tid == 0) load_wa_first();
     // ---- dz2 = LN2'(dy)
     float dz2v[16];
     {
@@ -428,15 +433,15 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
         }
       }
     }
-    cp_wait_all();                 // the weights have landed
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     // ---- dh = dz2 W_2 ; dz2 to HBM meanwhile
     if (warp == 4) {
+      umma::mbar_wait(lbar, lpar);       // [W_2^T | W_o^T] have landed
       umma::fence_after_sync();
       if (umma::elect_one()) {
-        issue_chain(tmem + C1, R0, Wa, HD, E, true);
+        issue_chain<false>(tmem + C1, R0, Wa, HD, E, true);
         umma::commit(bar);
       }
       __syncwarp();
@@ -477,9 +482,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     __syncthreads();
     // ---- d(x1) = dz2 + dh2 W_1 ; dz1 = LN1'(d(x1))
     if (warp == 4) {
+      if (!w1_waited) umma::mbar_wait(lbar + 1, 0);
       umma::fence_after_sync();
       if (umma::elect_one()) {
-        issue_chain(tmem + C2, R1, Wb, E, HD, true);
+        issue_chain<false>(tmem + C2, R1, Wb, E, HD, true);
         umma::commit(bar);
       }
       __syncwarp();
@@ -533,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     if (warp == 4) {
       umma::fence_after_sync();
       if (umma::elect_one()) {
-        issue_chain(tmem + C3, R0, Wa + E * HD * 4, E, E, true);
+        issue_chain<false>(tmem + C3, R0, Wa + E * HD * 4, E, E, true);
         umma::commit(bar);
       }
       __syncwarp();
@@ -543,8 +549,12 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     umma::fence_after_sync();
     __syncthreads();               // staging consumed; the dz1 slab and [W_2^T | W_o^T] are consumed too
     fill_tile<CH>(R0, a.q, row0, nrows, tid);
-    load_w_kmajor<E, 3 * E>(Wa, a.wqkvt, tid);
     cp_commit();
+    if (tid == 0) {                // W_qkv^T -> Wa, in flight during the attention
+      tma::expect_tx(lbar + 2, (uint32_t)(3 * E * E * 4));
+#pragma unroll
+      for (int kb = 0; kb < 3 * E / 32; ++kb) tma::load_tile(Wa + (size_t)kb * E * 128, &tm.wqkvt, kb * 32, 0, lbar + 2);
+    }
     if (act) {                     // dctx -> swizzled row-major tile
       float v[16];
       umma::tmem_ld16(trow + (uint32_t)(C3 + sl * 16), v);
@@ -582,14 +592,17 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
         attention_bwd_mma<E, CH>(R0, R1, R2, R3, Ls, Dl, rb, h * D, S, scale, lane, a.dq + row0 * E, a.dk + row0 * E, a.dv + row0 * E);
         __syncwarp();
       }
+      asm volatile("fence.proxy.async;" ::: "memory");   // this thread's dq / dk / dv stores (generic proxy) before the TMA reads them
       __syncthreads();             // dq / dk / dv of the tile are in HBM / L2; every tile is dead
-      fill_slab<CH>(R3, a.dq, row0, nrows, tid);
-      fill_slab<CH>(R1, a.dk, row0, nrows, tid);
-      fill_slab<CH>(R0, a.dv, row0, nrows, tid);
-      cp_wait_all();
-      umma::fence_proxy_async();
-      umma::fence_before_sync();
-      __syncthreads();
+      if (tid == 0) {              // read them back as K-major slabs (rows past the tile are other tiles' rows: never stored)
+        tma::expect_tx(lbar + 3, (uint32_t)(3 * TILE));
+#pragma unroll
+        for (int kb = 0; kb < E / 32; ++kb) {
+          tma::load_tile(R3 + (size_t)kb * kRows * 128, &tm.dq, kb * 32, (int)row0, lbar + 3);
+          tma::load_tile(R1 + (size_t)kb * kRows * 128, &tm.dk, kb * 32, (int)row0, lbar + 3);
+          tma::load_tile(R0 + (size_t)kb * kRows * 128, &tm.dv, kb * 32, (int)row0, lbar + 3);
+        }
+      }
     } else {
       // ---- attention backward: one (sequence, head) per warp.  Results replace dead operands of the same (sequence, head)
       //      block: dq -> k tile, dk -> q tile, dv -> v tile.
@@ -710,22 +723,24 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     }
     // ---- dx = dz1 + dq W_q + dk W_k + dv W_v
     if (warp == 4) {
+      umma::mbar_wait(lbar + 2, lpar);                       // W_qkv^T
+      if (SMAX == 32) umma::mbar_wait(lbar + 3, lpar);       // the dq / dk / dv slabs
       umma::fence_after_sync();
       if (umma::elect_one()) {
-        issue_chain(tmem + C4, R3, Wa, E, E, true);
-        issue_chain(tmem + C4, R1, Wa + (size_t)(E / 4) * E * 16, E, E, false);
-        issue_chain(tmem + C4, R0, Wa + (size_t)2 * (E / 4) * E * 16, E, E, false);
+        constexpr size_t WSTEP = (size_t)(E / 32) * E * 128;  // boxes of one of the three matrices
+        issue_chain<SMAX == 32>(tmem + C4, R3, Wa, E, E, true);
+        issue_chain<SMAX == 32>(tmem + C4, R1, Wa + WSTEP, E, E, false);
+        issue_chain<SMAX == 32>(tmem + C4, R0, Wa + 2 * WSTEP, E, E, false);
         umma::commit(bar);
       }
       __syncwarp();
     }
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
+    w1_waited = true;
+    lpar ^= 1;
     wa_ready = tile + (int)gridDim.x < a.n_tiles;
-    if (wa_ready) {                // the next tile's first weights, in flight during this epilogue
-      load_w_kmajor<HD, E>(Wa, a.w2t, tid);
-      load_w_kmajor<E, E>(Wa + E * HD * 4, a.wot, tid);
-    }
+    if (wa_ready && tid == 0) load_wa_first();   // the next tile's first weights, in flight during this epilogue
     if (act) {
       float v[16];
       umma::tmem_ld16(trow + (uint32_t)(C4 + sl * 16), v);
@@ -802,8 +817,20 @@ int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   const double T = (double)a.B * a.S;
+  BwdMaps tm;
+  {
+    const long long rows = (long long)a.B * a.S;
+    int rc = make_f32_tensor_map_sw(&tm.w2t, a.w2t, E, HD, HD);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.wot, a.wot, E, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.w1t, a.w1t, HD, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.wqkvt, a.wqkvt, 3 * E, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.dq, a.dq, E, rows, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.dk, a.dk, E, rows, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.dv, a.dv, E, rows, kRows);
+    if (rc) return rc;
+  }
   MivitProfScope prof("encoder_layer_bwd", 2.0 * T * (4.0 * E * E + 2.0 * E * HD) + 10.0 * a.B * NH * (double)a.S * a.S * (E / NH), st);
-  kern<<<grid, kThreads, smem, st>>>(a);
+  kern<<<grid, kThreads, smem, st>>>(a, tm);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
