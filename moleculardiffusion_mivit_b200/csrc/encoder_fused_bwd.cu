@@ -27,11 +27,14 @@ namespace {
 constexpr int kRows = 128;
 constexpr int kThreads = 512;   // 16 warps: warp w reads TMEM lane quarter w & 3 and owns column slice w >> 2 of every epilogue
 
-__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, const void* smem_src, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(col), "r"(row),
+               "r"(umma::smem_u32(smem_src))
+               : "memory");
 }
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be reused
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -62,6 +65,8 @@ struct BwdMaps {   // fp32 SWIZZLE_128B tensor maps (tma.cuh: make_f32_tensor_ma
   CUtensorMap w1t;           // [E, HD],  E-row boxes
   CUtensorMap wqkvt;         // [E, 3E],  E-row boxes
   CUtensorMap dq, dk, dv;    // [T, E],   128-row boxes (read back as A slabs, S <= 32)
+  CUtensorMap q, k, v;       // [T, E],   128-row boxes (the attention's row-major tiles)
+  CUtensorMap dz2, dh2, dx;  // stores: [T, E] / [T, HD] / [T, E], boxes of spt * S rows (the rows a tile owns)
 };
 
 // D[128 x N] (TMEM columns from `tmem`) (+)= A[128 x K] * B^T.  B = TMA-loaded weights: K / 32 boxes of [N rows][128 B]
@@ -81,14 +86,16 @@ __device__ __forceinline__ void issue_chain(uint32_t tmem, const uint8_t* a, con
   }
 }
 
-// XOR-swizzled row-major tile [128][CH x 16 B]: chunk c of row r lives at position c ^ (r & (CH - 1)).  A warp whose lanes
-// hold 32 consecutive rows and the same chunk index hits every bank group once (a padded layout would not fit here).
-// (Measured alternative: swizzling whole 64-byte head blocks, so that the attention loops address a block with one computed
-// offset + immediates, executes 7 % fewer instructions but pays 8-way instead of no bank conflicts on every thread-per-row
-// access: 121.5 vs 106.9 us per launch under ncu, profiles/r02_ncu_encoder_bwd.md.)
+// Row-major tiles live in the layout TMA produces (and consumes) for fp32 SWIZZLE_128B boxes of 32 floats: box c / 8 holds
+// [128 rows][128 B], and inside a row the 16-byte chunk c % 8 sits at position (c % 8) ^ (r % 8).  The q / k / v tiles are TMA
+// loads, the staging tiles TMA stores; lanes holding consecutive rows and the same chunk (every thread-per-row access, and the
+// MMA fragment loads of the attention) hit every bank once.
+// (Measured alternative for the thread-filled version of these tiles: swizzling whole 64-byte head blocks, so that the SIMT
+// attention loops address a block with one computed offset + immediates, executed 7 % fewer instructions but paid 8-way bank
+// conflicts on every thread-per-row access: 121.5 vs 106.9 us per launch under ncu, profiles/r02_ncu_encoder_bwd.md.)
 template <int CH>
 __device__ __forceinline__ uint32_t rm_off(int r, int c) {
-  return (uint32_t)r * (CH * 16) + (uint32_t)((c ^ (r & (CH - 1))) << 4);
+  return (uint32_t)(c >> 3) * (kRows * 128) + (uint32_t)r * 128 + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
 }
 template <int CH>
 __device__ __forceinline__ float4 rm_ld(const uint8_t* tile, int r, int c) {
@@ -105,16 +112,6 @@ __device__ __forceinline__ void copy_out(const uint8_t* tile, float* __restrict_
   for (int i = tid; i < nrows * CH; i += kThreads) {
     const int r = i / CH, c = i % CH;
     *reinterpret_cast<float4*>(g + (row0 + r) * gw + gc + 4 * c) = rm_ld<CH>(tile, r, c);
-  }
-}
-// global rows -> swizzled tile (cp.async; rows past nrows are zero)
-template <int CH>
-__device__ __forceinline__ void fill_tile(uint8_t* tile, const float* __restrict__ g, long long row0, int nrows, int tid) {
-  const uint4* src = reinterpret_cast<const uint4*>(g + row0 * (CH * 4));
-  for (int i = tid; i < kRows * CH; i += kThreads) {
-    const int r = i / CH, c = i % CH;
-    uint8_t* d = tile + rm_off<CH>(r, c);
-    if (r < nrows) cp16(d, src + i); else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
   }
 }
 // swizzled row-major tile -> K-major A slab [CH][128][16 B]; lanes walk rows (conflict-free on both sides)
@@ -356,8 +353,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
   float* lnacc = red + 2 * kRows * 4;                    // [LN1 | LN2][dgamma | dbeta][E]
   float* lsdl = lnacc + 4 * E;                           // [16 warps][L | D][SMAX]
   uint64_t* bar = reinterpret_cast<uint64_t*>(lsdl + 16 * 2 * SMAX);   // MMA completion
-  uint64_t* lbar = bar + 1;              // [4] TMA completion: W_2^T + W_o^T | W_1^T (once) | W_qkv^T | dq, dk, dv slabs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 4);
+  uint64_t* lbar = bar + 1;              // [6] TMA completion: W_2^T + W_o^T | W_1^T (once) | W_qkv^T | dq, dk, dv slabs | k, v | q
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 6);
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int qd = warp & 3, sl = warp >> 2;
   const int r = qd * 32 + lane;               // token row of this thread in every epilogue
@@ -366,8 +363,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
 
   if (tid == 0) {
     umma::mbar_init(bar, 1);
-    for (int i = 0; i < 4; ++i) umma::mbar_init(lbar + i, 1);
+    for (int i = 0; i < 6; ++i) umma::mbar_init(lbar + i, 1);
     umma::mbar_fence_init();
+    tma::prefetch_map(&tm.q); tma::prefetch_map(&tm.k); tma::prefetch_map(&tm.v);
+    tma::prefetch_map(&tm.dz2); tma::prefetch_map(&tm.dh2); tma::prefetch_map(&tm.dx);
     tma::prefetch_map(&tm.w2t); tma::prefetch_map(&tm.wot); tma::prefetch_map(&tm.w1t); tma::prefetch_map(&tm.wqkvt);
     tma::prefetch_map(&tm.dq); tma::prefetch_map(&tm.dk); tma::prefetch_map(&tm.dv);
   }
@@ -446,7 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       }
       __syncwarp();
     }
-    copy_out<CH>(R3, a.dz2, row0, nrows, E, 0, tid);
+    if (tid == 0) {                // dz2 to HBM: TMA store of the staging tile (boxes of the rows this tile owns)
+#pragma unroll
+      for (int kb = 0; kb < E / 32; ++kb) tma_store_box(&tm.dz2, R3 + (size_t)kb * kRows * 128, kb * 32, (int)row0);
+      bulk_commit();
+    }
     // the ReLU gate (sign of the stored relu(h)) of this thread's columns of both hidden chunks: in flight during the MMA
     float4 gate[HD / E][4];
 #pragma unroll
@@ -457,9 +460,11 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
                               : make_float4(0.f, 0.f, 0.f, 0.f);
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
-    __syncthreads();               // staging tile consumed
+    if (tid == 0) bulk_wait_read0();
+    __syncthreads();               // staging tile consumed (the TMA store has read it); the dz2 slab (R0) is consumed by the MMA
+    static_assert(HD / E == 2, "two hidden chunks: staged in R3 and R0");
 #pragma unroll
-    for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: ReLU gate, A operand, staged copy to HBM
+    for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: ReLU gate, A operand, staging tile
       if (act) {
         const int c0 = chunk * E + sl * 16;
         float v[16];
@@ -470,16 +475,21 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
           const float4 t = make_float4(h4.x > 0.f ? v[4 * c] : 0.f, h4.y > 0.f ? v[4 * c + 1] : 0.f, h4.z > 0.f ? v[4 * c + 2] : 0.f,
                                        h4.w > 0.f ? v[4 * c + 3] : 0.f);
           *reinterpret_cast<float4*>(R1 + ((size_t)(c0 / 4 + c) * kRows + r) * 16) = t;
-          rm_st<CH>(R3, r, sl * 4 + c, t);
+          rm_st<CH>(chunk == 0 ? R3 : R0, r, sl * 4 + c, t);
         }
       }
-      __syncthreads();
-      copy_out<CH>(R3, a.dh2, row0, nrows, HD, chunk * E, tid);
-      __syncthreads();
     }
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
+    if (tid == 0) {                // dh2 to HBM (the weight gradient of fc1 reads it there)
+#pragma unroll
+      for (int kb = 0; kb < E / 32; ++kb) {
+        tma_store_box(&tm.dh2, R3 + (size_t)kb * kRows * 128, kb * 32, (int)row0);
+        tma_store_box(&tm.dh2, R0 + (size_t)kb * kRows * 128, E + kb * 32, (int)row0);
+      }
+      bulk_commit();
+    }
     // ---- d(x1) = dz2 + dh2 W_1 ; dz1 = LN1'(d(x1))
     if (warp == 4) {
       if (!w1_waited) umma::mbar_wait(lbar + 1, 0);
@@ -510,9 +520,15 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       umma::mbar_wait(bar, parity); parity ^= 1;
       umma::fence_after_sync();
       // the dh2 slab is consumed: k and v tiles of the attention backward land in its place
-      fill_tile<CH>(R1, a.k, row0, nrows, tid);
-      fill_tile<CH>(R2, a.v, row0, nrows, tid);
-      cp_commit();
+      if (tid == 0) {
+        bulk_wait_read0();         // the dh2 staging tiles (R3, R0) have been read: LayerNorm 1' below rewrites them
+        tma::expect_tx(lbar + 4, (uint32_t)(2 * TILE));
+#pragma unroll
+        for (int kb = 0; kb < E / 32; ++kb) {
+          tma::load_tile(R1 + (size_t)kb * kRows * 128, &tm.k, kb * 32, (int)row0, lbar + 4);
+          tma::load_tile(R2 + (size_t)kb * kRows * 128, &tm.v, kb * 32, (int)row0, lbar + 4);
+        }
+      }
       float dyv[16];
       if (act) {
         umma::tmem_ld16(trow + (uint32_t)(C2 + sl * 16), dyv);
@@ -548,9 +564,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     __syncthreads();               // staging consumed; the dz1 slab and [W_2^T | W_o^T] are consumed too
-    fill_tile<CH>(R0, a.q, row0, nrows, tid);
-    cp_commit();
-    if (tid == 0) {                // W_qkv^T -> Wa, in flight during the attention
+    if (tid == 0) {                // q tile -> R0 and W_qkv^T -> Wa, in flight during the dctx epilogue / the attention
+      tma::expect_tx(lbar + 5, (uint32_t)TILE);
+#pragma unroll
+      for (int kb = 0; kb < E / 32; ++kb) tma::load_tile(R0 + (size_t)kb * kRows * 128, &tm.q, kb * 32, (int)row0, lbar + 5);
       tma::expect_tx(lbar + 2, (uint32_t)(3 * E * E * 4));
 #pragma unroll
       for (int kb = 0; kb < 3 * E / 32; ++kb) tma::load_tile(Wa + (size_t)kb * E * 128, &tm.wqkvt, kb * 32, 0, lbar + 2);
@@ -562,7 +579,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       for (int c = 0; c < 4; ++c)
         rm_st<CH>(R3, r, sl * 4 + c, live ? make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    cp_wait_all();
+    umma::mbar_wait(lbar + 4, lpar);   // k, v tiles
+    umma::mbar_wait(lbar + 5, lpar);   // q tile
     umma::fence_before_sync();
     __syncthreads();
     if constexpr (SMAX == 32) {
@@ -752,12 +770,16 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
         rm_st<CH>(R2, r, sl * 4 + c, make_float4(v[4 * c] + z4.x, v[4 * c + 1] + z4.y, v[4 * c + 2] + z4.z, v[4 * c + 3] + z4.w));
       }
     }
+    umma::fence_proxy_async();
     umma::fence_before_sync();
-    __syncthreads();
-    copy_out<CH>(R2, a.dx, row0, nrows, E, 0, tid);
-    __syncthreads();               // the next tile overwrites every buffer
+    __syncthreads();               // the next tile overwrites every buffer; R2 is next written by a TMA load issued by thread 0
+    if (tid == 0) {                // dx to HBM
+#pragma unroll
+      for (int kb = 0; kb < E / 32; ++kb) tma_store_box(&tm.dx, R2 + (size_t)kb * kRows * 128, kb * 32, (int)row0);
+      bulk_commit();
+    }
   }
-  cp_wait_all();
+  if (tid == 0) bulk_wait0();
   umma::fence_before_sync();
   __syncthreads();
   for (int i = tid; i < 4 * E; i += kThreads) {
@@ -812,7 +834,7 @@ int sm_count() {
 template <int E, int HD, int NH, int SMAX>
 int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   constexpr int WA = (3 * E * E > E * HD + E * E ? 3 * E * E : E * HD + E * E) * 4, WB = E * HD * 4;
-  const int smem = WA + WB + 4 * kRows * E * 4 + 2 * kRows * 4 * 4 + 4 * E * 4 + 16 * 2 * SMAX * 4 + 64;
+  const int smem = WA + WB + 4 * kRows * E * 4 + 2 * kRows * 4 * 4 + 4 * E * 4 + 16 * 2 * SMAX * 4 + 128;
   auto kern = encoder_layer_bwd_kernel<E, HD, NH, SMAX>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
@@ -827,6 +849,13 @@ int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     if (!rc) rc = make_f32_tensor_map_sw(&tm.dq, a.dq, E, rows, kRows);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.dk, a.dk, E, rows, kRows);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.dv, a.dv, E, rows, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.q, a.q, E, rows, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.k, a.k, E, rows, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.v, a.v, E, rows, kRows);
+    const int own = a.spt * a.S;   // rows a tile owns: the store boxes (the last tile is clipped at the end of the tensor)
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.dz2, a.dz2, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.dh2, a.dh2, HD, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.dx, a.dx, E, rows, own);
     if (rc) return rc;
   }
   MivitProfScope prof("encoder_layer_bwd", 2.0 * T * (4.0 * E * E + 2.0 * E * HD) + 10.0 * a.B * NH * (double)a.S * a.S * (E / NH), st);
