@@ -7,16 +7,17 @@
 // read, transposed store).  Here a CTA owns a tile of 128 token rows = floor(128 / S) whole sequences and walks the layer with
 // the tile resident on chip:
 //   x tile  --TMA-->  shared memory ([row][128 B] SWIZZLE_128B boxes of 32 floats, the tcgen05 K-major A operand)
-//   [q|k|v] = x W_qkv^T    ONE tcgen05.mma chain (kind::tf32, M = 128, N = 3E) -> TMEM -> +bias -> shared memory (row-major)
-//   attention              per (sequence, head) on one warp, flash style in registers (S <= 64, d = 16) -> ctx written straight
-//                          into the A-operand layout, row log-sum-exps to HBM
+//   [q|k|v] = x W_qkv^T    ONE tcgen05.mma chain (kind::tf32, M = 128, N = 3E) -> TMEM -> +bias -> row-major tiles in shared memory
+//   attention              per (sequence, head) on one warp with warp-level tensor-core MMAs (mma.sync m16n8k8 tf32; scores in
+//                          3xTF32, S <= 64, d = 16) -> ctx written straight into the A-operand layout, row log-sum-exps to HBM
 //   ao = ctx W_o^T         tcgen05 -> TMEM -> epilogue with thread = token row: + bias + residual, LayerNorm in registers
 //   h  = relu(x1 W_1^T)    tcgen05 -> TMEM -> +bias, ReLU -> shared memory (A layout)
-//   x2 = LN2(x1 + h W_2^T) tcgen05 -> TMEM -> epilogue: + bias + residual, LayerNorm -> HBM
+//   x2 = LN2(x1 + h W_2^T) tcgen05 -> TMEM -> epilogue: + bias + residual, LayerNorm
 // Weights arrive by TMA (one box per 32-float slice of the reduction dimension, SWIZZLE_128B) in two alternating buffers, one
-// phase ahead; activations produced on chip (ctx, x1, relu(h)) are written by the threads in the no-swizzle core-matrix order.  Everything the (unfused) backward reads is
-// written once, coalesced through a shared-memory staging tile: q, k, v, ctx, z1, x1, relu(h), z2, x2 and the LayerNorm / softmax
-// row statistics.  Same arithmetic as the unfused path (tf32 products, fp32 accumulation / softmax / LayerNorm).
+// phase ahead; activations produced on chip (ctx, x1, relu(h)) are written by the threads in the no-swizzle core-matrix order.
+// Everything the backward reads -- q, k, v, ctx, z1, x1, relu(h), z2, x2 -- leaves through row-major tiles in the TMA box layout
+// and TMA stores (the thread-copied version spent 25 % of its time in the copy loops, profiles/r02_ncu_encoder_fwd.md), the
+// LayerNorm / softmax row statistics directly.  tf32 products, fp32 accumulation / softmax / LayerNorm.
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
@@ -25,6 +26,7 @@
 namespace {
 
 constexpr int kRows = 128;
+constexpr int kThreads = 512;   // 16 warps: warp w reads TMEM lane quarter w & 3 and owns column slice w >> 2 of every epilogue
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -47,13 +49,14 @@ struct EncArgs {
   float ln_eps;
 };
 
-constexpr int kThreads = 512;   // 16 warps: warp w reads TMEM lane quarter w & 3 and owns column slice w >> 2 of every epilogue
-
 struct EncMaps {   // fp32 SWIZZLE_128B tensor maps (tma.cuh: make_f32_tensor_map_sw), boxes of 32 floats x rows
   CUtensorMap x;                       // [T, E], 128-row boxes
   CUtensorMap wq, wk, wv, wo;          // [E, E], E-row boxes
   CUtensorMap w1;                      // [HD, E], HD-row boxes
   CUtensorMap w2;                      // [E, HD], E-row boxes
+  // stores: boxes of spt * S rows (the rows a tile owns; the last tile is clipped at the end of the tensor)
+  CUtensorMap q, k, v, ctx, z1, x1, z2, x2;   // [T, E]
+  CUtensorMap hact;                            // [T, HD]
 };
 
 // D[128 x N] (TMEM columns [0, N)) = A[128 x K] * B^T.  B = TMA-loaded weights: K / 32 boxes of [N rows][128 B] SWIZZLE_128B
@@ -75,27 +78,149 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem, const uint8_t* a, cons
   umma::commit(bar);
 }
 
-// coalesced copy of a row-major staging tile [nrows][W] (row stride ld floats) to global rows [row0, row0 + nrows) of width gw
-// at column offset gc
-template <int W>
-__device__ __forceinline__ void copy_out(const float* __restrict__ stg, int ld, float* __restrict__ g, long long row0, int nrows,
-                                         int gw, int gc, int tid) {
-  constexpr int w4 = W / 4;
-  for (int i = tid; i < nrows * w4; i += kThreads) {
-    const int r = i / w4, c = i % w4;
-    *reinterpret_cast<float4*>(g + (row0 + r) * gw + gc + 4 * c) = *reinterpret_cast<const float4*>(stg + (size_t)r * ld + 4 * c);
-  }
+// Row-major tiles (q, k, v for the attention; every staging tile) live in the layout TMA consumes for fp32 SWIZZLE_128B boxes of
+// 32 floats: box c / 8 holds [128 rows][128 B], inside a row the 16-byte chunk c % 8 sits at position (c % 8) ^ (r % 8).  Lanes
+// holding consecutive rows and the same chunk -- the thread-per-row epilogues, the MMA fragment loads -- hit every bank once,
+// and a tile goes to HBM as E / 32 TMA stores instead of 2048 LDS + STG pairs.
+template <int CH>
+__device__ __forceinline__ uint32_t rm_off(int r, int c) {
+  return (uint32_t)(c >> 3) * (kRows * 128) + (uint32_t)r * 128 + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
+}
+template <int CH>
+__device__ __forceinline__ void rm_st(uint8_t* tile, int r, int c, float4 v) {
+  *reinterpret_cast<float4*>(tile + rm_off<CH>(r, c)) = v;
+}
+// element (row, col); rows past the tile are clamped (finite data: a masked 0 * NaN would poison the MMA)
+template <int CH>
+__device__ __forceinline__ float tile_el(const uint8_t* tile, int row, int col) {
+  row = min(row, kRows - 1);
+  return *reinterpret_cast<const float*>(tile + rm_off<CH>(row, col >> 2) + ((col & 3) << 2));
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, const void* smem_src, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(col), "r"(row),
+               "r"(umma::smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be reused
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// a whole E-wide tile -> rows [row0, ...) of a [T, W] matrix at column col0 (one elected thread)
+template <int E>
+__device__ __forceinline__ void store_tile(const CUtensorMap* tm, const uint8_t* tile, int col0, int row0) {
+#pragma unroll
+  for (int kb = 0; kb < E / 32; ++kb) tma_store_box(tm, tile + (size_t)kb * kRows * 128, col0 + kb * 32, row0);
 }
 
-template <int D>
-__device__ __forceinline__ float dot16(const float (&a)[D], const float* __restrict__ b) {
-  float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+// ---- warp-level tensor-core attention (mma.sync m16n8k8 tf32; fragment layouts: see encoder_fused_bwd.cu) -------------------
+__device__ __forceinline__ void mma_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {   // 3xTF32: x = hi + lo, hi exact in tf32
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// softmax(Q K^T / sqrt(d)) V of ONE (sequence, head) on one warp: rows rb .. rb + S of the q / k / v tiles, columns hc .. hc + 16.
+// Scores AND P V in 3xTF32 (error ~ fp32: the backward recomputes P from the stored log-sum-exp, and a plain-tf32 P V moved the
+// forward by 1e-4 -- enough to flip borderline ReLU masks of the feed-forward block against the fp32 attention of the unfused
+// path), base-2 exponentials; the score C fragments are reused as A fragments of P V (reduction index permuted inside groups of
+// 8, V rows loaded with the same permutation).
+// ctx goes straight into the K-major A slab of the out-projection, the natural-log row log-sum-exps to HBM.
+template <int E, int CH, int SMAX>
+__device__ __forceinline__ void attention_fwd_mma(const uint8_t* Qt, const uint8_t* Kt, const uint8_t* Vt, uint8_t* ctx_slab, int rb,
+                                                  int hc, int S, float scale, int lane, float* __restrict__ lse) {
+  constexpr int MT = SMAX / 16, NT = SMAX / 8;
+  const int gid = lane >> 2, tig = lane & 3;
+  const float sl2 = scale * 1.4426950408889634f;
+#pragma unroll 1
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r0 = mt * 16 + gid, r1 = r0 + 8;
+    if (mt * 16 >= S) break;
+    uint32_t ah[2][4], al[2][4];
 #pragma unroll
-  for (int c = 0; c < D; c += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(b + c);
-    p0 = fmaf(a[c], t.x, p0); p1 = fmaf(a[c + 1], t.y, p1); p2 = fmaf(a[c + 2], t.z, p2); p3 = fmaf(a[c + 3], t.w, p3);
+    for (int ks = 0; ks < 2; ++ks) {
+      const int ca = hc + ks * 8 + tig, cb = ca + 4;
+      tf32_split(tile_el<CH>(Qt, rb + r0, ca) * sl2, ah[ks][0], al[ks][0]);
+      tf32_split(tile_el<CH>(Qt, rb + r1, ca) * sl2, ah[ks][1], al[ks][1]);
+      tf32_split(tile_el<CH>(Qt, rb + r0, cb) * sl2, ah[ks][2], al[ks][2]);
+      tf32_split(tile_el<CH>(Qt, rb + r1, cb) * sl2, ah[ks][3], al[ks][3]);
+    }
+    float sc[NT][4];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int cr = rb + nt * 8 + gid;
+      uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int ca = hc + ks * 8 + tig;
+        tf32_split(tile_el<CH>(Kt, cr, ca), bh[ks][0], bl[ks][0]);
+        tf32_split(tile_el<CH>(Kt, cr, ca + 4), bh[ks][1], bl[ks][1]);
+      }
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        mma_16x8x8(sc[nt], al[ks], bh[ks]);
+        mma_16x8x8(sc[nt], ah[ks], bl[ks]);
+        mma_16x8x8(sc[nt], ah[ks], bh[ks]);
+      }
+      const int c0 = nt * 8 + 2 * tig;
+      if (c0 >= S) sc[nt][0] = sc[nt][2] = -INFINITY;
+      if (c0 + 1 >= S) sc[nt][1] = sc[nt][3] = -INFINITY;
+      m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    // a row lives in the four lanes of a quad
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+    uint32_t pah[NT][4], pal[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float p00 = exp2f(sc[nt][0] - m0), p01 = exp2f(sc[nt][1] - m0);     // masked columns: 2^(-inf) = 0
+      const float p10 = exp2f(sc[nt][2] - m1), p11 = exp2f(sc[nt][3] - m1);
+      s0 += p00 + p01;
+      s1 += p10 + p11;
+      tf32_split(p00, pah[nt][0], pal[nt][0]); tf32_split(p10, pah[nt][1], pal[nt][1]);
+      tf32_split(p01, pah[nt][2], pal[nt][2]); tf32_split(p11, pah[nt][3], pal[nt][3]);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    float o[2][4] = {};
+#pragma unroll
+    for (int ks = 0; ks < NT; ++ks) {
+      const int ta = rb + ks * 8 + 2 * tig, tb = ta + 1;            // tokens behind slots tig and tig + 4
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = hc + nt * 8 + gid;
+        uint32_t bh[2], bl[2];
+        tf32_split(tile_el<CH>(Vt, ta, col), bh[0], bl[0]);
+        tf32_split(tile_el<CH>(Vt, tb, col), bh[1], bl[1]);
+        mma_16x8x8(o[nt], pal[ks], bh);
+        mma_16x8x8(o[nt], pah[ks], bl);
+        mma_16x8x8(o[nt], pah[ks], bh);
+      }
+    }
+    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = hc + nt * 8 + 2 * tig;
+      uint8_t* d = ctx_slab + ((size_t)(col >> 2) * kRows) * 16 + (size_t)((col & 3) << 2);
+      if (r0 < S) *reinterpret_cast<float2*>(d + (size_t)(rb + r0) * 16) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
+      if (r1 < S) *reinterpret_cast<float2*>(d + (size_t)(rb + r1) * 16) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+    }
+    if (tig == 0) {
+      if (r0 < S) lse[r0] = m0 * 0.6931471805599453f + logf(s0);
+      if (r1 < S) lse[r1] = m1 * 0.6931471805599453f + logf(s1);
+    }
   }
-  return (p0 + p1) + (p2 + p3);
 }
 
 // LayerNorm over a token row whose E columns are split into 16-column slices over E/16 threads (one per column-slice warp):
@@ -139,25 +264,22 @@ __device__ __forceinline__ void layernorm_sliced(float (&v)[16], bool active, in
 template <int E, int HD, int NH, int SMAX>
 __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __grid_constant__ EncArgs a, const __grid_constant__ EncMaps tm) {
   constexpr int D = E / NH;                 // head dim (16 in every reference configuration)
-  constexpr int LD = E + 4;                 // row stride of the row-major tiles (floats): 16-byte aligned rows, spread banks
-  constexpr int XS_BYTES = E * 512;         // [E/4][128][16 B]
+  constexpr int CH = E / 4;                 // 16-byte chunks of an E-wide row
+  constexpr int TILE = kRows * E * 4;       // bytes of an E-wide tile (row-major in the TMA box layout, or a K-major slab)
   constexpr int WA_BYTES = (3 * E * E > E * HD ? 3 * E * E : E * HD) * 4;
   constexpr int WB_BYTES = (E * E > HD * E ? E * E : HD * E) * 4;
-  constexpr int ROW_BYTES = kRows * LD * 4;
-  constexpr int HS_BYTES = HD * 512;        // [HD/4][128][16 B]
   constexpr int NS = E / 16;                // active column slices of an E-wide epilogue
-  static_assert(HS_BYTES <= 2 * ROW_BYTES, "the hidden tile aliases the k / v tiles");
-  static_assert(HD % E == 0 && E % 32 == 0 && D % 4 == 0 && NS <= 4, "tile shapes");
+  static_assert(HD == 2 * E && E % 32 == 0 && D == 16 && NS <= 4, "tile shapes");
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* Xs = smem;                                   // A operand: x, then ctx, then x1
-  uint8_t* Wa = Xs + XS_BYTES;                          // W_qkv, then W_1
-  uint8_t* Wb = Wa + WA_BYTES;                          // W_o, then W_2
-  float* Qs = reinterpret_cast<float*>(Wb + WB_BYTES);  // q rows; later the copy-out staging tile
-  float* Ks = Qs + kRows * LD;
-  float* Vs = Ks + kRows * LD;
-  uint8_t* Hs = reinterpret_cast<uint8_t*>(Ks);         // A operand: relu(h) (aliases k, v)
-  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(Qs) + 3 * ROW_BYTES);   // [128][4] LayerNorm partial sums
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + kRows * 4);     // MMA completion
+  uint8_t* Xs = smem;                       // A operand: x (TMA), then ctx, then x1 (core-matrix slabs); staging tile of relu(h)[:, E:]
+  uint8_t* Wa = Xs + TILE;                  // W_qkv, then W_1
+  uint8_t* Wb = Wa + WA_BYTES;              // W_o, then W_2
+  uint8_t* Qs = Wb + WB_BYTES;              // q tile; then staging tile: ctx, z1, relu(h)[:, :E], z2
+  uint8_t* Ks = Qs + TILE;                  // k tile; then staging tile: x1, x2
+  uint8_t* Vs = Ks + TILE;                  // v tile
+  uint8_t* Hs = Ks;                         // A operand relu(h): [HD/4][128][16 B] over the k and v tiles
+  float* red = reinterpret_cast<float*>(Vs + TILE);                  // [128][4] LayerNorm partial sums
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + kRows * 4);      // MMA completion
   uint64_t* lbar = bar + 1;                                          // [3] TMA completion: x + W_qkv + W_o | W_1 | W_2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 3);
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
@@ -171,6 +293,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
     umma::mbar_fence_init();
     tma::prefetch_map(&tm.x); tma::prefetch_map(&tm.wq); tma::prefetch_map(&tm.wk); tma::prefetch_map(&tm.wv);
     tma::prefetch_map(&tm.wo); tma::prefetch_map(&tm.w1); tma::prefetch_map(&tm.w2);
+    tma::prefetch_map(&tm.q); tma::prefetch_map(&tm.k); tma::prefetch_map(&tm.v); tma::prefetch_map(&tm.ctx);
+    tma::prefetch_map(&tm.z1); tma::prefetch_map(&tm.x1); tma::prefetch_map(&tm.hact); tma::prefetch_map(&tm.z2); tma::prefetch_map(&tm.x2);
   }
   if (warp == 0) umma::tmem_alloc<256>(tmem_slot);
   umma::fence_before_sync();
@@ -180,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
   const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
   uint32_t parity = 0, lpar = 0;   // lpar: phase of the three load barriers (each completes once per tile)
   const float scale = rsqrtf((float)D);
+  const bool act = sl < NS;
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int seq0 = tile * a.spt;
@@ -188,9 +313,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
     const int nrows = nseq * S;
     const bool live = r < nrows;
     // ---- x tile + W_qkv (-> Wa) + W_o (-> Wb): 10 TMA boxes, one elected thread.  (Rows of the tile past nrows hold the next
-    //      tile's tokens, or zeros past the end of the tensor: every epilogue masks them with `live`.)
+    //      tile's tokens, or zeros past the end of the tensor: every epilogue masks them with `live`, the stores do not reach them.)
     if (tid == 0) {
-      tma::expect_tx(lbar, (uint32_t)(XS_BYTES + 4 * E * E * 4));
+      bulk_wait_read0();           // the previous tile's last stores have read their staging tiles (Xs among them)
+      tma::expect_tx(lbar, (uint32_t)(TILE + 4 * E * E * 4));
 #pragma unroll
       for (int kb = 0; kb < E / 32; ++kb) {
         tma::load_tile(Xs + (size_t)kb * kRows * 128, &tm.x, kb * 32, (int)row0, lbar);
@@ -209,8 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
     }
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
-    // W_1 -> Wa (free now), in flight during the q/k/v epilogue and the attention
-    if (tid == 0) {
+    if (tid == 0) {                // W_1 -> Wa (free now), in flight during the q/k/v epilogue and the attention
       tma::expect_tx(lbar + 1, (uint32_t)(HD * E * 4));
 #pragma unroll
       for (int kb = 0; kb < E / 32; ++kb) tma::load_tile(Wa + (size_t)kb * HD * 128, &tm.w1, kb * 32, 0, lbar + 1);
@@ -221,82 +346,50 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
       umma::tmem_ld16(trow + (uint32_t)(g * 16), v);
       const int which = (g * 16) / E, c0 = (g * 16) % E;
       const float* bias = which == 0 ? a.bq : which == 1 ? a.bk : a.bv;
-      float* dst = (which == 0 ? Qs : which == 1 ? Ks : Vs) + (size_t)r * LD + c0;
+      uint8_t* dst = which == 0 ? Qs : which == 1 ? Ks : Vs;
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
         const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + c));
-        *reinterpret_cast<float4*>(dst + c) = make_float4(v[c] + bb.x, v[c + 1] + bb.y, v[c + 2] + bb.z, v[c + 3] + bb.w);
-      }
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- q, k, v to HBM (the backward reads them) and the attention: one (sequence, head) per warp
-    copy_out<E>(Qs, LD, a.q, row0, nrows, E, 0, tid);
-    copy_out<E>(Ks, LD, a.k, row0, nrows, E, 0, tid);
-    copy_out<E>(Vs, LD, a.v, row0, nrows, E, 0, tid);
-    for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
-      const int sq = pair / NH, h = pair % NH, hc = h * D;
-      const float* Kb = Ks + (size_t)sq * S * LD + hc;
-      const float* Vb = Vs + (size_t)sq * S * LD + hc;
-      for (int i = lane; i < S; i += 32) {
-        float qi[D];
-#pragma unroll
-        for (int c = 0; c < D; c += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(Qs + (size_t)(sq * S + i) * LD + hc + c);
-          qi[c] = t.x * scale; qi[c + 1] = t.y * scale; qi[c + 2] = t.z * scale; qi[c + 3] = t.w * scale;
-        }
-        float sc[SMAX];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < SMAX; ++j)
-          if (j < S) {
-            sc[j] = dot16<D>(qi, Kb + (size_t)j * LD);
-            mx = fmaxf(mx, sc[j]);
-          }
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < SMAX; ++j)
-          if (j < S) {
-            sc[j] = expf(sc[j] - mx);
-            sum += sc[j];
-          }
-        float o[D] = {};
-#pragma unroll
-        for (int j = 0; j < SMAX; ++j)
-          if (j < S) {
-#pragma unroll
-            for (int c = 0; c < D; c += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(Vb + (size_t)j * LD + c);
-              o[c] = fmaf(sc[j], t.x, o[c]); o[c + 1] = fmaf(sc[j], t.y, o[c + 1]);
-              o[c + 2] = fmaf(sc[j], t.z, o[c + 2]); o[c + 3] = fmaf(sc[j], t.w, o[c + 3]);
-            }
-          }
-        const float inv = 1.0f / sum;
-        const int row = sq * S + i;
-#pragma unroll
-        for (int c = 0; c < D; c += 4)      // ctx straight into the A-operand layout of the out-projection
-          *reinterpret_cast<float4*>(Xs + ((size_t)((hc + c) / 4) * kRows + row) * 16) =
-              make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
-        a.lse[((size_t)(seq0 + sq) * NH + h) * S + i] = mx + logf(sum);
+        rm_st<CH>(dst, r, (c0 + c) >> 2, make_float4(v[c] + bb.x, v[c + 1] + bb.y, v[c + 2] + bb.z, v[c + 3] + bb.w));
       }
     }
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
-    // ---- ao = ctx W_o^T ; ctx to HBM meanwhile (staged row-major through Qs)
+    // ---- q, k, v to HBM (the backward reads them) and the attention: one (sequence, head) per warp
+    if (tid == 0) {
+      store_tile<E>(&tm.q, Qs, 0, (int)row0);
+      store_tile<E>(&tm.k, Ks, 0, (int)row0);
+      store_tile<E>(&tm.v, Vs, 0, (int)row0);
+      bulk_commit();
+    }
+    for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
+      const int sq = pair / NH, h = pair % NH;
+      attention_fwd_mma<E, CH, SMAX>(Qs, Ks, Vs, Xs, sq * S, h * D, S, scale, lane, a.lse + ((size_t)(seq0 + sq) * NH + h) * S);
+    }
+    if (tid == 0) bulk_wait_read0();   // the q / k / v stores have read the tiles: Qs becomes the ctx staging tile
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- ao = ctx W_o^T ; ctx to HBM meanwhile (core-matrix slab -> row-major tile -> TMA store)
     if (warp == 4) {
       umma::fence_after_sync();
       if (umma::elect_one()) issue_gemm<false>(tmem, Xs, Wb, E, E, bar);
       __syncwarp();
     }
-    for (int i = tid; i < kRows * (E / 4); i += kThreads) {   // Xs (core layout) -> Qs rows; lanes walk rows: conflict-free reads
+    for (int i = tid; i < kRows * CH; i += kThreads) {   // lanes walk rows: conflict-free on both sides
       const int c = i / kRows, rr = i % kRows;
-      *reinterpret_cast<float4*>(Qs + (size_t)rr * LD + 4 * c) = *reinterpret_cast<const float4*>(Xs + ((size_t)c * kRows + rr) * 16);
+      rm_st<CH>(Qs, rr, c, *reinterpret_cast<const float4*>(Xs + ((size_t)c * kRows + rr) * 16));
     }
+    umma::fence_proxy_async();
     __syncthreads();
-    copy_out<E>(Qs, LD, a.ctx, row0, nrows, E, 0, tid);
+    if (tid == 0) {
+      store_tile<E>(&tm.ctx, Qs, 0, (int)row0);
+      bulk_commit();
+    }
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
+    if (tid == 0) bulk_wait_read0();
     __syncthreads();               // ctx staging consumed, W_o consumed: Wb and Qs / Ks are free
     if (tid == 0) {                // W_2 -> Wb, in flight during LayerNorm 1 and fc1
       tma::expect_tx(lbar + 2, (uint32_t)(HD * E * 4));
@@ -304,7 +397,6 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
       for (int kb = 0; kb < HD / 32; ++kb) tma::load_tile(Wb + (size_t)kb * E * 128, &tm.w2, kb * 32, 0, lbar + 2);
     }
     float x1v[16];                 // this thread's 16 columns of the x1 row stay in registers for the second residual
-    const bool act = sl < NS;
     {
       float v[16];
       if (act) {
@@ -322,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
         }
 #pragma unroll
         for (int c = 0; c < 16; c += 4)          // z1 -> staging (Qs)
-          *reinterpret_cast<float4*>(Qs + (size_t)r * LD + sl * 16 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          rm_st<CH>(Qs, r, sl * 4 + c / 4, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
       }
       umma::fence_before_sync();
       float mean, rstd;
@@ -335,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
         for (int c = 0; c < 16; c += 4) {        // x1 -> A operand (Xs) and staging (Ks)
           const float4 t = make_float4(x1v[c], x1v[c + 1], x1v[c + 2], x1v[c + 3]);
           *reinterpret_cast<float4*>(Xs + ((size_t)((sl * 16 + c) / 4) * kRows + r) * 16) = t;
-          *reinterpret_cast<float4*>(Ks + (size_t)r * LD + sl * 16 + c) = t;
+          rm_st<CH>(Ks, r, sl * 4 + c / 4, t);
         }
       }
     }
@@ -349,13 +441,18 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
       if (umma::elect_one()) issue_gemm<false>(tmem, Xs, Wa, HD, E, bar);
       __syncwarp();
     }
-    copy_out<E>(Qs, LD, a.z1, row0, nrows, E, 0, tid);
-    copy_out<E>(Ks, LD, a.x1, row0, nrows, E, 0, tid);
+    if (tid == 0) {
+      store_tile<E>(&tm.z1, Qs, 0, (int)row0);
+      store_tile<E>(&tm.x1, Ks, 0, (int)row0);
+      bulk_commit();
+    }
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
-    __syncthreads();               // staging tiles consumed: Hs (aliases Ks / Vs) may be written
-#pragma unroll 1
-    for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: A operand + staged copy to HBM
+    if (tid == 0) bulk_wait_read0();
+    __syncthreads();               // staging tiles consumed, the x1 slab consumed: Hs (over Ks / Vs), Qs and Xs may be written
+    static_assert(HD / E == 2, "two hidden chunks: staged in Qs and Xs");
+#pragma unroll
+    for (int chunk = 0; chunk < HD / E; ++chunk) {          // E hidden columns at a time: A operand + staging tile
       if (act) {
         const int c0 = chunk * E + sl * 16;
         float v[16];
@@ -367,25 +464,29 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
                                  fmaxf(v[c + 3] + bb.w, 0.f));
           if (!live) t = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(Hs + ((size_t)((c0 + c) / 4) * kRows + r) * 16) = t;
-          *reinterpret_cast<float4*>(Qs + (size_t)r * LD + sl * 16 + c) = t;
+          rm_st<CH>(chunk == 0 ? Qs : Xs, r, sl * 4 + c / 4, t);
         }
       }
-      __syncthreads();
-      copy_out<E>(Qs, LD, a.hact, row0, nrows, HD, chunk * E, tid);
-      __syncthreads();
     }
-    umma::fence_before_sync();
     umma::fence_proxy_async();
+    umma::fence_before_sync();
     __syncthreads();
-    // ---- x2 = LN2(x1 + h W_2^T + b)
+    // ---- x2 = LN2(x1 + h W_2^T + b) ; relu(h) to HBM meanwhile
     if (warp == 4) {
       umma::mbar_wait(lbar + 2, lpar);   // W_2 has landed
       umma::fence_after_sync();
       if (umma::elect_one()) issue_gemm<false>(tmem, Hs, Wb, E, HD, bar);
       __syncwarp();
     }
+    if (tid == 0) {
+      store_tile<E>(&tm.hact, Qs, 0, (int)row0);
+      store_tile<E>(&tm.hact, Xs, E, (int)row0);
+      bulk_commit();
+    }
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
+    if (tid == 0) bulk_wait_read0();
+    __syncthreads();               // Qs is free for z2; Ks (under Hs) has been consumed by the MMA
     {
       float z[16];
       if (act) {
@@ -396,27 +497,28 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
           z[c] += x1v[c] + bb.x; z[c + 1] += x1v[c + 1] + bb.y; z[c + 2] += x1v[c + 2] + bb.z; z[c + 3] += x1v[c + 3] + bb.w;
         }
 #pragma unroll
-        for (int c = 0; c < 16; c += 4)
-          *reinterpret_cast<float4*>(Qs + (size_t)r * LD + sl * 16 + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
+        for (int c = 0; c < 16; c += 4) rm_st<CH>(Qs, r, sl * 4 + c / 4, make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]));
       }
       umma::fence_before_sync();
       float mean, rstd;
       layernorm_sliced<E>(z, act, r, sl, red, a.g2, a.be2, a.ln_eps, mean, rstd);
       if (act) {
         if (live && sl == 0) { a.m2[row0 + r] = mean; a.r2[row0 + r] = rstd; }
-        // Ks aliases Hs, which the fc2 MMA has finished reading (its commit was waited for above)
 #pragma unroll
-        for (int c = 0; c < 16; c += 4)
-          *reinterpret_cast<float4*>(Ks + (size_t)r * LD + sl * 16 + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
+        for (int c = 0; c < 16; c += 4) rm_st<CH>(Ks, r, sl * 4 + c / 4, make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]));
       }
     }
-    __syncthreads();
-    copy_out<E>(Qs, LD, a.z2, row0, nrows, E, 0, tid);
-    copy_out<E>(Ks, LD, a.x2, row0, nrows, E, 0, tid);
+    umma::fence_proxy_async();
     umma::fence_before_sync();
-    __syncthreads();               // the next tile overwrites every buffer
+    __syncthreads();               // the next tile overwrites every buffer (its first shared-memory writes are TMA loads by thread 0)
+    if (tid == 0) {
+      store_tile<E>(&tm.z2, Qs, 0, (int)row0);
+      store_tile<E>(&tm.x2, Ks, 0, (int)row0);
+      bulk_commit();
+    }
     lpar ^= 1;
   }
+  if (tid == 0) bulk_wait0();
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc<256>(tmem);
@@ -430,22 +532,32 @@ int sm_count() {
 
 template <int E, int HD, int NH, int SMAX>
 int launch_fwd(const EncArgs& a, cudaStream_t st) {
-  constexpr int LD = E + 4;
   constexpr int WA = (3 * E * E > E * HD ? 3 * E * E : E * HD) * 4, WB = (E * E > HD * E ? E * E : HD * E) * 4;
-  const int smem = E * 512 + WA + WB + 3 * kRows * LD * 4 + kRows * 4 * 4 + 64;
+  const int smem = 4 * kRows * E * 4 + WA + WB + kRows * 4 * 4 + 64;
   auto kern = encoder_layer_fwd_kernel<E, HD, NH, SMAX>;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   const double T = (double)a.B * a.S;
   EncMaps tm;
   {
-    int rc = make_f32_tensor_map_sw(&tm.x, a.x, E, (long long)a.B * a.S, kRows);
+    const long long rows = (long long)a.B * a.S;
+    const int own = a.spt * a.S;
+    int rc = make_f32_tensor_map_sw(&tm.x, a.x, E, rows, kRows);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.wq, a.wq, E, E, E);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.wk, a.wk, E, E, E);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.wv, a.wv, E, E, E);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.wo, a.wo, E, E, E);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.w1, a.w1, E, HD, HD);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.w2, a.w2, HD, E, E);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.q, a.q, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.k, a.k, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.v, a.v, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.ctx, a.ctx, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.z1, a.z1, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.x1, a.x1, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.z2, a.z2, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.x2, a.x2, E, rows, own);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.hact, a.hact, HD, rows, own);
     if (rc) return rc;
   }
   MivitProfScope prof("encoder_layer_fwd", 2.0 * T * (4.0 * E * E + 2.0 * E * HD) + 4.0 * a.B * NH * (double)a.S * a.S * (E / NH), st);
