@@ -167,9 +167,9 @@ __device__ __forceinline__ float tile_el(const uint8_t* tile, int row, int col) 
   return *reinterpret_cast<const float*>(tile + rm_off<CH>(row, col >> 2) + ((col & 3) << 2));
 }
 // Attention backward of ONE (sequence, head) on one warp with tensor-core MMAs (S <= 32, head dim 16).  Q / K / V / dctx are
-// the swizzled tiles Qt / Kt / Vt / Gt (rows rb .. rb + S of the CTA's tile, columns hc .. hc + 16); Ls / Dl = this warp's row
-// log-sum-exps and D_i = dctx_i . ctx_i (entries >= S are 0).  Two orientations, each in two halves of 16 rows:
-//   rows = queries i:  s = (scale Q) K^T (3xTF32), dP = G V^T  ->  dS = P (dP - D)  ->  dQ = scale dS K
+// the swizzled tiles Qt / Kt / Vt / Gt (rows rb .. rb + S of the CTA's tile, columns hc .. hc + 16); Ls = this warp's row
+// log-sum-exps (base 2), Dl = scratch for D_i = dctx_i . ctx_i.  Two orientations, each in two halves of 16 rows:
+//   rows = queries i:  s = (scale Q) K^T (3xTF32), dP = G V^T  ->  D_i = sum_j P dP, dS = P (dP - D)  ->  dQ = scale dS K
 //   rows = keys j:     s^T = (scale K) Q^T,        dP^T = V G^T ->  P^T, dS^T        ->  dV = P^T G,  dK = scale dS^T Q
 // The C fragments of the first stage are the A fragments of the second with the reduction index permuted inside each group of 8
 // (slot tig <-> token 2 tig, slot tig + 4 <-> token 2 tig + 1); the B fragments of the second stage are loaded with the same
@@ -177,7 +177,7 @@ __device__ __forceinline__ float tile_el(const uint8_t* tile, int row, int col) 
 // CTA reads them back from L2 as K-major slabs for the q/k/v input-gradient GEMM).
 template <int E, int CH>
 __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8_t* Kt, const uint8_t* Vt, const uint8_t* Gt,
-                                                  const float* Ls, const float* Dl, int rb, int hc, int S, float scale, int lane,
+                                                  const float* Ls, float* Dl, int rb, int hc, int S, float scale, int lane,
                                                   float* __restrict__ gdq, float* __restrict__ gdk, float* __restrict__ gdv) {
   const int gid = lane >> 2, tig = lane & 3;
   constexpr float kLog2e = 1.4426950408889634f;   // P = 2^(s log2e - L log2e): Ls holds L log2e, the scaled operand carries log2e
@@ -208,9 +208,11 @@ __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8
         tf32_split(tile_el<CH>(A2, rb + r0, cb), a2h[ks][2], a2l[ks][2]);
         tf32_split(tile_el<CH>(A2, rb + r1, cb), a2h[ks][3], a2l[ks][3]);
       }
-      // orientation 0: L, D belong to the rows; orientation 1: to the columns
-      const float Lr0 = Ls[r0], Lr1 = Ls[r1], Dr0 = Dl[r0], Dr1 = Dl[r1];
-      uint32_t pa[4][4], da[4][4];     // second-stage A fragments: P (orientation 1 only) and dS, one k-step per first-stage n-tile
+      // orientation 0: L belongs to the rows; orientation 1: L and D to the columns.  D_i = dctx_i . ctx_i = sum_j P_ij dP_ij is
+      // taken from the fragments of orientation 0 (a row lives in the four lanes of a quad) instead of re-reading ctx from HBM.
+      const float Lr0 = Ls[r0], Lr1 = Ls[r1];
+      float pv[4][4], dv[4][4];        // P and dP (then dS) of this lane's 2 rows x 8 columns
+      float Dr0 = 0.f, Dr1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int cr = rb + nt * 8 + gid;                            // row of the B-operand tiles
@@ -223,31 +225,58 @@ __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8
           tf32_split(tile_el<CH>(B2, cr, ca), b2h[ks][0], b2l[ks][0]);
           tf32_split(tile_el<CH>(B2, cr, ca + 4), b2h[ks][1], b2l[ks][1]);
         }
-        float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+        dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           mma_16x8x8(sc, al[ks], bh[ks]);
           mma_16x8x8(sc, ah[ks], bl[ks]);
           mma_16x8x8(sc, ah[ks], bh[ks]);
-          mma_16x8x8(dp, a2l[ks], b2h[ks]);
-          mma_16x8x8(dp, a2h[ks], b2l[ks]);
-          mma_16x8x8(dp, a2h[ks], b2h[ks]);
+          mma_16x8x8(dv[nt], a2l[ks], b2h[ks]);
+          mma_16x8x8(dv[nt], a2h[ks], b2l[ks]);
+          mma_16x8x8(dv[nt], a2h[ks], b2h[ks]);
         }
         const int c0 = nt * 8 + 2 * tig, c1 = c0 + 1;               // this lane's two columns
-        float L00, L01, L10, L11, D00, D01, D10, D11;               // (row r0 | r1, column c0 | c1)
+        float L00, L01, L10, L11;                                   // (row r0 | r1, column c0 | c1)
         if (orient == 0) {
-          L00 = L01 = Lr0; L10 = L11 = Lr1; D00 = D01 = Dr0; D10 = D11 = Dr1;
+          L00 = L01 = Lr0; L10 = L11 = Lr1;
         } else {
-          L00 = L10 = Ls[c0]; L01 = L11 = Ls[c1]; D00 = D10 = Dl[c0]; D01 = D11 = Dl[c1];
+          L00 = L10 = Ls[c0]; L01 = L11 = Ls[c1];
         }
         const bool v00 = r0 < S && c0 < S, v01 = r0 < S && c1 < S, v10 = r1 < S && c0 < S, v11 = r1 < S && c1 < S;
-        const float p00 = v00 ? exp2f(sc[0] - L00) : 0.f, p01 = v01 ? exp2f(sc[1] - L01) : 0.f;
-        const float p10 = v10 ? exp2f(sc[2] - L10) : 0.f, p11 = v11 ? exp2f(sc[3] - L11) : 0.f;
-        const float d00 = v00 ? p00 * (dp[0] - D00) : 0.f, d01 = v01 ? p01 * (dp[1] - D01) : 0.f;
-        const float d10 = v10 ? p10 * (dp[2] - D10) : 0.f, d11 = v11 ? p11 * (dp[3] - D11) : 0.f;
+        pv[nt][0] = v00 ? exp2f(sc[0] - L00) : 0.f; pv[nt][1] = v01 ? exp2f(sc[1] - L01) : 0.f;
+        pv[nt][2] = v10 ? exp2f(sc[2] - L10) : 0.f; pv[nt][3] = v11 ? exp2f(sc[3] - L11) : 0.f;
+        if (!v00) dv[nt][0] = 0.f;
+        if (!v01) dv[nt][1] = 0.f;
+        if (!v10) dv[nt][2] = 0.f;
+        if (!v11) dv[nt][3] = 0.f;
+        Dr0 = fmaf(pv[nt][0], dv[nt][0], fmaf(pv[nt][1], dv[nt][1], Dr0));
+        Dr1 = fmaf(pv[nt][2], dv[nt][2], fmaf(pv[nt][3], dv[nt][3], Dr1));
+      }
+      if (orient == 0) {
+        Dr0 += __shfl_xor_sync(0xffffffffu, Dr0, 1); Dr0 += __shfl_xor_sync(0xffffffffu, Dr0, 2);
+        Dr1 += __shfl_xor_sync(0xffffffffu, Dr1, 1); Dr1 += __shfl_xor_sync(0xffffffffu, Dr1, 2);
+        if (tig == 0) { Dl[r0] = Dr0; Dl[r1] = Dr1; }   // for orientation 1 (rows >= S: masked there)
+      }
+      uint32_t pa[4][4], da[4][4];     // second-stage A fragments: P (orientation 1 only) and dS, one k-step per first-stage n-tile
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c0 = nt * 8 + 2 * tig, c1 = c0 + 1;
+        float D00, D01, D10, D11;
+        if (orient == 0) {
+          D00 = D01 = Dr0; D10 = D11 = Dr1;
+        } else {
+          D00 = D10 = Dl[c0]; D01 = D11 = Dl[c1];
+        }
+        // (masked entries: P = 0 and dP was zeroed above, but D of a masked row / column may be anything: select, not multiply)
+        const bool v00 = r0 < S && c0 < S, v01 = r0 < S && c1 < S, v10 = r1 < S && c0 < S, v11 = r1 < S && c1 < S;
+        const float d00 = v00 ? pv[nt][0] * (dv[nt][0] - D00) : 0.f, d01 = v01 ? pv[nt][1] * (dv[nt][1] - D01) : 0.f;
+        const float d10 = v10 ? pv[nt][2] * (dv[nt][2] - D10) : 0.f, d11 = v11 ? pv[nt][3] * (dv[nt][3] - D11) : 0.f;
         // A fragment of k-step nt: slot tig <- column c0, slot tig + 4 <- column c1
         da[nt][0] = tf32_rna(d00); da[nt][1] = tf32_rna(d10); da[nt][2] = tf32_rna(d01); da[nt][3] = tf32_rna(d11);
-        if (orient == 1) { pa[nt][0] = tf32_rna(p00); pa[nt][1] = tf32_rna(p10); pa[nt][2] = tf32_rna(p01); pa[nt][3] = tf32_rna(p11); }
+        if (orient == 1) {
+          pa[nt][0] = tf32_rna(pv[nt][0]); pa[nt][1] = tf32_rna(pv[nt][2]); pa[nt][2] = tf32_rna(pv[nt][1]); pa[nt][3] = tf32_rna(pv[nt][3]);
+        }
       }
       float o1[2][4] = {}, o2[2][4] = {};     // orientation 0: o1 = dQ;  orientation 1: o1 = dK, o2 = dV
       const uint8_t* S1 = orient == 0 ? Kt : Qt;
@@ -279,6 +308,7 @@ __device__ __forceinline__ void attention_bwd_mma(const uint8_t* Qt, const uint8
         }
       }
     }
+    __syncwarp();   // orientation 1 reads the D_i orientation 0 wrote
   }
 }
 
@@ -589,23 +619,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       float* Dl = Ls + SMAX;
       for (int pair = warp; pair < nseq * NH; pair += kThreads / 32) {
         const int sq = pair / NH, h = pair % NH, rb = sq * S;
-        {   // D_i = dctx_i . ctx_i and the row log-sum-exp, lane = query row
-          float di = 0.f, li = 0.f;
-          if (lane < S) {
-            float gi[D];
-            ld_head<CH, D>(R3, rb + lane, h * (D / 4), gi, 1.f);
-            const float4* op = reinterpret_cast<const float4*>(a.ctx + (row0 + rb + lane) * E + h * D);
-#pragma unroll
-            for (int c = 0; c < D / 4; ++c) {
-              const float4 o4 = __ldg(op + c);
-              di = fmaf(gi[4 * c], o4.x, di); di = fmaf(gi[4 * c + 1], o4.y, di);
-              di = fmaf(gi[4 * c + 2], o4.z, di); di = fmaf(gi[4 * c + 3], o4.w, di);
-            }
-            li = __ldg(a.lse + ((size_t)(seq0 + sq) * NH + h) * S + lane);
-          }
-          Ls[lane] = li * 1.4426950408889634f;   // attention_bwd_mma works in base 2
-          Dl[lane] = di;
-        }
+        Ls[lane] = lane < S ? __ldg(a.lse + ((size_t)(seq0 + sq) * NH + h) * S + lane) * 1.4426950408889634f : 0.f;   // base 2
+        Dl[lane] = 0.f;
         __syncwarp();
         attention_bwd_mma<E, CH>(R0, R1, R2, R3, Ls, Dl, rb, h * D, S, scale, lane, a.dq + row0 * E, a.dk + row0 * E, a.dv + row0 * E);
         __syncwarp();

@@ -583,6 +583,8 @@ def test_forward_and_train_step_from_trajectories(golden_dir, kind, P, E):
     ("linear", 64, 4, 128, 2, 9, 60, 12, False, True),         # S = 61: two sequences per tile, two key passes per lane
     ("cnn", 32, 2, 64, 3, 9, 20, 30, True, False),             # _s size: E = 32, mean pooling, S = 20 (six sequences per tile)
     ("linear", 64, 4, 128, 2, 9, 63, 9, False, True),          # S = 64: the largest fused shape, two sequences per tile
+    ("linear", 64, 4, 128, 2, 9, 30, 18, True, True),          # S = 31, 18 sequences: the last tile holds 2 of 4 sequences (TMA boxes clipped)
+    ("cnn", 32, 2, 64, 2, 9, 12, 45, False, True),             # S = 13: 9 sequences per tile -> several (sequence, head) pairs per warp
 ])
 def test_fused_encoder_layer_matches_unfused_path_and_oracle(emb, E, H, HD, Lyr, P, Fr, B, pos, reg):
     """csrc/encoder_fused.cu / encoder_fused_bwd.cu: the persistent per-layer kernels (tf32 tcgen05 GEMMs chained through shared
