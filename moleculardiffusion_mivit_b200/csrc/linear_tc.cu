@@ -14,6 +14,7 @@
 // These GEMMs are HBM-bound (K, N <= 256 on 30k+ tokens): the point of the tensor path is to get the
 // math out of the way so the kernel streams at memory speed.
 #include "common.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 #include "vit.h"
 
@@ -258,8 +259,11 @@ linear_tc_kernel(const __grid_constant__ LinBatch batch, int M, int K, int N, in
 
 // ------------------------------------------------------------------ weight gradient -------------
 // warps 0-3 producers + final flush, warp 4 MMA issuer, warps 5-7 producers.
+// tmA / tmB (optional): fp32 tensor maps of dY / X with 32-byte-atom 128-byte swizzle (tma.cuh: make_f32_tensor_map_sw32) -- one
+// elected thread then stages both operands with TMA (N / 32 + K / 32 boxes of 128 rows per stage) instead of seven warps of cp.async.
 __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ dW,
-                                           float* __restrict__ db, int M, int N, int K, int s_begin, int s_end, int buf_bytes) {
+                                           float* __restrict__ db, int M, int N, int K, int s_begin, int s_end, int buf_bytes,
+                                           const CUtensorMap* tmA = nullptr, const CUtensorMap* tmB = nullptr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int nch = N / 4, kch = K / 4;
@@ -272,11 +276,12 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, const f
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      umma::mbar_init(full + i, 7);
+      umma::mbar_init(full + i, tmA != nullptr ? 1 : 7);
       umma::mbar_init(empty + i, 1);
     }
     umma::mbar_init(done, 1);
     umma::mbar_fence_init();
+    if (tmA != nullptr) { tma::prefetch_map(tmA); tma::prefetch_map(tmB); }
   }
   if (warp == 0) tmem_alloc_n(tmem_slot, K + 32);
   // bias gradient for free: a 33rd..-th column group of the B operand whose first column is all ones makes accumulator
@@ -295,7 +300,21 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, const f
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp != 4) {
+  if (tmA != nullptr) {
+    if (tid == 0) {   // TMA producer: rows past M read as zeros
+      int k = 0;
+      for (int s = s_begin; s < s_end; ++s, ++k) {
+        const int b = k & 1;
+        umma::mbar_wait(empty + b, ((k >> 1) & 1) ^ 1);
+        uint8_t* aslab = b ? buf1 : buf0;
+        uint8_t* bslab = aslab + a_bytes;
+        tma::expect_tx(full + b, (uint32_t)((N + K) * kRows * 4));
+        for (int g = 0; g < N / 32; ++g) tma::load_tile(aslab + (size_t)g * kRows * 128, tmA, g * 32, s * kRows, full + b);
+        for (int g = 0; g < K / 32; ++g) tma::load_tile(bslab + (size_t)g * kRows * 128, tmB, g * 32, s * kRows, full + b);
+      }
+    }
+  }
+  if (warp != 4 && tmA == nullptr) {
     const int pt = (warp < 4 ? warp : warp - 1) * 32 + lane;
     int k = 0;
     for (int s = s_begin; s < s_end; ++s, ++k) {
@@ -322,7 +341,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, const f
       __syncwarp();
       if (lane == 0) arrive(full + b);
     }
-  } else {
+  }
+  if (warp == 4) {
     const uint32_t idesc = idesc_tf32(128, db != nullptr ? K + 32 : K, 1, 1);
     // MN-major operands (SW128_BASE32B atoms): 32-channel groups kRows*128 bytes apart, 4-row groups 512 bytes apart
     const uint64_t da_b[2] = {make_desc_mn32(umma::smem_u32(buf0), kRows * 128u), make_desc_mn32(umma::smem_u32(buf1), kRows * 128u)};
@@ -374,12 +394,16 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, const f
   if (warp == 0) tmem_dealloc_n(tmem, K + 32);
 }
 
+struct LinMaps {
+  CUtensorMap a[4], b[4];   // dY / X of each problem (make_f32_tensor_map_sw32, 128-row boxes)
+};
 __global__ void __launch_bounds__(256, 1)
-linear_wgrad_tc_kernel(const __grid_constant__ LinBatch batch /* A = dY, W = X, Y = dW, bias = db */, int M, int N, int K,
-                       int n_stages, int stages_per_cta, int buf_bytes) {
+linear_wgrad_tc_kernel(const __grid_constant__ LinBatch batch /* A = dY, W = X, Y = dW, bias = db */, const __grid_constant__ LinMaps tm,
+                       int M, int N, int K, int n_stages, int stages_per_cta, int buf_bytes) {
   const int s_begin = blockIdx.x * stages_per_cta;
   wgrad_body(pick3(batch.A, (int)blockIdx.y), pick3(batch.W, (int)blockIdx.y), pick3(batch.Y, (int)blockIdx.y),
-             const_cast<float*>(pick3(batch.bias, (int)blockIdx.y)), M, N, K, s_begin, min(n_stages, s_begin + stages_per_cta), buf_bytes);
+             const_cast<float*>(pick3(batch.bias, (int)blockIdx.y)), M, N, K, s_begin, min(n_stages, s_begin + stages_per_cta), buf_bytes,
+             &tm.a[blockIdx.y], &tm.b[blockIdx.y]);
 }
 
 // Several weight gradients of DIFFERENT shapes over the same M rows in one launch (the six nn.Linear layers of an encoder layer):
@@ -396,14 +420,19 @@ struct WgradMulti {
   int cta0[kMaxMulti + 1];
   int nb;
 };
-__global__ void __launch_bounds__(256, 1) linear_wgrad_multi_kernel(const __grid_constant__ WgradMulti mp, int M, int n_stages, int buf_bytes) {
+struct WgradMaps {
+  CUtensorMap a[kMaxMulti], b[kMaxMulti];   // dY / X of each problem (make_f32_tensor_map_sw32, 128-row boxes)
+};
+__global__ void __launch_bounds__(256, 1) linear_wgrad_multi_kernel(const __grid_constant__ WgradMulti mp, const __grid_constant__ WgradMaps tm,
+                                                                    int M, int n_stages, int buf_bytes) {
   int pidx = 0;
 #pragma unroll
   for (int i = 1; i < kMaxMulti; ++i)
     if (i < mp.nb && (int)blockIdx.x >= mp.cta0[i]) pidx = i;
   const int local = (int)blockIdx.x - mp.cta0[pidx];
   const int s_begin = local * mp.spc[pidx];
-  wgrad_body(mp.dY[pidx], mp.X[pidx], mp.dW[pidx], mp.db[pidx], M, mp.N[pidx], mp.K[pidx], s_begin, min(n_stages, s_begin + mp.spc[pidx]), buf_bytes);
+  wgrad_body(mp.dY[pidx], mp.X[pidx], mp.dW[pidx], mp.db[pidx], M, mp.N[pidx], mp.K[pidx], s_begin, min(n_stages, s_begin + mp.spc[pidx]), buf_bytes,
+             &tm.a[pidx], &tm.b[pidx]);
 }
 
 int sm_count() {
@@ -471,8 +500,15 @@ int linear_wgrad_tc_batched(int nb, const float* const* dY, const float* const* 
   int ctas = n_stages < sm_count() ? n_stages : sm_count();
   const int spc = (n_stages + ctas - 1) / ctas;
   ctas = (n_stages + spc - 1) / spc;
+  LinMaps tm;
+  for (int i = 0; i < nb; ++i) {
+    int rc = make_f32_tensor_map_sw32(&tm.a[i], dY[i], N, M, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw32(&tm.b[i], X[i], K, M, kRows);
+    if (rc) return rc;
+  }
+  for (int i = nb; i < 4; ++i) { tm.a[i] = tm.a[0]; tm.b[i] = tm.b[0]; }
   MivitProfScope prof("linear_tc_wgrad", 2.0 * M * K * N * nb, st);
-  linear_wgrad_tc_kernel<<<dim3(ctas, nb), 256, smem, st>>>(b, M, N, K, n_stages, spc, buf_bytes);
+  linear_wgrad_tc_kernel<<<dim3(ctas, nb), 256, smem, st>>>(b, tm, M, N, K, n_stages, spc, buf_bytes);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -525,8 +561,15 @@ int linear_wgrad_tc_multi(int nb, const float* const* dY, const float* const* X,
   for (int i = nb + 1; i <= kMaxMulti; ++i) mp.cta0[i] = used;
   const int smem = 2 * buf_bytes + 256;
   MIVIT_CUDA_CHECK(cudaFuncSetAttribute(linear_wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  WgradMaps tm;
+  for (int i = 0; i < nb; ++i) {
+    int rc = make_f32_tensor_map_sw32(&tm.a[i], dY[i], N[i], M, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw32(&tm.b[i], X[i], K[i], M, kRows);
+    if (rc) return rc;
+  }
+  for (int i = nb; i < kMaxMulti; ++i) { tm.a[i] = tm.a[0]; tm.b[i] = tm.b[0]; }
   MivitProfScope prof("linear_tc_wgrad", flops, st);
-  linear_wgrad_multi_kernel<<<used, 256, smem, st>>>(mp, M, n_stages, buf_bytes);
+  linear_wgrad_multi_kernel<<<used, 256, smem, st>>>(mp, tm, M, n_stages, buf_bytes);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;

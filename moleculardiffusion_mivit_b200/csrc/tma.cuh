@@ -83,6 +83,26 @@ static inline int make_f32_tensor_map_sw(CUtensorMap* tm, const void* base, int 
   return MIVIT_OK;
 }
 
+// The same for MN-major tf32 operands (rows = reduction index, 32 floats of the M / N dimension per 128-byte line):
+// SWIZZLE_128B with 32-byte atoms = the UMMA layout SWIZZLE_128B_BASE32B, whose 32-byte chunks are XOR-ed with the row (the
+// address map linear_tc.cu's mn_off() reproduces when it fills shared memory with cp.async).
+static inline int make_f32_tensor_map_sw32(CUtensorMap* tm, const void* base, int cols, long long rows, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  mivit_tensor_map_encode_fn encode = mivit_tensor_map_encoder();
+  if (encode == nullptr) return MIVIT_ERR_CUDA;
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mivit_set_error("cuTensorMapEncodeTiled (128B swizzle, 32-byte atoms) failed (%d) for fp32 cols=%d rows=%lld box=%d", (int)r, cols, rows, box_rows);
+    return MIVIT_ERR_CUDA;
+  }
+  return MIVIT_OK;
+}
+
 namespace tma {
 
 // UMMA shared-memory descriptor for a swizzled row tile (pitch 128 -> SWIZZLE_128B, pitch 64 -> SWIZZLE_64B)
