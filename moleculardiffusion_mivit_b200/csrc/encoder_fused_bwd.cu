@@ -66,6 +66,7 @@ struct BwdMaps {   // fp32 SWIZZLE_128B tensor maps (tma.cuh: make_f32_tensor_ma
   CUtensorMap wqkvt;         // [E, 3E],  E-row boxes
   CUtensorMap dq, dk, dv;    // [T, E],   128-row boxes (read back as A slabs, S <= 32)
   CUtensorMap q, k, v;       // [T, E],   128-row boxes (the attention's row-major tiles)
+  CUtensorMap dy, z2;        // [T, E],   128-row boxes (inputs of LayerNorm 2', prefetched for the next tile)
   CUtensorMap dz2, dh2, dx;  // stores: [T, E] / [T, HD] / [T, E], boxes of spt * S rows (the rows a tile owns)
 };
 
@@ -383,8 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
   float* lnacc = red + 2 * kRows * 4;                    // [LN1 | LN2][dgamma | dbeta][E]
   float* lsdl = lnacc + 4 * E;                           // [16 warps][L | D][SMAX]
   uint64_t* bar = reinterpret_cast<uint64_t*>(lsdl + 16 * 2 * SMAX);   // MMA completion
-  uint64_t* lbar = bar + 1;              // [6] TMA completion: W_2^T + W_o^T | W_1^T (once) | W_qkv^T | dq, dk, dv slabs | k, v | q
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 6);
+  uint64_t* lbar = bar + 1;              // [7] TMA completion: W_2^T + W_o^T | W_1^T (once) | W_qkv^T | dq, dk, dv slabs | k, v | q | dy, z2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 7);
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   const int qd = warp & 3, sl = warp >> 2;
   const int r = qd * 32 + lane;               // token row of this thread in every epilogue
@@ -393,7 +394,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
 
   if (tid == 0) {
     umma::mbar_init(bar, 1);
-    for (int i = 0; i < 6; ++i) umma::mbar_init(lbar + i, 1);
+    for (int i = 0; i < 7; ++i) umma::mbar_init(lbar + i, 1);
+    tma::prefetch_map(&tm.dy); tma::prefetch_map(&tm.z2);
     umma::mbar_fence_init();
     tma::prefetch_map(&tm.q); tma::prefetch_map(&tm.k); tma::prefetch_map(&tm.v);
     tma::prefetch_map(&tm.dz2); tma::prefetch_map(&tm.dh2); tma::prefetch_map(&tm.dx);
@@ -420,6 +422,14 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       tma::load_tile(Wa + E * HD * 4 + (size_t)kb * E * 128, &tm.wot, kb * 32, 0, lbar);
     }
   };
+  auto load_in_first = [&](long long rows0) {   // dy -> R3 (the staging tile's place), z2 -> R1: both free between two tiles
+    tma::expect_tx(lbar + 6, (uint32_t)(2 * TILE));
+#pragma unroll
+    for (int kb = 0; kb < E / 32; ++kb) {
+      tma::load_tile(R3 + (size_t)kb * kRows * 128, &tm.dy, kb * 32, (int)rows0, lbar + 6);
+      tma::load_tile(R1 + (size_t)kb * kRows * 128, &tm.z2, kb * 32, (int)rows0, lbar + 6);
+    }
+  };
   if (tid == 0 && (int)blockIdx.x < a.n_tiles) {
     tma::expect_tx(lbar + 1, (uint32_t)(E * HD * 4));
 #pragma unroll
@@ -431,23 +441,27 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     const long long row0 = (long long)seq0 * S;
     const int nrows = nseq * S;
     const bool live = act && r < nrows;
-    if (!wa_ready && tid == 0) load_wa_first();
+    if (!wa_ready && tid == 0) {
+      load_wa_first();
+      load_in_first(row0);
+    }
     // ---- dz2 = LN2'(dy)
     float dz2v[16];
     {
       float dyv[16], zv[16];
       float m = 0.f, rs = 0.f;
       if (live) {
-        const float4* dp = reinterpret_cast<const float4*>(a.dy + (row0 + r) * E + sl * 16);
-        const float4* zp = reinterpret_cast<const float4*>(a.z2 + (row0 + r) * E + sl * 16);
+        m = __ldg(a.m2 + row0 + r);
+        rs = __ldg(a.r2 + row0 + r);
+      }
+      umma::mbar_wait(lbar + 6, lpar);   // dy and z2 tiles (TMA, requested during the previous tile)
+      if (live) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 d4 = dp[c], z4 = __ldg(zp + c);
+        for (int c = 0; c < 4; ++c) {   // this thread's own 64 bytes of both tiles (it overwrites exactly these with dz2 below)
+          const float4 d4 = rm_ld<CH>(R3, r, sl * 4 + c), z4 = rm_ld<CH>(R1, r, sl * 4 + c);
           dyv[4 * c] = d4.x; dyv[4 * c + 1] = d4.y; dyv[4 * c + 2] = d4.z; dyv[4 * c + 3] = d4.w;
           zv[4 * c] = z4.x; zv[4 * c + 1] = z4.y; zv[4 * c + 2] = z4.z; zv[4 * c + 3] = z4.w;
         }
-        m = __ldg(a.m2 + row0 + r);
-        rs = __ldg(a.r2 + row0 + r);
       } else {
 #pragma unroll
         for (int c = 0; c < 16; ++c) dyv[c] = zv[c] = 0.f;
@@ -773,7 +787,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     w1_waited = true;
     lpar ^= 1;
     wa_ready = tile + (int)gridDim.x < a.n_tiles;
-    if (wa_ready && tid == 0) load_wa_first();   // the next tile's first weights, in flight during this epilogue
+    if (wa_ready && tid == 0) {   // the next tile's first weights and LayerNorm inputs, in flight during this epilogue
+      load_wa_first();
+      load_in_first((long long)(tile + (int)gridDim.x) * a.spt * S);
+    }
     if (act) {
       float v[16];
       umma::tmem_ld16(trow + (uint32_t)(C4 + sl * 16), v);
@@ -867,6 +884,8 @@ int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     if (!rc) rc = make_f32_tensor_map_sw(&tm.q, a.q, E, rows, kRows);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.k, a.k, E, rows, kRows);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.v, a.v, E, rows, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.dy, a.dy, E, rows, kRows);
+    if (!rc) rc = make_f32_tensor_map_sw(&tm.z2, a.z2, E, rows, kRows);
     const int own = a.spt * a.S;   // rows a tile owns: the store boxes (the last tile is clipped at the end of the tensor)
     if (!rc) rc = make_f32_tensor_map_sw(&tm.dz2, a.dz2, E, rows, own);
     if (!rc) rc = make_f32_tensor_map_sw(&tm.dh2, a.dh2, HD, rows, own);
