@@ -387,6 +387,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
       store_tile<E>(&tm.ctx, Qs, 0, (int)row0);
       bulk_commit();
     }
+    float4 xres[4];                // the residual x of this thread's 16 columns (L2: the TMA load above brought the rows in): in flight during the MMA
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      xres[c] = (act && live) ? __ldg(reinterpret_cast<const float4*>(a.x + (row0 + r) * E + sl * 16) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     if (tid == 0) bulk_wait_read0();
@@ -402,10 +406,9 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_fwd_kernel(const __
       if (act) {
         umma::tmem_ld16(trow + (uint32_t)(sl * 16), v);
         if (live) {
-          const float4* xr = reinterpret_cast<const float4*>(a.x + (row0 + r) * E + sl * 16);
 #pragma unroll
           for (int c = 0; c < 16; c += 4) {
-            const float4 xx = __ldg(xr + c / 4), bb = __ldg(reinterpret_cast<const float4*>(a.bo + sl * 16 + c));
+            const float4 xx = xres[c / 4], bb = __ldg(reinterpret_cast<const float4*>(a.bo + sl * 16 + c));
             v[c] += xx.x + bb.x; v[c + 1] += xx.y + bb.y; v[c + 2] += xx.z + bb.z; v[c + 3] += xx.w + bb.w;
           }
         } else {

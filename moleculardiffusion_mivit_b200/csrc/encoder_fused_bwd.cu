@@ -782,6 +782,12 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
       }
       __syncwarp();
     }
+    // the residual dz1: this CTA wrote the rows above (L2); re-reading them frees 16 registers across the attention phase, and the
+    // loads are in flight during the last MMA chain
+    float4 zres[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      zres[c] = live ? __ldcg(reinterpret_cast<const float4*>(a.dz1 + (row0 + r) * E + sl * 16) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     umma::mbar_wait(bar, parity); parity ^= 1;
     umma::fence_after_sync();
     w1_waited = true;
@@ -794,11 +800,9 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_layer_bwd_kernel(const __
     if (act) {
       float v[16];
       umma::tmem_ld16(trow + (uint32_t)(C4 + sl * 16), v);
-      // the residual dz1: this CTA wrote the rows above (L2); re-reading them frees 16 registers across the attention phase
-      const float4* zp = reinterpret_cast<const float4*>(a.dz1 + (row0 + r) * E + sl * 16);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float4 z4 = live ? __ldcg(zp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 z4 = zres[c];
         rm_st<CH>(R2, r, sl * 4 + c, make_float4(v[4 * c] + z4.x, v[4 * c + 1] + z4.y, v[4 * c + 2] + z4.z, v[4 * c + 3] + z4.w));
       }
     }
