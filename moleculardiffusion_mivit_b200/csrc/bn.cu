@@ -3,6 +3,8 @@
 // (reference helpers/models.py:202-257), on the pitched-rows bf16 layout of conv_tc.cu.
 // All kernels here are HBM-bound element-wise / reduction passes: 16-byte vector accesses,
 // per-thread register partials, one atomic per channel per CTA.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "vit.h"
 
@@ -947,6 +949,11 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   const int ablocks = mivit_ceil_div(rows_pad, kApplyRowsPerCta);
+  if (dpooled != nullptr && raw_b != nullptr && bn_frames_supported(P, C) && getenv("MIVIT_NO_BN_FRAMES") == nullptr) {
+    // the pooled-gradient pair: one frame at a time, fed by TMA (bn_frames.cu)
+    MivitProfScope prof("bn_bwd_apply", (double)rows * P * P / ((double)(P + 1) * (P + 1)) * C * 2 * 4, st);
+    return bn_backward_pooled_frames(dpooled, raw_a, ss_a, coef_a, draw_a, raw_b, ss_b, coef_b, draw_b, rows, rows_pad, P, C, st);
+  }
   {
     MivitProfScope prof("bn_bwd_apply", (double)rows * P * P / ((double)(P + 1) * (P + 1)) * C * 2 * (2 * (raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
     BN_BWD_APPLY_LAUNCH(ablocks, up_a, up_b, dpooled, raw_a, ss_a, coef_a, draw_a, raw_b, ss_b, coef_b, draw_b, geo, rows_pad);

@@ -132,6 +132,11 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
                 const float* fsums /* with dpooled: per-frame sums of bn_apply_pool replace the reduction pass */,
                 int presummed /* sums already holds (sum g, sum g*raw_a) from conv_rows_dgrad_bnsums: no reduction pass */,
                 cudaStream_t st);
+// bn_frames.cu: the pooled-gradient BatchNorm pair one frame at a time (TMA-fed); same outputs as bn_backward's streaming pass
+bool bn_frames_supported(int P, int C);
+int bn_backward_pooled_frames(const float* dpooled, const __nv_bfloat16* raw_a, const float* ss_a, const float* coef_a,
+                              __nv_bfloat16* draw_a, const __nv_bfloat16* raw_b, const float* ss_b, const float* coef_b,
+                              __nv_bfloat16* draw_b, long long rows, long long rows_pad, int P, int C, cudaStream_t st);
 int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad,
                   int P, cudaStream_t st);
 int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st);
