@@ -838,6 +838,8 @@ int bn_apply_pool(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bflo
                   float* fsums, long long n_frames, int P, int C, cudaStream_t st) {
   if (n_frames <= 0) return MIVIT_OK;
   MivitProfScope prof("bn_apply_pool", (double)n_frames * P * P * C * 2 * 2, st);
+  if (bn_frames_supported(P, C) && getenv("MIVIT_NO_BN_FRAMES") == nullptr)   // one frame at a time, fed by TMA (bn_frames.cu)
+    return bn_apply_pool_frames(raw_a, ss_a, raw_b, ss_b, pooled, fsums, n_frames, P, C, st);
   long long grid = (n_frames + 7) / 8;   // one warp per frame, 8 warps per CTA, grid-stride over the frames
   if (grid > 148 * 2 * 8) grid = 148 * 2 * 8;
   BN_DISPATCH_C(C, (bn_apply_pool_kernel<CC><<<(unsigned)grid, 256, 0, st>>>(raw_a, ss_a, raw_b, ss_b, pooled, fsums, n_frames, P)));

@@ -176,11 +176,111 @@ bn_bwd_apply_pooled_frames_kernel(const __grid_constant__ CUtensorMap tmA, const
     for (long long i = rows * CH + tid; i < rows_pad * CH; i += kConsumers) { outA[i] = zero; outB[i] = zero; }
 }
 
+// pooled[f, c] = mean over the P x P pixels of relu(bn_a(raw_a) + bn_b(raw_b)) and, for the backward of this BatchNorm pair, the
+// per-frame masked sums fsums[f] = [n+ | sum mask * raw_a | sum mask * raw_b] (bn.cu: bn_apply_pool_kernel).
+template <int C>
+__global__ void __launch_bounds__(kConsumers + 32, 1)
+bn_apply_pool_frames_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const float* __restrict__ ss_a, const float* __restrict__ ss_b, float* __restrict__ pooled,
+                            float* __restrict__ fsums, int n_frames, int P) {
+  constexpr int CH = C / 8, NPL = kConsumers / CH, LPW = 32 / CH;   // pixel lanes per CTA / per warp
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int PP = P * P;
+  const int FB = PP * C * 2;
+  uint8_t* bufA = smem;
+  uint8_t* bufB = smem + 2 * FB;
+  float* red = reinterpret_cast<float*>(smem + 4 * FB);        // [8 warps][4 sums][C]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 8 * 4 * C);
+  uint64_t* empty = full + 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(full + i, 1);
+      umma::mbar_init(empty + i, kConsumers / 32);
+    }
+    umma::mbar_fence_init();
+    tma::prefetch_map(&tmA);
+    tma::prefetch_map(&tmB);
+  }
+  __syncthreads();
+  if (warp == kConsumers / 32) {
+    if (lane == 0) {
+      int k = 0;
+      for (int f = blockIdx.x; f < n_frames; f += gridDim.x, ++k) {
+        const int b = k & 1;
+        umma::mbar_wait(empty + b, ((k >> 1) & 1) ^ 1);
+        tma::expect_tx(full + b, (uint32_t)(2 * FB));
+        load_frame(bufA + (size_t)b * FB, &tmA, f, full + b);
+        load_frame(bufB + (size_t)b * FB, &tmB, f, full + b);
+      }
+    }
+    return;
+  }
+  const int ch = tid % CH, pl = tid / CH;
+  float sa[8], ha[8], sb[8], hb[8];
+  load8f(ss_a + ch * 8, sa); load8f(ss_a + C + ch * 8, ha);
+  load8f(ss_b + ch * 8, sb); load8f(ss_b + C + ch * 8, hb);
+  const float inv_pp = 1.0f / (float)PP;
+  int k = 0;
+  for (int f = blockIdx.x; f < n_frames; f += gridDim.x, ++k) {
+    const int b = k & 1;
+    umma::mbar_wait(full + b, (k >> 1) & 1);
+    const uint4* fa = reinterpret_cast<const uint4*>(bufA + (size_t)b * FB);
+    const uint4* fb = reinterpret_cast<const uint4*>(bufB + (size_t)b * FB);
+    float acc[8] = {}, cnt[8] = {}, ma[8] = {}, mb[8] = {};
+    for (int p = pl; p < PP; p += NPL) {
+      const uint4 ua = fa[p * CH + ch], ub = fb[p * CH + ch];
+      float a[8], bb[8];
+      unpack8(ua, a);
+      unpack8(ub, bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float pre = fmaf(a[i], sa[i], ha[i]);                 // == bn.cu bn_pre<true>: the backward recomputes this mask
+        pre += fmaf(bb[i], sb[i], hb[i]);
+        const float on = pre > 0.f ? 1.f : 0.f;
+        acc[i] = fmaf(on, pre, acc[i]);
+        cnt[i] += on;
+        ma[i] = fmaf(on, a[i], ma[i]);
+        mb[i] = fmaf(on, bb[i], mb[i]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) arrive(empty + b);     // this warp is done with the buffer
+    // pixel lanes of a warp, then the 8 warps through shared memory
+#pragma unroll
+    for (int o = CH; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        cnt[i] += __shfl_xor_sync(0xffffffffu, cnt[i], o);
+        ma[i] += __shfl_xor_sync(0xffffffffu, ma[i], o);
+        mb[i] += __shfl_xor_sync(0xffffffffu, mb[i], o);
+      }
+    }
+    if (lane < CH) {
+      float* rw = red + (size_t)warp * 4 * C + ch * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { rw[i] = acc[i]; rw[C + i] = cnt[i]; rw[2 * C + i] = ma[i]; rw[3 * C + i] = mb[i]; }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = tid; i < 4 * C; i += kConsumers) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[(size_t)w * 4 * C + i];
+      const int q = i / C, c = i - q * C;
+      if (q == 0) pooled[(size_t)f * C + c] = t * inv_pp;
+      else if (fsums != nullptr) fsums[(size_t)f * 3 * C + (q - 1) * C + c] = t;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    (void)LPW;
+  }
+}
+
 }  // namespace
 
 bool bn_frames_supported(int P, int C) {
   if (C != 64 && C != 128) return false;
-  const size_t smem = (size_t)4 * P * P * C * 2 + 2 * C * 4 + 64;
+  const size_t smem = (size_t)4 * P * P * C * 2 + 8 * 4 * C * 4 + 64;   // the larger of the two kernels' footprints
   return smem <= 227 * 1024 && P * P >= kConsumers / (C / 8) && P >= 1;
 }
 
@@ -207,6 +307,33 @@ int bn_backward_pooled_frames(const float* dpooled, const __nv_bfloat16* raw_a, 
     auto kern = bn_bwd_apply_pooled_frames_kernel<64>;
     MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, kConsumers + 32, smem, st>>>(tmA, tmB, dpooled, ss_a, coef_a, draw_a, ss_b, coef_b, draw_b, (int)n_frames, P, rows, rows_pad);
+  }
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+int bn_apply_pool_frames(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b, float* pooled,
+                         float* fsums, long long n_frames, int P, int C, cudaStream_t st) {
+  MIVIT_CHECK_ARG(bn_frames_supported(P, C), "frame-at-a-time BatchNorm + pool: unsupported shape");
+  MIVIT_CHECK_ARG(n_frames < (1ll << 31), "too many frames for one launch (%lld)", n_frames);
+  CUtensorMap tmA, tmB;
+  int rc = make_frame_map(&tmA, raw_a, C, P, n_frames);
+  if (!rc) rc = make_frame_map(&tmB, raw_b, C, P, n_frames);
+  if (rc) return rc;
+  const int smem = 4 * P * P * C * 2 + 8 * 4 * C * 4 + 64;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = (int)(n_frames < sms ? n_frames : sms);
+  if (grid <= 0) return MIVIT_OK;
+  if (C == 128) {
+    auto kern = bn_apply_pool_frames_kernel<128>;
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kConsumers + 32, smem, st>>>(tmA, tmB, ss_a, ss_b, pooled, fsums, (int)n_frames, P);
+  } else {
+    auto kern = bn_apply_pool_frames_kernel<64>;
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kConsumers + 32, smem, st>>>(tmA, tmB, ss_a, ss_b, pooled, fsums, (int)n_frames, P);
   }
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();

@@ -137,6 +137,8 @@ bool bn_frames_supported(int P, int C);
 int bn_backward_pooled_frames(const float* dpooled, const __nv_bfloat16* raw_a, const float* ss_a, const float* coef_a,
                               __nv_bfloat16* draw_a, const __nv_bfloat16* raw_b, const float* ss_b, const float* coef_b,
                               __nv_bfloat16* draw_b, long long rows, long long rows_pad, int P, int C, cudaStream_t st);
+int bn_apply_pool_frames(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b, float* pooled,
+                         float* fsums, long long n_frames, int P, int C, cudaStream_t st);
 int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad,
                   int P, cudaStream_t st);
 int conv0_wgrad(const float* frames, const __nv_bfloat16* draw0, float* dW0, long long rows, int P, cudaStream_t st);
