@@ -930,9 +930,16 @@ int bn_backward(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const floa
     MIVIT_LAUNCH_CHECK();
   } else {
     MivitProfScope prof("bn_bwd_reduce", (double)rows * P * P / ((double)(P + 1) * (P + 1)) * C * 2 * ((raw_b ? 2 : 1) + (dpooled ? 0 : up_b ? 2 : 1)), st);
-    BN_BWD_REDUCE_LAUNCH(blocks, up_a, up_b, dpooled, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, geo, rpb);
-    mivit_count_launch();
-    MIVIT_LAUNCH_CHECK();
+    const int n_streams = (raw_b ? 2 : 1) + (up_b ? 2 : 1);
+    if (dpooled == nullptr && up_a != nullptr && bn_reduce_frames_supported(P, C, n_streams) && getenv("MIVIT_NO_BN_FRAMES") == nullptr) {
+      // whole frames per stage, fed by TMA (bn_frames.cu)
+      const int rc = bn_backward_reduce_frames(up_a, up_b, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, rows, P, C, st);
+      if (rc) return rc;
+    } else {
+      BN_BWD_REDUCE_LAUNCH(blocks, up_a, up_b, dpooled, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, geo, rpb);
+      mivit_count_launch();
+      MIVIT_LAUNCH_CHECK();
+    }
   }
   // sums -> coefficient form + parameter gradients (C threads), then the streaming pass
   float* coef_a = sums + 3 * C;

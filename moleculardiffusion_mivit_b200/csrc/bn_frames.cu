@@ -276,6 +276,141 @@ bn_apply_pool_frames_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   }
 }
 
+// Reduction pass of a BatchNorm backward (bn.cu: bn_bwd_reduce_kernel<C, UP, DUAL>):
+//   sums[0][c] += sum m g,  sums[1][c] += sum m g xhat_a,  (DUAL) sums[2][c] += sum m g xhat_b,
+//   g = up_a (+ up_b),  m = 1[bn_a(raw_a) (+ bn_b(raw_b)) > 0],  xhat = (raw - mean) * invstd.
+// FPS frames per stage ({C, P, P, FPS} boxes; frames past the end read as zeros and contribute nothing).
+template <int C, int UP, bool DUAL>
+__global__ void __launch_bounds__(kConsumers + 32, 1)
+bn_bwd_reduce_frames_kernel(const __grid_constant__ CUtensorMap tmRa, const __grid_constant__ CUtensorMap tmRb,
+                            const __grid_constant__ CUtensorMap tmUa, const __grid_constant__ CUtensorMap tmUb,
+                            const float* __restrict__ ss_a, const float* __restrict__ mi_a, const float* __restrict__ ss_b,
+                            const float* __restrict__ mi_b, float* __restrict__ sums, int n_stages, int P, int fps) {
+  constexpr int CH = C / 8, NPL = kConsumers / CH;
+  constexpr int NS = (DUAL ? 2 : 1) + UP;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int SP = fps * P * P;                                   // pixels per stage
+  const int TX = SP * C * 2;                                    // bytes of one tensor's stage
+  const int TB = (TX + 127) & ~127;                             // its slot (TMA destinations are 128-byte aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)2 * NS * TB);
+  uint64_t* empty = full + 2;
+  float* red = reinterpret_cast<float*>(empty + 2);             // [3][8 warps][C]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(full + i, 1);
+      umma::mbar_init(empty + i, kConsumers / 32);
+    }
+    umma::mbar_fence_init();
+    tma::prefetch_map(&tmRa);
+    tma::prefetch_map(&tmUa);
+    if (DUAL) tma::prefetch_map(&tmRb);
+    if (UP == 2) tma::prefetch_map(&tmUb);
+  }
+  __syncthreads();
+  if (warp == kConsumers / 32) {
+    if (lane == 0) {
+      int k = 0;
+      for (int s = blockIdx.x; s < n_stages; s += gridDim.x, ++k) {
+        const int b = k & 1;
+        umma::mbar_wait(empty + b, ((k >> 1) & 1) ^ 1);
+        uint8_t* buf = smem + (size_t)b * NS * TB;
+        tma::expect_tx(full + b, (uint32_t)(NS * TX));
+        load_frame(buf, &tmRa, s * fps, full + b);
+        load_frame(buf + TB, &tmUa, s * fps, full + b);
+        if (DUAL) load_frame(buf + 2 * TB, &tmRb, s * fps, full + b);
+        if (UP == 2) load_frame(buf + (DUAL ? 3 : 2) * TB, &tmUb, s * fps, full + b);
+      }
+    }
+    return;
+  }
+  const int ch = tid % CH, pl = tid / CH;
+  float sa[8], ha[8], sb[8], hb[8];
+  load8f(ss_a + ch * 8, sa); load8f(ss_a + C + ch * 8, ha);
+  if (DUAL) { load8f(ss_b + ch * 8, sb); load8f(ss_b + C + ch * 8, hb); }
+  float s0[8] = {}, s1[8] = {}, s2[8] = {};   // sum g*x is accumulated and turned into sum g*xhat once at the end
+  int k = 0;
+  for (int s = blockIdx.x; s < n_stages; s += gridDim.x, ++k) {
+    const int b = k & 1;
+    umma::mbar_wait(full + b, (k >> 1) & 1);
+    const uint8_t* buf = smem + (size_t)b * NS * TB;
+    const uint4* ra = reinterpret_cast<const uint4*>(buf);
+    const uint4* ua = reinterpret_cast<const uint4*>(buf + TB);
+    const uint4* rb = reinterpret_cast<const uint4*>(buf + 2 * TB);
+    const uint4* ub = reinterpret_cast<const uint4*>(buf + (DUAL ? 3 : 2) * TB);
+    for (int p = pl; p < SP; p += NPL) {
+      float a[8], bb[8], g[8];
+      unpack8(ra[p * CH + ch], a);
+      unpack8(ua[p * CH + ch], g);
+      if (DUAL) unpack8(rb[p * CH + ch], bb);
+      if (UP == 2) {
+        float g2[8];
+        unpack8(ub[p * CH + ch], g2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += g2[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float pre = fmaf(a[i], sa[i], ha[i]);                 // == bn.cu bn_pre
+        if (DUAL) pre += fmaf(bb[i], sb[i], hb[i]);
+        const float gi = pre > 0.f ? g[i] : 0.f;
+        s0[i] += gi;
+        s1[i] = fmaf(gi, a[i], s1[i]);
+        if (DUAL) s2[i] = fmaf(gi, bb[i], s2[i]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) arrive(empty + b);
+  }
+  {
+    float m[8], iv[8];
+    load8f(mi_a + ch * 8, m);
+    load8f(mi_a + C + ch * 8, iv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = (s1[i] - m[i] * s0[i]) * iv[i];
+    if (DUAL) {
+      load8f(mi_b + ch * 8, m);
+      load8f(mi_b + C + ch * 8, iv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s2[i] = (s2[i] - m[i] * s0[i]) * iv[i];
+    }
+  }
+  // pixel lanes of a warp (32 / CH of them), then the 8 warps through shared memory, one atomic per channel and CTA
+#pragma unroll
+  for (int o = CH; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+      if (DUAL) s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+    }
+  }
+  if (lane < CH) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[(0 * 8 + warp) * C + ch * 8 + i] = s0[i];
+      red[(1 * 8 + warp) * C + ch * 8 + i] = s1[i];
+      if (DUAL) red[(2 * 8 + warp) * C + ch * 8 + i] = s2[i];
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  for (int i = tid; i < (DUAL ? 3 : 2) * C; i += kConsumers) {
+    const int q = i / C, c = i - q * C;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[(q * 8 + w) * C + c];
+    atomicAdd(sums + q * C + c, t);
+  }
+}
+
+// frames per stage and shared memory of the reduction kernel for a given shape (0: does not fit)
+int reduce_frames_per_stage(int P, int C, int ns) {
+  const int frame_bytes = P * P * C * 2;
+  int fps = (86 * 1024) / (ns * frame_bytes);    // ~86 KB per stage, two stages
+  if (fps > 256) fps = 256;
+  return fps;
+}
+
 }  // namespace
 
 bool bn_frames_supported(int P, int C) {
@@ -338,4 +473,73 @@ int bn_apply_pool_frames(const __nv_bfloat16* raw_a, const float* ss_a, const __
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
+}
+
+bool bn_reduce_frames_supported(int P, int C, int ns) {
+  return (C == 32 || C == 64 || C == 128) && P >= 1 && reduce_frames_per_stage(P, C, ns) >= 1;
+}
+
+// make_frame_map with `fps` frames per box
+static int make_stage_map(CUtensorMap* tm, const void* row0, int C, int P, long long n_frames, int fps) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)(P + 1), (cuuint64_t)(P + 1), (cuuint64_t)n_frames};
+  const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)(P + 1) * C * 2, (cuuint64_t)(P + 1) * (P + 1) * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)P, (cuuint32_t)P, (cuuint32_t)fps};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  mivit_tensor_map_encode_fn encode = mivit_tensor_map_encoder();
+  if (encode == nullptr) return MIVIT_ERR_CUDA;
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(row0), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mivit_set_error("cuTensorMapEncodeTiled failed (%d) for the stage view C=%d P=%d frames=%lld x %d", (int)r, C, P, n_frames, fps);
+    return MIVIT_ERR_CUDA;
+  }
+  return MIVIT_OK;
+}
+
+template <int C, int UP, bool DUAL>
+static int launch_reduce_frames(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const __nv_bfloat16* raw_a, const float* ss_a,
+                                const float* mi_a, const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, float* sums,
+                                long long n_frames, int P, cudaStream_t st) {
+  constexpr int NS = (DUAL ? 2 : 1) + UP;
+  const int fps = reduce_frames_per_stage(P, C, NS);
+  CUtensorMap tmRa, tmRb, tmUa, tmUb;
+  int rc = make_stage_map(&tmRa, raw_a, C, P, n_frames, fps);
+  if (!rc) rc = make_stage_map(&tmUa, up_a, C, P, n_frames, fps);
+  tmRb = tmRa;
+  tmUb = tmUa;
+  if (!rc && DUAL) rc = make_stage_map(&tmRb, raw_b, C, P, n_frames, fps);
+  if (!rc && UP == 2) rc = make_stage_map(&tmUb, up_b, C, P, n_frames, fps);
+  if (rc) return rc;
+  const int n_stages = (int)((n_frames + fps - 1) / fps);
+  const int smem = 2 * NS * ((fps * P * P * C * 2 + 127) & ~127) + 4 * 8 + 3 * 8 * C * 4 + 64;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = n_stages < sms ? n_stages : sms;
+  if (grid <= 0) return MIVIT_OK;
+  auto kern = bn_bwd_reduce_frames_kernel<C, UP, DUAL>;
+  MIVIT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, kConsumers + 32, smem, st>>>(tmRa, tmRb, tmUa, tmUb, ss_a, mi_a, ss_b, mi_b, sums, n_stages, P, fps);
+  mivit_count_launch();
+  MIVIT_LAUNCH_CHECK();
+  return MIVIT_OK;
+}
+
+int bn_backward_reduce_frames(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const __nv_bfloat16* raw_a, const float* ss_a,
+                              const float* mi_a, const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, float* sums,
+                              long long rows, int P, int C, cudaStream_t st) {
+  const long long n_frames = rows / ((long long)(P + 1) * (P + 1));
+  MIVIT_CHECK_ARG(n_frames < (1ll << 31), "too many frames for one launch (%lld)", n_frames);
+  const bool dual = raw_b != nullptr, two = up_b != nullptr;
+#define RF(CC)                                                                                                                    \
+  if (C == CC) {                                                                                                                  \
+    if (dual && two) return launch_reduce_frames<CC, 2, true>(up_a, up_b, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, n_frames, P, st);   \
+    if (dual) return launch_reduce_frames<CC, 1, true>(up_a, up_b, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, n_frames, P, st);          \
+    if (two) return launch_reduce_frames<CC, 2, false>(up_a, up_b, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, n_frames, P, st);          \
+    return launch_reduce_frames<CC, 1, false>(up_a, up_b, raw_a, ss_a, mi_a, raw_b, ss_b, mi_b, sums, n_frames, P, st);                   \
+  }
+  RF(32) RF(64) RF(128)
+#undef RF
+  mivit_set_error("BatchNorm width %d not supported", C);
+  return MIVIT_ERR_INVALID;
 }

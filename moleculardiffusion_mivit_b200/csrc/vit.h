@@ -137,6 +137,10 @@ bool bn_frames_supported(int P, int C);
 int bn_backward_pooled_frames(const float* dpooled, const __nv_bfloat16* raw_a, const float* ss_a, const float* coef_a,
                               __nv_bfloat16* draw_a, const __nv_bfloat16* raw_b, const float* ss_b, const float* coef_b,
                               __nv_bfloat16* draw_b, long long rows, long long rows_pad, int P, int C, cudaStream_t st);
+bool bn_reduce_frames_supported(int P, int C, int n_streams);
+int bn_backward_reduce_frames(const __nv_bfloat16* up_a, const __nv_bfloat16* up_b, const __nv_bfloat16* raw_a, const float* ss_a,
+                              const float* mi_a, const __nv_bfloat16* raw_b, const float* ss_b, const float* mi_b, float* sums,
+                              long long rows, int P, int C, cudaStream_t st);
 int bn_apply_pool_frames(const __nv_bfloat16* raw_a, const float* ss_a, const __nv_bfloat16* raw_b, const float* ss_b, float* pooled,
                          float* fsums, long long n_frames, int P, int C, cudaStream_t st);
 int conv0_forward(const float* frames, const float* W0, __nv_bfloat16* raw0, float* stats, long long rows, long long rows_pad,
