@@ -127,12 +127,16 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
     const int iss = warp - 1;
     const int row_taps = taps == 9 ? 3 : 1;
     if (iss * row_taps < ntap) {
-      constexpr bool kWide = CIN <= 64;   // the taps of a kernel row as one N = 3*CIN MMA (LBO = one tile row)
-      const uint32_t idesc = umma::make_idesc_bf16(128, kWide ? row_taps * CIN : CIN, 1, 1);
+      // the taps of a kernel row as ONE MMA per 64-channel region of X: N = 3 * min(CIN, 64), LBO = one tile row.  For
+      // C_in = 128 that is two N = 192 MMAs per 16 rows instead of three of N = 128: the dY operand crosses shared memory
+      // twice per kernel row instead of three times (20 KB instead of 24 KB per 192 tensor cycles).
+      constexpr int kRegionCh = CIN < 64 ? CIN : 64;
+      const uint32_t idesc = umma::make_idesc_bf16(128, row_taps * kRegionCh, 1, 1);
       // MN-major swizzled row tiles: LBO = next channel group, SBO = 8 rows; one row = pitch/16 address units
       const uint64_t da0 = tma::make_desc_sw(umma::smem_u32(smem), (uint32_t)C::kARegionBytes, 128u);
-      const uint64_t db0 = tma::make_desc_sw(umma::smem_u32(smem) + C::kABytes + (uint32_t)(halo * C::kBPitch),
-                                             kWide ? (uint32_t)C::kBPitch : (uint32_t)(xslab_rows * C::kBPitch), (uint32_t)C::kBPitch);
+      const uint64_t db0 = tma::make_desc_sw(umma::smem_u32(smem) + C::kABytes + (uint32_t)(halo * C::kBPitch), (uint32_t)C::kBPitch,
+                                             (uint32_t)C::kBPitch);
+      const uint32_t region_units = (uint32_t)(xslab_rows * C::kBPitch) >> 4;   // next 64-channel region of the X slab
       const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       const int t_first = iss * row_taps;                                  // first tap of this issuer's kernel row (CTA-local)
@@ -151,13 +155,10 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
           for (int kk = 0; kk < kStageRows / 16; ++kk) {
             const uint64_t da = ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)(kk * 16 * 8));                    // 16 rows x 128 B
             const uint32_t b_lo = b_lo0 + (uint32_t)(kk * 16 * (C::kBPitch / 16));
-            if (kWide) {
-              umma::mma_bf16(acc0, da, ((uint64_t)b_hi << 32) | b_lo, idesc, (!first || kk > 0) ? 1u : 0u);
-            } else {
-              for (int t = 0; t < row_taps; ++t)   // consecutive taps = consecutive tile rows
-                umma::mma_bf16(acc0 + (uint32_t)(t * CIN), da, ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)(t * (C::kBPitch / 16))), idesc,
-                               (!first || kk > 0) ? 1u : 0u);
-            }
+#pragma unroll
+            for (int reg = 0; reg < C::kBRegions; ++reg)
+              umma::mma_bf16(acc0 + (uint32_t)(reg * row_taps * kRegionCh), da, ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)reg * region_units),
+                             idesc, (!first || kk > 0) ? 1u : 0u);
           }
           if (groups == 1) umma::commit(empty + slot);
           else tma::commit_multicast(empty + slot, cmask);
@@ -175,11 +176,17 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
     umma::fence_after_sync();
     if (q * 32 < COUT) {
       const int co = q * 32 + lane;
+      // accumulator columns: (issuer's kernel row, 64-channel region, tap of the row, channel of the region)
+      const int row_taps = taps == 9 ? 3 : 1;
+      constexpr int kRegionCh = CIN < 64 ? CIN : 64;
       for (int t = 0; t < ntap; ++t) {
+        const int kr = t / row_taps, tr = t - kr * row_taps;
 #pragma unroll
         for (int cg = 0; cg < CIN / 32; ++cg) {
           float v[32];
-          umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * CIN + cg * 32), v);
+          const int reg = cg * 32 / 64, within = cg * 32 - reg * 64;
+          umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) +
+                              (uint32_t)(kr * row_taps * CIN + reg * row_taps * kRegionCh + tr * kRegionCh + within), v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) atomicAdd(dW + ((size_t)co * CIN + cg * 32 + i) * taps + tap0 + t, v[i]);
         }
