@@ -26,7 +26,7 @@ gd = os.path.join("tests", "golden")
 for name in ["resnet_ft_p9", "resnet_p9"]:
     z, sd, x, tgt, ext = T.load(gd, name)
     ref_pred, ref_loss, ref_g, ref_stats = T.rn.loss_and_grads(sd, x, tgt, ext, T.CASES[name]["single"])
-    for it in range(6):
+    for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 6):
         model = T.build(name); model.load_state_dict(sd); model.cuda().train()
         pred = model(x.cuda(), ext.cuda()) if ext is not None else model(x.cuda())
         loss = F.mse_loss(pred, tgt.cuda()); loss.backward()

@@ -30,31 +30,40 @@ def test_forward_loss_grads_match_oracle(golden_dir, name):
     import torch
     import torch.nn.functional as F
     z, sd, x, tgt, ext = load(golden_dir, name)
-    model = build(name)
-    assert list(model.state_dict().keys()) == list(sd.keys())                 # reference state_dict keys, same order
-    model.load_state_dict(sd)
-    model.cuda().train()
-    pred = model(x.cuda(), ext.cuda()) if ext is not None else model(x.cuda())
-    assert tuple(pred.shape) == z["pred"].shape
-    loss = F.mse_loss(pred, tgt.cuda())
-    loss.backward()
     ref_pred, ref_loss, ref_g, ref_stats = rn.loss_and_grads(sd, x, tgt, ext, CASES[name]["single"])
-    assert (pred.cpu() - ref_pred).abs().max().item() < 2e-5 * max(1.0, ref_pred.abs().max().item())
-    assert abs(loss.item() - float(z["loss"])) < 1e-5 * max(1.0, float(z["loss"]))
     gmax = max(float(v.norm()) for v in ref_g.values())
-    for k, p in model.named_parameters():
-        assert p.grad is not None, k
-        r = ref_g[k]
-        if float(r.norm()) < 1e-6 * gmax:
-            assert float(p.grad.cpu().norm()) < 1e-4 * gmax, k
-            continue
-        # fp32 on both sides: summation-order noise (measured <= 1.1e-5).  The BatchNorm statistics are accumulated with atomics, so
-        # the forward differs from run to run in the last bit, and in resnet_ft_p9 ONE pre-activation of layer2's 3x3 output sits
-        # within that bit of zero: in ~25 % of the runs its ReLU mask differs from the CPU oracle's and the BatchNorm affine
-        # gradients of that layer (sums over few pixels) move by 1.0e-3 (scripts/diag_resnet_flaky.py; poisoning the workspace
-        # with NaN changes nothing, i.e. no uninitialised read).  Weight gradients move by < 2e-5 in those runs.
-        tol = 3e-3 if (".bn" in k or "shortcut.1" in k) else 2e-4
-        assert relnorm(p.grad.cpu(), r) < tol, (k, relnorm(p.grad.cpu(), r))
+    # fp32 on both sides: summation-order noise (measured <= 1.1e-5).  The BatchNorm statistics are accumulated with atomics, so the
+    # forward differs from run to run in the last bit, and in resnet_ft_p9 ONE pre-activation of layer2's 3x3 output sits within
+    # that bit of zero: in ~25 % of the runs its ReLU mask differs from the CPU oracle's and the gradients that see that element
+    # move (BatchNorm affine gradients of that layer, sums over few pixels, by 1.0e-3; scripts/diag_resnet_flaky.py -- poisoning
+    # the workspace with NaN changes nothing, i.e. no uninitialised read).  Hence: EVERY run must be within the mask-flip bound
+    # (1e-2, still far below what a wrong kernel produces), and one of up to five runs within summation-order noise.
+    tight_fail = None
+    for attempt in range(5):
+        model = build(name)
+        assert list(model.state_dict().keys()) == list(sd.keys())                 # reference state_dict keys, same order
+        model.load_state_dict(sd)
+        model.cuda().train()
+        pred = model(x.cuda(), ext.cuda()) if ext is not None else model(x.cuda())
+        assert tuple(pred.shape) == z["pred"].shape
+        loss = F.mse_loss(pred, tgt.cuda())
+        loss.backward()
+        assert (pred.cpu() - ref_pred).abs().max().item() < 2e-5 * max(1.0, ref_pred.abs().max().item())
+        assert abs(loss.item() - float(z["loss"])) < 1e-5 * max(1.0, float(z["loss"]))
+        tight_fail = None
+        for k, p in model.named_parameters():
+            assert p.grad is not None, k
+            r = ref_g[k]
+            if float(r.norm()) < 1e-6 * gmax:
+                assert float(p.grad.cpu().norm()) < 1e-4 * gmax, k
+                continue
+            e = relnorm(p.grad.cpu(), r)
+            assert e < 1e-2, (k, e)
+            if e >= 2e-4 and tight_fail is None:
+                tight_fail = (k, e, attempt)
+        if tight_fail is None:
+            break
+    assert tight_fail is None, tight_fail
     msd = model.state_dict()
     for k, v in ref_stats.items():
         assert torch.allclose(msd[k].cpu().float(), v.float(), rtol=1e-4, atol=1e-6), k
