@@ -70,10 +70,9 @@ __device__ __forceinline__ WarpSmem carve(float* base, int n, int P) {
 __host__ __device__ inline int warp_smem_floats(int n, int P) { return 2 * n * P + 6 * n; }
 
 // (1) centres of the n sub-positions of frame f  (helpersGeneration.py:289-293)
-__device__ __forceinline__ void frame_centres(const RenderDev& d, const double* __restrict__ traj_seq, int f,
-                                              int lane, WarpSmem& w) {
-  const double* seg = traj_seq + (size_t)f * d.n * 2;
-  double mx = 0.0, my = 0.0;
+// frame mean of the scaled positions (the centring offset); every caller sums in the reference's order
+__device__ __forceinline__ void frame_mean(const RenderDev& d, const double* __restrict__ seg, double& mx, double& my) {
+  mx = 0.0; my = 0.0;
   if (d.center) {
     for (int p = 0; p < d.n; ++p) {  // sequential like np.mean(axis=0)
       mx += seg[2 * p] * d.scale;
@@ -82,21 +81,30 @@ __device__ __forceinline__ void frame_centres(const RenderDev& d, const double* 
     mx *= d.inv_n;   // (a reciprocal multiply instead of np.mean's division: 1 ulp of float64, no double-division subroutine)
     my *= d.inv_n;
   }
-  for (int p = lane; p < d.n; p += 32) {
-    const double cx = (seg[2 * p] * d.scale - mx) * (double)d.U;
-    const double cy = (seg[2 * p + 1] * d.scale * d.ysign - my) * (double)d.U;
-    // nearest grid node: any node gives a correct (node, offset) pair, the nearest one keeps the float32 offset small
-    int jx = (int)fmin(fmax(rint((cx + d.limit) * d.inv_step_d), 0.0), (double)(d.G - 1));
-    int jy = (int)fmin(fmax(rint((cy + d.limit) * d.inv_step_d), 0.0), (double)(d.G - 1));
-    const double ox = cx - (-(double)d.limit + jx * d.step_d);
-    const double oy = cy - (-(double)d.limit + jy * d.step_d);
-    w.jc[p] = jx;
-    w.jc[d.n + p] = jy;
-    w.c0[p] = (float)ox;
-    w.c0[d.n + p] = (float)oy;
-    const float fx = (float)ox, fy = (float)oy;
-    w.msq[p] = (float)((double)fx * (double)fx + (double)fy * (double)fy);
-  }
+}
+// sub-position p: (nearest grid node, float32 offset) per axis and the squared offset for the NaN rule
+__device__ __forceinline__ void centre_one(const RenderDev& d, const double* __restrict__ seg, double mx, double my, int p,
+                                           WarpSmem& w) {
+  const double cx = (seg[2 * p] * d.scale - mx) * (double)d.U;
+  const double cy = (seg[2 * p + 1] * d.scale * d.ysign - my) * (double)d.U;
+  // nearest grid node: any node gives a correct (node, offset) pair, the nearest one keeps the float32 offset small
+  int jx = (int)fmin(fmax(rint((cx + d.limit) * d.inv_step_d), 0.0), (double)(d.G - 1));
+  int jy = (int)fmin(fmax(rint((cy + d.limit) * d.inv_step_d), 0.0), (double)(d.G - 1));
+  const double ox = cx - (-(double)d.limit + jx * d.step_d);
+  const double oy = cy - (-(double)d.limit + jy * d.step_d);
+  w.jc[p] = jx;
+  w.jc[d.n + p] = jy;
+  w.c0[p] = (float)ox;
+  w.c0[d.n + p] = (float)oy;
+  const float fx = (float)ox, fy = (float)oy;
+  w.msq[p] = (float)((double)fx * (double)fx + (double)fy * (double)fy);
+}
+__device__ __forceinline__ void frame_centres(const RenderDev& d, const double* __restrict__ traj_seq, int f,
+                                              int lane, WarpSmem& w) {
+  const double* seg = traj_seq + (size_t)f * d.n * 2;
+  double mx, my;
+  frame_mean(d, seg, mx, my);
+  for (int p = lane; p < d.n; p += 32) centre_one(d, seg, mx, my, p, w);
 }
 
 // (2) axis table: block means of exp(-(k (k - 2 c0)) / 2 sigma^2)
@@ -156,19 +164,20 @@ struct Geo {
 };
 
 // spot intensities of the n sub-positions of frame f  (helpersGeneration.py:300)
+__device__ __forceinline__ void v1_intensity_one(const RenderDev& d, WarpSmem& w, int f, int n, int p, uint32_t seq) {
+  float z = 0.0f, z1;
+  if (!d.mean_noise) {
+    const uint4 r = philox4x32_10((uint32_t)(f * n + p), 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
+    box_muller_fast(r.x, r.y, z, z1);
+  }
+  float I = __fadd_rn(d.imean, __fmul_rn(d.istd, z));
+  if ((double)w.msq[p] * d.inv2s2_d > 745.0) I = __int_as_float(0x7fc00000);  // spot underflows: NaN frame (:305-308)
+  w.inten[p] = I;
+}
 template <class G>
 __device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, int f, int lane, uint32_t seq) {
   const int n = G::n(d);
-  for (int p = lane; p < n; p += 32) {
-    float z = 0.0f, z1;
-    if (!d.mean_noise) {
-      const uint4 r = philox4x32_10((uint32_t)(f * n + p), 0u, seq, stream_word(MIVIT_STREAM_INTENSITY, 0), d.k0, d.k1);
-      box_muller_fast(r.x, r.y, z, z1);
-    }
-    float I = __fadd_rn(d.imean, __fmul_rn(d.istd, z));
-    if ((double)w.msq[p] * d.inv2s2_d > 745.0) I = __int_as_float(0x7fc00000);  // spot underflows: NaN frame (:305-308)
-    w.inten[p] = I;
-  }
+  for (int p = lane; p < n; p += 32) v1_intensity_one(d, w, f, n, p, seq);
 }
 
 // axis table of the V1 kernels: tab[p][0][b] = block mean of the x profile, tab[p][1][a] = I_p * block mean of the y profile
@@ -176,32 +185,50 @@ __device__ __forceinline__ void v1_intensities(const RenderDev& d, WarpSmem& w, 
 template <class G>
 __device__ __forceinline__ void axis_table_v1(const RenderDev& d, int lane, WarpSmem& w) {
   const int P = G::P(d), U = G::U(d), n = G::n(d);
-  const int entries = 2 * n * P;
   const float c2 = -d.inv2s2 * 1.4426950408889634f;   // exp(-t/2s^2) = 2^(t * c2)
+  const float cs = c2 * d.step;
+  const float q = fast_ex2(2.0f * cs * d.step);
   const float invU = 1.0f / (float)U;
-  for (int e = lane; e < entries; e += 32) {
-    const int p = e / (2 * P);
-    const int r = e - p * 2 * P;
+  // lane = one (axis, block) entry r of the 2P per sub-position, loop over the sub-positions: the (p, axis, b) decomposition
+  // of a flat entry index cost 19 of 51 instructions per entry (ncu source page); here it is done once per lane and the
+  // shared-memory offsets of the unrolled loop are immediates.
+  for (int r = lane; r < 2 * P; r += 32) {
     const int axis = r >= P ? 1 : 0;
     const int b = r - axis * P;
-    const int idx = axis * n + p;
-    const float twoc0 = 2.0f * w.c0[idx];
-    const float kb = (float)(b * U - w.jc[idx]) * d.step;
-    float acc = 0.0f;
+    const int bU = b * U;
+    const float* c0p = w.c0 + axis * n;
+    const int* jcp = w.jc + axis * n;
+    float* tp = w.tab + r;
+#pragma unroll 10
+    for (int p = 0; p < n; ++p) {
+      const float twoc0 = 2.0f * c0p[p];
+      const float kb = (float)(bU - jcp[p]) * d.step;
+      // The exponent is quadratic in u, f(u) = c2 (kb + u s)(kb + u s - 2 c0), so consecutive samples differ by a geometric
+      // factor whose own ratio q = 2^(2 c2 s^2) is a launch constant: two exps per entry instead of U
+      //   e_0 = 2^f(0),  r_0 = 2^(c2 s (2 kb - 2 c0 + s)),  e_(u+1) = e_u r_u,  r_(u+1) = r_u q
+      // (relative error <= ~U roundings, 1e-6 at U = 5; explicit roundings: a contracted acc = fma(e, r, acc) would differ
+      // between the kernels' instantiations).  Far from the spot e_0 underflows to 0 and stays 0: the exact samples are
+      // < 2^-126 there; a ratio beyond 2^126 only occurs where e_0 has underflowed and is clamped so that 0 * r stays 0.
+      float e_u = fast_ex2(__fmul_rn(__fmul_rn(kb, __fsub_rn(kb, twoc0)), c2));
+      float r_u = fast_ex2(fminf(__fmul_rn(__fsub_rn(fmaf(2.0f, kb, d.step), twoc0), cs), 126.0f));
+      float acc = e_u;
 #pragma unroll
-    for (int u = 0; u < (TU_OR(G, 8)); ++u) {
-      if (u < U) {
-        const float k = kb + (float)u * d.step;
-        acc += fast_ex2(k * (k - twoc0) * c2);
+      for (int u = 1; u < (TU_OR(G, 8)); ++u) {
+        if (u < U) {
+          e_u = __fmul_rn(e_u, r_u);
+          r_u = __fmul_rn(r_u, q);
+          acc = __fadd_rn(acc, e_u);
+        }
       }
+      for (int u = TU_OR(G, 8); u < U; ++u) {   // generic geometry with an upsampling factor beyond 8: rolled remainder
+        e_u = __fmul_rn(e_u, r_u);
+        r_u = __fmul_rn(r_u, q);
+        acc = __fadd_rn(acc, e_u);
+      }
+      acc *= invU;
+      if (axis) acc *= w.inten[p];
+      tp[p * 2 * P] = acc;            // tab[(p * 2 + axis) * P + b]
     }
-    for (int u = TU_OR(G, 8); u < U; ++u) {   // generic geometry with an upsampling factor beyond 8: rolled remainder
-      const float k = kb + (float)u * d.step;
-      acc += fast_ex2(k * (k - twoc0) * c2);
-    }
-    acc *= invU;
-    if (axis) acc *= w.inten[p];
-    w.tab[e] = acc;                 // (p * 2 + axis) * P + b == e
   }
 }
 
@@ -209,7 +236,9 @@ __device__ __forceinline__ void axis_table_v1(const RenderDev& d, int lane, Warp
 // background (:312-313), multiplicative Poisson (:316-317), fused normalisation (:395) and hands (pixel index, value) to `sink`.
 // No divergent branch on the one-pixel pair that ends a row of odd length: its second column index is clamped and only the
 // sink call is predicated.
-template <class G, typename Sink>
+// kPairLoad: the two x-profile entries of a pixel pair are read as one 8-byte load (the warp's table must be 8-byte aligned:
+// true for render_v1_kernel, whose per-warp carve-up has an even number of floats).
+template <class G, bool kPairLoad = false, typename Sink>
 __device__ __forceinline__ void v1_frame_pixels(const RenderDev& d, const WarpSmem& w, int f, int lane, uint32_t seq,
                                                 const V1Noise& nz, Sink&& sink) {
   const int P = G::P(d), n = G::n(d);
@@ -224,11 +253,23 @@ __device__ __forceinline__ void v1_frame_pixels(const RenderDev& d, const WarpSm
       const float* ty = w.tab + P + a;                    // tab[p][1][a]
       const float* tx0 = w.tab + b0;                      // tab[p][0][b0]
       const float* tx1 = w.tab + (two ? b0 + 1 : b0);
+      if (kPairLoad) {
+        // (the pair that ends a row of odd length reads one float past the x profile -- the first y entry -- for a pixel
+        //  that is never stored)
 #pragma unroll 10
-      for (int p = 0; p < n; ++p) {
-        const float t = ty[p * 2 * P];
-        v0 = fmaf(t, tx0[p * 2 * P], v0);
-        v1 = fmaf(t, tx1[p * 2 * P], v1);
+        for (int p = 0; p < n; ++p) {
+          const float t = ty[p * 2 * P];
+          const float2 x2 = *reinterpret_cast<const float2*>(tx0 + p * 2 * P);
+          v0 = fmaf(t, x2.x, v0);
+          v1 = fmaf(t, x2.y, v1);
+        }
+      } else {
+#pragma unroll 10
+        for (int p = 0; p < n; ++p) {
+          const float t = ty[p * 2 * P];
+          v0 = fmaf(t, tx0[p * 2 * P], v0);
+          v1 = fmaf(t, tx1[p * 2 * P], v1);
+        }
       }
     }
     float z0 = 0.0f, z1 = 0.0f, k0f = d.poisson, k1f = d.poisson;
@@ -265,7 +306,9 @@ __device__ __forceinline__ V1Noise v1_noise_setup(const RenderDev& d, const Alia
   nz.alias = alias_s;
   nz.k0 = at.k0;
   nz.ptab = ptab;
-  nz.pc = poisson_setup(d.poisson);
+  nz.pc = PoissonConst{};
+  // (the PTRS constants cost ~90 instructions per warp: only when the alias table does not cover pn)
+  if (!nz.use_alias && d.poisson != -1.0f && !d.mean_noise) nz.pc = poisson_setup(d.poisson);
   if (d.poisson != -1.0f && !d.mean_noise) {
     if (nz.use_alias) {
       for (int i = threadIdx.x; i < kAliasEntries; i += blockDim.x) alias_s[i] = at.e[i];
@@ -300,15 +343,35 @@ __global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict
   __shared__ float ptab[kPoissonTable];
   __shared__ uint32_t alias_s[kAliasEntries];
   const V1Noise nz = v1_noise_setup(d, at, alias_s, ptab);
+  // Centres (float64) and spot intensities (one Philox block each) of the CTA's frames, one THREAD per (frame, sub-position):
+  // with one warp per frame these two steps ran on n = 10 of 32 lanes in every warp -- 360 of 1820 warp instructions per
+  // frame (ncu source page, profiles/r02_ncu_render.md); spread over the CTA they fill 3 warps instead of 8.
+  if (d.draw) {
+    const int n = G::n(d);
+    for (int t = threadIdx.x; t < warps * n; t += blockDim.x) {
+      const int wi = t / n, p = t - wi * n;
+      const long long gfi = (long long)blockIdx.x * warps + wi;
+      if (gfi >= n_frames_total) continue;
+      const long long si = gfi / d.F;
+      const int fi = (int)(gfi - si * d.F);
+      WarpSmem wo = carve(smem + (size_t)wi * warp_smem_floats(n, G::P(d)), n, G::P(d));
+      const double* seg = traj + (size_t)si * d.T * 2 + (size_t)fi * n * 2;
+      double mx, my;
+      frame_mean(d, seg, mx, my);
+      centre_one(d, seg, mx, my, p, wo);
+      v1_intensity_one(d, wo, fi, n, p, global_seq(d, si));
+    }
+  }
   __syncthreads();
   const long long gf = (long long)blockIdx.x * warps + warp;  // global frame index
   if (gf >= n_frames_total) return;
   const long long s = gf / d.F;
   const int f = (int)(gf - s * d.F);
   const uint32_t seq = global_seq(d, s);
-  v1_frame_tables<G>(d, traj, s, f, lane, seq, w);
+  if (d.draw) axis_table_v1<G>(d, lane, w);
+  __syncwarp();
   float* dst = out + s * d.out_seq_stride + (long long)f * G::P(d) * G::P(d);
-  v1_frame_pixels<G>(d, w, f, lane, seq, nz, [&](int pix, float v) { dst[pix] = v; });
+  v1_frame_pixels<G, true>(d, w, f, lane, seq, nz, [&](int pix, float v) { dst[pix] = v; });
 }
 
 // Renderer fused with the frame embedding of LinearProjectionEmbedding / CNNEmbedding (helpers/models.py:146-199:
