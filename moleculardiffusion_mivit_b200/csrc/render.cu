@@ -17,6 +17,7 @@
 // background and the Poisson factor from the pixel's own Philox stream, normalises and
 // stores -- consecutive lanes write consecutive pixels (coalesced, frames are contiguous).
 #include "common.cuh"
+#include <stdlib.h>
 #include "philox.cuh"
 #include "../../include/mivit.h"
 #include "vit.h"
@@ -331,8 +332,10 @@ __device__ __forceinline__ void v1_frame_tables(const RenderDev& d, const double
   __syncwarp();
 }
 
+// (256, 5): 48 registers instead of 56 (12 bytes of spills) buys a fifth resident CTA per SM, which hides the barrier after the
+// cooperative set-up phase: 0.0511 -> 0.0494 ms per 30 720 frames; 4- and 2-warp CTAs were slower (0.0533 / 0.0648 ms).
 template <int TP, int TU, int TN>
-__global__ void __launch_bounds__(256) render_v1_kernel(const double* __restrict__ traj, long long n_frames_total,
+__global__ void __launch_bounds__(256, 5) render_v1_kernel(const double* __restrict__ traj, long long n_frames_total,
                                                         RenderDev d, const __grid_constant__ AliasTable at,
                                                         float* __restrict__ out) {
   using G = Geo<TP, TU, TN>;
