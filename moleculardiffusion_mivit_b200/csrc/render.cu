@@ -69,6 +69,9 @@ __device__ __forceinline__ WarpSmem carve(float* base, int n, int P) {
   return w;
 }
 __host__ __device__ inline int warp_smem_floats(int n, int P) { return 2 * n * P + 6 * n; }
+// per-warp floats of the fused render->embedding kernel: tables + the rendered frame, both rounded to 16 bytes (the frame is
+// read back with 16-byte loads)
+__host__ __device__ inline int embed_warp_floats(int n, int P) { return ((warp_smem_floats(n, P) + 3) & ~3) + ((P * P + 3) & ~3); }
 
 // (1) centres of the n sub-positions of frame f  (helpersGeneration.py:289-293)
 // frame mean of the scaled positions (the centring offset); every caller sums in the reference's order
@@ -394,10 +397,10 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
   const int warps = blockDim.x >> 5;
   const int P = G::P(d), n = G::n(d), PP = P * P;
   float* wts = smem;                                       // [PP][E]
-  const int per_warp = warp_smem_floats(n, P) + PP;
-  float* mine = smem + (size_t)PP * E + (size_t)warp * per_warp;
+  const int per_warp = embed_warp_floats(n, P);
+  float* mine = smem + (((size_t)PP * E + 3) & ~(size_t)3) + (size_t)warp * per_warp;
   WarpSmem w = carve(mine, n, P);
-  float* px = mine + warp_smem_floats(n, P);               // [PP] rendered frame
+  float* px = mine + ((warp_smem_floats(n, P) + 3) & ~3);  // [PP] rendered frame, 16-byte aligned
   if (w_transposed) {
     for (int i = threadIdx.x; i < PP * E; i += blockDim.x) wts[i] = __ldg(W + i);
   } else {
@@ -418,10 +421,44 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
       if (fo != nullptr) fo[pix] = v;
     });
     __syncwarp();
-    for (int e = lane; e < E; e += 32) {
-      float acc = 0.f;
-      for (int pix = 0; pix < PP; ++pix) acc = fmaf(px[pix], wts[pix * E + e], acc);   // same summation order as a K-loop GEMM
-      emb[gf * E + e] = acc + __ldg(bias + e);
+    const bool emb_al8 = (reinterpret_cast<unsigned long long>(emb) & 7ull) == 0ull;
+    if ((E & 1) == 0) {
+      // lane = two adjacent output features: per 4 pixels one 16-byte load of the frame (broadcast), four 8-byte loads of the
+      // weights and 8 FMAs (the scalar loop below spends a pixel load, a weight load and an address per FMA: 1350 of the
+      // kernel's ~2500 instructions per frame).  Same summation order per output as a K-loop GEMM.
+      for (int e = 2 * lane; e < E; e += 64) {
+        float a0 = 0.f, a1 = 0.f;
+        const float* wp = wts + e;
+        int pix = 0;
+        for (; pix + 4 <= PP; pix += 4) {
+          const float4 f4 = *reinterpret_cast<const float4*>(px + pix);
+          const float2 w0 = *reinterpret_cast<const float2*>(wp + (size_t)pix * E);
+          const float2 w1 = *reinterpret_cast<const float2*>(wp + (size_t)(pix + 1) * E);
+          const float2 w2 = *reinterpret_cast<const float2*>(wp + (size_t)(pix + 2) * E);
+          const float2 w3 = *reinterpret_cast<const float2*>(wp + (size_t)(pix + 3) * E);
+          a0 = fmaf(f4.x, w0.x, a0); a1 = fmaf(f4.x, w0.y, a1);
+          a0 = fmaf(f4.y, w1.x, a0); a1 = fmaf(f4.y, w1.y, a1);
+          a0 = fmaf(f4.z, w2.x, a0); a1 = fmaf(f4.z, w2.y, a1);
+          a0 = fmaf(f4.w, w3.x, a0); a1 = fmaf(f4.w, w3.y, a1);
+        }
+        for (; pix < PP; ++pix) {
+          const float2 w0 = *reinterpret_cast<const float2*>(wp + (size_t)pix * E);
+          a0 = fmaf(px[pix], w0.x, a0); a1 = fmaf(px[pix], w0.y, a1);
+        }
+        const float o0 = a0 + __ldg(bias + e), o1 = a1 + __ldg(bias + e + 1);
+        if (emb_al8) {
+          *reinterpret_cast<float2*>(emb + gf * E + e) = make_float2(o0, o1);
+        } else {
+          emb[gf * E + e] = o0;
+          emb[gf * E + e + 1] = o1;
+        }
+      }
+    } else {
+      for (int e = lane; e < E; e += 32) {
+        float acc = 0.f;
+        for (int pix = 0; pix < PP; ++pix) acc = fmaf(px[pix], wts[pix * E + e], acc);   // same summation order as a K-loop GEMM
+        emb[gf * E + e] = acc + __ldg(bias + e);
+      }
     }
     __syncwarp();
   }
@@ -933,8 +970,8 @@ int render_embed_linear_launch(const double* traj, long long N, int T, const miv
   d.istd = (float)((double)prm->part_std / prm->n);
   d.out_seq_stride = frames_seq_stride;
   const int PP = d.P * d.P;
-  const size_t per_warp = (size_t)(warp_smem_floats(d.n, d.P) + PP) * sizeof(float);
-  const size_t wbytes = (size_t)PP * E * sizeof(float);
+  const size_t per_warp = (size_t)embed_warp_floats(d.n, d.P) * sizeof(float);
+  const size_t wbytes = (((size_t)PP * E + 3) & ~(size_t)3) * sizeof(float);
   int warps = 8;
   while (warps > 1 && wbytes + per_warp * warps > 200 * 1024) warps >>= 1;
   const size_t smem = wbytes + per_warp * warps;
