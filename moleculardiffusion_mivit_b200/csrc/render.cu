@@ -469,14 +469,17 @@ __global__ void __launch_bounds__(256) render_embed_linear_kernel(const double* 
 // bit-identical to the forward's frames) instead of being stored: the frames of a Linear / CNN-embedding ViT never exist
 // in HBM, forward or backward.  A CTA renders 8 frames (one per warp) into shared memory, then all 256 threads update
 // their register tile of dW: warp w owns EPW consecutive output features, lane l the pixels l, l + 32, ...
-template <int EPW, int PJ>
+// KG: the frame geometry is the reference's (U = 5, n = 10, P = 7 / 9 / 13 / 15 as implied by PJ) and compiled in, like in the
+// forward kernels (same code, same bits: the re-rendered frames equal the forward's).
+template <int EPW, int PJ, bool KG>
 __global__ void __launch_bounds__(256) render_embed_wgrad_kernel(const double* __restrict__ traj, long long n_frames_total,
                                                                  RenderDev d, const __grid_constant__ AliasTable at,
                                                                  const float* __restrict__ demb, int E,
                                                                  float* __restrict__ dW, float* __restrict__ db) {
+  using G = Geo<KG ? (PJ == 2 ? 7 : PJ == 3 ? 9 : PJ == 6 ? 13 : 15) : 0, KG ? 5 : 0, KG ? 10 : 0>;
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = d.P, n = d.n, PP = d.P * d.P;
+  const int P = G::P(d), n = G::n(d), PP = P * P;
   const int per_warp = warp_smem_floats(n, P) + PP;
   float* mine = smem + (size_t)warp * per_warp;
   WarpSmem w = carve(mine, n, P);
@@ -496,12 +499,30 @@ __global__ void __launch_bounds__(256) render_embed_wgrad_kernel(const double* _
   for (long long g0 = (long long)blockIdx.x * 8; g0 < n_frames_total; g0 += (long long)gridDim.x * 8) {
     const long long gf = g0 + warp;
     const bool live = gf < n_frames_total;
+    // centres and intensities of the CTA's 8 frames, one thread per (frame, sub-position) (see render_v1_kernel)
+    if (d.draw) {
+      for (int t = threadIdx.x; t < 8 * n; t += 256) {
+        const int wi = t / n, p = t - wi * n;
+        const long long gfi = g0 + wi;
+        if (gfi >= n_frames_total) continue;
+        const long long si = gfi / d.F;
+        const int fi = (int)(gfi - si * d.F);
+        WarpSmem wo = carve(smem + (size_t)wi * per_warp, n, P);
+        const double* seg = traj + (size_t)si * d.T * 2 + (size_t)fi * n * 2;
+        double mx, my;
+        frame_mean(d, seg, mx, my);
+        centre_one(d, seg, mx, my, p, wo);
+        v1_intensity_one(d, wo, fi, n, p, global_seq(d, si));
+      }
+    }
+    __syncthreads();
     if (live) {
       const long long s = gf / d.F;
       const int f = (int)(gf - s * d.F);
       const uint32_t seq = global_seq(d, s);
-      v1_frame_tables<Geo<0, 0, 0>>(d, traj, s, f, lane, seq, w);
-      v1_frame_pixels<Geo<0, 0, 0>>(d, w, f, lane, seq, nz, [&](int pix, float v) { px[pix] = v; });
+      if (d.draw) axis_table_v1<G>(d, lane, w);
+      __syncwarp();
+      v1_frame_pixels<G>(d, w, f, lane, seq, nz, [&](int pix, float v) { px[pix] = v; });
       for (int e = lane; e < E; e += 32) dsh[warp * E + e] = __ldg(demb + gf * E + e);
     } else {
       for (int pix = lane; pix < PP; pix += 32) px[pix] = 0.0f;
@@ -1004,22 +1025,29 @@ int render_embed_linear_launch(const double* traj, long long N, int T, const miv
   return MIVIT_OK;
 }
 
-template <int EPW, int PJ>
-static int wgrad_launch_t(const double* traj, long long frames, const RenderDev& d, const AliasTable& at, const float* demb, int E,
+template <int EPW, int PJ, bool KG>
+static int wgrad_launch_g(const double* traj, long long frames, const RenderDev& d, const AliasTable& at, const float* demb, int E,
                           float* dW, float* db, cudaStream_t st) {
   const size_t per_warp = (size_t)(warp_smem_floats(d.n, d.P) + d.P * d.P) * sizeof(float);
   const size_t smem = per_warp * 8 + (size_t)8 * E * sizeof(float);
   MIVIT_CHECK_ARG(smem <= 200 * 1024, "nPosPerFrame*output_size too large for shared memory (%zu bytes per frame)", per_warp);
   if (smem > 48 * 1024)
-    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_embed_wgrad_kernel<EPW, PJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIVIT_CUDA_CHECK(cudaFuncSetAttribute(render_embed_wgrad_kernel<EPW, PJ, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   long long blocks = (long long)sms * 2;
   if (blocks > mivit_ceil_div(frames, 8)) blocks = mivit_ceil_div(frames, 8);
-  render_embed_wgrad_kernel<EPW, PJ><<<(unsigned)blocks, 256, smem, st>>>(traj, frames, d, at, demb, E, dW, db);
+  render_embed_wgrad_kernel<EPW, PJ, KG><<<(unsigned)blocks, 256, smem, st>>>(traj, frames, d, at, demb, E, dW, db);
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
+}
+template <int EPW, int PJ>
+static int wgrad_launch_t(const double* traj, long long frames, const RenderDev& d, const AliasTable& at, const float* demb, int E,
+                          float* dW, float* db, cudaStream_t st) {
+  constexpr int kP = PJ == 2 ? 7 : PJ == 3 ? 9 : PJ == 6 ? 13 : 15;
+  if (d.U == 5 && d.n == 10 && d.P == kP) return wgrad_launch_g<EPW, PJ, true>(traj, frames, d, at, demb, E, dW, db, st);
+  return wgrad_launch_g<EPW, PJ, false>(traj, frames, d, at, demb, E, dW, db, st);
 }
 
 // dW [E][P*P] and db [E] are ACCUMULATED into (the caller zeroes them)
