@@ -453,6 +453,45 @@ def _check_against_oracle(model, cfg, sd, x, tgt, feats, ptol, gtol, emb_gtol=No
     return worst
 
 
+@pytest.mark.parametrize("P,Fr,B", [(13, 30, 8), (9, 21, 7), (7, 10, 3), (15, 6, 5), (12, 9, 2), (13, 3, 1)])
+def test_frame_batchnorm_kernels_match_row_kernels(P, Fr, B):
+    """The whole-frame TMA BatchNorm passes (csrc/bn_frames.cu: pooled pair forward / backward, the three backward reductions)
+    against the row-streaming kernels of csrc/bn.cu they replace (MIVIT_NO_BN_FRAMES=1 is the library's A/B switch): odd and even
+    patch sizes, frame counts that are no multiple of the frames per stage or of the grid, a single sequence.  The apply passes
+    are the same arithmetic operation for operation; the reductions differ in summation order only."""
+    import os
+    import torch
+    x, tgt = _bench_frames(B, P=P, Fr=Fr, seed=P + Fr)
+    _, _, sd = _deep_model(P, seed=2)
+    outs = []
+    for rows_only in (False, True):
+        if rows_only:
+            os.environ["MIVIT_NO_BN_FRAMES"] = "1"
+        try:
+            model, _, _ = _deep_model(P, seed=2)
+            model.load_state_dict(sd)
+            model.cuda().train()
+            pred = model(x)
+            ((pred - tgt) ** 2).mean().backward()
+            torch.cuda.synchronize()
+            outs.append((pred.detach().cpu(), {k: p.grad.cpu() for k, p in model.named_parameters()}))
+        finally:
+            os.environ.pop("MIVIT_NO_BN_FRAMES", None)
+    # forward: same arithmetic with the pooled sums reordered; the BatchNorm statistics (atomics) already differ from run to run
+    # in the last bit and the tf32 roundings of the transformer turn that into ~1e-4
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 5e-4 * max(1.0, outs[1][0].abs().max().item())
+    gmax = max(float(g.norm()) for g in outs[1][1].values())
+    for k, b in outs[1][1].items():
+        a = outs[0][1][k]
+        if float(b.norm()) > 1e-5 * gmax:
+            # bf16-stored gradients downstream of reordered fp32 sums: the chain down to the stem amplifies bf16 rounding flips and
+            # the tf32 attention projections do the same (measured over repeated runs: up to 1.1e-2 on initial_conv.weight and
+            # layer 0's k_proj.weight, everything else < 5e-3; the run-to-run spread of ONE path is of that size) -> the oracle
+            # bound 3e-2.  What this test guards is layout / addressing / staging of the frame kernels (a misaligned TMA slot at
+            # 32 channels once crashed exactly here), not rounding.
+            assert relnorm(a, b) < 3e-2, (k, relnorm(a, b))
+
+
 @pytest.mark.parametrize("feat", [None, "early", "late"])
 def test_product_shape_B32_matches_oracle(feat):
     """deepcnn_n at P=13, F=30, B=32 (992 tokens >= 512): the tf32 tcgen05 nn.Linear kernels, the batched q/k/v launch, the ReLU-gate
