@@ -63,6 +63,24 @@ def test_noise_free_matches_reference_golden(gold, gen, key, sl, n, center, over
     assert relmax(out, orc) < 2e-6
 
 
+@pytest.mark.parametrize("wavelength,P", [(70e-9, 9), (120e-9, 13), (40e-9, 7)])
+def test_sharp_psf_far_entries_underflow_without_nan(gold, gen, wavelength, P):
+    """PSF narrower than a high-resolution pixel (sigma 0.3-0.9 sub-pixels): most axis-table entries underflow and the ratio of the
+    geometric recurrence of the block samples (csrc/render.cu: axis_table_v1) exceeds 2^126 there -- the clamp must keep those
+    entries at 0 (0 * inf would be NaN) while the spot itself stays within the fp32 tolerance of the oracle."""
+    inp, _, _ = gold
+    props = dict(CLEAN, wavelength=wavelength, output_size=P)
+    t = inp["traj30"][:3].copy()
+    out = gen.trajectories_to_video(t, 10, True, props, _mean_noise=True)
+    orc = ro.render_v1(inp["traj30"][:3], 10, True, props)
+    assert np.isfinite(orc).all(), "the oracle itself underflows to NaN frames for this PSF: not the case this test is about"
+    assert np.isfinite(out).all()
+    assert out.max() > 0
+    flat, ref = out.reshape(*out.shape[:2], -1), orc.reshape(*orc.shape[:2], -1)
+    assert np.array_equal(flat.argmax(-1), ref.argmax(-1))
+    assert relmax(out, orc) < 1e-5
+
+
 def test_fused_normalisation_and_background(gold, gen):
     inp, g, _ = gold
     out = gen.trajectories_to_video(inp["traj30"][:2].copy(), 10, True, dict(C3_PROPS, poisson_noise=-1),
