@@ -798,9 +798,16 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
     // The skip path first: its gradient tensor leaves its slot before conv2's input gradient needs one (carve()).  Block 1 on
     // the product path keeps it for the ONE kernel that accumulates the conv1 (3x3) and skip (1x1) input gradients into one
     // accumulator and one output tensor (dinm); otherwise two convolutions, and BatchNorm's backward sums the two tensors.
-    CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
     const bool try_dual = impl == 1 && b == 0;   // (block 2: the resident weights would force 32-column slices, measured slower)
-    if (!try_dual) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
+    // Block 2 on the product path: the skip convolution's weight gradient AND input gradient from one pass over its output
+    // gradient (conv_skip_bwd.cu); otherwise the two stream kernels.
+    bool skip_fused = false;
+    if (impl == 1 && !try_dual)
+      CK(conv_skip_backward_fused(in[b]->row0, ds[b]->row0, w.wd_sk[b], g + R.sk_w, dins[b]->row0, rows, P, ci[b], co[b], st, &skip_fused));
+    if (!skip_fused) {
+      CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
+      if (!try_dual) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
+    }
     CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
     // conv2 input gradient; on the product path its epilogue also accumulates the backward sums of bn1 (no reduction pass)
     bool bn1_summed = false;
