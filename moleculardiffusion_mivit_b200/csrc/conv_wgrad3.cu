@@ -16,6 +16,8 @@
 //     the cluster, so a row range crosses L2 -> SM once instead of three times.  A ring slot is refilled
 //     only after the MMAs of all G CTAs have released it (tcgen05.commit multicast on the empty barrier).
 // Accumulators stay in TMEM over the CTA's whole row range and are flushed once with fp32 atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
@@ -45,8 +47,13 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, float* __restrict__ dW,
                       int n_stages, int stages_per_cta, int taps, ConvShifts shifts, int halo, int xslab_rows, int stage_bytes,
-                      int ring, int groups, int guard) {
+                      int ring, int groups, int guard, const __grid_constant__ CUtensorMap tmY2, float* __restrict__ dW2) {
   using C = WgCfg3<CIN, COUT>;
+  // dW2 != nullptr (9 taps, one CTA per row range): the weight gradient of the block's 1x1 SKIP convolution rides along -- same
+  // input X, its own output gradient dY2 staged next to dY, one more MMA per 16 rows against the centre tap's rows, one more
+  // accumulator (columns taps*CIN ...): X is read once for both and the skip's own stream kernel disappears.
+  const bool has2 = dW2 != nullptr;
+  const int a_bytes = C::kABytes * (has2 ? 2 : 1);
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_uniform(), lane = tid & 31;
   uint8_t* bars_base = smem + (size_t)ring * stage_bytes + C::kOverRead;   // past the M = 128 over-read of the last slot
@@ -85,16 +92,17 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (umma::elect_one()) {
-      const uint32_t bytes = (uint32_t)(C::kABytes + C::kBRegions * xslab_rows * C::kBPitch);
-      // load units = 32-row boxes: A region-major (kARegions x 4), then B (kBRegions x xslab_rows/32); CTA g takes u = g mod G
-      const int a_units = C::kARegions * (kStageRows / kBoxRows), xb = xslab_rows / kBoxRows;
+      const uint32_t bytes = (uint32_t)(a_bytes + C::kBRegions * xslab_rows * C::kBPitch);
+      // load units = 32-row boxes: A region-major (kARegions x 4) (twice with a second dY), then B (kBRegions x xslab_rows/32);
+      // CTA g takes u = g mod G
+      const int a1_units = C::kARegions * (kStageRows / kBoxRows), a_units = a1_units * (has2 ? 2 : 1), xb = xslab_rows / kBoxRows;
       const int n_units = a_units + C::kBRegions * xb;
       int slot = 0;
       uint32_t ph = 0;
       for (int s = s_begin; s < s_end; ++s) {
         umma::mbar_wait(empty + slot, ph ^ 1);
         uint8_t* aslab = smem + (size_t)slot * stage_bytes;
-        uint8_t* bslab = aslab + C::kABytes;
+        uint8_t* bslab = aslab + a_bytes;
         tma::expect_tx(full + slot, bytes);
         const int r0 = guard + s * kStageRows;
         for (int u = grp; u < n_units; u += groups) {
@@ -102,9 +110,10 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
           const CUtensorMap* tm;
           int ch0, row;
           if (u < a_units) {
-            const int reg = u / (kStageRows / kBoxRows), rb = u - reg * (kStageRows / kBoxRows);
-            dst = aslab + (size_t)reg * C::kARegionBytes + (size_t)rb * kBoxRows * 128;
-            tm = &tmY; ch0 = reg * 64; row = r0 + rb * kBoxRows;
+            const int second = u >= a1_units ? 1 : 0, v = u - second * a1_units;
+            const int reg = v / (kStageRows / kBoxRows), rb = v - reg * (kStageRows / kBoxRows);
+            dst = aslab + (size_t)second * C::kABytes + (size_t)reg * C::kARegionBytes + (size_t)rb * kBoxRows * 128;
+            tm = second ? &tmY2 : &tmY; ch0 = reg * 64; row = r0 + rb * kBoxRows;
           } else {
             const int v = u - a_units, reg = v / xb, rb = v - reg * xb;
             dst = bslab + ((size_t)reg * xslab_rows + (size_t)rb * kBoxRows) * C::kBPitch;
@@ -134,8 +143,12 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
       const uint32_t idesc = umma::make_idesc_bf16(128, row_taps * kRegionCh, 1, 1);
       // MN-major swizzled row tiles: LBO = next channel group, SBO = 8 rows; one row = pitch/16 address units
       const uint64_t da0 = tma::make_desc_sw(umma::smem_u32(smem), (uint32_t)C::kARegionBytes, 128u);
-      const uint64_t db0 = tma::make_desc_sw(umma::smem_u32(smem) + C::kABytes + (uint32_t)(halo * C::kBPitch), (uint32_t)C::kBPitch,
+      const uint64_t db0 = tma::make_desc_sw(umma::smem_u32(smem) + (uint32_t)a_bytes + (uint32_t)(halo * C::kBPitch), (uint32_t)C::kBPitch,
                                              (uint32_t)C::kBPitch);
+      // skip product (issued with the CENTRE kernel row, whose middle tap has shift 0): M = 128 (dY2), N = min(CIN, 64) per region
+      const bool skip_here = has2 && taps == 9 && iss == 1;
+      const uint32_t idesc2 = umma::make_idesc_bf16(128, kRegionCh, 1, 1);
+      const uint32_t acc2 = tmem + (uint32_t)(taps * CIN);
       const uint32_t region_units = (uint32_t)(xslab_rows * C::kBPitch) >> 4;   // next 64-channel region of the X slab
       const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
@@ -159,6 +172,14 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
             for (int reg = 0; reg < C::kBRegions; ++reg)
               umma::mma_bf16(acc0 + (uint32_t)(reg * row_taps * kRegionCh), da, ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)reg * region_units),
                              idesc, (!first || kk > 0) ? 1u : 0u);
+            if (skip_here) {
+              const uint64_t da2 = da + (uint64_t)(C::kABytes >> 4);                        // the second dY stage
+              const uint32_t b_mid = b_lo + (uint32_t)(C::kBPitch / 16);                    // centre tap = first tap of the row + 1
+#pragma unroll
+              for (int reg = 0; reg < C::kBRegions; ++reg)
+                umma::mma_bf16(acc2 + (uint32_t)(reg * kRegionCh), da2, ((uint64_t)b_hi << 32) | (b_mid + (uint32_t)reg * region_units), idesc2,
+                               (!first || kk > 0) ? 1u : 0u);
+            }
           }
           if (groups == 1) umma::commit(empty + slot);
           else tma::commit_multicast(empty + slot, cmask);
@@ -191,6 +212,15 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
           for (int i = 0; i < 32; ++i) atomicAdd(dW + ((size_t)co * CIN + cg * 32 + i) * taps + tap0 + t, v[i]);
         }
       }
+      if (has2) {   // the skip convolution's gradient: columns (64-channel region, channel of the region) behind the taps
+#pragma unroll
+        for (int cg = 0; cg < CIN / 32; ++cg) {
+          float v[32];
+          umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(taps * CIN + cg * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dW2 + (size_t)co * CIN + cg * 32 + i, v[i]);
+        }
+      }
     }
   }
   umma::fence_before_sync();
@@ -201,7 +231,7 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
 
 template <int CIN, int COUT>
 int launch_wgrad3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int taps,
-                  const ConvShifts& sh, cudaStream_t st, bool* fits) {
+                  const ConvShifts& sh, cudaStream_t st, bool* fits, const __nv_bfloat16* dY2 = nullptr, float* dW2 = nullptr) {
   using C = WgCfg3<CIN, COUT>;
   constexpr int guard = 128;
   const int halo = taps == 1 ? 0 : P + 2;
@@ -210,7 +240,9 @@ int launch_wgrad3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, lo
   if (taps == 9)   // the taps of a kernel row must be consecutive activation rows (true for stride-1 / pad-1 shifts)
     for (int kh = 0; kh < 3; ++kh) *fits = *fits && sh.d[kh * 3 + 1] == sh.d[kh * 3] + 1 && sh.d[kh * 3 + 2] == sh.d[kh * 3] + 2;
   if (!*fits) return MIVIT_OK;
-  int stage_bytes = C::kABytes + C::kBRegions * xslab_rows * C::kBPitch;
+  const bool has2 = dW2 != nullptr;
+  if (has2 && (taps != 9 || C::kTapsPerCta != 9 || (taps + 1) * CIN > 512)) { *fits = false; return MIVIT_OK; }
+  int stage_bytes = C::kABytes * (has2 ? 2 : 1) + C::kBRegions * xslab_rows * C::kBPitch;
   stage_bytes = (stage_bytes + 1023) & ~1023;   // swizzle atoms are 1024-byte aligned
   const int tail = C::kOverRead + (2 * kMaxRing + 1) * 8 + 64;
   int ring = (227 * 1024 - tail) / stage_bytes;
@@ -224,10 +256,15 @@ int launch_wgrad3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, lo
   const long long rows_pad = (rows + kStageRows - 1) / kStageRows * kStageRows;
   const int n_stages = (int)(rows_pad / kStageRows);
   const int groups = (taps + C::kTapsPerCta - 1) / C::kTapsPerCta;
-  CUtensorMap tmY, tmX;
+  CUtensorMap tmY, tmX, tmY2;
   {
     int rc = make_rows_tensor_map_sw(&tmY, dY - (size_t)guard * COUT, COUT, rows_pad + 2 * guard, kBoxRows);
     if (rc) return rc;
+    tmY2 = tmY;
+    if (has2) {
+      rc = make_rows_tensor_map_sw(&tmY2, dY2 - (size_t)guard * COUT, COUT, rows_pad + 2 * guard, kBoxRows);
+      if (rc) return rc;
+    }
     rc = make_rows_tensor_map_sw(&tmX, X - (size_t)guard * CIN, CIN, rows_pad + 2 * guard, kBoxRows);
     if (rc) return rc;
   }
@@ -252,9 +289,9 @@ int launch_wgrad3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, lo
   const int spc = (n_stages + ctas_x - 1) / ctas_x;
   ctas_x = (n_stages + spc - 1) / spc;
   char tag[48];
-  snprintf(tag, sizeof(tag), "conv_wgrad_tc_%dx%dx%d", CIN, COUT, taps);
+  snprintf(tag, sizeof(tag), "conv_wgrad_tc_%dx%dx%d%s", CIN, COUT, taps, has2 ? "+skip" : "");
   const double valid_rows = (double)rows * P * P / ((double)(P + 1) * (P + 1));
-  MivitProfScope prof(tag, 2.0 * valid_rows * taps * CIN * COUT, st);
+  MivitProfScope prof(tag, 2.0 * valid_rows * (taps + (has2 ? 1 : 0)) * CIN * COUT, st);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas_x, groups, 1);
   cfg.blockDim = dim3(256, 1, 1);
@@ -267,7 +304,8 @@ int launch_wgrad3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, lo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MIVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmY, tmX, dW, n_stages, spc, taps, sh, halo, xslab_rows, stage_bytes, ring, groups, guard));
+  MIVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmY, tmX, dW, n_stages, spc, taps, sh, halo, xslab_rows, stage_bytes, ring, groups, guard,
+                                      tmY2, dW2));
   mivit_count_launch();
   MIVIT_LAUNCH_CHECK();
   return MIVIT_OK;
@@ -293,4 +331,17 @@ int conv_rows_wgrad_v3(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* d
 #undef WG3_CASE
   *handled = false;
   return MIVIT_OK;
+}
+
+// 3x3 weight gradient + the 1x1 skip convolution's weight gradient of the same input in one launch (C_in = 32: all nine taps
+// and the skip accumulator fit one CTA's tensor memory).  *handled = false: not covered, nothing was launched.
+int conv_rows_wgrad_skip_v3(const __nv_bfloat16* X, const __nv_bfloat16* dY, const __nv_bfloat16* dYskip, float* dW, float* dWskip,
+                            long long rows, int P, int cin, int cout, const ConvShifts& sh, cudaStream_t st, bool* handled) {
+  static const bool off = getenv("MIVIT_NO_WGRAD_SKIP") != nullptr;   // A/B switch
+  *handled = false;
+  if (off || cin != 32 || cout != 64) return MIVIT_OK;
+  bool fits = true;
+  const int rc = launch_wgrad3<32, 64>(X, dY, dW, rows, P, 9, sh, st, &fits, dYskip, dWskip);
+  *handled = fits;
+  return rc;
 }

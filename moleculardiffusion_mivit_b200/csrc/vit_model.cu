@@ -804,8 +804,11 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
     bool skip_fused = false;
     if (impl == 1 && !try_dual)
       CK(conv_skip_backward_fused(in[b]->row0, ds[b]->row0, w.wd_sk[b], g + R.sk_w, dins[b]->row0, rows, P, ci[b], co[b], st, &skip_fused));
+    // Block 1 on the product path: the skip convolution's weight gradient rides along with conv1's (same input, conv_wgrad3.cu);
+    // its output gradient stays in its slot until then (carve())
+    const bool skip_with_c1 = impl == 1 && try_dual;
     if (!skip_fused) {
-      CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
+      if (!skip_with_c1) CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
       if (!try_dual) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
     }
     CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
@@ -821,7 +824,15 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
     CK(zero_guards(*d1[b], rp, st));
     CK(bn_backward(da1[b]->row0, nullptr, nullptr, r1[b]->row0, w.bn[i1].ss, w.bn[i1].mi, p + R.bn1_g, d1[b]->row0, g + R.bn1_g,
                    g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, bn1_summed ? 1 : 0, st));
-    CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
+    {
+      bool both = false;
+      if (skip_with_c1)
+        CK(conv_rows_wgrad_skip_v3(in[b]->row0, d1[b]->row0, ds[b]->row0, g + R.c1_w, g + R.sk_w, rows, P, ci[b], co[b], s3, st, &both));
+      if (!both) {
+        if (skip_with_c1) CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
+        CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
+      }
+    }
     fused_in[b] = false;
     if (try_dual) {
       bool handled = false;
