@@ -824,23 +824,32 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
     CK(zero_guards(*d1[b], rp, st));
     CK(bn_backward(da1[b]->row0, nullptr, nullptr, r1[b]->row0, w.bn[i1].ss, w.bn[i1].mi, p + R.bn1_g, d1[b]->row0, g + R.bn1_g,
                    g + R.bn1_b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.bn_sums, rows, rp, P, co[b], cnt, nullptr, bn1_summed ? 1 : 0, st));
-    {
-      bool both = false;
-      if (skip_with_c1)
-        CK(conv_rows_wgrad_skip_v3(in[b]->row0, d1[b]->row0, ds[b]->row0, g + R.c1_w, g + R.sk_w, rows, P, ci[b], co[b], s3, st, &both));
-      if (!both) {
-        if (skip_with_c1) CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
-        CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
+    // Block 1 on the product path: both weight gradients AND the dual-input dgrad from one pass over the two output gradients
+    // (conv_block1_bwd.cu); otherwise the ride-along weight gradient + the dual-input dgrad, or the separate kernels.
+    bool blk1 = false;
+    if (skip_with_c1)
+      CK(conv_block1_backward_fused(in[b]->row0, d1[b]->row0, ds[b]->row0, w.wd_c1[b], w.wd_sk[b], g + R.c1_w, g + R.sk_w, dinm[b]->row0,
+                                    rows, P, ci[b], co[b], s3, s3m, st, &blk1));
+    if (!blk1) {
+      {
+        bool both = false;
+        if (skip_with_c1)
+          CK(conv_rows_wgrad_skip_v3(in[b]->row0, d1[b]->row0, ds[b]->row0, g + R.c1_w, g + R.sk_w, rows, P, ci[b], co[b], s3, st, &both));
+        if (!both) {
+          if (skip_with_c1) CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
+          CK(conv_rows_wgrad(in[b]->row0, d1[b]->row0, g + R.c1_w, rows, P, ci[b], co[b], 9, s3, impl, st));
+        }
+      }
+      fused_in[b] = false;
+      if (try_dual) {
+        bool handled = false;
+        CK(conv_rows_forward_dual_v3(d1[b]->row0, w.wd_c1[b], ds[b]->row0, w.wd_sk[b], dinm[b]->row0, rows, P, co[b], co[b], ci[b], s3m,
+                                     st, &handled));
+        fused_in[b] = handled;
+        if (!handled) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
       }
     }
-    fused_in[b] = false;
-    if (try_dual) {
-      bool handled = false;
-      CK(conv_rows_forward_dual_v3(d1[b]->row0, w.wd_c1[b], ds[b]->row0, w.wd_sk[b], dinm[b]->row0, rows, P, co[b], co[b], ci[b], s3m,
-                                   st, &handled));
-      fused_in[b] = handled;
-      if (!handled) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
-    }
+    if (blk1) fused_in[b] = true;
     if (!fused_in[b]) CK(conv_rows_forward(d1[b]->row0, w.wd_c1[b], dinm[b]->row0, nullptr, rows, P, co[b], ci[b], 9, s3m, impl, st));
   }
   // act0 = relu(bn0(raw0)); upstream = conv1 path + skip path of block 1
