@@ -51,6 +51,9 @@ int pack_conv_weights(const float* W, __nv_bfloat16* out, int cout, int cin, int
 int conv_rows_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, float* dW, long long rows, int P, int cin, int cout,
                     int taps, const ConvShifts& sh, int impl, cudaStream_t st);
 
+int conv_layer64_backward_fused(const __nv_bfloat16* X, const __nv_bfloat16* dY, const __nv_bfloat16* Wd, float* dW, __nv_bfloat16* dX,
+                                long long rows, int P, int cin, int cout, const ConvShifts& sh_w, const ConvShifts& sh_d,
+                                cudaStream_t st, bool* handled);
 int conv_block1_backward_fused(const __nv_bfloat16* X, const __nv_bfloat16* dY1, const __nv_bfloat16* dY2, const __nv_bfloat16* Wd1,
                                const __nv_bfloat16* Wd2, float* dW1, float* dW2, __nv_bfloat16* dX, long long rows, int P, int cin,
                                int cout, const ConvShifts& sh_w, const ConvShifts& sh_d, cudaStream_t st, bool* handled);

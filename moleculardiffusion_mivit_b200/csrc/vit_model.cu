@@ -811,15 +811,22 @@ static int vit_backward_impl(const mivit_vit_config* c, int32_t B, const float* 
       if (!skip_with_c1) CK(conv_rows_wgrad(in[b]->row0, ds[b]->row0, g + R.sk_w, rows, P, ci[b], co[b], 1, s1, impl, st));
       if (!try_dual) CK(conv_rows_forward(ds[b]->row0, w.wd_sk[b], dins[b]->row0, nullptr, rows, P, co[b], ci[b], 1, s1, impl, st));
     }
-    CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
+    // conv2: block 1 (64 -> 64) on the product path computes weight gradient and input gradient in one pass over the output
+    // gradient (conv_layer64_bwd.cu); block 2 (128 -> 128) keeps the clustered weight gradient and the CTA-pair dgrad with the
+    // BatchNorm-backward sums in its epilogue.
+    bool c2_fused = false;
+    if (impl == 1 && b == 0)
+      CK(conv_layer64_backward_fused(a1[b]->row0, d2[b]->row0, w.wd_c2[b], g + R.c2_w, da1[b]->row0, rows, P, co[b], co[b], s3, s3m, st,
+                                     &c2_fused));
+    if (!c2_fused) CK(conv_rows_wgrad(a1[b]->row0, d2[b]->row0, g + R.c2_w, rows, P, co[b], co[b], 9, s3, impl, st));
     // conv2 input gradient; on the product path its epilogue also accumulates the backward sums of bn1 (no reduction pass)
     bool bn1_summed = false;
-    if (impl == 1) {
+    if (impl == 1 && !c2_fused) {
       MIVIT_CUDA_CHECK(cudaMemsetAsync(w.bn_sums, 0, 3 * co[b] * sizeof(float), st));
       CK(conv_rows_dgrad_bnsums(d2[b]->row0, w.wd_c2[b], da1[b]->row0, r1[b]->row0, w.bn[i1].ss, w.bn_sums, rows, P, co[b], co[b], s3m,
                                 st, &bn1_summed));
     }
-    if (!bn1_summed) CK(conv_rows_forward(d2[b]->row0, w.wd_c2[b], da1[b]->row0, nullptr, rows, P, co[b], co[b], 9, s3m, impl, st));
+    if (!bn1_summed && !c2_fused) CK(conv_rows_forward(d2[b]->row0, w.wd_c2[b], da1[b]->row0, nullptr, rows, P, co[b], co[b], 9, s3m, impl, st));
     // act1 = relu(bn1(raw1))
     CK(zero_guards(*d1[b], rp, st));
     CK(bn_backward(da1[b]->row0, nullptr, nullptr, r1[b]->row0, w.bn[i1].ss, w.bn[i1].mi, p + R.bn1_g, d1[b]->row0, g + R.bn1_g,
